@@ -1,0 +1,145 @@
+/*
+ * mptv.h -- C ABI of the B200 batched Merkle-Patricia-Trie proof verifier.
+ *
+ * This is the drop-in boundary for the one hot path of ChainSafe/zk-state-proofs:
+ *
+ *   crypto_ops::verify_merkle_proof(root_hash: B256, proof: Vec<Vec<u8>>, key: &[u8]) -> Vec<u8>
+ *       /root/reference/crypto-ops/src/lib.rs:8-23
+ *   crypto_ops::keccak::digest_keccak(bytes: &[u8]) -> [u8; 32]
+ *       /root/reference/crypto-ops/src/keccak.rs:6-12
+ *   crypto_ops::types::{MerkleProofInput, StorageProofInput}
+ *       /root/reference/crypto-ops/src/types.rs:4-19
+ *   trie-utils tx / receipt trie rebuild (EthTrie::new / insert / root_hash)
+ *       /root/reference/trie-utils/src/proofs/transaction.rs:41-66, proofs/receipt.rs:49-84
+ *
+ * The reference has no FFI of its own (it is a plain Rust function); these are the entry points a
+ * Rust `extern "C"` shim binds so that `verify_merkle_proof` and the new batched
+ * `verify_merkle_proofs(&[MerkleProofInput])` run on the GPU (INTEGRATION.md shows the binding).
+ * Plain pointers and sizes only.  Functions return 0 or a negative MPTV_ERR_*; they never throw
+ * and never abort.  One mptv_ctx is not thread-safe; separate contexts are.
+ *
+ * There is NO CPU fallback: without a usable CUDA device mptv_create fails.
+ */
+#ifndef MPTV_H
+#define MPTV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- per-proof verdicts: 1:1 with the reference's outcomes, evaluated in the reference's order */
+#define MPTV_ST_OK 0                 /* value returned                                   lib.rs:20-22 */
+#define MPTV_ST_INVALID_STATE_ROOT 1 /* "Invalid merkle proof: ..."                      lib.rs:14    */
+#define MPTV_ST_ROOT_NOT_CANONICAL 2 /* assert_eq!(root_hash, trie.root_hash())          lib.rs:19    */
+#define MPTV_ST_INVALID_PROOF 3      /* "Failed to verify Merkle Proof: InvalidProof"    lib.rs:21    */
+#define MPTV_ST_KEY_NOT_FOUND 4      /* "Key does not exist!"                            lib.rs:22    */
+#define MPTV_ST_PANIC_OTHER 5        /* raw panics inside eth_trie (Nibbles::from_compact ...)        */
+#define MPTV_ST_BAD_ROOT_LEN 6       /* root_hash.len() != 32 (guest try_into().unwrap()); host shim only */
+#define MPTV_ST_DEP_FAILED 7         /* nested: the account proof this root comes from was rejected, or
+                                        its value is not an Account RLP (storage-circuit main.rs:10-15) */
+
+/* ---- error codes */
+#define MPTV_OK 0
+#define MPTV_ERR_ARG (-1)    /* null / inconsistent argument                                         */
+#define MPTV_ERR_CUDA (-2)   /* CUDA runtime error; mptv_last_error(ctx) has the text                */
+#define MPTV_ERR_ALIGN (-3)  /* a node does not start on a 16-byte boundary of the arena             */
+#define MPTV_ERR_NOMEM (-4)
+#define MPTV_ERR_DEP (-5)    /* root_from_proof must point at an EARLIER, independent proof          */
+#define MPTV_ERR_NODEV (-6)  /* no CUDA device / CUDA extension unusable: there is no CPU fallback   */
+
+typedef struct mptv_ctx mptv_ctx;
+
+/*
+ * A batch in flat CSR form (what MerkleProofInput { proof, root_hash, key } x n_proofs flattens to):
+ *   node i      = node_bytes[node_off[i] .. node_off[i] + node_len[i])
+ *                 node_off[i] % 16 == 0, and node_bytes is readable up to the next multiple of 16
+ *                 after each node (padding bytes are never hashed)
+ *   proof p     = nodes [proof_first[p], proof_first[p+1])          (any order, duplicates allowed)
+ *   root of p   = roots[32p .. 32p+32)
+ *   key of p    = key_bytes[key_off[p] .. key_off[p+1])
+ *   root_from_proof (optional, may be NULL): -1, or the index d < p of an independent proof whose
+ *                 returned value is an Account RLP; then p's root is that account's storage_root
+ *                 and roots[32p..] is ignored (StorageProofInput, types.rs:11-19).
+ */
+typedef struct mptv_batch {
+  const uint8_t* node_bytes;
+  uint64_t node_bytes_len;
+  const uint64_t* node_off;  /* [n_nodes]     */
+  const uint32_t* node_len;  /* [n_nodes]     */
+  uint64_t n_nodes;
+  const uint32_t* proof_first; /* [n_proofs+1] */
+  uint64_t n_proofs;
+  const uint8_t* roots;      /* [32*n_proofs] */
+  const uint8_t* key_bytes;
+  const uint32_t* key_off;   /* [n_proofs+1]  */
+  const int32_t* root_from_proof; /* [n_proofs] or NULL */
+} mptv_batch;
+
+/* Results.  The returned value is always a contiguous slice of one supplied node, so it is
+ * reported as (offset into node_bytes, length); status != 0 gives (0, 0). */
+typedef struct mptv_result {
+  uint8_t* status;      /* [n_proofs] MPTV_ST_* */
+  uint64_t* value_off;  /* [n_proofs] */
+  uint32_t* value_len;  /* [n_proofs] */
+} mptv_result;
+
+/* device time of the last mptv_verify_batch_device / mptv_keccak256_batch_device call on a device,
+ * measured with CUDA events on the stream the kernels were launched on */
+typedef struct mptv_timings {
+  float bin_ms;     /* K0 rate-block binning            */
+  float keccak_ms;  /* K1 Keccak-256 of every node      */
+  float parse_ms;   /* K2a per-node decode              */
+  float walk_ms;    /* K2b walk (both waves)            */
+  float total_ms;
+  uint64_t n_nodes;
+  uint64_t n_perm;  /* Keccak-f permutations = sum ceil((len+1)/136); filled when known, else 0 */
+  uint32_t keccak_launches, other_launches;
+} mptv_timings;
+
+/* device_ids == NULL && n_devices == 0: use every visible CUDA device. */
+int mptv_create(const int* device_ids, int n_devices, mptv_ctx** out);
+void mptv_destroy(mptv_ctx* ctx);
+int mptv_device_count(const mptv_ctx* ctx);
+const char* mptv_last_error(const mptv_ctx* ctx);
+const char* mptv_strerror(int err);
+const char* mptv_status_name(int status);
+
+/* Host-buffer entry (what the Rust shim's verify_merkle_proofs calls): every pointer of `in` and
+ * `out` is HOST memory (pinned memory from mptv_alloc_pinned makes the copies faster).  The batch
+ * is cut into contiguous proof slices balanced by Keccak-f count, one slice per device of the
+ * context, with no inter-device traffic; slices are pipelined in chunks (H2D / kernels / D2H on
+ * per-device streams).  Blocks until `out` is filled. */
+int mptv_verify_batch(mptv_ctx* ctx, const mptv_batch* in, mptv_result* out);
+
+/* Device-resident entry: every pointer is DEVICE memory on the context's device `dev_index`.
+ * Asynchronous on `stream` (a cudaStream_t, NULL = the context's own stream for that device). */
+int mptv_verify_batch_device(mptv_ctx* ctx, int dev_index, const mptv_batch* in, mptv_result* out,
+                             void* stream);
+
+/* digest_keccak over a whole CSR arena: digests32[32i..] = keccak256(node i).  Host buffers. */
+int mptv_keccak256_batch(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node_bytes_len,
+                         const uint64_t* node_off, const uint32_t* node_len, uint64_t n_nodes,
+                         uint8_t* digests32);
+/* same, device pointers, asynchronous on `stream` */
+int mptv_keccak256_batch_device(mptv_ctx* ctx, int dev_index, const uint8_t* node_bytes,
+                                const uint64_t* node_off, const uint32_t* node_len, uint64_t n_nodes,
+                                uint8_t* digests32, void* stream);
+
+/* synchronises the device's stream and reports the device times of its last *_device call */
+int mptv_last_timings(mptv_ctx* ctx, int dev_index, mptv_timings* out);
+
+/* options: lanes per proof for the walk kernel (0 = choose from nodes/proof; else 8, 16 or 32),
+ * chunk size in bytes of node data for the host-buffer pipeline (0 = default) */
+int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value);
+
+/* page-locked host memory for arenas that are handed to mptv_verify_batch */
+void* mptv_alloc_pinned(size_t bytes);
+void mptv_free_pinned(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPTV_H */

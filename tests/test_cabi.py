@@ -1,0 +1,63 @@
+"""The C-ABI shared library loads and exports every symbol include/mptv.h declares (no compute
+calls: there is no GPU here), and the host mirror's wire types round-trip."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mptv.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mptv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import zk_state_proofs_b200 as z
+    from importlib import import_module
+    if not os.path.exists(z.lib_path()):
+        import subprocess, sys
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "zk-state-proofs_b200", "build.py")])
+    lib = ctypes.CDLL(z.lib_path())
+    syms = declared_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(lib, s), s
+
+
+def test_strerror_and_status_names_without_a_gpu():
+    import zk_state_proofs_b200 as z
+    L = z.load_library()
+    assert b"no CPU fallback" in L.mptv_strerror(-6)
+    assert L.mptv_status_name(4) == b"KEY_NOT_FOUND"
+    for k, v in z.STATUS_NAMES.items():
+        assert L.mptv_status_name(k).decode() == v
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    import zk_state_proofs_b200 as z
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(z.MptvError):
+        z.Verifier([0])
+    with pytest.raises(z.MptvError):
+        z.digest_keccak(b"abc")
+
+
+def test_borsh_roundtrip_and_flatten_layout():
+    import numpy as np
+    import zk_state_proofs_b200 as z
+    inp = z.MerkleProofInput([b"\x01" * 5, b"", b"\x02" * 33], b"\xaa" * 32, b"\x12\x34")
+    assert z.MerkleProofInput.from_borsh(inp.to_borsh()) == inp
+    b = z.flatten([inp, z.MerkleProofInput([b"\x07" * 17], b"\xbb" * 31, b"")])
+    assert b.n_proofs == 2 and b.n_nodes == 4
+    assert (b.node_off % 16 == 0).all()
+    assert list(b.node_len) == [5, 0, 33, 17]
+    assert list(b.proof_first) == [0, 3, 4]
+    assert b.bad_root_len is not None and list(b.bad_root_len) == [False, True]
+    assert b.node_bytes[int(b.node_off[2]):int(b.node_off[2]) + 33].tobytes() == b"\x02" * 33
+    assert b.n_perm() == 4

@@ -1,0 +1,29 @@
+"""zk-state-proofs_b200 -- B200-native batched Merkle-Patricia-Trie proof verifier.
+
+Host-side mirror of the reference's crypto-ops crate (/root/reference/crypto-ops/src/lib.rs,
+keccak.rs, types.rs) over the C ABI of include/mptv.h.  All compute runs in hand-written
+sm_100a CUDA (csrc/); there is no CPU fallback -- importing works anywhere, but every compute
+call raises if libmptv.so or a B200 is missing.
+"""
+from .crypto_ops import (  # noqa: F401
+    Batch,
+    MerkleProofInput,
+    MptvError,
+    StorageProofInput,
+    VerifyPanic,
+    Verifier,
+    STATUS_NAMES,
+    digest_keccak,
+    flatten,
+    lib_path,
+    load_library,
+    verify_merkle_proof,
+    verify_merkle_proofs,
+    verify_storage_proof_input,
+)
+
+__all__ = [
+    "Batch", "MerkleProofInput", "MptvError", "StorageProofInput", "VerifyPanic", "Verifier",
+    "STATUS_NAMES", "digest_keccak", "flatten", "lib_path", "load_library", "verify_merkle_proof",
+    "verify_merkle_proofs", "verify_storage_proof_input",
+]

@@ -1,0 +1,430 @@
+"""Host-side mirror of the reference's crypto-ops crate over the C ABI (include/mptv.h).
+
+Reference interface mirrored here (same names, argument meaning and error behaviour):
+  verify_merkle_proof(root_hash, proof, key) -> bytes     /root/reference/crypto-ops/src/lib.rs:8-23
+      panics in the reference -> raises VerifyPanic carrying the same message class
+  digest_keccak(data) -> 32 bytes                         /root/reference/crypto-ops/src/keccak.rs:6-12
+  MerkleProofInput / StorageProofInput (+ borsh wire form) /root/reference/crypto-ops/src/types.rs:4-19
+and the batched entry the north star adds:
+  verify_merkle_proofs([MerkleProofInput]) -> [bytes | VerifyPanic]
+The nested account -> storage flow of the risc0 storage guest
+(/root/reference/circuits/risc0-storage-proof/storage-proof-circuit/storage-circuit/src/main.rs:6-31)
+is verify_storage_proof_input().
+
+Everything here is plumbing: flatten to the CSR arena, call libmptv.so, slice the results.  No
+hashing, RLP decoding or trie walking happens on the CPU, and nothing under oracle/ is imported.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import struct
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+STATUS_NAMES = {
+    0: "OK", 1: "INVALID_STATE_ROOT", 2: "ROOT_NOT_CANONICAL", 3: "INVALID_PROOF",
+    4: "KEY_NOT_FOUND", 5: "PANIC_OTHER", 6: "BAD_ROOT_LEN", 7: "DEPENDENCY_FAILED",
+}
+# the reference's panic messages per verdict class (crypto-ops/src/lib.rs:14,19,21,22)
+PANIC_MESSAGES = {
+    1: "Invalid merkle proof",
+    2: "assertion `left == right` failed",
+    3: "Failed to verify Merkle Proof: InvalidProof",
+    4: "Key does not exist!",
+    5: "panicked inside eth_trie (invalid data / index out of bounds)",
+    6: "called `Result::unwrap()` on an `Err` value: TryFromSliceError",
+    7: "account proof rejected or not an Account RLP",
+}
+
+
+class MptvError(RuntimeError):
+    """libmptv.so missing, no B200, or a negative MPTV_ERR_* from the C ABI."""
+
+
+class VerifyPanic(Exception):
+    """The reference would have panicked; .status is the MPTV_ST_* class."""
+
+    def __init__(self, status: int):
+        self.status = status
+        super().__init__(f"{PANIC_MESSAGES.get(status, '?')} [{STATUS_NAMES.get(status, status)}]")
+
+    def __eq__(self, other):
+        return isinstance(other, VerifyPanic) and other.status == self.status
+
+    def __hash__(self):
+        return hash(("VerifyPanic", self.status))
+
+
+# ----------------------------------------------------------------------------- wire types
+def _borsh_bytes(b: bytes) -> bytes:
+    return struct.pack("<I", len(b)) + bytes(b)
+
+
+def _read_vec_u8(buf: memoryview, pos: int):
+    (n,) = struct.unpack_from("<I", buf, pos)
+    pos += 4
+    return bytes(buf[pos:pos + n]), pos + n
+
+
+@dataclass
+class MerkleProofInput:
+    """crypto-ops/src/types.rs:4-9"""
+    proof: List[bytes]
+    root_hash: bytes
+    key: bytes
+
+    def to_borsh(self) -> bytes:
+        out = struct.pack("<I", len(self.proof)) + b"".join(_borsh_bytes(n) for n in self.proof)
+        return out + _borsh_bytes(self.root_hash) + _borsh_bytes(self.key)
+
+    @classmethod
+    def from_borsh(cls, data: bytes) -> "MerkleProofInput":
+        buf = memoryview(data)
+        (n,) = struct.unpack_from("<I", buf, 0)
+        pos = 4
+        proof = []
+        for _ in range(n):
+            b, pos = _read_vec_u8(buf, pos)
+            proof.append(b)
+        root, pos = _read_vec_u8(buf, pos)
+        key, pos = _read_vec_u8(buf, pos)
+        if pos != len(data):
+            raise ValueError("trailing bytes after MerkleProofInput")
+        return cls(proof, root, key)
+
+
+@dataclass
+class StorageProofInput:
+    """crypto-ops/src/types.rs:11-19 (storage keys are un-hashed; the consumer hashes them)"""
+    account_proof: List[bytes]
+    storage_proofs: List[List[bytes]]
+    root_hash: bytes
+    account_key: bytes
+    storage_keys: List[bytes]
+    address_keccak: bytes
+
+    def to_borsh(self) -> bytes:
+        out = struct.pack("<I", len(self.account_proof)) + b"".join(_borsh_bytes(n) for n in self.account_proof)
+        out += struct.pack("<I", len(self.storage_proofs))
+        for pr in self.storage_proofs:
+            out += struct.pack("<I", len(pr)) + b"".join(_borsh_bytes(n) for n in pr)
+        out += _borsh_bytes(self.root_hash) + _borsh_bytes(self.account_key)
+        out += struct.pack("<I", len(self.storage_keys)) + b"".join(_borsh_bytes(k) for k in self.storage_keys)
+        return out + bytes(self.address_keccak)
+
+
+# ----------------------------------------------------------------------------- CSR batch
+@dataclass
+class Batch:
+    """Flat CSR form of n MerkleProofInputs (layout: include/mptv.h `mptv_batch`)."""
+    node_bytes: np.ndarray   # u8, nodes 16-byte aligned, total padded to 16
+    node_off: np.ndarray     # u64 [n_nodes]
+    node_len: np.ndarray     # u32 [n_nodes]
+    proof_first: np.ndarray  # u32 [n_proofs+1]
+    roots: np.ndarray        # u8 [32*n_proofs]
+    key_bytes: np.ndarray    # u8
+    key_off: np.ndarray      # u32 [n_proofs+1]
+    root_from_proof: Optional[np.ndarray] = None  # i32 [n_proofs]
+    bad_root_len: Optional[np.ndarray] = None     # bool [n_proofs]: root_hash.len() != 32
+
+    @property
+    def n_proofs(self) -> int:
+        return len(self.proof_first) - 1
+
+    @property
+    def n_nodes(self) -> int:
+        return len(self.node_len)
+
+    def n_perm(self) -> int:
+        """Algorithmic Keccak-f count: sum over nodes of ceil((len+1)/136)."""
+        return int((self.node_len.astype(np.int64) // 136 + 1).sum())
+
+    def value(self, off: int, ln: int) -> bytes:
+        return self.node_bytes[off:off + ln].tobytes()
+
+
+def flatten(inputs: Sequence[MerkleProofInput], root_from_proof: Optional[Sequence[int]] = None) -> Batch:
+    """MerkleProofInput x n  ->  CSR arena (every node on a 16-byte boundary)."""
+    n = len(inputs)
+    lens = np.fromiter((len(nd) for inp in inputs for nd in inp.proof), dtype=np.uint32)
+    counts = np.fromiter((len(inp.proof) for inp in inputs), dtype=np.int64, count=n)
+    proof_first = np.zeros(n + 1, np.uint32)
+    np.cumsum(counts, out=proof_first[1:])
+    padded = (lens.astype(np.uint64) + 15) & ~np.uint64(15)
+    node_off = np.zeros(len(lens), np.uint64)
+    if len(lens):
+        np.cumsum(padded[:-1], out=node_off[1:])
+    total = int(padded.sum())
+    node_bytes = np.zeros(total + 16, np.uint8)
+    i = 0
+    for inp in inputs:
+        for nd in inp.proof:
+            o = int(node_off[i])
+            node_bytes[o:o + len(nd)] = np.frombuffer(bytes(nd), np.uint8)
+            i += 1
+    roots = np.zeros(32 * n, np.uint8)
+    bad = np.zeros(n, bool)
+    klens = np.fromiter((len(inp.key) for inp in inputs), dtype=np.int64, count=n)
+    key_off = np.zeros(n + 1, np.uint32)
+    np.cumsum(klens, out=key_off[1:])
+    key_bytes = np.zeros(int(key_off[-1]) + 16, np.uint8)
+    for p, inp in enumerate(inputs):
+        if len(inp.root_hash) == 32:
+            roots[32 * p:32 * p + 32] = np.frombuffer(bytes(inp.root_hash), np.uint8)
+        else:
+            bad[p] = True
+        if inp.key:
+            key_bytes[int(key_off[p]):int(key_off[p + 1])] = np.frombuffer(bytes(inp.key), np.uint8)
+    rfp = None
+    if root_from_proof is not None:
+        rfp = np.asarray(root_from_proof, np.int32)
+    return Batch(node_bytes, node_off, lens, proof_first, roots, key_bytes, key_off, rfp, bad if bad.any() else None)
+
+
+# ----------------------------------------------------------------------------- C ABI
+class _CBatch(ctypes.Structure):
+    _fields_ = [
+        ("node_bytes", ctypes.c_void_p), ("node_bytes_len", ctypes.c_uint64),
+        ("node_off", ctypes.c_void_p), ("node_len", ctypes.c_void_p), ("n_nodes", ctypes.c_uint64),
+        ("proof_first", ctypes.c_void_p), ("n_proofs", ctypes.c_uint64), ("roots", ctypes.c_void_p),
+        ("key_bytes", ctypes.c_void_p), ("key_off", ctypes.c_void_p), ("root_from_proof", ctypes.c_void_p),
+    ]
+
+
+class _CResult(ctypes.Structure):
+    _fields_ = [("status", ctypes.c_void_p), ("value_off", ctypes.c_void_p), ("value_len", ctypes.c_void_p)]
+
+
+class Timings(ctypes.Structure):
+    _fields_ = [
+        ("bin_ms", ctypes.c_float), ("keccak_ms", ctypes.c_float), ("parse_ms", ctypes.c_float),
+        ("walk_ms", ctypes.c_float), ("total_ms", ctypes.c_float), ("n_nodes", ctypes.c_uint64),
+        ("n_perm", ctypes.c_uint64), ("keccak_launches", ctypes.c_uint32), ("other_launches", ctypes.c_uint32),
+    ]
+
+
+def lib_path() -> str:
+    return os.environ.get("MPTV_LIB", os.path.join(HERE, "libmptv.so"))
+
+
+_LIB = None
+
+
+def load_library():
+    """dlopen libmptv.so (built in-tree by build.py).  Raises MptvError when it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise MptvError(f"{path} not found: build it with `python zk-state-proofs_b200/build.py` "
+                        "(there is no CPU fallback)")
+    L = ctypes.CDLL(path)
+    vp, i32, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
+    L.mptv_create.restype = i32
+    L.mptv_create.argtypes = [ctypes.POINTER(ctypes.c_int), i32, ctypes.POINTER(vp)]
+    L.mptv_destroy.restype = None
+    L.mptv_destroy.argtypes = [vp]
+    L.mptv_device_count.restype = i32
+    L.mptv_device_count.argtypes = [vp]
+    L.mptv_last_error.restype = ctypes.c_char_p
+    L.mptv_last_error.argtypes = [vp]
+    L.mptv_strerror.restype = ctypes.c_char_p
+    L.mptv_strerror.argtypes = [i32]
+    L.mptv_status_name.restype = ctypes.c_char_p
+    L.mptv_status_name.argtypes = [i32]
+    L.mptv_verify_batch.restype = i32
+    L.mptv_verify_batch.argtypes = [vp, ctypes.POINTER(_CBatch), ctypes.POINTER(_CResult)]
+    L.mptv_verify_batch_device.restype = i32
+    L.mptv_verify_batch_device.argtypes = [vp, i32, ctypes.POINTER(_CBatch), ctypes.POINTER(_CResult), vp]
+    L.mptv_keccak256_batch.restype = i32
+    L.mptv_keccak256_batch.argtypes = [vp, vp, u64, vp, vp, u64, vp]
+    L.mptv_keccak256_batch_device.restype = i32
+    L.mptv_keccak256_batch_device.argtypes = [vp, i32, vp, vp, vp, u64, vp, vp]
+    L.mptv_last_timings.restype = i32
+    L.mptv_last_timings.argtypes = [vp, i32, ctypes.POINTER(Timings)]
+    L.mptv_set_option.restype = i32
+    L.mptv_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
+    L.mptv_alloc_pinned.restype = vp
+    L.mptv_alloc_pinned.argtypes = [ctypes.c_size_t]
+    L.mptv_free_pinned.restype = None
+    L.mptv_free_pinned.argtypes = [vp]
+    _LIB = L
+    return L
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+class Verifier:
+    """Owns an mptv_ctx (device memory + streams on the chosen GPUs)."""
+
+    def __init__(self, device_ids: Optional[Sequence[int]] = None):
+        self.lib = load_library()
+        self.ctx = ctypes.c_void_p()
+        if device_ids is None:
+            rc = self.lib.mptv_create(None, 0, ctypes.byref(self.ctx))
+        else:
+            arr = (ctypes.c_int * len(device_ids))(*device_ids)
+            rc = self.lib.mptv_create(arr, len(device_ids), ctypes.byref(self.ctx))
+        if rc != 0:
+            raise MptvError(f"mptv_create failed: {self.lib.mptv_strerror(rc).decode()}")
+
+    def close(self):
+        if getattr(self, "ctx", None) and self.ctx.value:
+            self.lib.mptv_destroy(self.ctx)
+            self.ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise MptvError(f"{what}: {self.lib.mptv_strerror(rc).decode()} "
+                            f"({self.lib.mptv_last_error(self.ctx).decode()})")
+
+    @property
+    def device_count(self) -> int:
+        return self.lib.mptv_device_count(self.ctx)
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.mptv_set_option(self.ctx, name.encode(), int(value)), f"set_option({name})")
+
+    # -- host-buffer entry (H2D + kernels + D2H inside the call)
+    def verify_batch(self, b: Batch):
+        n = b.n_proofs
+        status = np.zeros(n, np.uint8)
+        voff = np.zeros(n, np.uint64)
+        vlen = np.zeros(n, np.uint32)
+        if n == 0:
+            return status, voff, vlen
+        cb = _CBatch(_ptr(b.node_bytes), len(b.node_bytes), _ptr(b.node_off), _ptr(b.node_len), b.n_nodes,
+                     _ptr(b.proof_first), n, _ptr(b.roots), _ptr(b.key_bytes), _ptr(b.key_off),
+                     _ptr(b.root_from_proof))
+        cr = _CResult(_ptr(status), _ptr(voff), _ptr(vlen))
+        self._check(self.lib.mptv_verify_batch(self.ctx, ctypes.byref(cb), ctypes.byref(cr)), "mptv_verify_batch")
+        if b.bad_root_len is not None:
+            status[b.bad_root_len] = 6
+            voff[b.bad_root_len] = 0
+            vlen[b.bad_root_len] = 0
+        return status, voff, vlen
+
+    # -- device-resident entry: pointers are raw device addresses (ints), e.g. torch tensors' data_ptr()
+    def verify_batch_device(self, dev_index: int, ptrs: dict, n_nodes: int, n_proofs: int, out_ptrs: dict,
+                            stream: int = 0, node_bytes_len: int = 0):
+        cb = _CBatch(ptrs["node_bytes"], node_bytes_len, ptrs["node_off"], ptrs["node_len"], n_nodes,
+                     ptrs["proof_first"], n_proofs, ptrs["roots"], ptrs["key_bytes"], ptrs["key_off"],
+                     ptrs.get("root_from_proof"))
+        cr = _CResult(out_ptrs["status"], out_ptrs["value_off"], out_ptrs["value_len"])
+        self._check(self.lib.mptv_verify_batch_device(self.ctx, dev_index, ctypes.byref(cb), ctypes.byref(cr),
+                                                      ctypes.c_void_p(stream) if stream else None),
+                    "mptv_verify_batch_device")
+
+    def keccak256_batch_device(self, dev_index: int, node_bytes: int, node_off: int, node_len: int, n_nodes: int,
+                               digests: int, stream: int = 0):
+        self._check(self.lib.mptv_keccak256_batch_device(self.ctx, dev_index, node_bytes, node_off, node_len,
+                                                         n_nodes, digests,
+                                                         ctypes.c_void_p(stream) if stream else None),
+                    "mptv_keccak256_batch_device")
+
+    def last_timings(self, dev_index: int = 0) -> Timings:
+        t = Timings()
+        self._check(self.lib.mptv_last_timings(self.ctx, dev_index, ctypes.byref(t)), "mptv_last_timings")
+        return t
+
+    def keccak256_batch(self, node_bytes: np.ndarray, node_off: np.ndarray, node_len: np.ndarray) -> np.ndarray:
+        n = len(node_len)
+        out = np.zeros((n, 32), np.uint8)
+        if n:
+            self._check(self.lib.mptv_keccak256_batch(self.ctx, _ptr(node_bytes), len(node_bytes), _ptr(node_off),
+                                                      _ptr(node_len), n, _ptr(out)), "mptv_keccak256_batch")
+        return out
+
+    # -- reference-shaped API
+    def verify_merkle_proofs(self, inputs: Sequence[MerkleProofInput], root_from_proof=None):
+        """-> list of bytes (the value) or VerifyPanic (what the reference would have panicked with)."""
+        b = flatten(inputs, root_from_proof)
+        status, voff, vlen = self.verify_batch(b)
+        out = []
+        for p in range(len(inputs)):
+            if status[p] == 0:
+                out.append(b.value(int(voff[p]), int(vlen[p])))
+            else:
+                out.append(VerifyPanic(int(status[p])))
+        return out
+
+    def verify_merkle_proof(self, root_hash: bytes, proof: Sequence[bytes], key: bytes) -> bytes:
+        r = self.verify_merkle_proofs([MerkleProofInput(list(proof), bytes(root_hash), bytes(key))])[0]
+        if isinstance(r, VerifyPanic):
+            raise r
+        return r
+
+    def digest_keccak(self, data: bytes) -> bytes:
+        nb = np.zeros(((len(data) + 15) // 16) * 16 + 16, np.uint8)
+        nb[:len(data)] = np.frombuffer(bytes(data), np.uint8)
+        return self.keccak256_batch(nb, np.zeros(1, np.uint64), np.array([len(data)], np.uint32))[0].tobytes()
+
+    def verify_storage_proof_input(self, inp: StorageProofInput) -> List[bytes]:
+        """The risc0 storage guest (storage-circuit/src/main.rs:6-31): account proof under
+        address_keccak, then every storage proof under the account's storage_root with key
+        keccak(storage_key).  Returns the verified storage values; raises VerifyPanic like the guest."""
+        hashed = self._keccak_many(inp.storage_keys)
+        items = [MerkleProofInput(inp.account_proof, inp.root_hash, bytes(inp.address_keccak))]
+        rfp = [-1]
+        for pr, k in zip(inp.storage_proofs, hashed):
+            items.append(MerkleProofInput(pr, b"\x00" * 32, k))
+            rfp.append(0)
+        res = self.verify_merkle_proofs(items, rfp)
+        for r in res:
+            if isinstance(r, VerifyPanic):
+                raise r
+        return res[1:]
+
+    def _keccak_many(self, datas: Sequence[bytes]) -> List[bytes]:
+        if not datas:
+            return []
+        lens = np.array([len(d) for d in datas], np.uint32)
+        padded = (lens.astype(np.uint64) + 15) & ~np.uint64(15)
+        off = np.zeros(len(datas), np.uint64)
+        np.cumsum(padded[:-1], out=off[1:])
+        nb = np.zeros(int(padded.sum()) + 16, np.uint8)
+        for d, o in zip(datas, off):
+            nb[int(o):int(o) + len(d)] = np.frombuffer(bytes(d), np.uint8)
+        return [r.tobytes() for r in self.keccak256_batch(nb, off, lens)]
+
+
+_DEFAULT: Optional[Verifier] = None
+
+
+def _default() -> Verifier:
+    global _DEFAULT
+    if _DEFAULT is None:
+        _DEFAULT = Verifier([0])
+    return _DEFAULT
+
+
+def verify_merkle_proof(root_hash: bytes, proof: Sequence[bytes], key: bytes) -> bytes:
+    """Drop-in for crypto_ops::verify_merkle_proof (lib.rs:8): returns the value or raises VerifyPanic."""
+    return _default().verify_merkle_proof(root_hash, proof, key)
+
+
+def verify_merkle_proofs(inputs: Sequence[MerkleProofInput]):
+    return _default().verify_merkle_proofs(inputs)
+
+
+def digest_keccak(data: bytes) -> bytes:
+    """Drop-in for crypto_ops::keccak::digest_keccak (keccak.rs:6)."""
+    return _default().digest_keccak(data)
+
+
+def verify_storage_proof_input(inp: StorageProofInput) -> List[bytes]:
+    return _default().verify_storage_proof_input(inp)

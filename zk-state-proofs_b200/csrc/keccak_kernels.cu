@@ -1,0 +1,281 @@
+// keccak_kernels.cu -- K0 (rate-block binning) and K1 (batched Keccak-256 of proof nodes).
+//
+// K1 replaces crypto_ops::keccak::digest_keccak (/root/reference/crypto-ops/src/keccak.rs:6-12)
+// applied to every proof node (/root/reference/crypto-ops/src/lib.rs:10-13) for a whole batch:
+// one thread per node, state in registers (keccak_f1600.cuh), nodes read from a flat CSR arena.
+// Nodes are binned by their 136-byte rate-block count so that the 32 lanes of a warp run the
+// same number of permutations.  Node bytes are staged HBM -> shared memory one rate block at a
+// time by 1-D bulk async copies (cp.async.bulk, UBLKCP in SASS) into a 2-stage ring guarded by
+// one mbarrier per warp per stage, so the copy of block k+1/k+2 overlaps the permutation of k.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "keccak_f1600.cuh"
+#include "kernels.h"
+
+namespace mptv {
+
+// ------------------------------------------------------------------ K0: binning
+// bin(nb): exact for nb <= 64, then 16-block-wide bins, last bin is a catch-all.
+__host__ __device__ __forceinline__ uint32_t nb_bin(uint32_t nb) {
+  if (nb <= 64) return nb;
+  uint32_t b = 64 + (nb - 64 + 15) / 16;
+  return b < kNumBins - 1 ? b : kNumBins - 1;
+}
+
+__global__ void __launch_bounds__(256) k_bin_hist(const uint32_t* __restrict__ node_len, uint64_t n_nodes,
+                                                  uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[kNumBins];
+  for (int i = threadIdx.x; i < kNumBins; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  uint64_t base = (uint64_t)blockIdx.x * kBinNodesPerBlock;
+  uint64_t end = base + kBinNodesPerBlock < n_nodes ? base + kBinNodesPerBlock : n_nodes;
+  for (uint64_t i = base + threadIdx.x; i < end; i += blockDim.x)
+    atomicAdd(&sh[nb_bin(node_len[i] / 136 + 1)], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kNumBins; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// bins laid out in DESCENDING block count so the long nodes start first (tail balance)
+__global__ void k_bin_scan(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor) {
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int b = kNumBins - 1; b >= 0; b--) { cursor[b] = acc; acc += hist[b]; }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t* __restrict__ node_len, uint64_t n_nodes,
+                                                     uint32_t* __restrict__ cursor,
+                                                     uint32_t* __restrict__ order) {
+  __shared__ uint32_t cnt[kNumBins];
+  __shared__ uint32_t start[kNumBins];
+  for (int i = threadIdx.x; i < kNumBins; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  uint64_t base = (uint64_t)blockIdx.x * kBinNodesPerBlock;
+  uint64_t end = base + kBinNodesPerBlock < n_nodes ? base + kBinNodesPerBlock : n_nodes;
+  constexpr int kPer = kBinNodesPerBlock / 256;
+  uint32_t br[kPer];  // bin << 16 | rank within this CTA's share of the bin
+#pragma unroll
+  for (int j = 0; j < kPer; j++) {
+    uint64_t i = base + threadIdx.x + (uint64_t)j * 256;
+    if (i < end) {
+      const uint32_t b = nb_bin(node_len[i] / 136 + 1);
+      br[j] = (b << 16) | atomicAdd(&cnt[b], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kNumBins; i += blockDim.x)
+    if (cnt[i]) start[i] = atomicAdd(&cursor[i], cnt[i]);
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kPer; j++) {
+    uint64_t i = base + threadIdx.x + (uint64_t)j * 256;
+    if (i < end) order[start[br[j] >> 16] + (br[j] & 0xffffu)] = (uint32_t)i;
+  }
+}
+
+// ------------------------------------------------------------------ K1: Keccak-256
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "WAIT_%=:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra DONE_%=;\n"
+    "bra WAIT_%=;\n"
+    "DONE_%=:\n"
+    "}\n" ::"r"(bar), "r"(parity)
+    : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA engine)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
+// Stage geometry: rate block k of a node covers node bytes [136k, 136k+136).  With the node
+// 16-byte aligned in the arena the 16-byte aligned window that contains it is
+// [136k - 8*(k&1), +144).  One 144-byte slot per thread per stage; slot stride 144 B = 9 x 16 B.
+constexpr int kSlotBytes = 144;
+constexpr int kStages = 2;
+
+struct BlockCopy { uint32_t src_off; uint32_t bytes; };
+__device__ __forceinline__ BlockCopy block_copy(uint32_t k, uint32_t len) {
+  uint32_t a = 136u * k - 8u * (k & 1u);
+  uint32_t e = 136u * k + 136u;
+  if (e > len) e = len;
+  e = (e + 15u) & ~15u;
+  BlockCopy c;
+  c.src_off = a;
+  c.bytes = e > a ? e - a : 0u;
+  return c;
+}
+
+__global__ void __launch_bounds__(kKeccakThreads, kKeccakMinBlocks)
+k_keccak256_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base, const uint64_t* __restrict__ node_off,
+                  const uint32_t* __restrict__ node_len, const uint32_t* __restrict__ order,
+                  uint64_t n_nodes, uint8_t* __restrict__ digests) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // layout: [stage][thread] slots, then mbarriers [warp][stage]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kKeccakThreads * kSlotBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = smem_u32(&bars[warp * kStages]);
+  const uint32_t slot0 = smem_u32(smem + tid * kSlotBytes);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; s++) mbar_init(bar0 + 8 * s, 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
+
+  const uint64_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint64_t slot_idx = tile * kKeccakThreads + tid;
+    const bool have = slot_idx < n_nodes;
+    uint32_t node = 0, len = 0, nb = 0;
+    const uint8_t* src = node_bytes;
+    if (have) {
+      node = order ? order[slot_idx] : (uint32_t)slot_idx;
+      len = node_len[node];
+      nb = len / 136u + 1u;
+      src = node_bytes + (node_off[node] - byte_base);
+    }
+    uint32_t max_nb = nb;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      uint32_t t = __shfl_xor_sync(0xffffffffu, max_nb, o);
+      max_nb = t > max_nb ? t : max_nb;
+    }
+    uint32_t lo[25], hi[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) { lo[i] = 0; hi[i] = 0; }
+
+    // prologue: fill the ring
+#pragma unroll
+    for (int s = 0; s < kStages; s++) {
+      if ((uint32_t)s < max_nb) {
+        BlockCopy c = block_copy(s, len);
+        if ((uint32_t)s < nb && c.bytes) {
+          mbar_arrive_expect_tx(bar0 + 8 * s, c.bytes);
+          bulk_g2s(slot0 + s * (kKeccakThreads * kSlotBytes), src + c.src_off, c.bytes, bar0 + 8 * s);
+        } else {
+          mbar_arrive(bar0 + 8 * s);
+        }
+      }
+    }
+    for (uint32_t k = 0; k < max_nb; k++) {
+      const uint32_t s = k % kStages;
+      mbar_wait(bar0 + 8 * s, (phase_bits >> s) & 1u);
+      phase_bits ^= 1u << s;
+      const bool active = k < nb;
+      if (active) {
+        const uint32_t p = slot0 + s * (kKeccakThreads * kSlotBytes) + 8u * (k & 1u);
+        const uint32_t valid = len - 136u * k;  // bytes of this block that are message bytes
+        if (valid >= 136u) {
+#pragma unroll
+          for (int j = 0; j < 17; j++) {
+            uint2 w = lds64(p + 8 * j);
+            lo[j] ^= w.x;
+            hi[j] ^= w.y;
+          }
+        } else {
+          // last block: message tail, then pad10*1 with the Keccak delimiter 0x01 (keccak.rs:7 v256).
+          // Branch-free per 32-bit word; stale slot bytes beyond the copied range are masked off.
+#pragma unroll
+          for (int j = 0; j < 17; j++) {
+            uint2 w = lds64(p + 8 * j);
+            uint32_t v[2] = {w.x, w.y};
+#pragma unroll
+            for (int hlf = 0; hlf < 2; hlf++) {
+              const int wi = 2 * j + hlf;
+              const int keep = (int)valid - 4 * wi;  // message bytes in this word
+              const uint32_t msk = keep >= 4 ? 0xffffffffu : (keep <= 0 ? 0u : ((1u << (8 * keep)) - 1u));
+              uint32_t x = v[hlf] & msk;
+              if ((int)(valid >> 2) == wi) x ^= 1u << (8u * (valid & 3u));
+              v[hlf] = x;
+            }
+            lo[j] ^= v[0];
+            hi[j] ^= v[1];
+          }
+          hi[16] ^= 0x80000000u;
+        }
+      }
+      // the slot has been consumed into registers: refill it with block k + kStages
+      const uint32_t kn = k + kStages;
+      if (kn < max_nb) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        BlockCopy c = block_copy(kn, len);
+        if (kn < nb && c.bytes) {
+          mbar_arrive_expect_tx(bar0 + 8 * s, c.bytes);
+          bulk_g2s(slot0 + s * (kKeccakThreads * kSlotBytes), src + c.src_off, c.bytes, bar0 + 8 * s);
+        } else {
+          mbar_arrive(bar0 + 8 * s);
+        }
+      }
+      if (active) keccak_f1600(lo, hi);
+    }
+    if (have) {
+      uint4* out = reinterpret_cast<uint4*>(digests + (uint64_t)node * 32u);
+      out[0] = make_uint4(lo[0], hi[0], lo[1], hi[1]);
+      out[1] = make_uint4(lo[2], hi[2], lo[3], hi[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host launchers
+size_t keccak_smem_bytes() { return (size_t)kStages * kKeccakThreads * kSlotBytes + (kKeccakThreads / 32) * kStages * 8; }
+
+cudaError_t kernels_init_device() {
+  return cudaFuncSetAttribute(k_keccak256_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)keccak_smem_bytes());
+}
+
+cudaError_t launch_bin_nodes(const uint32_t* node_len, uint64_t n_nodes, uint32_t* hist_cursor /*2*kNumBins*/,
+                             uint32_t* order, cudaStream_t st) {
+  if (n_nodes == 0) return cudaSuccess;
+  uint32_t* hist = hist_cursor;
+  uint32_t* cursor = hist_cursor + kNumBins;
+  cudaError_t e = cudaMemsetAsync(hist_cursor, 0, 2 * kNumBins * sizeof(uint32_t), st);
+  if (e != cudaSuccess) return e;
+  unsigned blocks = (unsigned)((n_nodes + kBinNodesPerBlock - 1) / kBinNodesPerBlock);
+  k_bin_hist<<<blocks, 256, 0, st>>>(node_len, n_nodes, hist);
+  k_bin_scan<<<1, 32, 0, st>>>(hist, cursor);
+  k_bin_scatter<<<blocks, 256, 0, st>>>(node_len, n_nodes, cursor, order);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
+                                   const uint32_t* node_len, const uint32_t* order, uint64_t n_nodes,
+                                   uint8_t* digests, int sm_count, cudaStream_t st) {
+  if (n_nodes == 0) return cudaSuccess;
+  size_t smem = keccak_smem_bytes();
+  uint64_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
+  uint64_t grid = (uint64_t)sm_count * kKeccakMinBlocks;  // persistent: one wave of resident CTAs
+  if (grid > n_tiles) grid = n_tiles;
+  k_keccak256_nodes<<<(unsigned)grid, kKeccakThreads, smem, st>>>(node_bytes, byte_base, node_off, node_len, order,
+                                                                n_nodes, digests);
+  return cudaGetLastError();
+}
+
+}  // namespace mptv

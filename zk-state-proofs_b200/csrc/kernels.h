@@ -1,0 +1,74 @@
+// kernels.h -- internal launch interface between the CUDA kernels and the C-ABI layer (mptv_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace mptv {
+
+constexpr int kNumBins = 128;            // rate-block-count bins (K0)
+constexpr int kBinNodesPerBlock = 4096;  // nodes handled by one CTA of the binning kernels
+constexpr int kKeccakThreads = 128;      // K1 CTA size: one node per thread
+constexpr int kKeccakMinBlocks = 4;      // resident CTAs / SM  (=> <= 128 registers / thread)
+
+constexpr int kMaxInlineDepth = 16;      // K2a DFS stack: inline nodes nested deeper are rejected
+
+// verdict classes, 1:1 with the reference's outcomes (include/mptv.h MPTV_ST_*)
+enum : uint32_t {
+  kStOk = 0, kStInvalidStateRoot = 1, kStRootNotCanonical = 2, kStInvalidProof = 3,
+  kStKeyNotFound = 4, kStPanicOther = 5, kStBadRootLen = 6, kStDepFailed = 7
+};
+// K2a per-node record: kind[0:3) dec[3:5) canon[5] fast[6] hdr_len[7:10) mask16[10:26)
+enum : uint32_t { kKindEmpty = 0, kKindLeaf = 1, kKindExt = 2, kKindBranch = 3, kKindHash = 4 };
+enum : uint32_t { kDecOk = 0, kDecErr = 1, kDecPanic = 2 };
+__host__ __device__ __forceinline__ uint32_t make_meta(uint32_t kind, uint32_t dec, uint32_t canon, uint32_t fast,
+                                                       uint32_t hdr_len, uint32_t mask) {
+  return kind | (dec << 3) | (canon << 5) | (fast << 6) | (hdr_len << 7) | (mask << 10);
+}
+__host__ __device__ __forceinline__ uint32_t meta_kind(uint32_t m) { return m & 7u; }
+__host__ __device__ __forceinline__ uint32_t meta_dec(uint32_t m) { return (m >> 3) & 3u; }
+__host__ __device__ __forceinline__ uint32_t meta_canon(uint32_t m) { return (m >> 5) & 1u; }
+__host__ __device__ __forceinline__ uint32_t meta_fast(uint32_t m) { return (m >> 6) & 1u; }
+__host__ __device__ __forceinline__ uint32_t meta_hdr(uint32_t m) { return (m >> 7) & 7u; }
+__host__ __device__ __forceinline__ uint32_t meta_mask(uint32_t m) { return (m >> 10) & 0xffffu; }
+
+// device-resident batch in the CSR layout of include/mptv.h
+struct DeviceBatch {
+  const uint8_t* node_bytes;
+  const uint64_t* node_off;
+  const uint32_t* node_len;
+  uint64_t n_nodes;
+  const uint32_t* proof_first;
+  uint64_t n_proofs;
+  const uint8_t* roots;
+  const uint8_t* key_bytes;
+  const uint32_t* key_off;
+  const int32_t* root_from_proof;  // may be null
+  // slice view of a larger CSR (host-buffer pipeline): the arrays above hold the slice, but their
+  // VALUES are still global indices / offsets; these bases translate them.  All 0 for a whole batch.
+  uint64_t byte_base;   // node_off values are relative to node_bytes - byte_base
+  uint32_t node_base;   // proof_first values are node indices + node_base
+  uint32_t key_base;    // key_off values are offsets + key_base
+  uint64_t proof_base;  // root_from_proof values are proof indices + proof_base
+};
+
+// per-device one-time setup (dynamic shared memory opt-in); call with the device current
+cudaError_t kernels_init_device();
+
+// K0: order[] = node indices sorted by DESCENDING rate-block bin.  scratch = 2*kNumBins u32.
+cudaError_t launch_bin_nodes(const uint32_t* node_len, uint64_t n_nodes, uint32_t* scratch, uint32_t* order,
+                             cudaStream_t st);
+// K1: digests[32*i] = keccak256(node i).  order may be NULL (identity).
+cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
+                                   const uint32_t* node_len, const uint32_t* order, uint64_t n_nodes,
+                                   uint8_t* digests, int sm_count, cudaStream_t st);
+
+// K2a: meta[i] = eager-decode record of node i
+cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
+                               const uint32_t* node_len, uint64_t n_nodes, uint32_t* meta, cudaStream_t st);
+// K2b: wave 0 = proofs with their own root, wave 1 = proofs whose root is another proof's storage_root
+cudaError_t launch_verify_walk(const DeviceBatch& b, const uint8_t* digests, const uint32_t* meta, int wave,
+                               int lanes_per_proof, uint8_t* status, uint64_t* value_off, uint32_t* value_len,
+                               cudaStream_t st);
+
+}  // namespace mptv

@@ -1,0 +1,483 @@
+// mptv_api.cu -- the C ABI of include/mptv.h: context, per-device memory and streams, the
+// device-resident entry, and the host-buffer entry that shards a batch across the context's GPUs
+// as independent proof slices (no collective, no inter-device traffic) and pipelines each slice in
+// chunks.  Replaces the call boundary of crypto_ops::verify_merkle_proof
+// (/root/reference/crypto-ops/src/lib.rs:8) for batches of MerkleProofInput
+// (/root/reference/crypto-ops/src/types.rs:4-9).  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/mptv.h"
+#include "kernels.h"
+
+using namespace mptv;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, n); want = n; }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// one pipeline slot of the host-buffer path: device copies of a chunk's inputs and outputs
+struct Slot {
+  cudaStream_t stream = nullptr;
+  DevBuf node_bytes, node_off, node_len, proof_first, roots, key_bytes, key_off, rfp;
+  DevBuf status, value_off, value_len;
+  DevBuf digests, meta, order, bins;
+  void release() {
+    DevBuf* all[] = {&node_bytes, &node_off, &node_len, &proof_first, &roots, &key_bytes, &key_off, &rfp,
+                     &status, &value_off, &value_len, &digests, &meta, &order, &bins};
+    for (DevBuf* b : all) b->release();
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+  }
+};
+
+struct Device {
+  int id = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;  // device-resident entry
+  DevBuf digests, meta, order, bins;  // scratch of the device-resident entry
+  Slot slot[2];
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t last_stream = nullptr;
+  bool have_timing = false;
+  uint64_t last_nodes = 0;
+  uint32_t last_keccak_launches = 0, last_other_launches = 0;
+};
+
+}  // namespace
+
+struct mptv_ctx {
+  std::vector<Device> dev;
+  std::string err;
+  int lanes_per_proof = 0;          // 0 = auto
+  uint64_t chunk_bytes = 96ull << 20;  // node bytes per pipeline chunk of the host-buffer path
+  int binning = 1;
+};
+
+namespace {
+
+int fail_cuda(mptv_ctx* c, cudaError_t e, const char* where) {
+  char buf[256];
+  snprintf(buf, sizeof buf, "%s: %s", where, cudaGetErrorString(e));
+  if (c) c->err = buf;
+  return MPTV_ERR_CUDA;
+}
+#define CK(call)                                             \
+  do {                                                       \
+    cudaError_t e__ = (call);                                \
+    if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call); \
+  } while (0)
+
+int pick_lanes(const mptv_ctx* ctx, uint64_t n_nodes, uint64_t n_proofs) {
+  if (ctx->lanes_per_proof == 8 || ctx->lanes_per_proof == 16 || ctx->lanes_per_proof == 32)
+    return ctx->lanes_per_proof;
+  double avg = n_proofs ? (double)n_nodes / (double)n_proofs : 0.0;
+  return avg <= 8.5 ? 8 : (avg <= 17.0 ? 16 : 32);
+}
+
+// The whole device pipeline for one device-resident (slice of a) batch: K0 -> K1 -> K2a -> K2b.
+int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests, DevBuf& meta, DevBuf& order,
+                 DevBuf& bins, uint8_t* status, uint64_t* value_off, uint32_t* value_len, cudaStream_t st,
+                 bool timed) {
+  CK(digests.reserve(32 * (size_t)b.n_nodes + 32));
+  CK(meta.reserve(4 * (size_t)b.n_nodes + 4));
+  CK(order.reserve(4 * (size_t)b.n_nodes + 4));
+  CK(bins.reserve(2 * kNumBins * sizeof(uint32_t)));
+  if (timed) CK(cudaEventRecord(d.ev[0], st));
+  const uint32_t* ord = nullptr;
+  if (ctx->binning) {
+    CK(launch_bin_nodes(b.node_len, b.n_nodes, bins.as<uint32_t>(), order.as<uint32_t>(), st));
+    ord = order.as<uint32_t>();
+  }
+  if (timed) CK(cudaEventRecord(d.ev[1], st));
+  CK(launch_keccak256_nodes(b.node_bytes, b.byte_base, b.node_off, b.node_len, ord, b.n_nodes,
+                            digests.as<uint8_t>(), d.sm_count, st));
+  if (timed) CK(cudaEventRecord(d.ev[2], st));
+  CK(launch_parse_nodes(b.node_bytes, b.byte_base, b.node_off, b.node_len, b.n_nodes, meta.as<uint32_t>(), st));
+  if (timed) CK(cudaEventRecord(d.ev[3], st));
+  const int G = pick_lanes(ctx, b.n_nodes, b.n_proofs);
+  CK(launch_verify_walk(b, digests.as<uint8_t>(), meta.as<uint32_t>(), 0, G, status, value_off, value_len, st));
+  uint32_t other = 1 + 1 + (ctx->binning ? 3 : 0);
+  if (b.root_from_proof) {
+    CK(launch_verify_walk(b, digests.as<uint8_t>(), meta.as<uint32_t>(), 1, G, status, value_off, value_len, st));
+    other++;
+  }
+  if (timed) {
+    CK(cudaEventRecord(d.ev[4], st));
+    d.last_stream = st;
+    d.have_timing = true;
+    d.last_nodes = b.n_nodes;
+    d.last_keccak_launches = b.n_nodes ? 1 : 0;
+    d.last_other_launches = other;
+  }
+  return MPTV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mptv_strerror(int err) {
+  switch (err) {
+    case MPTV_OK: return "ok";
+    case MPTV_ERR_ARG: return "invalid argument";
+    case MPTV_ERR_CUDA: return "CUDA error (see mptv_last_error)";
+    case MPTV_ERR_ALIGN: return "node not 16-byte aligned in the arena";
+    case MPTV_ERR_NOMEM: return "out of memory";
+    case MPTV_ERR_DEP: return "root_from_proof must reference an earlier independent proof of the same slice";
+    case MPTV_ERR_NODEV: return "no usable CUDA device (there is no CPU fallback)";
+  }
+  return "unknown error";
+}
+
+const char* mptv_status_name(int s) {
+  static const char* n[] = {"OK", "INVALID_STATE_ROOT", "ROOT_NOT_CANONICAL", "INVALID_PROOF",
+                            "KEY_NOT_FOUND", "PANIC_OTHER", "BAD_ROOT_LEN", "DEPENDENCY_FAILED"};
+  return (s >= 0 && s < 8) ? n[s] : "?";
+}
+
+const char* mptv_last_error(const mptv_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }
+int mptv_device_count(const mptv_ctx* ctx) { return ctx ? (int)ctx->dev.size() : 0; }
+
+int mptv_create(const int* device_ids, int n_devices, mptv_ctx** out) {
+  if (!out) return MPTV_ERR_ARG;
+  *out = nullptr;
+  int visible = 0;
+  if (cudaGetDeviceCount(&visible) != cudaSuccess || visible <= 0) return MPTV_ERR_NODEV;
+  std::vector<int> ids;
+  if (device_ids == nullptr || n_devices <= 0) for (int i = 0; i < visible; i++) ids.push_back(i);
+  else for (int i = 0; i < n_devices; i++) {
+    if (device_ids[i] < 0 || device_ids[i] >= visible) return MPTV_ERR_ARG;
+    ids.push_back(device_ids[i]);
+  }
+  mptv_ctx* ctx = new mptv_ctx();
+  ctx->dev.resize(ids.size());
+  for (size_t i = 0; i < ids.size(); i++) {
+    Device& d = ctx->dev[i];
+    d.id = ids[i];
+    cudaError_t e = cudaSetDevice(d.id);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, d.id);
+    if (e == cudaSuccess && prop.major < 10) {  // sm_100a code only
+      delete ctx;
+      return MPTV_ERR_NODEV;
+    }
+    if (e == cudaSuccess) { d.sm_count = prop.multiProcessorCount; e = kernels_init_device(); }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+    for (int s = 0; s < 2 && e == cudaSuccess; s++) e = cudaStreamCreateWithFlags(&d.slot[s].stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 6 && e == cudaSuccess; k++) e = cudaEventCreate(&d.ev[k]);
+    if (e != cudaSuccess) {
+      fprintf(stderr, "mptv_create: device %d: %s\n", d.id, cudaGetErrorString(e));
+      mptv_destroy(ctx);
+      return MPTV_ERR_NODEV;
+    }
+  }
+  *out = ctx;
+  return MPTV_OK;
+}
+
+void mptv_destroy(mptv_ctx* ctx) {
+  if (!ctx) return;
+  for (Device& d : ctx->dev) {
+    cudaSetDevice(d.id);
+    cudaDeviceSynchronize();
+    d.digests.release(); d.meta.release(); d.order.release(); d.bins.release();
+    d.slot[0].release(); d.slot[1].release();
+    for (auto& e : d.ev) if (e) cudaEventDestroy(e);
+    if (d.stream) cudaStreamDestroy(d.stream);
+  }
+  delete ctx;
+}
+
+int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return MPTV_ERR_ARG;
+  if (!strcmp(name, "lanes_per_proof")) {
+    if (value != 0 && value != 8 && value != 16 && value != 32) return MPTV_ERR_ARG;
+    ctx->lanes_per_proof = (int)value;
+  } else if (!strcmp(name, "chunk_bytes")) {
+    if (value < (1 << 16)) return MPTV_ERR_ARG;
+    ctx->chunk_bytes = (uint64_t)value;
+  } else if (!strcmp(name, "binning")) {
+    ctx->binning = value ? 1 : 0;
+  } else return MPTV_ERR_ARG;
+  return MPTV_OK;
+}
+
+void* mptv_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+  return p;
+}
+void mptv_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------ device-resident entries
+int mptv_verify_batch_device(mptv_ctx* ctx, int dev_index, const mptv_batch* in, mptv_result* out, void* stream) {
+  if (!ctx || !in || !out || dev_index < 0 || dev_index >= (int)ctx->dev.size()) return MPTV_ERR_ARG;
+  if (in->n_nodes > 0xfffffff0ull) return MPTV_ERR_ARG;
+  Device& d = ctx->dev[dev_index];
+  CK(cudaSetDevice(d.id));
+  cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
+  DeviceBatch b;
+  b.node_bytes = in->node_bytes; b.node_off = in->node_off; b.node_len = in->node_len; b.n_nodes = in->n_nodes;
+  b.proof_first = in->proof_first; b.n_proofs = in->n_proofs; b.roots = in->roots;
+  b.key_bytes = in->key_bytes; b.key_off = in->key_off; b.root_from_proof = in->root_from_proof;
+  b.byte_base = 0; b.node_base = 0; b.key_base = 0; b.proof_base = 0;
+  return run_pipeline(ctx, d, b, d.digests, d.meta, d.order, d.bins, out->status, out->value_off, out->value_len,
+                      st, true);
+}
+
+int mptv_keccak256_batch_device(mptv_ctx* ctx, int dev_index, const uint8_t* node_bytes, const uint64_t* node_off,
+                                const uint32_t* node_len, uint64_t n_nodes, uint8_t* digests32, void* stream) {
+  if (!ctx || dev_index < 0 || dev_index >= (int)ctx->dev.size()) return MPTV_ERR_ARG;
+  if (n_nodes > 0xfffffff0ull) return MPTV_ERR_ARG;
+  Device& d = ctx->dev[dev_index];
+  CK(cudaSetDevice(d.id));
+  cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
+  CK(d.order.reserve(4 * (size_t)n_nodes + 4));
+  CK(d.bins.reserve(2 * kNumBins * sizeof(uint32_t)));
+  CK(cudaEventRecord(d.ev[0], st));
+  const uint32_t* ord = nullptr;
+  if (ctx->binning) {
+    CK(launch_bin_nodes(node_len, n_nodes, d.bins.as<uint32_t>(), d.order.as<uint32_t>(), st));
+    ord = d.order.as<uint32_t>();
+  }
+  CK(cudaEventRecord(d.ev[1], st));
+  CK(launch_keccak256_nodes(node_bytes, 0, node_off, node_len, ord, n_nodes, digests32, d.sm_count, st));
+  CK(cudaEventRecord(d.ev[2], st));
+  CK(cudaEventRecord(d.ev[3], st));
+  CK(cudaEventRecord(d.ev[4], st));
+  d.last_stream = st; d.have_timing = true; d.last_nodes = n_nodes;
+  d.last_keccak_launches = n_nodes ? 1 : 0; d.last_other_launches = ctx->binning ? 3 : 0;
+  return MPTV_OK;
+}
+
+int mptv_last_timings(mptv_ctx* ctx, int dev_index, mptv_timings* out) {
+  if (!ctx || !out || dev_index < 0 || dev_index >= (int)ctx->dev.size()) return MPTV_ERR_ARG;
+  Device& d = ctx->dev[dev_index];
+  memset(out, 0, sizeof *out);
+  if (!d.have_timing) return MPTV_ERR_ARG;
+  CK(cudaSetDevice(d.id));
+  CK(cudaEventSynchronize(d.ev[4]));
+  CK(cudaEventElapsedTime(&out->bin_ms, d.ev[0], d.ev[1]));
+  CK(cudaEventElapsedTime(&out->keccak_ms, d.ev[1], d.ev[2]));
+  CK(cudaEventElapsedTime(&out->parse_ms, d.ev[2], d.ev[3]));
+  CK(cudaEventElapsedTime(&out->walk_ms, d.ev[3], d.ev[4]));
+  CK(cudaEventElapsedTime(&out->total_ms, d.ev[0], d.ev[4]));
+  out->n_nodes = d.last_nodes;
+  out->keccak_launches = d.last_keccak_launches;
+  out->other_launches = d.last_other_launches;
+  return MPTV_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer entries
+}  // extern "C"
+
+namespace {
+
+struct Chunk { uint64_t p0, p1; };  // proof range
+
+// cut [p0, p1) into chunks of about `chunk_bytes` node bytes without splitting a dependency group
+int make_chunks(const mptv_batch* in, uint64_t p0, uint64_t p1, uint64_t chunk_bytes, std::vector<Chunk>& out) {
+  uint64_t s = p0;
+  while (s < p1) {
+    uint64_t e = s;
+    const uint64_t byte0 = in->node_off[in->proof_first[s]];
+    while (e < p1) {
+      const uint32_t nlast = in->proof_first[e + 1];
+      const uint64_t bytes_end = nlast > in->proof_first[s]
+                                   ? in->node_off[nlast - 1] + in->node_len[nlast - 1] : byte0;
+      if (e > s && bytes_end - byte0 > chunk_bytes && (!in->root_from_proof || in->root_from_proof[e] < 0)) break;
+      e++;
+    }
+    out.push_back({s, e});
+    s = e;
+  }
+  return MPTV_OK;
+}
+
+int validate_slice(const mptv_batch* in, uint64_t p0, uint64_t p1) {
+  for (uint64_t p = p0; p < p1; p++) {
+    if (in->proof_first[p + 1] < in->proof_first[p] || in->proof_first[p + 1] > in->n_nodes) return MPTV_ERR_ARG;
+    if (in->key_off[p + 1] < in->key_off[p]) return MPTV_ERR_ARG;
+  }
+  const uint32_t n0 = in->proof_first[p0], n1 = in->proof_first[p1];
+  uint64_t prev_end = 0;
+  for (uint32_t i = n0; i < n1; i++) {
+    const uint64_t o = in->node_off[i];
+    if (o & 15) return MPTV_ERR_ALIGN;
+    if (o < prev_end && i > n0) return MPTV_ERR_ARG;  // nodes must be laid out in index order
+    prev_end = o + in->node_len[i];
+    if (((prev_end + 15) & ~15ull) > ((in->node_bytes_len + 15) & ~15ull)) return MPTV_ERR_ARG;
+  }
+  return MPTV_OK;
+}
+
+// run one device's slice [p0, p1): chunked, double-buffered H2D -> kernels -> D2H
+int run_slice(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result* out, uint64_t p0, uint64_t p1) {
+  if (p1 <= p0) return MPTV_OK;
+  CK(cudaSetDevice(d.id));
+  int rc = validate_slice(in, p0, p1);
+  if (rc != MPTV_OK) return rc;
+  std::vector<Chunk> chunks;
+  make_chunks(in, p0, p1, ctx->chunk_bytes, chunks);
+  for (size_t ci = 0; ci < chunks.size(); ci++) {
+    const Chunk c = chunks[ci];
+    Slot& s = d.slot[ci & 1];
+    cudaStream_t st = s.stream;
+    CK(cudaStreamSynchronize(st));  // the slot's previous chunk (two back) must be drained
+    const uint64_t np = c.p1 - c.p0;
+    const uint32_t n0 = in->proof_first[c.p0], n1 = in->proof_first[c.p1];
+    const uint64_t nn = n1 - n0;
+    const uint64_t byte0 = nn ? in->node_off[n0] : 0;
+    uint64_t byte1 = nn ? in->node_off[n1 - 1] + in->node_len[n1 - 1] : 0;
+    if (byte1 > in->node_bytes_len) byte1 = in->node_bytes_len;  // device buffers carry 16 spare bytes
+    const uint32_t k0 = in->key_off[c.p0], k1 = in->key_off[c.p1];
+    if (in->root_from_proof)
+      for (uint64_t p = c.p0; p < c.p1; p++) {
+        const int32_t r = in->root_from_proof[p];
+        if (r >= 0 && ((uint64_t)r < c.p0 || (uint64_t)r >= p || in->root_from_proof[r] >= 0)) return MPTV_ERR_DEP;
+      }
+    CK(s.node_bytes.reserve(byte1 - byte0 + 16));
+    CK(s.node_off.reserve(8 * nn + 8));
+    CK(s.node_len.reserve(4 * nn + 4));
+    CK(s.proof_first.reserve(4 * (np + 1)));
+    CK(s.roots.reserve(32 * np));
+    CK(s.key_bytes.reserve((size_t)(k1 - k0) + 16));
+    CK(s.key_off.reserve(4 * (np + 1)));
+    CK(s.status.reserve(np));
+    CK(s.value_off.reserve(8 * np));
+    CK(s.value_len.reserve(4 * np));
+    if (in->root_from_proof) CK(s.rfp.reserve(4 * np));
+    CK(cudaMemcpyAsync(s.node_bytes.p, in->node_bytes + byte0, byte1 - byte0, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.node_off.p, in->node_off + n0, 8 * nn, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.node_len.p, in->node_len + n0, 4 * nn, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.proof_first.p, in->proof_first + c.p0, 4 * (np + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.roots.p, in->roots + 32 * c.p0, 32 * np, cudaMemcpyHostToDevice, st));
+    if (k1 > k0) CK(cudaMemcpyAsync(s.key_bytes.p, in->key_bytes + k0, k1 - k0, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.key_off.p, in->key_off + c.p0, 4 * (np + 1), cudaMemcpyHostToDevice, st));
+    if (in->root_from_proof)
+      CK(cudaMemcpyAsync(s.rfp.p, in->root_from_proof + c.p0, 4 * np, cudaMemcpyHostToDevice, st));
+    DeviceBatch b;
+    b.node_bytes = s.node_bytes.as<uint8_t>(); b.node_off = s.node_off.as<uint64_t>();
+    b.node_len = s.node_len.as<uint32_t>(); b.n_nodes = nn;
+    b.proof_first = s.proof_first.as<uint32_t>(); b.n_proofs = np; b.roots = s.roots.as<uint8_t>();
+    b.key_bytes = s.key_bytes.as<uint8_t>(); b.key_off = s.key_off.as<uint32_t>();
+    b.root_from_proof = in->root_from_proof ? s.rfp.as<int32_t>() : nullptr;
+    b.byte_base = byte0; b.node_base = n0; b.key_base = k0; b.proof_base = c.p0;
+    rc = run_pipeline(ctx, d, b, s.digests, s.meta, s.order, s.bins, s.status.as<uint8_t>(),
+                      s.value_off.as<uint64_t>(), s.value_len.as<uint32_t>(), st, false);
+    if (rc != MPTV_OK) return rc;
+    CK(cudaMemcpyAsync(out->status + c.p0, s.status.p, np, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->value_off + c.p0, s.value_off.p, 8 * np, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->value_len + c.p0, s.value_len.p, 4 * np, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(d.slot[0].stream));
+  CK(cudaStreamSynchronize(d.slot[1].stream));
+  return MPTV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mptv_verify_batch(mptv_ctx* ctx, const mptv_batch* in, mptv_result* out) {
+  if (!ctx || !in || !out) return MPTV_ERR_ARG;
+  if (in->n_proofs == 0) return MPTV_OK;
+  if (!in->node_off || !in->node_len || !in->proof_first || !in->roots || !in->key_off || !out->status ||
+      !out->value_off || !out->value_len)
+    return MPTV_ERR_ARG;
+  if (in->n_nodes > 0xfffffff0ull || in->proof_first[in->n_proofs] > in->n_nodes) return MPTV_ERR_ARG;
+  const int nd = (int)ctx->dev.size();
+  // slice boundaries: equal shares of the Keccak-f count (~ node bytes), never inside a dependency group
+  std::vector<uint64_t> cut(nd + 1, 0);
+  cut[nd] = in->n_proofs;
+  if (nd > 1) {
+    const uint32_t n_total = in->proof_first[in->n_proofs];
+    const uint64_t total = n_total ? in->node_off[n_total - 1] + in->node_len[n_total - 1] : 0;
+    uint64_t p = 0;
+    for (int k = 1; k < nd; k++) {
+      const uint64_t target = total / nd * k;
+      // binary search the first proof whose first node starts at or after `target`
+      uint64_t lo = p, hi = in->n_proofs;
+      while (lo < hi) {
+        const uint64_t mid = (lo + hi) / 2;
+        const uint32_t fn = in->proof_first[mid];
+        const uint64_t off = fn < n_total ? in->node_off[fn] : total;
+        if (off < target) lo = mid + 1; else hi = mid;
+      }
+      p = lo;
+      if (in->root_from_proof) while (p < in->n_proofs && in->root_from_proof[p] >= 0) p++;
+      cut[k] = p;
+    }
+  }
+  std::vector<int> rcs(nd, MPTV_OK);
+  if (nd == 1) {
+    rcs[0] = run_slice(ctx, ctx->dev[0], in, out, cut[0], cut[1]);
+  } else {
+    std::vector<std::thread> th;
+    for (int k = 0; k < nd; k++)
+      th.emplace_back([&, k] { rcs[k] = run_slice(ctx, ctx->dev[k], in, out, cut[k], cut[k + 1]); });
+    for (auto& t : th) t.join();
+  }
+  for (int k = 0; k < nd; k++) if (rcs[k] != MPTV_OK) return rcs[k];
+  return MPTV_OK;
+}
+
+int mptv_keccak256_batch(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node_bytes_len, const uint64_t* node_off,
+                         const uint32_t* node_len, uint64_t n_nodes, uint8_t* digests32) {
+  if (!ctx || (n_nodes && (!node_bytes || !node_off || !node_len || !digests32))) return MPTV_ERR_ARG;
+  if (n_nodes == 0) return MPTV_OK;
+  if (n_nodes > 0xfffffff0ull) return MPTV_ERR_ARG;
+  for (uint64_t i = 0; i < n_nodes; i++) {
+    if (node_off[i] & 15) return MPTV_ERR_ALIGN;
+    if (((node_off[i] + node_len[i] + 15) & ~15ull) > ((node_bytes_len + 15) & ~15ull)) return MPTV_ERR_ARG;
+  }
+  Device& d = ctx->dev[0];
+  Slot& s = d.slot[0];
+  CK(cudaSetDevice(d.id));
+  cudaStream_t st = s.stream;
+  const uint64_t padded = (node_bytes_len + 15) & ~15ull;
+  CK(s.node_bytes.reserve(padded + 16));
+  CK(s.node_off.reserve(8 * n_nodes));
+  CK(s.node_len.reserve(4 * n_nodes));
+  CK(s.digests.reserve(32 * n_nodes));
+  CK(s.order.reserve(4 * n_nodes));
+  CK(s.bins.reserve(2 * kNumBins * sizeof(uint32_t)));
+  CK(cudaMemsetAsync(s.node_bytes.p, 0, padded + 16, st));
+  CK(cudaMemcpyAsync(s.node_bytes.p, node_bytes, node_bytes_len, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.node_off.p, node_off, 8 * n_nodes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.node_len.p, node_len, 4 * n_nodes, cudaMemcpyHostToDevice, st));
+  const uint32_t* ord = nullptr;
+  if (ctx->binning) {
+    CK(launch_bin_nodes(s.node_len.as<uint32_t>(), n_nodes, s.bins.as<uint32_t>(), s.order.as<uint32_t>(), st));
+    ord = s.order.as<uint32_t>();
+  }
+  CK(launch_keccak256_nodes(s.node_bytes.as<uint8_t>(), 0, s.node_off.as<uint64_t>(), s.node_len.as<uint32_t>(), ord,
+                            n_nodes, s.digests.as<uint8_t>(), d.sm_count, st));
+  CK(cudaMemcpyAsync(digests32, s.digests.p, 32 * n_nodes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MPTV_OK;
+}
+
+}  // extern "C"

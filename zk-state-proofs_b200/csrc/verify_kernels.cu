@@ -1,0 +1,481 @@
+// verify_kernels.cu -- K2a (per-node eager RLP decode / canonical-form check) and
+// K2b (group-of-lanes-per-proof nibble walk with ballot/shuffle hash-link lookup).
+//
+// Together they replace, for a whole batch, what crypto_ops::verify_merkle_proof
+// (/root/reference/crypto-ops/src/lib.rs:8-23) does per proof after hashing:
+//   lib.rs:14  EthTrie::from(proof_db, root)      -> root lookup by digest + eager decode_node
+//   lib.rs:19  assert_eq!(root, trie.root_hash()) -> re-encode(decode(root)) == root bytes  (K3)
+//   lib.rs:20  trie.verify_proof(root, key, proof)-> len>=32 filter, Nibbles::from_raw, get_at
+//   lib.rs:21-22 the two expect()s                -> INVALID_PROOF / KEY_NOT_FOUND
+// The third-party behaviour (eth_trie@ade617b decode_node / get_at / write_node, alloy-rlp
+// Header::decode) is the rule set R1..R20 of SURVEY.md Appendix A, pinned against the
+// reference's own guest ELF through oracle/ (tests/golden/verify_vectors.json).
+//
+// K2a runs one thread per supplied node and records, in one u32 per node, what a visit of that
+// node by the reference would produce: decode status (ok / TrieError / raw panic, first failure in
+// the reference's decode order), node kind, whether it survives the root-only re-encode check,
+// and for plain branches the 16-bit occupancy map from which every child offset follows.
+// K2b walks each proof with a group of G lanes (G = 8, 16 or 32): lane j owns the digest of node
+// j; a child reference is found by comparing the 32-byte link against all digests at once
+// (shuffle-broadcast of the link words + ballot), leaf / extension paths are compared
+// nibble-parallel across the lanes, and the occupancy map turns the 16-way child selection into
+// a popcount.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace mptv {
+
+// ------------------------------------------------------------------ RLP header (alloy-rlp, R17)
+struct Hdr { uint32_t is_list, hdr_len, payload_len; };
+
+__device__ __forceinline__ uint32_t ldb(const uint8_t* p) { return (uint32_t)__ldg(p); }
+
+// strict canonical header of the item that starts at p with n bytes available
+__device__ bool rlp_hdr(const uint8_t* p, uint32_t n, Hdr& h) {
+  if (n == 0) return false;
+  uint32_t b = ldb(p);
+  if (b < 0x80) { h.is_list = 0; h.hdr_len = 0; h.payload_len = 1; return true; }
+  if (b < 0xB8) {
+    h.is_list = 0; h.hdr_len = 1; h.payload_len = b - 0x80;
+    if (h.payload_len == 1) {
+      if (n < 2) return false;
+      if (ldb(p + 1) < 0x80) return false;  // NonCanonicalSingleByte
+    }
+  } else if (b < 0xC0 || b >= 0xF8) {
+    h.is_list = b >= 0xF8 ? 1u : 0u;
+    uint32_t ll = h.is_list ? b - 0xF7 : b - 0xB7;
+    if (n < 1 + ll) return false;
+    if (ldb(p + 1) == 0) return false;  // LeadingZero
+    if (ll > 4) return false;           // cannot fit in a u32-sized node
+    uint32_t v = 0;
+    for (uint32_t i = 0; i < ll; i++) v = (v << 8) | ldb(p + 1 + i);
+    if (v < 56) return false;  // NonCanonicalSize
+    h.hdr_len = 1 + ll; h.payload_len = v;
+  } else {
+    h.is_list = 1; h.hdr_len = 1; h.payload_len = b - 0xC0;
+  }
+  return (uint64_t)h.hdr_len + h.payload_len <= (uint64_t)n;  // InputTooShort
+}
+
+// ------------------------------------------------------------------ K2a: per-node decode
+// Frame of the explicit DFS stack over nested inline nodes.
+struct Frame { uint32_t pos, end; uint8_t cnt, idx, leaf, pad; };
+
+// scan the items of the list at p[lst .. lst+hdr+payload): every header must be valid and fit;
+// returns the item count (18 means "more than 17") or -1 on a header error
+__device__ int scan_items(const uint8_t* p, uint32_t lst, const Hdr& h) {
+  uint32_t q = lst + h.hdr_len, e = q + h.payload_len;
+  int cnt = 0;
+  while (q < e) {
+    Hdr t;
+    if (!rlp_hdr(p + q, e - q, t)) return -1;
+    q += t.hdr_len + t.payload_len;
+    if (++cnt > 17) return 18;
+  }
+  return cnt;
+}
+
+__device__ __forceinline__ bool value_item_canonical(const Hdr& t) {
+  // R20 x R4: the value is re-encoded as an RLP string of the decoded value bytes; that reproduces
+  // the original item iff it was a string and not the 2-byte form 0x81 b (decoded as [0x81, b]).
+  return !t.is_list && !(t.hdr_len == 1 && t.payload_len == 1);
+}
+
+__device__ uint32_t parse_node(const uint8_t* p, uint32_t n) {
+  Hdr h;
+  if (!rlp_hdr(p, n, h)) return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);
+  uint32_t canon = (h.hdr_len + h.payload_len == n) ? 1u : 0u;  // trailing bytes (R18 vs R4)
+  if (!h.is_list) {
+    if (h.payload_len == 0) return make_meta(kKindEmpty, kDecOk, canon, 0, h.hdr_len, 0);
+    if (h.payload_len == 32) return make_meta(kKindHash, kDecOk, 0, 0, h.hdr_len, 0);
+    return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);
+  }
+  Frame st[kMaxInlineDepth];
+  int sp = 0;
+  {
+    int c = scan_items(p, 0, h);
+    if (c != 2 && c != 17) return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);
+    st[0].pos = h.hdr_len; st[0].end = h.hdr_len + h.payload_len;
+    st[0].cnt = (uint8_t)c; st[0].idx = 0; st[0].leaf = 0;
+  }
+  uint32_t top_kind = st[0].cnt == 17 ? kKindBranch : kKindExt;
+  uint32_t mask = 0, fast = st[0].cnt == 17 ? 1u : 0u;
+  while (sp >= 0) {
+    Frame& f = st[sp];
+    if (f.idx == f.cnt) { sp--; continue; }
+    Hdr t;
+    rlp_hdr(p + f.pos, f.end - f.pos, t);  // validated by scan_items
+    const uint32_t item = f.pos;
+    const uint32_t i = f.idx;
+    f.pos += t.hdr_len + t.payload_len;
+    f.idx++;
+    bool is_child = false;
+    if (f.cnt == 2) {
+      if (i == 0) {
+        // Nibbles::from_compact on the item's payload (R19); list/string flag not checked
+        if (t.payload_len == 0) return make_meta(kKindEmpty, kDecPanic, 0, 0, 0, 0);
+        uint32_t b = ldb(p + item + t.hdr_len);
+        uint32_t flag = b >> 4;
+        if (flag > 3) return make_meta(kKindEmpty, kDecPanic, 0, 0, 0, 0);
+        uint32_t nn = (t.payload_len - 1) * 2 + (flag & 1);
+        f.leaf = flag >= 2;
+        // decode_node calls key.is_leaf() = hex_data[len-1]: panics on an empty extension path
+        if (!f.leaf && nn == 0) return make_meta(kKindEmpty, kDecPanic, 0, 0, 0, 0);
+        if (t.is_list || (!(flag & 1) && (b & 15))) canon = 0;
+        if (sp == 0) top_kind = f.leaf ? kKindLeaf : kKindExt;
+      } else if (f.leaf) {
+        if (!value_item_canonical(t)) canon = 0;
+      } else {
+        is_child = true;
+      }
+    } else {
+      if (i < 16) is_child = true;
+      else if (!value_item_canonical(t)) canon = 0;
+    }
+    if (is_child) {
+      if (t.is_list) {
+        // inline node: decoded recursively; re-encodes in place only while < 32 bytes (write_node)
+        if (t.hdr_len + t.payload_len >= 32) canon = 0;
+        if (sp == 0) fast = 0;
+        if (sp + 1 >= kMaxInlineDepth) return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);
+        int c = scan_items(p, item, t);
+        if (c != 2 && c != 17) return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);
+        sp++;
+        st[sp].pos = item + t.hdr_len; st[sp].end = item + t.hdr_len + t.payload_len;
+        st[sp].cnt = (uint8_t)c; st[sp].idx = 0; st[sp].leaf = 0;
+      } else if (t.payload_len == 32) {
+        if (sp == 0) mask |= 1u << i;
+      } else if (t.payload_len != 0) {
+        return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);  // InvalidData (R16)
+      }
+    }
+  }
+  return make_meta(top_kind, kDecOk, canon, fast, h.hdr_len, mask);
+}
+
+__global__ void __launch_bounds__(256) k_parse_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base,
+                                                     const uint64_t* __restrict__ node_off,
+                                                     const uint32_t* __restrict__ node_len, uint64_t n_nodes,
+                                                     uint32_t* __restrict__ meta) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  meta[i] = parse_node(node_bytes + (node_off[i] - byte_base), node_len[i]);
+}
+
+// ------------------------------------------------------------------ K2b: the walk
+// alloy_rlp::decode_exact::<Account> (storage-circuit/src/main.rs:15): rlp([nonce u64, balance
+// U256, storage_root B256, code_hash B256]) with nothing left over.  Returns the offset of the
+// 32-byte storage_root inside v, or 0xffffffff.
+__device__ uint32_t account_storage_root_off(const uint8_t* v, uint32_t n) {
+  Hdr h, t;
+  if (!rlp_hdr(v, n, h) || !h.is_list) return 0xffffffffu;
+  if (h.hdr_len + h.payload_len != n) return 0xffffffffu;
+  uint32_t q = h.hdr_len, e = n, off = 0xffffffffu;
+  for (int i = 0; i < 4; i++) {
+    if (!rlp_hdr(v + q, e - q, t) || t.is_list) return 0xffffffffu;
+    if (i == 0 && t.payload_len > 8) return 0xffffffffu;
+    if (i == 1 && t.payload_len > 32) return 0xffffffffu;
+    if (i < 2 && t.payload_len > 0 && ldb(v + q + t.hdr_len) == 0) return 0xffffffffu;
+    if (i >= 2 && t.payload_len != 32) return 0xffffffffu;
+    if (i == 2) off = q + t.hdr_len;
+    q += t.hdr_len + t.payload_len;
+  }
+  return q == e ? off : 0xffffffffu;
+}
+
+__device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p) {
+  return ldb(p) | (ldb(p + 1) << 8) | (ldb(p + 2) << 16) | (ldb(p + 3) << 24);
+}
+
+template <int G>
+struct Group {
+  uint32_t gmask;   // lanes of this group within the warp
+  uint32_t gshift;  // first lane of the group
+  uint32_t lig;     // lane in group
+  __device__ Group() {
+    uint32_t lane = threadIdx.x & 31;
+    gshift = lane & ~(uint32_t)(G - 1);
+    lig = lane & (G - 1);
+    gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << gshift;
+  }
+  __device__ __forceinline__ uint32_t ballot(bool p) const {
+    return (__ballot_sync(gmask, p) & gmask) >> gshift;
+  }
+  __device__ __forceinline__ bool all(bool p) const { return __all_sync(gmask, p); }
+  __device__ __forceinline__ uint32_t bcast(uint32_t v, uint32_t src) const {
+    return __shfl_sync(gmask, v, src, G);
+  }
+};
+
+// key nibble at path index i; the terminator 16 sits at i == 2*klen (Nibbles::from_raw, R11)
+__device__ __forceinline__ uint32_t key_nibble(const uint8_t* key, uint32_t klen, uint32_t i) {
+  if (i >= 2 * klen) return 16;
+  uint32_t b = ldb(key + (i >> 1));
+  return (i & 1) ? (b & 15) : (b >> 4);
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+k_verify_walk(const DeviceBatch b, int wave, const uint8_t* __restrict__ digests,
+              const uint32_t* __restrict__ meta, uint8_t* status_out, uint64_t* value_off_out,
+              uint32_t* value_len_out) {
+  const uint8_t* __restrict__ node_bytes = b.node_bytes - b.byte_base;  // indexed by GLOBAL offsets
+  const uint64_t* __restrict__ node_off = b.node_off;
+  const uint32_t* __restrict__ node_len = b.node_len;
+  const uint32_t* __restrict__ proof_first = b.proof_first;
+  const uint64_t n_proofs = b.n_proofs;
+  const uint8_t* __restrict__ roots = b.roots;
+  const uint8_t* __restrict__ key_bytes = b.key_bytes - b.key_base;
+  const uint32_t* __restrict__ key_off = b.key_off;
+  const int32_t* __restrict__ root_from_proof = b.root_from_proof;
+  const Group<G> g;
+  const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (p >= n_proofs) return;  // uniform per group
+  const bool dependent = root_from_proof != nullptr && root_from_proof[p] >= 0;
+  if (dependent != (wave == 1)) return;
+
+  const uint32_t a = proof_first[p] - b.node_base, n = proof_first[p + 1] - proof_first[p];
+  const uint8_t* key = key_bytes + key_off[p];
+  const uint32_t klen = key_off[p + 1] - key_off[p];
+
+  uint32_t status = kStOk;
+  uint64_t voff = 0;
+  uint32_t vlen = 0;
+
+  // ---- the 32-byte root, as 8 words in every lane
+  uint32_t root[8];
+  {
+    const uint8_t* rp = roots + 32 * p;
+    if (dependent) {
+      // nested workload (storage-circuit/src/main.rs:10-27): root = storage_root of the account
+      // leaf proven by proof d, which wave 0 has already judged
+      const uint64_t d = (uint64_t)root_from_proof[p] - b.proof_base;
+      uint32_t so = 0xffffffffu;
+      if (status_out[d] == kStOk) so = account_storage_root_off(node_bytes + value_off_out[d], value_len_out[d]);
+      if (so == 0xffffffffu) status = kStDepFailed;
+      else rp = node_bytes + value_off_out[d] + so;
+    }
+    if (status == kStOk) {
+      uint32_t w = 0;
+      if (g.lig < 8) w = load_u32_unaligned(rp + 4 * g.lig);
+#pragma unroll
+      for (int i = 0; i < 8; i++) root[i] = g.bcast(w, i);
+    }
+  }
+
+  // ---- lane j caches digest / length of node j (first G nodes of the proof)
+  uint32_t dg[8];
+  uint32_t mylen = 0;
+  if (g.lig < n) {
+    const uint4* dp = reinterpret_cast<const uint4*>(digests + 32ull * (a + g.lig));
+    uint4 x = __ldg(dp), y = __ldg(dp + 1);
+    dg[0] = x.x; dg[1] = x.y; dg[2] = x.z; dg[3] = x.w; dg[4] = y.x; dg[5] = y.y; dg[6] = y.z; dg[7] = y.w;
+    mylen = node_len[a + g.lig];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) dg[i] = 0;
+  }
+
+  // lowest node index whose digest equals h (MemoryDB keyed by hash); `filtered` applies the
+  // DB2 admission rule of verify_proof: hash == root or len >= 32 (R5, R9)
+  auto find = [&](const uint32_t (&h)[8], bool filtered) -> int {
+    bool h_is_root = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) h_is_root &= (h[i] == root[i]);
+    const bool need_len = filtered && !h_is_root;
+    for (uint32_t base = 0; base < n; base += G) {
+      const uint32_t i = base + g.lig;
+      bool m = false;
+      if (i < n) {
+        uint32_t len_i;
+        if (base == 0) {
+          m = true;
+#pragma unroll
+          for (int k = 0; k < 8; k++) m &= (dg[k] == h[k]);
+          len_i = mylen;
+        } else {
+          const uint4* dp = reinterpret_cast<const uint4*>(digests + 32ull * (a + i));
+          uint4 x = __ldg(dp), y = __ldg(dp + 1);
+          m = x.x == h[0] && x.y == h[1] && x.z == h[2] && x.w == h[3] && y.x == h[4] && y.y == h[5] &&
+              y.z == h[6] && y.w == h[7];
+          len_i = node_len[a + i];
+        }
+        if (need_len && len_i < 32) m = false;
+      }
+      const uint32_t bal = g.ballot(m);
+      if (bal) return (int)(base + __ffs(bal) - 1);
+    }
+    return -1;
+  };
+  // 32-byte link at q (unaligned): lanes 0..7 assemble one word each, shuffle-broadcast
+  auto load_link = [&](const uint8_t* q, uint32_t (&h)[8]) {
+    uint32_t w = 0;
+    if (g.lig < 8) w = load_u32_unaligned(q + 4 * g.lig);
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] = g.bcast(w, i);
+  };
+
+  uint32_t cur = 0;
+  if (status == kStOk) {
+    // ---- lib.rs:14  EthTrie::from: root must be present (R2) and decodable (R3)
+    int ri = find(root, false);
+    if (ri < 0) status = kStInvalidStateRoot;
+    else {
+      const uint32_t m = meta[a + ri];
+      if (meta_dec(m) == kDecErr) status = kStInvalidStateRoot;
+      else if (meta_dec(m) == kDecPanic) status = kStPanicOther;
+      else if (meta_kind(m) == kKindHash) {
+        // commit() returns the inner hash; recover_from_db(inner) must find a decodable node or
+        // root_hash() panics; if it does the assert fails because inner != root
+        uint32_t h[8];
+        load_link(node_bytes + node_off[a + ri] + meta_hdr(m), h);
+        int j = find(h, false);
+        status = (j >= 0 && meta_dec(meta[a + j]) == kDecOk) ? kStRootNotCanonical : kStPanicOther;
+      } else if (!meta_canon(m)) status = kStRootNotCanonical;  // lib.rs:19 (R4)
+      cur = (uint32_t)ri;
+    }
+  }
+
+  if (status == kStOk) {
+    // ---- lib.rs:20  verify_proof -> get_at (R11-R16)
+    uint32_t idx = 0;  // path index
+    uint32_t lp = 0;   // offset of the current list node inside node `cur` (0 = the node itself)
+    uint32_t m = meta[a + cur];
+    const uint8_t* nb = node_bytes + node_off[a + cur];
+    uint32_t nl = node_len[a + cur];
+    if (meta_kind(m) == kKindEmpty) status = kStKeyNotFound;
+    bool done = status != kStOk;
+    for (uint32_t guard = 0; !done; guard++) {
+      if (guard > 4096) { status = kStInvalidProof; break; }
+      // the node was fully validated by K2a, so headers below are known to be well formed
+      Hdr lh;
+      rlp_hdr(nb + lp, nl - lp, lh);
+      int cnt;
+      if (lp == 0) cnt = meta_kind(m) == kKindBranch ? 17 : 2;
+      else cnt = scan_items(nb, lp, lh);
+      uint32_t child = 0;  // offset of the child item to follow
+      Hdr ch;
+      bool follow = false;
+      if (cnt == 2) {
+        Hdr ph;
+        const uint32_t it0 = lp + lh.hdr_len;
+        rlp_hdr(nb + it0, nl - it0, ph);
+        const uint8_t* pp = nb + it0 + ph.hdr_len;
+        const uint32_t b0 = ldb(pp);
+        const uint32_t odd = (b0 >> 4) & 1, leaf = (b0 >> 5) & 1;
+        const uint32_t nn = (ph.payload_len - 1) * 2 + odd;
+        const uint32_t rem = 2 * klen - idx;  // key nibbles left (terminator excluded)
+        bool ok = leaf ? (nn == rem) : (nn <= rem);
+        if (ok) {
+          // nibble-parallel compare: lane t checks nibbles t, t+G, ...
+          bool eq = true;
+          for (uint32_t t = g.lig; t < nn; t += G) {
+            const uint32_t qn = t + 2 - odd;  // nibble position in the hex-prefix byte string
+            const uint32_t pb = ldb(pp + (qn >> 1));
+            const uint32_t pnib = (qn & 1) ? (pb & 15) : (pb >> 4);
+            eq &= (pnib == key_nibble(key, klen, idx + t));
+          }
+          ok = g.all(eq);
+        }
+        const uint32_t it1 = it0 + ph.hdr_len + ph.payload_len;
+        if (!ok) { status = kStKeyNotFound; done = true; }
+        else if (leaf) {
+          Hdr vh;
+          rlp_hdr(nb + it1, nl - it1, vh);
+          if (vh.payload_len == 1) { voff = it1; vlen = vh.hdr_len + 1; }  // R20
+          else { voff = it1 + vh.hdr_len; vlen = vh.payload_len; }
+          done = true;
+        } else {
+          idx += nn;
+          child = it1;
+          rlp_hdr(nb + it1, nl - it1, ch);
+          follow = true;
+        }
+      } else {
+        const uint32_t nib = key_nibble(key, klen, idx);
+        uint32_t target = nib == 16 ? 16 : nib;
+        uint32_t q;
+        if (lp == 0 && meta_fast(m)) {
+          const uint32_t mk = meta_mask(m);
+          q = lh.hdr_len + target + 32u * __popc(mk & ((1u << target) - 1u));
+        } else {
+          q = lp + lh.hdr_len;
+          for (uint32_t i = 0; i < target; i++) {
+            Hdr t;
+            rlp_hdr(nb + q, nl - q, t);
+            q += t.hdr_len + t.payload_len;
+          }
+        }
+        rlp_hdr(nb + q, nl - q, ch);
+        if (nib == 16) {
+          // branch value (R14); empty => None
+          uint32_t vo, vl;
+          if (ch.payload_len == 1) { vo = q; vl = ch.hdr_len + 1; }
+          else { vo = q + ch.hdr_len; vl = ch.payload_len; }
+          if (vl == 0) status = kStKeyNotFound;
+          else { voff = vo; vlen = vl; }
+          done = true;
+        } else {
+          idx += 1;
+          child = q;
+          follow = true;
+        }
+      }
+      if (follow) {
+        if (ch.is_list) { lp = child; continue; }                         // inline node (R16)
+        if (ch.payload_len == 0) { status = kStKeyNotFound; break; }      // empty slot (R15)
+        uint32_t h[8];
+        load_link(nb + child + ch.hdr_len, h);
+        for (uint32_t hops = 0;; hops++) {
+          const int j = find(h, true);
+          if (j < 0 || hops > n) { status = kStInvalidProof; done = true; break; }  // R8 / R9
+          const uint32_t mj = meta[a + j];
+          if (meta_dec(mj) == kDecErr) { status = kStInvalidProof; done = true; break; }
+          if (meta_dec(mj) == kDecPanic) { status = kStPanicOther; done = true; break; }
+          if (meta_kind(mj) == kKindEmpty) { status = kStKeyNotFound; done = true; break; }
+          cur = (uint32_t)j; m = mj; lp = 0;
+          nb = node_bytes + node_off[a + cur];
+          nl = node_len[a + cur];
+          if (meta_kind(mj) != kKindHash) break;
+          load_link(nb + meta_hdr(mj), h);  // a node that is itself a bare hash reference
+        }
+      }
+    }
+  }
+
+  if (g.lig == 0) {
+    status_out[p] = (uint8_t)status;
+    const bool okv = status == kStOk;
+    value_off_out[p] = okv ? node_off[a + cur] + voff : 0ull;
+    value_len_out[p] = okv ? vlen : 0u;
+  }
+}
+
+// ------------------------------------------------------------------ host launchers
+cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
+                               const uint32_t* node_len, uint64_t n_nodes, uint32_t* meta, cudaStream_t st) {
+  if (n_nodes == 0) return cudaSuccess;
+  unsigned blocks = (unsigned)((n_nodes + 255) / 256);
+  k_parse_nodes<<<blocks, 256, 0, st>>>(node_bytes, byte_base, node_off, node_len, n_nodes, meta);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_verify_walk(const DeviceBatch& b, const uint8_t* digests, const uint32_t* meta, int wave,
+                               int lanes_per_proof, uint8_t* status, uint64_t* value_off, uint32_t* value_len,
+                               cudaStream_t st) {
+  if (b.n_proofs == 0) return cudaSuccess;
+  const int G = lanes_per_proof;
+  const uint64_t threads = b.n_proofs * (uint64_t)G;
+  const unsigned blocks = (unsigned)((threads + 255) / 256);
+#define MPTV_WALK(GG) \
+  k_verify_walk<GG><<<blocks, 256, 0, st>>>(b, wave, digests, meta, status, value_off, value_len)
+  if (G == 8) MPTV_WALK(8);
+  else if (G == 16) MPTV_WALK(16);
+  else MPTV_WALK(32);
+#undef MPTV_WALK
+  return cudaGetLastError();
+}
+
+}  // namespace mptv
