@@ -131,6 +131,10 @@ int mptv_keccak256_batch_device(mptv_ctx* ctx, int dev_index, const uint8_t* nod
 /* synchronises the device's stream and reports the device times of its last *_device call */
 int mptv_last_timings(mptv_ctx* ctx, int dev_index, mptv_timings* out);
 
+/* Integer issue-rate probe, the denominator of the Keccak roofline: runs a LOP3 (mode 0), SHF (mode 1)
+ * or Keccak-mix 122:58 (mode 2) kernel on every SM and reports 32-bit lane-operations per second. */
+int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops_per_s);
+
 /* options: lanes per proof for the walk kernel (0 = choose from nodes/proof; else 8, 16 or 32),
  * chunk size in bytes of node data for the host-buffer pipeline (0 = default) */
 int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value);

@@ -248,6 +248,8 @@ def load_library():
     L.mptv_keccak256_batch_device.argtypes = [vp, i32, vp, vp, vp, u64, vp, vp]
     L.mptv_last_timings.restype = i32
     L.mptv_last_timings.argtypes = [vp, i32, ctypes.POINTER(Timings)]
+    L.mptv_int_issue_peak.restype = i32
+    L.mptv_int_issue_peak.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double)]
     L.mptv_set_option.restype = i32
     L.mptv_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
     L.mptv_alloc_pinned.restype = vp
@@ -340,6 +342,12 @@ class Verifier:
         t = Timings()
         self._check(self.lib.mptv_last_timings(self.ctx, dev_index, ctypes.byref(t)), "mptv_last_timings")
         return t
+
+    def int_issue_peak(self, dev_index: int = 0, mode: int = 0) -> float:
+        """32-bit lane-operations / s of the alu pipe (0 = LOP3, 1 = SHF, 2 = Keccak mix)."""
+        v = ctypes.c_double()
+        self._check(self.lib.mptv_int_issue_peak(self.ctx, dev_index, mode, ctypes.byref(v)), "mptv_int_issue_peak")
+        return v.value
 
     def keccak256_batch(self, node_bytes: np.ndarray, node_off: np.ndarray, node_len: np.ndarray) -> np.ndarray:
         n = len(node_len)

@@ -90,7 +90,7 @@ __device__ __forceinline__ void keccak_round(uint32_t (&lo)[25], uint32_t (&hi)[
 #undef MPTV_RHOPI
 
 #ifndef MPTV_KECCAK_UNROLL
-#define MPTV_KECCAK_UNROLL 24
+#define MPTV_KECCAK_UNROLL 6
 #endif
 
 constexpr int kKeccakUnroll = MPTV_KECCAK_UNROLL;

@@ -5,8 +5,11 @@
 // one thread per node, state in registers (keccak_f1600.cuh), nodes read from a flat CSR arena.
 // Nodes are binned by their 136-byte rate-block count so that the 32 lanes of a warp run the
 // same number of permutations.  Node bytes are staged HBM -> shared memory one rate block at a
-// time by 1-D bulk async copies (cp.async.bulk, UBLKCP in SASS) into a 2-stage ring guarded by
-// one mbarrier per warp per stage, so the copy of block k+1/k+2 overlaps the permutation of k.
+// time by 16-byte asynchronous copies (cp.async / LDGSTS) into a 2-stage per-thread ring, so the
+// copy of blocks k+1, k+2 overlaps the permutation of block k.  (A first version issued one 1-D
+// bulk copy (cp.async.bulk / UBLKCP) per thread per block: UBLKCP takes uniform-register
+// operands, so the compiler serialised it over the 32 lanes -- ELECT + 5 R2UR + UBLKCP per lane,
+// 7.6 % of all issued instructions in profiles/r01_keccak_v1_ncu.txt -- and it was replaced.)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -79,34 +82,14 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t* __restrict_
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+// 16-byte asynchronous copy global -> shared (LDGSTS), L2-only caching: each lane streams its own
+// node, so the bytes are used exactly once by this SM.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-    "{\n"
-    ".reg .pred p;\n"
-    "WAIT_%=:\n"
-    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-    "@p bra DONE_%=;\n"
-    "bra WAIT_%=;\n"
-    "DONE_%=:\n"
-    "}\n" ::"r"(bar), "r"(parity)
-    : "memory");
-}
-// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA engine)
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
   uint2 v;
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -115,39 +98,35 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 
 // Stage geometry: rate block k of a node covers node bytes [136k, 136k+136).  With the node
 // 16-byte aligned in the arena the 16-byte aligned window that contains it is
-// [136k - 8*(k&1), +144).  One 144-byte slot per thread per stage; slot stride 144 B = 9 x 16 B.
+// [136k - 8*(k&1), +144) = nine 16-byte chunks.  One 144-byte slot per thread per stage; the slot
+// stride of 144 B = 9 x 16 B keeps the per-lane LDS.64 / LDGSTS.128 accesses spread over the banks.
+// A thread only ever touches its own slots, and cp.async completion (wait_group) is tracked per
+// thread, so the ring needs no barrier at all.
 constexpr int kSlotBytes = 144;
 constexpr int kStages = 2;
 
-struct BlockCopy { uint32_t src_off; uint32_t bytes; };
-__device__ __forceinline__ BlockCopy block_copy(uint32_t k, uint32_t len) {
-  uint32_t a = 136u * k - 8u * (k & 1u);
-  uint32_t e = 136u * k + 136u;
-  if (e > len) e = len;
-  e = (e + 15u) & ~15u;
-  BlockCopy c;
-  c.src_off = a;
-  c.bytes = e > a ? e - a : 0u;
-  return c;
+// issue the copies of block k of a node of `len` bytes into the slot at `dst` (one commit group)
+__device__ __forceinline__ void stage_block(uint32_t dst, const uint8_t* src, uint32_t k, uint32_t len, bool on) {
+  if (on) {
+    const uint32_t a = 136u * k - 8u * (k & 1u);
+    uint32_t e = 136u * k + 136u;
+    if (e > len) e = len;
+    const uint8_t* s = src + a;
+#pragma unroll
+    for (int c = 0; c < 9; c++)
+      if (a + 16u * c < e) cp_async16(dst + 16 * c, s + 16 * c);
+  }
+  cp_async_commit();
 }
 
 __global__ void __launch_bounds__(kKeccakThreads, kKeccakMinBlocks)
 k_keccak256_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base, const uint64_t* __restrict__ node_off,
                   const uint32_t* __restrict__ node_len, const uint32_t* __restrict__ order,
                   uint64_t n_nodes, uint8_t* __restrict__ digests) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  // layout: [stage][thread] slots, then mbarriers [warp][stage]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kKeccakThreads * kSlotBytes);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t bar0 = smem_u32(&bars[warp * kStages]);
+  extern __shared__ __align__(128) uint8_t smem[];  // [stage][thread] slots
+  const int tid = threadIdx.x;
   const uint32_t slot0 = smem_u32(smem + tid * kSlotBytes);
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < kStages; s++) mbar_init(bar0 + 8 * s, 32);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
+  constexpr uint32_t kStageStride = kKeccakThreads * kSlotBytes;
 
   const uint64_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -161,80 +140,52 @@ k_keccak256_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base, co
       nb = len / 136u + 1u;
       src = node_bytes + (node_off[node] - byte_base);
     }
-    uint32_t max_nb = nb;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      uint32_t t = __shfl_xor_sync(0xffffffffu, max_nb, o);
-      max_nb = t > max_nb ? t : max_nb;
-    }
     uint32_t lo[25], hi[25];
 #pragma unroll
     for (int i = 0; i < 25; i++) { lo[i] = 0; hi[i] = 0; }
 
-    // prologue: fill the ring
+    // prologue: fill the ring (empty commit groups keep the group count uniform)
 #pragma unroll
-    for (int s = 0; s < kStages; s++) {
-      if ((uint32_t)s < max_nb) {
-        BlockCopy c = block_copy(s, len);
-        if ((uint32_t)s < nb && c.bytes) {
-          mbar_arrive_expect_tx(bar0 + 8 * s, c.bytes);
-          bulk_g2s(slot0 + s * (kKeccakThreads * kSlotBytes), src + c.src_off, c.bytes, bar0 + 8 * s);
-        } else {
-          mbar_arrive(bar0 + 8 * s);
-        }
-      }
-    }
-    for (uint32_t k = 0; k < max_nb; k++) {
+    for (int s = 0; s < kStages; s++) stage_block(slot0 + s * kStageStride, src, s, len, (uint32_t)s < nb);
+
+    for (uint32_t k = 0; k < nb; k++) {
       const uint32_t s = k % kStages;
-      mbar_wait(bar0 + 8 * s, (phase_bits >> s) & 1u);
-      phase_bits ^= 1u << s;
-      const bool active = k < nb;
-      if (active) {
-        const uint32_t p = slot0 + s * (kKeccakThreads * kSlotBytes) + 8u * (k & 1u);
-        const uint32_t valid = len - 136u * k;  // bytes of this block that are message bytes
-        if (valid >= 136u) {
+      cp_async_wait<kStages - 1>();  // block k has landed in this thread's slot
+      const uint32_t p = slot0 + s * kStageStride + 8u * (k & 1u);
+      const uint32_t valid = len - 136u * k;  // message bytes from the start of this block
+      if (valid >= 136u) {
 #pragma unroll
-          for (int j = 0; j < 17; j++) {
-            uint2 w = lds64(p + 8 * j);
-            lo[j] ^= w.x;
-            hi[j] ^= w.y;
-          }
-        } else {
-          // last block: message tail, then pad10*1 with the Keccak delimiter 0x01 (keccak.rs:7 v256).
-          // Branch-free per 32-bit word; stale slot bytes beyond the copied range are masked off.
-#pragma unroll
-          for (int j = 0; j < 17; j++) {
-            uint2 w = lds64(p + 8 * j);
-            uint32_t v[2] = {w.x, w.y};
-#pragma unroll
-            for (int hlf = 0; hlf < 2; hlf++) {
-              const int wi = 2 * j + hlf;
-              const int keep = (int)valid - 4 * wi;  // message bytes in this word
-              const uint32_t msk = keep >= 4 ? 0xffffffffu : (keep <= 0 ? 0u : ((1u << (8 * keep)) - 1u));
-              uint32_t x = v[hlf] & msk;
-              if ((int)(valid >> 2) == wi) x ^= 1u << (8u * (valid & 3u));
-              v[hlf] = x;
-            }
-            lo[j] ^= v[0];
-            hi[j] ^= v[1];
-          }
-          hi[16] ^= 0x80000000u;
+        for (int j = 0; j < 17; j++) {
+          uint2 w = lds64(p + 8 * j);
+          lo[j] ^= w.x;
+          hi[j] ^= w.y;
         }
-      }
-      // the slot has been consumed into registers: refill it with block k + kStages
-      const uint32_t kn = k + kStages;
-      if (kn < max_nb) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        BlockCopy c = block_copy(kn, len);
-        if (kn < nb && c.bytes) {
-          mbar_arrive_expect_tx(bar0 + 8 * s, c.bytes);
-          bulk_g2s(slot0 + s * (kKeccakThreads * kSlotBytes), src + c.src_off, c.bytes, bar0 + 8 * s);
-        } else {
-          mbar_arrive(bar0 + 8 * s);
+      } else {
+        // last block: message tail, then pad10*1 with the Keccak delimiter 0x01 (keccak.rs:7 v256).
+        // Branch-free per 32-bit word; stale slot bytes beyond the copied range are masked off.
+#pragma unroll
+        for (int j = 0; j < 17; j++) {
+          uint2 w = lds64(p + 8 * j);
+          uint32_t v[2] = {w.x, w.y};
+#pragma unroll
+          for (int hlf = 0; hlf < 2; hlf++) {
+            const int wi = 2 * j + hlf;
+            const int keep = (int)valid - 4 * wi;  // message bytes in this word
+            const uint32_t msk = keep >= 4 ? 0xffffffffu : (keep <= 0 ? 0u : ((1u << (8 * keep)) - 1u));
+            uint32_t x = v[hlf] & msk;
+            if ((int)(valid >> 2) == wi) x ^= 1u << (8u * (valid & 3u));
+            v[hlf] = x;
+          }
+          lo[j] ^= v[0];
+          hi[j] ^= v[1];
         }
+        hi[16] ^= 0x80000000u;
       }
-      if (active) keccak_f1600(lo, hi);
+      // the slot now lives in registers: refill it with block k + kStages while we permute
+      stage_block(slot0 + s * kStageStride, src, k + kStages, len, k + kStages < nb);
+      keccak_f1600(lo, hi);
     }
+    cp_async_wait<0>();
     if (have) {
       uint4* out = reinterpret_cast<uint4*>(digests + (uint64_t)node * 32u);
       out[0] = make_uint4(lo[0], hi[0], lo[1], hi[1]);
@@ -244,7 +195,7 @@ k_keccak256_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base, co
 }
 
 // ------------------------------------------------------------------ host launchers
-size_t keccak_smem_bytes() { return (size_t)kStages * kKeccakThreads * kSlotBytes + (kKeccakThreads / 32) * kStages * 8; }
+size_t keccak_smem_bytes() { return (size_t)kStages * kKeccakThreads * kSlotBytes; }
 
 cudaError_t kernels_init_device() {
   return cudaFuncSetAttribute(k_keccak256_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -71,4 +71,7 @@ cudaError_t launch_verify_walk(const DeviceBatch& b, const uint8_t* digests, con
                                int lanes_per_proof, uint8_t* status, uint64_t* value_off, uint32_t* value_len,
                                cudaStream_t st);
 
+// integer issue-rate probe (microbench.cu): mode 0 = LOP3, 1 = SHF, 2 = Keccak mix
+cudaError_t run_int_peak(int mode, int sm_count, uint32_t* scratch, cudaStream_t st, double* ops_per_s);
+
 }  // namespace mptv

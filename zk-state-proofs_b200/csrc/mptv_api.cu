@@ -272,6 +272,16 @@ int mptv_keccak256_batch_device(mptv_ctx* ctx, int dev_index, const uint8_t* nod
   return MPTV_OK;
 }
 
+int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops_per_s) {
+  if (!ctx || !lane_ops_per_s || dev_index < 0 || dev_index >= (int)ctx->dev.size() || mode < 0 || mode > 2)
+    return MPTV_ERR_ARG;
+  Device& d = ctx->dev[dev_index];
+  CK(cudaSetDevice(d.id));
+  CK(d.order.reserve((size_t)d.sm_count * 8 * 256 * 4));
+  CK(run_int_peak(mode, d.sm_count, d.order.as<uint32_t>(), d.stream, lane_ops_per_s));
+  return MPTV_OK;
+}
+
 int mptv_last_timings(mptv_ctx* ctx, int dev_index, mptv_timings* out) {
   if (!ctx || !out || dev_index < 0 || dev_index >= (int)ctx->dev.size()) return MPTV_ERR_ARG;
   Device& d = ctx->dev[dev_index];
