@@ -59,7 +59,7 @@ def test_seeded_corpus_matches_oracle_including_offsets(verifier, oracle):
     assert (voff == ovoff).all()
 
 
-def test_small_chunks_and_no_binning_give_identical_results(verifier, golden):
+def test_small_chunks_no_binning_unfused_give_identical_results(verifier, golden):
     import zk_state_proofs_b200 as z
     vs = golden["vectors"]
     b = z.flatten(_inputs(z, vs))
@@ -69,9 +69,55 @@ def test_small_chunks_and_no_binning_give_identical_results(verifier, golden):
     verifier.set_option("binning", 0)
     c = verifier.verify_batch(b)
     verifier.set_option("binning", 1)
+    verifier.set_option("fused_classify", 0)  # every node decided by k_parse_nodes instead of K1's fast path
+    d = verifier.verify_batch(b)
+    verifier.set_option("fused_classify", 1)
     verifier.set_option("chunk_bytes", 96 << 20)
-    for x, y, w in zip(ref, a, c):
-        assert (x == y).all() and (x == w).all()
+    for x, y, w, v in zip(ref, a, c, d):
+        assert (x == y).all() and (x == w).all() and (x == v).all()
+
+
+def test_synthetic_state_proofs_mixed_match_oracle(verifier, oracle):
+    """config-2/3 shaped batch (inclusion, exclusion, all 7 mutators) at a size the oracle does in seconds."""
+    from workload import gen
+    trie = gen.SynthTrie(300_000, 2, kind=0)
+    b = gen.account_batch(trie, 60_000, seed=5, p_excl=0.10, p_mut=0.20)
+    st, voff, vlen = verifier.verify_batch(b)
+    d = dict(node_bytes=b.node_bytes, node_off=b.node_off, node_len=b.node_len, proof_first=b.proof_first,
+             roots=b.roots, key_bytes=b.key_bytes, key_off=b.key_off)
+    ost, ovoff, ovlen, pa, _ = oracle.verify_batch(d, nthreads=8)
+    assert pa == b.n_perm()
+    assert (st == ost).all() and (voff == ovoff).all() and (vlen == ovlen).all()
+    counts = np.bincount(st, minlength=8)
+    assert counts[0] > 40_000 and counts[1] > 0 and counts[3] > 0 and counts[4] > 0
+    # the returned value of an accepted inclusion proof is the account RLP the generator inserted
+    k, v = trie.entry(0)
+    one = verifier.verify_merkle_proof(trie.root.tobytes(), _proof_of(b, 0), b.key_bytes[:32].tobytes()) if st[0] == 0 else None
+    assert one is None or len(one) >= 70
+
+
+def _proof_of(b, p):
+    return [b.node_bytes[int(b.node_off[i]):int(b.node_off[i]) + int(b.node_len[i])].tobytes()
+            for i in range(int(b.proof_first[p]), int(b.proof_first[p + 1]))]
+
+
+def test_nested_account_storage_groups_match_oracle(verifier, oracle):
+    """config 3: storage proofs take their root from the verified account leaf (root_from_proof)."""
+    from workload import gen
+    state, tokens = gen.make_state_and_tokens(100_000, 4, 50_000, seed=3)
+    b = gen.nested_batch(state, tokens, 15_000, seed=3)
+    st, voff, vlen = verifier.verify_batch(b)
+    d = dict(node_bytes=b.node_bytes, node_off=b.node_off, node_len=b.node_len, proof_first=b.proof_first,
+             roots=b.roots, key_bytes=b.key_bytes, key_off=b.key_off, root_from_proof=b.root_from_proof)
+    ost, ovoff, ovlen, _, _ = oracle.verify_batch(d, nthreads=8)
+    assert (st == ost).all() and (voff == ovoff).all() and (vlen == ovlen).all()
+    counts = np.bincount(st, minlength=8)
+    assert counts[0] > 30_000 and counts[7] > 0 and counts[4] > 0
+    # chunked pipeline must keep groups together
+    verifier.set_option("chunk_bytes", 1 << 20)
+    st2, voff2, vlen2 = verifier.verify_batch(b)
+    verifier.set_option("chunk_bytes", 96 << 20)
+    assert (st2 == st).all() and (voff2 == voff).all() and (vlen2 == vlen).all()
 
 
 def test_single_proof_api_and_panics(verifier, golden):

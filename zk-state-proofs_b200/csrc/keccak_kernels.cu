@@ -119,10 +119,83 @@ __device__ __forceinline__ void stage_block(uint32_t dst, const uint8_t* src, ui
   cp_async_commit();
 }
 
+
+// ---- fused K2a fast path ---------------------------------------------------------------------
+// While block k of a node sits in this thread's shared-memory slot, classify the node without a
+// second pass over HBM.  Only the two shapes that make up real proofs are decided here:
+//   * plain branch: list of 17 items, each child 0x80 or 0xa0 + 32 bytes, value 0x80
+//   * plain leaf:   list of [hex-prefix string with flag 2/3 and canonical pad, string value that is
+//                   not the 2-byte form 0x81 b], nothing trailing
+// Everything else (extensions, inline children, branch values, odd RLP, trailing bytes, lists
+// >= 64 KiB) is marked kMetaSlow and decided by k_parse_nodes, which implements the full rule
+// set.  For the shapes decided here the record equals what k_parse_nodes would produce.
+constexpr uint32_t kClsScan = 0, kClsDone = 1, kClsOff = 2;
+
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// p = shared address of node byte 136*k.  cmeta carries the list header length between calls.
+__device__ __forceinline__ void classify_block(uint32_t p, uint32_t k, uint32_t len, uint32_t& pos, uint32_t& cm,
+                                               uint32_t& cls, uint32_t& cmeta) {
+  const uint32_t blk0 = 136u * k;
+  if (k == 0) {
+    cls = kClsDone;  // pessimistic: cmeta == kMetaSlow unless a shape below matches
+    if (len < 2) return;
+    const uint32_t b0 = lds8(p);
+    uint32_t hl, pay;
+    if (b0 >= 0xc0 && b0 <= 0xf7) { hl = 1; pay = b0 - 0xc0; }
+    else if (b0 == 0xf8) { hl = 2; pay = lds8(p + 1); if (pay < 56) return; }
+    else if (b0 == 0xf9 && len >= 3) { hl = 3; pay = (lds8(p + 1) << 8) | lds8(p + 2); if (pay < 256) return; }
+    else return;
+    if (hl + pay != len || pay == 0) return;
+    const uint32_t b = lds8(p + hl);
+    if (b != 0x80 && b != 0xa0) {
+      // candidate leaf: [path, value]
+      uint32_t phl, ppl;
+      if (b < 0x80) { phl = 0; ppl = 1; }
+      else if (b <= 0xb7) { phl = 1; ppl = b - 0x80; }
+      else return;
+      const uint32_t q = hl + phl + ppl;  // value item
+      if (ppl < 1 || q >= len) return;
+      const uint32_t f = lds8(p + hl + phl);
+      const uint32_t flag = f >> 4;
+      if (!(flag == 3 || (flag == 2 && (f & 15) == 0))) return;  // leaf with canonical pad only
+      if (ppl == 1 && phl == 1) return;                          // 0x81 xx would be non-canonical RLP here
+      const uint32_t v = lds8(p + q);
+      uint32_t vhl, vpl;
+      if (v < 0x80) { vhl = 0; vpl = 1; }
+      else if (v <= 0xb7) { vhl = 1; vpl = v - 0x80; if (vpl == 1) return; }
+      else if (v == 0xb8) { if (q + 1 >= len) return; vhl = 2; vpl = lds8(p + q + 1); if (vpl < 56) return; }
+      else if (v == 0xb9) { if (q + 2 >= len) return; vhl = 3; vpl = (lds8(p + q + 1) << 8) | lds8(p + q + 2); if (vpl < 256) return; }
+      else return;
+      if (q + vhl + vpl != len) return;
+      cmeta = make_meta(kKindLeaf, kDecOk, 1, 0, hl, 0);
+      return;
+    }
+    cls = kClsScan;
+    pos = hl;
+    cmeta = hl;  // remembered for the final record
+  }
+  uint32_t end = blk0 + 136u;
+  if (end > len) end = len;
+  while (pos < end) {
+    const uint32_t b = lds8(p + (pos - blk0));
+    const uint32_t cnt = cm >> 20;
+    if (b == 0xa0) { cm |= 1u << cnt; pos += 33; }
+    else if (b == 0x80) pos += 1;
+    else { cls = kClsDone; cmeta = kMetaSlow; return; }
+    cm += 1u << 20;
+    if (cnt >= 17) { cls = kClsDone; cmeta = kMetaSlow; return; }
+  }
+}
+
 __global__ void __launch_bounds__(kKeccakThreads, kKeccakMinBlocks)
 k_keccak256_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base, const uint64_t* __restrict__ node_off,
                   const uint32_t* __restrict__ node_len, const uint32_t* __restrict__ order,
-                  uint64_t n_nodes, uint8_t* __restrict__ digests) {
+                  uint64_t n_nodes, uint8_t* __restrict__ digests, uint32_t* __restrict__ meta_out) {
   extern __shared__ __align__(128) uint8_t smem[];  // [stage][thread] slots
   const int tid = threadIdx.x;
   const uint32_t slot0 = smem_u32(smem + tid * kSlotBytes);
@@ -143,6 +216,8 @@ k_keccak256_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base, co
     uint32_t lo[25], hi[25];
 #pragma unroll
     for (int i = 0; i < 25; i++) { lo[i] = 0; hi[i] = 0; }
+    // fused K2a fast path (see classify_* below): scan position, item count << 20 | occupancy map
+    uint32_t cpos = 0, ccm = 0, ccls = meta_out ? kClsScan : kClsOff, cmeta = kMetaSlow;
 
     // prologue: fill the ring (empty commit groups keep the group count uniform)
 #pragma unroll
@@ -153,6 +228,7 @@ k_keccak256_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base, co
       cp_async_wait<kStages - 1>();  // block k has landed in this thread's slot
       const uint32_t p = slot0 + s * kStageStride + 8u * (k & 1u);
       const uint32_t valid = len - 136u * k;  // message bytes from the start of this block
+      if (ccls == kClsScan) classify_block(p, k, len, cpos, ccm, ccls, cmeta);
       if (valid >= 136u) {
 #pragma unroll
         for (int j = 0; j < 17; j++) {
@@ -186,6 +262,16 @@ k_keccak256_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base, co
       keccak_f1600(lo, hi);
     }
     cp_async_wait<0>();
+    if (have && meta_out) {
+      if (ccls == kClsScan) {
+        // every block scanned without leaving the {0x80, 0xa0+32} alphabet: a plain branch iff it
+        // has exactly 17 items, ends exactly at the node's end and its value item is empty
+        const uint32_t cnt = ccm >> 20, mask = ccm & 0x1ffffu;
+        if (cnt == 17 && cpos == len && !(mask >> 16)) cmeta = make_meta(kKindBranch, kDecOk, 1, 1, cmeta, mask);
+        else cmeta = kMetaSlow;
+      }
+      meta_out[node] = cmeta;
+    }
     if (have) {
       uint4* out = reinterpret_cast<uint4*>(digests + (uint64_t)node * 32u);
       out[0] = make_uint4(lo[0], hi[0], lo[1], hi[1]);
@@ -218,14 +304,14 @@ cudaError_t launch_bin_nodes(const uint32_t* node_len, uint64_t n_nodes, uint32_
 
 cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
                                    const uint32_t* node_len, const uint32_t* order, uint64_t n_nodes,
-                                   uint8_t* digests, int sm_count, cudaStream_t st) {
+                                   uint8_t* digests, uint32_t* meta, int sm_count, cudaStream_t st) {
   if (n_nodes == 0) return cudaSuccess;
   size_t smem = keccak_smem_bytes();
   uint64_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
   uint64_t grid = (uint64_t)sm_count * kKeccakMinBlocks;  // persistent: one wave of resident CTAs
   if (grid > n_tiles) grid = n_tiles;
   k_keccak256_nodes<<<(unsigned)grid, kKeccakThreads, smem, st>>>(node_bytes, byte_base, node_off, node_len, order,
-                                                                n_nodes, digests);
+                                                                n_nodes, digests, meta);
   return cudaGetLastError();
 }
 

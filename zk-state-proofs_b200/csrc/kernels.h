@@ -25,6 +25,7 @@ __host__ __device__ __forceinline__ uint32_t make_meta(uint32_t kind, uint32_t d
                                                        uint32_t hdr_len, uint32_t mask) {
   return kind | (dec << 3) | (canon << 5) | (fast << 6) | (hdr_len << 7) | (mask << 10);
 }
+constexpr uint32_t kMetaSlow = 0xffffffffu;  // K1 could not classify the node: k_parse_nodes decides
 __host__ __device__ __forceinline__ uint32_t meta_kind(uint32_t m) { return m & 7u; }
 __host__ __device__ __forceinline__ uint32_t meta_dec(uint32_t m) { return (m >> 3) & 3u; }
 __host__ __device__ __forceinline__ uint32_t meta_canon(uint32_t m) { return (m >> 5) & 1u; }
@@ -58,14 +59,16 @@ cudaError_t kernels_init_device();
 // K0: order[] = node indices sorted by DESCENDING rate-block bin.  scratch = 2*kNumBins u32.
 cudaError_t launch_bin_nodes(const uint32_t* node_len, uint64_t n_nodes, uint32_t* scratch, uint32_t* order,
                              cudaStream_t st);
-// K1: digests[32*i] = keccak256(node i).  order may be NULL (identity).
+// K1: digests[32*i] = keccak256(node i).  order may be NULL (identity).  meta may be NULL; when
+// given, meta[i] receives the K2a record of plain branches / plain leaves and kMetaSlow otherwise.
 cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
                                    const uint32_t* node_len, const uint32_t* order, uint64_t n_nodes,
-                                   uint8_t* digests, int sm_count, cudaStream_t st);
+                                   uint8_t* digests, uint32_t* meta, int sm_count, cudaStream_t st);
 
-// K2a: meta[i] = eager-decode record of node i
+// K2a: meta[i] = eager-decode record of node i.  only_slow: leave records != kMetaSlow untouched
 cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
-                               const uint32_t* node_len, uint64_t n_nodes, uint32_t* meta, cudaStream_t st);
+                               const uint32_t* node_len, uint64_t n_nodes, uint32_t* meta, bool only_slow,
+                               cudaStream_t st);
 // K2b: wave 0 = proofs with their own root, wave 1 = proofs whose root is another proof's storage_root
 cudaError_t launch_verify_walk(const DeviceBatch& b, const uint8_t* digests, const uint32_t* meta, int wave,
                                int lanes_per_proof, uint8_t* status, uint64_t* value_off, uint32_t* value_len,

@@ -73,6 +73,7 @@ struct mptv_ctx {
   int lanes_per_proof = 0;          // 0 = auto
   uint64_t chunk_bytes = 96ull << 20;  // node bytes per pipeline chunk of the host-buffer path
   int binning = 1;
+  int fused_classify = 1;  // K1 also classifies plain branches / leaves (K2a fast path)
 };
 
 namespace {
@@ -112,9 +113,10 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
   }
   if (timed) CK(cudaEventRecord(d.ev[1], st));
   CK(launch_keccak256_nodes(b.node_bytes, b.byte_base, b.node_off, b.node_len, ord, b.n_nodes,
-                            digests.as<uint8_t>(), d.sm_count, st));
+                            digests.as<uint8_t>(), ctx->fused_classify ? meta.as<uint32_t>() : nullptr, d.sm_count, st));
   if (timed) CK(cudaEventRecord(d.ev[2], st));
-  CK(launch_parse_nodes(b.node_bytes, b.byte_base, b.node_off, b.node_len, b.n_nodes, meta.as<uint32_t>(), st));
+  CK(launch_parse_nodes(b.node_bytes, b.byte_base, b.node_off, b.node_len, b.n_nodes, meta.as<uint32_t>(),
+                        ctx->fused_classify != 0, st));
   if (timed) CK(cudaEventRecord(d.ev[3], st));
   const int G = pick_lanes(ctx, b.n_nodes, b.n_proofs);
   CK(launch_verify_walk(b, digests.as<uint8_t>(), meta.as<uint32_t>(), 0, G, status, value_off, value_len, st));
@@ -220,6 +222,8 @@ int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
     ctx->chunk_bytes = (uint64_t)value;
   } else if (!strcmp(name, "binning")) {
     ctx->binning = value ? 1 : 0;
+  } else if (!strcmp(name, "fused_classify")) {
+    ctx->fused_classify = value ? 1 : 0;
   } else return MPTV_ERR_ARG;
   return MPTV_OK;
 }
@@ -263,7 +267,7 @@ int mptv_keccak256_batch_device(mptv_ctx* ctx, int dev_index, const uint8_t* nod
     ord = d.order.as<uint32_t>();
   }
   CK(cudaEventRecord(d.ev[1], st));
-  CK(launch_keccak256_nodes(node_bytes, 0, node_off, node_len, ord, n_nodes, digests32, d.sm_count, st));
+  CK(launch_keccak256_nodes(node_bytes, 0, node_off, node_len, ord, n_nodes, digests32, nullptr, d.sm_count, st));
   CK(cudaEventRecord(d.ev[2], st));
   CK(cudaEventRecord(d.ev[3], st));
   CK(cudaEventRecord(d.ev[4], st));
@@ -484,7 +488,7 @@ int mptv_keccak256_batch(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node
     ord = s.order.as<uint32_t>();
   }
   CK(launch_keccak256_nodes(s.node_bytes.as<uint8_t>(), 0, s.node_off.as<uint64_t>(), s.node_len.as<uint32_t>(), ord,
-                            n_nodes, s.digests.as<uint8_t>(), d.sm_count, st));
+                            n_nodes, s.digests.as<uint8_t>(), nullptr, d.sm_count, st));
   CK(cudaMemcpyAsync(digests32, s.digests.p, 32 * n_nodes, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return MPTV_OK;

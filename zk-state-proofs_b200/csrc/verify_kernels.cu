@@ -132,7 +132,11 @@ __device__ uint32_t parse_node(const uint8_t* p, uint32_t n) {
       }
     } else {
       if (i < 16) is_child = true;
-      else if (!value_item_canonical(t)) canon = 0;
+      else {
+        if (!value_item_canonical(t)) canon = 0;
+        // "fast" (plain branch) promises the walk an EMPTY value item, i.e. exactly 0x80
+        if (sp == 0 && (t.is_list || t.payload_len != 0)) fast = 0;
+      }
     }
     if (is_child) {
       if (t.is_list) {
@@ -158,9 +162,10 @@ __device__ uint32_t parse_node(const uint8_t* p, uint32_t n) {
 __global__ void __launch_bounds__(256) k_parse_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base,
                                                      const uint64_t* __restrict__ node_off,
                                                      const uint32_t* __restrict__ node_len, uint64_t n_nodes,
-                                                     uint32_t* __restrict__ meta) {
+                                                     uint32_t* __restrict__ meta, bool only_slow) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_nodes) return;
+  if (only_slow && meta[i] != kMetaSlow) return;  // already decided by the fused fast path in K1
   meta[i] = parse_node(node_bytes + (node_off[i] - byte_base), node_len[i]);
 }
 
@@ -217,7 +222,7 @@ __device__ __forceinline__ uint32_t key_nibble(const uint8_t* key, uint32_t klen
 }
 
 template <int G>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_verify_walk(const DeviceBatch b, int wave, const uint8_t* __restrict__ digests,
               const uint32_t* __restrict__ meta, uint8_t* status_out, uint64_t* value_off_out,
               uint32_t* value_len_out) {
@@ -225,114 +230,115 @@ k_verify_walk(const DeviceBatch b, int wave, const uint8_t* __restrict__ digests
   const uint64_t* __restrict__ node_off = b.node_off;
   const uint32_t* __restrict__ node_len = b.node_len;
   const uint32_t* __restrict__ proof_first = b.proof_first;
-  const uint64_t n_proofs = b.n_proofs;
-  const uint8_t* __restrict__ roots = b.roots;
-  const uint8_t* __restrict__ key_bytes = b.key_bytes - b.key_base;
-  const uint32_t* __restrict__ key_off = b.key_off;
   const int32_t* __restrict__ root_from_proof = b.root_from_proof;
   const Group<G> g;
   const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  if (p >= n_proofs) return;  // uniform per group
+  if (p >= b.n_proofs) return;  // uniform per group
   const bool dependent = root_from_proof != nullptr && root_from_proof[p] >= 0;
   if (dependent != (wave == 1)) return;
 
   const uint32_t a = proof_first[p] - b.node_base, n = proof_first[p + 1] - proof_first[p];
-  const uint8_t* key = key_bytes + key_off[p];
-  const uint32_t klen = key_off[p + 1] - key_off[p];
+  const uint8_t* key = b.key_bytes + (b.key_off[p] - b.key_base);
+  const uint32_t klen = b.key_off[p + 1] - b.key_off[p];
 
   uint32_t status = kStOk;
   uint64_t voff = 0;
   uint32_t vlen = 0;
 
-  // ---- the 32-byte root, as 8 words in every lane
-  uint32_t root[8];
-  {
-    const uint8_t* rp = roots + 32 * p;
-    if (dependent) {
-      // nested workload (storage-circuit/src/main.rs:10-27): root = storage_root of the account
-      // leaf proven by proof d, which wave 0 has already judged
-      const uint64_t d = (uint64_t)root_from_proof[p] - b.proof_base;
-      uint32_t so = 0xffffffffu;
-      if (status_out[d] == kStOk) so = account_storage_root_off(node_bytes + value_off_out[d], value_len_out[d]);
-      if (so == 0xffffffffu) status = kStDepFailed;
-      else rp = node_bytes + value_off_out[d] + so;
-    }
-    if (status == kStOk) {
-      uint32_t w = 0;
-      if (g.lig < 8) w = load_u32_unaligned(rp + 4 * g.lig);
-#pragma unroll
-      for (int i = 0; i < 8; i++) root[i] = g.bcast(w, i);
-    }
+  // ---- where the 32-byte root lives
+  const uint8_t* rp = b.roots + 32 * p;
+  if (dependent) {
+    // nested workload (storage-circuit/src/main.rs:10-27): root = storage_root of the account
+    // leaf proven by proof d, which wave 0 has already judged
+    const uint64_t d = (uint64_t)root_from_proof[p] - b.proof_base;
+    uint32_t so = 0xffffffffu;
+    if (status_out[d] == kStOk) so = account_storage_root_off(node_bytes + value_off_out[d], value_len_out[d]);
+    if (so == 0xffffffffu) status = kStDepFailed;
+    else rp = node_bytes + value_off_out[d] + so;
   }
 
-  // ---- lane j caches digest / length of node j (first G nodes of the proof)
+  // ---- lane j owns node j of the proof (first G nodes): digest, length, offset, K2a record
   uint32_t dg[8];
-  uint32_t mylen = 0;
+  uint32_t mylen = 0, mymeta = 0;
+  uint64_t myoff = 0;
+  bool my_is_root = false;  // digest == root: admitted to DB2 whatever its length (R5)
   if (g.lig < n) {
     const uint4* dp = reinterpret_cast<const uint4*>(digests + 32ull * (a + g.lig));
     uint4 x = __ldg(dp), y = __ldg(dp + 1);
     dg[0] = x.x; dg[1] = x.y; dg[2] = x.z; dg[3] = x.w; dg[4] = y.x; dg[5] = y.y; dg[6] = y.z; dg[7] = y.w;
     mylen = node_len[a + g.lig];
+    mymeta = meta[a + g.lig];
+    myoff = node_off[a + g.lig];
   } else {
 #pragma unroll
     for (int i = 0; i < 8; i++) dg[i] = 0;
   }
-
-  // lowest node index whose digest equals h (MemoryDB keyed by hash); `filtered` applies the
-  // DB2 admission rule of verify_proof: hash == root or len >= 32 (R5, R9)
-  auto find = [&](const uint32_t (&h)[8], bool filtered) -> int {
-    bool h_is_root = true;
-#pragma unroll
-    for (int i = 0; i < 8; i++) h_is_root &= (h[i] == root[i]);
-    const bool need_len = filtered && !h_is_root;
-    for (uint32_t base = 0; base < n; base += G) {
-      const uint32_t i = base + g.lig;
-      bool m = false;
-      if (i < n) {
-        uint32_t len_i;
-        if (base == 0) {
-          m = true;
-#pragma unroll
-          for (int k = 0; k < 8; k++) m &= (dg[k] == h[k]);
-          len_i = mylen;
-        } else {
-          const uint4* dp = reinterpret_cast<const uint4*>(digests + 32ull * (a + i));
-          uint4 x = __ldg(dp), y = __ldg(dp + 1);
-          m = x.x == h[0] && x.y == h[1] && x.z == h[2] && x.w == h[3] && y.x == h[4] && y.y == h[5] &&
-              y.z == h[6] && y.w == h[7];
-          len_i = node_len[a + i];
-        }
-        if (need_len && len_i < 32) m = false;
-      }
-      const uint32_t bal = g.ballot(m);
-      if (bal) return (int)(base + __ffs(bal) - 1);
-    }
-    return -1;
+  auto meta_of = [&](uint32_t j) -> uint32_t { return j < (uint32_t)G ? g.bcast(mymeta, j) : meta[a + j]; };
+  auto len_of = [&](uint32_t j) -> uint32_t { return j < (uint32_t)G ? g.bcast(mylen, j) : node_len[a + j]; };
+  auto off_of = [&](uint32_t j) -> uint64_t {
+    if (j < (uint32_t)G)
+      return ((uint64_t)g.bcast((uint32_t)(myoff >> 32), j) << 32) | g.bcast((uint32_t)myoff, j);
+    return node_off[a + j];
   };
-  // 32-byte link at q (unaligned): lanes 0..7 assemble one word each, shuffle-broadcast
+  // 32 bytes at q (unaligned): lanes 0..7 assemble one word each, shuffle-broadcast to the group
   auto load_link = [&](const uint8_t* q, uint32_t (&h)[8]) {
     uint32_t w = 0;
     if (g.lig < 8) w = load_u32_unaligned(q + 4 * g.lig);
 #pragma unroll
     for (int i = 0; i < 8; i++) h[i] = g.bcast(w, i);
   };
+  // lowest node index whose digest equals h (MemoryDB keyed by hash).  `filtered` applies the DB2
+  // admission rule of verify_proof: digest == root or len >= 32 (R5, R9).
+  auto find = [&](const uint32_t (&h)[8], bool filtered) -> int {
+    bool m = g.lig < n;
+#pragma unroll
+    for (int k = 0; k < 8; k++) m &= (dg[k] == h[k]);
+    if (filtered && mylen < 32 && !my_is_root) m = false;
+    uint32_t bal = g.ballot(m);
+    if (bal) return (int)(__ffs(bal) - 1);
+    for (uint32_t base = G; base < n; base += G) {  // proofs with more than G nodes (rare)
+      const uint32_t i = base + g.lig;
+      m = false;
+      if (i < n) {
+        const uint4* dp = reinterpret_cast<const uint4*>(digests + 32ull * (a + i));
+        uint4 x = __ldg(dp), y = __ldg(dp + 1);
+        m = x.x == h[0] && x.y == h[1] && x.z == h[2] && x.w == h[3] && y.x == h[4] && y.y == h[5] &&
+            y.z == h[6] && y.w == h[7];
+        if (m && filtered && node_len[a + i] < 32) {
+          bool is_root = true;
+          for (int k = 0; k < 8; k++) is_root &= (load_u32_unaligned(rp + 4 * k) == h[k]);
+          m = is_root;
+        }
+      }
+      bal = g.ballot(m);
+      if (bal) return (int)(base + __ffs(bal) - 1);
+    }
+    return -1;
+  };
 
   uint32_t cur = 0;
   if (status == kStOk) {
     // ---- lib.rs:14  EthTrie::from: root must be present (R2) and decodable (R3)
-    int ri = find(root, false);
+    uint32_t h[8];
+    load_link(rp, h);
+    {
+      bool e = g.lig < n;
+#pragma unroll
+      for (int k = 0; k < 8; k++) e &= (dg[k] == h[k]);
+      my_is_root = e;
+    }
+    int ri = find(h, false);
     if (ri < 0) status = kStInvalidStateRoot;
     else {
-      const uint32_t m = meta[a + ri];
+      const uint32_t m = meta_of((uint32_t)ri);
       if (meta_dec(m) == kDecErr) status = kStInvalidStateRoot;
       else if (meta_dec(m) == kDecPanic) status = kStPanicOther;
       else if (meta_kind(m) == kKindHash) {
         // commit() returns the inner hash; recover_from_db(inner) must find a decodable node or
         // root_hash() panics; if it does the assert fails because inner != root
-        uint32_t h[8];
-        load_link(node_bytes + node_off[a + ri] + meta_hdr(m), h);
+        load_link(node_bytes + off_of((uint32_t)ri) + meta_hdr(m), h);
         int j = find(h, false);
-        status = (j >= 0 && meta_dec(meta[a + j]) == kDecOk) ? kStRootNotCanonical : kStPanicOther;
+        status = (j >= 0 && meta_dec(meta_of((uint32_t)j)) == kDecOk) ? kStRootNotCanonical : kStPanicOther;
       } else if (!meta_canon(m)) status = kStRootNotCanonical;  // lib.rs:19 (R4)
       cur = (uint32_t)ri;
     }
@@ -342,123 +348,122 @@ k_verify_walk(const DeviceBatch b, int wave, const uint8_t* __restrict__ digests
     // ---- lib.rs:20  verify_proof -> get_at (R11-R16)
     uint32_t idx = 0;  // path index
     uint32_t lp = 0;   // offset of the current list node inside node `cur` (0 = the node itself)
-    uint32_t m = meta[a + cur];
-    const uint8_t* nb = node_bytes + node_off[a + cur];
-    uint32_t nl = node_len[a + cur];
+    uint32_t m = meta_of(cur);
     if (meta_kind(m) == kKindEmpty) status = kStKeyNotFound;
     bool done = status != kStOk;
     for (uint32_t guard = 0; !done; guard++) {
       if (guard > 4096) { status = kStInvalidProof; break; }
-      // the node was fully validated by K2a, so headers below are known to be well formed
-      Hdr lh;
-      rlp_hdr(nb + lp, nl - lp, lh);
-      int cnt;
-      if (lp == 0) cnt = meta_kind(m) == kKindBranch ? 17 : 2;
-      else cnt = scan_items(nb, lp, lh);
-      uint32_t child = 0;  // offset of the child item to follow
-      Hdr ch;
-      bool follow = false;
-      if (cnt == 2) {
-        Hdr ph;
-        const uint32_t it0 = lp + lh.hdr_len;
-        rlp_hdr(nb + it0, nl - it0, ph);
-        const uint8_t* pp = nb + it0 + ph.hdr_len;
-        const uint32_t b0 = ldb(pp);
-        const uint32_t odd = (b0 >> 4) & 1, leaf = (b0 >> 5) & 1;
-        const uint32_t nn = (ph.payload_len - 1) * 2 + odd;
-        const uint32_t rem = 2 * klen - idx;  // key nibbles left (terminator excluded)
-        bool ok = leaf ? (nn == rem) : (nn <= rem);
-        if (ok) {
-          // nibble-parallel compare: lane t checks nibbles t, t+G, ...
-          bool eq = true;
-          for (uint32_t t = g.lig; t < nn; t += G) {
-            const uint32_t qn = t + 2 - odd;  // nibble position in the hex-prefix byte string
-            const uint32_t pb = ldb(pp + (qn >> 1));
-            const uint32_t pnib = (qn & 1) ? (pb & 15) : (pb >> 4);
-            eq &= (pnib == key_nibble(key, klen, idx + t));
+      const uint8_t* link = nullptr;  // where the 32-byte child reference to follow lives
+      if (lp == 0 && meta_fast(m)) {
+        // plain branch: 16 children that are each 0x80 or a 32-byte hash, empty value.  Child
+        // selection is a popcount over the occupancy map K2a recorded -- no node bytes are read
+        // except the link itself.
+        const uint32_t nib = key_nibble(key, klen, idx);
+        const uint32_t mk = meta_mask(m);
+        if (nib == 16 || !((mk >> nib) & 1u)) { status = kStKeyNotFound; break; }  // R14 (empty value) / R15
+        idx += 1;
+        link = node_bytes + off_of(cur) + meta_hdr(m) + nib + 32u * __popc(mk & ((1u << nib) - 1u)) + 1;
+      } else {
+        // general node (leaf, extension, branch with inline children or a value, inline node).
+        // K2a validated the whole node, so the headers below are known to be well formed.
+        const uint8_t* nb = node_bytes + off_of(cur);
+        const uint32_t nl = len_of(cur);
+        Hdr lh;
+        rlp_hdr(nb + lp, nl - lp, lh);
+        int cnt;
+        if (lp == 0) cnt = meta_kind(m) == kKindBranch ? 17 : 2;
+        else cnt = scan_items(nb, lp, lh);
+        uint32_t child = 0;
+        Hdr ch;
+        if (cnt == 2) {
+          Hdr ph;
+          const uint32_t it0 = lp + lh.hdr_len;
+          rlp_hdr(nb + it0, nl - it0, ph);
+          const uint8_t* pp = nb + it0 + ph.hdr_len;
+          const uint32_t b0 = ldb(pp);
+          const uint32_t odd = (b0 >> 4) & 1, leaf = (b0 >> 5) & 1;
+          const uint32_t nn = (ph.payload_len - 1) * 2 + odd;
+          const uint32_t rem = 2 * klen - idx;  // key nibbles left (terminator excluded)
+          bool ok = leaf ? (nn == rem) : (nn <= rem);
+          if (ok) {
+            // nibble-parallel compare: lane t checks nibbles t, t+G, ...
+            bool eq = true;
+            for (uint32_t t = g.lig; t < nn; t += G) {
+              const uint32_t qn = t + 2 - odd;  // nibble position in the hex-prefix byte string
+              const uint32_t pb = ldb(pp + (qn >> 1));
+              const uint32_t pnib = (qn & 1) ? (pb & 15) : (pb >> 4);
+              eq &= (pnib == key_nibble(key, klen, idx + t));
+            }
+            ok = g.all(eq);
           }
-          ok = g.all(eq);
-        }
-        const uint32_t it1 = it0 + ph.hdr_len + ph.payload_len;
-        if (!ok) { status = kStKeyNotFound; done = true; }
-        else if (leaf) {
-          Hdr vh;
-          rlp_hdr(nb + it1, nl - it1, vh);
-          if (vh.payload_len == 1) { voff = it1; vlen = vh.hdr_len + 1; }  // R20
-          else { voff = it1 + vh.hdr_len; vlen = vh.payload_len; }
-          done = true;
-        } else {
+          const uint32_t it1 = it0 + ph.hdr_len + ph.payload_len;
+          if (!ok) { status = kStKeyNotFound; break; }
+          rlp_hdr(nb + it1, nl - it1, ch);
+          if (leaf) {
+            if (ch.payload_len == 1) { voff = it1; vlen = ch.hdr_len + 1; }  // R20
+            else { voff = it1 + ch.hdr_len; vlen = ch.payload_len; }
+            break;
+          }
           idx += nn;
           child = it1;
-          rlp_hdr(nb + it1, nl - it1, ch);
-          follow = true;
-        }
-      } else {
-        const uint32_t nib = key_nibble(key, klen, idx);
-        uint32_t target = nib == 16 ? 16 : nib;
-        uint32_t q;
-        if (lp == 0 && meta_fast(m)) {
-          const uint32_t mk = meta_mask(m);
-          q = lh.hdr_len + target + 32u * __popc(mk & ((1u << target) - 1u));
         } else {
-          q = lp + lh.hdr_len;
-          for (uint32_t i = 0; i < target; i++) {
+          const uint32_t nib = key_nibble(key, klen, idx);
+          uint32_t q = lp + lh.hdr_len;
+          for (uint32_t i = 0; i < nib; i++) {  // nib == 16 walks to the value item
             Hdr t;
             rlp_hdr(nb + q, nl - q, t);
             q += t.hdr_len + t.payload_len;
           }
-        }
-        rlp_hdr(nb + q, nl - q, ch);
-        if (nib == 16) {
-          // branch value (R14); empty => None
-          uint32_t vo, vl;
-          if (ch.payload_len == 1) { vo = q; vl = ch.hdr_len + 1; }
-          else { vo = q + ch.hdr_len; vl = ch.payload_len; }
-          if (vl == 0) status = kStKeyNotFound;
-          else { voff = vo; vlen = vl; }
-          done = true;
-        } else {
+          rlp_hdr(nb + q, nl - q, ch);
+          if (nib == 16) {
+            // branch value (R14); empty => None
+            uint32_t vo, vl;
+            if (ch.payload_len == 1) { vo = q; vl = ch.hdr_len + 1; }
+            else { vo = q + ch.hdr_len; vl = ch.payload_len; }
+            if (vl == 0) status = kStKeyNotFound;
+            else { voff = vo; vlen = vl; }
+            break;
+          }
           idx += 1;
           child = q;
-          follow = true;
         }
-      }
-      if (follow) {
         if (ch.is_list) { lp = child; continue; }                         // inline node (R16)
         if (ch.payload_len == 0) { status = kStKeyNotFound; break; }      // empty slot (R15)
-        uint32_t h[8];
-        load_link(nb + child + ch.hdr_len, h);
-        for (uint32_t hops = 0;; hops++) {
-          const int j = find(h, true);
-          if (j < 0 || hops > n) { status = kStInvalidProof; done = true; break; }  // R8 / R9
-          const uint32_t mj = meta[a + j];
-          if (meta_dec(mj) == kDecErr) { status = kStInvalidProof; done = true; break; }
-          if (meta_dec(mj) == kDecPanic) { status = kStPanicOther; done = true; break; }
-          if (meta_kind(mj) == kKindEmpty) { status = kStKeyNotFound; done = true; break; }
-          cur = (uint32_t)j; m = mj; lp = 0;
-          nb = node_bytes + node_off[a + cur];
-          nl = node_len[a + cur];
-          if (meta_kind(mj) != kKindHash) break;
-          load_link(nb + meta_hdr(mj), h);  // a node that is itself a bare hash reference
-        }
+        link = nb + child + ch.hdr_len;
+      }
+      // ---- follow a hash reference: shuffle-broadcast the link, compare against every digest
+      uint32_t h[8];
+      load_link(link, h);
+      for (uint32_t hops = 0;; hops++) {
+        const int j = find(h, true);
+        if (j < 0 || hops > n) { status = kStInvalidProof; done = true; break; }  // R8 / R9
+        const uint32_t mj = meta_of((uint32_t)j);
+        if (meta_dec(mj) == kDecErr) { status = kStInvalidProof; done = true; break; }
+        if (meta_dec(mj) == kDecPanic) { status = kStPanicOther; done = true; break; }
+        if (meta_kind(mj) == kKindEmpty) { status = kStKeyNotFound; done = true; break; }
+        cur = (uint32_t)j; m = mj; lp = 0;
+        if (meta_kind(mj) != kKindHash) break;
+        load_link(node_bytes + off_of(cur) + meta_hdr(mj), h);  // a node that is itself a bare hash reference
       }
     }
   }
 
+  const uint64_t base_off = off_of(cur);
   if (g.lig == 0) {
     status_out[p] = (uint8_t)status;
     const bool okv = status == kStOk;
-    value_off_out[p] = okv ? node_off[a + cur] + voff : 0ull;
+    value_off_out[p] = okv ? base_off + voff : 0ull;
     value_len_out[p] = okv ? vlen : 0u;
   }
 }
 
 // ------------------------------------------------------------------ host launchers
 cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
-                               const uint32_t* node_len, uint64_t n_nodes, uint32_t* meta, cudaStream_t st) {
+                               const uint32_t* node_len, uint64_t n_nodes, uint32_t* meta, bool only_slow,
+                               cudaStream_t st) {
   if (n_nodes == 0) return cudaSuccess;
   unsigned blocks = (unsigned)((n_nodes + 255) / 256);
-  k_parse_nodes<<<blocks, 256, 0, st>>>(node_bytes, byte_base, node_off, node_len, n_nodes, meta);
+  k_parse_nodes<<<blocks, 256, 0, st>>>(node_bytes, byte_base, node_off, node_len, n_nodes, meta, only_slow);
   return cudaGetLastError();
 }
 
