@@ -11,6 +11,9 @@
 
 namespace mptv {
 
+// MODE 0: LOP3   1: SHF   2: Keccak mix (11 LOP3 : 5 SHF)
+//      3: IMAD (low 32)   4: IMAD.HI   5: IMAD.WIDE   6: LOP3 + IMAD 1:1   7: LOP3 + IMAD.HI 1:1
+//      8: LOP3 + IMAD.WIDE 2:1
 template <int MODE>
 __global__ void __launch_bounds__(256) k_int_peak(uint32_t* out, int iters) {
   uint32_t a[16];
@@ -19,12 +22,25 @@ __global__ void __launch_bounds__(256) k_int_peak(uint32_t* out, int iters) {
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-      const bool shf = MODE == 1 || (MODE == 2 && (j % 3) == 2);  // mode 2: 5 SHF : 11 LOP3 ~ 58:122
-      if (shf) {
-        asm volatile("shf.l.wrap.b32 %0, %1, %2, 7;" : "=r"(a[j]) : "r"(a[(j + 1) & 15]), "r"(a[(j + 5) & 15]));
+      const uint32_t x = a[j], y = a[(j + 1) & 15], z = a[(j + 5) & 15];
+      uint32_t r;
+      bool fma_op = false;
+      if (MODE == 6 || MODE == 7) fma_op = (j & 1);
+      if (MODE == 8) fma_op = (j % 3) == 2;
+      if (MODE == 1 || (MODE == 2 && (j % 3) == 2)) {
+        asm volatile("shf.l.wrap.b32 %0, %1, %2, 7;" : "=r"(r) : "r"(y), "r"(z));
+      } else if (MODE == 3 || (MODE == 6 && fma_op)) {
+        asm volatile("mad.lo.u32 %0, %1, 128, %2;" : "=r"(r) : "r"(y), "r"(z));
+      } else if (MODE == 4 || (MODE == 7 && fma_op)) {
+        asm volatile("mad.hi.u32 %0, %1, 128, %2;" : "=r"(r) : "r"(y), "r"(z));
+      } else if (MODE == 5 || (MODE == 8 && fma_op)) {
+        uint64_t w;
+        asm volatile("mad.wide.u32 %0, %1, 128, %2;" : "=l"(w) : "r"(y), "l"(((uint64_t)z << 32) | x));
+        r = (uint32_t)w ^ (uint32_t)(w >> 32);
       } else {
-        asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(a[j]) : "r"(a[j]), "r"(a[(j + 1) & 15]), "r"(a[(j + 5) & 15]));
+        asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(x), "r"(y), "r"(z));
       }
+      a[j] = r;
     }
   }
   uint32_t x = 0;
@@ -45,9 +61,17 @@ cudaError_t run_int_peak(int mode, int sm_count, uint32_t* scratch /* >= sm_coun
   float best = 1e30f;
   for (int rep = 0; rep < 4; rep++) {
     cudaEventRecord(e0, st);
-    if (mode == 0) k_int_peak<0><<<blocks, 256, 0, st>>>(scratch, iters);
-    else if (mode == 1) k_int_peak<1><<<blocks, 256, 0, st>>>(scratch, iters);
-    else k_int_peak<2><<<blocks, 256, 0, st>>>(scratch, iters);
+    switch (mode) {
+      case 0: k_int_peak<0><<<blocks, 256, 0, st>>>(scratch, iters); break;
+      case 1: k_int_peak<1><<<blocks, 256, 0, st>>>(scratch, iters); break;
+      case 2: k_int_peak<2><<<blocks, 256, 0, st>>>(scratch, iters); break;
+      case 3: k_int_peak<3><<<blocks, 256, 0, st>>>(scratch, iters); break;
+      case 4: k_int_peak<4><<<blocks, 256, 0, st>>>(scratch, iters); break;
+      case 5: k_int_peak<5><<<blocks, 256, 0, st>>>(scratch, iters); break;
+      case 6: k_int_peak<6><<<blocks, 256, 0, st>>>(scratch, iters); break;
+      case 7: k_int_peak<7><<<blocks, 256, 0, st>>>(scratch, iters); break;
+      default: k_int_peak<8><<<blocks, 256, 0, st>>>(scratch, iters); break;
+    }
     cudaEventRecord(e1, st);
     e = cudaEventSynchronize(e1);
     if (e != cudaSuccess) break;

@@ -38,8 +38,24 @@ struct DevBuf {
 };
 
 // one pipeline slot of the host-buffer path: device copies of a chunk's inputs and outputs
+struct HostBuf {  // page-locked staging for results (the caller's arrays may be pageable, and an
+  void* p = nullptr;  // async copy into pageable memory would stall the pipeline)
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct Slot {
   cudaStream_t stream = nullptr;
+  HostBuf h_status, h_value_off, h_value_len;
+  uint64_t pend_p0 = 0, pend_np = 0;  // results of this proof range are in flight into the staging buffers
   DevBuf node_bytes, node_off, node_len, proof_first, roots, key_bytes, key_off, rfp;
   DevBuf status, value_off, value_len;
   DevBuf digests, meta, order, bins;
@@ -47,17 +63,20 @@ struct Slot {
     DevBuf* all[] = {&node_bytes, &node_off, &node_len, &proof_first, &roots, &key_bytes, &key_off, &rfp,
                      &status, &value_off, &value_len, &digests, &meta, &order, &bins};
     for (DevBuf* b : all) b->release();
+    h_status.release(); h_value_off.release(); h_value_len.release();
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
 };
+
+constexpr int kSlots = 3;  // pipeline depth of the host-buffer path (H2D / kernels / D2H in flight)
 
 struct Device {
   int id = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;  // device-resident entry
   DevBuf digests, meta, order, bins;  // scratch of the device-resident entry
-  Slot slot[2];
+  Slot slot[kSlots];
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaStream_t last_stream = nullptr;
   bool have_timing = false;
@@ -187,7 +206,7 @@ int mptv_create(const int* device_ids, int n_devices, mptv_ctx** out) {
     }
     if (e == cudaSuccess) { d.sm_count = prop.multiProcessorCount; e = kernels_init_device(); }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
-    for (int s = 0; s < 2 && e == cudaSuccess; s++) e = cudaStreamCreateWithFlags(&d.slot[s].stream, cudaStreamNonBlocking);
+    for (int s = 0; s < kSlots && e == cudaSuccess; s++) e = cudaStreamCreateWithFlags(&d.slot[s].stream, cudaStreamNonBlocking);
     for (int k = 0; k < 6 && e == cudaSuccess; k++) e = cudaEventCreate(&d.ev[k]);
     if (e != cudaSuccess) {
       fprintf(stderr, "mptv_create: device %d: %s\n", d.id, cudaGetErrorString(e));
@@ -205,7 +224,7 @@ void mptv_destroy(mptv_ctx* ctx) {
     cudaSetDevice(d.id);
     cudaDeviceSynchronize();
     d.digests.release(); d.meta.release(); d.order.release(); d.bins.release();
-    d.slot[0].release(); d.slot[1].release();
+    for (int k = 0; k < kSlots; k++) d.slot[k].release();
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
     if (d.stream) cudaStreamDestroy(d.stream);
   }
@@ -277,7 +296,7 @@ int mptv_keccak256_batch_device(mptv_ctx* ctx, int dev_index, const uint8_t* nod
 }
 
 int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops_per_s) {
-  if (!ctx || !lane_ops_per_s || dev_index < 0 || dev_index >= (int)ctx->dev.size() || mode < 0 || mode > 2)
+  if (!ctx || !lane_ops_per_s || dev_index < 0 || dev_index >= (int)ctx->dev.size() || mode < 0 || mode > 8)
     return MPTV_ERR_ARG;
   Device& d = ctx->dev[dev_index];
   CK(cudaSetDevice(d.id));
@@ -311,23 +330,23 @@ namespace {
 
 struct Chunk { uint64_t p0, p1; };  // proof range
 
-// cut [p0, p1) into chunks of about `chunk_bytes` node bytes without splitting a dependency group
-int make_chunks(const mptv_batch* in, uint64_t p0, uint64_t p1, uint64_t chunk_bytes, std::vector<Chunk>& out) {
-  uint64_t s = p0;
-  while (s < p1) {
-    uint64_t e = s;
-    const uint64_t byte0 = in->node_off[in->proof_first[s]];
-    while (e < p1) {
-      const uint32_t nlast = in->proof_first[e + 1];
-      const uint64_t bytes_end = nlast > in->proof_first[s]
-                                   ? in->node_off[nlast - 1] + in->node_len[nlast - 1] : byte0;
-      if (e > s && bytes_end - byte0 > chunk_bytes && (!in->root_from_proof || in->root_from_proof[e] < 0)) break;
-      e++;
-    }
-    out.push_back({s, e});
-    s = e;
+// end of the chunk that starts at proof s: about `chunk_bytes` node bytes (binary search over the
+// monotone node offsets), never splitting a dependency group (a dependent follows its account proof)
+uint64_t next_chunk_end(const mptv_batch* in, uint64_t s, uint64_t p1, uint64_t chunk_bytes) {
+  const uint32_t n_total = in->proof_first[in->n_proofs];
+  const uint32_t fs = in->proof_first[s];
+  const uint64_t byte0 = fs < n_total ? in->node_off[fs] : 0;
+  const uint64_t target = byte0 + chunk_bytes;
+  uint64_t lo = s + 1, hi = p1;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) / 2;
+    const uint32_t fn = in->proof_first[mid];
+    const uint64_t off = fn < n_total ? in->node_off[fn] : ~0ull;
+    if (off < target) lo = mid + 1; else hi = mid;
   }
-  return MPTV_OK;
+  uint64_t e = lo;
+  if (in->root_from_proof) while (e < p1 && in->root_from_proof[e] >= 0) e++;
+  return e;
 }
 
 int validate_slice(const mptv_batch* in, uint64_t p0, uint64_t p1) {
@@ -347,19 +366,34 @@ int validate_slice(const mptv_batch* in, uint64_t p0, uint64_t p1) {
   return MPTV_OK;
 }
 
-// run one device's slice [p0, p1): chunked, double-buffered H2D -> kernels -> D2H
+// wait for the chunk a slot is working on and hand its results to the caller's arrays
+int drain_slot(mptv_ctx* ctx, Slot& s, mptv_result* out) {
+  CK(cudaStreamSynchronize(s.stream));
+  if (s.pend_np) {
+    memcpy(out->status + s.pend_p0, s.h_status.p, s.pend_np);
+    memcpy(out->value_off + s.pend_p0, s.h_value_off.p, 8 * s.pend_np);
+    memcpy(out->value_len + s.pend_p0, s.h_value_len.p, 4 * s.pend_np);
+    s.pend_np = 0;
+  }
+  return MPTV_OK;
+}
+
+// run one device's slice [p0, p1): chunked, multi-buffered H2D -> kernels -> D2H
 int run_slice(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result* out, uint64_t p0, uint64_t p1) {
   if (p1 <= p0) return MPTV_OK;
   CK(cudaSetDevice(d.id));
-  int rc = validate_slice(in, p0, p1);
-  if (rc != MPTV_OK) return rc;
-  std::vector<Chunk> chunks;
-  make_chunks(in, p0, p1, ctx->chunk_bytes, chunks);
-  for (size_t ci = 0; ci < chunks.size(); ci++) {
-    const Chunk c = chunks[ci];
-    Slot& s = d.slot[ci & 1];
+  int rc = MPTV_OK;
+  size_t ci = 0;
+  for (uint64_t cs = p0; cs < p1; ci++) {
+    const Chunk c = {cs, next_chunk_end(in, cs, p1, ctx->chunk_bytes)};
+    cs = c.p1;
+    Slot& s = d.slot[ci % kSlots];
     cudaStream_t st = s.stream;
-    CK(cudaStreamSynchronize(st));  // the slot's previous chunk (two back) must be drained
+    // argument checks of this chunk run on the host while earlier chunks are in flight
+    rc = validate_slice(in, c.p0, c.p1);
+    if (rc != MPTV_OK) return rc;
+    rc = drain_slot(ctx, s, out);  // the slot's previous chunk must be complete before its buffers are reused
+    if (rc != MPTV_OK) return rc;
     const uint64_t np = c.p1 - c.p0;
     const uint32_t n0 = in->proof_first[c.p0], n1 = in->proof_first[c.p1];
     const uint64_t nn = n1 - n0;
@@ -402,12 +436,18 @@ int run_slice(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result* out, 
     rc = run_pipeline(ctx, d, b, s.digests, s.meta, s.order, s.bins, s.status.as<uint8_t>(),
                       s.value_off.as<uint64_t>(), s.value_len.as<uint32_t>(), st, false);
     if (rc != MPTV_OK) return rc;
-    CK(cudaMemcpyAsync(out->status + c.p0, s.status.p, np, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out->value_off + c.p0, s.value_off.p, 8 * np, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out->value_len + c.p0, s.value_len.p, 4 * np, cudaMemcpyDeviceToHost, st));
+    CK(s.h_status.reserve(np));
+    CK(s.h_value_off.reserve(8 * np));
+    CK(s.h_value_len.reserve(4 * np));
+    CK(cudaMemcpyAsync(s.h_status.p, s.status.p, np, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_value_off.p, s.value_off.p, 8 * np, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_value_len.p, s.value_len.p, 4 * np, cudaMemcpyDeviceToHost, st));
+    s.pend_p0 = c.p0; s.pend_np = np;
   }
-  CK(cudaStreamSynchronize(d.slot[0].stream));
-  CK(cudaStreamSynchronize(d.slot[1].stream));
+  for (int k = 0; k < kSlots; k++) {
+    rc = drain_slot(ctx, d.slot[k], out);
+    if (rc != MPTV_OK) return rc;
+  }
   return MPTV_OK;
 }
 

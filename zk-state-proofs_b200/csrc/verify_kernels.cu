@@ -221,8 +221,11 @@ __device__ __forceinline__ uint32_t key_nibble(const uint8_t* key, uint32_t klen
   return (i & 1) ? (b & 15) : (b >> 4);
 }
 
+#ifndef MPTV_WALK_MINB
+#define MPTV_WALK_MINB 4  // measured on B200: 4 x 256 threads / SM beats 2, 3, 5, 6, 8 (tools/ sweep, r01)
+#endif
 template <int G>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, MPTV_WALK_MINB)
 k_verify_walk(const DeviceBatch b, int wave, const uint8_t* __restrict__ digests,
               const uint32_t* __restrict__ meta, uint8_t* status_out, uint64_t* value_off_out,
               uint32_t* value_len_out) {
@@ -280,13 +283,44 @@ k_verify_walk(const DeviceBatch b, int wave, const uint8_t* __restrict__ digests
       return ((uint64_t)g.bcast((uint32_t)(myoff >> 32), j) << 32) | g.bcast((uint32_t)myoff, j);
     return node_off[a + j];
   };
-  // 32 bytes at q (unaligned): lanes 0..7 assemble one word each, shuffle-broadcast to the group
+  // 32 bytes at q (unaligned): lanes 0..7 assemble one word each from two aligned words,
+  // shuffle-broadcast to the group
   auto load_link = [&](const uint8_t* q, uint32_t (&h)[8]) {
     uint32_t w = 0;
-    if (g.lig < 8) w = load_u32_unaligned(q + 4 * g.lig);
+    if (g.lig < 8) {
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)3) + g.lig;
+      w = __funnelshift_r(__ldg(wp), __ldg(wp + 1), 8u * (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3));
+    }
 #pragma unroll
     for (int i = 0; i < 8; i++) h[i] = g.bcast(w, i);
   };
+  // Speculative link prefetch: in a root-first proof node j sits at depth j when every node above
+  // it is a plain branch.  Lane j therefore fetches, up front and in parallel with all other lanes,
+  // the child reference its own node would hand out for key nibble j.  The walk uses lane cur's
+  // copy when it really arrives at node cur with path index cur, and reads memory otherwise, so
+  // this only shortens the dependent-load chain (one HBM latency instead of one per level); the
+  // reference's order-independent semantics (R6) are untouched.
+  uint32_t sl[8];
+  bool have_spec = false;
+  if (g.lig < n && mymeta != kMetaSlow && meta_dec(mymeta) == kDecOk && meta_fast(mymeta)) {
+    const uint32_t nibj = key_nibble(key, klen, g.lig);
+    const uint32_t mk = meta_mask(mymeta);
+    if (nibj < 16 && ((mk >> nibj) & 1u)) {
+      const uint8_t* q = node_bytes + myoff + meta_hdr(mymeta) + nibj + 32u * __popc(mk & ((1u << nibj) - 1u)) + 1;
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)3);
+      const uint32_t sh = 8u * (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3);
+      uint32_t w[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) w[i] = __ldg(wp + i);
+#pragma unroll
+      for (int i = 0; i < 8; i++) sl[i] = __funnelshift_r(w[i], w[i + 1], sh);
+      have_spec = true;
+    }
+  }
+  if (!have_spec) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) sl[i] = 0;
+  }
   // lowest node index whose digest equals h (MemoryDB keyed by hash).  `filtered` applies the DB2
   // admission rule of verify_proof: digest == root or len >= 32 (R5, R9).
   auto find = [&](const uint32_t (&h)[8], bool filtered) -> int {
@@ -354,6 +388,7 @@ k_verify_walk(const DeviceBatch b, int wave, const uint8_t* __restrict__ digests
     for (uint32_t guard = 0; !done; guard++) {
       if (guard > 4096) { status = kStInvalidProof; break; }
       const uint8_t* link = nullptr;  // where the 32-byte child reference to follow lives
+      bool use_spec = false;          // ... or take it from lane cur's prefetched copy
       if (lp == 0 && meta_fast(m)) {
         // plain branch: 16 children that are each 0x80 or a 32-byte hash, empty value.  Child
         // selection is a popcount over the occupancy map K2a recorded -- no node bytes are read
@@ -361,8 +396,10 @@ k_verify_walk(const DeviceBatch b, int wave, const uint8_t* __restrict__ digests
         const uint32_t nib = key_nibble(key, klen, idx);
         const uint32_t mk = meta_mask(m);
         if (nib == 16 || !((mk >> nib) & 1u)) { status = kStKeyNotFound; break; }  // R14 (empty value) / R15
+        const bool spec = cur < (uint32_t)G && idx == cur;  // lane cur prefetched exactly this link
         idx += 1;
-        link = node_bytes + off_of(cur) + meta_hdr(m) + nib + 32u * __popc(mk & ((1u << nib) - 1u)) + 1;
+        if (spec) use_spec = true;
+        else link = node_bytes + off_of(cur) + meta_hdr(m) + nib + 32u * __popc(mk & ((1u << nib) - 1u)) + 1;
       } else {
         // general node (leaf, extension, branch with inline children or a value, inline node).
         // K2a validated the whole node, so the headers below are known to be well formed.
@@ -433,7 +470,12 @@ k_verify_walk(const DeviceBatch b, int wave, const uint8_t* __restrict__ digests
       }
       // ---- follow a hash reference: shuffle-broadcast the link, compare against every digest
       uint32_t h[8];
-      load_link(link, h);
+      if (use_spec) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) h[i] = g.bcast(sl[i], cur);
+      } else {
+        load_link(link, h);
+      }
       for (uint32_t hops = 0;; hops++) {
         const int j = find(h, true);
         if (j < 0 || hops > n) { status = kStInvalidProof; done = true; break; }  // R8 / R9
