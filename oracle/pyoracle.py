@@ -81,6 +81,8 @@ class Oracle:
         L.mpto_account_storage_root.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p]
         L.mpto_verify_batch.restype = ctypes.c_int
         L.mpto_keccak256_batch.restype = ctypes.c_int
+        L.mpto_trie_roots.restype = ctypes.c_int
+        L.mpto_trie_get_proof.restype = ctypes.c_int
 
     def keccak256(self, data: bytes) -> bytes:
         out = ctypes.create_string_buffer(32)
@@ -134,6 +136,37 @@ class Oracle:
             ctypes.c_int(nthreads), ctypes.c_int(1 if mirror else 0),
             ctypes.byref(pa), ctypes.byref(pd))
         return status, voff, vlen, pa.value, pd.value
+
+    def trie_roots(self, kv, nthreads: int = 1):
+        """kv: dict(key_bytes u8, key_off u32[n+1], value_bytes u8, value_off u64[n], value_len u32[n],
+        trie_first u32[T+1]) -> (roots u8[T,32], perms, nodes_hashed)"""
+        T = len(kv["trie_first"]) - 1
+        roots = np.zeros((T, 32), np.uint8)
+        pa, nh = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        self.lib.mpto_trie_roots(
+            _p(kv["key_bytes"], ctypes.c_uint8), _p(kv["key_off"], ctypes.c_uint32),
+            _p(kv["value_bytes"], ctypes.c_uint8), _p(kv["value_off"], ctypes.c_uint64),
+            _p(kv["value_len"], ctypes.c_uint32), _p(kv["trie_first"], ctypes.c_uint32), ctypes.c_uint64(T),
+            _p(roots, ctypes.c_uint8), ctypes.c_int(nthreads), ctypes.byref(pa), ctypes.byref(nh))
+        return roots, pa.value, nh.value
+
+    def trie_get_proof(self, kv, t: int, key: bytes):
+        """-> (root bytes, [node bytes]) for trie t of kv"""
+        first = int(kv["trie_first"][t]); n = int(kv["trie_first"][t + 1]) - first
+        cap = 1 << 22
+        out = np.zeros(cap, np.uint8)
+        lens = np.zeros(256, np.uint32)
+        root = np.zeros(32, np.uint8)
+        cnt = self.lib.mpto_trie_get_proof(
+            _p(kv["key_bytes"], ctypes.c_uint8), _p(kv["key_off"], ctypes.c_uint32),
+            _p(kv["value_bytes"], ctypes.c_uint8), _p(kv["value_off"], ctypes.c_uint64),
+            _p(kv["value_len"], ctypes.c_uint32), ctypes.c_uint64(first), ctypes.c_uint64(n), bytes(key),
+            ctypes.c_uint32(len(key)), _p(out, ctypes.c_uint8), ctypes.c_uint64(cap), _p(lens, ctypes.c_uint32),
+            ctypes.c_uint32(256), _p(root, ctypes.c_uint8))
+        nodes, pos = [], 0
+        for i in range(cnt):
+            nodes.append(out[pos:pos + int(lens[i])].tobytes()); pos += int(lens[i])
+        return root.tobytes(), nodes
 
     def keccak256_batch(self, node_bytes, node_off, node_len):
         n = len(node_len)
