@@ -139,6 +139,52 @@ int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops
  * chunk size in bytes of node data for the host-buffer pipeline (0 = default) */
 int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value);
 
+/* ---------------------------------------------------------------------------------------------
+ * Trie rebuild: what trie-utils does per block with EthTrie::new + insert(rlp(i), bytes) x n +
+ * root_hash()  (/root/reference/trie-utils/src/proofs/transaction.rs:41-66, proofs/receipt.rs:49-84,
+ * src/receipt.rs:8-38), for a whole batch of independent tries at once.
+ *   item i      = key   key_bytes[key_off[i] .. key_off[i+1])            (<= 32 bytes)
+ *                 value value_bytes[value_off[i] .. value_off[i] + value_len[i])
+ *                 value_off[i] % 16 == 0, value_bytes readable up to the next multiple of 16 after
+ *                 each value; value_len[i] == 0 deletes the key (eth_trie: insert(k, b"") == remove)
+ *   trie t      = items [trie_first[t], trie_first[t+1]) applied in order (last write wins);
+ *                 at most 8192 items per trie (per-block tries; larger ones are refused: MPTV_ERR_ARG)
+ *   roots32     = [32 * n_tries]; an empty trie gives keccak256(0x80).
+ */
+typedef struct mptv_kv_batch {
+  const uint8_t* key_bytes;
+  const uint32_t* key_off;    /* [n_items+1] */
+  const uint8_t* value_bytes;
+  uint64_t value_bytes_len;
+  const uint64_t* value_off;  /* [n_items]   */
+  const uint32_t* value_len;  /* [n_items]   */
+  uint64_t n_items;
+  const uint32_t* trie_first; /* [n_tries+1] */
+  uint64_t n_tries;
+} mptv_kv_batch;
+
+/* device time of the last mptv_trie_roots_device call on a device (CUDA events on its stream) */
+typedef struct mptv_rebuild_timings {
+  float structure_ms; /* sort + skeleton + level lists (incl. the summary read-back)     */
+  float encode_ms;    /* sum over levels of the RLP encode launches                      */
+  float keccak_ms;    /* sum over levels of K0 + K1                                      */
+  float total_ms;
+  uint64_t n_nodes;   /* trie nodes built                                                */
+  uint64_t n_hashed;  /* nodes >= 32 bytes (+ roots): the ones write_node hashes         */
+  uint64_t n_perm;    /* algorithmic Keccak-f count = sum over hashed nodes ceil((len+1)/136) */
+  uint64_t arena_bytes;
+  uint32_t levels, keccak_launches, other_launches, pad;
+} mptv_rebuild_timings;
+
+/* host buffers; tries are sharded over the context's devices as contiguous slices balanced by
+ * value bytes, no inter-device traffic */
+int mptv_trie_roots(mptv_ctx* ctx, const mptv_kv_batch* in, uint8_t* roots32);
+/* device pointers on device `dev_index`; runs on `stream` (NULL = the context's stream) and
+ * returns after the launches of the last level are queued (it synchronises the stream twice in
+ * between to read back the level sizes) */
+int mptv_trie_roots_device(mptv_ctx* ctx, int dev_index, const mptv_kv_batch* in, uint8_t* roots32, void* stream);
+int mptv_last_rebuild_timings(mptv_ctx* ctx, int dev_index, mptv_rebuild_timings* out);
+
 /* page-locked host memory for arenas that are handed to mptv_verify_batch */
 void* mptv_alloc_pinned(size_t bytes);
 void mptv_free_pinned(void* p);

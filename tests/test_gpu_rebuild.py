@@ -1,0 +1,74 @@
+"""K4 parity: tx / receipt trie roots rebuilt on the GPU (through the C ABI) against the CPU
+restatement of eth_trie's insert + root_hash (oracle/trie_oracle.c) on the same seeded inputs --
+bit-exact 32-byte roots -- and closed through the verifier: proofs extracted from the rebuilt trie
+verify on the GPU against the GPU-built root and return the inserted bytes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _kv(z, d):
+    return z.KvBatch(d["key_bytes"], d["key_off"], d["value_bytes"], d["value_off"], d["value_len"], d["trie_first"])
+
+
+def test_random_tries_roots_match_oracle(verifier, oracle):
+    import zk_state_proofs_b200 as z
+    from tests.test_rebuild_oracle import make_kv, random_tries
+    for seed in (5, 6, 7):
+        tries = random_tries(seed, 300)
+        d = make_kv(tries)
+        want, perms, hashed = oracle.trie_roots(d, nthreads=8)
+        got = verifier.trie_roots(_kv(z, d))
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        assert len(bad) == 0, [(int(t), len(tries[t])) for t in bad[:10]]
+
+
+def test_flatten_kv_and_ordered_trie_root(verifier, oracle):
+    import zk_state_proofs_b200 as z
+    from oracle.pytrie import Trie
+    vals = [b"\x02" + bytes([i % 251]) * (100 + 3 * i) for i in range(200)]
+    root = verifier.ordered_trie_root(vals)
+    assert root == Trie({z.rlp_index(i): v for i, v in enumerate(vals)}, oracle.keccak256).root
+    assert verifier.ordered_trie_root([]).hex() == "56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421"
+    # KAT-1 of SURVEY.md Appendix E: single leaf {rlp(0): 0102..08}
+    assert verifier.ordered_trie_root([bytes(range(1, 9))]).hex() == \
+        "0e9985286c0f4a35519eeb86fa50ce8134ed1fd1bb88e6f74a9e4cb6f505079c"
+    assert verifier.trie_roots(z.flatten_kv([])).shape == (0, 32)
+
+
+def test_config4_shaped_blocks_match_oracle_and_close_through_the_verifier(verifier, oracle):
+    import zk_state_proofs_b200 as z
+    from workload import gen
+    for kind in ("tx", "receipt"):
+        kv = gen.block_tries(150, 300, kind=kind, seed=4)
+        want, perms, hashed = oracle.trie_roots(kv.as_dict(), nthreads=8)
+        got = verifier.trie_roots(kv)
+        assert (got == want).all(), kind
+        # timings / work counters of the device entry agree with the oracle's accounting
+        # (the host entry ran one chunk on device 0)
+        t = verifier.last_rebuild_timings(0)
+        assert t.n_perm == perms and t.n_hashed == hashed
+        # proofs out of the rebuilt trie (oracle's get_proof) verify on the GPU against the GPU root
+        inputs, expect = [], []
+        for blk in (0, 77, 149):
+            for i in (0, 1, 15, 127, 128, 299):
+                key = z.rlp_index(i)
+                root, nodes = oracle.trie_get_proof(kv.as_dict(), blk, key)
+                assert root == got[blk].tobytes()
+                inputs.append(z.MerkleProofInput(nodes, got[blk].tobytes(), key))
+                it = blk * 300 + i
+                o, ln = int(kv.value_off[it]), int(kv.value_len[it])
+                expect.append(kv.value_bytes[o:o + ln].tobytes())
+        assert verifier.verify_merkle_proofs(inputs) == expect
+
+
+def test_refuses_what_it_cannot_hold(verifier, oracle):
+    import zk_state_proofs_b200 as z
+    with pytest.raises(z.MptvError):
+        verifier.trie_roots(z.flatten_kv([[(b"k" * 33, b"v")]]))
+    with pytest.raises(z.MptvError):
+        verifier.trie_roots(z.flatten_kv([[(i.to_bytes(4, "big"), b"v") for i in range(8193)]]))
+    # the largest trie it does hold
+    kv = z.flatten_kv([[((i * 2654435761 % (1 << 32)).to_bytes(4, "big"), b"v" * (1 + i % 70)) for i in range(8192)]])
+    assert (verifier.trie_roots(kv) == oracle.trie_roots(kv.as_dict())[0]).all()

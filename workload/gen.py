@@ -199,3 +199,35 @@ def make_state_and_tokens(n_accounts: int, n_tokens: int, n_slots: int, seed: in
     pool = np.concatenate([t.root for t in tokens]) if tokens else None
     state = SynthTrie(n_accounts, seed, kind=0, pool_roots=pool)
     return state, tokens
+
+
+# ----------------------------------------------------------------------------- config 4: block tries
+def block_tries(n_blocks: int, per_block: int = 300, kind: str = "tx", seed: int = 4, pinned: bool = False):
+    """Synthetic per-block transaction (kind="tx") or receipt (kind="receipt") tries in the KvBatch
+    layout: key = rlp(index), value = opaque EIP-2718 bytes (first byte 0x02).  Sizes per SURVEY.md
+    section 8d config 4: txs log-normal, median 180 B, capped at 8 KB; receipts median ~1.5 KB
+    (256-byte bloom + 0..40 logs), tail to 30 KB."""
+    import zk_state_proofs_b200 as z
+    rng = np.random.default_rng(seed + (0 if kind == "tx" else 1000))
+    n = n_blocks * per_block
+    if kind == "tx":
+        lens = np.clip(rng.lognormal(np.log(180.0), 0.9, n), 100, 8192).astype(np.uint32)
+    else:
+        lens = np.clip(270 + rng.lognormal(np.log(1230.0), 1.0, n), 270, 30000).astype(np.uint32)
+    padded = (lens.astype(np.uint64) + 15) & ~np.uint64(15)
+    value_off = np.zeros(n, np.uint64)
+    np.cumsum(padded[:-1], out=value_off[1:])
+    total = int(padded.sum()) + 16
+    value_bytes = _alloc(total, np.uint8, pinned)
+    step = 1 << 28
+    for s in range(0, total, step):
+        e = min(total, s + step)
+        value_bytes[s:e] = rng.integers(0, 256, e - s, dtype=np.uint8)
+    value_bytes[value_off.astype(np.int64)] = 2
+    one = b"".join(z.rlp_index(i) for i in range(per_block))
+    klen = np.array([len(z.rlp_index(i)) for i in range(per_block)], np.int64)
+    key_bytes = np.frombuffer(one * n_blocks + b"\0" * 16, np.uint8).copy()
+    key_off = np.zeros(n + 1, np.uint32)
+    np.cumsum(np.tile(klen, n_blocks), out=key_off[1:])
+    trie_first = (np.arange(n_blocks + 1, dtype=np.uint64) * per_block).astype(np.uint32)
+    return z.KvBatch(key_bytes, key_off, value_bytes, value_off, lens, trie_first)

@@ -7,6 +7,7 @@ call raises if libmptv.so or a B200 is missing.
 """
 from .crypto_ops import (  # noqa: F401
     Batch,
+    KvBatch,
     MerkleProofInput,
     MptvError,
     StorageProofInput,
@@ -15,15 +16,19 @@ from .crypto_ops import (  # noqa: F401
     STATUS_NAMES,
     digest_keccak,
     flatten,
+    flatten_kv,
     lib_path,
     load_library,
+    ordered_trie_root,
+    rlp_index,
+    trie_roots,
     verify_merkle_proof,
     verify_merkle_proofs,
     verify_storage_proof_input,
 )
 
 __all__ = [
-    "Batch", "MerkleProofInput", "MptvError", "StorageProofInput", "VerifyPanic", "Verifier",
+    "Batch", "KvBatch", "flatten_kv", "ordered_trie_root", "rlp_index", "trie_roots", "MerkleProofInput", "MptvError", "StorageProofInput", "VerifyPanic", "Verifier",
     "STATUS_NAMES", "digest_keccak", "flatten", "lib_path", "load_library", "verify_merkle_proof",
     "verify_merkle_proofs", "verify_storage_proof_input",
 ]

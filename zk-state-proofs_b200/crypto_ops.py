@@ -7,6 +7,9 @@ Reference interface mirrored here (same names, argument meaning and error behavi
   MerkleProofInput / StorageProofInput (+ borsh wire form) /root/reference/crypto-ops/src/types.rs:4-19
 and the batched entry the north star adds:
   verify_merkle_proofs([MerkleProofInput]) -> [bytes | VerifyPanic]
+The tx / receipt trie rebuild that trie-utils performs with eth_trie
+(/root/reference/trie-utils/src/proofs/transaction.rs:41-66, proofs/receipt.rs:49-84) is
+trie_roots() / ordered_trie_root() over a KvBatch.
 The nested account -> storage flow of the risc0 storage guest
 (/root/reference/circuits/risc0-storage-proof/storage-proof-circuit/storage-circuit/src/main.rs:6-31)
 is verify_storage_proof_input().
@@ -186,7 +189,84 @@ def flatten(inputs: Sequence[MerkleProofInput], root_from_proof: Optional[Sequen
     return Batch(node_bytes, node_off, lens, proof_first, roots, key_bytes, key_off, rfp, bad if bad.any() else None)
 
 
+# ----------------------------------------------------------------------------- key/value batches (rebuild)
+@dataclass
+class KvBatch:
+    """Flat form of T independent tries' (key, value) insert lists (include/mptv.h `mptv_kv_batch`)."""
+    key_bytes: np.ndarray    # u8
+    key_off: np.ndarray      # u32 [n_items+1]
+    value_bytes: np.ndarray  # u8, values 16-byte aligned, total padded to 16
+    value_off: np.ndarray    # u64 [n_items]
+    value_len: np.ndarray    # u32 [n_items]; 0 = delete (eth_trie: insert(k, b"") removes k)
+    trie_first: np.ndarray   # u32 [n_tries+1]
+
+    @property
+    def n_items(self) -> int:
+        return len(self.value_len)
+
+    @property
+    def n_tries(self) -> int:
+        return len(self.trie_first) - 1
+
+    def as_dict(self):
+        return dict(key_bytes=self.key_bytes, key_off=self.key_off, value_bytes=self.value_bytes,
+                    value_off=self.value_off, value_len=self.value_len, trie_first=self.trie_first)
+
+
+def rlp_index(i: int) -> bytes:
+    """alloy_rlp::encode(index) -- the trie key of transaction / receipt i (transaction.rs:45)."""
+    if i == 0:
+        return b"\x80"
+    if i < 0x80:
+        return bytes([i])
+    be = i.to_bytes((i.bit_length() + 7) // 8, "big")
+    return bytes([0x80 + len(be)]) + be
+
+
+def flatten_kv(tries) -> KvBatch:
+    """[[(key, value), ...], ...] in insertion order -> KvBatch (every value on a 16-byte boundary)."""
+    keys = [k for t in tries for k, _ in t]
+    vals = [v for t in tries for _, v in t]
+    n = len(keys)
+    klens = np.fromiter((len(k) for k in keys), dtype=np.int64, count=n)
+    key_off = np.zeros(n + 1, np.uint32)
+    np.cumsum(klens, out=key_off[1:])
+    key_bytes = np.zeros(int(key_off[-1]) + 16, np.uint8)
+    if n:
+        key_bytes[:int(key_off[-1])] = np.frombuffer(b"".join(bytes(k) for k in keys), np.uint8)
+    value_len = np.fromiter((len(v) for v in vals), dtype=np.uint32, count=n)
+    padded = (value_len.astype(np.uint64) + 15) & ~np.uint64(15)
+    value_off = np.zeros(n, np.uint64)
+    if n:
+        np.cumsum(padded[:-1], out=value_off[1:])
+    value_bytes = np.zeros(int(padded.sum()) + 16, np.uint8)
+    for v, o in zip(vals, value_off):
+        if len(v):
+            value_bytes[int(o):int(o) + len(v)] = np.frombuffer(bytes(v), np.uint8)
+    counts = np.fromiter((len(t) for t in tries), dtype=np.int64, count=len(tries))
+    trie_first = np.zeros(len(tries) + 1, np.uint32)
+    np.cumsum(counts, out=trie_first[1:])
+    return KvBatch(key_bytes, key_off, value_bytes, value_off, value_len, trie_first)
+
+
 # ----------------------------------------------------------------------------- C ABI
+class _CKvBatch(ctypes.Structure):
+    _fields_ = [
+        ("key_bytes", ctypes.c_void_p), ("key_off", ctypes.c_void_p), ("value_bytes", ctypes.c_void_p),
+        ("value_bytes_len", ctypes.c_uint64), ("value_off", ctypes.c_void_p), ("value_len", ctypes.c_void_p),
+        ("n_items", ctypes.c_uint64), ("trie_first", ctypes.c_void_p), ("n_tries", ctypes.c_uint64),
+    ]
+
+
+class RebuildTimings(ctypes.Structure):
+    _fields_ = [
+        ("structure_ms", ctypes.c_float), ("encode_ms", ctypes.c_float), ("keccak_ms", ctypes.c_float),
+        ("total_ms", ctypes.c_float), ("n_nodes", ctypes.c_uint64), ("n_hashed", ctypes.c_uint64),
+        ("n_perm", ctypes.c_uint64), ("arena_bytes", ctypes.c_uint64), ("levels", ctypes.c_uint32),
+        ("keccak_launches", ctypes.c_uint32), ("other_launches", ctypes.c_uint32), ("pad", ctypes.c_uint32),
+    ]
+
+
 class _CBatch(ctypes.Structure):
     _fields_ = [
         ("node_bytes", ctypes.c_void_p), ("node_bytes_len", ctypes.c_uint64),
@@ -252,6 +332,12 @@ def load_library():
     L.mptv_int_issue_peak.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double)]
     L.mptv_set_option.restype = i32
     L.mptv_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
+    L.mptv_trie_roots.restype = i32
+    L.mptv_trie_roots.argtypes = [vp, ctypes.POINTER(_CKvBatch), vp]
+    L.mptv_trie_roots_device.restype = i32
+    L.mptv_trie_roots_device.argtypes = [vp, i32, ctypes.POINTER(_CKvBatch), vp, vp]
+    L.mptv_last_rebuild_timings.restype = i32
+    L.mptv_last_rebuild_timings.argtypes = [vp, i32, ctypes.POINTER(RebuildTimings)]
     L.mptv_alloc_pinned.restype = vp
     L.mptv_alloc_pinned.argtypes = [ctypes.c_size_t]
     L.mptv_free_pinned.restype = None
@@ -357,6 +443,36 @@ class Verifier:
                                                       _ptr(node_len), n, _ptr(out)), "mptv_keccak256_batch")
         return out
 
+    # -- trie rebuild (EthTrie::new / insert x n / root_hash for a batch of tries)
+    def trie_roots(self, kv: KvBatch) -> np.ndarray:
+        """-> u8 [n_tries, 32]; host buffers, sharded over the context's devices."""
+        roots = np.zeros((kv.n_tries, 32), np.uint8)
+        if kv.n_tries == 0:
+            return roots
+        cb = _CKvBatch(_ptr(kv.key_bytes), _ptr(kv.key_off), _ptr(kv.value_bytes), len(kv.value_bytes),
+                       _ptr(kv.value_off), _ptr(kv.value_len), kv.n_items, _ptr(kv.trie_first), kv.n_tries)
+        self._check(self.lib.mptv_trie_roots(self.ctx, ctypes.byref(cb), _ptr(roots)), "mptv_trie_roots")
+        return roots
+
+    def trie_roots_device(self, dev_index: int, ptrs: dict, n_items: int, n_tries: int, roots_ptr: int,
+                          stream: int = 0, value_bytes_len: int = 0):
+        cb = _CKvBatch(ptrs["key_bytes"], ptrs["key_off"], ptrs["value_bytes"], value_bytes_len, ptrs["value_off"],
+                       ptrs["value_len"], n_items, ptrs["trie_first"], n_tries)
+        self._check(self.lib.mptv_trie_roots_device(self.ctx, dev_index, ctypes.byref(cb), roots_ptr,
+                                                    ctypes.c_void_p(stream) if stream else None),
+                    "mptv_trie_roots_device")
+
+    def last_rebuild_timings(self, dev_index: int = 0) -> RebuildTimings:
+        t = RebuildTimings()
+        self._check(self.lib.mptv_last_rebuild_timings(self.ctx, dev_index, ctypes.byref(t)),
+                    "mptv_last_rebuild_timings")
+        return t
+
+    def ordered_trie_root(self, values: Sequence[bytes]) -> bytes:
+        """Root of the trie {rlp(i): values[i]} -- what transaction.rs:41-66 / receipt.rs:49-84 compute."""
+        kv = flatten_kv([[(rlp_index(i), v) for i, v in enumerate(values)]])
+        return self.trie_roots(kv)[0].tobytes()
+
     # -- reference-shaped API
     def verify_merkle_proofs(self, inputs: Sequence[MerkleProofInput], root_from_proof=None):
         """-> list of bytes (the value) or VerifyPanic (what the reference would have panicked with)."""
@@ -436,3 +552,11 @@ def digest_keccak(data: bytes) -> bytes:
 
 def verify_storage_proof_input(inp: StorageProofInput) -> List[bytes]:
     return _default().verify_storage_proof_input(inp)
+
+
+def trie_roots(kv: KvBatch) -> np.ndarray:
+    return _default().trie_roots(kv)
+
+
+def ordered_trie_root(values: Sequence[bytes]) -> bytes:
+    return _default().ordered_trie_root(values)

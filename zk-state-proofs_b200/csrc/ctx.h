@@ -1,0 +1,131 @@
+// ctx.h -- internal: the context behind the opaque mptv_ctx of include/mptv.h (per-device streams,
+// growable device / pinned buffers), shared by mptv_api.cu (verification) and rebuild_api.cu (tries).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mptv.h"
+#include "kernels.h"
+
+namespace mptv {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, n); want = n; }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// one pipeline slot of the host-buffer path: device copies of a chunk's inputs and outputs
+struct HostBuf {  // page-locked staging for results (the caller's arrays may be pageable, and an
+  void* p = nullptr;  // async copy into pageable memory would stall the pipeline)
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  HostBuf h_status, h_value_off, h_value_len;
+  uint64_t pend_p0 = 0, pend_np = 0;  // results of this proof range are in flight into the staging buffers
+  DevBuf node_bytes, node_off, node_len, proof_first, roots, key_bytes, key_off, rfp;
+  DevBuf status, value_off, value_len;
+  DevBuf digests, meta, order, bins;
+  void release() {
+    DevBuf* all[] = {&node_bytes, &node_off, &node_len, &proof_first, &roots, &key_bytes, &key_off, &rfp,
+                     &status, &value_off, &value_len, &digests, &meta, &order, &bins};
+    for (DevBuf* b : all) b->release();
+    h_status.release(); h_value_off.release(); h_value_len.release();
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+  }
+};
+
+// scratch + timing of the trie rebuild path (rebuild_api.cu)
+struct Rebuild {
+  DevBuf rec, off, len, digests, tcount, lvl_list, sum, arena, order, bins;
+  DevBuf in_key_bytes, in_key_off, in_value_bytes, in_value_off, in_value_len, in_trie_first, out_roots;  // host-buffer entry
+  HostBuf h_sum, h_roots;
+  cudaEvent_t ev_begin = nullptr, ev_struct = nullptr, ev_end = nullptr;
+  std::vector<cudaEvent_t> lvl_ev;  // 3 per level: before encode, after encode, after keccak
+  uint32_t levels = 0, keccak_launches = 0, other_launches = 0;
+  bool have_timing = false;
+  unsigned long long n_nodes = 0, n_hashed = 0, n_perm = 0, arena_bytes = 0;
+  void release() {
+    DevBuf* all[] = {&rec, &off, &len, &digests, &tcount, &lvl_list, &sum, &arena, &order, &bins, &in_key_bytes,
+                     &in_key_off, &in_value_bytes, &in_value_off, &in_value_len, &in_trie_first, &out_roots};
+    for (DevBuf* b : all) b->release();
+    h_sum.release(); h_roots.release();
+    for (cudaEvent_t e : lvl_ev) cudaEventDestroy(e);
+    lvl_ev.clear();
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_struct) cudaEventDestroy(ev_struct);
+    if (ev_end) cudaEventDestroy(ev_end);
+    ev_begin = ev_struct = ev_end = nullptr;
+  }
+};
+
+constexpr int kSlots = 3;  // pipeline depth of the host-buffer path (H2D / kernels / D2H in flight)
+
+struct Device {
+  int id = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;  // device-resident entry
+  DevBuf digests, meta, order, bins;  // scratch of the device-resident entry
+  Slot slot[kSlots];
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t last_stream = nullptr;
+  bool have_timing = false;
+  uint64_t last_nodes = 0;
+  uint32_t last_keccak_launches = 0, last_other_launches = 0;
+  Rebuild rb;
+};
+
+}  // namespace mptv
+
+struct mptv_ctx {
+  std::vector<mptv::Device> dev;
+  std::string err;
+  int lanes_per_proof = 0;          // 0 = auto
+  uint64_t chunk_bytes = 96ull << 20;  // node bytes per pipeline chunk of the host-buffer path
+  int binning = 1;
+  int fused_classify = 1;  // K1 also classifies plain branches / leaves (K2a fast path)
+};
+
+
+namespace mptv {
+
+inline int fail_cuda(mptv_ctx* c, cudaError_t e, const char* where) {
+  char buf[256];
+  snprintf(buf, sizeof buf, "%s: %s", where, cudaGetErrorString(e));
+  if (c) c->err = buf;
+  return MPTV_ERR_CUDA;
+}
+
+}  // namespace mptv
+
+#define CK(call)                                                     \
+  do {                                                               \
+    cudaError_t e__ = (call);                                        \
+    if (e__ != cudaSuccess) return mptv::fail_cuda(ctx, e__, #call); \
+  } while (0)

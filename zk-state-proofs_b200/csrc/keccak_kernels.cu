@@ -26,7 +26,10 @@ __host__ __device__ __forceinline__ uint32_t nb_bin(uint32_t nb) {
   return b < kNumBins - 1 ? b : kNumBins - 1;
 }
 
-__global__ void __launch_bounds__(256) k_bin_hist(const uint32_t* __restrict__ node_len, uint64_t n_nodes,
+// ids (may be NULL = identity): the list of node indices to bin -- the rebuild path bins one trie
+// level at a time out of a larger node table.
+__global__ void __launch_bounds__(256) k_bin_hist(const uint32_t* __restrict__ node_len,
+                                                  const uint32_t* __restrict__ ids, uint64_t n_nodes,
                                                   uint32_t* __restrict__ hist) {
   __shared__ uint32_t sh[kNumBins];
   for (int i = threadIdx.x; i < kNumBins; i += blockDim.x) sh[i] = 0;
@@ -34,7 +37,7 @@ __global__ void __launch_bounds__(256) k_bin_hist(const uint32_t* __restrict__ n
   uint64_t base = (uint64_t)blockIdx.x * kBinNodesPerBlock;
   uint64_t end = base + kBinNodesPerBlock < n_nodes ? base + kBinNodesPerBlock : n_nodes;
   for (uint64_t i = base + threadIdx.x; i < end; i += blockDim.x)
-    atomicAdd(&sh[nb_bin(node_len[i] / 136 + 1)], 1u);
+    atomicAdd(&sh[nb_bin(node_len[ids ? ids[i] : i] / 136 + 1)], 1u);
   __syncthreads();
   for (int i = threadIdx.x; i < kNumBins; i += blockDim.x)
     if (sh[i]) atomicAdd(&hist[i], sh[i]);
@@ -48,7 +51,8 @@ __global__ void k_bin_scan(const uint32_t* __restrict__ hist, uint32_t* __restri
   }
 }
 
-__global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t* __restrict__ node_len, uint64_t n_nodes,
+__global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t* __restrict__ node_len,
+                                                     const uint32_t* __restrict__ ids, uint64_t n_nodes,
                                                      uint32_t* __restrict__ cursor,
                                                      uint32_t* __restrict__ order) {
   __shared__ uint32_t cnt[kNumBins];
@@ -59,11 +63,13 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t* __restrict_
   uint64_t end = base + kBinNodesPerBlock < n_nodes ? base + kBinNodesPerBlock : n_nodes;
   constexpr int kPer = kBinNodesPerBlock / 256;
   uint32_t br[kPer];  // bin << 16 | rank within this CTA's share of the bin
+  uint32_t id[kPer];
 #pragma unroll
   for (int j = 0; j < kPer; j++) {
     uint64_t i = base + threadIdx.x + (uint64_t)j * 256;
     if (i < end) {
-      const uint32_t b = nb_bin(node_len[i] / 136 + 1);
+      id[j] = ids ? ids[i] : (uint32_t)i;
+      const uint32_t b = nb_bin(node_len[id[j]] / 136 + 1);
       br[j] = (b << 16) | atomicAdd(&cnt[b], 1u);
     }
   }
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t* __restrict_
 #pragma unroll
   for (int j = 0; j < kPer; j++) {
     uint64_t i = base + threadIdx.x + (uint64_t)j * 256;
-    if (i < end) order[start[br[j] >> 16] + (br[j] & 0xffffu)] = (uint32_t)i;
+    if (i < end) order[start[br[j] >> 16] + (br[j] & 0xffffu)] = id[j];
   }
 }
 
@@ -288,17 +294,17 @@ cudaError_t kernels_init_device() {
                               (int)keccak_smem_bytes());
 }
 
-cudaError_t launch_bin_nodes(const uint32_t* node_len, uint64_t n_nodes, uint32_t* hist_cursor /*2*kNumBins*/,
-                             uint32_t* order, cudaStream_t st) {
+cudaError_t launch_bin_nodes(const uint32_t* node_len, const uint32_t* ids, uint64_t n_nodes,
+                             uint32_t* hist_cursor /*2*kNumBins*/, uint32_t* order, cudaStream_t st) {
   if (n_nodes == 0) return cudaSuccess;
   uint32_t* hist = hist_cursor;
   uint32_t* cursor = hist_cursor + kNumBins;
   cudaError_t e = cudaMemsetAsync(hist_cursor, 0, 2 * kNumBins * sizeof(uint32_t), st);
   if (e != cudaSuccess) return e;
   unsigned blocks = (unsigned)((n_nodes + kBinNodesPerBlock - 1) / kBinNodesPerBlock);
-  k_bin_hist<<<blocks, 256, 0, st>>>(node_len, n_nodes, hist);
+  k_bin_hist<<<blocks, 256, 0, st>>>(node_len, ids, n_nodes, hist);
   k_bin_scan<<<1, 32, 0, st>>>(hist, cursor);
-  k_bin_scatter<<<blocks, 256, 0, st>>>(node_len, n_nodes, cursor, order);
+  k_bin_scatter<<<blocks, 256, 0, st>>>(node_len, ids, n_nodes, cursor, order);
   return cudaGetLastError();
 }
 

@@ -57,8 +57,9 @@ struct DeviceBatch {
 cudaError_t kernels_init_device();
 
 // K0: order[] = node indices sorted by DESCENDING rate-block bin.  scratch = 2*kNumBins u32.
-cudaError_t launch_bin_nodes(const uint32_t* node_len, uint64_t n_nodes, uint32_t* scratch, uint32_t* order,
-                             cudaStream_t st);
+// ids == NULL: nodes 0..n_nodes-1; else the n_nodes node indices listed in ids[].
+cudaError_t launch_bin_nodes(const uint32_t* node_len, const uint32_t* ids, uint64_t n_nodes, uint32_t* scratch,
+                             uint32_t* order, cudaStream_t st);
 // K1: digests[32*i] = keccak256(node i).  order may be NULL (identity).  meta may be NULL; when
 // given, meta[i] receives the K2a record of plain branches / plain leaves and kMetaSlow otherwise.
 cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
@@ -73,6 +74,46 @@ cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, co
 cudaError_t launch_verify_walk(const DeviceBatch& b, const uint8_t* digests, const uint32_t* meta, int wave,
                                int lanes_per_proof, uint8_t* status, uint64_t* value_off, uint32_t* value_len,
                                cudaStream_t st);
+
+// ------------------------------------------------------------------ K4: trie rebuild (rebuild_kernels.cu)
+constexpr int kTrieThreads = 256;       // CTA of k_trie_structure (one trie per CTA)
+constexpr int kTrieMaxItems = 8192;     // items per trie (shared-memory sort); larger tries are refused
+constexpr int kTrieMaxKeyLen = 32;      // key bytes (every Ethereum trie key is <= 32 bytes)
+constexpr int kMaxLevels = 136;         // node heights: < 2 * 64 nibbles + 2
+
+// device-resident key/value batch in the layout of include/mptv.h `mptv_kv_batch`
+struct TrieBatchDev {
+  const uint8_t* key_bytes;
+  const uint32_t* key_off;    // [n_items + 1]
+  const uint8_t* value_bytes;
+  const uint64_t* value_off;  // [n_items], 16-byte aligned
+  const uint32_t* value_len;  // [n_items], 0 = delete
+  const uint32_t* trie_first; // [n_tries + 1]
+  uint32_t n_tries;
+  uint64_t n_items;
+};
+struct TrieSummary {
+  unsigned long long arena_bytes, perms, nodes_hashed, n_nodes;
+  uint32_t max_items, max_key_len, error, pad;
+  uint32_t lvl_count[2 * kMaxLevels];   // [2h] hashed nodes of height h, [2h+1] inline (< 32 byte) nodes
+  uint32_t lvl_cursor[2 * kMaxLevels];
+};
+// scratch; node id = 3 * trie_first[t] + BFS index (a trie of n items has < 3n nodes)
+struct TrieWork {
+  uint4* rec;         // [3N] node records
+  uint64_t* off;      // [3N] arena offset of the node's encoding
+  uint32_t* len;      // [3N] encoded length
+  uint8_t* digests;   // [32 * 3N]
+  uint32_t* tcount;   // [T] nodes of trie t
+  uint32_t* lvl_list; // [3N] node ids grouped by (height, hashed?)
+  TrieSummary* sum;
+};
+cudaError_t trie_init_device();
+cudaError_t launch_trie_scan_input(const TrieBatchDev& in, TrieSummary* sum, cudaStream_t st);
+cudaError_t launch_trie_structure(const TrieBatchDev& in, const TrieWork& w, uint32_t max_items, cudaStream_t st);
+cudaError_t launch_trie_encode(const TrieBatchDev& in, const TrieWork& w, const uint32_t* list, uint32_t n_list,
+                               uint8_t* arena, cudaStream_t st);
+cudaError_t launch_trie_roots(const TrieBatchDev& in, const TrieWork& w, uint8_t* roots32, cudaStream_t st);
 
 // integer issue-rate probe (microbench.cu): mode 0 = LOP3, 1 = SHF, 2 = Keccak mix
 cudaError_t run_int_peak(int mode, int sm_count, uint32_t* scratch, cudaStream_t st, double* ops_per_s);

@@ -14,100 +14,11 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/mptv.h"
-#include "kernels.h"
+#include "ctx.h"
 
 using namespace mptv;
 
 namespace {
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t n) {
-    if (n <= cap) return cudaSuccess;
-    if (p) { cudaFree(p); p = nullptr; cap = 0; }
-    size_t want = n + n / 8 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) { e = cudaMalloc(&p, n); want = n; }
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-// one pipeline slot of the host-buffer path: device copies of a chunk's inputs and outputs
-struct HostBuf {  // page-locked staging for results (the caller's arrays may be pageable, and an
-  void* p = nullptr;  // async copy into pageable memory would stall the pipeline)
-  size_t cap = 0;
-  cudaError_t reserve(size_t n) {
-    if (n <= cap) return cudaSuccess;
-    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
-    size_t want = n + n / 8 + 256;
-    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
-struct Slot {
-  cudaStream_t stream = nullptr;
-  HostBuf h_status, h_value_off, h_value_len;
-  uint64_t pend_p0 = 0, pend_np = 0;  // results of this proof range are in flight into the staging buffers
-  DevBuf node_bytes, node_off, node_len, proof_first, roots, key_bytes, key_off, rfp;
-  DevBuf status, value_off, value_len;
-  DevBuf digests, meta, order, bins;
-  void release() {
-    DevBuf* all[] = {&node_bytes, &node_off, &node_len, &proof_first, &roots, &key_bytes, &key_off, &rfp,
-                     &status, &value_off, &value_len, &digests, &meta, &order, &bins};
-    for (DevBuf* b : all) b->release();
-    h_status.release(); h_value_off.release(); h_value_len.release();
-    if (stream) cudaStreamDestroy(stream);
-    stream = nullptr;
-  }
-};
-
-constexpr int kSlots = 3;  // pipeline depth of the host-buffer path (H2D / kernels / D2H in flight)
-
-struct Device {
-  int id = 0;
-  int sm_count = 0;
-  cudaStream_t stream = nullptr;  // device-resident entry
-  DevBuf digests, meta, order, bins;  // scratch of the device-resident entry
-  Slot slot[kSlots];
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  cudaStream_t last_stream = nullptr;
-  bool have_timing = false;
-  uint64_t last_nodes = 0;
-  uint32_t last_keccak_launches = 0, last_other_launches = 0;
-};
-
-}  // namespace
-
-struct mptv_ctx {
-  std::vector<Device> dev;
-  std::string err;
-  int lanes_per_proof = 0;          // 0 = auto
-  uint64_t chunk_bytes = 96ull << 20;  // node bytes per pipeline chunk of the host-buffer path
-  int binning = 1;
-  int fused_classify = 1;  // K1 also classifies plain branches / leaves (K2a fast path)
-};
-
-namespace {
-
-int fail_cuda(mptv_ctx* c, cudaError_t e, const char* where) {
-  char buf[256];
-  snprintf(buf, sizeof buf, "%s: %s", where, cudaGetErrorString(e));
-  if (c) c->err = buf;
-  return MPTV_ERR_CUDA;
-}
-#define CK(call)                                             \
-  do {                                                       \
-    cudaError_t e__ = (call);                                \
-    if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call); \
-  } while (0)
 
 int pick_lanes(const mptv_ctx* ctx, uint64_t n_nodes, uint64_t n_proofs) {
   if (ctx->lanes_per_proof == 8 || ctx->lanes_per_proof == 16 || ctx->lanes_per_proof == 32)
@@ -127,7 +38,7 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
   if (timed) CK(cudaEventRecord(d.ev[0], st));
   const uint32_t* ord = nullptr;
   if (ctx->binning) {
-    CK(launch_bin_nodes(b.node_len, b.n_nodes, bins.as<uint32_t>(), order.as<uint32_t>(), st));
+    CK(launch_bin_nodes(b.node_len, nullptr, b.n_nodes, bins.as<uint32_t>(), order.as<uint32_t>(), st));
     ord = order.as<uint32_t>();
   }
   if (timed) CK(cudaEventRecord(d.ev[1], st));
@@ -205,6 +116,7 @@ int mptv_create(const int* device_ids, int n_devices, mptv_ctx** out) {
       return MPTV_ERR_NODEV;
     }
     if (e == cudaSuccess) { d.sm_count = prop.multiProcessorCount; e = kernels_init_device(); }
+    if (e == cudaSuccess) e = trie_init_device();
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
     for (int s = 0; s < kSlots && e == cudaSuccess; s++) e = cudaStreamCreateWithFlags(&d.slot[s].stream, cudaStreamNonBlocking);
     for (int k = 0; k < 6 && e == cudaSuccess; k++) e = cudaEventCreate(&d.ev[k]);
@@ -225,6 +137,7 @@ void mptv_destroy(mptv_ctx* ctx) {
     cudaDeviceSynchronize();
     d.digests.release(); d.meta.release(); d.order.release(); d.bins.release();
     for (int k = 0; k < kSlots; k++) d.slot[k].release();
+    d.rb.release();
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
     if (d.stream) cudaStreamDestroy(d.stream);
   }
@@ -282,7 +195,7 @@ int mptv_keccak256_batch_device(mptv_ctx* ctx, int dev_index, const uint8_t* nod
   CK(cudaEventRecord(d.ev[0], st));
   const uint32_t* ord = nullptr;
   if (ctx->binning) {
-    CK(launch_bin_nodes(node_len, n_nodes, d.bins.as<uint32_t>(), d.order.as<uint32_t>(), st));
+    CK(launch_bin_nodes(node_len, nullptr, n_nodes, d.bins.as<uint32_t>(), d.order.as<uint32_t>(), st));
     ord = d.order.as<uint32_t>();
   }
   CK(cudaEventRecord(d.ev[1], st));
@@ -524,7 +437,7 @@ int mptv_keccak256_batch(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node
   CK(cudaMemcpyAsync(s.node_len.p, node_len, 4 * n_nodes, cudaMemcpyHostToDevice, st));
   const uint32_t* ord = nullptr;
   if (ctx->binning) {
-    CK(launch_bin_nodes(s.node_len.as<uint32_t>(), n_nodes, s.bins.as<uint32_t>(), s.order.as<uint32_t>(), st));
+    CK(launch_bin_nodes(s.node_len.as<uint32_t>(), nullptr, n_nodes, s.bins.as<uint32_t>(), s.order.as<uint32_t>(), st));
     ord = s.order.as<uint32_t>();
   }
   CK(launch_keccak256_nodes(s.node_bytes.as<uint8_t>(), 0, s.node_off.as<uint64_t>(), s.node_len.as<uint32_t>(), ord,

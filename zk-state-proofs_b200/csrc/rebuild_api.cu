@@ -1,0 +1,248 @@
+// rebuild_api.cu -- C ABI of the trie rebuild (include/mptv.h: mptv_trie_roots*): the host-side
+// driver of the level-synchronous K4 pipeline in rebuild_kernels.cu.  Replaces the call sequence
+// EthTrie::new / insert x n / root_hash of /root/reference/trie-utils/src/proofs/transaction.rs:41-66
+// and proofs/receipt.rs:49-84 for a batch of independent tries.  No CPU fallback: every hash, every
+// RLP byte and the trie structure itself are produced on the device.
+#include <string.h>
+
+#include <thread>
+#include <vector>
+
+#include "ctx.h"
+
+using namespace mptv;
+
+namespace {
+
+int rebuild_on_device(mptv_ctx* ctx, Device& d, const TrieBatchDev& in, uint8_t* roots32, cudaStream_t st) {
+  Rebuild& rb = d.rb;
+  if (!rb.ev_begin) {
+    CK(cudaEventCreate(&rb.ev_begin));
+    CK(cudaEventCreate(&rb.ev_struct));
+    CK(cudaEventCreate(&rb.ev_end));
+  }
+  const size_t N = (size_t)in.n_items, T = in.n_tries;
+  CK(rb.sum.reserve(sizeof(TrieSummary)));
+  CK(rb.h_sum.reserve(sizeof(TrieSummary)));
+  CK(rb.rec.reserve(sizeof(uint4) * 3 * N + 16));
+  CK(rb.off.reserve(8 * 3 * N + 8));
+  CK(rb.len.reserve(4 * 3 * N + 4));
+  CK(rb.digests.reserve(32 * 3 * N + 32));
+  CK(rb.lvl_list.reserve(4 * 3 * N + 4));
+  CK(rb.tcount.reserve(4 * T + 4));
+  CK(rb.bins.reserve(2 * kNumBins * sizeof(uint32_t)));
+  TrieWork w;
+  w.rec = rb.rec.as<uint4>(); w.off = rb.off.as<uint64_t>(); w.len = rb.len.as<uint32_t>();
+  w.digests = rb.digests.as<uint8_t>(); w.tcount = rb.tcount.as<uint32_t>(); w.lvl_list = rb.lvl_list.as<uint32_t>();
+  w.sum = rb.sum.as<TrieSummary>();
+  TrieSummary* hs = reinterpret_cast<TrieSummary*>(rb.h_sum.p);
+
+  CK(cudaEventRecord(rb.ev_begin, st));
+  // ---- pass 0: largest trie / longest key (sizes the shared-memory sort; refuses what K4 cannot hold)
+  CK(launch_trie_scan_input(in, w.sum, st));
+  CK(cudaMemcpyAsync(hs, w.sum, sizeof(TrieSummary), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (hs->max_items > (uint32_t)kTrieMaxItems || hs->max_key_len > (uint32_t)kTrieMaxKeyLen) {
+    ctx->err = "mptv_trie_roots: a trie has more than 8192 items or a key longer than 32 bytes";
+    return MPTV_ERR_ARG;
+  }
+  // ---- pass 1: structure, exact node sizes, level lists
+  CK(launch_trie_structure(in, w, hs->max_items, st));
+  CK(cudaMemcpyAsync(hs, w.sum, sizeof(TrieSummary), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventRecord(rb.ev_struct, st));
+  CK(rb.arena.reserve((size_t)hs->arena_bytes + 64));
+  uint32_t levels = 0, max_level_nodes = 0;
+  for (int h = 0; h < kMaxLevels; h++) {
+    const uint32_t c = hs->lvl_count[2 * h] + hs->lvl_count[2 * h + 1];
+    if (c) levels = h + 1;
+    if (hs->lvl_count[2 * h] > max_level_nodes) max_level_nodes = hs->lvl_count[2 * h];
+  }
+  CK(rb.order.reserve(4 * (size_t)max_level_nodes + 4));
+  while (rb.lvl_ev.size() < 3 * (size_t)levels) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    rb.lvl_ev.push_back(e);
+  }
+  // ---- pass 2: bottom-up, one encode launch + one hash launch per level
+  uint32_t start = 0, klaunch = 0, olaunch = 4;
+  for (uint32_t h = 0; h < levels; h++) {
+    const uint32_t nh = hs->lvl_count[2 * h], ni = hs->lvl_count[2 * h + 1];
+    const uint32_t* list = w.lvl_list + start;
+    CK(cudaEventRecord(rb.lvl_ev[3 * h], st));
+    CK(launch_trie_encode(in, w, list, nh + ni, rb.arena.as<uint8_t>(), st));
+    if (nh + ni) olaunch++;
+    CK(cudaEventRecord(rb.lvl_ev[3 * h + 1], st));
+    if (nh) {
+      const uint32_t* ord = list;
+      if (ctx->binning && nh >= 4096) {  // leaf levels: converge the warps on equal rate-block counts
+        CK(launch_bin_nodes(w.len, list, nh, rb.bins.as<uint32_t>(), rb.order.as<uint32_t>(), st));
+        ord = rb.order.as<uint32_t>();
+        olaunch += 3;
+      }
+      CK(launch_keccak256_nodes(rb.arena.as<uint8_t>(), 0, w.off, w.len, ord, nh, w.digests, nullptr, d.sm_count, st));
+      klaunch++;
+    }
+    CK(cudaEventRecord(rb.lvl_ev[3 * h + 2], st));
+    start += nh + ni;
+  }
+  CK(launch_trie_roots(in, w, roots32, st));
+  olaunch++;
+  CK(cudaEventRecord(rb.ev_end, st));
+  rb.levels = levels; rb.keccak_launches = klaunch; rb.other_launches = olaunch; rb.have_timing = true;
+  rb.n_nodes = hs->n_nodes; rb.n_hashed = hs->nodes_hashed; rb.n_perm = hs->perms; rb.arena_bytes = hs->arena_bytes;
+  return MPTV_OK;
+}
+
+// one device's share [t0, t1) of a host batch, in chunks of about `chunk` value bytes
+int rebuild_slice(mptv_ctx* ctx, Device& d, const mptv_kv_batch* in, uint8_t* roots32, uint64_t t0, uint64_t t1) {
+  if (t1 <= t0) return MPTV_OK;
+  CK(cudaSetDevice(d.id));
+  Rebuild& rb = d.rb;
+  cudaStream_t st = d.stream;
+  const uint64_t chunk = 4ull << 30;
+  for (uint64_t cs = t0; cs < t1;) {
+    uint64_t ce = cs + 1;
+    const uint32_t i0 = in->trie_first[cs];
+    const uint64_t b0 = i0 < in->n_items ? in->value_off[i0] : in->value_bytes_len;
+    while (ce < t1) {
+      const uint32_t ie = in->trie_first[ce + 1];
+      const uint64_t be = ie < in->n_items ? in->value_off[ie] : in->value_bytes_len;
+      if (be - b0 > chunk) break;
+      ce++;
+    }
+    const uint32_t i1 = in->trie_first[ce];
+    const uint64_t ni = i1 - i0, nt = ce - cs;
+    uint64_t b1 = b0;
+    if (ni) b1 = in->value_off[i1 - 1] + in->value_len[i1 - 1];
+    b1 = (b1 + 15) & ~15ull;
+    if (b1 > ((in->value_bytes_len + 15) & ~15ull)) return MPTV_ERR_ARG;
+    const uint32_t k0 = in->key_off[i0], k1 = in->key_off[i1];
+    // rebased copies of the index arrays (offsets relative to this chunk)
+    std::vector<uint32_t> koff(ni + 1), tfirst(nt + 1);
+    std::vector<uint64_t> voff(ni ? ni : 1);
+    for (uint64_t i = 0; i <= ni; i++) koff[i] = in->key_off[i0 + i] - k0;
+    for (uint64_t i = 0; i < ni; i++) {
+      const uint64_t o = in->value_off[i0 + i];
+      if (o & 15) return MPTV_ERR_ALIGN;
+      if (o < b0 || o + in->value_len[i0 + i] > b1) return MPTV_ERR_ARG;
+      voff[i] = o - b0;
+    }
+    for (uint64_t t = 0; t <= nt; t++) tfirst[t] = in->trie_first[cs + t] - i0;
+    CK(rb.in_key_bytes.reserve((size_t)(k1 - k0) + 16));
+    CK(rb.in_key_off.reserve(4 * (ni + 1)));
+    CK(rb.in_value_bytes.reserve((size_t)(b1 - b0) + 16));
+    CK(rb.in_value_off.reserve(8 * ni + 8));
+    CK(rb.in_value_len.reserve(4 * ni + 4));
+    CK(rb.in_trie_first.reserve(4 * (nt + 1)));
+    CK(rb.out_roots.reserve(32 * nt));
+    CK(rb.h_roots.reserve(32 * nt));
+    if (k1 > k0) CK(cudaMemcpyAsync(rb.in_key_bytes.p, in->key_bytes + k0, k1 - k0, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(rb.in_key_off.p, koff.data(), 4 * (ni + 1), cudaMemcpyHostToDevice, st));
+    uint64_t copy_end = b1 < in->value_bytes_len ? b1 : in->value_bytes_len;
+    if (copy_end > b0) CK(cudaMemcpyAsync(rb.in_value_bytes.p, in->value_bytes + b0, copy_end - b0, cudaMemcpyHostToDevice, st));
+    if (ni) {
+      CK(cudaMemcpyAsync(rb.in_value_off.p, voff.data(), 8 * ni, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(rb.in_value_len.p, in->value_len + i0, 4 * ni, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(rb.in_trie_first.p, tfirst.data(), 4 * (nt + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // the staging vectors above go out of scope per chunk
+    TrieBatchDev b;
+    b.key_bytes = rb.in_key_bytes.as<uint8_t>(); b.key_off = rb.in_key_off.as<uint32_t>();
+    b.value_bytes = rb.in_value_bytes.as<uint8_t>(); b.value_off = rb.in_value_off.as<uint64_t>();
+    b.value_len = rb.in_value_len.as<uint32_t>(); b.trie_first = rb.in_trie_first.as<uint32_t>();
+    b.n_tries = (uint32_t)nt; b.n_items = ni;
+    int rc = rebuild_on_device(ctx, d, b, rb.out_roots.as<uint8_t>(), st);
+    if (rc != MPTV_OK) return rc;
+    CK(cudaMemcpyAsync(rb.h_roots.p, rb.out_roots.p, 32 * nt, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(roots32 + 32 * cs, rb.h_roots.p, 32 * nt);
+    cs = ce;
+  }
+  return MPTV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mptv_trie_roots_device(mptv_ctx* ctx, int dev_index, const mptv_kv_batch* in, uint8_t* roots32, void* stream) {
+  if (!ctx || !in || dev_index < 0 || dev_index >= (int)ctx->dev.size()) return MPTV_ERR_ARG;
+  if (in->n_tries == 0) return MPTV_OK;
+  if (!roots32 || !in->trie_first || !in->key_off || in->n_tries > 0x7fffffffull || in->n_items > 0x50000000ull)
+    return MPTV_ERR_ARG;
+  if (in->n_items && (!in->key_bytes || !in->value_bytes || !in->value_off || !in->value_len)) return MPTV_ERR_ARG;
+  Device& d = ctx->dev[dev_index];
+  CK(cudaSetDevice(d.id));
+  cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
+  TrieBatchDev b;
+  b.key_bytes = in->key_bytes; b.key_off = in->key_off; b.value_bytes = in->value_bytes; b.value_off = in->value_off;
+  b.value_len = in->value_len; b.trie_first = in->trie_first; b.n_tries = (uint32_t)in->n_tries; b.n_items = in->n_items;
+  return rebuild_on_device(ctx, d, b, roots32, st);
+}
+
+int mptv_trie_roots(mptv_ctx* ctx, const mptv_kv_batch* in, uint8_t* roots32) {
+  if (!ctx || !in) return MPTV_ERR_ARG;
+  if (in->n_tries == 0) return MPTV_OK;
+  if (!roots32 || !in->trie_first || !in->key_off || in->n_tries > 0x7fffffffull || in->n_items > 0x50000000ull)
+    return MPTV_ERR_ARG;
+  if (in->n_items && (!in->key_bytes || !in->value_bytes || !in->value_off || !in->value_len)) return MPTV_ERR_ARG;
+  if (in->trie_first[in->n_tries] > in->n_items) return MPTV_ERR_ARG;
+  for (uint64_t t = 0; t < in->n_tries; t++)
+    if (in->trie_first[t + 1] < in->trie_first[t]) return MPTV_ERR_ARG;
+  for (uint64_t i = 0; i < in->n_items; i++)
+    if (in->key_off[i + 1] < in->key_off[i]) return MPTV_ERR_ARG;
+  for (uint64_t i = 0; i + 1 < in->n_items; i++)
+    if (in->value_off[i + 1] < in->value_off[i] + in->value_len[i]) return MPTV_ERR_ARG;  // laid out in item order
+  const int nd = (int)ctx->dev.size();
+  std::vector<uint64_t> cut(nd + 1, 0);
+  cut[nd] = in->n_tries;
+  if (nd > 1) {
+    uint64_t t = 0;
+    for (int k = 1; k < nd; k++) {
+      const uint64_t target = in->value_bytes_len / nd * k;
+      uint64_t lo = t, hi = in->n_tries;
+      while (lo < hi) {
+        const uint64_t mid = (lo + hi) / 2;
+        const uint32_t fi = in->trie_first[mid];
+        const uint64_t off = fi < in->n_items ? in->value_off[fi] : in->value_bytes_len;
+        if (off < target) lo = mid + 1; else hi = mid;
+      }
+      cut[k] = t = lo;
+    }
+  }
+  std::vector<int> rcs(nd, MPTV_OK);
+  if (nd == 1) rcs[0] = rebuild_slice(ctx, ctx->dev[0], in, roots32, cut[0], cut[1]);
+  else {
+    std::vector<std::thread> th;
+    for (int k = 0; k < nd; k++)
+      th.emplace_back([&, k] { rcs[k] = rebuild_slice(ctx, ctx->dev[k], in, roots32, cut[k], cut[k + 1]); });
+    for (auto& x : th) x.join();
+  }
+  for (int k = 0; k < nd; k++) if (rcs[k] != MPTV_OK) return rcs[k];
+  return MPTV_OK;
+}
+
+int mptv_last_rebuild_timings(mptv_ctx* ctx, int dev_index, mptv_rebuild_timings* out) {
+  if (!ctx || !out || dev_index < 0 || dev_index >= (int)ctx->dev.size()) return MPTV_ERR_ARG;
+  Device& d = ctx->dev[dev_index];
+  Rebuild& rb = d.rb;
+  memset(out, 0, sizeof *out);
+  if (!rb.have_timing) return MPTV_ERR_ARG;
+  CK(cudaSetDevice(d.id));
+  CK(cudaEventSynchronize(rb.ev_end));
+  CK(cudaEventElapsedTime(&out->structure_ms, rb.ev_begin, rb.ev_struct));
+  CK(cudaEventElapsedTime(&out->total_ms, rb.ev_begin, rb.ev_end));
+  for (uint32_t h = 0; h < rb.levels; h++) {
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, rb.lvl_ev[3 * h], rb.lvl_ev[3 * h + 1]));
+    CK(cudaEventElapsedTime(&b, rb.lvl_ev[3 * h + 1], rb.lvl_ev[3 * h + 2]));
+    out->encode_ms += a;
+    out->keccak_ms += b;
+  }
+  out->n_nodes = rb.n_nodes; out->n_hashed = rb.n_hashed; out->n_perm = rb.n_perm; out->arena_bytes = rb.arena_bytes;
+  out->levels = rb.levels; out->keccak_launches = rb.keccak_launches; out->other_launches = rb.other_launches;
+  return MPTV_OK;
+}
+
+}  // extern "C"

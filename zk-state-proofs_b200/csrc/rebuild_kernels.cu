@@ -1,0 +1,547 @@
+// rebuild_kernels.cu -- K4: level-synchronous Merkle-Patricia-Trie rebuild (root hashes, node arena).
+//
+// Replaces, for a whole batch of tries at once, what trie-utils does per block with eth_trie:
+//     let mut trie = EthTrie::new(memdb);
+//     for (i, tx) in txs { trie.insert(&rlp(i), &tx.eip2718_encoded()) }      transaction.rs:41-63
+//     trie.root_hash()                                                         transaction.rs:66
+//   /root/reference/trie-utils/src/proofs/transaction.rs:41-68, proofs/receipt.rs:49-86
+//
+// The MPT of a key/value set is unique, so the reference's sequential node surgery (insert_at:
+// leaf split, extension split, branch descent) is not replayed.  Instead:
+//   k_trie_structure  one CTA per trie: bitonic sort of the items by (key, insertion index),
+//                     last-write-wins + delete filter (insert(k, b"") removes k), adjacent-key LCP
+//                     in nibbles, then the trie skeleton in BFS order -- a branch per LCP interval,
+//                     an extension where a branch sits more than one nibble below its parent, a
+//                     leaf per key, a key that ends at a branch is that branch's value -- and, in
+//                     reverse BFS order, every node's exact encoded length and height.
+//   k_trie_level_*    counting sort of all nodes of the batch by (height, hashed?)
+//   k_trie_encode     per level, bottom-up: one warp per node writes its RLP encoding into the node
+//                     arena (children < 32 bytes embedded, others referenced by the digest that the
+//                     previous level's Keccak launch produced; commit()/write_node semantics)
+//   K0 + K1           (keccak_kernels.cu) hash all >= 32-byte nodes of the level in one launch
+// The leaf level carries > 95 % of the bytes and permutations of a tx / receipt trie.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace mptv {
+
+namespace {
+
+// ---- record packing: x = kind | height << 8 | path_start << 16 | path_len << 24
+//                      y = item (global item index; leaf: its key/value, ext: any key below it,
+//                          branch: the key whose value sits in the branch, or kNoItem)
+//                      z = first child (global node id); children are consecutive in BFS order
+//                      w = occupancy mask (branch) | hashed << 16
+constexpr uint32_t kNoItem = 0xffffffffu;
+enum : uint32_t { kTLeaf = 1, kTExt = 2, kTBranch = 3 };
+
+__device__ __forceinline__ uint32_t rec_kind(const uint4& r) { return r.x & 0xffu; }
+__device__ __forceinline__ uint32_t rec_height(const uint4& r) { return (r.x >> 8) & 0xffu; }
+__device__ __forceinline__ uint32_t rec_ps(const uint4& r) { return (r.x >> 16) & 0xffu; }
+__device__ __forceinline__ uint32_t rec_pl(const uint4& r) { return r.x >> 24; }
+__device__ __forceinline__ uint32_t rec_mask(const uint4& r) { return r.w & 0xffffu; }
+__device__ __forceinline__ uint32_t rec_hashed(const uint4& r) { return (r.w >> 16) & 1u; }
+
+// ---- RLP sizes (alloy-rlp / eth_trie write_node)
+__device__ __forceinline__ uint32_t hdr_size(uint32_t n) {
+  return n < 56 ? 1u : (n < 256 ? 2u : (n < 65536 ? 3u : (n < (1u << 24) ? 4u : 5u)));
+}
+__device__ __forceinline__ uint32_t str_item_size(uint32_t n, uint32_t first) {
+  return (n == 1 && first < 0x80) ? 1u : hdr_size(n) + n;
+}
+// hex-prefix encoded path of pl nibbles: pl/2 + 1 bytes (<= 33); a single byte is < 0x80 (flags <= 3)
+__device__ __forceinline__ uint32_t hp_item_size(uint32_t pl) { return pl < 2 ? 1u : 2u + pl / 2; }
+__device__ __forceinline__ uint32_t ref_size(uint32_t child_len) { return child_len < 32 ? child_len : 33u; }
+// payload length of a list whose whole encoding is `len` bytes
+__device__ __forceinline__ uint32_t payload_of(uint32_t len) {
+  return len - 1 < 56 ? len - 1 : (len - 2 < 256 ? len - 2 : (len - 3 < 65536 ? len - 3 : (len - 4 < (1u << 24) ? len - 4 : len - 5)));
+}
+__device__ __forceinline__ uint32_t put_hdr(uint8_t* o, uint32_t n, bool list) {
+  const uint32_t base = list ? 0xC0u : 0x80u;
+  if (n < 56) { o[0] = (uint8_t)(base + n); return 1; }
+  const uint32_t k = hdr_size(n) - 1;
+  o[0] = (uint8_t)(base + 55 + k);
+  for (uint32_t i = 0; i < k; i++) o[1 + i] = (uint8_t)(n >> (8 * (k - 1 - i)));
+  return 1 + k;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ input scan
+__global__ void __launch_bounds__(256) k_trie_scan_input(const TrieBatchDev in, TrieSummary* sum) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t mk = 0, mn = 0;
+  if (i < in.n_items) mk = in.key_off[i + 1] - in.key_off[i];
+  if (i < in.n_tries) mn = in.trie_first[i + 1] - in.trie_first[i];
+  for (int o = 16; o; o >>= 1) {
+    mk = max(mk, __shfl_xor_sync(0xffffffffu, mk, o));
+    mn = max(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (mk) atomicMax(&sum->max_key_len, mk);
+    if (mn) atomicMax(&sum->max_items, mn);
+  }
+}
+
+// ------------------------------------------------------------------ structure
+namespace {
+
+struct SortView {
+  uint64_t* pre;  // first 8 key bytes, big-endian, zero padded
+  uint32_t* idx;  // local item index (insertion order); kNoItem = padding, sorts last
+  uint8_t* kl;    // key length in bytes
+};
+
+// strict "a sorts after b" over (key bytes, key length, insertion index)
+__device__ bool sort_greater(const SortView& v, uint32_t a, uint32_t b, const uint8_t* key_bytes,
+                             const uint32_t* key_off /* of the trie's first item */) {
+  const uint32_t ia = v.idx[a], ib = v.idx[b];
+  if (ia == kNoItem || ib == kNoItem) return ia == kNoItem && ib != kNoItem;
+  const uint64_t pa = v.pre[a], pb = v.pre[b];
+  if (pa != pb) return pa > pb;
+  const uint32_t la = v.kl[a], lb = v.kl[b];
+  if (la > 8 && lb > 8) {
+    const uint8_t* ka = key_bytes + key_off[ia];
+    const uint8_t* kb = key_bytes + key_off[ib];
+    const uint32_t n = la < lb ? la : lb;
+    for (uint32_t i = 8; i < n; i++) {
+      const uint32_t x = ka[i], y = kb[i];
+      if (x != y) return x > y;
+    }
+  }
+  if (la != lb) return la > lb;  // equal up to the shorter key: the prefix sorts first
+  return ia > ib;
+}
+
+__device__ bool keys_equal(const SortView& v, uint32_t a, uint32_t b, const uint8_t* key_bytes,
+                           const uint32_t* key_off) {
+  if (v.pre[a] != v.pre[b] || v.kl[a] != v.kl[b]) return false;
+  const uint32_t l = v.kl[a];
+  const uint8_t* ka = key_bytes + key_off[v.idx[a]];
+  const uint8_t* kb = key_bytes + key_off[v.idx[b]];
+  for (uint32_t i = 8; i < l; i++)
+    if (ka[i] != kb[i]) return false;
+  return true;
+}
+
+// nibble i of sorted key j
+__device__ __forceinline__ uint32_t key_nib(const SortView& v, uint32_t j, uint32_t i, const uint8_t* key_bytes,
+                                            const uint32_t* key_off) {
+  const uint32_t by = i >> 1;
+  const uint32_t b = by < 8 ? (uint32_t)(v.pre[j] >> (56 - 8 * by)) & 0xffu : key_bytes[key_off[v.idx[j]] + by];
+  return (i & 1) ? (b & 15u) : (b >> 4);
+}
+
+// common prefix of sorted keys j and j+1 in nibbles
+__device__ uint32_t lcp_nibbles(const SortView& v, uint32_t j, const uint8_t* key_bytes, const uint32_t* key_off) {
+  const uint32_t la = v.kl[j], lb = v.kl[j + 1];
+  const uint32_t cap = 2 * (la < lb ? la : lb);
+  const uint64_t x = v.pre[j] ^ v.pre[j + 1];
+  uint32_t c;
+  if (x) c = (uint32_t)__clzll((long long)x) >> 2;
+  else {
+    c = 16;
+    if (la > 8 && lb > 8) {
+      const uint8_t* ka = key_bytes + key_off[v.idx[j]];
+      const uint8_t* kb = key_bytes + key_off[v.idx[j + 1]];
+      const uint32_t n = la < lb ? la : lb;
+      uint32_t i = 8;
+      while (i < n && ka[i] == kb[i]) i++;
+      c = 2 * i;
+      if (i < n && ((ka[i] ^ kb[i]) >> 4) == 0) c++;
+    }
+  }
+  return c < cap ? c : cap;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kTrieThreads) k_trie_structure(const TrieBatchDev in, const TrieWork w, uint32_t cap) {
+  extern __shared__ __align__(16) uint8_t tsm[];
+  SortView v;
+  v.pre = reinterpret_cast<uint64_t*>(tsm);
+  v.idx = reinterpret_cast<uint32_t*>(tsm + 8ull * cap);
+  v.kl = tsm + 12ull * cap;
+  uint8_t* lcp = tsm + 13ull * cap;
+  __shared__ uint32_t s_hist[2 * kMaxLevels];
+  __shared__ uint32_t s_scan[kTrieThreads];
+  __shared__ uint32_t s_m, s_count;
+  __shared__ unsigned long long s_arena_base;
+
+  const uint32_t t = blockIdx.x;
+  const uint32_t first = in.trie_first[t];
+  const uint32_t n = in.trie_first[t + 1] - first;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t* koff = in.key_off + first;  // local item i: key_bytes[koff[i] .. koff[i+1])
+  const uint32_t base = 3u * first;           // node ids of this trie: base + BFS index
+  for (uint32_t i = tid; i < 2 * kMaxLevels; i += kTrieThreads) s_hist[i] = 0;
+  if (n == 0) {
+    if (tid == 0) w.tcount[t] = 0;
+    return;
+  }
+  uint32_t np2 = 2;
+  while (np2 < n) np2 <<= 1;
+
+  // ---- load: key prefixes, lengths, identity permutation
+  for (uint32_t i = tid; i < np2; i += kTrieThreads) {
+    uint64_t p = ~0ull;
+    uint32_t id = kNoItem, l = 255;
+    if (i < n) {
+      id = i;
+      l = koff[i + 1] - koff[i];
+      p = 0;
+      const uint8_t* k = in.key_bytes + koff[i];
+      for (uint32_t b = 0; b < 8 && b < l; b++) p |= (uint64_t)k[b] << (56 - 8 * b);
+    }
+    v.pre[i] = p; v.idx[i] = id; v.kl[i] = (uint8_t)l;
+  }
+  __syncthreads();
+
+  // ---- bitonic sort by (key, insertion index)
+  for (uint32_t k = 2; k <= np2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = tid; i < np2; i += kTrieThreads) {
+        const uint32_t x = i ^ j;
+        if (x > i) {
+          const bool up = (i & k) == 0;
+          if (sort_greater(v, i, x, in.key_bytes, koff) == up) {
+            const uint64_t p = v.pre[i]; v.pre[i] = v.pre[x]; v.pre[x] = p;
+            const uint32_t q = v.idx[i]; v.idx[i] = v.idx[x]; v.idx[x] = q;
+            const uint8_t l = v.kl[i]; v.kl[i] = v.kl[x]; v.kl[x] = l;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- last write wins, empty value deletes; compact the live keys in place
+  {
+    const uint32_t seg = (n + kTrieThreads - 1) / kTrieThreads;  // <= kTrieMaxItems / kTrieThreads
+    const uint32_t s0 = tid * seg, s1 = min(n, s0 + seg);
+    uint64_t kp[kTrieMaxItems / kTrieThreads];
+    uint32_t ki[kTrieMaxItems / kTrieThreads];
+    uint8_t kn[kTrieMaxItems / kTrieThreads];
+    uint32_t cnt = 0;
+    for (uint32_t s = s0; s < s1; s++) {
+      const bool last = (s + 1 == n) || !keys_equal(v, s, s + 1, in.key_bytes, koff);
+      if (last && in.value_len[first + v.idx[s]] != 0) {
+        kp[cnt] = v.pre[s]; ki[cnt] = v.idx[s]; kn[cnt] = v.kl[s];
+        cnt++;
+      }
+    }
+    s_scan[tid] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t acc = 0;
+      for (uint32_t i = 0; i < kTrieThreads; i++) { const uint32_t c = s_scan[i]; s_scan[i] = acc; acc += c; }
+      s_m = acc;
+    }
+    __syncthreads();
+    const uint32_t o = s_scan[tid];
+    for (uint32_t c = 0; c < cnt; c++) { v.pre[o + c] = kp[c]; v.idx[o + c] = ki[c]; v.kl[o + c] = kn[c]; }
+    __syncthreads();
+  }
+  const uint32_t m = s_m;
+  for (uint32_t j = tid; j + 1 < m; j += kTrieThreads) lcp[j] = (uint8_t)lcp_nibbles(v, j, in.key_bytes, koff);
+  __syncthreads();
+
+  // ---- skeleton (thread 0): BFS over key ranges; w.off doubles as the queue (lo | hi << 16 | depth << 32)
+  if (tid == 0) {
+    uint32_t head = 0, tail = 0;
+    if (m) w.off[base + tail++] = (uint64_t)m << 16;
+    while (head < tail) {
+      const uint64_t q = w.off[base + head];
+      const uint32_t id = head++;
+      const uint32_t lo = (uint32_t)q & 0xffffu, hi = (uint32_t)(q >> 16) & 0xffffu, d = (uint32_t)(q >> 32);
+      uint4 r = make_uint4(0, kNoItem, 0, 0);
+      if (hi - lo == 1) {
+        r.x = kTLeaf | (d << 16) | ((2u * v.kl[lo] - d) << 24);
+        r.y = first + v.idx[lo];
+      } else {
+        uint32_t c = 255;
+        for (uint32_t j = lo; j + 1 < hi; j++) c = min(c, (uint32_t)lcp[j]);
+        if (c > d) {
+          r.x = kTExt | (d << 16) | ((c - d) << 24);
+          r.y = first + v.idx[lo];
+          r.z = base + tail;
+          w.off[base + tail++] = (uint64_t)lo | ((uint64_t)hi << 16) | ((uint64_t)c << 32);
+        } else {
+          uint32_t l2 = lo;
+          if (2u * v.kl[lo] == d) { r.y = first + v.idx[lo]; l2 = lo + 1; }  // this key ends here: branch value
+          r.x = kTBranch | (d << 16);
+          r.z = base + tail;
+          uint32_t mask = 0, gs = l2;
+          for (uint32_t j = l2; j < hi; j++) {
+            if (j + 1 == hi || lcp[j] == d) {
+              mask |= 1u << key_nib(v, gs, d, in.key_bytes, koff);
+              w.off[base + tail++] = (uint64_t)gs | ((uint64_t)(j + 1) << 16) | ((uint64_t)(d + 1) << 32);
+              gs = j + 1;
+            }
+          }
+          r.w = mask;
+        }
+      }
+      w.rec[base + id] = r;
+    }
+    // ---- reverse BFS order: exact encoded length, height, arena offset (relative), level histogram
+    const uint32_t count = tail;
+    unsigned long long bytes = 0, perms = 0, hashed_nodes = 0;
+    for (uint32_t id = count; id-- > 0;) {
+      uint4 r = w.rec[base + id];
+      uint32_t payload, h = 0;
+      if (rec_kind(r) == kTLeaf) {
+        const uint32_t vl = in.value_len[r.y];
+        const uint32_t v0 = vl == 1 ? in.value_bytes[in.value_off[r.y]] : 0u;
+        payload = hp_item_size(rec_pl(r)) + str_item_size(vl, v0);
+      } else if (rec_kind(r) == kTExt) {
+        payload = hp_item_size(rec_pl(r)) + ref_size(w.len[r.z]);
+        h = rec_height(w.rec[r.z]) + 1;
+      } else {
+        const uint32_t mask = rec_mask(r), nc = __popc(mask);
+        payload = 16 - nc;
+        for (uint32_t c = 0; c < nc; c++) {
+          payload += ref_size(w.len[r.z + c]);
+          h = max(h, rec_height(w.rec[r.z + c]) + 1);
+        }
+        if (r.y == kNoItem) payload += 1;
+        else {
+          const uint32_t vl = in.value_len[r.y];
+          payload += str_item_size(vl, vl == 1 ? in.value_bytes[in.value_off[r.y]] : 0u);
+        }
+      }
+      const uint32_t len = hdr_size(payload) + payload;
+      const uint32_t hashed = (len >= 32 || id == 0) ? 1u : 0u;  // write_node: >= 32 bytes by hash; the root always
+      r.x |= h << 8;
+      r.w |= hashed << 16;
+      w.rec[base + id] = r;
+      w.len[base + id] = len;
+      w.off[base + id] = bytes;
+      bytes += (len + 15u) & ~15u;
+      if (hashed) { perms += len / 136u + 1u; hashed_nodes++; }
+      s_hist[2 * h + (hashed ? 0 : 1)]++;
+    }
+    s_count = count;
+    w.tcount[t] = count;
+    s_arena_base = atomicAdd(&w.sum->arena_bytes, bytes);
+    atomicAdd(&w.sum->perms, perms);
+    atomicAdd(&w.sum->nodes_hashed, hashed_nodes);
+    atomicAdd(&w.sum->n_nodes, (unsigned long long)count);
+  }
+  __syncthreads();
+  const uint32_t count = s_count;
+  const unsigned long long ab = s_arena_base;
+  for (uint32_t id = tid; id < count; id += kTrieThreads) w.off[base + id] += ab;
+  for (uint32_t i = tid; i < 2 * kMaxLevels; i += kTrieThreads)
+    if (s_hist[i]) atomicAdd(&w.sum->lvl_count[i], s_hist[i]);
+}
+
+// ------------------------------------------------------------------ level lists
+__global__ void k_trie_level_scan(TrieSummary* sum) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int i = 0; i < 2 * kMaxLevels; i++) { sum->lvl_cursor[i] = acc; acc += sum->lvl_count[i]; }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_trie_level_scatter(const TrieBatchDev in, const TrieWork w) {
+  __shared__ uint32_t cnt[2 * kMaxLevels];
+  __shared__ uint32_t start[2 * kMaxLevels];
+  const uint32_t t = blockIdx.x, tid = threadIdx.x;
+  const uint32_t count = w.tcount[t];
+  if (count == 0) return;
+  const uint32_t base = 3u * in.trie_first[t];
+  for (uint32_t i = tid; i < 2 * kMaxLevels; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  for (uint32_t id = tid; id < count; id += blockDim.x) {
+    const uint4 r = w.rec[base + id];
+    atomicAdd(&cnt[2 * rec_height(r) + (rec_hashed(r) ? 0 : 1)], 1u);
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < 2 * kMaxLevels; i += blockDim.x) {
+    if (cnt[i]) start[i] = atomicAdd(&w.sum->lvl_cursor[i], cnt[i]);
+    cnt[i] = 0;
+  }
+  __syncthreads();
+  for (uint32_t id = tid; id < count; id += blockDim.x) {
+    const uint4 r = w.rec[base + id];
+    const uint32_t k = 2 * rec_height(r) + (rec_hashed(r) ? 0 : 1);
+    w.lvl_list[start[k] + atomicAdd(&cnt[k], 1u)] = base + id;
+  }
+}
+
+// ------------------------------------------------------------------ encode
+namespace {
+
+// nibble i of item's key
+__device__ __forceinline__ uint32_t item_nib(const uint8_t* key, uint32_t i) {
+  const uint32_t b = key[i >> 1];
+  return (i & 1) ? (b & 15u) : (b >> 4);
+}
+
+// byte i of the hex-prefix encoding of nibbles [ps, ps+pl) of key (Nibbles::encode_compact)
+__device__ __forceinline__ uint32_t hp_byte(const uint8_t* key, uint32_t ps, uint32_t pl, bool leaf, uint32_t i) {
+  const uint32_t odd = pl & 1u;
+  if (i == 0) return (leaf ? 0x20u : 0u) | (odd ? (0x10u | item_nib(key, ps)) : 0u);
+  const uint32_t q = ps + odd + 2 * (i - 1);
+  return (item_nib(key, q) << 4) | item_nib(key, q + 1);
+}
+
+// warp-cooperative copy of n bytes from a 4-byte aligned src to an arbitrarily aligned dst;
+// src must be readable up to the next multiple of 4 after src + n
+__device__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane) {
+  uint32_t hb = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;
+  if (hb > n) hb = n;
+  if (lane < hb) dst[lane] = src[lane];
+  const uint32_t nw = (n - hb) >> 2;
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + hb);
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(src);
+  const uint32_t sh = 8u * hb;  // src byte hb + 4w sits hb bytes into word w
+  for (uint32_t k = lane; k < nw; k += 32) {
+    const uint32_t a = __ldg(sw + k);
+    const uint32_t b = hb ? __ldg(sw + k + 1) : 0u;
+    dw[k] = __funnelshift_r(a, b, sh);
+  }
+  const uint32_t done = hb + 4u * nw;
+  if (lane < n - done) dst[done + lane] = src[done + lane];
+}
+
+// RLP string item for a value (leaf item 1 / branch item 16), written by the whole warp
+__device__ uint32_t warp_put_value(uint8_t* dst, const uint8_t* val, uint32_t vl, uint32_t lane) {
+  const uint32_t v0 = vl ? val[0] : 0u;
+  if (vl == 1 && v0 < 0x80) {
+    if (lane == 0) dst[0] = (uint8_t)v0;
+    return 1;
+  }
+  const uint32_t h = hdr_size(vl);
+  if (lane == 0) put_hdr(dst, vl, false);
+  warp_copy(dst + h, val, vl, lane);
+  return h + vl;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256) k_trie_encode(const TrieBatchDev in, const TrieWork w, const uint32_t* __restrict__ list,
+                                                     uint32_t n_list, uint8_t* __restrict__ arena) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wi >= n_list) return;
+  const uint32_t node = list[wi];
+  const uint4 r = w.rec[node];
+  const uint32_t len = w.len[node];
+  uint8_t* dst = arena + w.off[node];
+  const uint32_t kind = rec_kind(r);
+  if (kind == kTLeaf || kind == kTExt) {
+    const uint8_t* key = in.key_bytes + in.key_off[r.y];
+    const uint32_t ps = rec_ps(r), pl = rec_pl(r);
+    const uint32_t hpn = pl / 2 + 1;
+    const uint32_t pis = hp_item_size(pl);
+    const uint32_t payload = payload_of(len);
+    const uint32_t hl = len - payload;
+    if (lane == 0) {
+      put_hdr(dst, payload, true);
+      if (hpn > 1) dst[hl] = (uint8_t)(0x80 + hpn);
+    }
+    uint8_t* pp = dst + hl + (hpn > 1 ? 1 : 0);
+    for (uint32_t i = lane; i < hpn; i += 32) pp[i] = (uint8_t)hp_byte(key, ps, pl, kind == kTLeaf, i);
+    uint8_t* vp = dst + hl + pis;
+    if (kind == kTLeaf) {
+      warp_put_value(vp, in.value_bytes + in.value_off[r.y], in.value_len[r.y], lane);
+    } else {
+      const uint32_t cl = w.len[r.z];
+      if (cl < 32) { if (lane < cl) vp[lane] = arena[w.off[r.z] + lane]; }
+      else {
+        if (lane == 0) vp[0] = 0xa0;
+        vp[1 + lane] = w.digests[32ull * r.z + lane];
+      }
+    }
+  } else {
+    const uint32_t mask = rec_mask(r);
+    const uint32_t payload = payload_of(len);
+    const uint32_t hl = len - payload;
+    // lanes 0..15: child slots; lane 16: value item
+    uint32_t sz = 0, child = 0, cl = 0;
+    const bool has = lane < 16 && ((mask >> lane) & 1u);
+    if (lane < 16) {
+      if (has) { child = r.z + __popc(mask & ((1u << lane) - 1u)); cl = w.len[child]; sz = ref_size(cl); }
+      else sz = 1;
+    }
+    uint32_t vl = 0;
+    const uint8_t* val = nullptr;
+    if (r.y != kNoItem) { vl = in.value_len[r.y]; val = in.value_bytes + in.value_off[r.y]; }
+    if (lane == 16) sz = (r.y == kNoItem) ? 1u : str_item_size(vl, vl ? val[0] : 0u);
+    uint32_t incl = sz;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += x;
+    }
+    uint8_t* ip = dst + hl + (incl - sz);
+    if (lane == 0) put_hdr(dst, payload, true);
+    if (lane < 16) {
+      if (!has) ip[0] = 0x80;
+      else if (cl < 32) { const uint8_t* s = arena + w.off[child]; for (uint32_t i = 0; i < cl; i++) ip[i] = s[i]; }
+      else { ip[0] = 0xa0; const uint8_t* s = w.digests + 32ull * child; for (uint32_t i = 0; i < 32; i++) ip[1 + i] = s[i]; }
+    }
+    const uint32_t voff = __shfl_sync(0xffffffffu, incl - sz, 16);
+    if (r.y == kNoItem) { if (lane == 16) ip[0] = 0x80; }
+    else warp_put_value(dst + hl + voff, val, vl, lane);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_trie_roots(const TrieBatchDev in, const TrieWork w, uint8_t* __restrict__ roots32) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t t = i >> 3;
+  const uint32_t part = (uint32_t)i & 7u;
+  if (t >= in.n_tries) return;
+  // keccak256(rlp("")) -- EthTrie::new's root before any insert
+  const uint32_t kEmpty[8] = {0x171fe856u, 0xa655cc1bu, 0xe64583ffu, 0x6ef8c092u, 0x1be0485bu, 0xc0ad6c99u, 0xb52f6201u, 0x21b463e3u};
+  uint32_t x = kEmpty[part];
+  if (w.tcount[t]) x = reinterpret_cast<const uint32_t*>(w.digests + 32ull * (3ull * in.trie_first[t]))[part];
+  reinterpret_cast<uint32_t*>(roots32 + 32 * t)[part] = x;
+}
+
+// ------------------------------------------------------------------ host launchers
+size_t trie_structure_smem(uint32_t cap) { return 14ull * cap; }
+
+cudaError_t trie_init_device() {
+  return cudaFuncSetAttribute(k_trie_structure, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)trie_structure_smem(kTrieMaxItems));
+}
+
+cudaError_t launch_trie_scan_input(const TrieBatchDev& in, TrieSummary* sum, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(sum, 0, sizeof(TrieSummary), st);
+  if (e != cudaSuccess) return e;
+  const uint64_t n = in.n_items > in.n_tries ? in.n_items : in.n_tries;
+  if (n == 0) return cudaSuccess;
+  k_trie_scan_input<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, sum);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_trie_structure(const TrieBatchDev& in, const TrieWork& w, uint32_t max_items, cudaStream_t st) {
+  if (in.n_tries == 0) return cudaSuccess;
+  uint32_t cap = 2;
+  while (cap < max_items) cap <<= 1;
+  k_trie_structure<<<in.n_tries, kTrieThreads, trie_structure_smem(cap), st>>>(in, w, cap);
+  k_trie_level_scan<<<1, 32, 0, st>>>(w.sum);
+  k_trie_level_scatter<<<in.n_tries, 128, 0, st>>>(in, w);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_trie_encode(const TrieBatchDev& in, const TrieWork& w, const uint32_t* list, uint32_t n_list,
+                               uint8_t* arena, cudaStream_t st) {
+  if (n_list == 0) return cudaSuccess;
+  const unsigned blocks = (n_list + 7) / 8;
+  k_trie_encode<<<blocks, 256, 0, st>>>(in, w, list, n_list, arena);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_trie_roots(const TrieBatchDev& in, const TrieWork& w, uint8_t* roots32, cudaStream_t st) {
+  if (in.n_tries == 0) return cudaSuccess;
+  const uint64_t threads = (uint64_t)in.n_tries * 8;
+  k_trie_roots<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(in, w, roots32);
+  return cudaGetLastError();
+}
+
+}  // namespace mptv
