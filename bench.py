@@ -6,11 +6,16 @@
         --master-port P bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the reference's CPU path on the host cores
 
-Workload at every N (weak scaling, one process per GPU, no data-path collective): BASELINE.json
-configs[1] -- a batch of 1 M account proofs against a synthetic 10 M-account state trie (SURVEY.md
-section 8d config 2), built by workload/ (no RPC, no network).  A "step" is one pass of the whole
-verification hot path (K0 binning, K1 Keccak-256 of every node, K2a decode, K2b walk) over that
-batch.  The 3 GB node arena is far larger than L2 (126 MB), so every step streams from HBM.
+Default workload at every N (weak scaling, one process per GPU, no data-path collective):
+BASELINE.json configs[1] -- a batch of 1 M account proofs against a synthetic 10 M-account state trie
+(SURVEY.md section 8d config 2), built by workload/ (no RPC, no network).  A "step" is one pass of
+the whole verification hot path (K0 binning, K1 Keccak-256 of every node, K2a decode, K2b walk)
+over that batch.  The 3 GB node arena is far larger than L2 (126 MB), so every step streams from HBM.
+--workload selects the other BASELINE.json configs (same JSON shape):
+  config3  4 M nested account + storage-slot proofs (1 M groups of 1 + 3), 80/10/10 incl/excl/mutated
+  config4  tx + receipt trie root rebuild for 10 k blocks x 300 (metric: tries/s)
+  config5  64 M mixed account/storage proofs, strong scaling: each rank verifies 64 M / N proofs per
+           step as repeated passes over its own resident 4 M-proof pool (sampling with replacement)
 
 `value`  : proofs / s with the batch resident in HBM, CUDA events on the launch stream, max over ranks.
 `e2e`    : the same metric through the host-buffer C-ABI entry (mptv_verify_batch) from pinned host
@@ -44,8 +49,14 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"])
     ap.add_argument("--accounts", type=int, default=10_000_000)
-    ap.add_argument("--proofs", type=int, default=1_000_000)
+    ap.add_argument("--proofs", type=int, default=0, help="proofs per GPU per pass (0 = the config's size)")
+    ap.add_argument("--slots", type=int, default=1_000_000, help="slots per ERC-20 storage trie (config3/5)")
+    ap.add_argument("--tokens", type=int, default=64, help="distinct storage tries (config3/5)")
+    ap.add_argument("--total-proofs", type=int, default=64_000_000, help="config5: proofs per step over all GPUs")
+    ap.add_argument("--blocks", type=int, default=10_000, help="config4: blocks (one tx trie + one receipt trie each)")
+    ap.add_argument("--per-block", type=int, default=300)
     ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -53,19 +64,51 @@ def parse_args():
     return ap.parse_args()
 
 
+DEFAULT_PROOFS = dict(config2=1_000_000, config3=4_000_000, config5=4_000_000)
+
+
+def n_proofs_of(a):
+    return a.proofs or DEFAULT_PROOFS[a.workload]
+
+
 def workload_name(a):
-    return (f"config2: {a.proofs} account proofs vs synthetic {a.accounts}-account state trie "
-            f"(key=keccak(address), value=account RLP), seed 2")
+    if a.workload == "config2":
+        return (f"config2: {n_proofs_of(a)} account proofs vs synthetic {a.accounts}-account state trie "
+                f"(key=keccak(address), value=account RLP), seed 2")
+    if a.workload == "config3":
+        return (f"config3: {n_proofs_of(a)} nested proofs = {n_proofs_of(a) // 4} groups x (1 account proof in a "
+                f"{a.accounts}-account state trie + 3 ERC-20 slot proofs in one of {a.tokens} {a.slots}-slot storage "
+                f"tries, root taken from the verified account leaf); 80% inclusion / 10% exclusion / 10% mutated "
+                f"(7 mutators), seed 3")
+    if a.workload == "config5":
+        return (f"config5: {a.total_proofs} mixed proofs per step over all GPUs (half account, half storage with "
+                f"its account in the same shard, 2% mutated), as repeated passes over a resident "
+                f"{n_proofs_of(a)}-proof pool per GPU (sampling with replacement), seed 5")
+    return (f"config4: transaction + receipt trie root rebuild for {a.blocks} blocks x {a.per_block} "
+            f"(tx log-normal median 180 B cap 8 KB; receipts median ~1.5 KB tail 30 KB), seed 4")
 
 
 def build_batch(a, rank, pinned):
     from workload import gen
+    n = n_proofs_of(a)
     t0 = time.time()
-    trie = gen.SynthTrie(a.accounts, 2, kind=0)
-    t1 = time.time()
-    batch = gen.account_batch(trie, a.proofs, seed=2 + 1000 * rank, pinned=pinned)
+    if a.workload == "config2":
+        trie = gen.SynthTrie(a.accounts, 2, kind=0)
+        t1 = time.time()
+        batch = gen.account_batch(trie, n, seed=2 + 1000 * rank, pinned=pinned)
+        trie.close()
+    else:
+        seed = 3 if a.workload == "config3" else 5
+        state, tokens = gen.make_state_and_tokens(a.accounts, a.tokens, a.slots, seed=seed)
+        t1 = time.time()
+        if a.workload == "config3":
+            batch = gen.nested_batch(state, tokens, n // 4, seed=seed + 1000 * rank, pinned=pinned)
+        else:
+            batch = gen.mixed_batch(state, tokens, n, seed=seed + 1000 * rank, pinned=pinned)
+        state.close()
+        for t in tokens:
+            t.close()
     t2 = time.time()
-    trie.close()
     return batch, dict(trie_build_s=round(t1 - t0, 2), proofs_emit_s=round(t2 - t1, 2))
 
 
@@ -140,12 +183,42 @@ def cpu_baseline(b, n_sample, cores):
     s = sub_batch(b, n_sample)
     d = batch_dict(s)
     o.verify_batch(d, nthreads=cores, mirror=True)  # warm-up (page-in)
+    passes = 0
     t0 = time.perf_counter()
-    st, voff, vlen, pa, pd = o.verify_batch(d, nthreads=cores, mirror=True)
-    dt = time.perf_counter() - t0
+    while True:
+        st, voff, vlen, pa, pd = o.verify_batch(d, nthreads=cores, mirror=True)
+        passes += 1
+        dt = time.perf_counter() - t0
+        if dt * cores >= 12.0 or passes >= 8:  # about 10-30 s of CPU work
+            break
+    dt /= passes
     return dict(value=n_sample / dt, unit=UNIT, cores=cores, kind="port",
-                sample=f"first {n_sample} proofs of the same batch, 1 timed pass after 1 warm-up pass",
-                keccak_f_per_sec_algorithmic=pa / dt, keccak_f_per_sec_executed=pd / dt, seconds=round(dt, 3)), st, voff, vlen
+                sample=f"first {n_sample} proofs of the same batch, {passes} timed pass(es) after 1 warm-up pass",
+                keccak_f_per_sec_algorithmic=pa / dt, keccak_f_per_sec_executed=pd / dt,
+                seconds=round(dt * passes, 3)), st, voff, vlen
+
+
+def sample_size(a, n_proofs, cores):
+    n = a.cpu_sample or min(n_proofs, 62_500 * cores)
+    if a.workload in ("config3", "config5"):
+        g = 4 if a.workload == "config3" else 2
+        n -= n % g  # whole dependency groups
+    return max(n, 1)
+
+
+def rebuild_kv(a, rank, pinned):
+    """config 4: per block one transaction trie and one receipt trie (interleaved), one KvBatch"""
+    from workload import gen
+    t0 = time.time()
+    kv = gen.block_tries(a.blocks, a.per_block, "both", seed=4 + 1000 * rank, pinned=pinned)
+    return kv, dict(gen_s=round(time.time() - t0, 2))
+
+
+def sub_kv(kv, n_tries):
+    import zk_state_proofs_b200 as z
+    ni = int(kv.trie_first[n_tries])
+    return z.KvBatch(kv.key_bytes, kv.key_off[:ni + 1], kv.value_bytes, kv.value_off[:ni], kv.value_len[:ni],
+                     kv.trie_first[:n_tries + 1])
 
 
 def run_reference(a):
@@ -153,43 +226,84 @@ def run_reference(a):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    b, gen_info = build_batch(a, 0, pinned=False)
-    n_sample = a.cpu_sample or min(a.proofs, 100_000 * max(1, cores // 4))
     from oracle.pyoracle import Oracle
     o = Oracle()
-    d = batch_dict(sub_batch(b, n_sample))
+    ref_note = ("C restatement of the reference's CPU path (oracle/, mirror mode: same redundant hashing as the "
+                "Rust code) on all host cores; the Rust reference cannot be built here (no rustc)")
+    if a.workload == "config4":
+        kv, _ = rebuild_kv(a, 0, pinned=False)
+        n_sample = a.cpu_sample or min(kv.n_tries, 250 * cores)
+        d = sub_kv(kv, n_sample).as_dict()
+        run = lambda: o.trie_roots(d, nthreads=cores)[1]
+        metric, unit, what = "mpt_trie_roots_rebuilt_per_sec", "tries/s", f"first {n_sample} tries of the config-4 batch per step"
+        scaling = "weak"
+    else:
+        b, _ = build_batch(a, 0, pinned=False)
+        n_sample = sample_size(a, b.n_proofs, cores)
+        d = batch_dict(sub_batch(b, n_sample))
+        run = lambda: o.verify_batch(d, nthreads=cores, mirror=True)[3]
+        metric, unit, what = METRIC, UNIT, f"first {n_sample} proofs of the {a.workload} batch per step"
+        scaling = "strong" if a.workload == "config5" else "weak"
     for _ in range(a.warmup):
-        o.verify_batch(d, nthreads=cores, mirror=True)
+        run()
     t0 = time.perf_counter()
     pa = 0
     for _ in range(a.steps):
-        _, _, _, pa, _ = o.verify_batch(d, nthreads=cores, mirror=True)
+        pa = run()
     dt = (time.perf_counter() - t0) / a.steps
     v = n_sample / dt
-    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
-                ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u32",
+    line = dict(metric=metric, value=v, unit=unit, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                ms_per_step=dt * 1e3, higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="u32",
                 data="synthetic", impl="reference",
-                config=dict(workload=workload_name(a), reference_arm="C restatement of crypto_ops::verify_merkle_proof "
-                            "(oracle/mpt_oracle.c, mirror mode: same redundant hashing as the Rust code); the Rust "
-                            "reference cannot be built here (no rustc)", sample_proofs=n_sample),
-                cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
-                                  sample=f"first {n_sample} proofs of the config-2 batch per step"),
+                config=dict(workload=workload_name(a), reference_arm=ref_note, sample=n_sample),
+                cpu_baseline=dict(value=v, unit=unit, cores=cores, kind="port", sample=what),
                 keccak_f_per_sec=pa / dt,
-                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+                e2e=dict(value=v, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
     return 0
 
 
-def main():
-    a = parse_args()
-    if a.impl == "reference":
-        return run_reference(a)
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
-    import numpy as np
+
+def keccak_roofline(ver, n_perm, keccak_ms, alg_bytes, launches_note):
+    peaks = load_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    int_peak = max(ver.int_issue_peak(0, m) for m in (0, 2))  # lane-ops / s, measured now on this GPU
+    keccak_s = keccak_ms * 1e-3
+    ach_int = n_perm * I_PERM * 1.0 / keccak_s
+    ach_hbm = alg_bytes / keccak_s / 1e9
+    return dict(
+        kernel="k_keccak256_nodes", bound="int32_issue",
+        achieved=ach_int / 1e12, peak=int_peak / 1e12, unit="Tlaneop/s", frac=ach_int / int_peak,
+        peak_source="LOP3/SHF probe (mptv_int_issue_peak) run in this process on this GPU",
+        algorithmic_ops_per_launch=n_perm * I_PERM, launch_ms=keccak_ms, launches=launches_note,
+        keccak_f_per_sec=n_perm / keccak_s, keccak_f_per_sec_at_peak=int_peak / I_PERM,
+        hbm=dict(bound="hbm", achieved=ach_hbm, peak=hbm_peak, unit="GB/s", frac=ach_hbm / hbm_peak,
+                 peak_source="MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
+                 algorithmic_bytes_per_launch=alg_bytes),
+        traffic=TRAFFIC_NOTE.get("k_keccak256_nodes"),
+    )
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of
+# this kernel on this workload (profiles/); None until a capture of the current kernel exists
+TRAFFIC_NOTE = {}
+try:
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as _f:
+        TRAFFIC_NOTE = json.load(_f)
+except Exception:
+    pass
+
+
+def dist_setup():
     import torch
     import torch.distributed as dist
-    import zk_state_proofs_b200 as z
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -198,7 +312,152 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
 
+
+def reduce_max(x, world, dev):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return float(x)
+    t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(xs, world, dev):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return [float(x) for x in xs]
+    t = torch.tensor([float(x) for x in xs], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t.tolist()]
+
+
+def main_rebuild(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import zk_state_proofs_b200 as z
+    rank, world, local = dist_setup()
+    dev = torch.device("cuda", local)
+    ver = z.Verifier([local])
+    kv, gen_info = rebuild_kv(a, rank, pinned=True)
+    value_total = int(kv.value_len.astype(np.int64).sum())
+
+    def to_dev(x):
+        return torch.from_numpy(x.view(np.uint8) if x.dtype != np.uint8 else x).to(dev)
+    d_in = {k: to_dev(getattr(kv, k)) for k in ["key_bytes", "key_off", "value_bytes", "value_off", "value_len", "trie_first"]}
+    d_roots = torch.zeros(32 * kv.n_tries, dtype=torch.uint8, device=dev)
+    ptrs = {k: v.data_ptr() for k, v in d_in.items()}
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        ver.trie_roots_device(0, ptrs, kv.n_items, kv.n_tries, d_roots.data_ptr(), stream=stream.cuda_stream,
+                              value_bytes_len=len(kv.value_bytes))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
+    ev0.record(stream)
+    ks = []
+    for _ in range(a.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    t_end = time.time()
+    total_ms = ev0.elapsed_time(ev1)
+    tm = ver.last_rebuild_timings(0)
+    launches = (tm.keccak_launches + tm.other_launches) * a.steps
+    for _ in range(3):
+        step()
+        t = ver.last_rebuild_timings(0)
+        ks.append((t.structure_ms, t.encode_ms, t.keccak_ms, t.total_ms))
+    kavg = np.array([[tm.structure_ms, tm.encode_ms, tm.keccak_ms, tm.total_ms]] + ks).mean(axis=0)
+    clocks = sampler.stop(t_begin, t_end)
+    ms_per_step = reduce_max(total_ms / a.steps, world, dev)
+    all_tries, all_perm = reduce_sum([kv.n_tries, tm.n_perm], world, dev)
+    value = all_tries / (ms_per_step * 1e-3)
+    roots = d_roots.cpu().numpy().reshape(-1, 32)
+
+    e2e = None
+    if not a.no_e2e:
+        ver.trie_roots(kv)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(min(a.steps, 3)):
+            eroots = ver.trie_roots(kv)
+        torch.cuda.synchronize()
+        dt = reduce_max((time.perf_counter() - t0) / min(a.steps, 3), world, dev)
+        h2d = sum(int(getattr(kv, k).nbytes) for k in ["key_off", "value_bytes", "value_off", "value_len", "trie_first"]) + int(kv.key_off[-1])
+        e2e = dict(value=all_tries / dt, unit="tries/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=32 * kv.n_tries,
+                   ms_per_step=dt * 1e3, host_memory="pinned values, pageable index arrays",
+                   timer="host wall clock around the blocking C-ABI call")
+        assert (eroots == roots).all(), "host and device entries disagree"
+
+    roofline = keccak_roofline(ver, tm.n_perm, float(kavg[2]), int(tm.arena_bytes) + 32 * int(tm.n_hashed),
+                               f"{tm.keccak_launches} (one per trie level), summed")
+    line = dict(metric="mpt_trie_roots_rebuilt_per_sec", value=value, unit="tries/s", n_gpus=world, steps=a.steps,
+                warmup=max(a.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="u32", data="synthetic",
+                config=dict(workload=workload_name(a), tries_per_gpu=kv.n_tries, items_per_gpu=kv.n_items,
+                            value_bytes_per_gpu=value_total, trie_nodes_per_gpu=int(tm.n_nodes),
+                            hashed_nodes_per_gpu=int(tm.n_hashed), keccak_f_per_gpu=int(tm.n_perm), levels=int(tm.levels),
+                            l2="inputs (GBs of values per step) exceed the 126 MB L2; no flush needed",
+                            parallelism=f"{world} independent trie slices, one process per GPU, no collective", **gen_info),
+                keccak_f_per_sec=all_perm / (ms_per_step * 1e-3),
+                leaves_per_sec=all_tries * a.per_block / (ms_per_step * 1e-3),
+                kernel_ms=dict(structure=float(kavg[0]), encode=float(kavg[1]), keccak=float(kavg[2]), total=float(kavg[3])),
+                roofline=roofline, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
+    if rank == 0:
+        if world == 1 and not a.no_cpu_baseline:
+            from oracle.pyoracle import Oracle
+            o = Oracle()
+            cores = os.cpu_count() or 1
+            n_sample = a.cpu_sample or min(kv.n_tries, 250 * cores)
+            d = sub_kv(kv, n_sample).as_dict()
+            t0 = time.perf_counter()
+            oroots, pa, nh = o.trie_roots(d, nthreads=cores)
+            dt = time.perf_counter() - t0
+            same = bool((oroots == roots[:n_sample]).all())
+            line["cpu_baseline"] = dict(value=n_sample / dt, unit="tries/s", cores=cores, kind="port",
+                                        sample=f"first {n_sample} tries of the same batch, 1 timed pass",
+                                        keccak_f_per_sec=pa / dt, seconds=round(dt, 3),
+                                        gpu_results_identical_on_sample=same)
+            if not same:
+                line["parity_error"] = "GPU roots differ from the oracle on the CPU-baseline sample"
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+    if a.workload == "config4":
+        return main_rebuild(a)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import zk_state_proofs_b200 as z
+
+    rank, world, local = dist_setup()
     ver = z.Verifier([local])  # one process per GPU; the context owns this rank's device only
     if a.lanes:
         ver.set_option("lanes_per_proof", a.lanes)
@@ -206,12 +465,18 @@ def main():
     n_proofs, n_nodes, n_perm = b.n_proofs, b.n_nodes, b.n_perm()
     node_bytes_total = int(b.node_len.astype(np.int64).sum())
     dev = torch.device("cuda", local)
+    # config 5: a step = total_proofs / world proofs on this rank = `passes` passes over its resident pool
+    passes = 1
+    if a.workload == "config5":
+        passes = max(1, round(a.total_proofs / world / n_proofs))
 
     # ---- device-resident copies (plumbing only: torch owns the buffers, libmptv.so does the work)
     def to_dev(x):
         return torch.from_numpy(x.view(np.uint8) if x.dtype != np.uint8 else x).to(dev)
-    d_in = {k: to_dev(getattr(b, k)) for k in ["node_bytes", "node_off", "node_len", "proof_first", "roots",
-                                               "key_bytes", "key_off"]}
+    names = ["node_bytes", "node_off", "node_len", "proof_first", "roots", "key_bytes", "key_off"]
+    if b.root_from_proof is not None:
+        names.append("root_from_proof")
+    d_in = {k: to_dev(getattr(b, k)) for k in names}
     d_status = torch.zeros(n_proofs, dtype=torch.uint8, device=dev)
     d_voff = torch.zeros(n_proofs, dtype=torch.int64, device=dev)
     d_vlen = torch.zeros(n_proofs, dtype=torch.int32, device=dev)
@@ -223,8 +488,9 @@ def main():
     assert stream.cuda_stream != 0
 
     def step():
-        ver.verify_batch_device(0, ptrs, n_nodes, n_proofs, outp, stream=stream.cuda_stream,
-                                node_bytes_len=len(b.node_bytes))
+        for _ in range(passes):
+            ver.verify_batch_device(0, ptrs, n_nodes, n_proofs, outp, stream=stream.cuda_stream,
+                                    node_bytes_len=len(b.node_bytes))
 
     def barrier():
         if world > 1:
@@ -242,36 +508,27 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin = time.time()
     ev0.record(stream)
-    kernel_ms = dict(bin=0.0, keccak=0.0, parse=0.0, walk=0.0)
-    launches = 0
     for _ in range(a.steps):
         step()
     ev1.record(stream)
     barrier()
     t_end = time.time()
     total_ms = ev0.elapsed_time(ev1)
-    tm = ver.last_timings(0)  # per-kernel split of the LAST timed step (events on the same stream)
-    launches = (tm.keccak_launches + tm.other_launches) * a.steps
-    # extra (untimed) steps to average the per-kernel split
+    tm = ver.last_timings(0)  # per-kernel split of the LAST timed pass (events on the same stream)
+    launches = (tm.keccak_launches + tm.other_launches) * a.steps * passes
+    # extra (untimed) passes to average the per-kernel split
     ks = []
     for _ in range(3):
-        step()
+        ver.verify_batch_device(0, ptrs, n_nodes, n_proofs, outp, stream=stream.cuda_stream,
+                                node_bytes_len=len(b.node_bytes))
         t = ver.last_timings(0)
         ks.append((t.bin_ms, t.keccak_ms, t.parse_ms, t.walk_ms, t.total_ms))
     ks = np.array([[tm.bin_ms, tm.keccak_ms, tm.parse_ms, tm.walk_ms, tm.total_ms]] + ks)
     kavg = ks.mean(axis=0)
     clocks = sampler.stop(t_begin, t_end)
 
-    ms_per_step = total_ms / a.steps
-    if world > 1:
-        t = torch.tensor([ms_per_step], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_per_step = float(t.item())
-        tot = torch.tensor([float(n_proofs), float(n_perm)], device=dev, dtype=torch.float64)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        all_proofs, all_perm = float(tot[0].item()), float(tot[1].item())
-    else:
-        all_proofs, all_perm = float(n_proofs), float(n_perm)
+    ms_per_step = reduce_max(total_ms / a.steps, world, dev)
+    all_proofs, all_perm = reduce_sum([n_proofs * passes, n_perm * passes], world, dev)
     value = all_proofs / (ms_per_step * 1e-3)
 
     # ---- results of the device path, to check below
@@ -282,54 +539,29 @@ def main():
     # ---- e2e through the host-buffer C-ABI entry (pinned host memory, H2D + D2H inside)
     e2e = None
     if not a.no_e2e:
+        e_steps = a.steps if passes == 1 else 1
         for _ in range(2):
             ver.verify_batch(b)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(a.steps):
+        for _ in range(e_steps * passes):
             est, evoff, evlen = ver.verify_batch(b)
         torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / a.steps
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        h2d = sum(int(getattr(b, k).nbytes) for k in ["node_bytes", "node_off", "node_len", "proof_first", "roots",
-                                                       "key_off"]) + int(b.key_off[-1])
-        e2e = dict(value=all_proofs / dt, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=13 * n_proofs,
+        dt = reduce_max((time.perf_counter() - t0) / e_steps, world, dev)
+        h2d = sum(int(getattr(b, k).nbytes) for k in names if k != "key_bytes") + int(b.key_off[-1])
+        e2e = dict(value=all_proofs / dt, unit=UNIT, h2d_bytes_per_step=h2d * passes, d2h_bytes_per_step=13 * n_proofs * passes,
                    ms_per_step=dt * 1e3, host_memory="pinned", timer="host wall clock around the blocking C-ABI call")
         assert (est == st).all() and (evoff == voff).all() and (evlen == vlen).all(), "host and device entries disagree"
 
     # ---- roofline of the dominant kernel (K1), rank 0's device
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    int_peak = max(ver.int_issue_peak(0, m) for m in (0, 2))  # lane-ops / s, measured now on this GPU
-    keccak_s = float(kavg[1]) * 1e-3
-    ach_int = n_perm * I_PERM * 1.0 / keccak_s
-    ach_hbm = (node_bytes_total + 32 * n_nodes) / keccak_s / 1e9
-    roofline = dict(
-        kernel="k_keccak256_nodes", bound="int32_issue",
-        achieved=ach_int / 1e12, peak=int_peak / 1e12, unit="Tlaneop/s", frac=ach_int / int_peak,
-        peak_source="LOP3/SHF probe (mptv_int_issue_peak) run in this process on this GPU",
-        algorithmic_ops_per_launch=n_perm * I_PERM, launch_ms=float(kavg[1]),
-        keccak_f_per_sec=n_perm / keccak_s, keccak_f_per_sec_at_peak=int_peak / I_PERM,
-        hbm=dict(bound="hbm", achieved=ach_hbm, peak=hbm_peak, unit="GB/s", frac=ach_hbm / hbm_peak,
-                 peak_source="MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
-                 algorithmic_bytes_per_launch=node_bytes_total + 32 * n_nodes),
-        traffic=None,
-    )
+    roofline = keccak_roofline(ver, n_perm, float(kavg[1]), node_bytes_total + 32 * n_nodes, "1 per pass")
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
-                ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u32",
-                data="synthetic",
-                config=dict(workload=workload_name(a), proofs_per_gpu=n_proofs, nodes_per_gpu=n_nodes,
-                            keccak_f_per_gpu=n_perm, node_bytes_per_gpu=node_bytes_total,
-                            l2="inputs (3 GB arena per step) exceed the 126 MB L2; no flush needed",
+                ms_per_step=ms_per_step, higher_is_better=True, scaling="strong" if a.workload == "config5" else "weak",
+                vs_baseline=None, dtype="u32", data="synthetic",
+                config=dict(workload=workload_name(a), proofs_per_gpu=n_proofs, passes_per_step=passes,
+                            nodes_per_gpu=n_nodes, keccak_f_per_gpu=n_perm, node_bytes_per_gpu=node_bytes_total,
+                            l2="inputs (GBs of node bytes per pass) exceed the 126 MB L2; no flush needed",
                             parallelism=f"{world} independent proof slices, one process per GPU, no collective",
                             **gen_info),
                 keccak_f_per_sec=all_perm / (ms_per_step * 1e-3),
@@ -339,11 +571,10 @@ def main():
 
     # ---- parity + CPU baseline (rank 0, N = 1): the oracle is the checker, never the thing measured
     if rank == 0:
-        n_ok = int((st == 0).sum())
         line["verdicts"] = {z.STATUS_NAMES[i]: int(c) for i, c in enumerate(np.bincount(st, minlength=8)) if c}
         if world == 1 and not a.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_sample = a.cpu_sample or min(n_proofs, 100_000 * max(1, cores // 4))
+            n_sample = sample_size(a, n_proofs, cores)
             cb, ost, ovoff, ovlen = cpu_baseline(b, n_sample, cores)
             same = bool((ost == st[:n_sample]).all() and (ovoff == voff[:n_sample]).all() and
                         (ovlen == vlen[:n_sample]).all())

@@ -204,16 +204,23 @@ def make_state_and_tokens(n_accounts: int, n_tokens: int, n_slots: int, seed: in
 # ----------------------------------------------------------------------------- config 4: block tries
 def block_tries(n_blocks: int, per_block: int = 300, kind: str = "tx", seed: int = 4, pinned: bool = False):
     """Synthetic per-block transaction (kind="tx") or receipt (kind="receipt") tries in the KvBatch
-    layout: key = rlp(index), value = opaque EIP-2718 bytes (first byte 0x02).  Sizes per SURVEY.md
-    section 8d config 4: txs log-normal, median 180 B, capped at 8 KB; receipts median ~1.5 KB
-    (256-byte bloom + 0..40 logs), tail to 30 KB."""
+    layout, or both interleaved (kind="both": trie 2b = block b's transactions, 2b+1 = its receipts):
+    key = rlp(index), value = opaque EIP-2718 bytes (first byte 0x02).  Sizes per SURVEY.md section 8d
+    config 4: txs log-normal, median 180 B, capped at 8 KB; receipts median ~1.5 KB (256-byte bloom +
+    0..40 logs), tail to 30 KB."""
     import zk_state_proofs_b200 as z
-    rng = np.random.default_rng(seed + (0 if kind == "tx" else 1000))
-    n = n_blocks * per_block
+    rng = np.random.default_rng(seed + {"tx": 0, "receipt": 1000, "both": 2000}[kind])
+    n_tries = n_blocks * (2 if kind == "both" else 1)
+    n = n_tries * per_block
+    tx_lens = lambda k: np.clip(rng.lognormal(np.log(180.0), 0.9, k), 100, 8192).astype(np.uint32)
+    rc_lens = lambda k: np.clip(270 + rng.lognormal(np.log(1230.0), 1.0, k), 270, 30000).astype(np.uint32)
     if kind == "tx":
-        lens = np.clip(rng.lognormal(np.log(180.0), 0.9, n), 100, 8192).astype(np.uint32)
+        lens = tx_lens(n)
+    elif kind == "receipt":
+        lens = rc_lens(n)
     else:
-        lens = np.clip(270 + rng.lognormal(np.log(1230.0), 1.0, n), 270, 30000).astype(np.uint32)
+        lens = np.stack([tx_lens(n // 2).reshape(n_blocks, per_block), rc_lens(n // 2).reshape(n_blocks, per_block)],
+                        axis=1).reshape(-1)
     padded = (lens.astype(np.uint64) + 15) & ~np.uint64(15)
     value_off = np.zeros(n, np.uint64)
     np.cumsum(padded[:-1], out=value_off[1:])
@@ -226,8 +233,8 @@ def block_tries(n_blocks: int, per_block: int = 300, kind: str = "tx", seed: int
     value_bytes[value_off.astype(np.int64)] = 2
     one = b"".join(z.rlp_index(i) for i in range(per_block))
     klen = np.array([len(z.rlp_index(i)) for i in range(per_block)], np.int64)
-    key_bytes = np.frombuffer(one * n_blocks + b"\0" * 16, np.uint8).copy()
+    key_bytes = np.frombuffer(one * n_tries + b"\0" * 16, np.uint8).copy()
     key_off = np.zeros(n + 1, np.uint32)
-    np.cumsum(np.tile(klen, n_blocks), out=key_off[1:])
-    trie_first = (np.arange(n_blocks + 1, dtype=np.uint64) * per_block).astype(np.uint32)
+    np.cumsum(np.tile(klen, n_tries), out=key_off[1:])
+    trie_first = (np.arange(n_tries + 1, dtype=np.uint64) * per_block).astype(np.uint32)
     return z.KvBatch(key_bytes, key_off, value_bytes, value_off, lens, trie_first)
