@@ -259,7 +259,7 @@ def run_reference(a):
                 cpu_baseline=dict(value=v, unit=unit, cores=cores, kind="port", sample=what),
                 keccak_f_per_sec=pa / dt,
                 e2e=dict(value=v, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -439,14 +439,26 @@ def main_rebuild(a):
                                         gpu_results_identical_on_sample=same)
             if not same:
                 line["parity_error"] = "GPU roots differ from the oracle on the CPU-baseline sample"
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) to stderr"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     a = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # libraries that print to fd 1 (e.g. "NCCL version ...") now land on stderr
     if a.impl == "reference":
         return run_reference(a)
     if a.workload == "config4":
@@ -582,7 +594,7 @@ def main():
             line["cpu_baseline"] = cb
             if not same:
                 line["parity_error"] = "GPU results differ from the oracle on the CPU-baseline sample"
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

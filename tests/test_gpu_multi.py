@@ -1,0 +1,53 @@
+"""N > 1 on real GPUs (skipped on a 1-GPU box): (a) one context over two devices -- the C ABI's own
+slice-per-device path -- and (b) one process per GPU under torchrun with the NCCL gather of
+zk_state_proofs_b200.sharding.verify_sharded, both against the single-GPU result."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _batches():
+    from workload import gen
+    state, tokens = gen.make_state_and_tokens(200_000, 3, 20_000, seed=3)
+    return gen.nested_batch(state, tokens, 10_000, seed=21), gen.block_tries(40, 300, "both", seed=4)
+
+
+def test_one_context_two_devices_matches_one_device(verifier):
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import zk_state_proofs_b200 as z
+    b, kv = _batches()
+    one = verifier.verify_batch(b)
+    two = z.Verifier([0, 1])
+    assert two.device_count == 2
+    two.set_option("chunk_bytes", 4 << 20)
+    got = two.verify_batch(b)
+    for x, y in zip(one, got):
+        assert (x == y).all()
+    assert (two.trie_roots(kv) == verifier.trie_roots(kv)).all()
+    two.close()
+
+
+def test_torchrun_two_ranks_nccl_matches_one_device(verifier, tmp_path):
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    b, _ = _batches()
+    st, voff, vlen = verifier.verify_batch(b)
+    out = str(tmp_path / "sharded.npz")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                           "--master-addr", "127.0.0.1", "--master-port", "29517",
+                           os.path.join(ROOT, "tests", "_sharded_nccl.py"), out], env=env, timeout=600)
+    z = np.load(out)
+    assert (z["st"] == st).all() and (z["voff"] == voff).all() and (z["vlen"] == vlen).all()
