@@ -185,6 +185,32 @@ int mptv_trie_roots(mptv_ctx* ctx, const mptv_kv_batch* in, uint8_t* roots32);
 int mptv_trie_roots_device(mptv_ctx* ctx, int dev_index, const mptv_kv_batch* in, uint8_t* roots32, void* stream);
 int mptv_last_rebuild_timings(mptv_ctx* ctx, int dev_index, mptv_rebuild_timings* out);
 
+/* Rebuild + Trie::get_proof: what get_ethereum_transaction_proof_inputs / get_ethereum_receipt_proof_inputs
+ * do after fetching the block (/root/reference/trie-utils/src/proofs/transaction.rs:41-73,
+ * proofs/receipt.rs:49-92): build the tries, take root_hash(), and for every target (trie, key) emit
+ * the encoded nodes on the key's path, root first (the root always, other nodes only when referenced
+ * by hash; for an absent key the path that proves its absence).  The output is laid out as an
+ * mptv_batch arena (every node on a 16-byte boundary), so {proof q, roots32[trie[q]], key q} can be
+ * handed straight to mptv_verify_batch.  Host buffers, device 0 of the context. */
+typedef struct mptv_proof_targets {
+  const uint32_t* trie;      /* [n_targets] trie the key is looked up in */
+  const uint8_t* key_bytes;  /* target q key = key_bytes[key_off[q] .. key_off[q+1]) */
+  const uint32_t* key_off;   /* [n_targets+1] */
+  uint64_t n_targets;
+} mptv_proof_targets;
+typedef struct mptv_proofs_out {
+  uint8_t* node_bytes;       /* caller-allocated, node_bytes_cap bytes */
+  uint64_t node_bytes_cap;
+  uint64_t* node_off;        /* [nodes_cap] */
+  uint32_t* node_len;        /* [nodes_cap] */
+  uint64_t nodes_cap;
+  uint32_t* proof_first;     /* [n_targets+1] */
+  uint64_t n_nodes;          /* out: nodes written -- or required, when MPTV_ERR_NOMEM is returned */
+  uint64_t node_bytes_len;   /* out: bytes written -- or required */
+} mptv_proofs_out;
+int mptv_trie_proofs(mptv_ctx* ctx, const mptv_kv_batch* in, const mptv_proof_targets* targets, uint8_t* roots32,
+                     mptv_proofs_out* out);
+
 /* page-locked host memory for arenas that are handed to mptv_verify_batch */
 void* mptv_alloc_pinned(size_t bytes);
 void mptv_free_pinned(void* p);

@@ -258,6 +258,17 @@ class _CKvBatch(ctypes.Structure):
     ]
 
 
+class _CProofTargets(ctypes.Structure):
+    _fields_ = [("trie", ctypes.c_void_p), ("key_bytes", ctypes.c_void_p), ("key_off", ctypes.c_void_p),
+                ("n_targets", ctypes.c_uint64)]
+
+
+class _CProofsOut(ctypes.Structure):
+    _fields_ = [("node_bytes", ctypes.c_void_p), ("node_bytes_cap", ctypes.c_uint64), ("node_off", ctypes.c_void_p),
+                ("node_len", ctypes.c_void_p), ("nodes_cap", ctypes.c_uint64), ("proof_first", ctypes.c_void_p),
+                ("n_nodes", ctypes.c_uint64), ("node_bytes_len", ctypes.c_uint64)]
+
+
 class RebuildTimings(ctypes.Structure):
     _fields_ = [
         ("structure_ms", ctypes.c_float), ("encode_ms", ctypes.c_float), ("keccak_ms", ctypes.c_float),
@@ -338,6 +349,9 @@ def load_library():
     L.mptv_trie_roots_device.argtypes = [vp, i32, ctypes.POINTER(_CKvBatch), vp, vp]
     L.mptv_last_rebuild_timings.restype = i32
     L.mptv_last_rebuild_timings.argtypes = [vp, i32, ctypes.POINTER(RebuildTimings)]
+    L.mptv_trie_proofs.restype = i32
+    L.mptv_trie_proofs.argtypes = [vp, ctypes.POINTER(_CKvBatch), ctypes.POINTER(_CProofTargets), vp,
+                                   ctypes.POINTER(_CProofsOut)]
     L.mptv_alloc_pinned.restype = vp
     L.mptv_alloc_pinned.argtypes = [ctypes.c_size_t]
     L.mptv_free_pinned.restype = None
@@ -467,6 +481,51 @@ class Verifier:
         self._check(self.lib.mptv_last_rebuild_timings(self.ctx, dev_index, ctypes.byref(t)),
                     "mptv_last_rebuild_timings")
         return t
+
+    def trie_proofs(self, kv: KvBatch, targets):
+        """Rebuild the tries and extract Trie::get_proof for every target (trie index, key bytes).
+        -> (roots u8[n_tries, 32], Batch) where proof q of the batch belongs to target q and its root /
+        key fields are already filled in, i.e. the batch can be verified as it is."""
+        nq = len(targets)
+        roots = np.zeros((kv.n_tries, 32), np.uint8)
+        t_trie = np.fromiter((t for t, _ in targets), dtype=np.uint32, count=nq)
+        klens = np.fromiter((len(k) for _, k in targets), dtype=np.int64, count=nq)
+        key_off = np.zeros(nq + 1, np.uint32)
+        np.cumsum(klens, out=key_off[1:])
+        key_bytes = np.zeros(int(key_off[-1]) + 16, np.uint8)
+        if nq:
+            key_bytes[:int(key_off[-1])] = np.frombuffer(b"".join(bytes(k) for _, k in targets), np.uint8)
+        cb = _CKvBatch(_ptr(kv.key_bytes), _ptr(kv.key_off), _ptr(kv.value_bytes), len(kv.value_bytes),
+                       _ptr(kv.value_off), _ptr(kv.value_len), kv.n_items, _ptr(kv.trie_first), kv.n_tries)
+        tg = _CProofTargets(_ptr(t_trie), _ptr(key_bytes), _ptr(key_off), nq)
+        proof_first = np.zeros(nq + 1, np.uint32)
+        cap_nodes, cap_bytes = 8 * nq + 8, 1024 * nq + 4096
+        for _ in range(2):
+            node_bytes = np.zeros(cap_bytes, np.uint8)
+            node_off = np.zeros(cap_nodes, np.uint64)
+            node_len = np.zeros(cap_nodes, np.uint32)
+            out = _CProofsOut(_ptr(node_bytes), cap_bytes, _ptr(node_off), _ptr(node_len), cap_nodes,
+                              _ptr(proof_first), 0, 0)
+            rc = self.lib.mptv_trie_proofs(self.ctx, ctypes.byref(cb), ctypes.byref(tg), _ptr(roots), ctypes.byref(out))
+            if rc != -4:  # MPTV_ERR_NOMEM: the struct now holds the required capacities
+                break
+            cap_nodes, cap_bytes = int(out.n_nodes) + 8, int(out.node_bytes_len) + 16
+        self._check(rc, "mptv_trie_proofs")
+        nn, nb = int(out.n_nodes), int(out.node_bytes_len)
+        b = Batch(node_bytes[:nb], node_off[:nn], node_len[:nn], proof_first,
+                  np.ascontiguousarray(roots[t_trie].reshape(-1)) if nq else np.zeros(0, np.uint8),
+                  key_bytes, key_off, None, None)
+        return roots, b
+
+    def transaction_proof_inputs(self, encoded_txs: Sequence[bytes], target_index: int) -> MerkleProofInput:
+        """The RPC-free half of get_ethereum_transaction_proof_inputs (transaction.rs:41-73) and
+        get_ethereum_receipt_proof_inputs (receipt.rs:49-92): trie {rlp(i): encoded item i}, root_hash(),
+        get_proof(rlp(target_index))."""
+        kv = flatten_kv([[(rlp_index(i), v) for i, v in enumerate(encoded_txs)]])
+        key = rlp_index(target_index)
+        roots, b = self.trie_proofs(kv, [(0, key)])
+        proof = [b.node_bytes[int(o):int(o) + int(n)].tobytes() for o, n in zip(b.node_off, b.node_len)]
+        return MerkleProofInput(proof, roots[0].tobytes(), key)
 
     def ordered_trie_root(self, values: Sequence[bytes]) -> bytes:
         """Root of the trie {rlp(i): values[i]} -- what transaction.rs:41-66 / receipt.rs:49-84 compute."""

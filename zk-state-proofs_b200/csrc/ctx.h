@@ -65,6 +65,7 @@ struct Slot {
 struct Rebuild {
   DevBuf rec, off, len, digests, tcount, lvl_list, sum, arena, order, bins;
   DevBuf in_key_bytes, in_key_off, in_value_bytes, in_value_off, in_value_len, in_trie_first, out_roots;  // host-buffer entry
+  DevBuf q_trie, q_key_bytes, q_key_off, q_cnt, q_bytes, q_proof_first, q_byte_first, q_out_bytes, q_out_off, q_out_len;  // get_proof
   HostBuf h_sum, h_roots;
   cudaEvent_t ev_begin = nullptr, ev_struct = nullptr, ev_end = nullptr;
   std::vector<cudaEvent_t> lvl_ev;  // 3 per level: before encode, after encode, after keccak
@@ -73,7 +74,8 @@ struct Rebuild {
   unsigned long long n_nodes = 0, n_hashed = 0, n_perm = 0, arena_bytes = 0;
   void release() {
     DevBuf* all[] = {&rec, &off, &len, &digests, &tcount, &lvl_list, &sum, &arena, &order, &bins, &in_key_bytes,
-                     &in_key_off, &in_value_bytes, &in_value_off, &in_value_len, &in_trie_first, &out_roots};
+                     &in_key_off, &in_value_bytes, &in_value_off, &in_value_len, &in_trie_first, &out_roots, &q_trie, &q_key_bytes,
+                     &q_key_off, &q_cnt, &q_bytes, &q_proof_first, &q_byte_first, &q_out_bytes, &q_out_off, &q_out_len};
     for (DevBuf* b : all) b->release();
     h_sum.release(); h_roots.release();
     for (cudaEvent_t e : lvl_ev) cudaEventDestroy(e);

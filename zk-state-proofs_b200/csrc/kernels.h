@@ -114,6 +114,14 @@ cudaError_t launch_trie_structure(const TrieBatchDev& in, const TrieWork& w, uin
 cudaError_t launch_trie_encode(const TrieBatchDev& in, const TrieWork& w, const uint32_t* list, uint32_t n_list,
                                uint8_t* arena, cudaStream_t st);
 cudaError_t launch_trie_roots(const TrieBatchDev& in, const TrieWork& w, uint8_t* roots32, cudaStream_t st);
+// get_proof after a rebuild: per-target node counts / padded bytes and their exclusive scans, then the copy
+cudaError_t launch_trie_proof_count(const TrieBatchDev& in, const TrieWork& w, const uint32_t* target_trie,
+                                    const uint8_t* tkey_bytes, const uint32_t* tkey_off, uint32_t n_targets, uint32_t* cnt,
+                                    uint64_t* bytes, uint32_t* proof_first, uint64_t* byte_first, cudaStream_t st);
+cudaError_t launch_trie_proof_emit(const TrieBatchDev& in, const TrieWork& w, const uint8_t* arena, const uint32_t* target_trie,
+                                   const uint8_t* tkey_bytes, const uint32_t* tkey_off, uint32_t n_targets,
+                                   const uint32_t* proof_first, const uint64_t* byte_first, uint8_t* out_bytes,
+                                   uint64_t* out_off, uint32_t* out_len, cudaStream_t st);
 
 // integer issue-rate probe (microbench.cu): mode 0 = LOP3, 1 = SHF, 2 = Keccak mix
 cudaError_t run_int_peak(int mode, int sm_count, uint32_t* scratch, cudaStream_t st, double* ops_per_s);

@@ -94,6 +94,51 @@ int rebuild_on_device(mptv_ctx* ctx, Device& d, const TrieBatchDev& in, uint8_t*
   return MPTV_OK;
 }
 
+// copies tries [cs, ce) of a host batch to the device (offsets rebased to the chunk) -> b
+int upload_kv(mptv_ctx* ctx, Device& d, const mptv_kv_batch* in, uint64_t cs, uint64_t ce, TrieBatchDev& b, cudaStream_t st) {
+  Rebuild& rb = d.rb;
+  const uint32_t i0 = in->trie_first[cs], i1 = in->trie_first[ce];
+  const uint64_t ni = i1 - i0, nt = ce - cs;
+  const uint64_t b0 = i0 < in->n_items ? in->value_off[i0] : in->value_bytes_len;
+  uint64_t b1 = b0;
+  if (ni) b1 = in->value_off[i1 - 1] + in->value_len[i1 - 1];
+  b1 = (b1 + 15) & ~15ull;
+  if (b1 > ((in->value_bytes_len + 15) & ~15ull)) return MPTV_ERR_ARG;
+  const uint32_t k0 = in->key_off[i0], k1 = in->key_off[i1];
+  // rebased copies of the index arrays (offsets relative to this chunk)
+  std::vector<uint32_t> koff(ni + 1), tfirst(nt + 1);
+  std::vector<uint64_t> voff(ni ? ni : 1);
+  for (uint64_t i = 0; i <= ni; i++) koff[i] = in->key_off[i0 + i] - k0;
+  for (uint64_t i = 0; i < ni; i++) {
+    const uint64_t o = in->value_off[i0 + i];
+    if (o & 15) return MPTV_ERR_ALIGN;
+    if (o < b0 || o + in->value_len[i0 + i] > b1) return MPTV_ERR_ARG;
+    voff[i] = o - b0;
+  }
+  for (uint64_t t = 0; t <= nt; t++) tfirst[t] = in->trie_first[cs + t] - i0;
+  CK(rb.in_key_bytes.reserve((size_t)(k1 - k0) + 16));
+  CK(rb.in_key_off.reserve(4 * (ni + 1)));
+  CK(rb.in_value_bytes.reserve((size_t)(b1 - b0) + 16));
+  CK(rb.in_value_off.reserve(8 * ni + 8));
+  CK(rb.in_value_len.reserve(4 * ni + 4));
+  CK(rb.in_trie_first.reserve(4 * (nt + 1)));
+  if (k1 > k0) CK(cudaMemcpyAsync(rb.in_key_bytes.p, in->key_bytes + k0, k1 - k0, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(rb.in_key_off.p, koff.data(), 4 * (ni + 1), cudaMemcpyHostToDevice, st));
+  const uint64_t copy_end = b1 < in->value_bytes_len ? b1 : in->value_bytes_len;
+  if (copy_end > b0) CK(cudaMemcpyAsync(rb.in_value_bytes.p, in->value_bytes + b0, copy_end - b0, cudaMemcpyHostToDevice, st));
+  if (ni) {
+    CK(cudaMemcpyAsync(rb.in_value_off.p, voff.data(), 8 * ni, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(rb.in_value_len.p, in->value_len + i0, 4 * ni, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemcpyAsync(rb.in_trie_first.p, tfirst.data(), 4 * (nt + 1), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // the staging vectors above go out of scope
+  b.key_bytes = rb.in_key_bytes.as<uint8_t>(); b.key_off = rb.in_key_off.as<uint32_t>();
+  b.value_bytes = rb.in_value_bytes.as<uint8_t>(); b.value_off = rb.in_value_off.as<uint64_t>();
+  b.value_len = rb.in_value_len.as<uint32_t>(); b.trie_first = rb.in_trie_first.as<uint32_t>();
+  b.n_tries = (uint32_t)nt; b.n_items = ni;
+  return MPTV_OK;
+}
+
 // one device's share [t0, t1) of a host batch, in chunks of about `chunk` value bytes
 int rebuild_slice(mptv_ctx* ctx, Device& d, const mptv_kv_batch* in, uint8_t* roots32, uint64_t t0, uint64_t t1) {
   if (t1 <= t0) return MPTV_OK;
@@ -111,54 +156,33 @@ int rebuild_slice(mptv_ctx* ctx, Device& d, const mptv_kv_batch* in, uint8_t* ro
       if (be - b0 > chunk) break;
       ce++;
     }
-    const uint32_t i1 = in->trie_first[ce];
-    const uint64_t ni = i1 - i0, nt = ce - cs;
-    uint64_t b1 = b0;
-    if (ni) b1 = in->value_off[i1 - 1] + in->value_len[i1 - 1];
-    b1 = (b1 + 15) & ~15ull;
-    if (b1 > ((in->value_bytes_len + 15) & ~15ull)) return MPTV_ERR_ARG;
-    const uint32_t k0 = in->key_off[i0], k1 = in->key_off[i1];
-    // rebased copies of the index arrays (offsets relative to this chunk)
-    std::vector<uint32_t> koff(ni + 1), tfirst(nt + 1);
-    std::vector<uint64_t> voff(ni ? ni : 1);
-    for (uint64_t i = 0; i <= ni; i++) koff[i] = in->key_off[i0 + i] - k0;
-    for (uint64_t i = 0; i < ni; i++) {
-      const uint64_t o = in->value_off[i0 + i];
-      if (o & 15) return MPTV_ERR_ALIGN;
-      if (o < b0 || o + in->value_len[i0 + i] > b1) return MPTV_ERR_ARG;
-      voff[i] = o - b0;
-    }
-    for (uint64_t t = 0; t <= nt; t++) tfirst[t] = in->trie_first[cs + t] - i0;
-    CK(rb.in_key_bytes.reserve((size_t)(k1 - k0) + 16));
-    CK(rb.in_key_off.reserve(4 * (ni + 1)));
-    CK(rb.in_value_bytes.reserve((size_t)(b1 - b0) + 16));
-    CK(rb.in_value_off.reserve(8 * ni + 8));
-    CK(rb.in_value_len.reserve(4 * ni + 4));
-    CK(rb.in_trie_first.reserve(4 * (nt + 1)));
+    const uint64_t nt = ce - cs;
+    TrieBatchDev b;
+    int rc = upload_kv(ctx, d, in, cs, ce, b, st);
+    if (rc != MPTV_OK) return rc;
     CK(rb.out_roots.reserve(32 * nt));
     CK(rb.h_roots.reserve(32 * nt));
-    if (k1 > k0) CK(cudaMemcpyAsync(rb.in_key_bytes.p, in->key_bytes + k0, k1 - k0, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(rb.in_key_off.p, koff.data(), 4 * (ni + 1), cudaMemcpyHostToDevice, st));
-    uint64_t copy_end = b1 < in->value_bytes_len ? b1 : in->value_bytes_len;
-    if (copy_end > b0) CK(cudaMemcpyAsync(rb.in_value_bytes.p, in->value_bytes + b0, copy_end - b0, cudaMemcpyHostToDevice, st));
-    if (ni) {
-      CK(cudaMemcpyAsync(rb.in_value_off.p, voff.data(), 8 * ni, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(rb.in_value_len.p, in->value_len + i0, 4 * ni, cudaMemcpyHostToDevice, st));
-    }
-    CK(cudaMemcpyAsync(rb.in_trie_first.p, tfirst.data(), 4 * (nt + 1), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));  // the staging vectors above go out of scope per chunk
-    TrieBatchDev b;
-    b.key_bytes = rb.in_key_bytes.as<uint8_t>(); b.key_off = rb.in_key_off.as<uint32_t>();
-    b.value_bytes = rb.in_value_bytes.as<uint8_t>(); b.value_off = rb.in_value_off.as<uint64_t>();
-    b.value_len = rb.in_value_len.as<uint32_t>(); b.trie_first = rb.in_trie_first.as<uint32_t>();
-    b.n_tries = (uint32_t)nt; b.n_items = ni;
-    int rc = rebuild_on_device(ctx, d, b, rb.out_roots.as<uint8_t>(), st);
+    rc = rebuild_on_device(ctx, d, b, rb.out_roots.as<uint8_t>(), st);
     if (rc != MPTV_OK) return rc;
     CK(cudaMemcpyAsync(rb.h_roots.p, rb.out_roots.p, 32 * nt, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     memcpy(roots32 + 32 * cs, rb.h_roots.p, 32 * nt);
     cs = ce;
   }
+  return MPTV_OK;
+}
+
+int check_kv(const mptv_kv_batch* in, const uint8_t* roots32) {
+  if (!roots32 || !in->trie_first || !in->key_off || in->n_tries > 0x7fffffffull || in->n_items > 0x50000000ull)
+    return MPTV_ERR_ARG;
+  if (in->n_items && (!in->key_bytes || !in->value_bytes || !in->value_off || !in->value_len)) return MPTV_ERR_ARG;
+  if (in->trie_first[in->n_tries] > in->n_items) return MPTV_ERR_ARG;
+  for (uint64_t t = 0; t < in->n_tries; t++)
+    if (in->trie_first[t + 1] < in->trie_first[t]) return MPTV_ERR_ARG;
+  for (uint64_t i = 0; i < in->n_items; i++)
+    if (in->key_off[i + 1] < in->key_off[i]) return MPTV_ERR_ARG;
+  for (uint64_t i = 0; i + 1 < in->n_items; i++)
+    if (in->value_off[i + 1] < in->value_off[i] + in->value_len[i]) return MPTV_ERR_ARG;  // laid out in item order
   return MPTV_OK;
 }
 
@@ -184,16 +208,8 @@ int mptv_trie_roots_device(mptv_ctx* ctx, int dev_index, const mptv_kv_batch* in
 int mptv_trie_roots(mptv_ctx* ctx, const mptv_kv_batch* in, uint8_t* roots32) {
   if (!ctx || !in) return MPTV_ERR_ARG;
   if (in->n_tries == 0) return MPTV_OK;
-  if (!roots32 || !in->trie_first || !in->key_off || in->n_tries > 0x7fffffffull || in->n_items > 0x50000000ull)
-    return MPTV_ERR_ARG;
-  if (in->n_items && (!in->key_bytes || !in->value_bytes || !in->value_off || !in->value_len)) return MPTV_ERR_ARG;
-  if (in->trie_first[in->n_tries] > in->n_items) return MPTV_ERR_ARG;
-  for (uint64_t t = 0; t < in->n_tries; t++)
-    if (in->trie_first[t + 1] < in->trie_first[t]) return MPTV_ERR_ARG;
-  for (uint64_t i = 0; i < in->n_items; i++)
-    if (in->key_off[i + 1] < in->key_off[i]) return MPTV_ERR_ARG;
-  for (uint64_t i = 0; i + 1 < in->n_items; i++)
-    if (in->value_off[i + 1] < in->value_off[i] + in->value_len[i]) return MPTV_ERR_ARG;  // laid out in item order
+  const int ck = check_kv(in, roots32);
+  if (ck != MPTV_OK) return ck;
   const int nd = (int)ctx->dev.size();
   std::vector<uint64_t> cut(nd + 1, 0);
   cut[nd] = in->n_tries;
@@ -220,6 +236,78 @@ int mptv_trie_roots(mptv_ctx* ctx, const mptv_kv_batch* in, uint8_t* roots32) {
     for (auto& x : th) x.join();
   }
   for (int k = 0; k < nd; k++) if (rcs[k] != MPTV_OK) return rcs[k];
+  return MPTV_OK;
+}
+
+int mptv_trie_proofs(mptv_ctx* ctx, const mptv_kv_batch* in, const mptv_proof_targets* tg, uint8_t* roots32,
+                     mptv_proofs_out* out) {
+  if (!ctx || !in || !tg || !out) return MPTV_ERR_ARG;
+  out->n_nodes = 0; out->node_bytes_len = 0;
+  const uint64_t nq = tg->n_targets;
+  if (nq > 0xfffffff0ull || (nq && (!tg->trie || !tg->key_off || !out->proof_first))) return MPTV_ERR_ARG;
+  if (in->n_tries == 0) return nq ? MPTV_ERR_ARG : MPTV_OK;
+  const int ck = check_kv(in, roots32);
+  if (ck != MPTV_OK) return ck;
+  for (uint64_t q = 0; q < nq; q++) {
+    if (tg->trie[q] >= in->n_tries || tg->key_off[q + 1] < tg->key_off[q] ||
+        tg->key_off[q + 1] - tg->key_off[q] > (uint32_t)kTrieMaxKeyLen)
+      return MPTV_ERR_ARG;
+  }
+  Device& d = ctx->dev[0];
+  Rebuild& rb = d.rb;
+  CK(cudaSetDevice(d.id));
+  cudaStream_t st = d.stream;
+  TrieBatchDev b;
+  int rc = upload_kv(ctx, d, in, 0, in->n_tries, b, st);
+  if (rc != MPTV_OK) return rc;
+  CK(rb.out_roots.reserve(32 * in->n_tries));
+  rc = rebuild_on_device(ctx, d, b, rb.out_roots.as<uint8_t>(), st);
+  if (rc != MPTV_OK) return rc;
+  CK(cudaMemcpyAsync(roots32, rb.out_roots.p, 32 * in->n_tries, cudaMemcpyDeviceToHost, st));
+  if (nq == 0) { CK(cudaStreamSynchronize(st)); return MPTV_OK; }
+  TrieWork w;
+  w.rec = rb.rec.as<uint4>(); w.off = rb.off.as<uint64_t>(); w.len = rb.len.as<uint32_t>();
+  w.digests = rb.digests.as<uint8_t>(); w.tcount = rb.tcount.as<uint32_t>(); w.lvl_list = rb.lvl_list.as<uint32_t>();
+  w.sum = rb.sum.as<TrieSummary>();
+  const uint32_t kb = tg->key_off[nq];
+  CK(rb.q_trie.reserve(4 * nq));
+  CK(rb.q_key_bytes.reserve((size_t)kb + 16));
+  CK(rb.q_key_off.reserve(4 * (nq + 1)));
+  CK(rb.q_cnt.reserve(4 * nq));
+  CK(rb.q_bytes.reserve(8 * nq));
+  CK(rb.q_proof_first.reserve(4 * (nq + 1)));
+  CK(rb.q_byte_first.reserve(8 * (nq + 1)));
+  CK(cudaMemcpyAsync(rb.q_trie.p, tg->trie, 4 * nq, cudaMemcpyHostToDevice, st));
+  if (kb) CK(cudaMemcpyAsync(rb.q_key_bytes.p, tg->key_bytes, kb, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(rb.q_key_off.p, tg->key_off, 4 * (nq + 1), cudaMemcpyHostToDevice, st));
+  CK(launch_trie_proof_count(b, w, rb.q_trie.as<uint32_t>(), rb.q_key_bytes.as<uint8_t>(), rb.q_key_off.as<uint32_t>(),
+                             (uint32_t)nq, rb.q_cnt.as<uint32_t>(), rb.q_bytes.as<uint64_t>(),
+                             rb.q_proof_first.as<uint32_t>(), rb.q_byte_first.as<uint64_t>(), st));
+  uint32_t total_nodes = 0;
+  uint64_t total_bytes = 0;
+  CK(cudaMemcpyAsync(&total_nodes, rb.q_proof_first.as<uint32_t>() + nq, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&total_bytes, rb.q_byte_first.as<uint64_t>() + nq, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  out->n_nodes = total_nodes;
+  out->node_bytes_len = total_bytes + 16;
+  if (total_nodes > out->nodes_cap || total_bytes + 16 > out->node_bytes_cap || !out->node_bytes || !out->node_off ||
+      !out->node_len)
+    return MPTV_ERR_NOMEM;  // n_nodes / node_bytes_len hold what is required
+  CK(rb.q_out_bytes.reserve((size_t)total_bytes + 16));
+  CK(rb.q_out_off.reserve(8 * (size_t)total_nodes + 8));
+  CK(rb.q_out_len.reserve(4 * (size_t)total_nodes + 4));
+  CK(cudaMemsetAsync(rb.q_out_bytes.p, 0, (size_t)total_bytes + 16, st));
+  CK(launch_trie_proof_emit(b, w, rb.arena.as<uint8_t>(), rb.q_trie.as<uint32_t>(), rb.q_key_bytes.as<uint8_t>(),
+                            rb.q_key_off.as<uint32_t>(), (uint32_t)nq, rb.q_proof_first.as<uint32_t>(),
+                            rb.q_byte_first.as<uint64_t>(), rb.q_out_bytes.as<uint8_t>(), rb.q_out_off.as<uint64_t>(),
+                            rb.q_out_len.as<uint32_t>(), st));
+  CK(cudaMemcpyAsync(out->node_bytes, rb.q_out_bytes.p, (size_t)total_bytes + 16, cudaMemcpyDeviceToHost, st));
+  if (total_nodes) {
+    CK(cudaMemcpyAsync(out->node_off, rb.q_out_off.p, 8 * (size_t)total_nodes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->node_len, rb.q_out_len.p, 4 * (size_t)total_nodes, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaMemcpyAsync(out->proof_first, rb.q_proof_first.p, 4 * (nq + 1), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return MPTV_OK;
 }
 

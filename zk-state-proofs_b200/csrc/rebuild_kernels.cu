@@ -545,3 +545,138 @@ cudaError_t launch_trie_roots(const TrieBatchDev& in, const TrieWork& w, uint8_t
 }
 
 }  // namespace mptv
+
+// ------------------------------------------------------------------ get_proof (after a rebuild)
+// Trie::get_proof(key) of eth_trie for targets (trie, key): the encoded nodes on the key's path,
+// root first -- the root always, every other node only when its parent references it by hash
+// (>= 32 bytes); inline nodes are part of their parent.  The walk stops at a leaf, at an
+// extension whose path the key does not share, at an empty branch slot or when the key is
+// exhausted (proof of absence).  /root/reference/trie-utils/src/proofs/transaction.rs:66-73,
+// proofs/receipt.rs:84-92 (trie.get_proof(&key)).
+namespace mptv {
+
+namespace {
+
+// visits the path; fn(node id) for every emitted node
+template <class F>
+__device__ void proof_walk(const TrieBatchDev& in, const TrieWork& w, uint32_t trie, const uint8_t* key, uint32_t klen, F fn) {
+  if (w.tcount[trie] == 0) return;
+  uint32_t node = 3u * in.trie_first[trie];
+  uint32_t idx = 0;
+  const uint32_t plen = 2 * klen;
+  for (;;) {
+    const uint4 r = w.rec[node];
+    if ((r.w >> 16) & 1u) fn(node);
+    const uint32_t kind = r.x & 0xffu;
+    if (kind == kTLeaf) return;
+    if (kind == kTExt) {
+      const uint32_t ps = (r.x >> 16) & 0xffu, pl = r.x >> 24;
+      if (plen - idx < pl) return;
+      const uint8_t* ek = in.key_bytes + in.key_off[r.y];
+      for (uint32_t i = 0; i < pl; i++) {
+        const uint32_t a = ek[(ps + i) >> 1], b = key[(idx + i) >> 1];
+        const uint32_t na = ((ps + i) & 1) ? (a & 15u) : (a >> 4), nb = ((idx + i) & 1) ? (b & 15u) : (b >> 4);
+        if (na != nb) return;
+      }
+      idx += pl;
+      node = r.z;
+    } else {
+      if (idx >= plen) return;
+      const uint32_t b = key[idx >> 1];
+      const uint32_t nib = (idx & 1) ? (b & 15u) : (b >> 4);
+      const uint32_t mask = r.w & 0xffffu;
+      if (!((mask >> nib) & 1u)) return;
+      node = r.z + __popc(mask & ((1u << nib) - 1u));
+      idx++;
+    }
+  }
+}
+}  // namespace
+
+// pass 1: nodes and (16-byte padded) bytes per target
+__global__ void __launch_bounds__(256) k_trie_proof_count(const TrieBatchDev in, const TrieWork w, const uint32_t* __restrict__ target_trie,
+                                                          const uint8_t* __restrict__ tkey_bytes, const uint32_t* __restrict__ tkey_off,
+                                                          uint32_t n_targets, uint32_t* __restrict__ cnt, uint64_t* __restrict__ bytes) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_targets) return;
+  uint32_t c = 0;
+  uint64_t b = 0;
+  proof_walk(in, w, target_trie[q], tkey_bytes + tkey_off[q], tkey_off[q + 1] - tkey_off[q],
+             [&](uint32_t node) { c++; b += (w.len[node] + 15u) & ~15u; });
+  cnt[q] = c;
+  bytes[q] = b;
+}
+
+// exclusive scan of cnt -> proof_first[n+1] and bytes -> byte_first[n+1]; one CTA, chunk per thread
+__global__ void __launch_bounds__(1024) k_trie_proof_scan(const uint32_t* __restrict__ cnt, const uint64_t* __restrict__ bytes,
+                                                          uint32_t n, uint32_t* __restrict__ proof_first,
+                                                          uint64_t* __restrict__ byte_first) {
+  __shared__ unsigned long long sc[1024], sb[1024];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t per = (n + 1023) / 1024;
+  const uint32_t s0 = min(n, tid * per), s1 = min(n, s0 + per);
+  unsigned long long c = 0, b = 0;
+  for (uint32_t i = s0; i < s1; i++) { c += cnt[i]; b += bytes[i]; }
+  sc[tid] = c; sb[tid] = b;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long ac = 0, ab = 0;
+    for (int i = 0; i < 1024; i++) {
+      const unsigned long long x = sc[i], y = sb[i];
+      sc[i] = ac; sb[i] = ab;
+      ac += x; ab += y;
+    }
+    proof_first[n] = (uint32_t)ac;
+    byte_first[n] = ab;
+  }
+  __syncthreads();
+  c = sc[tid]; b = sb[tid];
+  for (uint32_t i = s0; i < s1; i++) {
+    proof_first[i] = (uint32_t)c; byte_first[i] = b;
+    c += cnt[i]; b += bytes[i];
+  }
+}
+
+// pass 2: one warp per target copies its nodes into the output arena
+__global__ void __launch_bounds__(256) k_trie_proof_emit(const TrieBatchDev in, const TrieWork w, const uint8_t* __restrict__ arena,
+                                                         const uint32_t* __restrict__ target_trie, const uint8_t* __restrict__ tkey_bytes,
+                                                         const uint32_t* __restrict__ tkey_off, uint32_t n_targets,
+                                                         const uint32_t* __restrict__ proof_first, const uint64_t* __restrict__ byte_first,
+                                                         uint8_t* __restrict__ out_bytes, uint64_t* __restrict__ out_off,
+                                                         uint32_t* __restrict__ out_len) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= n_targets) return;
+  uint32_t k = proof_first[q];
+  uint64_t o = byte_first[q];
+  proof_walk(in, w, target_trie[q], tkey_bytes + tkey_off[q], tkey_off[q + 1] - tkey_off[q], [&](uint32_t node) {
+    const uint32_t len = w.len[node];
+    const uint4* s = reinterpret_cast<const uint4*>(arena + w.off[node]);  // 16-byte aligned slots on both sides
+    uint4* d = reinterpret_cast<uint4*>(out_bytes + o);
+    for (uint32_t i = lane; i < (len + 15u) / 16u; i += 32) d[i] = s[i];
+    if (lane == 0) { out_off[k] = o; out_len[k] = len; }
+    k++;
+    o += (len + 15u) & ~15u;
+  });
+}
+
+cudaError_t launch_trie_proof_count(const TrieBatchDev& in, const TrieWork& w, const uint32_t* target_trie,
+                                    const uint8_t* tkey_bytes, const uint32_t* tkey_off, uint32_t n_targets, uint32_t* cnt,
+                                    uint64_t* bytes, uint32_t* proof_first, uint64_t* byte_first, cudaStream_t st) {
+  if (n_targets == 0) return cudaSuccess;
+  k_trie_proof_count<<<(n_targets + 255) / 256, 256, 0, st>>>(in, w, target_trie, tkey_bytes, tkey_off, n_targets, cnt, bytes);
+  k_trie_proof_scan<<<1, 1024, 0, st>>>(cnt, bytes, n_targets, proof_first, byte_first);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_trie_proof_emit(const TrieBatchDev& in, const TrieWork& w, const uint8_t* arena, const uint32_t* target_trie,
+                                   const uint8_t* tkey_bytes, const uint32_t* tkey_off, uint32_t n_targets,
+                                   const uint32_t* proof_first, const uint64_t* byte_first, uint8_t* out_bytes,
+                                   uint64_t* out_off, uint32_t* out_len, cudaStream_t st) {
+  if (n_targets == 0) return cudaSuccess;
+  k_trie_proof_emit<<<(n_targets + 7) / 8, 256, 0, st>>>(in, w, arena, target_trie, tkey_bytes, tkey_off, n_targets, proof_first,
+                                                         byte_first, out_bytes, out_off, out_len);
+  return cudaGetLastError();
+}
+
+}  // namespace mptv
