@@ -211,6 +211,37 @@ typedef struct mptv_proofs_out {
 int mptv_trie_proofs(mptv_ctx* ctx, const mptv_kv_batch* in, const mptv_proof_targets* targets, uint8_t* roots32,
                      mptv_proofs_out* out);
 
+/* ---------------------------------------------------------------------------------------------
+ * Host-side formats in front of the hot path (no GPU needed for these).
+ *
+ * mptv_flatten_borsh: n borsh-serialised MerkleProofInput blobs (types.rs:4-9; blob i =
+ * blobs[blob_off[i] .. blob_off[i+1])) -> one CSR batch, multi-threaded (n_threads <= 0: all
+ * cores), in page-locked memory when `pinned`.  Malformed borsh (what borsh::from_slice rejects)
+ * gives MPTV_ERR_ARG.  A root_hash that is not 32 bytes is flagged in bad_root (the guests'
+ * try_into().unwrap() panic, MPTV_ST_BAD_ROOT_LEN) and its proof is verified against a zero root. */
+typedef struct mptv_host_batch mptv_host_batch;
+int mptv_flatten_borsh(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, int pinned,
+                       mptv_host_batch** out);
+const mptv_batch* mptv_host_batch_view(const mptv_host_batch* hb);
+const uint8_t* mptv_host_batch_bad_root(const mptv_host_batch* hb); /* [n_proofs] */
+void mptv_host_batch_free(mptv_host_batch* hb);
+
+/* alloy_rlp::encode(index): the trie key of transaction / receipt `index` (transaction.rs:45); returns the length */
+uint32_t mptv_rlp_index(uint64_t index, uint8_t out[9]);
+
+/* trie-utils insert_receipt's leaf bytes (receipt.rs:8-38): [prefix] ++ rlp([status, cumulative_gas_used,
+ * bloom, logs]); prefix < 0 = legacy receipt (no type byte).  Returns the encoded length; writes
+ * min(length, cap) bytes (call with out == NULL to size). */
+typedef struct mptv_log {
+  const uint8_t* address;  /* 20 bytes */
+  const uint8_t* topics;   /* 32 * n_topics bytes */
+  uint32_t n_topics;
+  const uint8_t* data;
+  uint32_t data_len;
+} mptv_log;
+uint64_t mptv_encode_receipt(int prefix, int status, uint64_t cumulative_gas_used, const uint8_t* bloom256,
+                             const mptv_log* logs, uint32_t n_logs, uint8_t* out, uint64_t cap);
+
 /* page-locked host memory for arenas that are handed to mptv_verify_batch */
 void* mptv_alloc_pinned(size_t bytes);
 void mptv_free_pinned(void* p);

@@ -1,0 +1,80 @@
+"""StorageProofInput (crypto-ops/src/types.rs:11-19) through the batched GPU path against the storage
+guest's flow (storage-circuit/src/main.rs:6-31) restated with the oracle: verify the account proof under
+address_keccak, decode the Account RLP, verify every storage proof under its storage_root with key
+keccak(storage_key)."""
+import random
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rlp_account(nonce, balance, storage_root, code_hash):
+    from oracle.pytrie import rlp_list, rlp_str, rlp_uint
+    return rlp_list([rlp_uint(nonce), rlp_uint(balance), rlp_str(storage_root), rlp_str(code_hash)])
+
+
+def _world(oracle, seed, n_accounts=40, n_slots=30):
+    from oracle.pytrie import Trie, rlp_uint
+    rng = random.Random(seed)
+    k = oracle.keccak256
+    storages, accounts = [], {}
+    for a in range(n_accounts):
+        addr = rng.randbytes(20)
+        slots = {rng.randbytes(32): rng.randrange(1, 1 << rng.choice([7, 8, 64, 255])) for _ in range(rng.randrange(1, n_slots))}
+        st = Trie({k(s): rlp_uint(v) for s, v in slots.items()}, k)
+        accounts[addr] = (slots, st)
+        storages.append(st)
+    state = Trie({k(addr): _rlp_account(rng.randrange(1 << 20), rng.randrange(1 << 100), st.root, rng.randbytes(32))
+                  for addr, (slots, st) in accounts.items()}, k)
+    return state, accounts
+
+
+def _guest(oracle, inp):
+    """the storage guest, with the oracle as verify_merkle_proof"""
+    st, val, _, _ = oracle.verify(inp.root_hash, inp.account_proof, inp.address_keccak)
+    if st != 0:
+        return st
+    sr = oracle.account_storage_root(val)
+    if sr is None:
+        return 7
+    out = []
+    for pr, key in zip(inp.storage_proofs, inp.storage_keys):
+        st, val, _, _ = oracle.verify(sr, pr, oracle.keccak256(key))
+        if st != 0:
+            return st
+        out.append(val)
+    return out
+
+
+def test_storage_proof_inputs_batched_match_guest_flow(verifier, oracle):
+    import zk_state_proofs_b200 as z
+    state, accounts = _world(oracle, 3)
+    rng = random.Random(4)
+    k = oracle.keccak256
+    inputs = []
+    for addr, (slots, st) in accounts.items():
+        keys = rng.sample(list(slots), min(3, len(slots)))
+        if rng.random() < 0.3:
+            keys.append(rng.randbytes(32))  # absent slot -> "Key does not exist!"
+        inp = z.StorageProofInput(state.proof(k(addr)), [st.proof(k(s)) for s in keys], state.root, addr, keys, k(addr))
+        u = rng.random()
+        if u < 0.1:
+            inp.account_proof = inp.account_proof[:-1]            # truncated account proof
+        elif u < 0.2 and inp.storage_proofs[0]:
+            n = bytearray(inp.storage_proofs[0][-1]); n[-1] ^= 1
+            inp.storage_proofs[0] = inp.storage_proofs[0][:-1] + [bytes(n)]   # tampered storage leaf
+        elif u < 0.3:
+            inp.address_keccak = k(b"someone else")               # wrong account key
+        inputs.append(inp)
+    got = verifier.verify_storage_proof_inputs(inputs)
+    n_ok = 0
+    for inp, g in zip(inputs, got):
+        want = _guest(oracle, inp)
+        if isinstance(want, int):
+            assert isinstance(g, z.VerifyPanic) and g.status == want, (g, want)
+        else:
+            assert g == want
+            n_ok += 1
+            assert verifier.verify_storage_proof_input(inp) == want   # the single-input entry agrees
+    assert n_ok >= 15 and n_ok < len(inputs)

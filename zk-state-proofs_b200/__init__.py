@@ -15,8 +15,12 @@ from .crypto_ops import (  # noqa: F401
     Verifier,
     STATUS_NAMES,
     digest_keccak,
+    Log,
+    encode_receipt,
     flatten,
+    flatten_borsh,
     flatten_kv,
+    rlp_index_native,
     lib_path,
     load_library,
     ordered_trie_root,
@@ -28,6 +32,7 @@ from .crypto_ops import (  # noqa: F401
 )
 
 __all__ = [
+    "Log", "encode_receipt", "flatten_borsh", "rlp_index_native",
     "Batch", "KvBatch", "flatten_kv", "ordered_trie_root", "rlp_index", "trie_roots", "MerkleProofInput", "MptvError", "StorageProofInput", "VerifyPanic", "Verifier",
     "STATUS_NAMES", "digest_keccak", "flatten", "lib_path", "load_library", "verify_merkle_proof",
     "verify_merkle_proofs", "verify_storage_proof_input",

@@ -189,6 +189,86 @@ def flatten(inputs: Sequence[MerkleProofInput], root_from_proof: Optional[Sequen
     return Batch(node_bytes, node_off, lens, proof_first, roots, key_bytes, key_off, rfp, bad if bad.any() else None)
 
 
+class _HostBatchOwner:
+    """keeps an mptv_host_batch (C++-owned arrays) alive while numpy views of it exist"""
+
+    def __init__(self, lib, handle):
+        self.lib, self.handle = lib, handle
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.mptv_host_batch_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def _view(ptr, n, dtype):
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype)
+    ct = {np.uint8: ctypes.c_uint8, np.uint32: ctypes.c_uint32, np.uint64: ctypes.c_uint64}[dtype]
+    return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(int(n),))
+
+
+def flatten_borsh(blobs: Sequence[bytes], threads: int = 0, pinned: bool = False) -> Batch:
+    """borsh(MerkleProofInput) x n -> CSR batch through the multi-threaded C++ flattener
+    (csrc/host_codec.cpp, mptv_flatten_borsh).  The arrays are views of C++-owned (optionally
+    page-locked) memory kept alive by the returned Batch."""
+    L = load_library()
+    n = len(blobs)
+    lens = np.fromiter((len(x) for x in blobs), dtype=np.int64, count=n)
+    off = np.zeros(n + 1, np.uint64)
+    np.cumsum(lens, out=off[1:])
+    buf = np.frombuffer(b"".join(bytes(x) for x in blobs) + b"\0", np.uint8)
+    h = ctypes.c_void_p()
+    rc = L.mptv_flatten_borsh(buf.ctypes.data, off.ctypes.data, n, threads, 1 if pinned else 0, ctypes.byref(h))
+    if rc != 0:
+        raise ValueError(f"mptv_flatten_borsh: {L.mptv_strerror(rc).decode()} (malformed borsh MerkleProofInput?)")
+    owner = _HostBatchOwner(L, h)
+    v = ctypes.cast(L.mptv_host_batch_view(h), ctypes.POINTER(_CBatch)).contents
+    bad = _view(L.mptv_host_batch_bad_root(h), n, np.uint8).astype(bool)
+    b = Batch(_view(v.node_bytes, v.node_bytes_len, np.uint8), _view(v.node_off, v.n_nodes, np.uint64),
+              _view(v.node_len, v.n_nodes, np.uint32), _view(v.proof_first, n + 1, np.uint32),
+              _view(v.roots, 32 * n, np.uint8), _view(v.key_bytes, int(_view(v.key_off, n + 1, np.uint32)[-1]) + 16, np.uint8),
+              _view(v.key_off, n + 1, np.uint32), None, bad if bad.any() else None)
+    b._owner = owner
+    return b
+
+
+@dataclass
+class Log:
+    """trie-utils/src/types.rs:11-15"""
+    address: bytes            # 20 bytes
+    topics: List[bytes]       # 32 bytes each
+    data: bytes
+
+
+class _CLog(ctypes.Structure):
+    _fields_ = [("address", ctypes.c_char_p), ("topics", ctypes.c_char_p), ("n_topics", ctypes.c_uint32),
+                ("data", ctypes.c_char_p), ("data_len", ctypes.c_uint32)]
+
+
+def encode_receipt(status: bool, cumulative_gas_used: int, bloom: bytes, logs: Sequence[Log],
+                   prefix: Optional[int] = None) -> bytes:
+    """The leaf bytes insert_receipt puts into the receipt trie (trie-utils/src/receipt.rs:8-38):
+    [prefix] ++ rlp([status, cumulative_gas_used, bloom, logs]); prefix None = legacy receipt."""
+    L = load_library()
+    if len(bloom) != 256 or any(len(l.address) != 20 or any(len(t) != 32 for t in l.topics) for l in logs):
+        raise ValueError("bloom must be 256 bytes, addresses 20, topics 32")
+    arr = (_CLog * max(1, len(logs)))()
+    keep = []
+    for i, l in enumerate(logs):
+        t = b"".join(l.topics)
+        keep.append((bytes(l.address), t, bytes(l.data)))
+        arr[i] = _CLog(keep[-1][0], keep[-1][1], len(l.topics), keep[-1][2], len(l.data))
+    p = -1 if prefix is None else int(prefix)
+    n = L.mptv_encode_receipt(p, 1 if status else 0, int(cumulative_gas_used), bytes(bloom), arr, len(logs), None, 0)
+    out = ctypes.create_string_buffer(n)
+    L.mptv_encode_receipt(p, 1 if status else 0, int(cumulative_gas_used), bytes(bloom), arr, len(logs), out, n)
+    return out.raw
+
+
 # ----------------------------------------------------------------------------- key/value batches (rebuild)
 @dataclass
 class KvBatch:
@@ -221,6 +301,13 @@ def rlp_index(i: int) -> bytes:
         return bytes([i])
     be = i.to_bytes((i.bit_length() + 7) // 8, "big")
     return bytes([0x80 + len(be)]) + be
+
+
+def rlp_index_native(i: int) -> bytes:
+    """the same through the C++ host codec (mptv_rlp_index)"""
+    out = ctypes.create_string_buffer(9)
+    n = load_library().mptv_rlp_index(int(i), out)
+    return out.raw[:n]
 
 
 def flatten_kv(tries) -> KvBatch:
@@ -352,6 +439,19 @@ def load_library():
     L.mptv_trie_proofs.restype = i32
     L.mptv_trie_proofs.argtypes = [vp, ctypes.POINTER(_CKvBatch), ctypes.POINTER(_CProofTargets), vp,
                                    ctypes.POINTER(_CProofsOut)]
+    L.mptv_flatten_borsh.restype = i32
+    L.mptv_flatten_borsh.argtypes = [vp, vp, u64, i32, i32, ctypes.POINTER(vp)]
+    L.mptv_host_batch_view.restype = vp
+    L.mptv_host_batch_view.argtypes = [vp]
+    L.mptv_host_batch_bad_root.restype = vp
+    L.mptv_host_batch_bad_root.argtypes = [vp]
+    L.mptv_host_batch_free.restype = None
+    L.mptv_host_batch_free.argtypes = [vp]
+    L.mptv_rlp_index.restype = ctypes.c_uint32
+    L.mptv_rlp_index.argtypes = [u64, ctypes.c_char_p]
+    L.mptv_encode_receipt.restype = u64
+    L.mptv_encode_receipt.argtypes = [i32, i32, u64, ctypes.c_char_p, ctypes.POINTER(_CLog), ctypes.c_uint32,
+                                      ctypes.c_char_p, u64]
     L.mptv_alloc_pinned.restype = vp
     L.mptv_alloc_pinned.argtypes = [ctypes.c_size_t]
     L.mptv_free_pinned.restype = None
@@ -571,6 +671,33 @@ class Verifier:
             if isinstance(r, VerifyPanic):
                 raise r
         return res[1:]
+
+    def verify_storage_proof_inputs(self, inputs: Sequence[StorageProofInput]):
+        """Batched storage guest: every input's account proof and all of its storage proofs in ONE
+        device batch (storage keys hashed in one Keccak launch, storage roots taken on the device from
+        the verified account leaves).  -> per input: list of storage values, or the VerifyPanic the
+        guest would have died with (the first failing proof in the guest's order)."""
+        all_keys = [k for inp in inputs for k in inp.storage_keys]
+        hashed = self._keccak_many(all_keys)
+        items, rfp, spans = [], [], []
+        hk = 0
+        for inp in inputs:
+            if len(inp.storage_proofs) != len(inp.storage_keys):
+                raise ValueError("storage_proofs and storage_keys differ in length")
+            a = len(items)
+            items.append(MerkleProofInput(inp.account_proof, inp.root_hash, bytes(inp.address_keccak)))
+            rfp.append(-1)
+            for pr in inp.storage_proofs:
+                items.append(MerkleProofInput(pr, b"\x00" * 32, hashed[hk]))
+                rfp.append(a)
+                hk += 1
+            spans.append((a, len(items)))
+        res = self.verify_merkle_proofs(items, rfp) if items else []
+        out = []
+        for a, e in spans:
+            bad = next((r for r in res[a:e] if isinstance(r, VerifyPanic)), None)
+            out.append(bad if bad is not None else res[a + 1:e])
+        return out
 
     def _keccak_many(self, datas: Sequence[bytes]) -> List[bytes]:
         if not datas:

@@ -1,0 +1,246 @@
+// host_codec.cpp -- host-side data formats either side of the hot path, in C++
+// because the reference's host side is compiled code:
+//   * borsh(MerkleProofInput) blobs -> the CSR arena of include/mptv.h, multi-threaded, two passes
+//     (size, then copy), every node on a 16-byte boundary, optionally straight into page-locked memory.
+//     Wire format: /root/reference/crypto-ops/src/types.rs:4-9 (derive BorshSerialize: Vec<Vec<u8>>,
+//     Vec<u8>, Vec<u8> with u32-LE length prefixes), produced by the prover
+//     (/root/reference/prover/src/bin/main.rs:41,67) and decoded by the guests
+//     (/root/reference/circuits/sp1-merkle-proof/src/main.rs:5-6).
+//   * the receipt leaf encoder of trie-utils: [prefix] ++ rlp([status, cumulative_gas_used, bloom, logs])
+//     (/root/reference/trie-utils/src/receipt.rs:8-38, Log: src/types.rs:11-35; known answer:
+//     /root/reference/trie-utils/tests/rlp.rs:12) and alloy_rlp::encode(index), the trie key
+//     (/root/reference/trie-utils/src/proofs/transaction.rs:45).
+// No hashing, trie walking or RLP *decoding* happens here: this is layout work in front of the GPU.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
+
+#include "../../include/mptv.h"
+
+struct mptv_host_batch {
+  mptv_batch view;
+  uint8_t* bad_root = nullptr;  // [n] 1 where root_hash.len() != 32
+  bool pinned = false;
+  void* blocks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n_blocks = 0;
+};
+
+namespace {
+
+void* host_alloc(mptv_host_batch* hb, size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  if (hb->pinned) {
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) p = nullptr;
+  } else {
+    if (posix_memalign(&p, 64, bytes) != 0) p = nullptr;
+  }
+  if (p) hb->blocks[hb->n_blocks++] = p;
+  return p;
+}
+
+inline bool rd_u32(const uint8_t* p, const uint8_t* end, uint32_t& v) {
+  if (end - p < 4) return false;
+  v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+  return true;
+}
+
+struct Shape { uint32_t n_nodes; uint32_t key_len; uint64_t padded_bytes; uint8_t ok; uint8_t bad_root; };
+
+// pass 1: walk one blob, no copies
+Shape shape_of(const uint8_t* p, const uint8_t* end) {
+  Shape s = {0, 0, 0, 0, 0};
+  uint32_t n, len;
+  if (!rd_u32(p, end, n)) return s;
+  p += 4;
+  for (uint32_t i = 0; i < n; i++) {
+    if (!rd_u32(p, end, len) || (uint64_t)(end - p - 4) < len) return s;
+    p += 4 + len;
+    s.padded_bytes += ((uint64_t)len + 15) & ~15ull;
+  }
+  s.n_nodes = n;
+  if (!rd_u32(p, end, len) || (uint64_t)(end - p - 4) < len) return s;
+  s.bad_root = len != 32;
+  p += 4 + len;
+  if (!rd_u32(p, end, len) || (uint64_t)(end - p - 4) < len) return s;
+  s.key_len = len;
+  p += 4 + len;
+  s.ok = p == end;  // borsh::from_slice rejects trailing bytes
+  return s;
+}
+
+template <class F>
+void parallel_for(uint64_t n, int n_threads, F f) {
+  if (n_threads <= 1 || n < 1024) { f(0, n); return; }
+  std::vector<std::thread> th;
+  const uint64_t per = (n + n_threads - 1) / n_threads;
+  for (int t = 0; t < n_threads; t++) {
+    const uint64_t lo = std::min(n, per * t), hi = std::min(n, lo + per);
+    if (lo < hi) th.emplace_back([=] { f(lo, hi); });
+  }
+  for (auto& x : th) x.join();
+}
+
+// ---- RLP writers (alloy-rlp Encodable)
+struct Out {
+  uint8_t* p; uint64_t cap; uint64_t n = 0;
+  void put(uint8_t b) { if (n < cap) p[n] = b; n++; }
+  void put(const uint8_t* s, uint64_t k) {
+    if (n + k <= cap) memcpy(p + n, s, k);
+    else if (n < cap) memcpy(p + n, s, cap - n);
+    n += k;
+  }
+};
+inline uint32_t be_len(uint64_t v) { uint32_t k = 0; while (v) { k++; v >>= 8; } return k; }
+inline uint64_t hdr_len(uint64_t payload) { return payload < 56 ? 1 : 1 + be_len(payload); }
+void put_hdr(Out& o, uint64_t payload, bool list) {
+  const uint8_t base = list ? 0xC0 : 0x80;
+  if (payload < 56) { o.put((uint8_t)(base + payload)); return; }
+  const uint32_t k = be_len(payload);
+  o.put((uint8_t)(base + 55 + k));
+  for (uint32_t i = 0; i < k; i++) o.put((uint8_t)(payload >> (8 * (k - 1 - i))));
+}
+inline uint64_t str_len(const uint8_t* s, uint64_t n) { return (n == 1 && s[0] < 0x80) ? 1 : hdr_len(n) + n; }
+void put_str(Out& o, const uint8_t* s, uint64_t n) {
+  if (n == 1 && s[0] < 0x80) { o.put(s[0]); return; }
+  put_hdr(o, n, false);
+  o.put(s, n);
+}
+inline uint64_t u64_len(uint64_t v) { return v < 0x80 ? 1 : 1 + be_len(v); }
+void put_u64(Out& o, uint64_t v) {
+  if (v == 0) { o.put(0x80); return; }
+  if (v < 0x80) { o.put((uint8_t)v); return; }
+  const uint32_t k = be_len(v);
+  o.put((uint8_t)(0x80 + k));
+  for (uint32_t i = 0; i < k; i++) o.put((uint8_t)(v >> (8 * (k - 1 - i))));
+}
+inline uint64_t log_payload(const mptv_log& l) {
+  const uint64_t topics = 33ull * l.n_topics;
+  return 21 + hdr_len(topics) + topics + str_len(l.data, l.data_len);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mptv_flatten_borsh(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, int pinned,
+                       mptv_host_batch** out) {
+  if (!out || (n && (!blobs || !blob_off))) return MPTV_ERR_ARG;
+  *out = nullptr;
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  std::vector<Shape> sh(n);
+  std::atomic<int> bad(0);
+  parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi; i++) {
+      if (blob_off[i + 1] < blob_off[i]) { bad = 1; continue; }
+      sh[i] = shape_of(blobs + blob_off[i], blobs + blob_off[i + 1]);
+      if (!sh[i].ok) bad = 1;
+    }
+  });
+  if (bad) return MPTV_ERR_ARG;
+  // exclusive scans (serial: three adds per input)
+  std::vector<uint64_t> node_first(n + 1, 0), byte_first(n + 1, 0), key_first(n + 1, 0);
+  for (uint64_t i = 0; i < n; i++) {
+    node_first[i + 1] = node_first[i] + sh[i].n_nodes;
+    byte_first[i + 1] = byte_first[i] + sh[i].padded_bytes;
+    key_first[i + 1] = key_first[i] + sh[i].key_len;
+  }
+  if (node_first[n] > 0xfffffff0ull || key_first[n] > 0xfffffff0ull) return MPTV_ERR_ARG;
+  mptv_host_batch* hb = new mptv_host_batch();
+  hb->pinned = pinned != 0;
+  const uint64_t nn = node_first[n], nb = byte_first[n] + 16;
+  uint8_t* node_bytes = (uint8_t*)host_alloc(hb, nb);
+  uint64_t* node_off = (uint64_t*)host_alloc(hb, 8 * nn);
+  uint32_t* node_len = (uint32_t*)host_alloc(hb, 4 * nn);
+  uint32_t* proof_first = (uint32_t*)host_alloc(hb, 4 * (n + 1));
+  uint8_t* roots = (uint8_t*)host_alloc(hb, 32 * n);
+  uint8_t* key_bytes = (uint8_t*)host_alloc(hb, key_first[n] + 16);
+  uint32_t* key_off = (uint32_t*)host_alloc(hb, 4 * (n + 1));
+  hb->bad_root = (uint8_t*)host_alloc(hb, n);
+  if (!node_bytes || !node_off || !node_len || !proof_first || !roots || !key_bytes || !key_off || !hb->bad_root) {
+    mptv_host_batch_free(hb);
+    return MPTV_ERR_NOMEM;
+  }
+  memset(node_bytes + byte_first[n], 0, 16);
+  memset(key_bytes + key_first[n], 0, 16);
+  proof_first[n] = (uint32_t)nn;
+  key_off[n] = (uint32_t)key_first[n];
+  // pass 2: copy
+  parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi; i++) {
+      const uint8_t* p = blobs + blob_off[i] + 4;
+      uint64_t k = node_first[i], o = byte_first[i];
+      proof_first[i] = (uint32_t)k;
+      for (uint32_t j = 0; j < sh[i].n_nodes; j++) {
+        const uint32_t len = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+        memcpy(node_bytes + o, p + 4, len);
+        const uint64_t pad = (((uint64_t)len + 15) & ~15ull) - len;
+        if (pad) memset(node_bytes + o + len, 0, pad);
+        node_off[k] = o; node_len[k] = len;
+        k++; o += len + pad; p += 4 + len;
+      }
+      const uint32_t rl = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+      if (rl == 32) memcpy(roots + 32 * i, p + 4, 32); else memset(roots + 32 * i, 0, 32);
+      hb->bad_root[i] = rl != 32;
+      p += 4 + rl;
+      key_off[i] = (uint32_t)key_first[i];
+      memcpy(key_bytes + key_first[i], p + 4, sh[i].key_len);
+    }
+  });
+  hb->view.node_bytes = node_bytes; hb->view.node_bytes_len = nb;
+  hb->view.node_off = node_off; hb->view.node_len = node_len; hb->view.n_nodes = nn;
+  hb->view.proof_first = proof_first; hb->view.n_proofs = n; hb->view.roots = roots;
+  hb->view.key_bytes = key_bytes; hb->view.key_off = key_off; hb->view.root_from_proof = nullptr;
+  *out = hb;
+  return MPTV_OK;
+}
+
+const mptv_batch* mptv_host_batch_view(const mptv_host_batch* hb) { return hb ? &hb->view : nullptr; }
+const uint8_t* mptv_host_batch_bad_root(const mptv_host_batch* hb) { return hb ? hb->bad_root : nullptr; }
+
+void mptv_host_batch_free(mptv_host_batch* hb) {
+  if (!hb) return;
+  for (int i = 0; i < hb->n_blocks; i++) {
+    if (hb->pinned) cudaFreeHost(hb->blocks[i]); else free(hb->blocks[i]);
+  }
+  delete hb;
+}
+
+uint32_t mptv_rlp_index(uint64_t index, uint8_t out[9]) {
+  Out o{out, 9};
+  put_u64(o, index);
+  return (uint32_t)o.n;
+}
+
+uint64_t mptv_encode_receipt(int prefix, int status, uint64_t cumulative_gas_used, const uint8_t* bloom256,
+                             const mptv_log* logs, uint32_t n_logs, uint8_t* out, uint64_t cap) {
+  uint64_t logs_payload = 0;
+  for (uint32_t i = 0; i < n_logs; i++) { const uint64_t p = log_payload(logs[i]); logs_payload += hdr_len(p) + p; }
+  const uint64_t payload = 1 + u64_len(cumulative_gas_used) + 3 + 256 + hdr_len(logs_payload) + logs_payload;
+  Out o{out, out ? cap : 0};
+  if (prefix >= 0) o.put((uint8_t)prefix);
+  put_hdr(o, payload, true);
+  o.put(status ? 0x01 : 0x80);  // bool: alloy-rlp encodes false as the empty string
+  put_u64(o, cumulative_gas_used);
+  put_hdr(o, 256, false);
+  o.put(bloom256, 256);
+  put_hdr(o, logs_payload, true);
+  for (uint32_t i = 0; i < n_logs; i++) {
+    const mptv_log& l = logs[i];
+    put_hdr(o, log_payload(l), true);
+    o.put(0x94);
+    o.put(l.address, 20);
+    put_hdr(o, 33ull * l.n_topics, true);
+    for (uint32_t t = 0; t < l.n_topics; t++) { o.put(0xa0); o.put(l.topics + 32 * t, 32); }
+    put_str(o, l.data, l.data_len);
+  }
+  return o.n;
+}
+
+}  // extern "C"
