@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace mptv {
@@ -35,6 +37,7 @@ namespace {
 //                      z = first child (global node id); children are consecutive in BFS order
 //                      w = occupancy mask (branch) | hashed << 16
 constexpr uint32_t kNoItem = 0xffffffffu;
+constexpr uint32_t kPending = 0xffffffffu;  // w of a BFS queue entry that has not been expanded yet
 enum : uint32_t { kTLeaf = 1, kTExt = 2, kTBranch = 3 };
 
 __device__ __forceinline__ uint32_t rec_kind(const uint4& r) { return r.x & 0xffu; }
@@ -158,7 +161,12 @@ __device__ uint32_t lcp_nibbles(const SortView& v, uint32_t j, const uint8_t* ke
 
 }  // namespace
 
-__global__ void __launch_bounds__(kTrieThreads) k_trie_structure(const TrieBatchDev in, const TrieWork w, uint32_t cap) {
+// Shared-memory plan: [pre u64 | idx u32 | kl u8 | lcp u8] x cap for the sort, then (node_cap > 0) the
+// node records and lengths of this trie, so that the two serial passes of thread 0 (skeleton, inner-node
+// sizes) never wait on global memory; tries too large for that (3 n nodes x 20 B) work out of the global
+// node table through the same pointers.
+__global__ void __launch_bounds__(kTrieThreads) k_trie_structure(const TrieBatchDev in, const TrieWork w, uint32_t cap,
+                                                                 uint32_t node_cap) {
   extern __shared__ __align__(16) uint8_t tsm[];
   SortView v;
   v.pre = reinterpret_cast<uint64_t*>(tsm);
@@ -167,8 +175,8 @@ __global__ void __launch_bounds__(kTrieThreads) k_trie_structure(const TrieBatch
   uint8_t* lcp = tsm + 13ull * cap;
   __shared__ uint32_t s_hist[2 * kMaxLevels];
   __shared__ uint32_t s_scan[kTrieThreads];
-  __shared__ uint32_t s_m, s_count;
-  __shared__ unsigned long long s_arena_base;
+  __shared__ uint32_t s_m;
+  __shared__ unsigned long long s_arena_base, s_perms, s_hashed;
 
   const uint32_t t = blockIdx.x;
   const uint32_t first = in.trie_first[t];
@@ -177,10 +185,14 @@ __global__ void __launch_bounds__(kTrieThreads) k_trie_structure(const TrieBatch
   const uint32_t* koff = in.key_off + first;  // local item i: key_bytes[koff[i] .. koff[i+1])
   const uint32_t base = 3u * first;           // node ids of this trie: base + BFS index
   for (uint32_t i = tid; i < 2 * kMaxLevels; i += kTrieThreads) s_hist[i] = 0;
+  if (tid == 0) { s_perms = 0; s_hashed = 0; }
   if (n == 0) {
     if (tid == 0) w.tcount[t] = 0;
     return;
   }
+  const bool in_smem = 3u * n <= node_cap;
+  uint4* R = in_smem ? reinterpret_cast<uint4*>(tsm + ((14ull * cap + 15) & ~15ull)) : w.rec + base;
+  uint32_t* Ln = in_smem ? reinterpret_cast<uint32_t*>(tsm + ((14ull * cap + 15) & ~15ull) + 16ull * node_cap) : w.len + base;
   uint32_t np2 = 2;
   while (np2 < n) np2 <<= 1;
 
@@ -248,63 +260,120 @@ __global__ void __launch_bounds__(kTrieThreads) k_trie_structure(const TrieBatch
   for (uint32_t j = tid; j + 1 < m; j += kTrieThreads) lcp[j] = (uint8_t)lcp_nibbles(v, j, in.key_bytes, koff);
   __syncthreads();
 
-  // ---- skeleton (thread 0): BFS over key ranges; w.off doubles as the queue (lo | hi << 16 | depth << 32)
+  // ---- skeleton: level-synchronous BFS over key ranges inside the CTA.  A pending entry sits in R[id]
+  //      as x = lo | hi << 16, y = depth until it is expanded into the node's record.  Each round
+  //      expands the current frontier [head, tail): leaves one per thread, inner nodes one per warp
+  //      (the lanes scan the range's LCP values together: min-reduce for the extension test, ballot +
+  //      popcount to cut the range into the branch's child groups, which get consecutive ids).
+  __shared__ uint32_t s_tail;
+  __shared__ uint32_t s_round[kMaxLevels + 2];  // s_round[r] = first node id created for round r
+  const uint32_t lane = tid & 31u, warp = tid >> 5;
+  constexpr uint32_t kWarps = kTrieThreads / 32;
   if (tid == 0) {
-    uint32_t head = 0, tail = 0;
-    if (m) w.off[base + tail++] = (uint64_t)m << 16;
-    while (head < tail) {
-      const uint64_t q = w.off[base + head];
-      const uint32_t id = head++;
-      const uint32_t lo = (uint32_t)q & 0xffffu, hi = (uint32_t)(q >> 16) & 0xffffu, d = (uint32_t)(q >> 32);
-      uint4 r = make_uint4(0, kNoItem, 0, 0);
-      if (hi - lo == 1) {
-        r.x = kTLeaf | (d << 16) | ((2u * v.kl[lo] - d) << 24);
-        r.y = first + v.idx[lo];
-      } else {
-        uint32_t c = 255;
-        for (uint32_t j = lo; j + 1 < hi; j++) c = min(c, (uint32_t)lcp[j]);
-        if (c > d) {
-          r.x = kTExt | (d << 16) | ((c - d) << 24);
-          r.y = first + v.idx[lo];
-          r.z = base + tail;
-          w.off[base + tail++] = (uint64_t)lo | ((uint64_t)hi << 16) | ((uint64_t)c << 32);
-        } else {
-          uint32_t l2 = lo;
-          if (2u * v.kl[lo] == d) { r.y = first + v.idx[lo]; l2 = lo + 1; }  // this key ends here: branch value
-          r.x = kTBranch | (d << 16);
-          r.z = base + tail;
-          uint32_t mask = 0, gs = l2;
-          for (uint32_t j = l2; j < hi; j++) {
-            if (j + 1 == hi || lcp[j] == d) {
-              mask |= 1u << key_nib(v, gs, d, in.key_bytes, koff);
-              w.off[base + tail++] = (uint64_t)gs | ((uint64_t)(j + 1) << 16) | ((uint64_t)(d + 1) << 32);
-              gs = j + 1;
-            }
-          }
-          r.w = mask;
-        }
-      }
-      w.rec[base + id] = r;
+    s_tail = m ? 1u : 0u;
+    if (m) R[0] = make_uint4(m << 16, 0, 0, kPending);
+    s_round[0] = 0;
+  }
+  __syncthreads();
+  uint32_t rounds = 0;
+  for (uint32_t head = 0;;) {
+    const uint32_t tail = s_tail;
+    __syncthreads();  // everyone has read the frontier's end before anyone appends to it
+    if (head == tail) break;
+    if (tid == 0) s_round[rounds + 1] = tail;
+    for (uint32_t e = head + tid; e < tail; e += kTrieThreads) {
+      const uint4 q = R[e];
+      const uint32_t lo = q.x & 0xffffu, hi = q.x >> 16, d = q.y;
+      if (hi - lo == 1)
+        R[e] = make_uint4(kTLeaf | (d << 16) | ((2u * v.kl[lo] - d) << 24), first + v.idx[lo], 0, 0);
     }
-    // ---- reverse BFS order: exact encoded length, height, arena offset (relative), level histogram
-    const uint32_t count = tail;
-    unsigned long long bytes = 0, perms = 0, hashed_nodes = 0;
-    for (uint32_t id = count; id-- > 0;) {
-      uint4 r = w.rec[base + id];
-      uint32_t payload, h = 0;
-      if (rec_kind(r) == kTLeaf) {
-        const uint32_t vl = in.value_len[r.y];
-        const uint32_t v0 = vl == 1 ? in.value_bytes[in.value_off[r.y]] : 0u;
-        payload = hp_item_size(rec_pl(r)) + str_item_size(vl, v0);
-      } else if (rec_kind(r) == kTExt) {
-        payload = hp_item_size(rec_pl(r)) + ref_size(w.len[r.z]);
-        h = rec_height(w.rec[r.z]) + 1;
+    __syncthreads();  // leaf records are in place; what is still pending is an inner node
+    for (uint32_t e = head + warp; e < tail; e += kWarps) {
+      const uint4 q = R[e];
+      if (q.w != kPending) continue;
+      const uint32_t lo = q.x & 0xffffu, hi = q.x >> 16, d = q.y;
+      uint32_t c = 255;
+      for (uint32_t j = lo + lane; j + 1 < hi; j += 32) c = min(c, (uint32_t)lcp[j]);
+      for (int o = 16; o; o >>= 1) c = min(c, __shfl_xor_sync(0xffffffffu, c, o));
+      uint4 r = make_uint4(0, kNoItem, 0, 0);
+      if (c > d) {
+        uint32_t at = 0;
+        if (lane == 0) at = atomicAdd(&s_tail, 1u);
+        at = __shfl_sync(0xffffffffu, at, 0);
+        r.x = kTExt | (d << 16) | ((c - d) << 24);
+        r.y = first + v.idx[lo];
+        r.z = base + at;
+        if (lane == 0) R[at] = make_uint4(lo | (hi << 16), c, 0, kPending);
       } else {
-        const uint32_t mask = rec_mask(r), nc = __popc(mask);
+        uint32_t l2 = lo;
+        if (2u * v.kl[lo] == d) { r.y = first + v.idx[lo]; l2 = lo + 1; }  // this key ends here: branch value
+        // pass 1: number of child groups = boundaries j in [l2, hi) with j + 1 == hi or lcp[j] == d
+        uint32_t nc = 0;
+        for (uint32_t b0 = l2; b0 < hi; b0 += 32) {
+          const uint32_t j = b0 + lane;
+          const bool bd = j < hi && (j + 1 == hi || lcp[j] == d);
+          nc += __popc(__ballot_sync(0xffffffffu, bd));
+        }
+        uint32_t fc = 0;
+        if (lane == 0) fc = atomicAdd(&s_tail, nc);
+        fc = __shfl_sync(0xffffffffu, fc, 0);
+        // pass 2: emit the groups in key order
+        uint32_t mask = 0, ord0 = 0, gs_carry = l2;
+        for (uint32_t b0 = l2; b0 < hi; b0 += 32) {
+          const uint32_t j = b0 + lane;
+          const bool bd = j < hi && (j + 1 == hi || lcp[j] == d);
+          const uint32_t bal = __ballot_sync(0xffffffffu, bd);
+          if (bd) {
+            const uint32_t below = bal & ((1u << lane) - 1u);
+            const uint32_t gs = below ? b0 + (31u - __clz(below)) + 1u : gs_carry;
+            mask |= 1u << key_nib(v, gs, d, in.key_bytes, koff);
+            R[fc + ord0 + __popc(below)] = make_uint4(gs | ((j + 1) << 16), d + 1, 0, kPending);
+          }
+          if (bal) gs_carry = b0 + (31u - __clz(bal)) + 1u;
+          ord0 += __popc(bal);
+        }
+        for (int o = 16; o; o >>= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
+        r.x = kTBranch | (d << 16);
+        r.z = base + fc;
+        r.w = mask;
+      }
+      if (lane == 0) R[e] = r;
+    }
+    __syncthreads();
+    head = tail;
+    rounds++;
+  }
+  const uint32_t count = s_tail;
+
+  // ---- leaf lengths (parallel: one global value_len read per leaf, all in flight at once)
+  for (uint32_t id = tid; id < count; id += kTrieThreads) {
+    const uint4 r = R[id];
+    if (rec_kind(r) == kTLeaf) {
+      const uint32_t vl = in.value_len[r.y];
+      const uint32_t v0 = vl == 1 ? in.value_bytes[in.value_off[r.y]] : 0u;
+      const uint32_t payload = hp_item_size(rec_pl(r)) + str_item_size(vl, v0);
+      Ln[id] = hdr_size(payload) + payload;
+    }
+  }
+  __syncthreads();
+
+  // ---- inner nodes, rounds in reverse (children before parents), one thread per node: length, height
+  for (uint32_t rd = rounds; rd-- > 0;) {
+    const uint32_t r0 = s_round[rd], r1 = s_round[rd + 1];
+    for (uint32_t id = r0 + tid; id < r1; id += kTrieThreads) {
+      uint4 r = R[id];
+      if (rec_kind(r) == kTLeaf) continue;
+      uint32_t payload, h = 0;
+      const uint32_t c0 = r.z - base;
+      if (rec_kind(r) == kTExt) {
+        payload = hp_item_size(rec_pl(r)) + ref_size(Ln[c0]);
+        h = rec_height(R[c0]) + 1;
+      } else {
+        const uint32_t nc = __popc(rec_mask(r));
         payload = 16 - nc;
         for (uint32_t c = 0; c < nc; c++) {
-          payload += ref_size(w.len[r.z + c]);
-          h = max(h, rec_height(w.rec[r.z + c]) + 1);
+          payload += ref_size(Ln[c0 + c]);
+          h = max(h, rec_height(R[c0 + c]) + 1);
         }
         if (r.y == kNoItem) payload += 1;
         else {
@@ -312,28 +381,50 @@ __global__ void __launch_bounds__(kTrieThreads) k_trie_structure(const TrieBatch
           payload += str_item_size(vl, vl == 1 ? in.value_bytes[in.value_off[r.y]] : 0u);
         }
       }
-      const uint32_t len = hdr_size(payload) + payload;
-      const uint32_t hashed = (len >= 32 || id == 0) ? 1u : 0u;  // write_node: >= 32 bytes by hash; the root always
       r.x |= h << 8;
-      r.w |= hashed << 16;
-      w.rec[base + id] = r;
-      w.len[base + id] = len;
-      w.off[base + id] = bytes;
-      bytes += (len + 15u) & ~15u;
-      if (hashed) { perms += len / 136u + 1u; hashed_nodes++; }
-      s_hist[2 * h + (hashed ? 0 : 1)]++;
+      R[id] = r;
+      Ln[id] = hdr_size(payload) + payload;
     }
-    s_count = count;
-    w.tcount[t] = count;
-    s_arena_base = atomicAdd(&w.sum->arena_bytes, bytes);
-    atomicAdd(&w.sum->perms, perms);
-    atomicAdd(&w.sum->nodes_hashed, hashed_nodes);
-    atomicAdd(&w.sum->n_nodes, (unsigned long long)count);
+    __syncthreads();
   }
-  __syncthreads();
-  const uint32_t count = s_count;
-  const unsigned long long ab = s_arena_base;
-  for (uint32_t id = tid; id < count; id += kTrieThreads) w.off[base + id] += ab;
+
+  // ---- hashed flag, level histogram, Keccak-f count, arena offsets (block scan over id chunks)
+  {
+    const uint32_t seg = (count + kTrieThreads - 1) / kTrieThreads;
+    const uint32_t s0 = min(count, tid * seg), s1 = min(count, s0 + seg);
+    uint32_t bytes = 0, perms = 0, nh = 0;
+    for (uint32_t id = s0; id < s1; id++) {
+      const uint32_t len = Ln[id];
+      const uint32_t hashed = (len >= 32 || id == 0) ? 1u : 0u;  // write_node: >= 32 bytes by hash; the root always
+      uint4 r = R[id];
+      r.w |= hashed << 16;
+      R[id] = r;
+      bytes += (len + 15u) & ~15u;
+      if (hashed) { perms += len / 136u + 1u; nh++; }
+      atomicAdd(&s_hist[2 * rec_height(r) + (hashed ? 0 : 1)], 1u);
+    }
+    s_scan[tid] = bytes;
+    if (perms) { atomicAdd(&s_perms, (unsigned long long)perms); atomicAdd(&s_hashed, (unsigned long long)nh); }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long acc = 0;
+      for (uint32_t i = 0; i < kTrieThreads; i++) { const uint32_t c = s_scan[i]; s_scan[i] = (uint32_t)acc; acc += c; }
+      w.tcount[t] = count;
+      s_arena_base = atomicAdd(&w.sum->arena_bytes, acc);
+      atomicAdd(&w.sum->perms, s_perms);
+      atomicAdd(&w.sum->nodes_hashed, s_hashed);
+      atomicAdd(&w.sum->n_nodes, (unsigned long long)count);
+    }
+    __syncthreads();
+    unsigned long long o = s_arena_base + s_scan[tid];
+    for (uint32_t id = s0; id < s1; id++) {
+      w.off[base + id] = o;
+      o += (Ln[id] + 15u) & ~15u;
+    }
+  }
+  if (in_smem) {
+    for (uint32_t id = tid; id < count; id += kTrieThreads) { w.rec[base + id] = R[id]; w.len[base + id] = Ln[id]; }
+  }
   for (uint32_t i = tid; i < 2 * kMaxLevels; i += kTrieThreads)
     if (s_hist[i]) atomicAdd(&w.sum->lvl_count[i], s_hist[i]);
 }
@@ -503,11 +594,13 @@ __global__ void __launch_bounds__(256) k_trie_roots(const TrieBatchDev in, const
 }
 
 // ------------------------------------------------------------------ host launchers
-size_t trie_structure_smem(uint32_t cap) { return 14ull * cap; }
+size_t trie_structure_smem(uint32_t cap, uint32_t node_cap) { return ((14ull * cap + 15) & ~15ull) + 20ull * node_cap; }
+// node records live in shared memory while the CTA's footprint stays small enough for several CTAs per SM
+constexpr uint32_t kTrieSmemNodeItems = 1024;
 
 cudaError_t trie_init_device() {
   return cudaFuncSetAttribute(k_trie_structure, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)trie_structure_smem(kTrieMaxItems));
+                              (int)trie_structure_smem(kTrieMaxItems, 3 * kTrieSmemNodeItems));
 }
 
 cudaError_t launch_trie_scan_input(const TrieBatchDev& in, TrieSummary* sum, cudaStream_t st) {
@@ -523,7 +616,8 @@ cudaError_t launch_trie_structure(const TrieBatchDev& in, const TrieWork& w, uin
   if (in.n_tries == 0) return cudaSuccess;
   uint32_t cap = 2;
   while (cap < max_items) cap <<= 1;
-  k_trie_structure<<<in.n_tries, kTrieThreads, trie_structure_smem(cap), st>>>(in, w, cap);
+  const uint32_t node_cap = 3 * std::min(max_items, kTrieSmemNodeItems);  // larger tries use the global table
+  k_trie_structure<<<in.n_tries, kTrieThreads, trie_structure_smem(cap, node_cap), st>>>(in, w, cap, node_cap);
   k_trie_level_scan<<<1, 32, 0, st>>>(w.sum);
   k_trie_level_scatter<<<in.n_tries, 128, 0, st>>>(in, w);
   return cudaGetLastError();
