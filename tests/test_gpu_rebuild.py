@@ -12,7 +12,15 @@ def _kv(z, d):
     return z.KvBatch(d["key_bytes"], d["key_off"], d["value_bytes"], d["value_off"], d["value_len"], d["trie_first"])
 
 
-def test_random_tries_roots_match_oracle(verifier, oracle):
+@pytest.fixture(params=[1, 0], ids=["fused_leaf_hash", "materialised_leaves"])
+def leaf_mode(request, verifier):
+    """both leaf-level paths: K1L (leaves hashed straight from the value arena) and encode + K1"""
+    verifier.set_option("fused_leaf_hash", request.param)
+    yield request.param
+    verifier.set_option("fused_leaf_hash", 1)
+
+
+def test_random_tries_roots_match_oracle(verifier, oracle, leaf_mode):
     import zk_state_proofs_b200 as z
     from tests.test_rebuild_oracle import make_kv, random_tries
     for seed in (5, 6, 7):
@@ -22,6 +30,19 @@ def test_random_tries_roots_match_oracle(verifier, oracle):
         got = verifier.trie_roots(_kv(z, d))
         bad = np.nonzero((got != want).any(axis=1))[0]
         assert len(bad) == 0, [(int(t), len(tries[t])) for t in bad[:10]]
+
+
+def test_leaf_prefix_alignments_all_phases(verifier, oracle, leaf_mode):
+    """every (prefix length mod 16, value length) phase of the fused leaf hash: values of 1..600 bytes under
+    keys of 1, 2, 3 and 32 bytes (path items of different lengths), incl. lengths around the 136-byte rate"""
+    import zk_state_proofs_b200 as z
+    tries = []
+    for klen in (1, 2, 3, 32):
+        for base in range(0, 600, 50):
+            tries.append([(bytes([(7 * i + 1) % 256]) * klen if klen < 32 else bytes([i % 256]) + bytes(31),
+                           bytes([(i * 13 + j) % 256 for j in range(base + i + 1)])) for i in range(50)])
+    kv = z.flatten_kv(tries)
+    assert (verifier.trie_roots(kv) == oracle.trie_roots(kv.as_dict(), nthreads=8)[0]).all()
 
 
 def test_flatten_kv_and_ordered_trie_root(verifier, oracle):
@@ -37,7 +58,7 @@ def test_flatten_kv_and_ordered_trie_root(verifier, oracle):
     assert verifier.trie_roots(z.flatten_kv([])).shape == (0, 32)
 
 
-def test_config4_shaped_blocks_match_oracle_and_close_through_the_verifier(verifier, oracle):
+def test_config4_shaped_blocks_match_oracle_and_close_through_the_verifier(verifier, oracle, leaf_mode):
     import zk_state_proofs_b200 as z
     from workload import gen
     for kind in ("tx", "receipt"):
@@ -79,7 +100,7 @@ def _proofs(b):
              for i in range(int(b.proof_first[q]), int(b.proof_first[q + 1]))] for q in range(b.n_proofs)]
 
 
-def test_get_proof_matches_oracle_and_verifies(verifier, oracle):
+def test_get_proof_matches_oracle_and_verifies(verifier, oracle, leaf_mode):
     """mptv_trie_proofs == eth_trie get_proof as restated by the oracle, node for node, and the batch
     it returns verifies as it is (rebuild -> get_proof -> verify_merkle_proof, all on the GPU)."""
     import random

@@ -71,6 +71,7 @@ struct Rebuild {
   std::vector<cudaEvent_t> lvl_ev;  // 3 per level: before encode, after encode, after keccak
   uint32_t levels = 0, keccak_launches = 0, other_launches = 0;
   bool have_timing = false;
+  bool leaves_in_arena = true;  // false after a fused (K1L) rebuild: hashed leaves were never written
   unsigned long long n_nodes = 0, n_hashed = 0, n_perm = 0, arena_bytes = 0;
   void release() {
     DevBuf* all[] = {&rec, &off, &len, &digests, &tcount, &lvl_list, &sum, &arena, &order, &bins, &in_key_bytes,
@@ -112,6 +113,7 @@ struct mptv_ctx {
   uint64_t chunk_bytes = 96ull << 20;  // node bytes per pipeline chunk of the host-buffer path
   int binning = 1;
   int fused_classify = 1;  // K1 also classifies plain branches / leaves (K2a fast path)
+  int fused_leaf_hash = 1; // rebuild: hash leaves straight from the value arena (K1L), no encode pass
 };
 
 

@@ -15,6 +15,7 @@
 
 #include "keccak_f1600.cuh"
 #include "kernels.h"
+#include "trie_rec.cuh"
 
 namespace mptv {
 
@@ -286,12 +287,162 @@ k_keccak256_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base, co
   }
 }
 
+// ------------------------------------------------------------------ K1L: fused leaf encode + Keccak-256
+// Trie rebuild, leaf level (> 95 % of the bytes of a tx / receipt trie): the leaf node
+//     rlp([hex_prefix(path), value])            eth_trie write_node, Node::Leaf
+// is never materialised.  Each thread builds the <= 42-byte RLP prefix (list header, path item, value
+// header) of its leaf in shared memory and streams the VALUE bytes straight from the caller's value
+// arena through the same per-thread cp.async ring as K1; the byte misalignment between the node and
+// the 16-byte aligned value (the prefix length) is taken out with one funnel shift per absorbed word.
+// This removes one write + one read of every leaf byte from HBM and a whole encode launch.
+constexpr int kLeafHead = 48;                       // room in front of the window for the prefix of block 0
+constexpr int kLeafSlotBytes = kLeafHead + 160;     // ten 16-byte chunks cover 136 bytes at any alignment
+
+// issue the copies for block k: value bytes [136k - P, 136k + 136 - P) clipped to [0, vl)
+__device__ __forceinline__ void stage_leaf_block(uint32_t dst, const uint8_t* val, uint32_t k, uint32_t P, uint32_t vl,
+                                                 bool on) {
+  if (on) {
+    const uint32_t vstart = k ? 136u * k - P : 0u;
+    const uint32_t a = vstart & ~15u;
+    uint32_t e = 136u * k + 136u - P;
+    if (e > vl) e = vl;
+    const uint8_t* s = val + a;
+#pragma unroll
+    for (int c = 0; c < 10; c++)
+      if (a + 16u * c < e) cp_async16(dst + kLeafHead + 16 * c, s + 16 * c);
+  }
+  cp_async_commit();
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kKeccakThreads, kKeccakMinBlocks)
+k_keccak256_leaves(const TrieBatchDev in, const uint4* __restrict__ rec, const uint32_t* __restrict__ node_len,
+                   const uint32_t* __restrict__ order, uint32_t n_nodes, uint8_t* __restrict__ digests) {
+  extern __shared__ __align__(128) uint8_t smem[];  // [stage][thread] slots
+  const int tid = threadIdx.x;
+  const uint32_t slot0 = smem_u32(smem + tid * kLeafSlotBytes);
+  constexpr uint32_t kStageStride = kKeccakThreads * kLeafSlotBytes;
+
+  const uint32_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t slot_idx = tile * kKeccakThreads + tid;
+    const bool have = slot_idx < n_nodes;
+    uint32_t node = 0, len = 0, nb = 0, vl = 0, P = 0;
+    const uint8_t* val = in.value_bytes;
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (have) {
+      node = order[slot_idx];
+      r = rec[node];
+      len = node_len[node];
+      nb = len / 136u + 1u;
+      vl = in.value_len[r.y];
+      val = in.value_bytes + in.value_off[r.y];
+      P = len - vl;  // list header + path item + value header (0 when the value encodes as itself)
+    }
+    uint32_t lo[25], hi[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) { lo[i] = 0; hi[i] = 0; }
+#pragma unroll
+    for (int s = 0; s < kStages; s++) stage_leaf_block(slot0 + s * kStageStride, val, s, P, vl, (uint32_t)s < nb);
+    if (have) {
+      // the prefix, right in front of value byte 0 in the stage-0 slot
+      uint32_t q = slot0 + kLeafHead - P;
+      const uint32_t payload = payload_of(len), hl = len - payload;
+      if (hl == 1) sts8(q, 0xC0u + payload);
+      else {
+        sts8(q, 0xF7u + (hl - 1));
+        for (uint32_t i = 1; i < hl; i++) sts8(q + i, (payload >> (8 * (hl - 1 - i))) & 0xffu);
+      }
+      q += hl;
+      const uint32_t ps = rec_ps(r), pl = rec_pl(r), hpn = pl / 2 + 1;
+      const uint8_t* key = in.key_bytes + in.key_off[r.y];
+      if (hpn > 1) sts8(q++, 0x80u + hpn);
+      for (uint32_t i = 0; i < hpn; i++) sts8(q + i, hp_byte(key, ps, pl, true, i));
+      q += hpn;
+      const uint32_t vh = slot0 + kLeafHead - q;  // bytes left for the value's string header
+      if (vh == 1) sts8(q, 0x80u + vl);
+      else if (vh > 1) {
+        sts8(q, 0xB7u + (vh - 1));
+        for (uint32_t i = 1; i < vh; i++) sts8(q + i, (vl >> (8 * (vh - 1 - i))) & 0xffu);
+      }
+    }
+    for (uint32_t k = 0; k < nb; k++) {
+      const uint32_t s = k % kStages;
+      cp_async_wait<kStages - 1>();
+      const uint32_t base = k ? (uint32_t)kLeafHead + ((136u * k - P) & 15u) : (uint32_t)kLeafHead - P;
+      const uint32_t p = slot0 + s * kStageStride + (base & ~3u);
+      const uint32_t beta = 8u * (base & 3u);
+      const uint32_t valid = len - 136u * k;
+      uint32_t prev = lds32(p);
+      if (valid >= 136u) {
+#pragma unroll
+        for (int j = 0; j < 17; j++) {
+          const uint32_t a = lds32(p + 8 * j + 4), b = lds32(p + 8 * j + 8);
+          lo[j] ^= __funnelshift_r(prev, a, beta);
+          hi[j] ^= __funnelshift_r(a, b, beta);
+          prev = b;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 17; j++) {
+          const uint32_t a = lds32(p + 8 * j + 4), b = lds32(p + 8 * j + 8);
+          uint32_t v[2] = {__funnelshift_r(prev, a, beta), __funnelshift_r(a, b, beta)};
+          prev = b;
+#pragma unroll
+          for (int hlf = 0; hlf < 2; hlf++) {
+            const int wi = 2 * j + hlf;
+            const int keep = (int)valid - 4 * wi;
+            const uint32_t msk = keep >= 4 ? 0xffffffffu : (keep <= 0 ? 0u : ((1u << (8 * keep)) - 1u));
+            uint32_t x = v[hlf] & msk;
+            if ((int)(valid >> 2) == wi) x ^= 1u << (8u * (valid & 3u));
+            v[hlf] = x;
+          }
+          lo[j] ^= v[0];
+          hi[j] ^= v[1];
+        }
+        hi[16] ^= 0x80000000u;
+      }
+      stage_leaf_block(slot0 + s * kStageStride, val, k + kStages, P, vl, k + kStages < nb);
+      keccak_f1600(lo, hi);
+    }
+    cp_async_wait<0>();
+    if (have) {
+      uint4* out = reinterpret_cast<uint4*>(digests + (uint64_t)node * 32u);
+      out[0] = make_uint4(lo[0], hi[0], lo[1], hi[1]);
+      out[1] = make_uint4(lo[2], hi[2], lo[3], hi[3]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host launchers
 size_t keccak_smem_bytes() { return (size_t)kStages * kKeccakThreads * kSlotBytes; }
 
 cudaError_t kernels_init_device() {
-  return cudaFuncSetAttribute(k_keccak256_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)keccak_smem_bytes());
+  cudaError_t e = cudaFuncSetAttribute(k_keccak256_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)keccak_smem_bytes());
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_keccak256_leaves, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              kStages * kKeccakThreads * kLeafSlotBytes);
+}
+
+cudaError_t launch_keccak256_leaves(const TrieBatchDev& in, const uint4* rec, const uint32_t* node_len,
+                                    const uint32_t* order, uint32_t n_nodes, uint8_t* digests, int sm_count,
+                                    cudaStream_t st) {
+  if (n_nodes == 0) return cudaSuccess;
+  const size_t smem = (size_t)kStages * kKeccakThreads * kLeafSlotBytes;
+  uint32_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
+  uint32_t grid = (uint32_t)sm_count * kKeccakMinBlocks;
+  if (grid > n_tiles) grid = n_tiles;
+  k_keccak256_leaves<<<grid, kKeccakThreads, smem, st>>>(in, rec, node_len, order, n_nodes, digests);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_bin_nodes(const uint32_t* node_len, const uint32_t* ids, uint64_t n_nodes,

@@ -109,6 +109,10 @@ struct TrieWork {
   TrieSummary* sum;
 };
 cudaError_t trie_init_device();
+// K1L: digests of the level-0 hashed leaves straight from the key/value arrays (no materialised encoding)
+cudaError_t launch_keccak256_leaves(const TrieBatchDev& in, const uint4* rec, const uint32_t* node_len,
+                                    const uint32_t* order, uint32_t n_nodes, uint8_t* digests, int sm_count,
+                                    cudaStream_t st);
 cudaError_t launch_trie_scan_input(const TrieBatchDev& in, TrieSummary* sum, cudaStream_t st);
 cudaError_t launch_trie_structure(const TrieBatchDev& in, const TrieWork& w, uint32_t max_items, cudaStream_t st);
 cudaError_t launch_trie_encode(const TrieBatchDev& in, const TrieWork& w, const uint32_t* list, uint32_t n_list,
@@ -121,7 +125,7 @@ cudaError_t launch_trie_proof_count(const TrieBatchDev& in, const TrieWork& w, c
 cudaError_t launch_trie_proof_emit(const TrieBatchDev& in, const TrieWork& w, const uint8_t* arena, const uint32_t* target_trie,
                                    const uint8_t* tkey_bytes, const uint32_t* tkey_off, uint32_t n_targets,
                                    const uint32_t* proof_first, const uint64_t* byte_first, uint8_t* out_bytes,
-                                   uint64_t* out_off, uint32_t* out_len, cudaStream_t st);
+                                   uint64_t* out_off, uint32_t* out_len, bool leaves_in_arena, cudaStream_t st);
 
 // integer issue-rate probe (microbench.cu): mode 0 = LOP3, 1 = SHF, 2 = Keccak mix
 cudaError_t run_int_peak(int mode, int sm_count, uint32_t* scratch, cudaStream_t st, double* ops_per_s);

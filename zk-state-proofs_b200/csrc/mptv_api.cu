@@ -156,6 +156,8 @@ int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
     ctx->binning = value ? 1 : 0;
   } else if (!strcmp(name, "fused_classify")) {
     ctx->fused_classify = value ? 1 : 0;
+  } else if (!strcmp(name, "fused_leaf_hash")) {
+    ctx->fused_leaf_hash = value ? 1 : 0;
   } else return MPTV_ERR_ARG;
   return MPTV_OK;
 }

@@ -69,9 +69,13 @@ int rebuild_on_device(mptv_ctx* ctx, Device& d, const TrieBatchDev& in, uint8_t*
   for (uint32_t h = 0; h < levels; h++) {
     const uint32_t nh = hs->lvl_count[2 * h], ni = hs->lvl_count[2 * h + 1];
     const uint32_t* list = w.lvl_list + start;
+    // height 0 = leaves.  Fused path: the >= 32-byte leaves are hashed straight from the value arena
+    // (K1L) and never written; only the inline (< 32 byte) leaves are encoded, for their parents to embed.
+    const bool fused = h == 0 && ctx->fused_leaf_hash;
     CK(cudaEventRecord(rb.lvl_ev[3 * h], st));
-    CK(launch_trie_encode(in, w, list, nh + ni, rb.arena.as<uint8_t>(), st));
-    if (nh + ni) olaunch++;
+    if (fused) CK(launch_trie_encode(in, w, list + nh, ni, rb.arena.as<uint8_t>(), st));
+    else CK(launch_trie_encode(in, w, list, nh + ni, rb.arena.as<uint8_t>(), st));
+    if (fused ? ni : nh + ni) olaunch++;
     CK(cudaEventRecord(rb.lvl_ev[3 * h + 1], st));
     if (nh) {
       const uint32_t* ord = list;
@@ -80,7 +84,8 @@ int rebuild_on_device(mptv_ctx* ctx, Device& d, const TrieBatchDev& in, uint8_t*
         ord = rb.order.as<uint32_t>();
         olaunch += 3;
       }
-      CK(launch_keccak256_nodes(rb.arena.as<uint8_t>(), 0, w.off, w.len, ord, nh, w.digests, nullptr, d.sm_count, st));
+      if (fused) CK(launch_keccak256_leaves(in, w.rec, w.len, ord, nh, w.digests, d.sm_count, st));
+      else CK(launch_keccak256_nodes(rb.arena.as<uint8_t>(), 0, w.off, w.len, ord, nh, w.digests, nullptr, d.sm_count, st));
       klaunch++;
     }
     CK(cudaEventRecord(rb.lvl_ev[3 * h + 2], st));
@@ -89,6 +94,7 @@ int rebuild_on_device(mptv_ctx* ctx, Device& d, const TrieBatchDev& in, uint8_t*
   CK(launch_trie_roots(in, w, roots32, st));
   olaunch++;
   CK(cudaEventRecord(rb.ev_end, st));
+  rb.leaves_in_arena = !ctx->fused_leaf_hash;
   rb.levels = levels; rb.keccak_launches = klaunch; rb.other_launches = olaunch; rb.have_timing = true;
   rb.n_nodes = hs->n_nodes; rb.n_hashed = hs->nodes_hashed; rb.n_perm = hs->perms; rb.arena_bytes = hs->arena_bytes;
   return MPTV_OK;
@@ -300,7 +306,7 @@ int mptv_trie_proofs(mptv_ctx* ctx, const mptv_kv_batch* in, const mptv_proof_ta
   CK(launch_trie_proof_emit(b, w, rb.arena.as<uint8_t>(), rb.q_trie.as<uint32_t>(), rb.q_key_bytes.as<uint8_t>(),
                             rb.q_key_off.as<uint32_t>(), (uint32_t)nq, rb.q_proof_first.as<uint32_t>(),
                             rb.q_byte_first.as<uint64_t>(), rb.q_out_bytes.as<uint8_t>(), rb.q_out_off.as<uint64_t>(),
-                            rb.q_out_len.as<uint32_t>(), st));
+                            rb.q_out_len.as<uint32_t>(), rb.leaves_in_arena, st));
   CK(cudaMemcpyAsync(out->node_bytes, rb.q_out_bytes.p, (size_t)total_bytes + 16, cudaMemcpyDeviceToHost, st));
   if (total_nodes) {
     CK(cudaMemcpyAsync(out->node_off, rb.q_out_off.p, 8 * (size_t)total_nodes, cudaMemcpyDeviceToHost, st));

@@ -26,51 +26,9 @@
 #include <algorithm>
 
 #include "kernels.h"
+#include "trie_rec.cuh"
 
 namespace mptv {
-
-namespace {
-
-// ---- record packing: x = kind | height << 8 | path_start << 16 | path_len << 24
-//                      y = item (global item index; leaf: its key/value, ext: any key below it,
-//                          branch: the key whose value sits in the branch, or kNoItem)
-//                      z = first child (global node id); children are consecutive in BFS order
-//                      w = occupancy mask (branch) | hashed << 16
-constexpr uint32_t kNoItem = 0xffffffffu;
-constexpr uint32_t kPending = 0xffffffffu;  // w of a BFS queue entry that has not been expanded yet
-enum : uint32_t { kTLeaf = 1, kTExt = 2, kTBranch = 3 };
-
-__device__ __forceinline__ uint32_t rec_kind(const uint4& r) { return r.x & 0xffu; }
-__device__ __forceinline__ uint32_t rec_height(const uint4& r) { return (r.x >> 8) & 0xffu; }
-__device__ __forceinline__ uint32_t rec_ps(const uint4& r) { return (r.x >> 16) & 0xffu; }
-__device__ __forceinline__ uint32_t rec_pl(const uint4& r) { return r.x >> 24; }
-__device__ __forceinline__ uint32_t rec_mask(const uint4& r) { return r.w & 0xffffu; }
-__device__ __forceinline__ uint32_t rec_hashed(const uint4& r) { return (r.w >> 16) & 1u; }
-
-// ---- RLP sizes (alloy-rlp / eth_trie write_node)
-__device__ __forceinline__ uint32_t hdr_size(uint32_t n) {
-  return n < 56 ? 1u : (n < 256 ? 2u : (n < 65536 ? 3u : (n < (1u << 24) ? 4u : 5u)));
-}
-__device__ __forceinline__ uint32_t str_item_size(uint32_t n, uint32_t first) {
-  return (n == 1 && first < 0x80) ? 1u : hdr_size(n) + n;
-}
-// hex-prefix encoded path of pl nibbles: pl/2 + 1 bytes (<= 33); a single byte is < 0x80 (flags <= 3)
-__device__ __forceinline__ uint32_t hp_item_size(uint32_t pl) { return pl < 2 ? 1u : 2u + pl / 2; }
-__device__ __forceinline__ uint32_t ref_size(uint32_t child_len) { return child_len < 32 ? child_len : 33u; }
-// payload length of a list whose whole encoding is `len` bytes
-__device__ __forceinline__ uint32_t payload_of(uint32_t len) {
-  return len - 1 < 56 ? len - 1 : (len - 2 < 256 ? len - 2 : (len - 3 < 65536 ? len - 3 : (len - 4 < (1u << 24) ? len - 4 : len - 5)));
-}
-__device__ __forceinline__ uint32_t put_hdr(uint8_t* o, uint32_t n, bool list) {
-  const uint32_t base = list ? 0xC0u : 0x80u;
-  if (n < 56) { o[0] = (uint8_t)(base + n); return 1; }
-  const uint32_t k = hdr_size(n) - 1;
-  o[0] = (uint8_t)(base + 55 + k);
-  for (uint32_t i = 0; i < k; i++) o[1 + i] = (uint8_t)(n >> (8 * (k - 1 - i)));
-  return 1 + k;
-}
-
-}  // namespace
 
 // ------------------------------------------------------------------ input scan
 __global__ void __launch_bounds__(256) k_trie_scan_input(const TrieBatchDev in, TrieSummary* sum) {
@@ -466,20 +424,6 @@ __global__ void __launch_bounds__(128) k_trie_level_scatter(const TrieBatchDev i
 // ------------------------------------------------------------------ encode
 namespace {
 
-// nibble i of item's key
-__device__ __forceinline__ uint32_t item_nib(const uint8_t* key, uint32_t i) {
-  const uint32_t b = key[i >> 1];
-  return (i & 1) ? (b & 15u) : (b >> 4);
-}
-
-// byte i of the hex-prefix encoding of nibbles [ps, ps+pl) of key (Nibbles::encode_compact)
-__device__ __forceinline__ uint32_t hp_byte(const uint8_t* key, uint32_t ps, uint32_t pl, bool leaf, uint32_t i) {
-  const uint32_t odd = pl & 1u;
-  if (i == 0) return (leaf ? 0x20u : 0u) | (odd ? (0x10u | item_nib(key, ps)) : 0u);
-  const uint32_t q = ps + odd + 2 * (i - 1);
-  return (item_nib(key, q) << 4) | item_nib(key, q + 1);
-}
-
 // warp-cooperative copy of n bytes from a 4-byte aligned src to an arbitrarily aligned dst;
 // src must be readable up to the next multiple of 4 after src + n
 __device__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane) {
@@ -514,15 +458,11 @@ __device__ uint32_t warp_put_value(uint8_t* dst, const uint8_t* val, uint32_t vl
 
 }  // namespace
 
-__global__ void __launch_bounds__(256) k_trie_encode(const TrieBatchDev in, const TrieWork w, const uint32_t* __restrict__ list,
-                                                     uint32_t n_list, uint8_t* __restrict__ arena) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (wi >= n_list) return;
-  const uint32_t node = list[wi];
+// one warp writes the RLP encoding of `node` to dst (children are read from `arena` / w.digests)
+__device__ void warp_encode_node(const TrieBatchDev& in, const TrieWork& w, const uint8_t* __restrict__ arena, uint32_t node,
+                                 uint8_t* __restrict__ dst, uint32_t lane) {
   const uint4 r = w.rec[node];
   const uint32_t len = w.len[node];
-  uint8_t* dst = arena + w.off[node];
   const uint32_t kind = rec_kind(r);
   if (kind == kTLeaf || kind == kTExt) {
     const uint8_t* key = in.key_bytes + in.key_off[r.y];
@@ -579,6 +519,15 @@ __global__ void __launch_bounds__(256) k_trie_encode(const TrieBatchDev in, cons
     if (r.y == kNoItem) { if (lane == 16) ip[0] = 0x80; }
     else warp_put_value(dst + hl + voff, val, vl, lane);
   }
+}
+
+__global__ void __launch_bounds__(256) k_trie_encode(const TrieBatchDev in, const TrieWork w, const uint32_t* __restrict__ list,
+                                                     uint32_t n_list, uint8_t* __restrict__ arena) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wi >= n_list) return;
+  const uint32_t node = list[wi];
+  warp_encode_node(in, w, arena, node, arena + w.off[node], lane);
 }
 
 __global__ void __launch_bounds__(256) k_trie_roots(const TrieBatchDev in, const TrieWork w, uint8_t* __restrict__ roots32) {
@@ -737,7 +686,7 @@ __global__ void __launch_bounds__(256) k_trie_proof_emit(const TrieBatchDev in, 
                                                          const uint32_t* __restrict__ tkey_off, uint32_t n_targets,
                                                          const uint32_t* __restrict__ proof_first, const uint64_t* __restrict__ byte_first,
                                                          uint8_t* __restrict__ out_bytes, uint64_t* __restrict__ out_off,
-                                                         uint32_t* __restrict__ out_len) {
+                                                         uint32_t* __restrict__ out_len, int leaves_in_arena) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= n_targets) return;
@@ -745,9 +694,14 @@ __global__ void __launch_bounds__(256) k_trie_proof_emit(const TrieBatchDev in, 
   uint64_t o = byte_first[q];
   proof_walk(in, w, target_trie[q], tkey_bytes + tkey_off[q], tkey_off[q + 1] - tkey_off[q], [&](uint32_t node) {
     const uint32_t len = w.len[node];
-    const uint4* s = reinterpret_cast<const uint4*>(arena + w.off[node]);  // 16-byte aligned slots on both sides
-    uint4* d = reinterpret_cast<uint4*>(out_bytes + o);
-    for (uint32_t i = lane; i < (len + 15u) / 16u; i += 32) d[i] = s[i];
+    if (!leaves_in_arena && (w.rec[node].x & 0xffu) == kTLeaf) {
+      // hashed leaves were digested straight from the value arena (K1L): encode this one now
+      warp_encode_node(in, w, arena, node, out_bytes + o, lane);
+    } else {
+      const uint4* s = reinterpret_cast<const uint4*>(arena + w.off[node]);  // 16-byte aligned slots on both sides
+      uint4* d = reinterpret_cast<uint4*>(out_bytes + o);
+      for (uint32_t i = lane; i < (len + 15u) / 16u; i += 32) d[i] = s[i];
+    }
     if (lane == 0) { out_off[k] = o; out_len[k] = len; }
     k++;
     o += (len + 15u) & ~15u;
@@ -766,10 +720,10 @@ cudaError_t launch_trie_proof_count(const TrieBatchDev& in, const TrieWork& w, c
 cudaError_t launch_trie_proof_emit(const TrieBatchDev& in, const TrieWork& w, const uint8_t* arena, const uint32_t* target_trie,
                                    const uint8_t* tkey_bytes, const uint32_t* tkey_off, uint32_t n_targets,
                                    const uint32_t* proof_first, const uint64_t* byte_first, uint8_t* out_bytes,
-                                   uint64_t* out_off, uint32_t* out_len, cudaStream_t st) {
+                                   uint64_t* out_off, uint32_t* out_len, bool leaves_in_arena, cudaStream_t st) {
   if (n_targets == 0) return cudaSuccess;
   k_trie_proof_emit<<<(n_targets + 7) / 8, 256, 0, st>>>(in, w, arena, target_trie, tkey_bytes, tkey_off, n_targets, proof_first,
-                                                         byte_first, out_bytes, out_off, out_len);
+                                                         byte_first, out_bytes, out_off, out_len, leaves_in_arena ? 1 : 0);
   return cudaGetLastError();
 }
 
