@@ -7,6 +7,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[1, 0], ids=["fast_walk", "cooperative_walk_only"])
+def walk_mode(request, verifier):
+    """both walk configurations: K2f (thread per proof) + K2b on the deferred rest, and K2b on everything"""
+    verifier.set_option("fast_walk", request.param)
+    yield request.param
+    verifier.set_option("fast_walk", 1)
+
+
 def _inputs(z, vs):
     return [z.MerkleProofInput(v["proof_b"], v["root_b"], v["key_b"]) for v in vs]
 
@@ -30,7 +38,7 @@ def test_keccak_digests_match_oracle(verifier, oracle):
 
 
 @pytest.mark.parametrize("lanes", [0, 8, 16, 32])
-def test_golden_vectors_from_reference_elf(verifier, golden, lanes):
+def test_golden_vectors_from_reference_elf(verifier, golden, lanes, walk_mode):
     import zk_state_proofs_b200 as z
     verifier.set_option("lanes_per_proof", lanes)
     vs = golden["vectors"]
@@ -45,7 +53,7 @@ def test_golden_vectors_from_reference_elf(verifier, golden, lanes):
     assert not bad, (len(bad), bad[:10])
 
 
-def test_seeded_corpus_matches_oracle_including_offsets(verifier, oracle):
+def test_seeded_corpus_matches_oracle_including_offsets(verifier, oracle, walk_mode):
     import zk_state_proofs_b200 as z
     from oracle.fuzzgen import corpus
     cases = corpus(2024, oracle.keccak256, 60, 1500, 3000)
@@ -77,7 +85,7 @@ def test_small_chunks_no_binning_unfused_give_identical_results(verifier, golden
         assert (x == y).all() and (x == w).all() and (x == v).all()
 
 
-def test_synthetic_state_proofs_mixed_match_oracle(verifier, oracle):
+def test_synthetic_state_proofs_mixed_match_oracle(verifier, oracle, walk_mode):
     """config-2/3 shaped batch (inclusion, exclusion, all 7 mutators) at a size the oracle does in seconds."""
     from workload import gen
     trie = gen.SynthTrie(300_000, 2, kind=0)
@@ -101,7 +109,7 @@ def _proof_of(b, p):
             for i in range(int(b.proof_first[p]), int(b.proof_first[p + 1]))]
 
 
-def test_nested_account_storage_groups_match_oracle(verifier, oracle):
+def test_nested_account_storage_groups_match_oracle(verifier, oracle, walk_mode):
     """config 3: storage proofs take their root from the verified account leaf (root_from_proof)."""
     from workload import gen
     state, tokens = gen.make_state_and_tokens(100_000, 4, 50_000, seed=3)

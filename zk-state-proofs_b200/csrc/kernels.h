@@ -70,9 +70,11 @@ cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base
 cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
                                const uint32_t* node_len, uint64_t n_nodes, uint32_t* meta, bool only_slow,
                                cudaStream_t st);
-// K2b: wave 0 = proofs with their own root, wave 1 = proofs whose root is another proof's storage_root
+// K2f + K2b: the thread-per-proof chain check decides what it can, K2b the deferred rest.
+// wave 0 = proofs with their own root, wave 1 = proofs whose root is another proof's storage_root
 cudaError_t launch_verify_walk(const DeviceBatch& b, const uint8_t* digests, const uint32_t* meta, int wave,
                                int lanes_per_proof, uint8_t* status, uint64_t* value_off, uint32_t* value_len,
+                               uint32_t* defer /* scratch [1 + n_proofs]; NULL = K2b on every proof */, int sm_count,
                                cudaStream_t st);
 
 // ------------------------------------------------------------------ K4: trie rebuild (rebuild_kernels.cu)

@@ -29,12 +29,14 @@ int pick_lanes(const mptv_ctx* ctx, uint64_t n_nodes, uint64_t n_proofs) {
 
 // The whole device pipeline for one device-resident (slice of a) batch: K0 -> K1 -> K2a -> K2b.
 int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests, DevBuf& meta, DevBuf& order,
-                 DevBuf& bins, uint8_t* status, uint64_t* value_off, uint32_t* value_len, cudaStream_t st,
+                 DevBuf& bins, DevBuf& defer, uint8_t* status, uint64_t* value_off, uint32_t* value_len, cudaStream_t st,
                  bool timed) {
   CK(digests.reserve(32 * (size_t)b.n_nodes + 32));
   CK(meta.reserve(4 * (size_t)b.n_nodes + 4));
   CK(order.reserve(4 * (size_t)b.n_nodes + 4));
   CK(bins.reserve(2 * kNumBins * sizeof(uint32_t)));
+  CK(defer.reserve(4 * (size_t)b.n_proofs + 8));
+  uint32_t* dl = ctx->fast_walk ? defer.as<uint32_t>() : nullptr;
   if (timed) CK(cudaEventRecord(d.ev[0], st));
   const uint32_t* ord = nullptr;
   if (ctx->binning) {
@@ -49,11 +51,13 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
                         ctx->fused_classify != 0, st));
   if (timed) CK(cudaEventRecord(d.ev[3], st));
   const int G = pick_lanes(ctx, b.n_nodes, b.n_proofs);
-  CK(launch_verify_walk(b, digests.as<uint8_t>(), meta.as<uint32_t>(), 0, G, status, value_off, value_len, st));
-  uint32_t other = 1 + 1 + (ctx->binning ? 3 : 0);
+  CK(launch_verify_walk(b, digests.as<uint8_t>(), meta.as<uint32_t>(), 0, G, status, value_off, value_len, dl,
+                        d.sm_count, st));
+  uint32_t other = 1 + 1 + (dl ? 1 : 0) + (ctx->binning ? 3 : 0);
   if (b.root_from_proof) {
-    CK(launch_verify_walk(b, digests.as<uint8_t>(), meta.as<uint32_t>(), 1, G, status, value_off, value_len, st));
-    other++;
+    CK(launch_verify_walk(b, digests.as<uint8_t>(), meta.as<uint32_t>(), 1, G, status, value_off, value_len, dl,
+                          d.sm_count, st));
+    other += dl ? 2 : 1;
   }
   if (timed) {
     CK(cudaEventRecord(d.ev[4], st));
@@ -135,7 +139,7 @@ void mptv_destroy(mptv_ctx* ctx) {
   for (Device& d : ctx->dev) {
     cudaSetDevice(d.id);
     cudaDeviceSynchronize();
-    d.digests.release(); d.meta.release(); d.order.release(); d.bins.release();
+    d.digests.release(); d.meta.release(); d.order.release(); d.bins.release(); d.defer.release();
     for (int k = 0; k < kSlots; k++) d.slot[k].release();
     d.rb.release();
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -156,6 +160,8 @@ int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
     ctx->binning = value ? 1 : 0;
   } else if (!strcmp(name, "fused_classify")) {
     ctx->fused_classify = value ? 1 : 0;
+  } else if (!strcmp(name, "fast_walk")) {
+    ctx->fast_walk = value ? 1 : 0;
   } else if (!strcmp(name, "fused_leaf_hash")) {
     ctx->fused_leaf_hash = value ? 1 : 0;
   } else return MPTV_ERR_ARG;
@@ -181,7 +187,7 @@ int mptv_verify_batch_device(mptv_ctx* ctx, int dev_index, const mptv_batch* in,
   b.proof_first = in->proof_first; b.n_proofs = in->n_proofs; b.roots = in->roots;
   b.key_bytes = in->key_bytes; b.key_off = in->key_off; b.root_from_proof = in->root_from_proof;
   b.byte_base = 0; b.node_base = 0; b.key_base = 0; b.proof_base = 0;
-  return run_pipeline(ctx, d, b, d.digests, d.meta, d.order, d.bins, out->status, out->value_off, out->value_len,
+  return run_pipeline(ctx, d, b, d.digests, d.meta, d.order, d.bins, d.defer, out->status, out->value_off, out->value_len,
                       st, true);
 }
 
@@ -348,7 +354,7 @@ int run_slice(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result* out, 
     b.key_bytes = s.key_bytes.as<uint8_t>(); b.key_off = s.key_off.as<uint32_t>();
     b.root_from_proof = in->root_from_proof ? s.rfp.as<int32_t>() : nullptr;
     b.byte_base = byte0; b.node_base = n0; b.key_base = k0; b.proof_base = c.p0;
-    rc = run_pipeline(ctx, d, b, s.digests, s.meta, s.order, s.bins, s.status.as<uint8_t>(),
+    rc = run_pipeline(ctx, d, b, s.digests, s.meta, s.order, s.bins, s.defer, s.status.as<uint8_t>(),
                       s.value_off.as<uint64_t>(), s.value_len.as<uint32_t>(), st, false);
     if (rc != MPTV_OK) return rc;
     CK(s.h_status.reserve(np));

@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace mptv {
@@ -225,18 +227,14 @@ __device__ __forceinline__ uint32_t key_nibble(const uint8_t* key, uint32_t klen
 #define MPTV_WALK_MINB 4  // measured on B200: 4 x 256 threads / SM beats 2, 3, 5, 6, 8 (tools/ sweep, r01)
 #endif
 template <int G>
-__global__ void __launch_bounds__(256, MPTV_WALK_MINB)
-k_verify_walk(const DeviceBatch b, int wave, const uint8_t* __restrict__ digests,
-              const uint32_t* __restrict__ meta, uint8_t* status_out, uint64_t* value_off_out,
-              uint32_t* value_len_out) {
+__device__ void walk_one(const DeviceBatch& b, int wave, const Group<G>& g, const uint64_t p,
+                         const uint8_t* __restrict__ digests, const uint32_t* __restrict__ meta, uint8_t* status_out,
+                         uint64_t* value_off_out, uint32_t* value_len_out) {
   const uint8_t* __restrict__ node_bytes = b.node_bytes - b.byte_base;  // indexed by GLOBAL offsets
   const uint64_t* __restrict__ node_off = b.node_off;
   const uint32_t* __restrict__ node_len = b.node_len;
   const uint32_t* __restrict__ proof_first = b.proof_first;
   const int32_t* __restrict__ root_from_proof = b.root_from_proof;
-  const Group<G> g;
-  const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  if (p >= b.n_proofs) return;  // uniform per group
   const bool dependent = root_from_proof != nullptr && root_from_proof[p] >= 0;
   if (dependent != (wave == 1)) return;
 
@@ -499,6 +497,128 @@ k_verify_walk(const DeviceBatch b, int wave, const uint8_t* __restrict__ digests
   }
 }
 
+// list == NULL: every proof of the batch (filtered by wave); else the *count proofs K2f deferred.
+// Persistent: each group of G lanes strides over its share of the work list.
+template <int G>
+__global__ void __launch_bounds__(256, MPTV_WALK_MINB)
+k_verify_walk(const DeviceBatch b, int wave, const uint8_t* __restrict__ digests,
+              const uint32_t* __restrict__ meta, uint8_t* status_out, uint64_t* value_off_out,
+              uint32_t* value_len_out, const uint32_t* __restrict__ list, const uint32_t* __restrict__ count) {
+  const Group<G> g;
+  const uint64_t n = list ? (uint64_t)*count : b.n_proofs;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x / G;
+  for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; i < n; i += stride)  // uniform per group
+    walk_one<G>(b, wave, g, list ? (uint64_t)list[i] : i, digests, meta, status_out, value_off_out, value_len_out);
+}
+
+// ------------------------------------------------------------------ K2f: one thread per proof, the common case
+// A well-formed proof as eth_trie's get_proof emits it is a CHAIN: node 0 hashes to the root, node i is
+// a plain branch (16 x {empty | 32-byte hash}, no value) whose child for the key's nibble i is the
+// hash of node i+1, and the chain ends in a plain leaf or an empty slot.  For such a proof the
+// reference's hash-keyed lookups (R5-R8) can only ever find node i+1 (or a byte-identical copy), so
+// the verdict and value follow from comparing each link with the NEXT digest -- one thread, no
+// shuffles, ~40 instructions per level.  Anything else (shuffled or junk-interleaved order,
+// extensions, inline children, branch values, short nodes, non-canonical roots, decode errors,
+// missing nodes, tampered bytes) is not judged here: the proof is appended to the deferred list and
+// the cooperative kernel K2b, which implements the full rule set, decides it.
+__device__ __forceinline__ bool eq32_unaligned(const uint8_t* q, const uint8_t* d32 /* 16-byte aligned */) {
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)3);
+  const uint32_t sh = 8u * (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3);
+  const uint4 x = __ldg(reinterpret_cast<const uint4*>(d32)), y = __ldg(reinterpret_cast<const uint4*>(d32) + 1);
+  uint32_t w[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) w[i] = __ldg(wp + i);
+  const uint32_t d[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+  uint32_t diff = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) diff |= __funnelshift_r(w[i], w[i + 1], sh) ^ d[i];
+  return diff == 0;
+}
+
+// true: decided (outputs written); false: defer to K2b
+__device__ bool fast_one(const DeviceBatch& b, uint64_t p, bool dependent, const uint8_t* __restrict__ digests,
+                         const uint32_t* __restrict__ meta, uint8_t* status_out, uint64_t* value_off_out,
+                         uint32_t* value_len_out) {
+  const uint8_t* __restrict__ node_bytes = b.node_bytes - b.byte_base;
+  const uint32_t a = b.proof_first[p] - b.node_base, n = b.proof_first[p + 1] - b.proof_first[p];
+  if (n == 0) return false;
+  const uint8_t* key = b.key_bytes + (b.key_off[p] - b.key_base);
+  const uint32_t klen = b.key_off[p + 1] - b.key_off[p];
+  const uint8_t* rp = b.roots + 32 * p;
+  if (dependent) {
+    const uint64_t d = (uint64_t)b.root_from_proof[p] - b.proof_base;
+    if (status_out[d] != kStOk) return false;
+    const uint32_t so = account_storage_root_off(node_bytes + value_off_out[d], value_len_out[d]);
+    if (so == 0xffffffffu) return false;
+    rp = node_bytes + value_off_out[d] + so;
+  }
+  if (!eq32_unaligned(rp, digests + 32ull * a)) return false;  // lib.rs:14: node 0 must be the root
+  uint32_t idx = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t m = meta[a + i];
+    if (m == kMetaSlow || meta_dec(m) != kDecOk) return false;
+    const uint32_t nl = b.node_len[a + i];
+    if (i == 0 ? !meta_canon(m) : nl < 32) return false;  // lib.rs:19 on the root; R9 admission otherwise
+    const uint64_t off = b.node_off[a + i];
+    if (meta_kind(m) == kKindBranch && meta_fast(m)) {
+      const uint32_t nib = key_nibble(key, klen, idx);
+      const uint32_t mk = meta_mask(m);
+      if (nib == 16 || !((mk >> nib) & 1u)) {  // R14 (no value in a plain branch) / R15
+        status_out[p] = (uint8_t)kStKeyNotFound; value_off_out[p] = 0; value_len_out[p] = 0;
+        return true;
+      }
+      if (i + 1 >= n) return false;
+      const uint8_t* link = node_bytes + off + meta_hdr(m) + nib + 32u * __popc(mk & ((1u << nib) - 1u)) + 1;
+      if (!eq32_unaligned(link, digests + 32ull * (a + i + 1))) return false;
+      idx++;
+    } else if (meta_kind(m) == kKindLeaf) {
+      const uint8_t* nb = node_bytes + off;
+      Hdr lh, ph, ch;
+      rlp_hdr(nb, nl, lh);  // validated by K1 / K2a
+      const uint32_t it0 = lh.hdr_len;
+      rlp_hdr(nb + it0, nl - it0, ph);
+      const uint8_t* pp = nb + it0 + ph.hdr_len;
+      const uint32_t odd = (ldb(pp) >> 4) & 1;
+      const uint32_t nn = (ph.payload_len - 1) * 2 + odd;
+      bool ok = nn == 2 * klen - idx;  // R12: the whole remaining path, length and nibbles
+      for (uint32_t t = 0; ok && t < nn; t++) {
+        const uint32_t qn = t + 2 - odd;
+        const uint32_t pb = ldb(pp + (qn >> 1));
+        ok = ((qn & 1) ? (pb & 15) : (pb >> 4)) == key_nibble(key, klen, idx + t);
+      }
+      if (!ok) { status_out[p] = (uint8_t)kStKeyNotFound; value_off_out[p] = 0; value_len_out[p] = 0; return true; }
+      const uint32_t it1 = it0 + ph.hdr_len + ph.payload_len;
+      rlp_hdr(nb + it1, nl - it1, ch);
+      status_out[p] = (uint8_t)kStOk;
+      if (ch.payload_len == 1) { value_off_out[p] = off + it1; value_len_out[p] = ch.hdr_len + 1; }  // R20
+      else { value_off_out[p] = off + it1 + ch.hdr_len; value_len_out[p] = ch.payload_len; }
+      return true;
+    } else return false;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(256) k_verify_fast(const DeviceBatch b, int wave, const uint8_t* __restrict__ digests,
+                                                     const uint32_t* __restrict__ meta, uint8_t* status_out,
+                                                     uint64_t* value_off_out, uint32_t* value_len_out,
+                                                     uint32_t* __restrict__ defer_list, uint32_t* __restrict__ defer_count) {
+  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool defer = false;
+  if (p < b.n_proofs) {
+    const bool dependent = b.root_from_proof != nullptr && b.root_from_proof[p] >= 0;
+    if (dependent == (wave == 1))
+      defer = !fast_one(b, p, dependent, digests, meta, status_out, value_off_out, value_len_out);
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, defer);
+  if (bal) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == (uint32_t)(__ffs(bal) - 1)) base = atomicAdd(defer_count, (uint32_t)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+    if (defer) defer_list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)p;
+  }
+}
+
 // ------------------------------------------------------------------ host launchers
 cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
                                const uint32_t* node_len, uint64_t n_nodes, uint32_t* meta, bool only_slow,
@@ -511,13 +631,24 @@ cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, co
 
 cudaError_t launch_verify_walk(const DeviceBatch& b, const uint8_t* digests, const uint32_t* meta, int wave,
                                int lanes_per_proof, uint8_t* status, uint64_t* value_off, uint32_t* value_len,
-                               cudaStream_t st) {
+                               uint32_t* defer /* [1 + n_proofs] or NULL = no fast path */, int sm_count, cudaStream_t st) {
   if (b.n_proofs == 0) return cudaSuccess;
   const int G = lanes_per_proof;
   const uint64_t threads = b.n_proofs * (uint64_t)G;
-  const unsigned blocks = (unsigned)((threads + 255) / 256);
+  uint64_t blocks = (threads + 255) / 256;
+  const uint32_t* list = nullptr;
+  const uint32_t* count = nullptr;
+  if (defer) {
+    cudaError_t e = cudaMemsetAsync(defer, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    k_verify_fast<<<(unsigned)((b.n_proofs + 255) / 256), 256, 0, st>>>(b, wave, digests, meta, status, value_off, value_len,
+                                                                        defer + 1, defer);
+    list = defer + 1;
+    count = defer;
+    blocks = std::min<uint64_t>(blocks, (uint64_t)sm_count * MPTV_WALK_MINB);  // the deferred list is short: one resident wave
+  }
 #define MPTV_WALK(GG) \
-  k_verify_walk<GG><<<blocks, 256, 0, st>>>(b, wave, digests, meta, status, value_off, value_len)
+  k_verify_walk<GG><<<(unsigned)blocks, 256, 0, st>>>(b, wave, digests, meta, status, value_off, value_len, list, count)
   if (G == 8) MPTV_WALK(8);
   else if (G == 16) MPTV_WALK(16);
   else MPTV_WALK(32);
