@@ -287,7 +287,8 @@ __device__ void walk_one(const DeviceBatch& b, int wave, const Group<G>& g, cons
     uint32_t w = 0;
     if (g.lig < 8) {
       const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)3) + g.lig;
-      w = __funnelshift_r(__ldg(wp), __ldg(wp + 1), 8u * (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3));
+      const uint32_t sh = 8u * (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3);
+      w = __funnelshift_r(__ldg(wp), sh ? __ldg(wp + 1) : 0u, sh);  // aligned: never read past the 32 bytes
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) h[i] = g.bcast(w, i);
@@ -309,7 +310,8 @@ __device__ void walk_one(const DeviceBatch& b, int wave, const Group<G>& g, cons
       const uint32_t sh = 8u * (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3);
       uint32_t w[9];
 #pragma unroll
-      for (int i = 0; i < 9; i++) w[i] = __ldg(wp + i);
+      for (int i = 0; i < 8; i++) w[i] = __ldg(wp + i);
+      w[8] = sh ? __ldg(wp + 8) : 0u;
 #pragma unroll
       for (int i = 0; i < 8; i++) sl[i] = __funnelshift_r(w[i], w[i + 1], sh);
       have_spec = true;
@@ -527,7 +529,8 @@ __device__ __forceinline__ bool eq32_unaligned(const uint8_t* q, const uint8_t* 
   const uint4 x = __ldg(reinterpret_cast<const uint4*>(d32)), y = __ldg(reinterpret_cast<const uint4*>(d32) + 1);
   uint32_t w[9];
 #pragma unroll
-  for (int i = 0; i < 9; i++) w[i] = __ldg(wp + i);
+  for (int i = 0; i < 8; i++) w[i] = __ldg(wp + i);
+  w[8] = sh ? __ldg(wp + 8) : 0u;  // an aligned reference ends exactly at its 8th word: never read past it
   const uint32_t d[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
   uint32_t diff = 0;
 #pragma unroll
