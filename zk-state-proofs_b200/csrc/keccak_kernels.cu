@@ -202,14 +202,27 @@ __device__ __forceinline__ void classify_block(uint32_t p, uint32_t k, uint32_t 
 __global__ void __launch_bounds__(kKeccakThreads, kKeccakMinBlocks)
 k_keccak256_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base, const uint64_t* __restrict__ node_off,
                   const uint32_t* __restrict__ node_len, const uint32_t* __restrict__ order,
-                  uint64_t n_nodes, uint8_t* __restrict__ digests, uint32_t* __restrict__ meta_out) {
+                  uint64_t n_nodes, uint8_t* __restrict__ digests, uint32_t* __restrict__ meta_out,
+                  uint32_t* __restrict__ tile_counter) {
   extern __shared__ __align__(128) uint8_t smem[];  // [stage][thread] slots
+  __shared__ uint32_t s_tile;
   const int tid = threadIdx.x;
   const uint32_t slot0 = smem_u32(smem + tid * kSlotBytes);
   constexpr uint32_t kStageStride = kKeccakThreads * kSlotBytes;
 
+  // Tiles of 128 nodes are handed out by an atomic counter: with the nodes sorted by DESCENDING block
+  // count this is longest-processing-time-first scheduling, so the CTAs finish together (a static
+  // round-robin leaves the CTA that draws the longest tile of every round far behind on long-tailed
+  // inputs such as receipt tries).
   const uint64_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
-  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (uint64_t tile = blockIdx.x;; tile += gridDim.x) {
+    if (tile_counter) {
+      __syncthreads();
+      if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+      __syncthreads();
+      tile = s_tile;
+    }
+    if (tile >= n_tiles) break;
     const uint64_t slot_idx = tile * kKeccakThreads + tid;
     const bool have = slot_idx < n_nodes;
     uint32_t node = 0, len = 0, nb = 0;
@@ -325,14 +338,23 @@ __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
 
 __global__ void __launch_bounds__(kKeccakThreads, kKeccakMinBlocks)
 k_keccak256_leaves(const TrieBatchDev in, const uint4* __restrict__ rec, const uint32_t* __restrict__ node_len,
-                   const uint32_t* __restrict__ order, uint32_t n_nodes, uint8_t* __restrict__ digests) {
+                   const uint32_t* __restrict__ order, uint32_t n_nodes, uint8_t* __restrict__ digests,
+                   uint32_t* __restrict__ tile_counter) {
   extern __shared__ __align__(128) uint8_t smem[];  // [stage][thread] slots
+  __shared__ uint32_t s_tile;
   const int tid = threadIdx.x;
   const uint32_t slot0 = smem_u32(smem + tid * kLeafSlotBytes);
   constexpr uint32_t kStageStride = kKeccakThreads * kLeafSlotBytes;
 
   const uint32_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (uint32_t tile = blockIdx.x;; tile += gridDim.x) {  // dynamic tiles: see k_keccak256_nodes
+    if (tile_counter) {
+      __syncthreads();
+      if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+      __syncthreads();
+      tile = s_tile;
+    }
+    if (tile >= n_tiles) break;
     const uint32_t slot_idx = tile * kKeccakThreads + tid;
     const bool have = slot_idx < n_nodes;
     uint32_t node = 0, len = 0, nb = 0, vl = 0, P = 0;
@@ -434,14 +456,18 @@ cudaError_t kernels_init_device() {
 }
 
 cudaError_t launch_keccak256_leaves(const TrieBatchDev& in, const uint4* rec, const uint32_t* node_len,
-                                    const uint32_t* order, uint32_t n_nodes, uint8_t* digests, int sm_count,
-                                    cudaStream_t st) {
+                                    const uint32_t* order, uint32_t n_nodes, uint8_t* digests, uint32_t* tile_counter,
+                                    int sm_count, cudaStream_t st) {
   if (n_nodes == 0) return cudaSuccess;
+  if (tile_counter) {
+    cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+  }
   const size_t smem = (size_t)kStages * kKeccakThreads * kLeafSlotBytes;
   uint32_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
   uint32_t grid = (uint32_t)sm_count * kKeccakMinBlocks;
   if (grid > n_tiles) grid = n_tiles;
-  k_keccak256_leaves<<<grid, kKeccakThreads, smem, st>>>(in, rec, node_len, order, n_nodes, digests);
+  k_keccak256_leaves<<<grid, kKeccakThreads, smem, st>>>(in, rec, node_len, order, n_nodes, digests, tile_counter);
   return cudaGetLastError();
 }
 
@@ -461,14 +487,19 @@ cudaError_t launch_bin_nodes(const uint32_t* node_len, const uint32_t* ids, uint
 
 cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
                                    const uint32_t* node_len, const uint32_t* order, uint64_t n_nodes,
-                                   uint8_t* digests, uint32_t* meta, int sm_count, cudaStream_t st) {
+                                   uint8_t* digests, uint32_t* meta, uint32_t* tile_counter, int sm_count,
+                                   cudaStream_t st) {
   if (n_nodes == 0) return cudaSuccess;
+  if (tile_counter) {
+    cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+  }
   size_t smem = keccak_smem_bytes();
   uint64_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
   uint64_t grid = (uint64_t)sm_count * kKeccakMinBlocks;  // persistent: one wave of resident CTAs
   if (grid > n_tiles) grid = n_tiles;
   k_keccak256_nodes<<<(unsigned)grid, kKeccakThreads, smem, st>>>(node_bytes, byte_base, node_off, node_len, order,
-                                                                n_nodes, digests, meta);
+                                                                n_nodes, digests, meta, tile_counter);
   return cudaGetLastError();
 }
 

@@ -7,6 +7,7 @@
 namespace mptv {
 
 constexpr int kNumBins = 128;            // rate-block-count bins (K0)
+constexpr int kBinScratchWords = 2 * kNumBins + 4;  // hist | cursor | K1 tile counter
 constexpr int kBinNodesPerBlock = 4096;  // nodes handled by one CTA of the binning kernels
 constexpr int kKeccakThreads = 128;      // K1 CTA size: one node per thread
 constexpr int kKeccakMinBlocks = 4;      // resident CTAs / SM  (=> <= 128 registers / thread)
@@ -64,7 +65,8 @@ cudaError_t launch_bin_nodes(const uint32_t* node_len, const uint32_t* ids, uint
 // given, meta[i] receives the K2a record of plain branches / plain leaves and kMetaSlow otherwise.
 cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
                                    const uint32_t* node_len, const uint32_t* order, uint64_t n_nodes,
-                                   uint8_t* digests, uint32_t* meta, int sm_count, cudaStream_t st);
+                                   uint8_t* digests, uint32_t* meta, uint32_t* tile_counter /* 1 u32 of scratch or NULL */,
+                                   int sm_count, cudaStream_t st);
 
 // K2a: meta[i] = eager-decode record of node i.  only_slow: leave records != kMetaSlow untouched
 cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
@@ -113,8 +115,8 @@ struct TrieWork {
 cudaError_t trie_init_device();
 // K1L: digests of the level-0 hashed leaves straight from the key/value arrays (no materialised encoding)
 cudaError_t launch_keccak256_leaves(const TrieBatchDev& in, const uint4* rec, const uint32_t* node_len,
-                                    const uint32_t* order, uint32_t n_nodes, uint8_t* digests, int sm_count,
-                                    cudaStream_t st);
+                                    const uint32_t* order, uint32_t n_nodes, uint8_t* digests, uint32_t* tile_counter,
+                                    int sm_count, cudaStream_t st);
 cudaError_t launch_trie_scan_input(const TrieBatchDev& in, TrieSummary* sum, cudaStream_t st);
 cudaError_t launch_trie_structure(const TrieBatchDev& in, const TrieWork& w, uint32_t max_items, cudaStream_t st);
 cudaError_t launch_trie_encode(const TrieBatchDev& in, const TrieWork& w, const uint32_t* list, uint32_t n_list,

@@ -34,7 +34,7 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
   CK(digests.reserve(32 * (size_t)b.n_nodes + 32));
   CK(meta.reserve(4 * (size_t)b.n_nodes + 4));
   CK(order.reserve(4 * (size_t)b.n_nodes + 4));
-  CK(bins.reserve(2 * kNumBins * sizeof(uint32_t)));
+  CK(bins.reserve(kBinScratchWords * sizeof(uint32_t)));
   CK(defer.reserve(4 * (size_t)b.n_proofs + 8));
   uint32_t* dl = ctx->fast_walk ? defer.as<uint32_t>() : nullptr;
   if (timed) CK(cudaEventRecord(d.ev[0], st));
@@ -45,7 +45,8 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
   }
   if (timed) CK(cudaEventRecord(d.ev[1], st));
   CK(launch_keccak256_nodes(b.node_bytes, b.byte_base, b.node_off, b.node_len, ord, b.n_nodes,
-                            digests.as<uint8_t>(), ctx->fused_classify ? meta.as<uint32_t>() : nullptr, d.sm_count, st));
+                            digests.as<uint8_t>(), ctx->fused_classify ? meta.as<uint32_t>() : nullptr,
+                            bins.as<uint32_t>() + 2 * kNumBins, d.sm_count, st));
   if (timed) CK(cudaEventRecord(d.ev[2], st));
   CK(launch_parse_nodes(b.node_bytes, b.byte_base, b.node_off, b.node_len, b.n_nodes, meta.as<uint32_t>(),
                         ctx->fused_classify != 0, st));
@@ -199,7 +200,7 @@ int mptv_keccak256_batch_device(mptv_ctx* ctx, int dev_index, const uint8_t* nod
   CK(cudaSetDevice(d.id));
   cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
   CK(d.order.reserve(4 * (size_t)n_nodes + 4));
-  CK(d.bins.reserve(2 * kNumBins * sizeof(uint32_t)));
+  CK(d.bins.reserve(kBinScratchWords * sizeof(uint32_t)));
   CK(cudaEventRecord(d.ev[0], st));
   const uint32_t* ord = nullptr;
   if (ctx->binning) {
@@ -207,7 +208,8 @@ int mptv_keccak256_batch_device(mptv_ctx* ctx, int dev_index, const uint8_t* nod
     ord = d.order.as<uint32_t>();
   }
   CK(cudaEventRecord(d.ev[1], st));
-  CK(launch_keccak256_nodes(node_bytes, 0, node_off, node_len, ord, n_nodes, digests32, nullptr, d.sm_count, st));
+  CK(launch_keccak256_nodes(node_bytes, 0, node_off, node_len, ord, n_nodes, digests32, nullptr,
+                            d.bins.as<uint32_t>() + 2 * kNumBins, d.sm_count, st));
   CK(cudaEventRecord(d.ev[2], st));
   CK(cudaEventRecord(d.ev[3], st));
   CK(cudaEventRecord(d.ev[4], st));
@@ -438,7 +440,7 @@ int mptv_keccak256_batch(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node
   CK(s.node_len.reserve(4 * n_nodes));
   CK(s.digests.reserve(32 * n_nodes));
   CK(s.order.reserve(4 * n_nodes));
-  CK(s.bins.reserve(2 * kNumBins * sizeof(uint32_t)));
+  CK(s.bins.reserve(kBinScratchWords * sizeof(uint32_t)));
   CK(cudaMemsetAsync(s.node_bytes.p, 0, padded + 16, st));
   CK(cudaMemcpyAsync(s.node_bytes.p, node_bytes, node_bytes_len, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(s.node_off.p, node_off, 8 * n_nodes, cudaMemcpyHostToDevice, st));
@@ -449,7 +451,7 @@ int mptv_keccak256_batch(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node
     ord = s.order.as<uint32_t>();
   }
   CK(launch_keccak256_nodes(s.node_bytes.as<uint8_t>(), 0, s.node_off.as<uint64_t>(), s.node_len.as<uint32_t>(), ord,
-                            n_nodes, s.digests.as<uint8_t>(), nullptr, d.sm_count, st));
+                            n_nodes, s.digests.as<uint8_t>(), nullptr, s.bins.as<uint32_t>() + 2 * kNumBins, d.sm_count, st));
   CK(cudaMemcpyAsync(digests32, s.digests.p, 32 * n_nodes, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return MPTV_OK;

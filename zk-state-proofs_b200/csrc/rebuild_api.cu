@@ -30,7 +30,7 @@ int rebuild_on_device(mptv_ctx* ctx, Device& d, const TrieBatchDev& in, uint8_t*
   CK(rb.digests.reserve(32 * 3 * N + 32));
   CK(rb.lvl_list.reserve(4 * 3 * N + 4));
   CK(rb.tcount.reserve(4 * T + 4));
-  CK(rb.bins.reserve(2 * kNumBins * sizeof(uint32_t)));
+  CK(rb.bins.reserve(kBinScratchWords * sizeof(uint32_t)));
   TrieWork w;
   w.rec = rb.rec.as<uint4>(); w.off = rb.off.as<uint64_t>(); w.len = rb.len.as<uint32_t>();
   w.digests = rb.digests.as<uint8_t>(); w.tcount = rb.tcount.as<uint32_t>(); w.lvl_list = rb.lvl_list.as<uint32_t>();
@@ -84,8 +84,9 @@ int rebuild_on_device(mptv_ctx* ctx, Device& d, const TrieBatchDev& in, uint8_t*
         ord = rb.order.as<uint32_t>();
         olaunch += 3;
       }
-      if (fused) CK(launch_keccak256_leaves(in, w.rec, w.len, ord, nh, w.digests, d.sm_count, st));
-      else CK(launch_keccak256_nodes(rb.arena.as<uint8_t>(), 0, w.off, w.len, ord, nh, w.digests, nullptr, d.sm_count, st));
+      uint32_t* tiles = rb.bins.as<uint32_t>() + 2 * kNumBins;
+      if (fused) CK(launch_keccak256_leaves(in, w.rec, w.len, ord, nh, w.digests, tiles, d.sm_count, st));
+      else CK(launch_keccak256_nodes(rb.arena.as<uint8_t>(), 0, w.off, w.len, ord, nh, w.digests, nullptr, tiles, d.sm_count, st));
       klaunch++;
     }
     CK(cudaEventRecord(rb.lvl_ev[3 * h + 2], st));
