@@ -12,6 +12,7 @@ BASELINE.json configs[1] -- a batch of 1 M account proofs against a synthetic 10
 the whole verification hot path (K0 binning, K1 Keccak-256 of every node, K2a decode, K2b walk)
 over that batch.  The 3 GB node arena is far larger than L2 (126 MB), so every step streams from HBM.
 --workload selects the other BASELINE.json configs (same JSON shape):
+  config1  ONE tx-inclusion proof (index 15 of a synthetic 200-tx block trie) per call: call latency
   config3  4 M nested account + storage-slot proofs (1 M groups of 1 + 3), 80/10/10 incl/excl/mutated
   config4  tx + receipt trie root rebuild for 10 k blocks x 300 (metric: tries/s)
   config5  64 M mixed account/storage proofs, strong scaling: each rank verifies 64 M / N proofs per
@@ -49,7 +50,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"])
+    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3", "config4", "config5"])
     ap.add_argument("--accounts", type=int, default=10_000_000)
     ap.add_argument("--proofs", type=int, default=0, help="proofs per GPU per pass (0 = the config's size)")
     ap.add_argument("--slots", type=int, default=1_000_000, help="slots per ERC-20 storage trie (config3/5)")
@@ -72,6 +73,9 @@ def n_proofs_of(a):
 
 
 def workload_name(a):
+    if a.workload == "config1":
+        return ("config1: single tx inclusion proof via verify_merkle_proof (index 15 of a synthetic 200-tx block "
+                "trie, txs 100-300 B, seed 1), one proof per call")
     if a.workload == "config2":
         return (f"config2: {n_proofs_of(a)} account proofs vs synthetic {a.accounts}-account state trie "
                 f"(key=keccak(address), value=account RLP), seed 2")
@@ -221,6 +225,70 @@ def sub_kv(kv, n_tries):
                      kv.trie_first[:n_tries + 1])
 
 
+def config1_input():
+    """200-tx block, prove index 15 (trie-utils/tests/transaction.rs:13); the proof comes from the committed
+    golden vectors (built by oracle/gen_golden.py and judged by the reference ELF)"""
+    import gzip
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "verify_vectors.json.gz"), "rb") as f:
+        vs = json.loads(f.read())["vectors"]
+    v = next(v for v in vs if v["tag"] == "config1/tx15")
+    return bytes.fromhex(v["root"]), [bytes.fromhex(n) for n in v["proof"]], bytes.fromhex(v["key"]), bytes.fromhex(v["value"])
+
+
+def main_single(a):
+    """config 1: latency of ONE verify_merkle_proof call through the public API (host buffers in, value out)"""
+    import torch
+    import zk_state_proofs_b200 as z
+    rank, world, local = dist_setup()
+    ver = z.Verifier([local])
+    root, proof, key, want = config1_input()
+    inp = z.MerkleProofInput(proof, root, key)
+    b = z.flatten([inp])
+    for _ in range(max(a.warmup, 3) * 20):
+        ver.verify_batch(b)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    n_calls = max(a.steps, 1) * 200
+    t_begin = time.time()
+    t0 = time.perf_counter()
+    for _ in range(n_calls):
+        st, voff, vlen = ver.verify_batch(b)
+    dt = (time.perf_counter() - t0) / n_calls
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end)
+    assert st[0] == 0 and b.value(int(voff[0]), int(vlen[0])) == want
+    assert ver.verify_merkle_proof(root, proof, key) == want
+    h2d = sum(int(getattr(b, k).nbytes) for k in ["node_bytes", "node_off", "node_len", "proof_first", "roots", "key_off"]) + len(key)
+    line = dict(metric=METRIC, value=1.0 / dt, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
+                ms_per_step=dt * 1e3 * 200, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u32",
+                data="synthetic",
+                config=dict(workload=workload_name(a), calls_per_step=200, nodes=b.n_nodes, keccak_f=b.n_perm(),
+                            note="latency-bound: one blocking C-ABI call = 8 H2D copies + 9 launches + 3 D2H copies; "
+                                 "there is no device-resident variant of a single-proof call, so value == e2e"),
+                latency_us=dt * 1e6, keccak_f_per_sec=b.n_perm() / dt,
+                roofline=None,
+                e2e=dict(value=1.0 / dt, unit=UNIT, h2d_bytes_per_step=h2d * 200, d2h_bytes_per_step=13 * 200,
+                         ms_per_step=dt * 1e3 * 200, host_memory="pageable",
+                         timer="host wall clock around the blocking C-ABI call"),
+                gpu_launches=9 * n_calls, clocks=clocks)
+    if rank == 0:
+        if not a.no_cpu_baseline:
+            from oracle.pyoracle import Oracle
+            o = Oracle()
+            t0 = time.perf_counter()
+            reps = 20000
+            for _ in range(reps):
+                r = o.verify(root, proof, key, mirror=True)
+            cdt = (time.perf_counter() - t0) / reps
+            line["cpu_baseline"] = dict(value=1.0 / cdt, unit=UNIT, cores=1, kind="port", latency_us=cdt * 1e6,
+                                        sample=f"{reps} calls of the C restatement (mirror mode) on the same proof, incl. ctypes overhead",
+                                        gpu_results_identical_on_sample=bool(r[0] == 0 and r[1] == want))
+        emit(line)
+    return 0
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -228,6 +296,25 @@ def run_reference(a):
     cores = os.cpu_count() or 1
     from oracle.pyoracle import Oracle
     o = Oracle()
+    if a.workload == "config1":
+        root, proof, key, want = config1_input()
+        for _ in range(a.warmup * 200):
+            o.verify(root, proof, key, mirror=True)
+        n_calls = max(a.steps, 1) * 2000
+        t0 = time.perf_counter()
+        for _ in range(n_calls):
+            r = o.verify(root, proof, key, mirror=True)
+        dt = (time.perf_counter() - t0) / n_calls
+        assert r[0] == 0 and r[1] == want
+        emit(dict(metric=METRIC, value=1.0 / dt, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                  ms_per_step=dt * 1e3 * 2000, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u32",
+                  data="synthetic", impl="reference", latency_us=dt * 1e6,
+                  config=dict(workload=workload_name(a), calls_per_step=2000,
+                              reference_arm="C restatement of crypto_ops::verify_merkle_proof (mirror mode), one thread, "
+                                            "called through ctypes; the Rust reference cannot be built here (no rustc)"),
+                  cpu_baseline=dict(value=1.0 / dt, unit=UNIT, cores=1, kind="port", sample=f"{n_calls} calls on the same proof"),
+                  e2e=dict(value=1.0 / dt, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0))
+        return 0
     ref_note = ("C restatement of the reference's CPU path (oracle/, mirror mode: same redundant hashing as the "
                 "Rust code) on all host cores; the Rust reference cannot be built here (no rustc)")
     if a.workload == "config4":
@@ -463,6 +550,8 @@ def main():
         return run_reference(a)
     if a.workload == "config4":
         return main_rebuild(a)
+    if a.workload == "config1":
+        return main_single(a)
 
     import numpy as np
     import torch

@@ -217,7 +217,9 @@ int mptv_trie_proofs(mptv_ctx* ctx, const mptv_kv_batch* in, const mptv_proof_ta
  * mptv_flatten_borsh: n borsh-serialised MerkleProofInput blobs (types.rs:4-9; blob i =
  * blobs[blob_off[i] .. blob_off[i+1])) -> one CSR batch, multi-threaded (n_threads <= 0: all
  * cores), in page-locked memory when `pinned`.  Malformed borsh (what borsh::from_slice rejects)
- * gives MPTV_ERR_ARG.  A root_hash that is not 32 bytes is flagged in bad_root (the guests'
+ * gives MPTV_ERR_ARG.  *out must be NULL, or a handle returned by an earlier call: its buffers are then
+ * recycled (grown when needed), so a steady-state pipeline pays for page faults / page-locking once.
+ * A root_hash that is not 32 bytes is flagged in bad_root (the guests'
  * try_into().unwrap() panic, MPTV_ST_BAD_ROOT_LEN) and its proof is verified against a zero root. */
 typedef struct mptv_host_batch mptv_host_batch;
 int mptv_flatten_borsh(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, int pinned,

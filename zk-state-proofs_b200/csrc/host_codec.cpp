@@ -27,21 +27,29 @@ struct mptv_host_batch {
   mptv_batch view;
   uint8_t* bad_root = nullptr;  // [n] 1 where root_hash.len() != 32
   bool pinned = false;
+  // the eight arrays of the batch; kept (and grown) across calls when the handle is reused, so a
+  // steady-state pipeline pays for page faults / page-locking once
   void* blocks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  int n_blocks = 0;
+  size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
 
-void* host_alloc(mptv_host_batch* hb, size_t bytes) {
-  void* p = nullptr;
+void* host_alloc(mptv_host_batch* hb, int slot, size_t bytes) {
   if (bytes == 0) bytes = 16;
-  if (hb->pinned) {
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) p = nullptr;
-  } else {
-    if (posix_memalign(&p, 64, bytes) != 0) p = nullptr;
+  if (hb->blocks[slot] && hb->cap[slot] >= bytes) return hb->blocks[slot];
+  if (hb->blocks[slot]) {
+    if (hb->pinned) cudaFreeHost(hb->blocks[slot]); else free(hb->blocks[slot]);
+    hb->blocks[slot] = nullptr; hb->cap[slot] = 0;
   }
-  if (p) hb->blocks[hb->n_blocks++] = p;
+  void* p = nullptr;
+  const size_t want = bytes + bytes / 8;
+  if (hb->pinned) {
+    if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) p = nullptr;
+  } else {
+    if (posix_memalign(&p, 64, want) != 0) p = nullptr;
+  }
+  if (p) { hb->blocks[slot] = p; hb->cap[slot] = want; }
   return p;
 }
 
@@ -132,7 +140,8 @@ extern "C" {
 int mptv_flatten_borsh(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, int pinned,
                        mptv_host_batch** out) {
   if (!out || (n && (!blobs || !blob_off))) return MPTV_ERR_ARG;
-  *out = nullptr;
+  mptv_host_batch* reuse = *out;  // NULL, or a handle from an earlier call whose buffers are recycled
+  if (reuse && reuse->pinned != (pinned != 0)) return MPTV_ERR_ARG;
   if (n_threads <= 0) n_threads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   std::vector<Shape> sh(n);
   std::atomic<int> bad(0);
@@ -152,19 +161,20 @@ int mptv_flatten_borsh(const uint8_t* blobs, const uint64_t* blob_off, uint64_t 
     key_first[i + 1] = key_first[i] + sh[i].key_len;
   }
   if (node_first[n] > 0xfffffff0ull || key_first[n] > 0xfffffff0ull) return MPTV_ERR_ARG;
-  mptv_host_batch* hb = new mptv_host_batch();
+  mptv_host_batch* hb = reuse ? reuse : new mptv_host_batch();
   hb->pinned = pinned != 0;
   const uint64_t nn = node_first[n], nb = byte_first[n] + 16;
-  uint8_t* node_bytes = (uint8_t*)host_alloc(hb, nb);
-  uint64_t* node_off = (uint64_t*)host_alloc(hb, 8 * nn);
-  uint32_t* node_len = (uint32_t*)host_alloc(hb, 4 * nn);
-  uint32_t* proof_first = (uint32_t*)host_alloc(hb, 4 * (n + 1));
-  uint8_t* roots = (uint8_t*)host_alloc(hb, 32 * n);
-  uint8_t* key_bytes = (uint8_t*)host_alloc(hb, key_first[n] + 16);
-  uint32_t* key_off = (uint32_t*)host_alloc(hb, 4 * (n + 1));
-  hb->bad_root = (uint8_t*)host_alloc(hb, n);
+  uint8_t* node_bytes = (uint8_t*)host_alloc(hb, 0, nb);
+  uint64_t* node_off = (uint64_t*)host_alloc(hb, 1, 8 * nn);
+  uint32_t* node_len = (uint32_t*)host_alloc(hb, 2, 4 * nn);
+  uint32_t* proof_first = (uint32_t*)host_alloc(hb, 3, 4 * (n + 1));
+  uint8_t* roots = (uint8_t*)host_alloc(hb, 4, 32 * n);
+  uint8_t* key_bytes = (uint8_t*)host_alloc(hb, 5, key_first[n] + 16);
+  uint32_t* key_off = (uint32_t*)host_alloc(hb, 6, 4 * (n + 1));
+  hb->bad_root = (uint8_t*)host_alloc(hb, 7, n);
   if (!node_bytes || !node_off || !node_len || !proof_first || !roots || !key_bytes || !key_off || !hb->bad_root) {
     mptv_host_batch_free(hb);
+    *out = nullptr;
     return MPTV_ERR_NOMEM;
   }
   memset(node_bytes + byte_first[n], 0, 16);
@@ -206,7 +216,8 @@ const uint8_t* mptv_host_batch_bad_root(const mptv_host_batch* hb) { return hb ?
 
 void mptv_host_batch_free(mptv_host_batch* hb) {
   if (!hb) return;
-  for (int i = 0; i < hb->n_blocks; i++) {
+  for (int i = 0; i < 8; i++) {
+    if (!hb->blocks[i]) continue;
     if (hb->pinned) cudaFreeHost(hb->blocks[i]); else free(hb->blocks[i]);
   }
   delete hb;
