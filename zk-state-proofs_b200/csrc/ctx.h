@@ -44,18 +44,20 @@ struct HostBuf {  // page-locked staging for results (the caller's arrays may be
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+constexpr size_t kPackedChunkBytes = 256 << 10;  // chunks up to this size cross PCIe as one packed copy
+
 struct Slot {
   cudaStream_t stream = nullptr;
-  HostBuf h_status, h_value_off, h_value_len;
+  HostBuf h_results, h_in;
   uint64_t pend_p0 = 0, pend_np = 0;  // results of this proof range are in flight into the staging buffers
   DevBuf node_bytes, node_off, node_len, proof_first, roots, key_bytes, key_off, rfp;
-  DevBuf status, value_off, value_len;
+  DevBuf results, in_pack;
   DevBuf digests, meta, order, bins, defer;
   void release() {
     DevBuf* all[] = {&node_bytes, &node_off, &node_len, &proof_first, &roots, &key_bytes, &key_off, &rfp,
-                     &status, &value_off, &value_len, &digests, &meta, &order, &bins, &defer};
+                     &results, &in_pack, &digests, &meta, &order, &bins, &defer};
     for (DevBuf* b : all) b->release();
-    h_status.release(); h_value_off.release(); h_value_len.release();
+    h_results.release(); h_in.release();
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }

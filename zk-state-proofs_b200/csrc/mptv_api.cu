@@ -39,14 +39,18 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
   uint32_t* dl = ctx->fast_walk ? defer.as<uint32_t>() : nullptr;
   if (timed) CK(cudaEventRecord(d.ev[0], st));
   const uint32_t* ord = nullptr;
-  if (ctx->binning) {
+  // a batch that does not even fill one wave of K1 CTAs gains nothing from binning or from dynamic tiles:
+  // skip their launches (what matters for a single-proof call is latency)
+  const bool one_wave = b.n_nodes <= (uint64_t)d.sm_count * kKeccakMinBlocks * kKeccakThreads / 4;
+  const bool binned = ctx->binning && !one_wave;
+  if (binned) {
     CK(launch_bin_nodes(b.node_len, nullptr, b.n_nodes, bins.as<uint32_t>(), order.as<uint32_t>(), st));
     ord = order.as<uint32_t>();
   }
   if (timed) CK(cudaEventRecord(d.ev[1], st));
   CK(launch_keccak256_nodes(b.node_bytes, b.byte_base, b.node_off, b.node_len, ord, b.n_nodes,
                             digests.as<uint8_t>(), ctx->fused_classify ? meta.as<uint32_t>() : nullptr,
-                            bins.as<uint32_t>() + 2 * kNumBins, d.sm_count, st));
+                            one_wave ? nullptr : bins.as<uint32_t>() + 2 * kNumBins, d.sm_count, st));
   if (timed) CK(cudaEventRecord(d.ev[2], st));
   CK(launch_parse_nodes(b.node_bytes, b.byte_base, b.node_off, b.node_len, b.n_nodes, meta.as<uint32_t>(),
                         ctx->fused_classify != 0, st));
@@ -54,7 +58,7 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
   const int G = pick_lanes(ctx, b.n_nodes, b.n_proofs);
   CK(launch_verify_walk(b, digests.as<uint8_t>(), meta.as<uint32_t>(), 0, G, status, value_off, value_len, dl,
                         d.sm_count, st));
-  uint32_t other = 1 + 1 + (dl ? 1 : 0) + (ctx->binning ? 3 : 0);
+  uint32_t other = 1 + 1 + (dl ? 1 : 0) + (binned ? 3 : 0);
   if (b.root_from_proof) {
     CK(launch_verify_walk(b, digests.as<uint8_t>(), meta.as<uint32_t>(), 1, G, status, value_off, value_len, dl,
                           d.sm_count, st));
@@ -290,16 +294,20 @@ int validate_slice(const mptv_batch* in, uint64_t p0, uint64_t p1) {
 }
 
 // wait for the chunk a slot is working on and hand its results to the caller's arrays
+// results of a chunk travel as ONE block: [value_off u64 x np | value_len u32 x np | status u8 x np]
 int drain_slot(mptv_ctx* ctx, Slot& s, mptv_result* out) {
   CK(cudaStreamSynchronize(s.stream));
   if (s.pend_np) {
-    memcpy(out->status + s.pend_p0, s.h_status.p, s.pend_np);
-    memcpy(out->value_off + s.pend_p0, s.h_value_off.p, 8 * s.pend_np);
-    memcpy(out->value_len + s.pend_p0, s.h_value_len.p, 4 * s.pend_np);
+    const uint8_t* h = static_cast<const uint8_t*>(s.h_results.p);
+    memcpy(out->value_off + s.pend_p0, h, 8 * s.pend_np);
+    memcpy(out->value_len + s.pend_p0, h + 8 * s.pend_np, 4 * s.pend_np);
+    memcpy(out->status + s.pend_p0, h + 12 * s.pend_np, s.pend_np);
     s.pend_np = 0;
   }
   return MPTV_OK;
 }
+
+inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // run one device's slice [p0, p1): chunked, multi-buffered H2D -> kernels -> D2H
 int run_slice(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result* out, uint64_t p0, uint64_t p1) {
@@ -329,42 +337,68 @@ int run_slice(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result* out, 
         const int32_t r = in->root_from_proof[p];
         if (r >= 0 && ((uint64_t)r < c.p0 || (uint64_t)r >= p || in->root_from_proof[r] >= 0)) return MPTV_ERR_DEP;
       }
-    CK(s.node_bytes.reserve(byte1 - byte0 + 16));
-    CK(s.node_off.reserve(8 * nn + 8));
-    CK(s.node_len.reserve(4 * nn + 4));
-    CK(s.proof_first.reserve(4 * (np + 1)));
-    CK(s.roots.reserve(32 * np));
-    CK(s.key_bytes.reserve((size_t)(k1 - k0) + 16));
-    CK(s.key_off.reserve(4 * (np + 1)));
-    CK(s.status.reserve(np));
-    CK(s.value_off.reserve(8 * np));
-    CK(s.value_len.reserve(4 * np));
-    if (in->root_from_proof) CK(s.rfp.reserve(4 * np));
-    CK(cudaMemcpyAsync(s.node_bytes.p, in->node_bytes + byte0, byte1 - byte0, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s.node_off.p, in->node_off + n0, 8 * nn, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s.node_len.p, in->node_len + n0, 4 * nn, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s.proof_first.p, in->proof_first + c.p0, 4 * (np + 1), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s.roots.p, in->roots + 32 * c.p0, 32 * np, cudaMemcpyHostToDevice, st));
-    if (k1 > k0) CK(cudaMemcpyAsync(s.key_bytes.p, in->key_bytes + k0, k1 - k0, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s.key_off.p, in->key_off + c.p0, 4 * (np + 1), cudaMemcpyHostToDevice, st));
-    if (in->root_from_proof)
-      CK(cudaMemcpyAsync(s.rfp.p, in->root_from_proof + c.p0, 4 * np, cudaMemcpyHostToDevice, st));
     DeviceBatch b;
-    b.node_bytes = s.node_bytes.as<uint8_t>(); b.node_off = s.node_off.as<uint64_t>();
-    b.node_len = s.node_len.as<uint32_t>(); b.n_nodes = nn;
-    b.proof_first = s.proof_first.as<uint32_t>(); b.n_proofs = np; b.roots = s.roots.as<uint8_t>();
-    b.key_bytes = s.key_bytes.as<uint8_t>(); b.key_off = s.key_off.as<uint32_t>();
-    b.root_from_proof = in->root_from_proof ? s.rfp.as<int32_t>() : nullptr;
+    const size_t nbytes = (size_t)(byte1 - byte0), kbytes = (size_t)(k1 - k0);
+    const size_t small_total = up16(nbytes + 16) + up16(8 * nn) + up16(4 * nn) + 2 * up16(4 * (np + 1)) + up16(32 * np) +
+                               up16(kbytes + 16) + (in->root_from_proof ? up16(4 * np) : 0);
+    if (small_total <= kPackedChunkBytes) {
+      // small chunk (a single verify_merkle_proof call, a handful of proofs): every input array is packed
+      // into one page-locked staging block and crosses PCIe as ONE copy -- latency, not bandwidth, matters
+      CK(s.h_in.reserve(small_total));
+      CK(s.in_pack.reserve(small_total));
+      uint8_t* h = static_cast<uint8_t*>(s.h_in.p);
+      uint8_t* dv = s.in_pack.as<uint8_t>();
+      size_t o = 0;
+      auto put = [&](const void* src, size_t bytes, size_t reserve_bytes) {
+        if (bytes) memcpy(h + o, src, bytes);
+        uint8_t* at = dv + o;
+        o += up16(reserve_bytes);
+        return at;
+      };
+      b.node_bytes = put(in->node_bytes + byte0, nbytes, nbytes + 16);
+      b.node_off = reinterpret_cast<const uint64_t*>(put(in->node_off + n0, 8 * nn, 8 * nn));
+      b.node_len = reinterpret_cast<const uint32_t*>(put(in->node_len + n0, 4 * nn, 4 * nn));
+      b.proof_first = reinterpret_cast<const uint32_t*>(put(in->proof_first + c.p0, 4 * (np + 1), 4 * (np + 1)));
+      b.roots = put(in->roots + 32 * c.p0, 32 * np, 32 * np);
+      b.key_bytes = put(in->key_bytes + k0, kbytes, kbytes + 16);
+      b.key_off = reinterpret_cast<const uint32_t*>(put(in->key_off + c.p0, 4 * (np + 1), 4 * (np + 1)));
+      b.root_from_proof = in->root_from_proof
+                              ? reinterpret_cast<const int32_t*>(put(in->root_from_proof + c.p0, 4 * np, 4 * np))
+                              : nullptr;
+      CK(cudaMemcpyAsync(dv, h, o, cudaMemcpyHostToDevice, st));
+    } else {
+      CK(s.node_bytes.reserve(nbytes + 16));
+      CK(s.node_off.reserve(8 * nn + 8));
+      CK(s.node_len.reserve(4 * nn + 4));
+      CK(s.proof_first.reserve(4 * (np + 1)));
+      CK(s.roots.reserve(32 * np));
+      CK(s.key_bytes.reserve(kbytes + 16));
+      CK(s.key_off.reserve(4 * (np + 1)));
+      if (in->root_from_proof) CK(s.rfp.reserve(4 * np));
+      CK(cudaMemcpyAsync(s.node_bytes.p, in->node_bytes + byte0, nbytes, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(s.node_off.p, in->node_off + n0, 8 * nn, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(s.node_len.p, in->node_len + n0, 4 * nn, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(s.proof_first.p, in->proof_first + c.p0, 4 * (np + 1), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(s.roots.p, in->roots + 32 * c.p0, 32 * np, cudaMemcpyHostToDevice, st));
+      if (k1 > k0) CK(cudaMemcpyAsync(s.key_bytes.p, in->key_bytes + k0, kbytes, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(s.key_off.p, in->key_off + c.p0, 4 * (np + 1), cudaMemcpyHostToDevice, st));
+      if (in->root_from_proof)
+        CK(cudaMemcpyAsync(s.rfp.p, in->root_from_proof + c.p0, 4 * np, cudaMemcpyHostToDevice, st));
+      b.node_bytes = s.node_bytes.as<uint8_t>(); b.node_off = s.node_off.as<uint64_t>();
+      b.node_len = s.node_len.as<uint32_t>();
+      b.proof_first = s.proof_first.as<uint32_t>(); b.roots = s.roots.as<uint8_t>();
+      b.key_bytes = s.key_bytes.as<uint8_t>(); b.key_off = s.key_off.as<uint32_t>();
+      b.root_from_proof = in->root_from_proof ? s.rfp.as<int32_t>() : nullptr;
+    }
+    b.n_nodes = nn; b.n_proofs = np;
     b.byte_base = byte0; b.node_base = n0; b.key_base = k0; b.proof_base = c.p0;
-    rc = run_pipeline(ctx, d, b, s.digests, s.meta, s.order, s.bins, s.defer, s.status.as<uint8_t>(),
-                      s.value_off.as<uint64_t>(), s.value_len.as<uint32_t>(), st, false);
+    CK(s.results.reserve(13 * np + 16));
+    CK(s.h_results.reserve(13 * np + 16));
+    uint8_t* res = s.results.as<uint8_t>();
+    rc = run_pipeline(ctx, d, b, s.digests, s.meta, s.order, s.bins, s.defer, res + 12 * np,
+                      reinterpret_cast<uint64_t*>(res), reinterpret_cast<uint32_t*>(res + 8 * np), st, false);
     if (rc != MPTV_OK) return rc;
-    CK(s.h_status.reserve(np));
-    CK(s.h_value_off.reserve(8 * np));
-    CK(s.h_value_len.reserve(4 * np));
-    CK(cudaMemcpyAsync(s.h_status.p, s.status.p, np, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(s.h_value_off.p, s.value_off.p, 8 * np, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(s.h_value_len.p, s.value_len.p, 4 * np, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_results.p, res, 13 * np, cudaMemcpyDeviceToHost, st));
     s.pend_p0 = c.p0; s.pend_np = np;
   }
   for (int k = 0; k < kSlots; k++) {
