@@ -29,9 +29,8 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-// one pipeline slot of the host-buffer path: device copies of a chunk's inputs and outputs
-struct HostBuf {  // page-locked staging for results (the caller's arrays may be pageable, and an
-  void* p = nullptr;  // async copy into pageable memory would stall the pipeline)
+struct HostBuf {  // page-locked staging (an async copy from / into pageable memory would stall the pipeline)
+  void* p = nullptr;
   size_t cap = 0;
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
@@ -44,6 +43,7 @@ struct HostBuf {  // page-locked staging for results (the caller's arrays may be
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// one pipeline slot of the host-buffer path: device copies of a chunk's inputs and outputs
 constexpr size_t kPackedChunkBytes = 256 << 10;  // chunks up to this size cross PCIe as one packed copy
 
 struct Slot {
@@ -63,10 +63,25 @@ struct Slot {
   }
 };
 
+// one of the two input stages of the host-buffer rebuild path (copy of chunk c+1 overlaps the rebuild of chunk c)
+struct KvStage {
+  DevBuf key_bytes, key_off, value_bytes, value_off, value_len, trie_first;
+  HostBuf h_koff, h_voff, h_tfirst, h_vlen, h_keys;  // index arrays rebased to the chunk; staged small arrays
+  cudaEvent_t up = nullptr;          // the stage's copies have landed
+  void release() {
+    DevBuf* all[] = {&key_bytes, &key_off, &value_bytes, &value_off, &value_len, &trie_first};
+    for (DevBuf* b : all) b->release();
+    h_koff.release(); h_voff.release(); h_tfirst.release(); h_vlen.release(); h_keys.release();
+    if (up) cudaEventDestroy(up);
+    up = nullptr;
+  }
+};
+
 // scratch + timing of the trie rebuild path (rebuild_api.cu)
 struct Rebuild {
   DevBuf rec, off, len, digests, tcount, lvl_list, sum, arena, order, bins;
-  DevBuf in_key_bytes, in_key_off, in_value_bytes, in_value_off, in_value_len, in_trie_first, out_roots;  // host-buffer entry
+  KvStage stage[2];  // host-buffer entry
+  DevBuf out_roots;
   DevBuf q_trie, q_key_bytes, q_key_off, q_cnt, q_bytes, q_proof_first, q_byte_first, q_out_bytes, q_out_off, q_out_len;  // get_proof
   HostBuf h_sum, h_roots;
   cudaEvent_t ev_begin = nullptr, ev_struct = nullptr, ev_end = nullptr;
@@ -76,8 +91,8 @@ struct Rebuild {
   bool leaves_in_arena = true;  // false after a fused (K1L) rebuild: hashed leaves were never written
   unsigned long long n_nodes = 0, n_hashed = 0, n_perm = 0, arena_bytes = 0;
   void release() {
-    DevBuf* all[] = {&rec, &off, &len, &digests, &tcount, &lvl_list, &sum, &arena, &order, &bins, &in_key_bytes,
-                     &in_key_off, &in_value_bytes, &in_value_off, &in_value_len, &in_trie_first, &out_roots, &q_trie, &q_key_bytes,
+    stage[0].release(); stage[1].release();
+    DevBuf* all[] = {&rec, &off, &len, &digests, &tcount, &lvl_list, &sum, &arena, &order, &bins, &out_roots, &q_trie, &q_key_bytes,
                      &q_key_off, &q_cnt, &q_bytes, &q_proof_first, &q_byte_first, &q_out_bytes, &q_out_off, &q_out_len};
     for (DevBuf* b : all) b->release();
     h_sum.release(); h_roots.release();

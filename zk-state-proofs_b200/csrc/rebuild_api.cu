@@ -101,9 +101,11 @@ int rebuild_on_device(mptv_ctx* ctx, Device& d, const TrieBatchDev& in, uint8_t*
   return MPTV_OK;
 }
 
-// copies tries [cs, ce) of a host batch to the device (offsets rebased to the chunk) -> b
-int upload_kv(mptv_ctx* ctx, Device& d, const mptv_kv_batch* in, uint64_t cs, uint64_t ce, TrieBatchDev& b, cudaStream_t st) {
-  Rebuild& rb = d.rb;
+// queues the copy of tries [cs, ce) of a host batch into one of the two input stages (offsets rebased
+// to the chunk through page-locked staging, value bytes straight from the caller's arena); asynchronous
+// on `st`, completion = stage.up
+int upload_kv(mptv_ctx* ctx, Device& d, const mptv_kv_batch* in, uint64_t cs, uint64_t ce, KvStage& g, TrieBatchDev& b,
+              cudaStream_t st) {
   const uint32_t i0 = in->trie_first[cs], i1 = in->trie_first[ce];
   const uint64_t ni = i1 - i0, nt = ce - cs;
   const uint64_t b0 = i0 < in->n_items ? in->value_off[i0] : in->value_bytes_len;
@@ -112,9 +114,15 @@ int upload_kv(mptv_ctx* ctx, Device& d, const mptv_kv_batch* in, uint64_t cs, ui
   b1 = (b1 + 15) & ~15ull;
   if (b1 > ((in->value_bytes_len + 15) & ~15ull)) return MPTV_ERR_ARG;
   const uint32_t k0 = in->key_off[i0], k1 = in->key_off[i1];
-  // rebased copies of the index arrays (offsets relative to this chunk)
-  std::vector<uint32_t> koff(ni + 1), tfirst(nt + 1);
-  std::vector<uint64_t> voff(ni ? ni : 1);
+  if (!g.up) CK(cudaEventCreateWithFlags(&g.up, cudaEventDisableTiming));
+  CK(g.h_koff.reserve(4 * (ni + 1)));
+  CK(g.h_voff.reserve(8 * ni + 8));
+  CK(g.h_tfirst.reserve(4 * (nt + 1)));
+  CK(g.h_vlen.reserve(4 * ni + 4));
+  CK(g.h_keys.reserve((size_t)(k1 - k0) + 16));
+  uint32_t* koff = static_cast<uint32_t*>(g.h_koff.p);
+  uint64_t* voff = static_cast<uint64_t*>(g.h_voff.p);
+  uint32_t* tfirst = static_cast<uint32_t*>(g.h_tfirst.p);
   for (uint64_t i = 0; i <= ni; i++) koff[i] = in->key_off[i0 + i] - k0;
   for (uint64_t i = 0; i < ni; i++) {
     const uint64_t o = in->value_off[i0 + i];
@@ -123,58 +131,78 @@ int upload_kv(mptv_ctx* ctx, Device& d, const mptv_kv_batch* in, uint64_t cs, ui
     voff[i] = o - b0;
   }
   for (uint64_t t = 0; t <= nt; t++) tfirst[t] = in->trie_first[cs + t] - i0;
-  CK(rb.in_key_bytes.reserve((size_t)(k1 - k0) + 16));
-  CK(rb.in_key_off.reserve(4 * (ni + 1)));
-  CK(rb.in_value_bytes.reserve((size_t)(b1 - b0) + 16));
-  CK(rb.in_value_off.reserve(8 * ni + 8));
-  CK(rb.in_value_len.reserve(4 * ni + 4));
-  CK(rb.in_trie_first.reserve(4 * (nt + 1)));
-  if (k1 > k0) CK(cudaMemcpyAsync(rb.in_key_bytes.p, in->key_bytes + k0, k1 - k0, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(rb.in_key_off.p, koff.data(), 4 * (ni + 1), cudaMemcpyHostToDevice, st));
-  const uint64_t copy_end = b1 < in->value_bytes_len ? b1 : in->value_bytes_len;
-  if (copy_end > b0) CK(cudaMemcpyAsync(rb.in_value_bytes.p, in->value_bytes + b0, copy_end - b0, cudaMemcpyHostToDevice, st));
-  if (ni) {
-    CK(cudaMemcpyAsync(rb.in_value_off.p, voff.data(), 8 * ni, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(rb.in_value_len.p, in->value_len + i0, 4 * ni, cudaMemcpyHostToDevice, st));
+  CK(g.key_bytes.reserve((size_t)(k1 - k0) + 16));
+  CK(g.key_off.reserve(4 * (ni + 1)));
+  CK(g.value_bytes.reserve((size_t)(b1 - b0) + 16));
+  CK(g.value_off.reserve(8 * ni + 8));
+  CK(g.value_len.reserve(4 * ni + 4));
+  CK(g.trie_first.reserve(4 * (nt + 1)));
+  // every small array goes through page-locked staging (a copy from pageable memory would block this
+  // thread until the stream has drained, i.e. behind the previous chunk's gigabyte of values) and is
+  // queued BEFORE the value bytes, which are copied straight out of the caller's arena
+  if (k1 > k0) {
+    memcpy(g.h_keys.p, in->key_bytes + k0, k1 - k0);
+    CK(cudaMemcpyAsync(g.key_bytes.p, g.h_keys.p, k1 - k0, cudaMemcpyHostToDevice, st));
   }
-  CK(cudaMemcpyAsync(rb.in_trie_first.p, tfirst.data(), 4 * (nt + 1), cudaMemcpyHostToDevice, st));
-  CK(cudaStreamSynchronize(st));  // the staging vectors above go out of scope
-  b.key_bytes = rb.in_key_bytes.as<uint8_t>(); b.key_off = rb.in_key_off.as<uint32_t>();
-  b.value_bytes = rb.in_value_bytes.as<uint8_t>(); b.value_off = rb.in_value_off.as<uint64_t>();
-  b.value_len = rb.in_value_len.as<uint32_t>(); b.trie_first = rb.in_trie_first.as<uint32_t>();
+  CK(cudaMemcpyAsync(g.key_off.p, koff, 4 * (ni + 1), cudaMemcpyHostToDevice, st));
+  if (ni) {
+    memcpy(g.h_vlen.p, in->value_len + i0, 4 * ni);
+    CK(cudaMemcpyAsync(g.value_off.p, voff, 8 * ni, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g.value_len.p, g.h_vlen.p, 4 * ni, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemcpyAsync(g.trie_first.p, tfirst, 4 * (nt + 1), cudaMemcpyHostToDevice, st));
+  const uint64_t copy_end = b1 < in->value_bytes_len ? b1 : in->value_bytes_len;
+  if (copy_end > b0) CK(cudaMemcpyAsync(g.value_bytes.p, in->value_bytes + b0, copy_end - b0, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(g.up, st));
+  b.key_bytes = g.key_bytes.as<uint8_t>(); b.key_off = g.key_off.as<uint32_t>();
+  b.value_bytes = g.value_bytes.as<uint8_t>(); b.value_off = g.value_off.as<uint64_t>();
+  b.value_len = g.value_len.as<uint32_t>(); b.trie_first = g.trie_first.as<uint32_t>();
   b.n_tries = (uint32_t)nt; b.n_items = ni;
   return MPTV_OK;
 }
 
-// one device's share [t0, t1) of a host batch, in chunks of about `chunk` value bytes
+// end of the chunk of tries that starts at cs: about `chunk` value bytes
+uint64_t kv_chunk_end(const mptv_kv_batch* in, uint64_t cs, uint64_t t1, uint64_t chunk) {
+  uint64_t ce = cs + 1;
+  const uint32_t i0 = in->trie_first[cs];
+  const uint64_t b0 = i0 < in->n_items ? in->value_off[i0] : in->value_bytes_len;
+  while (ce < t1) {
+    const uint32_t ie = in->trie_first[ce + 1];
+    const uint64_t be = ie < in->n_items ? in->value_off[ie] : in->value_bytes_len;
+    if (be - b0 > chunk) break;
+    ce++;
+  }
+  return ce;
+}
+
+// one device's share [t0, t1) of a host batch: chunks of about 1 GiB of values, the copy of chunk c+1
+// (copy stream, second input stage) overlapping the rebuild of chunk c
 int rebuild_slice(mptv_ctx* ctx, Device& d, const mptv_kv_batch* in, uint8_t* roots32, uint64_t t0, uint64_t t1) {
   if (t1 <= t0) return MPTV_OK;
   CK(cudaSetDevice(d.id));
   Rebuild& rb = d.rb;
-  cudaStream_t st = d.stream;
-  const uint64_t chunk = 4ull << 30;
-  for (uint64_t cs = t0; cs < t1;) {
-    uint64_t ce = cs + 1;
-    const uint32_t i0 = in->trie_first[cs];
-    const uint64_t b0 = i0 < in->n_items ? in->value_off[i0] : in->value_bytes_len;
-    while (ce < t1) {
-      const uint32_t ie = in->trie_first[ce + 1];
-      const uint64_t be = ie < in->n_items ? in->value_off[ie] : in->value_bytes_len;
-      if (be - b0 > chunk) break;
-      ce++;
+  cudaStream_t st = d.stream, cp = d.slot[0].stream;
+  const uint64_t chunk = 1ull << 30;
+  TrieBatchDev cur, nxt;
+  uint64_t cs = t0, ce = kv_chunk_end(in, cs, t1, chunk);
+  int rc = upload_kv(ctx, d, in, cs, ce, rb.stage[0], cur, cp);
+  if (rc != MPTV_OK) return rc;
+  for (int k = 0; cs < t1; k ^= 1) {
+    const uint64_t ns = ce, ne = ns < t1 ? kv_chunk_end(in, ns, t1, chunk) : ns;
+    if (ns < t1) {  // stage k^1 is free: the rebuild that read it was synchronised at the end of the last iteration
+      rc = upload_kv(ctx, d, in, ns, ne, rb.stage[k ^ 1], nxt, cp);
+      if (rc != MPTV_OK) return rc;
     }
     const uint64_t nt = ce - cs;
-    TrieBatchDev b;
-    int rc = upload_kv(ctx, d, in, cs, ce, b, st);
-    if (rc != MPTV_OK) return rc;
+    CK(cudaStreamWaitEvent(st, rb.stage[k].up, 0));
     CK(rb.out_roots.reserve(32 * nt));
     CK(rb.h_roots.reserve(32 * nt));
-    rc = rebuild_on_device(ctx, d, b, rb.out_roots.as<uint8_t>(), st);
+    rc = rebuild_on_device(ctx, d, cur, rb.out_roots.as<uint8_t>(), st);
     if (rc != MPTV_OK) return rc;
     CK(cudaMemcpyAsync(rb.h_roots.p, rb.out_roots.p, 32 * nt, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     memcpy(roots32 + 32 * cs, rb.h_roots.p, 32 * nt);
-    cs = ce;
+    cs = ns; ce = ne; cur = nxt;
   }
   return MPTV_OK;
 }
@@ -265,7 +293,7 @@ int mptv_trie_proofs(mptv_ctx* ctx, const mptv_kv_batch* in, const mptv_proof_ta
   CK(cudaSetDevice(d.id));
   cudaStream_t st = d.stream;
   TrieBatchDev b;
-  int rc = upload_kv(ctx, d, in, 0, in->n_tries, b, st);
+  int rc = upload_kv(ctx, d, in, 0, in->n_tries, rb.stage[0], b, st);
   if (rc != MPTV_OK) return rc;
   CK(rb.out_roots.reserve(32 * in->n_tries));
   rc = rebuild_on_device(ctx, d, b, rb.out_roots.as<uint8_t>(), st);
