@@ -1,0 +1,96 @@
+"""Error behaviour of the C ABI on a GPU box: argument errors come back as negative MPTV_ERR_* codes
+(never an abort, never a silent fallback), separate contexts work from separate threads, and a big
+fuzz corpus agrees with the oracle verdict for verdict."""
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_argument_errors_are_reported(verifier, golden):
+    import zk_state_proofs_b200 as z
+    vs = golden["vectors"][:50]
+    b = z.flatten([z.MerkleProofInput(v["proof_b"], v["root_b"], v["key_b"]) for v in vs])
+    # a node that does not start on a 16-byte boundary
+    bad = z.Batch(b.node_bytes, b.node_off.copy(), b.node_len, b.proof_first, b.roots, b.key_bytes, b.key_off, None, None)
+    bad.node_off[3] += 8
+    with pytest.raises(z.MptvError, match="16-byte"):
+        verifier.verify_batch(bad)
+    # a node that runs past the arena
+    bad = z.Batch(b.node_bytes, b.node_off, b.node_len.copy(), b.proof_first, b.roots, b.key_bytes, b.key_off, None, None)
+    bad.node_len[-1] = 1 << 30
+    with pytest.raises(z.MptvError):
+        verifier.verify_batch(bad)
+    # proof_first not monotone / beyond n_nodes
+    bad = z.Batch(b.node_bytes, b.node_off, b.node_len, b.proof_first.copy(), b.roots, b.key_bytes, b.key_off, None, None)
+    bad.proof_first[5] = b.n_nodes + 7
+    with pytest.raises(z.MptvError):
+        verifier.verify_batch(bad)
+    # root_from_proof must point at an EARLIER independent proof
+    rfp = np.full(b.n_proofs, -1, np.int32)
+    rfp[2] = 9
+    with pytest.raises(z.MptvError, match="root_from_proof"):
+        verifier.verify_batch(z.Batch(b.node_bytes, b.node_off, b.node_len, b.proof_first, b.roots, b.key_bytes,
+                                      b.key_off, rfp, None))
+    rfp[2] = 1
+    rfp[1] = 0
+    with pytest.raises(z.MptvError, match="root_from_proof"):
+        verifier.verify_batch(z.Batch(b.node_bytes, b.node_off, b.node_len, b.proof_first, b.roots, b.key_bytes,
+                                      b.key_off, rfp, None))
+    # rebuild: misaligned value
+    kv = z.flatten_kv([[(b"\x01", b"v" * 40), (b"\x02", b"w" * 40)]])
+    kv.value_off[1] += 4
+    with pytest.raises(z.MptvError):
+        verifier.trie_roots(kv)
+    # options
+    with pytest.raises(z.MptvError):
+        verifier.set_option("lanes_per_proof", 7)
+    with pytest.raises(z.MptvError):
+        verifier.set_option("no_such_option", 1)
+    # and the context is still usable afterwards
+    st, _, _ = verifier.verify_batch(b)
+    assert st.tolist() == [v["status"] for v in vs]
+
+
+def test_separate_contexts_from_separate_threads(golden):
+    import zk_state_proofs_b200 as z
+    vs = golden["vectors"]
+    inputs = [z.MerkleProofInput(v["proof_b"], v["root_b"], v["key_b"]) for v in vs]
+    want = [v["status"] for v in vs]
+    errs = []
+
+    def work(seed):
+        try:
+            ver = z.Verifier([0])
+            rng = np.random.default_rng(seed)
+            for _ in range(5):
+                idx = rng.permutation(len(inputs))[:700]
+                st, _, _ = ver.verify_batch(z.flatten([inputs[i] for i in idx]))
+                assert st.tolist() == [want[i] for i in idx]
+            ver.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(s,)) for s in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+
+
+def test_large_fuzz_corpus_matches_oracle(verifier, oracle):
+    """20 k generated + mutated + malformed cases (oracle/fuzzgen.py), GPU verdict and value == C restatement"""
+    import zk_state_proofs_b200 as z
+    from oracle.fuzzgen import corpus
+    cases = corpus(777, oracle.keccak256, 150, 8000, 12000)
+    b = z.flatten([z.MerkleProofInput(c["proof"], c["root"], c["key"]) for c in cases])
+    st, voff, vlen = verifier.verify_batch(b)
+    d = dict(node_bytes=b.node_bytes, node_off=b.node_off, node_len=b.node_len, proof_first=b.proof_first,
+             roots=b.roots, key_bytes=b.key_bytes, key_off=b.key_off)
+    ost, ovoff, ovlen, _, _ = oracle.verify_batch(d, nthreads=8)
+    bad = np.nonzero((st != ost) | (voff != ovoff) | (vlen != ovlen))[0]
+    assert len(bad) == 0, [(cases[i]["tag"], int(st[i]), int(ost[i])) for i in bad[:10]]
+    assert len(set(st.tolist())) >= 6
