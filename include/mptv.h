@@ -97,6 +97,8 @@ typedef struct mptv_timings {
   uint64_t n_nodes;
   uint64_t n_perm;  /* Keccak-f permutations = sum ceil((len+1)/136); filled when known, else 0 */
   uint32_t keccak_launches, other_launches;
+  uint64_t n_unique_nodes; /* "dedup_nodes" runs: distinct nodes actually hashed (0 otherwise) ... */
+  uint64_t n_unique_perm;  /* ... and their Keccak-f count                                        */
 } mptv_timings;
 
 /* device_ids == NULL && n_devices == 0: use every visible CUDA device. */
@@ -135,8 +137,17 @@ int mptv_last_timings(mptv_ctx* ctx, int dev_index, mptv_timings* out);
  * or Keccak-mix 122:58 (mode 2) kernel on every SM and reports 32-bit lane-operations per second. */
 int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops_per_s);
 
-/* options: lanes per proof for the walk kernel (0 = choose from nodes/proof; else 8, 16 or 32),
- * chunk size in bytes of node data for the host-buffer pipeline (0 = default) */
+/* options (name, value):
+ *   "lanes_per_proof"  K2b lanes per proof: 0 = choose from nodes/proof, else 8, 16 or 32
+ *   "chunk_bytes"      node bytes per pipeline chunk of the host-buffer entry
+ *   "binning"          K0 rate-block binning on / off              (default 1)
+ *   "fused_classify"   K1 also classifies plain branches / leaves  (default 1)
+ *   "fast_walk"        K2f thread-per-proof chain check + K2b on the deferred rest (default 1)
+ *   "fused_leaf_hash"  rebuild: K1L hashes leaves straight from the value arena (default 1)
+ *   "dedup_nodes"      hash each DISTINCT node of a batch once and share the digest (default 0).
+ *                      Results are identical; the executed Keccak-f count drops.  The reference hashes
+ *                      every supplied node, so numbers measured with this option are a SECOND,
+ *                      separately labelled figure, never the headline. */
 int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value);
 
 /* ---------------------------------------------------------------------------------------------

@@ -7,12 +7,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[1, 0], ids=["fast_walk", "cooperative_walk_only"])
+@pytest.fixture(params=[(1, 0), (0, 0), (1, 1)], ids=["fast_walk", "cooperative_walk_only", "fast_walk+dedup_nodes"])
 def walk_mode(request, verifier):
-    """both walk configurations: K2f (thread per proof) + K2b on the deferred rest, and K2b on everything"""
-    verifier.set_option("fast_walk", request.param)
+    """walk configurations: K2f (thread per proof) + K2b on the deferred rest, K2b on everything, and the
+    optional node de-duplication in front of K1 (every distinct node hashed once, digests shared)"""
+    verifier.set_option("fast_walk", request.param[0])
+    verifier.set_option("dedup_nodes", request.param[1])
     yield request.param
     verifier.set_option("fast_walk", 1)
+    verifier.set_option("dedup_nodes", 0)
 
 
 def _inputs(z, vs):
@@ -139,6 +142,49 @@ def test_single_proof_api_and_panics(verifier, golden):
     with pytest.raises(z.VerifyPanic) as e:
         verifier.verify_merkle_proof(b"\x00" * 31, v["proof_b"], v["key_b"])
     assert e.value.status == 6
+
+
+def test_dedup_counts_and_padding_is_not_compared(verifier, oracle):
+    """dedup_nodes: the unique-node count is exact (nodes equal byte for byte are merged, padding garbage after a
+    node never matters, near-duplicates are kept apart) and the results do not change"""
+    import zk_state_proofs_b200 as z
+    from workload import gen
+    trie = gen.SynthTrie(200_000, 2, kind=0)
+    b = gen.account_batch(trie, 40_000, seed=5, p_excl=0.05, p_mut=0.10)
+    want = verifier.verify_batch(b)
+    # scribble over the padding bytes between nodes: duplicates must still be found, results unchanged
+    nb = b.node_bytes.copy()
+    rng = np.random.default_rng(3)
+    ends = (b.node_off + b.node_len.astype(np.uint64)).astype(np.int64)
+    pad = (-b.node_len.astype(np.int64)) % 16
+    for k in range(1, 16):
+        sel = ends[pad >= k] + (k - 1)
+        nb[sel] = rng.integers(0, 256, len(sel), dtype=np.uint8)
+    b2 = z.Batch(nb, b.node_off, b.node_len, b.proof_first, b.roots, b.key_bytes, b.key_off, None, None)
+    verifier.set_option("dedup_nodes", 1)
+    try:
+        got = verifier.verify_batch(b2)
+        # exact number of distinct nodes, from the host
+        seen = set()
+        for o, n in zip(b.node_off.tolist(), b.node_len.tolist()):
+            seen.add(b.node_bytes[o:o + n].tobytes())
+        import torch
+        dev = torch.device("cuda", 0)
+        t = {k: torch.from_numpy(getattr(b2, k).view(np.uint8) if getattr(b2, k).dtype != np.uint8 else getattr(b2, k)).to(dev)
+             for k in ["node_bytes", "node_off", "node_len", "proof_first", "roots", "key_bytes", "key_off"]}
+        d_st = torch.zeros(b2.n_proofs, dtype=torch.uint8, device=dev)
+        d_vo = torch.zeros(b2.n_proofs, dtype=torch.int64, device=dev)
+        d_vl = torch.zeros(b2.n_proofs, dtype=torch.int32, device=dev)
+        verifier.verify_batch_device(0, {k: v.data_ptr() for k, v in t.items()}, b2.n_nodes, b2.n_proofs,
+                                     dict(status=d_st.data_ptr(), value_off=d_vo.data_ptr(), value_len=d_vl.data_ptr()),
+                                     node_bytes_len=len(b2.node_bytes))
+        tm = verifier.last_timings(0)
+        assert tm.n_unique_nodes == len(seen) < b.n_nodes
+        assert (d_st.cpu().numpy() == want[0]).all()
+    finally:
+        verifier.set_option("dedup_nodes", 0)
+    for x, y in zip(want, got):
+        assert (x == y).all()
 
 
 def test_empty_and_degenerate_batches(verifier):

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmptv.so")
-SOURCES = ["keccak_kernels.cu", "verify_kernels.cu", "rebuild_kernels.cu", "microbench.cu", "mptv_api.cu", "rebuild_api.cu", "host_codec.cpp"]
+SOURCES = ["keccak_kernels.cu", "verify_kernels.cu", "rebuild_kernels.cu", "dedup_kernels.cu", "microbench.cu", "mptv_api.cu", "rebuild_api.cu", "host_codec.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-pthread", "-shared", "-cudart", "static",

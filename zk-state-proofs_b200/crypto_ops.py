@@ -383,6 +383,7 @@ class Timings(ctypes.Structure):
         ("bin_ms", ctypes.c_float), ("keccak_ms", ctypes.c_float), ("parse_ms", ctypes.c_float),
         ("walk_ms", ctypes.c_float), ("total_ms", ctypes.c_float), ("n_nodes", ctypes.c_uint64),
         ("n_perm", ctypes.c_uint64), ("keccak_launches", ctypes.c_uint32), ("other_launches", ctypes.c_uint32),
+        ("n_unique_nodes", ctypes.c_uint64), ("n_unique_perm", ctypes.c_uint64),
     ]
 
 

@@ -52,10 +52,10 @@ struct Slot {
   uint64_t pend_p0 = 0, pend_np = 0;  // results of this proof range are in flight into the staging buffers
   DevBuf node_bytes, node_off, node_len, proof_first, roots, key_bytes, key_off, rfp;
   DevBuf results, in_pack;
-  DevBuf digests, meta, order, bins, defer;
+  DevBuf digests, meta, order, bins, defer, dedup;
   void release() {
     DevBuf* all[] = {&node_bytes, &node_off, &node_len, &proof_first, &roots, &key_bytes, &key_off, &rfp,
-                     &results, &in_pack, &digests, &meta, &order, &bins, &defer};
+                     &results, &in_pack, &digests, &meta, &order, &bins, &defer, &dedup};
     for (DevBuf* b : all) b->release();
     h_results.release(); h_in.release();
     if (stream) cudaStreamDestroy(stream);
@@ -111,7 +111,8 @@ struct Device {
   int id = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;  // device-resident entry
-  DevBuf digests, meta, order, bins, defer;  // scratch of the device-resident entry
+  DevBuf digests, meta, order, bins, defer, dedup;  // scratch of the device-resident entry
+  uint64_t last_unique_nodes = 0, last_unique_perm = 0;  // of the last dedup_nodes run
   Slot slot[kSlots];
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaStream_t last_stream = nullptr;
@@ -130,6 +131,7 @@ struct mptv_ctx {
   uint64_t chunk_bytes = 96ull << 20;  // node bytes per pipeline chunk of the host-buffer path
   int binning = 1;
   int fused_classify = 1;  // K1 also classifies plain branches / leaves (K2a fast path)
+  int dedup_nodes = 0;     // hash each DISTINCT node once (secondary mode, reported separately)
   int fast_walk = 1;       // K2f decides chain-shaped proofs one thread each; K2b gets the deferred rest
   int fused_leaf_hash = 1; // rebuild: hash leaves straight from the value arena (K1L), no encode pass
 };

@@ -29,19 +29,36 @@ __host__ __device__ __forceinline__ uint32_t nb_bin(uint32_t nb) {
 
 // ids (may be NULL = identity): the list of node indices to bin -- the rebuild path bins one trie
 // level at a time out of a larger node table.
+// keep (may be NULL): only nodes with keep[i] == i take part (dedup_nodes: the representatives); then
+// totals[0] / totals[1] receive the number of kept nodes and their Keccak-f count.
 __global__ void __launch_bounds__(256) k_bin_hist(const uint32_t* __restrict__ node_len,
                                                   const uint32_t* __restrict__ ids, uint64_t n_nodes,
-                                                  uint32_t* __restrict__ hist) {
+                                                  uint32_t* __restrict__ hist, const uint32_t* __restrict__ keep,
+                                                  unsigned long long* __restrict__ totals) {
   __shared__ uint32_t sh[kNumBins];
+  __shared__ unsigned long long s_perm;
   for (int i = threadIdx.x; i < kNumBins; i += blockDim.x) sh[i] = 0;
+  if (threadIdx.x == 0) s_perm = 0;
   __syncthreads();
   uint64_t base = (uint64_t)blockIdx.x * kBinNodesPerBlock;
   uint64_t end = base + kBinNodesPerBlock < n_nodes ? base + kBinNodesPerBlock : n_nodes;
-  for (uint64_t i = base + threadIdx.x; i < end; i += blockDim.x)
-    atomicAdd(&sh[nb_bin(node_len[ids ? ids[i] : i] / 136 + 1)], 1u);
+  uint32_t perms = 0;
+  for (uint64_t i = base + threadIdx.x; i < end; i += blockDim.x) {
+    const uint32_t id = ids ? ids[i] : (uint32_t)i;
+    if (keep && keep[id] != id) continue;
+    const uint32_t nb = node_len[id] / 136 + 1;
+    perms += nb;
+    atomicAdd(&sh[nb_bin(nb)], 1u);
+  }
+  if (totals && perms) atomicAdd(&s_perm, (unsigned long long)perms);
   __syncthreads();
+  uint32_t kept = 0;
   for (int i = threadIdx.x; i < kNumBins; i += blockDim.x)
-    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+    if (sh[i]) { atomicAdd(&hist[i], sh[i]); kept += sh[i]; }
+  if (totals) {
+    if (kept) atomicAdd(&totals[0], (unsigned long long)kept);
+    if (threadIdx.x == 0 && s_perm) atomicAdd(&totals[1], s_perm);
+  }
 }
 
 // bins laid out in DESCENDING block count so the long nodes start first (tail balance)
@@ -55,7 +72,7 @@ __global__ void k_bin_scan(const uint32_t* __restrict__ hist, uint32_t* __restri
 __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t* __restrict__ node_len,
                                                      const uint32_t* __restrict__ ids, uint64_t n_nodes,
                                                      uint32_t* __restrict__ cursor,
-                                                     uint32_t* __restrict__ order) {
+                                                     uint32_t* __restrict__ order, const uint32_t* __restrict__ keep) {
   __shared__ uint32_t cnt[kNumBins];
   __shared__ uint32_t start[kNumBins];
   for (int i = threadIdx.x; i < kNumBins; i += blockDim.x) cnt[i] = 0;
@@ -63,13 +80,15 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t* __restrict_
   uint64_t base = (uint64_t)blockIdx.x * kBinNodesPerBlock;
   uint64_t end = base + kBinNodesPerBlock < n_nodes ? base + kBinNodesPerBlock : n_nodes;
   constexpr int kPer = kBinNodesPerBlock / 256;
-  uint32_t br[kPer];  // bin << 16 | rank within this CTA's share of the bin
+  uint32_t br[kPer];  // bin << 16 | rank within this CTA's share of the bin; 0xffffffff = not kept
   uint32_t id[kPer];
 #pragma unroll
   for (int j = 0; j < kPer; j++) {
     uint64_t i = base + threadIdx.x + (uint64_t)j * 256;
+    br[j] = 0xffffffffu;
     if (i < end) {
       id[j] = ids ? ids[i] : (uint32_t)i;
+      if (keep && keep[id[j]] != id[j]) continue;
       const uint32_t b = nb_bin(node_len[id[j]] / 136 + 1);
       br[j] = (b << 16) | atomicAdd(&cnt[b], 1u);
     }
@@ -81,7 +100,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t* __restrict_
 #pragma unroll
   for (int j = 0; j < kPer; j++) {
     uint64_t i = base + threadIdx.x + (uint64_t)j * 256;
-    if (i < end) order[start[br[j] >> 16] + (br[j] & 0xffffu)] = id[j];
+    if (i < end && br[j] != 0xffffffffu) order[start[br[j] >> 16] + (br[j] & 0xffffu)] = id[j];
   }
 }
 
@@ -472,16 +491,21 @@ cudaError_t launch_keccak256_leaves(const TrieBatchDev& in, const uint4* rec, co
 }
 
 cudaError_t launch_bin_nodes(const uint32_t* node_len, const uint32_t* ids, uint64_t n_nodes,
-                             uint32_t* hist_cursor /*2*kNumBins*/, uint32_t* order, cudaStream_t st) {
+                             uint32_t* hist_cursor /*2*kNumBins*/, uint32_t* order, cudaStream_t st,
+                             const uint32_t* keep, unsigned long long* totals) {
   if (n_nodes == 0) return cudaSuccess;
   uint32_t* hist = hist_cursor;
   uint32_t* cursor = hist_cursor + kNumBins;
   cudaError_t e = cudaMemsetAsync(hist_cursor, 0, 2 * kNumBins * sizeof(uint32_t), st);
   if (e != cudaSuccess) return e;
   unsigned blocks = (unsigned)((n_nodes + kBinNodesPerBlock - 1) / kBinNodesPerBlock);
-  k_bin_hist<<<blocks, 256, 0, st>>>(node_len, ids, n_nodes, hist);
+  if (totals) {
+    e = cudaMemsetAsync(totals, 0, 16, st);
+    if (e != cudaSuccess) return e;
+  }
+  k_bin_hist<<<blocks, 256, 0, st>>>(node_len, ids, n_nodes, hist, keep, totals);
   k_bin_scan<<<1, 32, 0, st>>>(hist, cursor);
-  k_bin_scatter<<<blocks, 256, 0, st>>>(node_len, ids, n_nodes, cursor, order);
+  k_bin_scatter<<<blocks, 256, 0, st>>>(node_len, ids, n_nodes, cursor, order, keep);
   return cudaGetLastError();
 }
 

@@ -59,8 +59,11 @@ cudaError_t kernels_init_device();
 
 // K0: order[] = node indices sorted by DESCENDING rate-block bin.  scratch = 2*kNumBins u32.
 // ids == NULL: nodes 0..n_nodes-1; else the n_nodes node indices listed in ids[].
+// keep != NULL: only nodes with keep[i] == i are binned (order[] then holds just those) and totals[0..1]
+// (device) receive their count and Keccak-f count.
 cudaError_t launch_bin_nodes(const uint32_t* node_len, const uint32_t* ids, uint64_t n_nodes, uint32_t* scratch,
-                             uint32_t* order, cudaStream_t st);
+                             uint32_t* order, cudaStream_t st, const uint32_t* keep = nullptr,
+                             unsigned long long* totals = nullptr);
 // K1: digests[32*i] = keccak256(node i).  order may be NULL (identity).  meta may be NULL; when
 // given, meta[i] receives the K2a record of plain branches / plain leaves and kMetaSlow otherwise.
 cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
@@ -130,6 +133,13 @@ cudaError_t launch_trie_proof_emit(const TrieBatchDev& in, const TrieWork& w, co
                                    const uint8_t* tkey_bytes, const uint32_t* tkey_off, uint32_t n_targets,
                                    const uint32_t* proof_first, const uint64_t* byte_first, uint8_t* out_bytes,
                                    uint64_t* out_off, uint32_t* out_len, bool leaves_in_arena, cudaStream_t st);
+
+// optional node de-duplication in front of K1 (dedup_kernels.cu): dup_of[i] = the node whose digest node i
+// shares (itself when unique)
+cudaError_t launch_dedup_find(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off, const uint32_t* node_len,
+                              uint32_t n_nodes, unsigned long long* keys, uint32_t* vals, uint32_t table_size /* power of 2 */,
+                              uint32_t* slot_of, uint32_t* dup_of, cudaStream_t st);
+cudaError_t launch_dedup_scatter(uint32_t n_nodes, const uint32_t* dup_of, uint8_t* digests, uint32_t* meta, cudaStream_t st);
 
 // integer issue-rate probe (microbench.cu): mode 0 = LOP3, 1 = SHF, 2 = Keccak mix
 cudaError_t run_int_peak(int mode, int sm_count, uint32_t* scratch, cudaStream_t st, double* ops_per_s);

@@ -29,7 +29,7 @@ int pick_lanes(const mptv_ctx* ctx, uint64_t n_nodes, uint64_t n_proofs) {
 
 // The whole device pipeline for one device-resident (slice of a) batch: K0 -> K1 -> K2a -> K2b.
 int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests, DevBuf& meta, DevBuf& order,
-                 DevBuf& bins, DevBuf& defer, uint8_t* status, uint64_t* value_off, uint32_t* value_len, cudaStream_t st,
+                 DevBuf& bins, DevBuf& defer, DevBuf& dedup, uint8_t* status, uint64_t* value_off, uint32_t* value_len, cudaStream_t st,
                  bool timed) {
   CK(digests.reserve(32 * (size_t)b.n_nodes + 32));
   CK(meta.reserve(4 * (size_t)b.n_nodes + 4));
@@ -43,14 +43,42 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
   // skip their launches (what matters for a single-proof call is latency)
   const bool one_wave = b.n_nodes <= (uint64_t)d.sm_count * kKeccakMinBlocks * kKeccakThreads / 4;
   const bool binned = ctx->binning && !one_wave;
-  if (binned) {
+  // optional: hash every DISTINCT node once (a secondary, separately reported mode; see dedup_kernels.cu)
+  const bool dd = ctx->dedup_nodes && !one_wave;
+  uint64_t n_hash = b.n_nodes;
+  uint32_t* dup_of = nullptr;
+  d.last_unique_nodes = 0; d.last_unique_perm = 0;
+  if (dd) {
+    uint32_t tsz = 1;
+    while (tsz < 2 * b.n_nodes) tsz <<= 1;
+    const size_t nn = (size_t)b.n_nodes;
+    CK(dedup.reserve(16 + 12ull * tsz + 8 * nn + 64));
+    uint8_t* base = dedup.as<uint8_t>();
+    unsigned long long* totals = reinterpret_cast<unsigned long long*>(base);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(base + 16);
+    uint32_t* vals = reinterpret_cast<uint32_t*>(base + 16 + 8ull * tsz);
+    uint32_t* slot_of = vals + tsz;
+    dup_of = slot_of + nn;
+    CK(launch_dedup_find(b.node_bytes, b.byte_base, b.node_off, b.node_len, (uint32_t)b.n_nodes, keys, vals, tsz, slot_of,
+                         dup_of, st));
+    // K0 bins only the representatives and counts them (per-CTA aggregated, no hot atomics)
+    CK(launch_bin_nodes(b.node_len, nullptr, b.n_nodes, bins.as<uint32_t>(), order.as<uint32_t>(), st, dup_of, totals));
+    unsigned long long hc[2] = {0, 0};
+    CK(cudaMemcpyAsync(hc, totals, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));  // the number of unique nodes sizes the K1 launch
+    n_hash = hc[0];
+    ord = order.as<uint32_t>();
+    d.last_unique_nodes = hc[0]; d.last_unique_perm = hc[1];
+  } else if (binned) {
     CK(launch_bin_nodes(b.node_len, nullptr, b.n_nodes, bins.as<uint32_t>(), order.as<uint32_t>(), st));
     ord = order.as<uint32_t>();
   }
   if (timed) CK(cudaEventRecord(d.ev[1], st));
-  CK(launch_keccak256_nodes(b.node_bytes, b.byte_base, b.node_off, b.node_len, ord, b.n_nodes,
+  CK(launch_keccak256_nodes(b.node_bytes, b.byte_base, b.node_off, b.node_len, ord, n_hash,
                             digests.as<uint8_t>(), ctx->fused_classify ? meta.as<uint32_t>() : nullptr,
                             one_wave ? nullptr : bins.as<uint32_t>() + 2 * kNumBins, d.sm_count, st));
+  if (dd) CK(launch_dedup_scatter((uint32_t)b.n_nodes, dup_of, digests.as<uint8_t>(),
+                                  ctx->fused_classify ? meta.as<uint32_t>() : nullptr, st));
   if (timed) CK(cudaEventRecord(d.ev[2], st));
   CK(launch_parse_nodes(b.node_bytes, b.byte_base, b.node_off, b.node_len, b.n_nodes, meta.as<uint32_t>(),
                         ctx->fused_classify != 0, st));
@@ -58,7 +86,7 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
   const int G = pick_lanes(ctx, b.n_nodes, b.n_proofs);
   CK(launch_verify_walk(b, digests.as<uint8_t>(), meta.as<uint32_t>(), 0, G, status, value_off, value_len, dl,
                         d.sm_count, st));
-  uint32_t other = 1 + 1 + (dl ? 1 : 0) + (binned ? 3 : 0);
+  uint32_t other = 1 + 1 + (dl ? 1 : 0) + ((binned || dd) ? 3 : 0) + (dd ? 3 : 0);
   if (b.root_from_proof) {
     CK(launch_verify_walk(b, digests.as<uint8_t>(), meta.as<uint32_t>(), 1, G, status, value_off, value_len, dl,
                           d.sm_count, st));
@@ -144,7 +172,7 @@ void mptv_destroy(mptv_ctx* ctx) {
   for (Device& d : ctx->dev) {
     cudaSetDevice(d.id);
     cudaDeviceSynchronize();
-    d.digests.release(); d.meta.release(); d.order.release(); d.bins.release(); d.defer.release();
+    d.digests.release(); d.meta.release(); d.order.release(); d.bins.release(); d.defer.release(); d.dedup.release();
     for (int k = 0; k < kSlots; k++) d.slot[k].release();
     d.rb.release();
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
@@ -165,6 +193,8 @@ int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
     ctx->binning = value ? 1 : 0;
   } else if (!strcmp(name, "fused_classify")) {
     ctx->fused_classify = value ? 1 : 0;
+  } else if (!strcmp(name, "dedup_nodes")) {
+    ctx->dedup_nodes = value ? 1 : 0;
   } else if (!strcmp(name, "fast_walk")) {
     ctx->fast_walk = value ? 1 : 0;
   } else if (!strcmp(name, "fused_leaf_hash")) {
@@ -192,7 +222,7 @@ int mptv_verify_batch_device(mptv_ctx* ctx, int dev_index, const mptv_batch* in,
   b.proof_first = in->proof_first; b.n_proofs = in->n_proofs; b.roots = in->roots;
   b.key_bytes = in->key_bytes; b.key_off = in->key_off; b.root_from_proof = in->root_from_proof;
   b.byte_base = 0; b.node_base = 0; b.key_base = 0; b.proof_base = 0;
-  return run_pipeline(ctx, d, b, d.digests, d.meta, d.order, d.bins, d.defer, out->status, out->value_off, out->value_len,
+  return run_pipeline(ctx, d, b, d.digests, d.meta, d.order, d.bins, d.defer, d.dedup, out->status, out->value_off, out->value_len,
                       st, true);
 }
 
@@ -245,6 +275,8 @@ int mptv_last_timings(mptv_ctx* ctx, int dev_index, mptv_timings* out) {
   CK(cudaEventElapsedTime(&out->walk_ms, d.ev[3], d.ev[4]));
   CK(cudaEventElapsedTime(&out->total_ms, d.ev[0], d.ev[4]));
   out->n_nodes = d.last_nodes;
+  out->n_unique_nodes = d.last_unique_nodes;
+  out->n_unique_perm = d.last_unique_perm;
   out->keccak_launches = d.last_keccak_launches;
   out->other_launches = d.last_other_launches;
   return MPTV_OK;
@@ -395,7 +427,7 @@ int run_slice(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result* out, 
     CK(s.results.reserve(13 * np + 16));
     CK(s.h_results.reserve(13 * np + 16));
     uint8_t* res = s.results.as<uint8_t>();
-    rc = run_pipeline(ctx, d, b, s.digests, s.meta, s.order, s.bins, s.defer, res + 12 * np,
+    rc = run_pipeline(ctx, d, b, s.digests, s.meta, s.order, s.bins, s.defer, s.dedup, res + 12 * np,
                       reinterpret_cast<uint64_t*>(res), reinterpret_cast<uint32_t*>(res + 8 * np), st, false);
     if (rc != MPTV_OK) return rc;
     CK(cudaMemcpyAsync(s.h_results.p, res, 13 * np, cudaMemcpyDeviceToHost, st));
