@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--pageable", action="store_true", help="e2e from ordinary (pageable) host memory instead of pinned")
     ap.add_argument("--dedup", action="store_true",
                     help="SECONDARY number: hash each distinct node of the batch once (dedup_nodes option); the "
                          "headline always hashes every supplied node, as the reference does")
@@ -567,7 +568,7 @@ def main():
         ver.set_option("lanes_per_proof", a.lanes)
     if a.dedup:
         ver.set_option("dedup_nodes", 1)
-    b, gen_info = build_batch(a, rank, pinned=True)
+    b, gen_info = build_batch(a, rank, pinned=not a.pageable)
     n_proofs, n_nodes, n_perm = b.n_proofs, b.n_nodes, b.n_perm()
     node_bytes_total = int(b.node_len.astype(np.int64).sum())
     dev = torch.device("cuda", local)
@@ -656,7 +657,8 @@ def main():
         dt = reduce_max((time.perf_counter() - t0) / e_steps, world, dev)
         h2d = sum(int(getattr(b, k).nbytes) for k in names if k != "key_bytes") + int(b.key_off[-1])
         e2e = dict(value=all_proofs / dt, unit=UNIT, h2d_bytes_per_step=h2d * passes, d2h_bytes_per_step=13 * n_proofs * passes,
-                   ms_per_step=dt * 1e3, host_memory="pinned", timer="host wall clock around the blocking C-ABI call")
+                   ms_per_step=dt * 1e3, host_memory="pageable" if a.pageable else "pinned",
+                   timer="host wall clock around the blocking C-ABI call")
         assert (est == st).all() and (evoff == voff).all() and (evlen == vlen).all(), "host and device entries disagree"
 
     # ---- roofline of the dominant kernel (K1), rank 0's device

@@ -549,10 +549,14 @@ __device__ bool fast_one(const DeviceBatch& b, uint64_t p, bool dependent, const
   const uint32_t klen = b.key_off[p + 1] - b.key_off[p];
   const uint8_t* rp = b.roots + 32 * p;
   if (dependent) {
+    // storage-circuit main.rs:10-27: the root is the storage_root of the account the earlier proof returned
     const uint64_t d = (uint64_t)b.root_from_proof[p] - b.proof_base;
-    if (status_out[d] != kStOk) return false;
-    const uint32_t so = account_storage_root_off(node_bytes + value_off_out[d], value_len_out[d]);
-    if (so == 0xffffffffu) return false;
+    uint32_t so = 0xffffffffu;
+    if (status_out[d] == kStOk) so = account_storage_root_off(node_bytes + value_off_out[d], value_len_out[d]);
+    if (so == 0xffffffffu) {  // account proof rejected, or its value is not an Account RLP
+      status_out[p] = (uint8_t)kStDepFailed; value_off_out[p] = 0; value_len_out[p] = 0;
+      return true;
+    }
     rp = node_bytes + value_off_out[d] + so;
   }
   if (!eq32_unaligned(rp, digests + 32ull * a)) return false;  // lib.rs:14: node 0 must be the root
