@@ -362,7 +362,7 @@ def load_peaks():
         return {}
 
 
-def keccak_roofline(ver, n_perm, keccak_ms, alg_bytes, launches_note):
+def keccak_roofline(ver, n_perm, keccak_ms, alg_bytes, launches_note, traffic_key=None):
     peaks = load_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     int_peak = max(ver.int_issue_peak(0, m) for m in (0, 2))  # lane-ops / s, measured now on this GPU
@@ -378,7 +378,8 @@ def keccak_roofline(ver, n_perm, keccak_ms, alg_bytes, launches_note):
         hbm=dict(bound="hbm", achieved=ach_hbm, peak=hbm_peak, unit="GB/s", frac=ach_hbm / hbm_peak,
                  peak_source="MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
                  algorithmic_bytes_per_launch=alg_bytes),
-        traffic=TRAFFIC_NOTE.get("k_keccak256_nodes"),
+        # measured DRAM bytes of ONE launch of this kernel on exactly this workload (ncu --set full), else None
+        traffic=TRAFFIC_NOTE.get(traffic_key) if traffic_key else None,
     )
 
 
@@ -663,7 +664,9 @@ def main():
 
     # ---- roofline of the dominant kernel (K1), rank 0's device
     perm_executed = int(tm.n_unique_perm) if a.dedup else n_perm
-    roofline = keccak_roofline(ver, perm_executed, float(kavg[1]), node_bytes_total + 32 * n_nodes, "1 per pass")
+    full_config2 = a.workload == "config2" and not a.dedup and n_proofs == 1_000_000 and a.accounts == 10_000_000
+    roofline = keccak_roofline(ver, perm_executed, float(kavg[1]), node_bytes_total + 32 * n_nodes, "1 per pass",
+                               "k_keccak256_nodes" if full_config2 else None)
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
                 ms_per_step=ms_per_step, higher_is_better=True, scaling="strong" if a.workload == "config5" else "weak",
