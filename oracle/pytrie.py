@@ -102,6 +102,8 @@ class Trie:
         """Nodes on the path of `key`, root first: the root always, other nodes only when
         referenced by hash (>= 32 bytes), like eth_trie's get_proof."""
         from .pyrlp import split_list  # local import to keep module load light
+        if self.root_enc == b"\x80":
+            return []  # empty trie: eth_trie's get_proof pushes the root only when it is not Node::Empty
         out = [self.root_enc]
         path = nibbles(key) + [16]
         enc = self.root_enc

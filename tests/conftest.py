@@ -27,6 +27,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def rebuild_golden():
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "rebuild_vectors.json.gz"), "rb") as f:
+        return json.loads(f.read())
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle.pyoracle import Oracle, build
     build()
