@@ -61,3 +61,20 @@ def test_borsh_roundtrip_and_flatten_layout():
     assert b.bad_root_len is not None and list(b.bad_root_len) == [False, True]
     assert b.node_bytes[int(b.node_off[2]):int(b.node_off[2]) + 33].tobytes() == b"\x02" * 33
     assert b.n_perm() == 4
+
+
+def test_wire_forms_of_both_input_types_roundtrip():
+    """borsh (what the prover feeds the guests, prover/src/bin/main.rs:41) and serde JSON (types.rs derives both)"""
+    import json
+    import zk_state_proofs_b200 as z
+    m = z.MerkleProofInput([b"\x01\x02", b"", b"\xff" * 40], b"\xaa" * 32, b"\x80")
+    assert z.MerkleProofInput.from_json(m.to_json()) == m
+    assert json.loads(m.to_json())["key"] == [128]
+    s = z.StorageProofInput([b"\x01" * 3, b"\x02" * 70], [[b"\x03" * 5], [], [b"\x04", b"\x05" * 33]], b"\xbb" * 32,
+                            b"\x11" * 20, [b"\x21" * 32, b"", b"\x22" * 32], bytes(range(32)))
+    w = s.to_borsh()
+    assert z.StorageProofInput.from_borsh(w) == s and z.StorageProofInput.from_json(s.to_json()) == s
+    # borsh layout: u32 count, then u32-prefixed byte vectors; the fixed [u8; 32] has no length prefix
+    assert w[:4] == (2).to_bytes(4, "little") and w[4:8] == (3).to_bytes(4, "little") and w[-32:] == bytes(range(32))
+    with pytest.raises(ValueError):
+        z.StorageProofInput.from_borsh(w + b"\x00")

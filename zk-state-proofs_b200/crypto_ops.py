@@ -100,6 +100,17 @@ class MerkleProofInput:
             raise ValueError("trailing bytes after MerkleProofInput")
         return cls(proof, root, key)
 
+    # serde form (types.rs:4 derives Serialize / Deserialize): byte vectors are JSON arrays of numbers
+    def to_json(self) -> str:
+        import json
+        return json.dumps(dict(proof=[list(n) for n in self.proof], root_hash=list(self.root_hash), key=list(self.key)))
+
+    @classmethod
+    def from_json(cls, text: str) -> "MerkleProofInput":
+        import json
+        d = json.loads(text)
+        return cls([bytes(n) for n in d["proof"]], bytes(d["root_hash"]), bytes(d["key"]))
+
 
 @dataclass
 class StorageProofInput:
@@ -119,6 +130,49 @@ class StorageProofInput:
         out += _borsh_bytes(self.root_hash) + _borsh_bytes(self.account_key)
         out += struct.pack("<I", len(self.storage_keys)) + b"".join(_borsh_bytes(k) for k in self.storage_keys)
         return out + bytes(self.address_keccak)
+
+    @classmethod
+    def from_borsh(cls, data: bytes) -> "StorageProofInput":
+        buf = memoryview(data)
+
+        def vec_vec(pos):
+            (n,) = struct.unpack_from("<I", buf, pos)
+            pos += 4
+            out = []
+            for _ in range(n):
+                b, pos = _read_vec_u8(buf, pos)
+                out.append(b)
+            return out, pos
+
+        account_proof, pos = vec_vec(0)
+        (ns,) = struct.unpack_from("<I", buf, pos)
+        pos += 4
+        storage_proofs = []
+        for _ in range(ns):
+            pr, pos = vec_vec(pos)
+            storage_proofs.append(pr)
+        root, pos = _read_vec_u8(buf, pos)
+        akey, pos = _read_vec_u8(buf, pos)
+        skeys, pos = vec_vec(pos)
+        if len(data) - pos != 32:
+            raise ValueError("StorageProofInput must end with the 32-byte address_keccak")
+        return cls(account_proof, storage_proofs, root, akey, skeys, bytes(buf[pos:pos + 32]))
+
+    def to_json(self) -> str:
+        import json
+        return json.dumps(dict(account_proof=[list(n) for n in self.account_proof],
+                               storage_proofs=[[list(n) for n in pr] for pr in self.storage_proofs],
+                               root_hash=list(self.root_hash), account_key=list(self.account_key),
+                               storage_keys=[list(k) for k in self.storage_keys],
+                               address_keccak=list(self.address_keccak)))
+
+    @classmethod
+    def from_json(cls, text: str) -> "StorageProofInput":
+        import json
+        d = json.loads(text)
+        return cls([bytes(n) for n in d["account_proof"]], [[bytes(n) for n in pr] for pr in d["storage_proofs"]],
+                   bytes(d["root_hash"]), bytes(d["account_key"]), [bytes(k) for k in d["storage_keys"]],
+                   bytes(d["address_keccak"]))
 
 
 # ----------------------------------------------------------------------------- CSR batch
