@@ -154,7 +154,10 @@ __global__ void __launch_bounds__(kTrieThreads) k_trie_structure(const TrieBatch
   uint32_t np2 = 2;
   while (np2 < n) np2 <<= 1;
 
-  // ---- load: key prefixes, lengths, identity permutation
+  // ---- load: key prefixes, lengths, identity permutation; and is item i's key exactly rlp(i)?
+  // (that is how trie-utils keys every transaction / receipt trie: alloy_rlp::encode(index) in block
+  // order, transaction.rs:45) -- then the sorted order is known without sorting
+  bool indexed = true;
   for (uint32_t i = tid; i < np2; i += kTrieThreads) {
     uint64_t p = ~0ull;
     uint32_t id = kNoItem, l = 255;
@@ -164,17 +167,33 @@ __global__ void __launch_bounds__(kTrieThreads) k_trie_structure(const TrieBatch
       p = 0;
       const uint8_t* k = in.key_bytes + koff[i];
       for (uint32_t b = 0; b < 8 && b < l; b++) p |= (uint64_t)k[b] << (56 - 8 * b);
+      // alloy_rlp::encode(i) for i < 65536: 0x80 | i (< 0x80) | 0x81 i | 0x82 hi lo
+      const uint64_t want = i == 0 ? 0x80ull << 56
+                            : i < 0x80 ? (uint64_t)i << 56
+                            : i < 0x100 ? (0x81ull << 56) | ((uint64_t)i << 48)
+                                        : (0x82ull << 56) | ((uint64_t)i << 40);
+      const uint32_t wl = i < 0x80 ? 1u : (i < 0x100 ? 2u : 3u);
+      indexed = indexed && p == want && l == wl;
     }
     v.pre[i] = p; v.idx[i] = id; v.kl[i] = (uint8_t)l;
   }
-  __syncthreads();
+  indexed = __syncthreads_and(indexed);
 
-  // ---- bitonic sort by (key, insertion index)
-  for (uint32_t k = 2; k <= np2; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t i = tid; i < np2; i += kTrieThreads) {
-        const uint32_t x = i ^ j;
-        if (x > i) {
+  if (indexed) {
+    // byte order of rlp(i): 0x01..0x7f (items 1..127), 0x80 (item 0), 0x81 0x80.. (128..255), 0x82.. (256..):
+    // the first k = min(n, 128) entries rotate left by one, everything else is already in place
+    const uint32_t k = n < 128 ? n : 128;
+    uint64_t p = 0; uint32_t q = 0, l = 0;
+    if (tid < k) { const uint32_t src = tid + 1 == k ? 0 : tid + 1; p = v.pre[src]; q = v.idx[src]; l = v.kl[src]; }
+    __syncthreads();
+    if (tid < k) { v.pre[tid] = p; v.idx[tid] = q; v.kl[tid] = (uint8_t)l; }
+    __syncthreads();
+  } else {
+    // ---- bitonic sort by (key, insertion index): one compare-exchange per thread per step
+    for (uint32_t k = 2; k <= np2; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t t2 = tid; t2 < np2 / 2; t2 += kTrieThreads) {
+          const uint32_t i = ((t2 & ~(j - 1)) << 1) | (t2 & (j - 1)), x = i | j;
           const bool up = (i & k) == 0;
           if (sort_greater(v, i, x, in.key_bytes, koff) == up) {
             const uint64_t p = v.pre[i]; v.pre[i] = v.pre[x]; v.pre[x] = p;
@@ -182,8 +201,8 @@ __global__ void __launch_bounds__(kTrieThreads) k_trie_structure(const TrieBatch
             const uint8_t l = v.kl[i]; v.kl[i] = v.kl[x]; v.kl[x] = l;
           }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
 
