@@ -478,8 +478,11 @@ __device__ uint32_t warp_put_value(uint8_t* dst, const uint8_t* val, uint32_t vl
 }  // namespace
 
 // one warp writes the RLP encoding of `node` to dst (children are read from `arena` / w.digests)
+constexpr uint32_t kEncStage = 576;  // per-warp shared staging: a branch without a value is at most 3 + 16 * 33 + 1 bytes
+
+// sbuf: kEncStage bytes of shared memory owned by this warp (16-byte aligned)
 __device__ void warp_encode_node(const TrieBatchDev& in, const TrieWork& w, const uint8_t* __restrict__ arena, uint32_t node,
-                                 uint8_t* __restrict__ dst, uint32_t lane) {
+                                 uint8_t* __restrict__ dst, uint32_t lane, uint8_t* sbuf) {
   const uint4 r = w.rec[node];
   const uint32_t len = w.len[node];
   const uint32_t kind = rec_kind(r);
@@ -527,26 +530,46 @@ __device__ void warp_encode_node(const TrieBatchDev& in, const TrieWork& w, cons
       const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
       if ((int)lane >= o) incl += x;
     }
-    uint8_t* ip = dst + hl + (incl - sz);
-    if (lane == 0) put_hdr(dst, payload, true);
+    // A branch without a value (every inner node of a tx / receipt / state trie) is assembled in shared
+    // memory and leaves as coalesced 16-byte stores; writing the 33-byte items straight to global memory
+    // costs one scattered byte store per lane per byte (30 x the sector writes).
+    const bool staged = r.y == kNoItem && len <= kEncStage;
+    uint8_t* out = staged ? sbuf : dst;
+    uint8_t* ip = out + hl + (incl - sz);
+    if (lane == 0) put_hdr(out, payload, true);
     if (lane < 16) {
       if (!has) ip[0] = 0x80;
       else if (cl < 32) { const uint8_t* s = arena + w.off[child]; for (uint32_t i = 0; i < cl; i++) ip[i] = s[i]; }
-      else { ip[0] = 0xa0; const uint8_t* s = w.digests + 32ull * child; for (uint32_t i = 0; i < 32; i++) ip[1 + i] = s[i]; }
+      else {
+        ip[0] = 0xa0;
+        const uint4* s = reinterpret_cast<const uint4*>(w.digests + 32ull * child);
+        const uint4 a = s[0], b = s[1];
+        const uint32_t ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 32; i++) ip[1 + i] = (uint8_t)(ws[i >> 2] >> (8 * (i & 3)));
+      }
     }
     const uint32_t voff = __shfl_sync(0xffffffffu, incl - sz, 16);
     if (r.y == kNoItem) { if (lane == 16) ip[0] = 0x80; }
     else warp_put_value(dst + hl + voff, val, vl, lane);
+    if (staged) {
+      __syncwarp();
+      const uint4* s4 = reinterpret_cast<const uint4*>(sbuf);
+      uint4* d4 = reinterpret_cast<uint4*>(dst);  // node slots are 16-byte aligned and padded to 16
+      for (uint32_t c = lane; c < (len + 15u) / 16u; c += 32) d4[c] = s4[c];
+      __syncwarp();
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) k_trie_encode(const TrieBatchDev in, const TrieWork w, const uint32_t* __restrict__ list,
                                                      uint32_t n_list, uint8_t* __restrict__ arena) {
   const uint32_t lane = threadIdx.x & 31u;
+  __shared__ __align__(16) uint8_t s_enc[8][kEncStage];
   const uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (wi >= n_list) return;
   const uint32_t node = list[wi];
-  warp_encode_node(in, w, arena, node, arena + w.off[node], lane);
+  warp_encode_node(in, w, arena, node, arena + w.off[node], lane, s_enc[threadIdx.x >> 5]);
 }
 
 __global__ void __launch_bounds__(256) k_trie_roots(const TrieBatchDev in, const TrieWork w, uint8_t* __restrict__ roots32) {
@@ -706,6 +729,7 @@ __global__ void __launch_bounds__(256) k_trie_proof_emit(const TrieBatchDev in, 
                                                          const uint32_t* __restrict__ proof_first, const uint64_t* __restrict__ byte_first,
                                                          uint8_t* __restrict__ out_bytes, uint64_t* __restrict__ out_off,
                                                          uint32_t* __restrict__ out_len, int leaves_in_arena) {
+  __shared__ __align__(16) uint8_t s_enc[8][kEncStage];
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= n_targets) return;
@@ -715,7 +739,7 @@ __global__ void __launch_bounds__(256) k_trie_proof_emit(const TrieBatchDev in, 
     const uint32_t len = w.len[node];
     if (!leaves_in_arena && (w.rec[node].x & 0xffu) == kTLeaf) {
       // hashed leaves were digested straight from the value arena (K1L): encode this one now
-      warp_encode_node(in, w, arena, node, out_bytes + o, lane);
+      warp_encode_node(in, w, arena, node, out_bytes + o, lane, s_enc[threadIdx.x >> 5]);
     } else {
       const uint4* s = reinterpret_cast<const uint4*>(arena + w.off[node]);  // 16-byte aligned slots on both sides
       uint4* d = reinterpret_cast<uint4*>(out_bytes + o);
