@@ -121,8 +121,7 @@ static uint32_t put_hdr(uint8_t *o, uint32_t n, int list) {
   for (int i = 0; i < k; i++) o[1 + i] = t[k - 1 - i];
   return 1 + (uint32_t)k;
 }
-static uint32_t hdr_size(uint32_t n) { return n < 56 ? 1 : (n < 256 ? 2 : (n < 65536 ? 3 : (n < (1u << 24) ? 4 : 5))); }
-static uint32_t str_size(const uint8_t *s, uint32_t n) { return (n == 1 && s[0] < 0x80) ? 1 : hdr_size(n) + n; }
+
 static uint32_t put_str(uint8_t *o, const uint8_t *s, uint32_t n) {
   if (n == 1 && s[0] < 0x80) { o[0] = s[0]; return 1; }
   uint32_t h = put_hdr(o, n, 0);
