@@ -174,3 +174,27 @@ def test_rebuild_golden_vectors_on_gpu(verifier, rebuild_golden, leaf_mode):
         assert st[q] == p["status"]
         if p["status"] == 0:
             assert b.value(int(voff[q]), int(vlen[q])).hex() == p["value"]
+
+
+def test_adversarial_shapes_on_gpu(verifier, oracle, leaf_mode):
+    """deep prefix chains, 63-nibble extensions, full fan-out, the 32-byte inline boundary, the empty key:
+    roots and proofs equal the oracle's, and the proofs verify"""
+    import zk_state_proofs_b200 as z
+    from tests.test_rebuild_oracle import adversarial_tries, make_kv
+    tries = adversarial_tries()
+    d = make_kv(tries)
+    kv = _kv(z, d)
+    want = oracle.trie_roots(d, nthreads=4)[0]
+    targets = [(t, k) for t, kvs in enumerate(tries) for k in list(dict(kvs))[:8]]
+    targets += [(0, bytes(range(1, 20)) + b"\xee"), (1, b"\x01" * 32), (3, b""), (3, b"\x05\x05")]  # absent keys
+    roots, b = verifier.trie_proofs(kv, targets)
+    assert (roots == want).all(), np.nonzero((roots != want).any(axis=1))[0]
+    got = _proofs(b)
+    for (t, k), nodes in zip(targets, got):
+        assert nodes == oracle.trie_get_proof(d, t, k)[1], (t, k.hex())
+    st, voff, vlen = verifier.verify_batch(b)
+    for q, (t, k) in enumerate(targets):
+        o = oracle.verify(roots[t].tobytes(), got[q], k)
+        assert st[q] == o[0]
+        if o[0] == 0:
+            assert b.value(int(voff[q]), int(vlen[q])) == o[1]

@@ -113,3 +113,37 @@ def test_rebuild_golden_vectors(oracle, rebuild_golden):
             assert st == p["status"] and (val.hex() if val is not None else None) == p["value"]
             n += 1
     assert n >= 190
+
+
+def adversarial_tries():
+    """shapes that stress the skeleton: deep prefix chains (a branch value at every level), long shared
+    prefixes (extensions of up to 63 nibbles), full fan-out, the inline / hashed size boundary at 32 bytes,
+    the empty key, 1-byte values on both sides of 0x80"""
+    T = []
+    base = bytes(range(1, 33))
+    T.append([(base[:i], bytes([i]) * (1 + i % 5)) for i in range(0, 33)])                   # nested prefixes, 33 levels
+    T.append([(base[:31] + bytes([b]), b"v" * 40) for b in (0x00, 0x01, 0x10, 0xff)])        # 62-nibble extension
+    T.append([(base[:31] + bytes([0x50 | b]), b"w" * (30 + b)) for b in range(16)])          # 63-nibble extension
+    T.append([(bytes([a]), bytes([a]) * 3) for a in range(256)])                             # 16 x 16 full fan-out, inline leaves
+    T.append([(bytes([a, b]), bytes([a ^ b]) * (a % 40 + 1)) for a in range(0, 256, 17) for b in range(0, 256, 5)])
+    for pad in range(24, 36):                                                                # leaf encodings of 29..41 bytes
+        T.append([(b"\x12\x34", b"x" * pad), (b"\x12\x35", b"y" * pad), (b"\x99", b"z" * pad)])
+    T.append([(b"", b"empty key"), (b"\x00", b"\x00"), (b"\x00\x00", b"\x7f"), (b"\x01", b"\x80"), (b"\x02", b"\xff")])
+    T.append([(b"", b"only the empty key")])
+    T.append([(b"\xab" * 32, b"one 32-byte key")])
+    T.append([(b"k", b"a"), (b"k", b""), (b"k", b"b"), (b"j", b"c"), (b"j", b"")])            # overwrite / delete / re-insert
+    T.append([(bytes([i % 7, i % 3]), bytes([i])) for i in range(200)])                      # heavy duplication, last write wins
+    return T
+
+
+def test_adversarial_shapes_match_independent_builder(oracle):
+    tries = adversarial_tries()
+    kv = make_kv(tries)
+    roots, _, _ = oracle.trie_roots(kv, nthreads=2)
+    for t, kvs in enumerate(tries):
+        d = dict(kvs)
+        T = Trie(d, oracle.keccak256)
+        assert T.root == roots[t].tobytes(), t
+        for k in list(d)[:6]:
+            root, nodes = oracle.trie_get_proof(kv, t, k)
+            assert nodes == T.proof(k), (t, k.hex())
