@@ -44,6 +44,44 @@ APPENDIX_E = [
 ]
 
 
+def nested_cases(keccak):
+    """Inline nodes nested far deeper than any real trie produces (an inline node is < 32 bytes): chains of
+    inline extensions (2 bytes a level) and inline branches inside inline branches, as the root node (the
+    lib.rs:19 re-encode assert fires: an inline child >= 32 bytes is not canonical) and below a hashed root
+    (accepted by the reference at every depth).  Tags "deviation/..." mark the one documented limit of this
+    repository (inline BRANCH nesting beyond 63 levels is rejected); the recorded outcome is the reference's."""
+    from .pytrie import hex_prefix, rlp_list, rlp_str
+    nibs = [(i * 7 + 3) % 16 for i in range(128)]
+    key = bytes((nibs[2 * i] << 4) | nibs[2 * i + 1] for i in range(64))
+    out = []
+
+    def under_root(node, tag):
+        slots = [b"\x80"] * 16
+        slots[nibs[0]] = rlp_str(keccak(node))
+        root_node = rlp_list(slots + [b"\x80"])
+        out.append(dict(root=keccak(root_node), proof=[root_node, node], key=key, tag=tag))
+
+    for D in (1, 15, 16, 17, 40, 63, 64, 65, 100, 120):
+        node = rlp_list([rlp_str(hex_prefix(nibs[1 + D:], True)), rlp_str(b"value-bytes-0123456789")])
+        for k in range(D - 1, -1, -1):
+            node = rlp_list([rlp_str(hex_prefix([nibs[1 + k]], False)), node])
+        under_root(node, f"nested/ext-chain-{D}")
+        if D in (1, 16, 64, 100):
+            chain0 = rlp_list([rlp_str(hex_prefix(nibs[D:], True)), rlp_str(b"value-bytes-0123456789")])
+            for k in range(D - 1, -1, -1):
+                chain0 = rlp_list([rlp_str(hex_prefix([nibs[k]], False)), chain0])
+            out.append(dict(root=keccak(chain0), proof=[chain0], key=key, tag=f"nested/ext-chain-as-root-{D}"))
+    for B in (1, 2, 10, 40, 62, 63, 64, 70):
+        node = rlp_list([rlp_str(hex_prefix(nibs[1 + B:], True)), rlp_str(b"v")])
+        for k in range(B - 1, -1, -1):
+            slots = [b"\x80"] * 16
+            slots[nibs[1 + k]] = node
+            node = rlp_list(slots + [b"\x80"])
+        # the top branch is frame 0 and the leaf sits B levels below it: 63 is the deepest this repository decodes
+        under_root(node, ("deviation/" if B > 63 else "nested/") + f"branch-in-branch-{B}")
+    return out
+
+
 def main():
     seed, n_tries, n_mut, n_weird = 7, 40, 500, 1200
     o = Oracle()
@@ -59,6 +97,8 @@ def main():
     t = Trie(kv, o.keccak256)
     for i in (15, 0, 127, 128, 199, 200):
         cases.append(dict(root=t.root, proof=t.proof(rlp_uint(i)), key=rlp_uint(i), tag=f"config1/tx{i}"))
+
+    cases += nested_cases(o.keccak256)
 
     def one(c):
         return ref.run(c["root"], c["proof"], c["key"])

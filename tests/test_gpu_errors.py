@@ -58,7 +58,7 @@ def test_separate_contexts_from_separate_threads(golden):
     import zk_state_proofs_b200 as z
     vs = golden["vectors"]
     inputs = [z.MerkleProofInput(v["proof_b"], v["root_b"], v["key_b"]) for v in vs]
-    want = [v["status"] for v in vs]
+    want = [v["expect_status"] for v in vs]
     errs = []
 
     def work(seed):

@@ -12,7 +12,10 @@ constexpr int kBinNodesPerBlock = 4096;  // nodes handled by one CTA of the binn
 constexpr int kKeccakThreads = 128;      // K1 CTA size: one node per thread
 constexpr int kKeccakMinBlocks = 4;      // resident CTAs / SM  (=> <= 128 registers / thread)
 
-constexpr int kMaxInlineDepth = 16;      // K2a DFS stack: inline nodes nested deeper are rejected
+// K2a DFS stack.  Inline extensions chain as tail calls (no stack); inline nodes under a BRANCH nested
+// deeper than this -- >= 1.1 KB of purpose-built bytes, an inline node being < 32 bytes in any real trie --
+// are rejected as InvalidData where the reference would recurse on (same rule in oracle/mpt_oracle.c).
+constexpr int kMaxInlineDepth = 64;
 
 // verdict classes, 1:1 with the reference's outcomes (include/mptv.h MPTV_ST_*)
 enum : uint32_t {

@@ -63,7 +63,7 @@ __device__ bool rlp_hdr(const uint8_t* p, uint32_t n, Hdr& h) {
 
 // ------------------------------------------------------------------ K2a: per-node decode
 // Frame of the explicit DFS stack over nested inline nodes.
-struct Frame { uint32_t pos, end; uint8_t cnt, idx, leaf, pad; };
+struct Frame { uint32_t pos, end; uint8_t cnt, idx, leaf, top; };
 
 // scan the items of the list at p[lst .. lst+hdr+payload): every header must be valid and fit;
 // returns the item count (18 means "more than 17") or -1 on a header error
@@ -100,7 +100,7 @@ __device__ uint32_t parse_node(const uint8_t* p, uint32_t n) {
     int c = scan_items(p, 0, h);
     if (c != 2 && c != 17) return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);
     st[0].pos = h.hdr_len; st[0].end = h.hdr_len + h.payload_len;
-    st[0].cnt = (uint8_t)c; st[0].idx = 0; st[0].leaf = 0;
+    st[0].cnt = (uint8_t)c; st[0].idx = 0; st[0].leaf = 0; st[0].top = 1;
   }
   uint32_t top_kind = st[0].cnt == 17 ? kKindBranch : kKindExt;
   uint32_t mask = 0, fast = st[0].cnt == 17 ? 1u : 0u;
@@ -126,7 +126,7 @@ __device__ uint32_t parse_node(const uint8_t* p, uint32_t n) {
         // decode_node calls key.is_leaf() = hex_data[len-1]: panics on an empty extension path
         if (!f.leaf && nn == 0) return make_meta(kKindEmpty, kDecPanic, 0, 0, 0, 0);
         if (t.is_list || (!(flag & 1) && (b & 15))) canon = 0;
-        if (sp == 0) top_kind = f.leaf ? kKindLeaf : kKindExt;
+        if (f.top) top_kind = f.leaf ? kKindLeaf : kKindExt;
       } else if (f.leaf) {
         if (!value_item_canonical(t)) canon = 0;
       } else {
@@ -137,22 +137,28 @@ __device__ uint32_t parse_node(const uint8_t* p, uint32_t n) {
       else {
         if (!value_item_canonical(t)) canon = 0;
         // "fast" (plain branch) promises the walk an EMPTY value item, i.e. exactly 0x80
-        if (sp == 0 && (t.is_list || t.payload_len != 0)) fast = 0;
+        if (f.top && (t.is_list || t.payload_len != 0)) fast = 0;
       }
     }
     if (is_child) {
       if (t.is_list) {
         // inline node: decoded recursively; re-encodes in place only while < 32 bytes (write_node)
         if (t.hdr_len + t.payload_len >= 32) canon = 0;
-        if (sp == 0) fast = 0;
-        if (sp + 1 >= kMaxInlineDepth) return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);
+        if (f.top) fast = 0;
         int c = scan_items(p, item, t);
         if (c != 2 && c != 17) return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);
-        sp++;
+        // An extension's child is the LAST item of its list: nothing of the parent is left to visit, so
+        // the child takes over the parent's frame (a tail call) -- chains of inline extensions, 2 bytes
+        // a level, may be arbitrarily deep.  Only inline nodes under a BRANCH consume stack.
+        const bool tail = f.cnt == 2;
+        if (!tail) {
+          if (sp + 1 >= kMaxInlineDepth) return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);  // documented limit
+          sp++;
+        }
         st[sp].pos = item + t.hdr_len; st[sp].end = item + t.hdr_len + t.payload_len;
-        st[sp].cnt = (uint8_t)c; st[sp].idx = 0; st[sp].leaf = 0;
+        st[sp].cnt = (uint8_t)c; st[sp].idx = 0; st[sp].leaf = 0; st[sp].top = 0;
       } else if (t.payload_len == 32) {
-        if (sp == 0) mask |= 1u << i;
+        if (f.top) mask |= 1u << i;
       } else if (t.payload_len != 0) {
         return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);  // InvalidData (R16)
       }
@@ -386,7 +392,7 @@ __device__ void walk_one(const DeviceBatch& b, int wave, const Group<G>& g, cons
     if (meta_kind(m) == kKindEmpty) status = kStKeyNotFound;
     bool done = status != kStOk;
     for (uint32_t guard = 0; !done; guard++) {
-      if (guard > 4096) { status = kStInvalidProof; break; }
+      if (guard > 2 * klen + n + 8) { status = kStInvalidProof; break; }  // every step consumes a nibble or a node
       const uint8_t* link = nullptr;  // where the 32-byte child reference to follow lives
       bool use_spec = false;          // ... or take it from lane cur's prefetched copy
       if (lp == 0 && meta_fast(m)) {
