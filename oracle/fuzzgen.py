@@ -270,11 +270,88 @@ def weird_cases(rng: random.Random, keccak, n: int):
     return out
 
 
-def corpus(seed: int, keccak, n_tries: int, n_mut: int, n_weird: int):
+def _nested(rng, depth, used, corrupt):
+    """An inline node nested `depth` levels deep.  -> (encoding, nibble path to its value, value).
+    `used` = nibbles consumed above (the leaf picks its path length so that the whole key is byte aligned);
+    `corrupt` = probability of planting one decode fault (bad hex-prefix flag, 3-item list, 31-byte child
+    string, empty extension path) somewhere on or beside the path."""
+    kind = rng.choice(["ext", "branch", "branch", "leaf"]) if depth > 0 else "leaf"
+    if kind == "leaf":
+        n = rng.randint(0, 4)
+        if (used + n) & 1:
+            n += 1
+        nib = [rng.randrange(16) for _ in range(n)]
+        val = rng.choice([b"\x05", b"\xcc", b"", rng.randbytes(3), rng.randbytes(20), rng.randbytes(60)])
+        hp = bytearray(hex_prefix(nib, True))
+        if rng.random() < corrupt:
+            hp[0] = (hp[0] & 0x0F) | (rng.choice([4, 7, 12]) << 4)
+        items = [rlp_str(bytes(hp)), rlp_str(val)]
+        if rng.random() < corrupt:
+            items.append(b"\x01")
+        return rlp_list(items), nib, val
+    if kind == "ext":
+        nib = [rng.randrange(16) for _ in range(rng.randint(1, 3))]
+        if rng.random() < corrupt * 0.5:
+            nib = []
+        child, path, val = _nested(rng, depth - 1, used + len(nib), corrupt)
+        return rlp_list([rlp_str(hex_prefix(nib, False)), child]), nib + path, val
+    slot = rng.randrange(16)
+    child, path, val = _nested(rng, depth - 1, used + 1, corrupt)
+    slots = []
+    for i in range(16):
+        if i == slot:
+            slots.append(child)
+        else:
+            r = rng.random()
+            if r < 0.80: slots.append(b"\x80")
+            elif r < 0.88: slots.append(rlp_str(rng.randbytes(32)))
+            elif r < 0.96: slots.append(_inline_leaf(rng, True))
+            elif r < 0.96 + corrupt: slots.append(rlp_str(rng.randbytes(rng.choice([31, 33, 5]))))
+            else: slots.append(_nested(rng, min(depth - 1, 2), 0, corrupt)[0])
+    bval = b"\x80" if rng.random() < 0.9 else rlp_str(rng.randbytes(rng.randint(1, 9)))
+    return rlp_list(slots + [bval]), [slot] + path, val
+
+
+def nested_cases(rng: random.Random, keccak, n: int):
+    """Inline nodes inside inline nodes, up to 12 levels, as the root node and below a hashed root, with the
+    key that leads to the innermost value (or a neighbour of it) and an occasional planted decode fault."""
+    out = []
+    for _ in range(n):
+        depth = rng.randint(1, 12)
+        corrupt = rng.choice([0.0, 0.0, 0.03, 0.1])
+        as_root = rng.random() < 0.4
+        node, path, _ = _nested(rng, depth, 0 if as_root else 1, corrupt)
+        if as_root:
+            proof, root, nib = [node], keccak(node), path
+        else:
+            slot = rng.randrange(16)
+            slots = [b"\x80"] * 16
+            slots[slot] = rlp_str(keccak(node)) if len(node) >= 32 or rng.random() < 0.5 else node
+            rootn = rlp_list(slots + [b"\x80"])
+            proof, root, nib = [rootn, node], keccak(rootn), [slot] + path
+        if len(nib) & 1:
+            nib = nib + [rng.randrange(16)]
+        key = bytes((nib[i] << 4) | nib[i + 1] for i in range(0, len(nib), 2))
+        r = rng.random()
+        if r < 0.15 and key:       # a neighbouring key: leaves the path somewhere inside the nesting
+            k = bytearray(key); i = rng.randrange(len(k)); k[i] ^= 1 << rng.randrange(8); key = bytes(k)
+        elif r < 0.22:
+            key = key[:-1]
+        elif r < 0.28:
+            key = key + bytes([rng.randrange(256)])
+        if rng.random() < 0.2:
+            rng.shuffle(proof)
+        out.append(dict(root=root, proof=proof, key=key, tag="nested/root" if as_root else "nested/child"))
+    return out
+
+
+def corpus(seed: int, keccak, n_tries: int, n_mut: int, n_weird: int, n_nested: int = 0):
     rng = random.Random(seed)
     base = valid_cases(rng, keccak, n_tries)
     out = list(base)
     for _ in range(n_mut):
         out.append(mutate(rng, rng.choice(base), keccak))
     out += weird_cases(rng, keccak, n_weird)
+    if n_nested:
+        out += nested_cases(rng, keccak, n_nested)
     return out

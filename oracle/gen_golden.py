@@ -99,6 +99,9 @@ def main():
         cases.append(dict(root=t.root, proof=t.proof(rlp_uint(i)), key=rlp_uint(i), tag=f"config1/tx{i}"))
 
     cases += nested_cases(o.keccak256)
+    import random as _random
+    from .fuzzgen import nested_cases as fuzz_nested
+    cases += [dict(c, tag="fuzz-" + c["tag"]) for c in fuzz_nested(_random.Random(99), o.keccak256, 600)]
 
     def one(c):
         return ref.run(c["root"], c["proof"], c["key"])
