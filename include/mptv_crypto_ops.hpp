@@ -16,6 +16,7 @@
 //
 // There is no CPU fallback: constructing a Verifier without a B200 throws.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstring>
@@ -198,12 +199,14 @@ class Verifier {
   // the risc0 storage guest: account proof under address_keccak, then every storage proof under the
   // account's storage_root with key keccak(storage_key); returns the storage values, throws like the guest
   std::vector<Bytes> verify_storage_proof_input(const StorageProofInput& in) {
-    std::vector<B256> hashed = keccak_many(in.storage_keys);
+    // the guest zips storage_proofs with storage_keys (main.rs:18-21): the shorter list decides
+    const size_t n_pairs = std::min(in.storage_proofs.size(), in.storage_keys.size());
+    std::vector<B256> hashed = keccak_many(std::vector<Bytes>(in.storage_keys.begin(), in.storage_keys.begin() + n_pairs));
     std::vector<MerkleProofInput> items;
     std::vector<int32_t> rfp;
     items.push_back({in.account_proof, in.root_hash, Bytes(in.address_keccak.begin(), in.address_keccak.end())});
     rfp.push_back(-1);
-    for (size_t i = 0; i < in.storage_proofs.size(); i++) {
+    for (size_t i = 0; i < n_pairs; i++) {
       items.push_back({in.storage_proofs[i], Bytes(32, 0), Bytes(hashed[i].begin(), hashed[i].end())});
       rfp.push_back(0);
     }

@@ -715,7 +715,8 @@ class Verifier:
         """The risc0 storage guest (storage-circuit/src/main.rs:6-31): account proof under
         address_keccak, then every storage proof under the account's storage_root with key
         keccak(storage_key).  Returns the verified storage values; raises VerifyPanic like the guest."""
-        hashed = self._keccak_many(inp.storage_keys)
+        n = min(len(inp.storage_proofs), len(inp.storage_keys))  # .zip() in the guest: the shorter list decides
+        hashed = self._keccak_many(inp.storage_keys[:n])
         items = [MerkleProofInput(inp.account_proof, inp.root_hash, bytes(inp.address_keccak))]
         rfp = [-1]
         for pr, k in zip(inp.storage_proofs, hashed):
@@ -732,17 +733,16 @@ class Verifier:
         device batch (storage keys hashed in one Keccak launch, storage roots taken on the device from
         the verified account leaves).  -> per input: list of storage values, or the VerifyPanic the
         guest would have died with (the first failing proof in the guest's order)."""
-        all_keys = [k for inp in inputs for k in inp.storage_keys]
-        hashed = self._keccak_many(all_keys)
+        # the guest zips storage_proofs with storage_keys (main.rs:18-21): the shorter list decides
+        pairs = [list(zip(inp.storage_proofs, inp.storage_keys)) for inp in inputs]
+        hashed = self._keccak_many([k for ps in pairs for _, k in ps])
         items, rfp, spans = [], [], []
         hk = 0
-        for inp in inputs:
-            if len(inp.storage_proofs) != len(inp.storage_keys):
-                raise ValueError("storage_proofs and storage_keys differ in length")
+        for inp, ps in zip(inputs, pairs):
             a = len(items)
             items.append(MerkleProofInput(inp.account_proof, inp.root_hash, bytes(inp.address_keccak)))
             rfp.append(-1)
-            for pr in inp.storage_proofs:
+            for pr, _ in ps:
                 items.append(MerkleProofInput(pr, b"\x00" * 32, hashed[hk]))
                 rfp.append(a)
                 hk += 1
