@@ -86,7 +86,7 @@ cudaError_t launch_verify_walk(const DeviceBatch& b, const uint8_t* digests, con
                                cudaStream_t st);
 
 // ------------------------------------------------------------------ K4: trie rebuild (rebuild_kernels.cu)
-constexpr int kTrieThreads = 256;       // CTA of k_trie_structure (one trie per CTA)
+constexpr int kTrieThreads = 128;       // CTA of k_trie_structure (one trie per CTA)
 constexpr int kTrieMaxItems = 8192;     // items per trie (shared-memory sort); larger tries are refused
 constexpr int kTrieMaxKeyLen = 32;      // key bytes (every Ethereum trie key is <= 32 bytes)
 constexpr int kMaxLevels = 136;         // node heights: < 2 * 64 nibbles + 2

@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kTrieThreads) k_trie_structure(const TrieBatch
   if (indexed) {
     // byte order of rlp(i): 0x01..0x7f (items 1..127), 0x80 (item 0), 0x81 0x80.. (128..255), 0x82.. (256..):
     // the first k = min(n, 128) entries rotate left by one, everything else is already in place
+    static_assert(kTrieThreads >= 128, "the rotation below gives one of the first 128 entries to each thread");
     const uint32_t k = n < 128 ? n : 128;
     uint64_t p = 0; uint32_t q = 0, l = 0;
     if (tid < k) { const uint32_t src = tid + 1 == k ? 0 : tid + 1; p = v.pre[src]; q = v.idx[src]; l = v.kl[src]; }
