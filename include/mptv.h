@@ -144,6 +144,8 @@ int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops
  *   "fused_classify"   K1 also classifies plain branches / leaves  (default 1)
  *   "fast_walk"        K2f thread-per-proof chain check + K2b on the deferred rest (default 1)
  *   "fused_leaf_hash"  rebuild: K1L hashes leaves straight from the value arena (default 1)
+ *   "long_leaf_bin", "long_leaf_ctas"  rebuild: leaves of at least this many rate blocks are hashed in a launch of
+ *                      their own with this many 4-warp CTAs per SM (defaults 33 and 1; tuning knobs)
  *   "dedup_nodes"      hash each DISTINCT node of a batch once and share the digest (default 0).
  *                      Results are identical; the executed Keccak-f count drops.  The reference hashes
  *                      every supplied node, so numbers measured with this option are a SECOND,

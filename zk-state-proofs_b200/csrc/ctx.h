@@ -133,6 +133,8 @@ struct mptv_ctx {
   int fused_classify = 1;  // K1 also classifies plain branches / leaves (K2a fast path)
   int dedup_nodes = 0;     // hash each DISTINCT node once (secondary mode, reported separately)
   int fast_walk = 1;       // K2f decides chain-shaped proofs one thread each; K2b gets the deferred rest
+  int long_leaf_bin = mptv::kLongLeafBin;  // rebuild: leaves in rate-block bins >= this are hashed in their own launch ...
+  int long_leaf_ctas = 1;            // ... with this many K1L CTAs (of 4 warps) per SM
   int fused_leaf_hash = 1; // rebuild: hash leaves straight from the value arena (K1L), no encode pass
 };
 

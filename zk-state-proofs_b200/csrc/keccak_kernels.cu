@@ -476,7 +476,7 @@ cudaError_t kernels_init_device() {
 
 cudaError_t launch_keccak256_leaves(const TrieBatchDev& in, const uint4* rec, const uint32_t* node_len,
                                     const uint32_t* order, uint32_t n_nodes, uint8_t* digests, uint32_t* tile_counter,
-                                    int sm_count, cudaStream_t st) {
+                                    int sm_count, cudaStream_t st, int ctas_per_sm) {
   if (n_nodes == 0) return cudaSuccess;
   if (tile_counter) {
     cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(uint32_t), st);
@@ -484,7 +484,7 @@ cudaError_t launch_keccak256_leaves(const TrieBatchDev& in, const uint4* rec, co
   }
   const size_t smem = (size_t)kStages * kKeccakThreads * kLeafSlotBytes;
   uint32_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
-  uint32_t grid = (uint32_t)sm_count * kKeccakMinBlocks;
+  uint32_t grid = (uint32_t)sm_count * (ctas_per_sm > 0 && ctas_per_sm < kKeccakMinBlocks ? ctas_per_sm : kKeccakMinBlocks);
   if (grid > n_tiles) grid = n_tiles;
   k_keccak256_leaves<<<grid, kKeccakThreads, smem, st>>>(in, rec, node_len, order, n_nodes, digests, tile_counter);
   return cudaGetLastError();

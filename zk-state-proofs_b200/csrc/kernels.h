@@ -7,6 +7,7 @@
 namespace mptv {
 
 constexpr int kNumBins = 128;            // rate-block-count bins (K0)
+constexpr int kLongLeafBin = 33;         // rebuild: leaves of more than 32 rate blocks (> 4.3 KB) are hashed in their own launch
 constexpr int kBinScratchWords = 2 * kNumBins + 4;  // hist | cursor | K1 tile counter
 constexpr int kBinNodesPerBlock = 4096;  // nodes handled by one CTA of the binning kernels
 constexpr int kKeccakThreads = 128;      // K1 CTA size: one node per thread
@@ -122,7 +123,7 @@ cudaError_t trie_init_device();
 // K1L: digests of the level-0 hashed leaves straight from the key/value arrays (no materialised encoding)
 cudaError_t launch_keccak256_leaves(const TrieBatchDev& in, const uint4* rec, const uint32_t* node_len,
                                     const uint32_t* order, uint32_t n_nodes, uint8_t* digests, uint32_t* tile_counter,
-                                    int sm_count, cudaStream_t st);
+                                    int sm_count, cudaStream_t st, int ctas_per_sm = 0 /* 0 = full occupancy */);
 cudaError_t launch_trie_scan_input(const TrieBatchDev& in, TrieSummary* sum, cudaStream_t st);
 cudaError_t launch_trie_structure(const TrieBatchDev& in, const TrieWork& w, uint32_t max_items, cudaStream_t st);
 cudaError_t launch_trie_encode(const TrieBatchDev& in, const TrieWork& w, const uint32_t* list, uint32_t n_list,

@@ -197,6 +197,12 @@ int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
     ctx->dedup_nodes = value ? 1 : 0;
   } else if (!strcmp(name, "fast_walk")) {
     ctx->fast_walk = value ? 1 : 0;
+  } else if (!strcmp(name, "long_leaf_bin")) {
+    if (value < 1 || value > kNumBins) return MPTV_ERR_ARG;
+    ctx->long_leaf_bin = (int)value;
+  } else if (!strcmp(name, "long_leaf_ctas")) {
+    if (value < 1 || value > kKeccakMinBlocks) return MPTV_ERR_ARG;
+    ctx->long_leaf_ctas = (int)value;
   } else if (!strcmp(name, "fused_leaf_hash")) {
     ctx->fused_leaf_hash = value ? 1 : 0;
   } else return MPTV_ERR_ARG;

@@ -85,7 +85,22 @@ int rebuild_on_device(mptv_ctx* ctx, Device& d, const TrieBatchDev& in, uint8_t*
         olaunch += 3;
       }
       uint32_t* tiles = rb.bins.as<uint32_t>() + 2 * kNumBins;
-      if (fused) CK(launch_keccak256_leaves(in, w.rec, w.len, ord, nh, w.digests, tiles, d.sm_count, st));
+      if (fused && ord != list) {
+        // Long values first, on their own and with ONE warp per scheduler: a 30 KB receipt is 221 sequential
+        // permutations, and sharing a scheduler with three warps of short leaves the hardware starves such a
+        // chain until everything else has finished (measured: the longest tiles ended with the kernel,
+        // whatever their length).  Alone, a warp has the alu pipe to itself and Keccak's ILP keeps it busy.
+        uint32_t hist[kNumBins];
+        CK(cudaMemcpyAsync(hist, rb.bins.p, sizeof hist, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        uint32_t n_long = 0;
+        for (int bb = ctx->long_leaf_bin; bb < kNumBins; bb++) n_long += hist[bb];
+        if (n_long) {
+          CK(launch_keccak256_leaves(in, w.rec, w.len, ord, n_long, w.digests, tiles, d.sm_count, st, ctx->long_leaf_ctas));
+          klaunch++;
+        }
+        CK(launch_keccak256_leaves(in, w.rec, w.len, ord + n_long, nh - n_long, w.digests, tiles, d.sm_count, st));
+      } else if (fused) CK(launch_keccak256_leaves(in, w.rec, w.len, ord, nh, w.digests, tiles, d.sm_count, st));
       else CK(launch_keccak256_nodes(rb.arena.as<uint8_t>(), 0, w.off, w.len, ord, nh, w.digests, nullptr, tiles, d.sm_count, st));
       klaunch++;
     }
