@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "keccak_f1600.cuh"
 #include "kernels.h"
 #include "trie_rec.cuh"
@@ -62,10 +64,17 @@ __global__ void __launch_bounds__(256) k_bin_hist(const uint32_t* __restrict__ n
 }
 
 // bins laid out in DESCENDING block count so the long nodes start first (tail balance)
-__global__ void k_bin_scan(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor) {
+// cursor[kNumBins + 1] (the word after K1's tile counter) receives the number of nodes in bins >= long_bin:
+// order[0 .. split) are the "long" nodes that K1 / K1L hash in a launch of their own
+__global__ void k_bin_scan(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, int long_bin) {
   if (threadIdx.x == 0) {
-    uint32_t acc = 0;
-    for (int b = kNumBins - 1; b >= 0; b--) { cursor[b] = acc; acc += hist[b]; }
+    uint32_t acc = 0, split = 0;
+    for (int b = kNumBins - 1; b >= 0; b--) {
+      cursor[b] = acc;
+      acc += hist[b];
+      if (b == long_bin) split = acc;
+    }
+    cursor[kNumBins + 1] = split;
   }
 }
 
@@ -221,8 +230,8 @@ __device__ __forceinline__ void classify_block(uint32_t p, uint32_t k, uint32_t 
 __global__ void __launch_bounds__(kKeccakThreads, kKeccakMinBlocks)
 k_keccak256_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base, const uint64_t* __restrict__ node_off,
                   const uint32_t* __restrict__ node_len, const uint32_t* __restrict__ order,
-                  uint64_t n_nodes, uint8_t* __restrict__ digests, uint32_t* __restrict__ meta_out,
-                  uint32_t* __restrict__ tile_counter) {
+                  uint64_t n_nodes_all, uint8_t* __restrict__ digests, uint32_t* __restrict__ meta_out,
+                  uint32_t* __restrict__ tile_counter, const uint32_t* __restrict__ split, int part) {
   extern __shared__ __align__(128) uint8_t smem[];  // [stage][thread] slots
   __shared__ uint32_t s_tile;
   const int tid = threadIdx.x;
@@ -233,6 +242,13 @@ k_keccak256_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base, co
   // count this is longest-processing-time-first scheduling, so the CTAs finish together (a static
   // round-robin leaves the CTA that draws the longest tile of every round far behind on long-tailed
   // inputs such as receipt tries).
+  // split != NULL: this launch hashes one side of order[] -- part 0 the long nodes [0, *split), part 1 the rest.
+  // A long sequential chain (a 30 KB receipt leaf is 221 permutations) that shares a scheduler with warps of
+  // short nodes is starved until everything else has drained, so the long side runs first, on its own, with one
+  // warp per scheduler (Keccak's instruction-level parallelism keeps the alu pipe busy from a single warp).
+  const uint64_t n_long = split ? (uint64_t)*split : 0;
+  const uint64_t first = (split && part == 1) ? n_long : 0;
+  const uint64_t n_nodes = split ? (part == 0 ? n_long : n_nodes_all - n_long) : n_nodes_all;
   const uint64_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
   for (uint64_t tile = blockIdx.x;; tile += gridDim.x) {
     if (tile_counter) {
@@ -242,8 +258,8 @@ k_keccak256_nodes(const uint8_t* __restrict__ node_bytes, uint64_t byte_base, co
       tile = s_tile;
     }
     if (tile >= n_tiles) break;
-    const uint64_t slot_idx = tile * kKeccakThreads + tid;
-    const bool have = slot_idx < n_nodes;
+    const uint64_t slot_idx = first + tile * kKeccakThreads + tid;
+    const bool have = slot_idx < first + n_nodes;
     uint32_t node = 0, len = 0, nb = 0;
     const uint8_t* src = node_bytes;
     if (have) {
@@ -357,14 +373,17 @@ __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
 
 __global__ void __launch_bounds__(kKeccakThreads, kKeccakMinBlocks)
 k_keccak256_leaves(const TrieBatchDev in, const uint4* __restrict__ rec, const uint32_t* __restrict__ node_len,
-                   const uint32_t* __restrict__ order, uint32_t n_nodes, uint8_t* __restrict__ digests,
-                   uint32_t* __restrict__ tile_counter) {
+                   const uint32_t* __restrict__ order, uint32_t n_nodes_all, uint8_t* __restrict__ digests,
+                   uint32_t* __restrict__ tile_counter, const uint32_t* __restrict__ split, int part) {
   extern __shared__ __align__(128) uint8_t smem[];  // [stage][thread] slots
   __shared__ uint32_t s_tile;
   const int tid = threadIdx.x;
   const uint32_t slot0 = smem_u32(smem + tid * kLeafSlotBytes);
   constexpr uint32_t kStageStride = kKeccakThreads * kLeafSlotBytes;
 
+  const uint32_t n_long = split ? *split : 0u;  // long / short sides of order[]: see k_keccak256_nodes
+  const uint32_t first = (split && part == 1) ? n_long : 0u;
+  const uint32_t n_nodes = split ? (part == 0 ? n_long : n_nodes_all - n_long) : n_nodes_all;
   const uint32_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
   for (uint32_t tile = blockIdx.x;; tile += gridDim.x) {  // dynamic tiles: see k_keccak256_nodes
     if (tile_counter) {
@@ -374,8 +393,8 @@ k_keccak256_leaves(const TrieBatchDev in, const uint4* __restrict__ rec, const u
       tile = s_tile;
     }
     if (tile >= n_tiles) break;
-    const uint32_t slot_idx = tile * kKeccakThreads + tid;
-    const bool have = slot_idx < n_nodes;
+    const uint32_t slot_idx = first + tile * kKeccakThreads + tid;
+    const bool have = slot_idx < first + n_nodes;
     uint32_t node = 0, len = 0, nb = 0, vl = 0, P = 0;
     const uint8_t* val = in.value_bytes;
     uint4 r = make_uint4(0, 0, 0, 0);
@@ -474,25 +493,30 @@ cudaError_t kernels_init_device() {
                               kStages * kKeccakThreads * kLeafSlotBytes);
 }
 
+// split (device word written by launch_bin_nodes, or NULL): two launches, the long nodes first with
+// long_ctas CTAs per SM, then the rest at full occupancy
 cudaError_t launch_keccak256_leaves(const TrieBatchDev& in, const uint4* rec, const uint32_t* node_len,
                                     const uint32_t* order, uint32_t n_nodes, uint8_t* digests, uint32_t* tile_counter,
-                                    int sm_count, cudaStream_t st, int ctas_per_sm) {
+                                    int sm_count, cudaStream_t st, const uint32_t* split, int long_ctas) {
   if (n_nodes == 0) return cudaSuccess;
-  if (tile_counter) {
-    cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(uint32_t), st);
-    if (e != cudaSuccess) return e;
-  }
   const size_t smem = (size_t)kStages * kKeccakThreads * kLeafSlotBytes;
   uint32_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
-  uint32_t grid = (uint32_t)sm_count * (ctas_per_sm > 0 && ctas_per_sm < kKeccakMinBlocks ? ctas_per_sm : kKeccakMinBlocks);
+  uint32_t grid = (uint32_t)sm_count * kKeccakMinBlocks;
   if (grid > n_tiles) grid = n_tiles;
-  k_keccak256_leaves<<<grid, kKeccakThreads, smem, st>>>(in, rec, node_len, order, n_nodes, digests, tile_counter);
+  for (int part = split ? 0 : 1; part < 2; part++) {
+    if (tile_counter) {
+      cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(uint32_t), st);
+      if (e != cudaSuccess) return e;
+    }
+    const uint32_t g = (split && part == 0) ? std::min<uint32_t>(grid, (uint32_t)sm_count * (uint32_t)long_ctas) : grid;
+    k_keccak256_leaves<<<g, kKeccakThreads, smem, st>>>(in, rec, node_len, order, n_nodes, digests, tile_counter, split, part);
+  }
   return cudaGetLastError();
 }
 
 cudaError_t launch_bin_nodes(const uint32_t* node_len, const uint32_t* ids, uint64_t n_nodes,
-                             uint32_t* hist_cursor /*2*kNumBins*/, uint32_t* order, cudaStream_t st,
-                             const uint32_t* keep, unsigned long long* totals) {
+                             uint32_t* hist_cursor /*kBinScratchWords*/, uint32_t* order, cudaStream_t st,
+                             const uint32_t* keep, unsigned long long* totals, int long_bin) {
   if (n_nodes == 0) return cudaSuccess;
   uint32_t* hist = hist_cursor;
   uint32_t* cursor = hist_cursor + kNumBins;
@@ -504,7 +528,7 @@ cudaError_t launch_bin_nodes(const uint32_t* node_len, const uint32_t* ids, uint
     if (e != cudaSuccess) return e;
   }
   k_bin_hist<<<blocks, 256, 0, st>>>(node_len, ids, n_nodes, hist, keep, totals);
-  k_bin_scan<<<1, 32, 0, st>>>(hist, cursor);
+  k_bin_scan<<<1, 32, 0, st>>>(hist, cursor, long_bin);
   k_bin_scatter<<<blocks, 256, 0, st>>>(node_len, ids, n_nodes, cursor, order, keep);
   return cudaGetLastError();
 }
@@ -512,18 +536,21 @@ cudaError_t launch_bin_nodes(const uint32_t* node_len, const uint32_t* ids, uint
 cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
                                    const uint32_t* node_len, const uint32_t* order, uint64_t n_nodes,
                                    uint8_t* digests, uint32_t* meta, uint32_t* tile_counter, int sm_count,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, const uint32_t* split, int long_ctas) {
   if (n_nodes == 0) return cudaSuccess;
-  if (tile_counter) {
-    cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(uint32_t), st);
-    if (e != cudaSuccess) return e;
-  }
   size_t smem = keccak_smem_bytes();
   uint64_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
   uint64_t grid = (uint64_t)sm_count * kKeccakMinBlocks;  // persistent: one wave of resident CTAs
   if (grid > n_tiles) grid = n_tiles;
-  k_keccak256_nodes<<<(unsigned)grid, kKeccakThreads, smem, st>>>(node_bytes, byte_base, node_off, node_len, order,
-                                                                n_nodes, digests, meta, tile_counter);
+  for (int part = split ? 0 : 1; part < 2; part++) {
+    if (tile_counter) {
+      cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(uint32_t), st);
+      if (e != cudaSuccess) return e;
+    }
+    const uint64_t g = (split && part == 0) ? std::min<uint64_t>(grid, (uint64_t)sm_count * long_ctas) : grid;
+    k_keccak256_nodes<<<(unsigned)g, kKeccakThreads, smem, st>>>(node_bytes, byte_base, node_off, node_len, order, n_nodes,
+                                                                 digests, meta, tile_counter, split, part);
+  }
   return cudaGetLastError();
 }
 

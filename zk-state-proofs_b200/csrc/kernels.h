@@ -7,7 +7,7 @@
 namespace mptv {
 
 constexpr int kNumBins = 128;            // rate-block-count bins (K0)
-constexpr int kLongLeafBin = 33;         // rebuild: leaves of more than 32 rate blocks (> 4.3 KB) are hashed in their own launch
+constexpr int kLongLeafBin = 33;         // nodes of more than 32 rate blocks (> 4.3 KB) are hashed in a launch of their own
 constexpr int kBinScratchWords = 2 * kNumBins + 4;  // hist | cursor | K1 tile counter
 constexpr int kBinNodesPerBlock = 4096;  // nodes handled by one CTA of the binning kernels
 constexpr int kKeccakThreads = 128;      // K1 CTA size: one node per thread
@@ -67,13 +67,15 @@ cudaError_t kernels_init_device();
 // (device) receive their count and Keccak-f count.
 cudaError_t launch_bin_nodes(const uint32_t* node_len, const uint32_t* ids, uint64_t n_nodes, uint32_t* scratch,
                              uint32_t* order, cudaStream_t st, const uint32_t* keep = nullptr,
-                             unsigned long long* totals = nullptr);
+                             unsigned long long* totals = nullptr, int long_bin = kLongLeafBin);
+// the device word (inside launch_bin_nodes' scratch) that holds the number of nodes in bins >= long_bin
+inline const uint32_t* bin_split_word(const uint32_t* scratch) { return scratch + 2 * kNumBins + 1; }
 // K1: digests[32*i] = keccak256(node i).  order may be NULL (identity).  meta may be NULL; when
 // given, meta[i] receives the K2a record of plain branches / plain leaves and kMetaSlow otherwise.
 cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
                                    const uint32_t* node_len, const uint32_t* order, uint64_t n_nodes,
                                    uint8_t* digests, uint32_t* meta, uint32_t* tile_counter /* 1 u32 of scratch or NULL */,
-                                   int sm_count, cudaStream_t st);
+                                   int sm_count, cudaStream_t st, const uint32_t* split = nullptr, int long_ctas = 1);
 
 // K2a: meta[i] = eager-decode record of node i.  only_slow: leave records != kMetaSlow untouched
 cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
@@ -123,7 +125,7 @@ cudaError_t trie_init_device();
 // K1L: digests of the level-0 hashed leaves straight from the key/value arrays (no materialised encoding)
 cudaError_t launch_keccak256_leaves(const TrieBatchDev& in, const uint4* rec, const uint32_t* node_len,
                                     const uint32_t* order, uint32_t n_nodes, uint8_t* digests, uint32_t* tile_counter,
-                                    int sm_count, cudaStream_t st, int ctas_per_sm = 0 /* 0 = full occupancy */);
+                                    int sm_count, cudaStream_t st, const uint32_t* split = nullptr, int long_ctas = 1);
 cudaError_t launch_trie_scan_input(const TrieBatchDev& in, TrieSummary* sum, cudaStream_t st);
 cudaError_t launch_trie_structure(const TrieBatchDev& in, const TrieWork& w, uint32_t max_items, cudaStream_t st);
 cudaError_t launch_trie_encode(const TrieBatchDev& in, const TrieWork& w, const uint32_t* list, uint32_t n_list,

@@ -62,7 +62,8 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
     CK(launch_dedup_find(b.node_bytes, b.byte_base, b.node_off, b.node_len, (uint32_t)b.n_nodes, keys, vals, tsz, slot_of,
                          dup_of, st));
     // K0 bins only the representatives and counts them (per-CTA aggregated, no hot atomics)
-    CK(launch_bin_nodes(b.node_len, nullptr, b.n_nodes, bins.as<uint32_t>(), order.as<uint32_t>(), st, dup_of, totals));
+    CK(launch_bin_nodes(b.node_len, nullptr, b.n_nodes, bins.as<uint32_t>(), order.as<uint32_t>(), st, dup_of, totals,
+                        ctx->long_leaf_bin));
     unsigned long long hc[2] = {0, 0};
     CK(cudaMemcpyAsync(hc, totals, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));  // the number of unique nodes sizes the K1 launch
@@ -70,13 +71,16 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
     ord = order.as<uint32_t>();
     d.last_unique_nodes = hc[0]; d.last_unique_perm = hc[1];
   } else if (binned) {
-    CK(launch_bin_nodes(b.node_len, nullptr, b.n_nodes, bins.as<uint32_t>(), order.as<uint32_t>(), st));
+    CK(launch_bin_nodes(b.node_len, nullptr, b.n_nodes, bins.as<uint32_t>(), order.as<uint32_t>(), st, nullptr, nullptr,
+                        ctx->long_leaf_bin));
     ord = order.as<uint32_t>();
   }
+  // binned: nodes of more than 32 rate blocks (tx / receipt leaves of several KB) are hashed first, on their own
+  const uint32_t* split = (binned || dd) ? bin_split_word(bins.as<uint32_t>()) : nullptr;
   if (timed) CK(cudaEventRecord(d.ev[1], st));
   CK(launch_keccak256_nodes(b.node_bytes, b.byte_base, b.node_off, b.node_len, ord, n_hash,
                             digests.as<uint8_t>(), ctx->fused_classify ? meta.as<uint32_t>() : nullptr,
-                            one_wave ? nullptr : bins.as<uint32_t>() + 2 * kNumBins, d.sm_count, st));
+                            one_wave ? nullptr : bins.as<uint32_t>() + 2 * kNumBins, d.sm_count, st, split, ctx->long_leaf_ctas));
   if (dd) CK(launch_dedup_scatter((uint32_t)b.n_nodes, dup_of, digests.as<uint8_t>(),
                                   ctx->fused_classify ? meta.as<uint32_t>() : nullptr, st));
   if (timed) CK(cudaEventRecord(d.ev[2], st));
@@ -97,7 +101,7 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
     d.last_stream = st;
     d.have_timing = true;
     d.last_nodes = b.n_nodes;
-    d.last_keccak_launches = b.n_nodes ? 1 : 0;
+    d.last_keccak_launches = b.n_nodes ? (split ? 2 : 1) : 0;
     d.last_other_launches = other;
   }
   return MPTV_OK;

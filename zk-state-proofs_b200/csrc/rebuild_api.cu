@@ -80,29 +80,18 @@ int rebuild_on_device(mptv_ctx* ctx, Device& d, const TrieBatchDev& in, uint8_t*
     if (nh) {
       const uint32_t* ord = list;
       if (ctx->binning && nh >= 4096) {  // leaf levels: converge the warps on equal rate-block counts
-        CK(launch_bin_nodes(w.len, list, nh, rb.bins.as<uint32_t>(), rb.order.as<uint32_t>(), st));
+        CK(launch_bin_nodes(w.len, list, nh, rb.bins.as<uint32_t>(), rb.order.as<uint32_t>(), st, nullptr, nullptr,
+                            ctx->long_leaf_bin));
         ord = rb.order.as<uint32_t>();
         olaunch += 3;
       }
       uint32_t* tiles = rb.bins.as<uint32_t>() + 2 * kNumBins;
-      if (fused && ord != list) {
-        // Long values first, on their own and with ONE warp per scheduler: a 30 KB receipt is 221 sequential
-        // permutations, and sharing a scheduler with three warps of short leaves the hardware starves such a
-        // chain until everything else has finished (measured: the longest tiles ended with the kernel,
-        // whatever their length).  Alone, a warp has the alu pipe to itself and Keccak's ILP keeps it busy.
-        uint32_t hist[kNumBins];
-        CK(cudaMemcpyAsync(hist, rb.bins.p, sizeof hist, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        uint32_t n_long = 0;
-        for (int bb = ctx->long_leaf_bin; bb < kNumBins; bb++) n_long += hist[bb];
-        if (n_long) {
-          CK(launch_keccak256_leaves(in, w.rec, w.len, ord, n_long, w.digests, tiles, d.sm_count, st, ctx->long_leaf_ctas));
-          klaunch++;
-        }
-        CK(launch_keccak256_leaves(in, w.rec, w.len, ord + n_long, nh - n_long, w.digests, tiles, d.sm_count, st));
-      } else if (fused) CK(launch_keccak256_leaves(in, w.rec, w.len, ord, nh, w.digests, tiles, d.sm_count, st));
-      else CK(launch_keccak256_nodes(rb.arena.as<uint8_t>(), 0, w.off, w.len, ord, nh, w.digests, nullptr, tiles, d.sm_count, st));
-      klaunch++;
+      // binned levels: the long nodes (> 32 rate blocks) are hashed first, in a launch of their own
+      const uint32_t* split = ord != list ? bin_split_word(rb.bins.as<uint32_t>()) : nullptr;
+      if (fused) CK(launch_keccak256_leaves(in, w.rec, w.len, ord, nh, w.digests, tiles, d.sm_count, st, split, ctx->long_leaf_ctas));
+      else CK(launch_keccak256_nodes(rb.arena.as<uint8_t>(), 0, w.off, w.len, ord, nh, w.digests, nullptr, tiles, d.sm_count, st,
+                                     split, ctx->long_leaf_ctas));
+      klaunch += split ? 2 : 1;
     }
     CK(cudaEventRecord(rb.lvl_ev[3 * h + 2], st));
     start += nh + ni;
