@@ -198,3 +198,24 @@ def test_adversarial_shapes_on_gpu(verifier, oracle, leaf_mode):
         assert st[q] == o[0]
         if o[0] == 0:
             assert b.value(int(voff[q]), int(vlen[q])) == o[1]
+
+
+def test_closed_loop_every_receipt_proves_and_verifies(verifier, leaf_mode):
+    """rebuild 60 receipt tries, extract the inclusion proof of EVERY receipt, verify all of them: every verdict
+    is OK and every returned value is the inserted receipt (long leaves: up to 30 KB = 221 rate blocks, so the
+    long-node launches of K1 and K1L are exercised)"""
+    import zk_state_proofs_b200 as z
+    from workload import gen
+    kv = gen.block_tries(60, 300, "receipt", seed=8)
+    keys = [z.rlp_index(i) for i in range(300)]
+    targets = [(t, keys[i]) for t in range(60) for i in range(300)]
+    roots, b = verifier.trie_proofs(kv, targets)
+    st, voff, vlen = verifier.verify_batch(b)
+    assert (st == 0).all() and (vlen == kv.value_len).all()
+    rng = np.random.default_rng(1)
+    for q in rng.choice(len(targets), 400, replace=False):
+        o, n = int(kv.value_off[q]), int(kv.value_len[q])
+        assert b.value(int(voff[q]), int(vlen[q])) == kv.value_bytes[o:o + n].tobytes()
+    # and an absent index proves absent in every trie
+    roots2, b2 = verifier.trie_proofs(kv, [(t, z.rlp_index(300)) for t in range(60)])
+    assert (roots2 == roots).all() and (verifier.verify_batch(b2)[0] == 4).all()
