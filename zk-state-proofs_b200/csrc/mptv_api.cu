@@ -248,12 +248,14 @@ int mptv_keccak256_batch_device(mptv_ctx* ctx, int dev_index, const uint8_t* nod
   CK(cudaEventRecord(d.ev[0], st));
   const uint32_t* ord = nullptr;
   if (ctx->binning) {
-    CK(launch_bin_nodes(node_len, nullptr, n_nodes, d.bins.as<uint32_t>(), d.order.as<uint32_t>(), st));
+    CK(launch_bin_nodes(node_len, nullptr, n_nodes, d.bins.as<uint32_t>(), d.order.as<uint32_t>(), st, nullptr, nullptr,
+                        ctx->long_leaf_bin));
     ord = d.order.as<uint32_t>();
   }
   CK(cudaEventRecord(d.ev[1], st));
   CK(launch_keccak256_nodes(node_bytes, 0, node_off, node_len, ord, n_nodes, digests32, nullptr,
-                            d.bins.as<uint32_t>() + 2 * kNumBins, d.sm_count, st));
+                            d.bins.as<uint32_t>() + 2 * kNumBins, d.sm_count, st,
+                            ord ? bin_split_word(d.bins.as<uint32_t>()) : nullptr, ctx->long_leaf_ctas));
   CK(cudaEventRecord(d.ev[2], st));
   CK(cudaEventRecord(d.ev[3], st));
   CK(cudaEventRecord(d.ev[4], st));
@@ -523,11 +525,13 @@ int mptv_keccak256_batch(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node
   CK(cudaMemcpyAsync(s.node_len.p, node_len, 4 * n_nodes, cudaMemcpyHostToDevice, st));
   const uint32_t* ord = nullptr;
   if (ctx->binning) {
-    CK(launch_bin_nodes(s.node_len.as<uint32_t>(), nullptr, n_nodes, s.bins.as<uint32_t>(), s.order.as<uint32_t>(), st));
+    CK(launch_bin_nodes(s.node_len.as<uint32_t>(), nullptr, n_nodes, s.bins.as<uint32_t>(), s.order.as<uint32_t>(), st, nullptr,
+                        nullptr, ctx->long_leaf_bin));
     ord = s.order.as<uint32_t>();
   }
   CK(launch_keccak256_nodes(s.node_bytes.as<uint8_t>(), 0, s.node_off.as<uint64_t>(), s.node_len.as<uint32_t>(), ord,
-                            n_nodes, s.digests.as<uint8_t>(), nullptr, s.bins.as<uint32_t>() + 2 * kNumBins, d.sm_count, st));
+                            n_nodes, s.digests.as<uint8_t>(), nullptr, s.bins.as<uint32_t>() + 2 * kNumBins, d.sm_count, st,
+                            ord ? bin_split_word(s.bins.as<uint32_t>()) : nullptr, ctx->long_leaf_ctas));
   CK(cudaMemcpyAsync(digests32, s.digests.p, 32 * n_nodes, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return MPTV_OK;
