@@ -544,6 +544,16 @@ __device__ __forceinline__ bool eq32_unaligned(const uint8_t* q, const uint8_t* 
   return diff == 0;
 }
 
+// does any of the proof's n digests equal the 32 bytes at q?  (first word first: a miss costs one load per node)
+__device__ bool digest_present(const uint8_t* q, const uint8_t* dg, uint32_t n) {
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(q) & ~(uintptr_t)3);
+  const uint32_t sh = 8u * (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3);
+  const uint32_t w0 = __funnelshift_r(__ldg(wp), sh ? __ldg(wp + 1) : 0u, sh);
+  for (uint32_t t = 0; t < n; t++)
+    if (__ldg(reinterpret_cast<const uint32_t*>(dg + 32ull * t)) == w0 && eq32_unaligned(q, dg + 32ull * t)) return true;
+  return false;
+}
+
 // true: decided (outputs written); false: defer to K2b
 __device__ bool fast_one(const DeviceBatch& b, uint64_t p, bool dependent, const uint8_t* __restrict__ digests,
                          const uint32_t* __restrict__ meta, uint8_t* status_out, uint64_t* value_off_out,
@@ -565,7 +575,13 @@ __device__ bool fast_one(const DeviceBatch& b, uint64_t p, bool dependent, const
     }
     rp = node_bytes + value_off_out[d] + so;
   }
-  if (!eq32_unaligned(rp, digests + 32ull * a)) return false;  // lib.rs:14: node 0 must be the root
+  if (!eq32_unaligned(rp, digests + 32ull * a)) {
+    // node 0 is not the root.  If NO supplied node hashes to the root the verdict is InvalidStateRoot whatever
+    // the order (R2: tampered / dropped root node, wrong root); if some other node does, K2b sorts it out.
+    if (digest_present(rp, digests + 32ull * a, n)) return false;
+    status_out[p] = (uint8_t)kStInvalidStateRoot; value_off_out[p] = 0; value_len_out[p] = 0;
+    return true;
+  }
   uint32_t idx = 0;
   for (uint32_t i = 0; i < n; i++) {
     const uint32_t m = meta[a + i];
@@ -580,9 +596,15 @@ __device__ bool fast_one(const DeviceBatch& b, uint64_t p, bool dependent, const
         status_out[p] = (uint8_t)kStKeyNotFound; value_off_out[p] = 0; value_len_out[p] = 0;
         return true;
       }
-      if (i + 1 >= n) return false;
       const uint8_t* link = node_bytes + off + meta_hdr(m) + nib + 32u * __popc(mk & ((1u << nib) - 1u)) + 1;
-      if (!eq32_unaligned(link, digests + 32ull * (a + i + 1))) return false;
+      if (i + 1 >= n || !eq32_unaligned(link, digests + 32ull * (a + i + 1))) {
+        // the next node is not the child.  If NO supplied node has that digest the reference's lookup misses
+        // (R8: truncated proof, tampered child, wrong key into an unproven subtree) -> InvalidProof; if some
+        // node does (shuffled or padded proofs) the full rule set of K2b decides.
+        if (digest_present(link, digests + 32ull * a, n)) return false;
+        status_out[p] = (uint8_t)kStInvalidProof; value_off_out[p] = 0; value_len_out[p] = 0;
+        return true;
+      }
       idx++;
     } else if (meta_kind(m) == kKindLeaf) {
       const uint8_t* nb = node_bytes + off;
