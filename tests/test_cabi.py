@@ -78,3 +78,17 @@ def test_wire_forms_of_both_input_types_roundtrip():
     assert w[:4] == (2).to_bytes(4, "little") and w[4:8] == (3).to_bytes(4, "little") and w[-32:] == bytes(range(32))
     with pytest.raises(ValueError):
         z.StorageProofInput.from_borsh(w + b"\x00")
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """the boundary is a C ABI: include/mptv.h compiles as C99 (-pedantic) and a C program links libmptv.so"""
+    import subprocess
+    import zk_state_proofs_b200 as z
+    z.load_library()
+    exe = str(tmp_path / "cabi_smoke")
+    libdir = os.path.dirname(z.lib_path())
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "cabi_smoke.c"), "-o", exe, "-L", libdir, "-l:libmptv.so",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "rlp(300) has 3 bytes" in out.stdout
