@@ -54,3 +54,34 @@ def test_flatten_borsh_rejects_what_borsh_rejects():
     for bad in [good[:-1], good + b"\x00", good[:3], b"\xff\xff\xff\xff" + good[4:], b""]:
         with pytest.raises(ValueError):
             z.flatten_borsh([good, bad])
+
+
+def test_property_borsh_roundtrip_and_flatten_agree():
+    """hypothesis: arbitrary MerkleProofInputs survive borsh, and the C++ flattener lays them out exactly like the
+    plain Python flatten() (offsets, lengths, 16-byte alignment, roots, keys, bad-root flags)"""
+    from hypothesis import given, settings, strategies as st
+    import zk_state_proofs_b200 as z
+
+    node = st.binary(min_size=0, max_size=600)
+    inp = st.builds(z.MerkleProofInput, st.lists(node, min_size=0, max_size=9),
+                    st.one_of(st.binary(min_size=32, max_size=32), st.binary(min_size=0, max_size=40)),
+                    st.binary(min_size=0, max_size=70))
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(inp, min_size=0, max_size=12))
+    def check(inputs):
+        blobs = [i.to_borsh() for i in inputs]
+        assert [z.MerkleProofInput.from_borsh(b) for b in blobs] == inputs
+        got, want = z.flatten_borsh(blobs, threads=2), z.flatten(inputs)
+        assert got.n_proofs == want.n_proofs and got.n_nodes == want.n_nodes
+        for name in ["node_off", "node_len", "proof_first", "roots", "key_off"]:
+            assert (getattr(got, name) == getattr(want, name)).all()
+        for o, n in zip(want.node_off.tolist(), want.node_len.tolist()):
+            assert (got.node_bytes[o:o + n] == want.node_bytes[o:o + n]).all()
+        k = int(want.key_off[-1])
+        assert (got.key_bytes[:k] == want.key_bytes[:k]).all()
+        gb = np.zeros(len(inputs), bool) if got.bad_root_len is None else got.bad_root_len
+        wb = np.zeros(len(inputs), bool) if want.bad_root_len is None else want.bad_root_len
+        assert (gb == wb).all()
+
+    check()
