@@ -345,7 +345,52 @@ def nested_cases(rng: random.Random, keccak, n: int):
     return out
 
 
-def corpus(seed: int, keccak, n_tries: int, n_mut: int, n_weird: int, n_nested: int = 0):
+def resealed_cases(rng: random.Random, keccak, base, n: int):
+    """Corrupt ONE node of a valid root-first proof at the byte level (bit flips, inserted / deleted / overwritten
+    bytes, truncation) and then RE-SEAL the chain: every ancestor gets the corrupted child's new hash and the
+    root hash is recomputed, so all hash links hold and the reference really decodes and walks the corrupted
+    node (a plain flip only ever yields a dangling link)."""
+    out = []
+    chains = [c for c in base if len(c["proof"]) >= 1 and c["tag"].endswith(("/incl", "/absent"))]
+    while len(out) < n and chains:
+        c = rng.choice(chains)
+        proof = [bytes(p) for p in c["proof"]]
+        i = rng.randrange(len(proof))
+        b = bytearray(proof[i])
+        for _ in range(rng.choice([1, 1, 1, 2, 3])):
+            op = rng.choice(["flip", "flip", "set", "ins", "del", "trunc", "hdr"])
+            if not b:
+                break
+            j = rng.randrange(len(b))
+            if op == "flip": b[j] ^= 1 << rng.randrange(8)
+            elif op == "set": b[j] = rng.choice([0x00, 0x7f, 0x80, 0x81, 0xa0, 0xb7, 0xb8, 0xc0, 0xc1, 0xf7, 0xf8, 0xff])
+            elif op == "ins": b.insert(j, rng.randrange(256))
+            elif op == "del": del b[j]
+            elif op == "trunc": del b[rng.randrange(len(b)):]
+            else: b[rng.randrange(min(4, len(b)))] = rng.randrange(256)   # aim at the list / first item header
+        old = proof[i]
+        proof[i] = bytes(b)
+        ok = True
+        for j in range(i - 1, -1, -1):   # propagate the new hash up the chain
+            oh, nh = keccak(old), keccak(proof[j + 1])
+            if len(old) < 32 or oh not in proof[j]:
+                ok = False   # the child was inline / not referenced by hash: skip this one
+                break
+            old = proof[j]
+            proof[j] = proof[j].replace(oh, nh, 1)
+        if not ok:
+            continue
+        root = keccak(proof[0])   # the re-sealed root (the chain is root first)
+        key = c["key"]
+        if rng.random() < 0.1:
+            key = key[:-1] if rng.random() < 0.5 else key + bytes([rng.randrange(256)])
+        if rng.random() < 0.1:
+            rng.shuffle(proof)
+        out.append(dict(root=root, proof=proof, key=key, tag=c["tag"] + f"+reseal{i}"))
+    return out
+
+
+def corpus(seed: int, keccak, n_tries: int, n_mut: int, n_weird: int, n_nested: int = 0, n_reseal: int = 0):
     rng = random.Random(seed)
     base = valid_cases(rng, keccak, n_tries)
     out = list(base)
@@ -354,4 +399,6 @@ def corpus(seed: int, keccak, n_tries: int, n_mut: int, n_weird: int, n_nested: 
     out += weird_cases(rng, keccak, n_weird)
     if n_nested:
         out += nested_cases(rng, keccak, n_nested)
+    if n_reseal:
+        out += resealed_cases(rng, keccak, base, n_reseal)
     return out

@@ -102,6 +102,11 @@ def main():
     import random as _random
     from .fuzzgen import nested_cases as fuzz_nested
     cases += [dict(c, tag="fuzz-" + c["tag"]) for c in fuzz_nested(_random.Random(99), o.keccak256, 600)]
+    # byte-level corruption of one node with the hash chain re-sealed above it (the family that found the
+    # "bare 32-byte string with trailing bytes panics" rule)
+    from .fuzzgen import resealed_cases, valid_cases
+    rr = _random.Random(123)
+    cases += resealed_cases(rr, o.keccak256, valid_cases(rr, o.keccak256, 30), 300)
 
     def one(c):
         return ref.run(c["root"], c["proof"], c["key"])

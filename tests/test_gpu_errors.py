@@ -82,11 +82,11 @@ def test_separate_contexts_from_separate_threads(golden):
 
 
 def test_large_fuzz_corpus_matches_oracle(verifier, oracle):
-    """28 k generated + mutated + malformed + deeply nested cases (oracle/fuzzgen.py), GPU verdict and value ==
-    C restatement (which agrees with the reference ELF on 400 k such cases, oracle/fuzz_vs_ref.py)"""
+    """40 k generated + mutated + malformed + deeply nested + corrupted-and-re-sealed cases (oracle/fuzzgen.py), GPU
+    verdict and value == C restatement (which agrees with the reference ELF on 1.3 M such cases, oracle/fuzz_vs_ref.py)"""
     import zk_state_proofs_b200 as z
     from oracle.fuzzgen import corpus
-    cases = corpus(777, oracle.keccak256, 150, 8000, 12000, 8000)
+    cases = corpus(777, oracle.keccak256, 150, 8000, 12000, 8000, 12000)
     b = z.flatten([z.MerkleProofInput(c["proof"], c["root"], c["key"]) for c in cases])
     st, voff, vlen = verifier.verify_batch(b)
     d = dict(node_bytes=b.node_bytes, node_off=b.node_off, node_len=b.node_len, proof_first=b.proof_first,

@@ -91,7 +91,12 @@ __device__ uint32_t parse_node(const uint8_t* p, uint32_t n) {
   uint32_t canon = (h.hdr_len + h.payload_len == n) ? 1u : 0u;  // trailing bytes (R18 vs R4)
   if (!h.is_list) {
     if (h.payload_len == 0) return make_meta(kKindEmpty, kDecOk, canon, 0, h.hdr_len, 0);
-    if (h.payload_len == 32) return make_meta(kKindHash, kDecOk, 0, 0, h.hdr_len, 0);
+    if (h.payload_len == 32) {
+      // the reference converts EVERYTHING after the header to a B256 (FixedBytes::from_slice): a bare
+      // 32-byte string followed by anything is a raw panic, not a hash node with ignored trailing bytes
+      if (n != h.hdr_len + 32u) return make_meta(kKindEmpty, kDecPanic, 0, 0, 0, 0);
+      return make_meta(kKindHash, kDecOk, 0, 0, h.hdr_len, 0);
+    }
     return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);
   }
   Frame st[kMaxInlineDepth];
