@@ -219,3 +219,21 @@ def test_closed_loop_every_receipt_proves_and_verifies(verifier, leaf_mode):
     # and an absent index proves absent in every trie
     roots2, b2 = verifier.trie_proofs(kv, [(t, z.rlp_index(300)) for t in range(60)])
     assert (roots2 == roots).all() and (verifier.verify_batch(b2)[0] == 4).all()
+
+
+def test_prefix_heavy_random_tries_on_gpu(verifier, oracle, leaf_mode):
+    """2 000 random tries with prefix-sharing keys of 0..32 bytes, overwrites, deletes, values around the inline
+    boundary: GPU roots == oracle roots, and sampled proofs == oracle proofs"""
+    import zk_state_proofs_b200 as z
+    from tests.test_rebuild_oracle import make_kv, prefix_heavy_tries
+    for seed in (100, 101, 102, 103, 104):
+        tries = prefix_heavy_tries(seed, 400)
+        d = make_kv(tries)
+        want = oracle.trie_roots(d, nthreads=8)[0]
+        targets = [(t, kvs[0][0]) for t, kvs in enumerate(tries)][:150]
+        roots, b = verifier.trie_proofs(_kv(z, d), targets)
+        bad = np.nonzero((roots != want).any(axis=1))[0]
+        assert len(bad) == 0, (seed, [int(t) for t in bad[:5]])
+        got = _proofs(b)
+        for (t, k), nodes in zip(targets, got):
+            assert nodes == oracle.trie_get_proof(d, t, k)[1], (seed, t, k.hex())

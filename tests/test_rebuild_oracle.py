@@ -147,3 +147,38 @@ def test_adversarial_shapes_match_independent_builder(oracle):
         for k in list(d)[:6]:
             root, nodes = oracle.trie_get_proof(kv, t, k)
             assert nodes == T.proof(k), (t, k.hex())
+
+
+def prefix_heavy_tries(seed, n_tries):
+    """random tries whose keys share prefixes at every granularity (nibble-level forks, keys that are prefixes of
+    other keys, 0..32-byte keys), with overwrites, deletes and values around the 32-byte inline boundary"""
+    rng = random.Random(seed)
+    tries = []
+    for _ in range(n_tries):
+        n = rng.choice([1, 2, 3, 4, 8, 20, 60, 150])
+        stems = [rng.randbytes(rng.randint(0, 31)) for _ in range(rng.randint(1, 4))]
+        kvs = []
+        for _ in range(n):
+            r = rng.random()
+            stem = rng.choice(stems)
+            if r < 0.3:
+                k = stem
+            elif r < 0.7:
+                k = stem + rng.randbytes(rng.randint(1, 32 - len(stem))) if len(stem) < 32 else stem
+            elif r < 0.85 and stem:
+                b = bytearray(stem); b[-1] ^= rng.choice([0x01, 0x10, 0x0f, 0xf0]); k = bytes(b)   # fork inside the last byte
+            else:
+                k = rng.randbytes(rng.choice([0, 1, 2, 32]))
+            k = k[:32]
+            v = b"" if rng.random() < 0.08 else rng.randbytes(rng.choice([1, 1, 2, 20, 28, 29, 30, 31, 32, 33, 60, 200]))
+            kvs.append((k, v))
+        tries.append(kvs)
+    return tries
+
+
+def test_prefix_heavy_tries_match_independent_builder(oracle):
+    tries = prefix_heavy_tries(77, 300)
+    kv = make_kv(tries)
+    roots, _, _ = oracle.trie_roots(kv, nthreads=4)
+    for t, kvs in enumerate(tries):
+        assert Trie(dict(kvs), oracle.keccak256).root == roots[t].tobytes(), t
