@@ -1,4 +1,5 @@
-// keccak_kernels.cu -- K0 (rate-block binning) and K1 (batched Keccak-256 of proof nodes).
+// keccak_kernels.cu -- K0 (rate-block binning), K1 (batched Keccak-256 of proof nodes) and K1L (the trie
+// rebuild's fused leaf encode + Keccak-256, further down).
 //
 // K1 replaces crypto_ops::keccak::digest_keccak (/root/reference/crypto-ops/src/keccak.rs:6-12)
 // applied to every proof node (/root/reference/crypto-ops/src/lib.rs:10-13) for a whole batch:

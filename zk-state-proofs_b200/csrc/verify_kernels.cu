@@ -1,5 +1,6 @@
-// verify_kernels.cu -- K2a (per-node eager RLP decode / canonical-form check) and
-// K2b (group-of-lanes-per-proof nibble walk with ballot/shuffle hash-link lookup).
+// verify_kernels.cu -- K2a (per-node eager RLP decode / canonical-form check), K2f (thread-per-proof
+// check of chain-shaped proofs, the common case) and K2b (group-of-lanes-per-proof nibble walk with
+// ballot/shuffle hash-link lookup: the full rule set, run on whatever K2f defers).
 //
 // Together they replace, for a whole batch, what crypto_ops::verify_merkle_proof
 // (/root/reference/crypto-ops/src/lib.rs:8-23) does per proof after hashing:
