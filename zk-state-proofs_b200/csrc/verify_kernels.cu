@@ -592,10 +592,13 @@ __device__ bool fast_one(const DeviceBatch& b, uint64_t p, bool dependent, const
   for (uint32_t i = 0; i < n; i++) {
     const uint32_t m = meta[a + i];
     if (m == kMetaSlow || meta_dec(m) != kDecOk) return false;
-    const uint32_t nl = b.node_len[a + i];
+    const bool plain_branch = meta_kind(m) == kKindBranch && meta_fast(m);
+    // a plain branch's length follows from its record (header + 16 + 1 item bytes + 32 per hashed child):
+    // no need to touch node_len for the levels above the leaf
+    const uint32_t nl = plain_branch ? meta_hdr(m) + 17u + 32u * __popc(meta_mask(m)) : b.node_len[a + i];
     if (i == 0 ? !meta_canon(m) : nl < 32) return false;  // lib.rs:19 on the root; R9 admission otherwise
     const uint64_t off = b.node_off[a + i];
-    if (meta_kind(m) == kKindBranch && meta_fast(m)) {
+    if (plain_branch) {
       const uint32_t nib = key_nibble(key, klen, idx);
       const uint32_t mk = meta_mask(m);
       if (nib == 16 || !((mk >> nib) & 1u)) {  // R14 (no value in a plain branch) / R15
