@@ -116,6 +116,12 @@ const char* mptv_status_name(int status);
  * per-device streams).  Blocks until `out` is filled. */
 int mptv_verify_batch(mptv_ctx* ctx, const mptv_batch* in, mptv_result* out);
 
+/* The storage guest's flow in one call (storage-circuit/src/main.rs:17-27): like mptv_verify_batch, but
+ * every proof p with hash_key[p] != 0 is looked up under keccak256(key p) instead of key p -- the guest's
+ * `digest_keccak(&key)` for storage slots.  The keys are hashed on the device (one K1 launch); `in` is not
+ * modified.  hash_key == NULL behaves exactly like mptv_verify_batch. */
+int mptv_verify_batch_hashed_keys(mptv_ctx* ctx, const mptv_batch* in, const uint8_t* hash_key, mptv_result* out);
+
 /* Device-resident entry: every pointer is DEVICE memory on the context's device `dev_index`.
  * Asynchronous on `stream` (a cudaStream_t, NULL = the context's own stream for that device). */
 int mptv_verify_batch_device(mptv_ctx* ctx, int dev_index, const mptv_batch* in, mptv_result* out,

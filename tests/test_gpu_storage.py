@@ -78,3 +78,28 @@ def test_storage_proof_inputs_batched_match_guest_flow(verifier, oracle):
             n_ok += 1
             assert verifier.verify_storage_proof_input(inp) == want   # the single-input entry agrees
     assert n_ok >= 15 and n_ok < len(inputs)
+
+
+def test_hashed_keys_entry_equals_two_step_flow(verifier, oracle):
+    """mptv_verify_batch_hashed_keys (storage keys hashed on the device inside the call) == hashing them first"""
+    import numpy as np
+    import zk_state_proofs_b200 as z
+    state, accounts = _world(oracle, 9, n_accounts=25)
+    k = oracle.keccak256
+    items, rfp, flags, items_hashed = [], [], [], []
+    for addr, (slots, st) in accounts.items():
+        a = len(items)
+        items.append(z.MerkleProofInput(state.proof(k(addr)), state.root, k(addr)))
+        items_hashed.append(items[-1])
+        rfp.append(-1)
+        flags.append(0)
+        for s in list(slots)[:3] + [b"\x07" * 32]:
+            items.append(z.MerkleProofInput(st.proof(k(s)), b"\x00" * 32, s))            # raw slot key
+            items_hashed.append(z.MerkleProofInput(st.proof(k(s)), b"\x00" * 32, k(s)))  # hashed by the caller
+            rfp.append(a)
+            flags.append(1)
+    got = verifier.verify_batch_hashed_keys(z.flatten(items, rfp), np.array(flags, np.uint8))
+    want = verifier.verify_batch(z.flatten(items_hashed, rfp))
+    for x, y in zip(got, want):
+        assert (x == y).all()
+    assert (got[0] == 0).sum() > 60 and (got[0] == 4).sum() >= 20

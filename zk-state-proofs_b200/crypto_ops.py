@@ -473,6 +473,8 @@ def load_library():
     L.mptv_status_name.argtypes = [i32]
     L.mptv_verify_batch.restype = i32
     L.mptv_verify_batch.argtypes = [vp, ctypes.POINTER(_CBatch), ctypes.POINTER(_CResult)]
+    L.mptv_verify_batch_hashed_keys.restype = i32
+    L.mptv_verify_batch_hashed_keys.argtypes = [vp, ctypes.POINTER(_CBatch), vp, ctypes.POINTER(_CResult)]
     L.mptv_verify_batch_device.restype = i32
     L.mptv_verify_batch_device.argtypes = [vp, i32, ctypes.POINTER(_CBatch), ctypes.POINTER(_CResult), vp]
     L.mptv_keccak256_batch.restype = i32
@@ -569,6 +571,27 @@ class Verifier:
                      _ptr(b.root_from_proof))
         cr = _CResult(_ptr(status), _ptr(voff), _ptr(vlen))
         self._check(self.lib.mptv_verify_batch(self.ctx, ctypes.byref(cb), ctypes.byref(cr)), "mptv_verify_batch")
+        if b.bad_root_len is not None:
+            status[b.bad_root_len] = 6
+            voff[b.bad_root_len] = 0
+            vlen[b.bad_root_len] = 0
+        return status, voff, vlen
+
+    def verify_batch_hashed_keys(self, b: Batch, hash_key: np.ndarray):
+        """mptv_verify_batch_hashed_keys: proofs flagged in hash_key are looked up under keccak256(key)."""
+        n = b.n_proofs
+        status = np.zeros(n, np.uint8)
+        voff = np.zeros(n, np.uint64)
+        vlen = np.zeros(n, np.uint32)
+        if n == 0:
+            return status, voff, vlen
+        hk = np.ascontiguousarray(hash_key, np.uint8)
+        cb = _CBatch(_ptr(b.node_bytes), len(b.node_bytes), _ptr(b.node_off), _ptr(b.node_len), b.n_nodes,
+                     _ptr(b.proof_first), n, _ptr(b.roots), _ptr(b.key_bytes), _ptr(b.key_off),
+                     _ptr(b.root_from_proof))
+        cr = _CResult(_ptr(status), _ptr(voff), _ptr(vlen))
+        self._check(self.lib.mptv_verify_batch_hashed_keys(self.ctx, ctypes.byref(cb), _ptr(hk), ctypes.byref(cr)),
+                    "mptv_verify_batch_hashed_keys")
         if b.bad_root_len is not None:
             status[b.bad_root_len] = 6
             voff[b.bad_root_len] = 0

@@ -499,6 +499,46 @@ int mptv_verify_batch(mptv_ctx* ctx, const mptv_batch* in, mptv_result* out) {
   return MPTV_OK;
 }
 
+int mptv_verify_batch_hashed_keys(mptv_ctx* ctx, const mptv_batch* in, const uint8_t* hash_key, mptv_result* out) {
+  if (!hash_key) return mptv_verify_batch(ctx, in, out);
+  if (!ctx || !in || !out) return MPTV_ERR_ARG;
+  if (in->n_proofs == 0) return MPTV_OK;
+  if (!in->key_off) return MPTV_ERR_ARG;
+  const uint64_t n = in->n_proofs;
+  // 1. the flagged keys as a 16-byte aligned arena -> keccak256 on the device
+  std::vector<uint64_t> koff;
+  std::vector<uint32_t> klen;
+  std::vector<uint8_t> arena;
+  for (uint64_t p = 0; p < n; p++) {
+    if (!hash_key[p]) continue;
+    if (in->key_off[p + 1] < in->key_off[p]) return MPTV_ERR_ARG;
+    const uint32_t l = in->key_off[p + 1] - in->key_off[p];
+    koff.push_back(arena.size());
+    klen.push_back(l);
+    if (l) arena.insert(arena.end(), in->key_bytes + in->key_off[p], in->key_bytes + in->key_off[p] + l);
+    arena.resize((arena.size() + 15) & ~(size_t)15, 0);
+  }
+  arena.resize(arena.size() + 16, 0);
+  std::vector<uint8_t> dig(32 * koff.size() + 1);
+  int rc = mptv_keccak256_batch(ctx, arena.data(), arena.size(), koff.data(), klen.data(), koff.size(), dig.data());
+  if (rc != MPTV_OK) return rc;
+  // 2. the same batch with those keys replaced by their digests
+  std::vector<uint8_t> keys;
+  std::vector<uint32_t> off(n + 1, 0);
+  size_t h = 0;
+  for (uint64_t p = 0; p < n; p++) {
+    if (hash_key[p]) { keys.insert(keys.end(), dig.begin() + 32 * h, dig.begin() + 32 * h + 32); h++; }
+    else keys.insert(keys.end(), in->key_bytes + in->key_off[p], in->key_bytes + in->key_off[p + 1]);
+    if (keys.size() > 0xfffffff0ull) return MPTV_ERR_ARG;
+    off[p + 1] = (uint32_t)keys.size();
+  }
+  keys.resize(keys.size() + 16, 0);
+  mptv_batch b = *in;
+  b.key_bytes = keys.data();
+  b.key_off = off.data();
+  return mptv_verify_batch(ctx, &b, out);
+}
+
 int mptv_keccak256_batch(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node_bytes_len, const uint64_t* node_off,
                          const uint32_t* node_len, uint64_t n_nodes, uint8_t* digests32) {
   if (!ctx || (n_nodes && (!node_bytes || !node_off || !node_len || !digests32))) return MPTV_ERR_ARG;
