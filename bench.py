@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--pageable", action="store_true", help="e2e from ordinary (pageable) host memory instead of pinned")
+    ap.add_argument("--l2-fetch", type=int, default=0, help="L2 fetch granularity hint in bytes (32/64/128; 0 = leave the default)")
     ap.add_argument("--dedup", action="store_true",
                     help="SECONDARY number: hash each distinct node of the batch once (dedup_nodes option); the "
                          "headline always hashes every supplied node, as the reference does")
@@ -435,6 +436,8 @@ def main_rebuild(a):
     rank, world, local = dist_setup()
     dev = torch.device("cuda", local)
     ver = z.Verifier([local])
+    if a.l2_fetch:
+        ver.set_option("l2_fetch_granularity", a.l2_fetch)
     kv, gen_info = rebuild_kv(a, rank, pinned=True)
     value_total = int(kv.value_len.astype(np.int64).sum())
 
@@ -569,6 +572,8 @@ def main():
         ver.set_option("lanes_per_proof", a.lanes)
     if a.dedup:
         ver.set_option("dedup_nodes", 1)
+    if a.l2_fetch:
+        ver.set_option("l2_fetch_granularity", a.l2_fetch)
     b, gen_info = build_batch(a, rank, pinned=not a.pageable)
     n_proofs, n_nodes, n_perm = b.n_proofs, b.n_nodes, b.n_perm()
     node_bytes_total = int(b.node_len.astype(np.int64).sum())

@@ -152,6 +152,8 @@ int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops
  *   "fused_leaf_hash"  rebuild: K1L hashes leaves straight from the value arena (default 1)
  *   "long_leaf_bin", "long_leaf_ctas"  rebuild: leaves of at least this many rate blocks are hashed in a launch of
  *                      their own with this many 4-warp CTAs per SM (defaults 33 and 1; tuning knobs)
+ *   "l2_fetch_granularity"  32, 64 or 128: device-wide cudaLimitMaxL2FetchGranularity hint for the context's GPUs
+ *                      (left at the driver default unless set; a tuning knob)
  *   "dedup_nodes"      hash each DISTINCT node of a batch once and share the digest (default 0).
  *                      Results are identical; the executed Keccak-f count drops.  The reference hashes
  *                      every supplied node, so numbers measured with this option are a SECOND,

@@ -209,6 +209,14 @@ int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
     ctx->long_leaf_ctas = (int)value;
   } else if (!strcmp(name, "fused_leaf_hash")) {
     ctx->fused_leaf_hash = value ? 1 : 0;
+  } else if (!strcmp(name, "l2_fetch_granularity")) {
+    // device-wide hint: how many bytes an L2 miss brings in from HBM (the nodes are short, 16-byte aligned
+    // runs reached in binned order, so wider fetches mostly bring in bytes of a neighbour nobody asked for yet)
+    if (value != 32 && value != 64 && value != 128) return MPTV_ERR_ARG;
+    for (Device& d : ctx->dev) {
+      CK(cudaSetDevice(d.id));
+      CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+    }
   } else return MPTV_ERR_ARG;
   return MPTV_OK;
 }
