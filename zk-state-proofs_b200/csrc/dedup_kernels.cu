@@ -42,7 +42,7 @@ __device__ __forceinline__ uint4 masked_chunk(const uint4* a, uint32_t c, uint32
 
 }  // namespace
 
-// pass 1: a group of 8 lanes fingerprints the WHOLE content of a node (position-salted mix of every 16-byte
+// pass 1: a group of 8 lanes fingerprints the WHOLE content of a node (position-salted sum over every 16-byte
 // chunk, so near-duplicates -- a tampered copy of a node -- do not collide), then one lane claims / joins
 // the node's table slot and keeps the smallest node index per fingerprint.  The table is read before it
 // is written: the root node of a 1 M-proof batch would otherwise queue a million atomics on one address.
@@ -56,11 +56,18 @@ __global__ void __launch_bounds__(256) k_dedup_insert(const uint8_t* __restrict_
   const uint32_t gmask = 0xffu << (lane & ~7u);
   const uint32_t len = node_len[i];
   const uint4* a = reinterpret_cast<const uint4*>(node_bytes + (node_off[i] - byte_base));
+  // multilinear in the 64-bit halves with a position-dependent odd multiplier per half: a difference in any
+  // single half always changes h (odd multipliers are bijections), moved chunks change it too, and the
+  // two 64-bit multiplies per 16 bytes are half the work of mixing every half separately
   uint64_t h = 0;
+  uint64_t m1 = (0x9e3779b97f4a7c15ull + 0xd6e8feb86659fd92ull * (uint64_t)l8) | 1ull;
+  uint64_t m2 = (0xc2b2ae3d27d4eb4full + 0xa0761d6478bd642eull * (uint64_t)l8) | 1ull;
   for (uint32_t c = l8; 16 * c < len; c += 8) {
     const uint4 x = masked_chunk(a, c, len);
     const uint64_t lo = ((uint64_t)x.y << 32) | x.x, hi = ((uint64_t)x.w << 32) | x.z;
-    h ^= mix64(lo + 0x9e3779b97f4a7c15ull * (2 * c + 1)) + mix64(hi ^ (0xc2b2ae3d27d4eb4full * (2 * c + 2)));
+    h += lo * m1 + hi * m2;
+    m1 += 8ull * 0xd6e8feb86659fd92ull;  // even steps keep the multipliers odd
+    m2 += 8ull * 0xa0761d6478bd642eull;
   }
   for (int o = 4; o; o >>= 1) h ^= __shfl_xor_sync(gmask, h, o, 8);
   if (l8) return;
