@@ -54,6 +54,32 @@ def test_argument_errors_are_reported(verifier, golden):
     assert st.tolist() == [v["status"] for v in vs]
 
 
+def test_error_in_a_late_chunk_leaves_nothing_in_flight(verifier, golden):
+    """A bad node in the LAST pipeline chunk is reported after earlier chunks were already queued; the call must
+    not return while they are in flight, and a following, smaller call must not see their results."""
+    import zk_state_proofs_b200 as z
+    vs = golden["vectors"]
+    big = z.flatten([z.MerkleProofInput(v["proof_b"], v["root_b"], v["key_b"]) for v in vs])
+    verifier.set_option("chunk_bytes", 1 << 16)  # dozens of chunks over the three slots
+    try:
+        bad = z.Batch(big.node_bytes, big.node_off.copy(), big.node_len, big.proof_first, big.roots, big.key_bytes,
+                      big.key_off, None, None)
+        bad.node_off[-1] += 8
+        with pytest.raises(z.MptvError, match="16-byte"):
+            verifier.verify_batch(bad)
+        few = vs[100:107]
+        small = z.flatten([z.MerkleProofInput(v["proof_b"], v["root_b"], v["key_b"]) for v in few])
+        st, voff, vlen = verifier.verify_batch(small)
+        assert st.tolist() == [v["expect_status"] for v in few]
+        for v, s_, o, l in zip(few, st, voff, vlen):
+            if s_ == 0:
+                assert small.value(int(o), int(l)) == v["value_b"]
+        st, _, _ = verifier.verify_batch(big)
+        assert st.tolist() == [v["expect_status"] for v in vs]
+    finally:
+        verifier.set_option("chunk_bytes", 96 << 20)
+
+
 def test_separate_contexts_from_separate_threads(golden):
     import zk_state_proofs_b200 as z
     vs = golden["vectors"]

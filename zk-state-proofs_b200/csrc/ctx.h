@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -127,6 +128,7 @@ struct Device {
 struct mptv_ctx {
   std::vector<mptv::Device> dev;
   std::string err;
+  std::mutex err_mu;  // the host entries run one thread per device
   int lanes_per_proof = 0;          // 0 = auto
   uint64_t chunk_bytes = 96ull << 20;  // node bytes per pipeline chunk of the host-buffer path
   int binning = 1;
@@ -144,8 +146,25 @@ namespace mptv {
 inline int fail_cuda(mptv_ctx* c, cudaError_t e, const char* where) {
   char buf[256];
   snprintf(buf, sizeof buf, "%s: %s", where, cudaGetErrorString(e));
-  if (c) c->err = buf;
+  if (c) { std::lock_guard<std::mutex> g(c->err_mu); c->err = buf; }
   return MPTV_ERR_CUDA;
+}
+
+inline int fail_msg(mptv_ctx* c, int rc, const char* msg) {
+  if (c) { std::lock_guard<std::mutex> g(c->err_mu); c->err = msg; }
+  return rc;
+}
+
+// A host entry that fails half way must not return while copies that read the caller's buffers (or kernels
+// that will write results a later call would pick up) are still queued: wait for everything this device
+// has in flight and forget the pending result blocks.
+inline void quiesce(Device& d) {
+  cudaSetDevice(d.id);
+  if (d.stream) cudaStreamSynchronize(d.stream);
+  for (Slot& s : d.slot) {
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    s.pend_np = 0;
+  }
 }
 
 }  // namespace mptv

@@ -362,7 +362,7 @@ int drain_slot(mptv_ctx* ctx, Slot& s, mptv_result* out) {
 inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // run one device's slice [p0, p1): chunked, multi-buffered H2D -> kernels -> D2H
-int run_slice(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result* out, uint64_t p0, uint64_t p1) {
+int run_slice_chunks(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result* out, uint64_t p0, uint64_t p1) {
   if (p1 <= p0) return MPTV_OK;
   CK(cudaSetDevice(d.id));
   int rc = MPTV_OK;
@@ -460,6 +460,12 @@ int run_slice(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result* out, 
   return MPTV_OK;
 }
 
+int run_slice(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result* out, uint64_t p0, uint64_t p1) {
+  const int rc = run_slice_chunks(ctx, d, in, out, p0, p1);
+  if (rc != MPTV_OK) quiesce(d);  // earlier chunks may still be reading the caller's buffers / owe results
+  return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -547,8 +553,8 @@ int mptv_verify_batch_hashed_keys(mptv_ctx* ctx, const mptv_batch* in, const uin
   return mptv_verify_batch(ctx, &b, out);
 }
 
-int mptv_keccak256_batch(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node_bytes_len, const uint64_t* node_off,
-                         const uint32_t* node_len, uint64_t n_nodes, uint8_t* digests32) {
+static int keccak256_batch_run(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node_bytes_len, const uint64_t* node_off,
+                               const uint32_t* node_len, uint64_t n_nodes, uint8_t* digests32) {
   if (!ctx || (n_nodes && (!node_bytes || !node_off || !node_len || !digests32))) return MPTV_ERR_ARG;
   if (n_nodes == 0) return MPTV_OK;
   if (n_nodes > 0xfffffff0ull) return MPTV_ERR_ARG;
@@ -583,6 +589,13 @@ int mptv_keccak256_batch(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node
   CK(cudaMemcpyAsync(digests32, s.digests.p, 32 * n_nodes, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return MPTV_OK;
+}
+
+int mptv_keccak256_batch(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node_bytes_len, const uint64_t* node_off,
+                         const uint32_t* node_len, uint64_t n_nodes, uint8_t* digests32) {
+  const int rc = keccak256_batch_run(ctx, node_bytes, node_bytes_len, node_off, node_len, n_nodes, digests32);
+  if (rc != MPTV_OK && ctx && !ctx->dev.empty()) quiesce(ctx->dev[0]);
+  return rc;
 }
 
 }  // extern "C"

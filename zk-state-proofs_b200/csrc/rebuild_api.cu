@@ -43,7 +43,7 @@ int rebuild_on_device(mptv_ctx* ctx, Device& d, const TrieBatchDev& in, uint8_t*
   CK(cudaMemcpyAsync(hs, w.sum, sizeof(TrieSummary), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (hs->max_items > (uint32_t)kTrieMaxItems || hs->max_key_len > (uint32_t)kTrieMaxKeyLen) {
-    ctx->err = "mptv_trie_roots: a trie has more than 8192 items or a key longer than 32 bytes";
+    fail_msg(ctx, MPTV_ERR_ARG, "mptv_trie_roots: a trie has more than 8192 items or a key longer than 32 bytes");
     return MPTV_ERR_ARG;
   }
   // ---- pass 1: structure, exact node sizes, level lists
@@ -181,7 +181,7 @@ uint64_t kv_chunk_end(const mptv_kv_batch* in, uint64_t cs, uint64_t t1, uint64_
 
 // one device's share [t0, t1) of a host batch: chunks of about 1 GiB of values, the copy of chunk c+1
 // (copy stream, second input stage) overlapping the rebuild of chunk c
-int rebuild_slice(mptv_ctx* ctx, Device& d, const mptv_kv_batch* in, uint8_t* roots32, uint64_t t0, uint64_t t1) {
+int rebuild_slice_run(mptv_ctx* ctx, Device& d, const mptv_kv_batch* in, uint8_t* roots32, uint64_t t0, uint64_t t1) {
   if (t1 <= t0) return MPTV_OK;
   CK(cudaSetDevice(d.id));
   Rebuild& rb = d.rb;
@@ -209,6 +209,12 @@ int rebuild_slice(mptv_ctx* ctx, Device& d, const mptv_kv_batch* in, uint8_t* ro
     cs = ns; ce = ne; cur = nxt;
   }
   return MPTV_OK;
+}
+
+int rebuild_slice(mptv_ctx* ctx, Device& d, const mptv_kv_batch* in, uint8_t* roots32, uint64_t t0, uint64_t t1) {
+  const int rc = rebuild_slice_run(ctx, d, in, roots32, t0, t1);
+  if (rc != MPTV_OK) quiesce(d);  // the next chunk's copy may still be reading the caller's arena
+  return rc;
 }
 
 int check_kv(const mptv_kv_batch* in, const uint8_t* roots32) {
@@ -278,8 +284,8 @@ int mptv_trie_roots(mptv_ctx* ctx, const mptv_kv_batch* in, uint8_t* roots32) {
   return MPTV_OK;
 }
 
-int mptv_trie_proofs(mptv_ctx* ctx, const mptv_kv_batch* in, const mptv_proof_targets* tg, uint8_t* roots32,
-                     mptv_proofs_out* out) {
+static int trie_proofs_run(mptv_ctx* ctx, const mptv_kv_batch* in, const mptv_proof_targets* tg, uint8_t* roots32,
+                           mptv_proofs_out* out) {
   if (!ctx || !in || !tg || !out) return MPTV_ERR_ARG;
   out->n_nodes = 0; out->node_bytes_len = 0;
   const uint64_t nq = tg->n_targets;
@@ -348,6 +354,13 @@ int mptv_trie_proofs(mptv_ctx* ctx, const mptv_kv_batch* in, const mptv_proof_ta
   CK(cudaMemcpyAsync(out->proof_first, rb.q_proof_first.p, 4 * (nq + 1), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return MPTV_OK;
+}
+
+int mptv_trie_proofs(mptv_ctx* ctx, const mptv_kv_batch* in, const mptv_proof_targets* tg, uint8_t* roots32,
+                     mptv_proofs_out* out) {
+  const int rc = trie_proofs_run(ctx, in, tg, roots32, out);
+  if (rc != MPTV_OK && ctx && !ctx->dev.empty()) quiesce(ctx->dev[0]);
+  return rc;
 }
 
 int mptv_last_rebuild_timings(mptv_ctx* ctx, int dev_index, mptv_rebuild_timings* out) {
