@@ -46,7 +46,7 @@ extern "C" {
 #define MPTV_ERR_ARG (-1)    /* null / inconsistent argument                                         */
 #define MPTV_ERR_CUDA (-2)   /* CUDA runtime error; mptv_last_error(ctx) has the text                */
 #define MPTV_ERR_ALIGN (-3)  /* a node does not start on a 16-byte boundary of the arena             */
-#define MPTV_ERR_NOMEM (-4)
+#define MPTV_ERR_NOMEM (-4)  /* device / pinned allocation failed, or an output capacity is too small     */
 #define MPTV_ERR_DEP (-5)    /* root_from_proof must point at an EARLIER, independent proof          */
 #define MPTV_ERR_NODEV (-6)  /* no CUDA device / CUDA extension unusable: there is no CPU fallback   */
 

@@ -147,6 +147,10 @@ inline int fail_cuda(mptv_ctx* c, cudaError_t e, const char* where) {
   char buf[256];
   snprintf(buf, sizeof buf, "%s: %s", where, cudaGetErrorString(e));
   if (c) { std::lock_guard<std::mutex> g(c->err_mu); c->err = buf; }
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();  // not sticky: the context stays usable for a smaller batch
+    return MPTV_ERR_NOMEM;
+  }
   return MPTV_ERR_CUDA;
 }
 

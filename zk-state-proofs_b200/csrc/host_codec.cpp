@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -137,8 +138,8 @@ inline uint64_t log_payload(const mptv_log& l) {
 
 extern "C" {
 
-int mptv_flatten_borsh(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, int pinned,
-                       mptv_host_batch** out) {
+static int flatten_borsh_run(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, int pinned,
+                             mptv_host_batch** out) {
   if (!out || (n && (!blobs || !blob_off))) return MPTV_ERR_ARG;
   mptv_host_batch* reuse = *out;  // NULL, or a handle from an earlier call whose buffers are recycled
   if (reuse && reuse->pinned != (pinned != 0)) return MPTV_ERR_ARG;
@@ -209,6 +210,15 @@ int mptv_flatten_borsh(const uint8_t* blobs, const uint64_t* blob_off, uint64_t 
   hb->view.key_bytes = key_bytes; hb->view.key_off = key_off; hb->view.root_from_proof = nullptr;
   *out = hb;
   return MPTV_OK;
+}
+
+int mptv_flatten_borsh(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, int pinned,
+                       mptv_host_batch** out) {
+  try {  // the C ABI never throws: the per-input tables below are sized by the caller's n
+    return flatten_borsh_run(blobs, blob_off, n, n_threads, pinned, out);
+  } catch (...) {
+    return MPTV_ERR_NOMEM;
+  }
 }
 
 const mptv_batch* mptv_host_batch_view(const mptv_host_batch* hb) { return hb ? &hb->view : nullptr; }

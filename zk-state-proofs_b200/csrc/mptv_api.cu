@@ -44,7 +44,7 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
   const bool one_wave = b.n_nodes <= (uint64_t)d.sm_count * kKeccakMinBlocks * kKeccakThreads / 4;
   const bool binned = ctx->binning && !one_wave;
   // optional: hash every DISTINCT node once (a secondary, separately reported mode; see dedup_kernels.cu)
-  const bool dd = ctx->dedup_nodes && !one_wave;
+  const bool dd = ctx->dedup_nodes && !one_wave && b.n_nodes <= (1ull << 30);  // the table has 2^k >= 2 n slots, k <= 31
   uint64_t n_hash = b.n_nodes;
   uint32_t* dup_of = nullptr;
   d.last_unique_nodes = 0; d.last_unique_perm = 0;
@@ -152,7 +152,8 @@ int mptv_create(const int* device_ids, int n_devices, mptv_ctx** out) {
     cudaError_t e = cudaSetDevice(d.id);
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, d.id);
-    if (e == cudaSuccess && prop.major < 10) {  // sm_100a code only
+    if (e == cudaSuccess && (prop.major != 10 || prop.minor != 0)) {  // the library holds sm_100a code only
+      fprintf(stderr, "mptv_create: device %d is sm_%d%d, this library is built for sm_100a (B200)\n", d.id, prop.major, prop.minor);
       delete ctx;
       return MPTV_ERR_NODEV;
     }
@@ -513,7 +514,7 @@ int mptv_verify_batch(mptv_ctx* ctx, const mptv_batch* in, mptv_result* out) {
   return MPTV_OK;
 }
 
-int mptv_verify_batch_hashed_keys(mptv_ctx* ctx, const mptv_batch* in, const uint8_t* hash_key, mptv_result* out) {
+static int verify_batch_hashed_keys_run(mptv_ctx* ctx, const mptv_batch* in, const uint8_t* hash_key, mptv_result* out) {
   if (!hash_key) return mptv_verify_batch(ctx, in, out);
   if (!ctx || !in || !out) return MPTV_ERR_ARG;
   if (in->n_proofs == 0) return MPTV_OK;
@@ -551,6 +552,14 @@ int mptv_verify_batch_hashed_keys(mptv_ctx* ctx, const mptv_batch* in, const uin
   b.key_bytes = keys.data();
   b.key_off = off.data();
   return mptv_verify_batch(ctx, &b, out);
+}
+
+int mptv_verify_batch_hashed_keys(mptv_ctx* ctx, const mptv_batch* in, const uint8_t* hash_key, mptv_result* out) {
+  try {  // the key tables below are host vectors sized by the batch; the C ABI never throws
+    return verify_batch_hashed_keys_run(ctx, in, hash_key, out);
+  } catch (...) {
+    return MPTV_ERR_NOMEM;
+  }
 }
 
 static int keccak256_batch_run(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node_bytes_len, const uint64_t* node_off,
