@@ -56,7 +56,7 @@ typedef struct mptv_ctx mptv_ctx;
  * A batch in flat CSR form (what MerkleProofInput { proof, root_hash, key } x n_proofs flattens to):
  *   node i      = node_bytes[node_off[i] .. node_off[i] + node_len[i])
  *                 node_off[i] % 16 == 0, and node_bytes is readable up to the next multiple of 16
- *                 after each node (padding bytes are never hashed)
+ *                 after each node (padding bytes are never hashed); node_len[i] <= 0xffff0000
  *   proof p     = nodes [proof_first[p], proof_first[p+1])          (any order, duplicates allowed)
  *   root of p   = roots[32p .. 32p+32)
  *   key of p    = key_bytes[key_off[p] .. key_off[p+1])

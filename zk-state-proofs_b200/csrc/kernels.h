@@ -6,6 +6,7 @@
 
 namespace mptv {
 
+constexpr uint32_t kMaxNodeLen = 0xffff0000u;  // 32-bit byte positions inside a node (136 k + 136) must not wrap
 constexpr int kNumBins = 128;            // rate-block-count bins (K0)
 constexpr int kLongLeafBin = 33;         // nodes of more than 32 rate blocks (> 4.3 KB) are hashed in a launch of their own
 constexpr int kBinScratchWords = 2 * kNumBins + 4;  // hist | cursor | K1 tile counter

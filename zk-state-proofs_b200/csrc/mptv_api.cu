@@ -339,6 +339,7 @@ int validate_slice(const mptv_batch* in, uint64_t p0, uint64_t p1) {
   for (uint32_t i = n0; i < n1; i++) {
     const uint64_t o = in->node_off[i];
     if (o & 15) return MPTV_ERR_ALIGN;
+    if (in->node_len[i] > kMaxNodeLen) return MPTV_ERR_ARG;
     if (o < prev_end && i > n0) return MPTV_ERR_ARG;  // nodes must be laid out in index order
     prev_end = o + in->node_len[i];
     if (((prev_end + 15) & ~15ull) > ((in->node_bytes_len + 15) & ~15ull)) return MPTV_ERR_ARG;
@@ -569,6 +570,7 @@ static int keccak256_batch_run(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_
   if (n_nodes > 0xfffffff0ull) return MPTV_ERR_ARG;
   for (uint64_t i = 0; i < n_nodes; i++) {
     if (node_off[i] & 15) return MPTV_ERR_ALIGN;
+    if (node_len[i] > kMaxNodeLen) return MPTV_ERR_ARG;
     if (((node_off[i] + node_len[i] + 15) & ~15ull) > ((node_bytes_len + 15) & ~15ull)) return MPTV_ERR_ARG;
   }
   Device& d = ctx->dev[0];
