@@ -270,14 +270,15 @@ def main_single(a):
                 ms_per_step=dt * 1e3 * 200, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u32",
                 data="synthetic",
                 config=dict(workload=workload_name(a), calls_per_step=200, nodes=b.n_nodes, keccak_f=b.n_perm(),
-                            note="latency-bound: one blocking C-ABI call = 8 H2D copies + 9 launches + 3 D2H copies; "
+                            note="latency-bound: one blocking C-ABI call = 1 packed H2D copy + 4 kernels (K1, K2a, K2f, K2b; a "
+                                 "batch below one wave skips binning) + 1 D2H copy; "
                                  "there is no device-resident variant of a single-proof call, so value == e2e"),
                 latency_us=dt * 1e6, keccak_f_per_sec=b.n_perm() / dt,
                 roofline=None,
                 e2e=dict(value=1.0 / dt, unit=UNIT, h2d_bytes_per_step=h2d * 200, d2h_bytes_per_step=13 * 200,
                          ms_per_step=dt * 1e3 * 200, host_memory="pageable",
                          timer="host wall clock around the blocking C-ABI call"),
-                gpu_launches=9 * n_calls, clocks=clocks)
+                gpu_launches=4 * n_calls, clocks=clocks)
     if rank == 0:
         if not a.no_cpu_baseline:
             from oracle.pyoracle import Oracle
