@@ -75,6 +75,42 @@ def test_seeded_corpus_matches_oracle_including_offsets(verifier, oracle, walk_m
     assert (voff == ovoff).all()
 
 
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_long_proofs_beyond_the_lane_group(verifier, oracle, lanes, walk_mode):
+    """Proofs with far more nodes than lanes in a group (the reference takes ANY multiset of nodes): the
+    path's own nodes scattered among up to 100 junk strings, foreign nodes of other proofs and duplicates."""
+    import random
+    import zk_state_proofs_b200 as z
+    from oracle.fuzzgen import corpus
+    rng = random.Random(77)
+    base = corpus(4242, oracle.keccak256, 40, 400, 300)
+    pool = [n for c in base for n in c["proof"] if n]
+    cases = []
+    for c in base:
+        proof = list(c["proof"])
+        for _ in range(rng.choice([0, 3, 7, 9, 15, 17, 31, 33, 60, 100])):
+            r = rng.random()
+            extra = rng.randbytes(rng.randint(1, 80)) if r < 0.4 else (rng.choice(pool) if r < 0.8 or not proof
+                                                                       else rng.choice(proof))
+            proof.insert(rng.randrange(len(proof) + 1), extra)
+        if rng.random() < 0.5:
+            rng.shuffle(proof)
+        cases.append(dict(root=c["root"], proof=proof, key=c["key"], tag=c["tag"]))
+    b = z.flatten([z.MerkleProofInput(c["proof"], c["root"], c["key"]) for c in cases])
+    verifier.set_option("lanes_per_proof", lanes)
+    try:
+        st, voff, vlen = verifier.verify_batch(b)
+    finally:
+        verifier.set_option("lanes_per_proof", 0)
+    d = dict(node_bytes=b.node_bytes, node_off=b.node_off, node_len=b.node_len, proof_first=b.proof_first,
+             roots=b.roots, key_bytes=b.key_bytes, key_off=b.key_off)
+    ost, ovoff, ovlen, _, _ = oracle.verify_batch(d, nthreads=4)
+    assert (st == ost).all(), [(cases[i]["tag"], len(cases[i]["proof"]), st[i], ost[i]) for i in np.nonzero(st != ost)[0][:10]]
+    # duplicates of the node that holds the value: both sides report the first copy in proof order
+    assert (vlen == ovlen).all() and (voff == ovoff).all()
+    assert (np.array([len(c["proof"]) for c in cases]) > 32).sum() > 50
+
+
 def test_small_chunks_no_binning_unfused_give_identical_results(verifier, golden):
     import zk_state_proofs_b200 as z
     vs = golden["vectors"]
