@@ -1,6 +1,6 @@
 """oracle/fuzz_vs_ref.py -- TEST INFRASTRUCTURE.  Live differential fuzz of the C restatement
 (oracle/mpt_oracle.c) against the reference's own guest ELF.  Usage:
-    python -m oracle.fuzz_vs_ref [seed] [n_tries] [n_mut] [n_weird] [n_nested] [n_reseal]
+    python -m oracle.fuzz_vs_ref [seed] [n_tries] [n_mut] [n_weird] [n_nested] [n_reseal] [n_padded]
 """
 import sys
 import time
@@ -18,9 +18,10 @@ def main():
     n_weird = int(sys.argv[4]) if len(sys.argv) > 4 else 4000
     n_nested = int(sys.argv[5]) if len(sys.argv) > 5 else 2000
     n_reseal = int(sys.argv[6]) if len(sys.argv) > 6 else 4000
+    n_padded = int(sys.argv[7]) if len(sys.argv) > 7 else 1000
     o = Oracle()
     ref = RefElf()
-    cases = corpus(seed, o.keccak256, n_tries, n_mut, n_weird, n_nested, n_reseal)
+    cases = corpus(seed, o.keccak256, n_tries, n_mut, n_weird, n_nested, n_reseal, n_padded)
     t0 = time.time()
 
     def one(c):

@@ -390,7 +390,27 @@ def resealed_cases(rng: random.Random, keccak, base, n: int):
     return out
 
 
-def corpus(seed: int, keccak, n_tries: int, n_mut: int, n_weird: int, n_nested: int = 0, n_reseal: int = 0):
+def padded_cases(rng: random.Random, cases, n: int):
+    """Long proofs: a case's own nodes scattered among up to 100 junk strings, nodes of OTHER cases and
+    duplicates of its own nodes (the reference accepts any multiset of nodes, lib.rs:10-13)."""
+    pool = [nd for c in cases for nd in c["proof"] if nd]
+    out = []
+    for _ in range(n):
+        c = rng.choice(cases)
+        proof = list(c["proof"])
+        for _ in range(rng.choice([3, 7, 9, 15, 17, 31, 33, 60, 100])):
+            r = rng.random()
+            extra = rng.randbytes(rng.randint(1, 80)) if r < 0.4 else (rng.choice(pool) if r < 0.8 or not proof
+                                                                       else rng.choice(proof))
+            proof.insert(rng.randrange(len(proof) + 1), extra)
+        if rng.random() < 0.5:
+            rng.shuffle(proof)
+        out.append(dict(root=c["root"], proof=proof, key=c["key"], tag="padded/" + c["tag"]))
+    return out
+
+
+def corpus(seed: int, keccak, n_tries: int, n_mut: int, n_weird: int, n_nested: int = 0, n_reseal: int = 0,
+           n_padded: int = 0):
     rng = random.Random(seed)
     base = valid_cases(rng, keccak, n_tries)
     out = list(base)
@@ -401,4 +421,6 @@ def corpus(seed: int, keccak, n_tries: int, n_mut: int, n_weird: int, n_nested: 
         out += nested_cases(rng, keccak, n_nested)
     if n_reseal:
         out += resealed_cases(rng, keccak, base, n_reseal)
+    if n_padded:  # drawn last, so corpora made without it are unchanged
+        out += padded_cases(rng, list(out), n_padded)
     return out

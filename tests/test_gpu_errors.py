@@ -112,7 +112,7 @@ def test_large_fuzz_corpus_matches_oracle(verifier, oracle):
     verdict and value == C restatement (which agrees with the reference ELF on 1.3 M such cases, oracle/fuzz_vs_ref.py)"""
     import zk_state_proofs_b200 as z
     from oracle.fuzzgen import corpus
-    cases = corpus(777, oracle.keccak256, 150, 8000, 12000, 8000, 12000)
+    cases = corpus(777, oracle.keccak256, 150, 8000, 12000, 8000, 12000, 2000)
     b = z.flatten([z.MerkleProofInput(c["proof"], c["root"], c["key"]) for c in cases])
     st, voff, vlen = verifier.verify_batch(b)
     d = dict(node_bytes=b.node_bytes, node_off=b.node_off, node_len=b.node_len, proof_first=b.proof_first,

@@ -10,7 +10,7 @@ def test_fuzz_small(oracle):
     from oracle.fuzzgen import corpus
     from oracle.pyoracle import RefElf
     ref = RefElf()
-    cases = corpus(12345, oracle.keccak256, 20, 300, 700)
+    cases = corpus(12345, oracle.keccak256, 20, 300, 700, 100, 100, 60)
     bad = []
     for c in cases:
         a = oracle.verify(c["root"], c["proof"], c["key"])

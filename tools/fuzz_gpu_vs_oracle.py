@@ -21,7 +21,7 @@ modes = [dict(fast_walk=1, dedup_nodes=0), dict(fast_walk=0, dedup_nodes=0), dic
 total, bad, hist = 0, 0, Counter()
 t0 = time.time()
 for seed in range(first, first + n_seeds):
-    cases = corpus(seed, o.keccak256, 300, 15000, 20000, 15000, 30000)
+    cases = corpus(seed, o.keccak256, 300, 15000, 20000, 15000, 30000, 4000)
     b = z.flatten_borsh([z.MerkleProofInput(c["proof"], c["root"], c["key"]).to_borsh() for c in cases], threads=0)
     d = dict(node_bytes=b.node_bytes, node_off=b.node_off, node_len=b.node_len, proof_first=b.proof_first,
              roots=b.roots, key_bytes=b.key_bytes, key_off=b.key_off)
