@@ -63,8 +63,6 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--pageable", action="store_true", help="e2e from ordinary (pageable) host memory instead of pinned")
-    ap.add_argument("--overlap", type=int, default=-1, help="node ranges of the overlapped pipeline (0 = sequential; -1 = library default)")
-    ap.add_argument("--overlap-ctas", type=int, default=0, help="K1 CTAs per SM while a walk runs beside it (0 = library default)")
     ap.add_argument("--l2-fetch", type=int, default=0, help="L2 fetch granularity hint in bytes (32/64/128; 0 = leave the default)")
     ap.add_argument("--dedup", action="store_true",
                     help="SECONDARY number: hash each distinct node of the batch once (dedup_nodes option); the "
@@ -577,10 +575,6 @@ def main():
         ver.set_option("dedup_nodes", 1)
     if a.l2_fetch:
         ver.set_option("l2_fetch_granularity", a.l2_fetch)
-    if a.overlap >= 0:
-        ver.set_option("overlap_ranges", a.overlap)
-    if a.overlap_ctas:
-        ver.set_option("overlap_keccak_ctas", a.overlap_ctas)
     b, gen_info = build_batch(a, rank, pinned=not a.pageable)
     n_proofs, n_nodes, n_perm = b.n_proofs, b.n_nodes, b.n_perm()
     node_bytes_total = int(b.node_len.astype(np.int64).sum())

@@ -107,21 +107,14 @@ def test_separate_contexts_from_separate_threads(golden):
     assert not errs, errs
 
 
-@pytest.mark.parametrize("overlap", [0, 3, 7])
-def test_large_fuzz_corpus_matches_oracle(verifier, oracle, overlap):
+def test_large_fuzz_corpus_matches_oracle(verifier, oracle):
     """40 k generated + mutated + malformed + deeply nested + corrupted-and-re-sealed cases (oracle/fuzzgen.py), GPU
     verdict and value == C restatement (which agrees with the reference ELF on 1.3 M such cases, oracle/fuzz_vs_ref.py)"""
     import zk_state_proofs_b200 as z
     from oracle.fuzzgen import corpus
     cases = corpus(777, oracle.keccak256, 150, 8000, 12000, 8000, 12000, 2000)
     b = z.flatten([z.MerkleProofInput(c["proof"], c["root"], c["key"]) for c in cases])
-    verifier.set_option("overlap_ranges", overlap)  # the overlapped pipeline: proofs walked range by range
-    verifier.set_option("overlap_min_nodes", 1 if overlap else 0)
-    try:
-        st, voff, vlen = verifier.verify_batch(b)
-    finally:
-        verifier.set_option("overlap_ranges", 0)
-        verifier.set_option("overlap_min_nodes", 0)
+    st, voff, vlen = verifier.verify_batch(b)
     d = dict(node_bytes=b.node_bytes, node_off=b.node_off, node_len=b.node_len, proof_first=b.proof_first,
              roots=b.roots, key_bytes=b.key_bytes, key_off=b.key_off)
     ost, ovoff, ovlen, _, _ = oracle.verify_batch(d, nthreads=8)

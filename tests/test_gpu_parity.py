@@ -7,21 +7,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[(1, 0, 0), (0, 0, 0), (1, 1, 0), (1, 0, 3)],
-                ids=["fast_walk", "cooperative_walk_only", "fast_walk+dedup_nodes", "overlapped_ranges"])
+@pytest.fixture(params=[(1, 0), (0, 0), (1, 1)], ids=["fast_walk", "cooperative_walk_only", "fast_walk+dedup_nodes"])
 def walk_mode(request, verifier):
-    """walk configurations: K2f (thread per proof) + K2b on the deferred rest, K2b on everything, the
-    optional node de-duplication in front of K1 (every distinct node hashed once, digests shared), and the
-    overlapped pipeline (nodes hashed in ranges, each range's proofs walked while the next range is hashed)"""
+    """walk configurations: K2f (thread per proof) + K2b on the deferred rest, K2b on everything, and the
+    optional node de-duplication in front of K1 (every distinct node hashed once, digests shared)"""
     verifier.set_option("fast_walk", request.param[0])
     verifier.set_option("dedup_nodes", request.param[1])
-    verifier.set_option("overlap_ranges", request.param[2])
-    verifier.set_option("overlap_min_nodes", 1 if request.param[2] else 0)
     yield request.param
     verifier.set_option("fast_walk", 1)
     verifier.set_option("dedup_nodes", 0)
-    verifier.set_option("overlap_ranges", 0)
-    verifier.set_option("overlap_min_nodes", 0)
 
 
 def _inputs(z, vs):

@@ -17,10 +17,7 @@ n_seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 first = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
 o = Oracle()
 ver = z.Verifier([0])
-modes = [dict(fast_walk=1, dedup_nodes=0, overlap_ranges=0, overlap_min_nodes=0),
-         dict(fast_walk=0, dedup_nodes=0, overlap_ranges=0, overlap_min_nodes=0),
-         dict(fast_walk=1, dedup_nodes=1, overlap_ranges=0, overlap_min_nodes=0),
-         dict(fast_walk=1, dedup_nodes=0, overlap_ranges=5, overlap_min_nodes=1)]
+modes = [dict(fast_walk=1, dedup_nodes=0), dict(fast_walk=0, dedup_nodes=0), dict(fast_walk=1, dedup_nodes=1)]
 total, bad, hist = 0, 0, Counter()
 t0 = time.time()
 for seed in range(first, first + n_seeds):

@@ -107,7 +107,6 @@ struct Rebuild {
 };
 
 constexpr int kSlots = 3;  // pipeline depth of the host-buffer path (H2D / kernels / D2H in flight)
-constexpr int kMaxOverlap = 16;  // node ranges of the overlapped device pipeline ("overlap_ranges")
 
 struct Device {
   int id = 0;
@@ -117,12 +116,6 @@ struct Device {
   uint64_t last_unique_nodes = 0, last_unique_perm = 0;  // of the last dedup_nodes run
   Slot slot[kSlots];
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  // overlapped pipeline: K0 / K1 run on `aux` (highest priority), the walk of node range s on the caller's
-  // stream while K1 hashes range s+1
-  cudaStream_t aux = nullptr;
-  cudaEvent_t ov_done[kMaxOverlap] = {}, ov_join = nullptr;  // K1 of range s has finished / the call may start hashing
-  cudaEvent_t ov_t[3 * kMaxOverlap] = {};                    // timing on aux: before K0s, after K0s, after K1 of range s
-  int last_overlap = 0;                                      // ranges of the last timed run (0 = sequential pipeline)
   cudaStream_t last_stream = nullptr;
   bool have_timing = false;
   uint64_t last_nodes = 0;
@@ -145,9 +138,6 @@ struct mptv_ctx {
   int long_leaf_bin = mptv::kLongLeafBin;  // rebuild: leaves in rate-block bins >= this are hashed in their own launch ...
   int long_leaf_ctas = 1;            // ... with this many K1L CTAs (of 4 warps) per SM
   int fused_leaf_hash = 1; // rebuild: hash leaves straight from the value arena (K1L), no encode pass
-  int overlap_ranges = 0;  // >= 2: hash the nodes in this many ranges and walk range s while range s+1 is hashed
-  int64_t overlap_min_nodes = 0;  // 0 = only batches with >= 16 K1 waves per range
-  int overlap_keccak_ctas = 3;  // K1 CTAs per SM in that mode (the 4th CTA's registers go to the walk kernels)
 };
 
 

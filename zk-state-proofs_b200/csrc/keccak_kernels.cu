@@ -537,12 +537,11 @@ cudaError_t launch_bin_nodes(const uint32_t* node_len, const uint32_t* ids, uint
 cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
                                    const uint32_t* node_len, const uint32_t* order, uint64_t n_nodes,
                                    uint8_t* digests, uint32_t* meta, uint32_t* tile_counter, int sm_count,
-                                   cudaStream_t st, const uint32_t* split, int long_ctas, int ctas_per_sm) {
+                                   cudaStream_t st, const uint32_t* split, int long_ctas) {
   if (n_nodes == 0) return cudaSuccess;
   size_t smem = keccak_smem_bytes();
   uint64_t n_tiles = (n_nodes + kKeccakThreads - 1) / kKeccakThreads;
-  if (ctas_per_sm <= 0 || ctas_per_sm > kKeccakMinBlocks) ctas_per_sm = kKeccakMinBlocks;
-  uint64_t grid = (uint64_t)sm_count * ctas_per_sm;  // persistent: one wave of resident CTAs
+  uint64_t grid = (uint64_t)sm_count * kKeccakMinBlocks;  // persistent: one wave of resident CTAs
   if (grid > n_tiles) grid = n_tiles;
   for (int part = split ? 0 : 1; part < 2; part++) {
     if (tile_counter) {

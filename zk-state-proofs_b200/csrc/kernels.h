@@ -76,13 +76,7 @@ inline const uint32_t* bin_split_word(const uint32_t* scratch) { return scratch 
 cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
                                    const uint32_t* node_len, const uint32_t* order, uint64_t n_nodes,
                                    uint8_t* digests, uint32_t* meta, uint32_t* tile_counter /* 1 u32 of scratch or NULL */,
-                                   int sm_count, cudaStream_t st, const uint32_t* split = nullptr, int long_ctas = 1,
-                                   int ctas_per_sm = 0 /* 0 = kKeccakMinBlocks; fewer leaves registers to a co-running kernel */);
-
-// Restricts a walk launch to the proofs whose LAST node index (local to the batch) lies in (lo, hi] -- plus, when
-// `first`, the proofs that end at node 0 (empty proofs at the head of the batch).  Used by the overlapped
-// pipeline, where nodes are hashed range by range and a range's proofs are walked while the next is hashed.
-struct NodeRange { uint32_t lo, hi; int first; };
+                                   int sm_count, cudaStream_t st, const uint32_t* split = nullptr, int long_ctas = 1);
 
 // K2a: meta[i] = eager-decode record of node i.  only_slow: leave records != kMetaSlow untouched
 cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
@@ -93,7 +87,7 @@ cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, co
 cudaError_t launch_verify_walk(const DeviceBatch& b, const uint8_t* digests, const uint32_t* meta, int wave,
                                int lanes_per_proof, uint8_t* status, uint64_t* value_off, uint32_t* value_len,
                                uint32_t* defer /* scratch [1 + n_proofs]; NULL = K2b on every proof */, int sm_count,
-                               cudaStream_t st, const NodeRange* range = nullptr);
+                               cudaStream_t st);
 
 // ------------------------------------------------------------------ K4: trie rebuild (rebuild_kernels.cu)
 constexpr int kTrieThreads = 128;       // CTA of k_trie_structure (one trie per CTA)

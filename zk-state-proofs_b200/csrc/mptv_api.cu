@@ -27,72 +27,6 @@ int pick_lanes(const mptv_ctx* ctx, uint64_t n_nodes, uint64_t n_proofs) {
   return avg <= 8.5 ? 8 : (avg <= 17.0 ? 16 : 32);
 }
 
-// The same pipeline with the walk hidden under the hashing: the nodes are cut into S ranges; K0 of every range
-// and then K1 of range 0, 1, ... run back to back on the device's HIGH-PRIORITY auxiliary stream, while K2a /
-// K2f / K2b of range s run on the caller's stream as soon as K1 of range s has finished, i.e. beside K1 of
-// range s + 1.  A proof belongs to the range its LAST node lies in, so every node it names has been hashed when
-// it is walked; a dependent proof follows its account proof, whose verdict therefore comes from the same or
-// an earlier range, and the caller's stream takes the ranges in order.  From range 1 on K1 runs with one CTA
-// per SM less than usual, which frees exactly the registers one CTA of the walk kernels needs; the stream
-// priority makes the block scheduler place K1's persistent CTAs first whenever both kernels have CTAs pending.
-int run_pipeline_overlapped(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests, DevBuf& meta, DevBuf& order,
-                            DevBuf& bins, DevBuf& defer, uint8_t* status, uint64_t* value_off, uint32_t* value_len,
-                            cudaStream_t st, bool timed, int S) {
-  CK(digests.reserve(32 * (size_t)b.n_nodes + 32));
-  CK(meta.reserve(4 * (size_t)b.n_nodes + 4));
-  CK(order.reserve(4 * (size_t)b.n_nodes + 4));
-  CK(bins.reserve((size_t)S * kBinScratchWords * sizeof(uint32_t)));
-  CK(defer.reserve(4 * (size_t)b.n_proofs + 8));
-  uint32_t* dl = defer.as<uint32_t>();
-  const int G = pick_lanes(ctx, b.n_nodes, b.n_proofs);
-  cudaStream_t hi = d.aux;
-  if (timed) CK(cudaEventRecord(d.ev[0], st));
-  CK(cudaEventRecord(d.ov_join, st));  // the hashing starts after whatever the caller queued before this call
-  CK(cudaStreamWaitEvent(hi, d.ov_join, 0));
-  uint32_t klaunch = 0, other = 0;
-  auto lo_of = [&](int s) { return b.n_nodes * (uint64_t)s / S; };
-  if (timed) CK(cudaEventRecord(d.ov_t[0], hi));
-  for (int s = 0; s < S; s++) {
-    const uint64_t n0 = lo_of(s), nn = lo_of(s + 1) - n0;
-    CK(launch_bin_nodes(b.node_len + n0, nullptr, nn, bins.as<uint32_t>() + (size_t)s * kBinScratchWords,
-                        order.as<uint32_t>() + n0, hi, nullptr, nullptr, ctx->long_leaf_bin));
-    other += 3;
-  }
-  if (timed) CK(cudaEventRecord(d.ov_t[1], hi));
-  for (int s = 0; s < S; s++) {
-    const uint64_t n0 = lo_of(s), nn = lo_of(s + 1) - n0;
-    uint32_t* bs = bins.as<uint32_t>() + (size_t)s * kBinScratchWords;
-    CK(launch_keccak256_nodes(b.node_bytes, b.byte_base, b.node_off + n0, b.node_len + n0, order.as<uint32_t>() + n0, nn,
-                              digests.as<uint8_t>() + 32 * n0, ctx->fused_classify ? meta.as<uint32_t>() + n0 : nullptr,
-                              bs + 2 * kNumBins, d.sm_count, hi, bin_split_word(bs), ctx->long_leaf_ctas,
-                              s == 0 ? 0 : ctx->overlap_keccak_ctas));
-    if (timed) CK(cudaEventRecord(d.ov_t[2 + s], hi));
-    CK(cudaEventRecord(d.ov_done[s], hi));
-    klaunch += 2;
-  }
-  for (int s = 0; s < S; s++) {
-    const uint64_t n0 = lo_of(s), n1 = lo_of(s + 1), nn = n1 - n0;
-    CK(cudaStreamWaitEvent(st, d.ov_done[s], 0));
-    CK(launch_parse_nodes(b.node_bytes, b.byte_base, b.node_off + n0, b.node_len + n0, nn, meta.as<uint32_t>() + n0,
-                          ctx->fused_classify != 0, st));
-    const NodeRange r = {(uint32_t)n0, (uint32_t)n1, s == 0 ? 1 : 0};
-    CK(launch_verify_walk(b, digests.as<uint8_t>(), meta.as<uint32_t>(), 0, G, status, value_off, value_len, dl, d.sm_count,
-                          st, &r));
-    other += 3;
-    if (b.root_from_proof) {
-      CK(launch_verify_walk(b, digests.as<uint8_t>(), meta.as<uint32_t>(), 1, G, status, value_off, value_len, dl,
-                            d.sm_count, st, &r));
-      other += 2;
-    }
-  }
-  if (timed) {
-    CK(cudaEventRecord(d.ev[4], st));
-    d.last_stream = st; d.have_timing = true; d.last_nodes = b.n_nodes; d.last_overlap = S;
-    d.last_keccak_launches = klaunch; d.last_other_launches = other;
-  }
-  return MPTV_OK;
-}
-
 // The whole device pipeline for one device-resident (slice of a) batch: K0 -> K1 -> K2a -> K2b.
 int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests, DevBuf& meta, DevBuf& order,
                  DevBuf& bins, DevBuf& defer, DevBuf& dedup, uint8_t* status, uint64_t* value_off, uint32_t* value_len, cudaStream_t st,
@@ -111,14 +45,6 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
   const bool binned = ctx->binning && !one_wave;
   // optional: hash every DISTINCT node once (a secondary, separately reported mode; see dedup_kernels.cu)
   const bool dd = ctx->dedup_nodes && !one_wave && b.n_nodes <= (1ull << 30);  // the table has 2^k >= 2 n slots, k <= 31
-  // big batches on the standard configuration: hide the walk under the hashing (see run_pipeline_overlapped)
-  const uint64_t ov_min = ctx->overlap_min_nodes > 0
-                              ? (uint64_t)ctx->overlap_min_nodes
-                              : (uint64_t)ctx->overlap_ranges * 16 * d.sm_count * kKeccakMinBlocks * kKeccakThreads;
-  if (ctx->overlap_ranges >= 2 && binned && !dd && dl && b.n_nodes >= ov_min)
-    return run_pipeline_overlapped(ctx, d, b, digests, meta, order, bins, defer, status, value_off, value_len, st, timed,
-                                   ctx->overlap_ranges);
-  if (timed) d.last_overlap = 0;
   uint64_t n_hash = b.n_nodes;
   uint32_t* dup_of = nullptr;
   d.last_unique_nodes = 0; d.last_unique_perm = 0;
@@ -236,12 +162,6 @@ int mptv_create(const int* device_ids, int n_devices, mptv_ctx** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
     for (int s = 0; s < kSlots && e == cudaSuccess; s++) e = cudaStreamCreateWithFlags(&d.slot[s].stream, cudaStreamNonBlocking);
     for (int k = 0; k < 6 && e == cudaSuccess; k++) e = cudaEventCreate(&d.ev[k]);
-    int prio_least = 0, prio_greatest = 0;
-    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&d.aux, cudaStreamNonBlocking, prio_greatest);
-    for (int k = 0; k < kMaxOverlap && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&d.ov_done[k], cudaEventDisableTiming);
-    for (int k = 0; k < 3 * kMaxOverlap && e == cudaSuccess; k++) e = cudaEventCreate(&d.ov_t[k]);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ov_join, cudaEventDisableTiming);
     if (e != cudaSuccess) {
       fprintf(stderr, "mptv_create: device %d: %s\n", d.id, cudaGetErrorString(e));
       mptv_destroy(ctx);
@@ -261,10 +181,6 @@ void mptv_destroy(mptv_ctx* ctx) {
     for (int k = 0; k < kSlots; k++) d.slot[k].release();
     d.rb.release();
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
-    for (auto& e : d.ov_done) if (e) cudaEventDestroy(e);
-    for (auto& e : d.ov_t) if (e) cudaEventDestroy(e);
-    if (d.ov_join) cudaEventDestroy(d.ov_join);
-    if (d.aux) cudaStreamDestroy(d.aux);
     if (d.stream) cudaStreamDestroy(d.stream);
   }
   delete ctx;
@@ -294,15 +210,6 @@ int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
     ctx->long_leaf_ctas = (int)value;
   } else if (!strcmp(name, "fused_leaf_hash")) {
     ctx->fused_leaf_hash = value ? 1 : 0;
-  } else if (!strcmp(name, "overlap_ranges")) {
-    if (value < 0 || value > kMaxOverlap) return MPTV_ERR_ARG;
-    ctx->overlap_ranges = (int)value;
-  } else if (!strcmp(name, "overlap_min_nodes")) {
-    if (value < 0) return MPTV_ERR_ARG;
-    ctx->overlap_min_nodes = value;
-  } else if (!strcmp(name, "overlap_keccak_ctas")) {
-    if (value < 1 || value > kKeccakMinBlocks) return MPTV_ERR_ARG;
-    ctx->overlap_keccak_ctas = (int)value;
   } else if (!strcmp(name, "l2_fetch_granularity")) {
     // device-wide hint: how many bytes an L2 miss brings in from HBM (the nodes are short, 16-byte aligned
     // runs reached in binned order, so wider fetches mostly bring in bytes of a neighbour nobody asked for yet)
@@ -383,18 +290,6 @@ int mptv_last_timings(mptv_ctx* ctx, int dev_index, mptv_timings* out) {
   if (!d.have_timing) return MPTV_ERR_ARG;
   CK(cudaSetDevice(d.id));
   CK(cudaEventSynchronize(d.ev[4]));
-  if (d.last_overlap) {
-    // overlapped pipeline: K0 and K1 run back to back on the high-priority stream (events there); parse and most
-    // of the walk run beside K1, walk_ms is what is left exposed after the last range's hashing
-    CK(cudaEventElapsedTime(&out->total_ms, d.ev[0], d.ev[4]));
-    CK(cudaEventElapsedTime(&out->bin_ms, d.ov_t[0], d.ov_t[1]));
-    CK(cudaEventElapsedTime(&out->keccak_ms, d.ov_t[1], d.ov_t[1 + d.last_overlap]));
-    CK(cudaEventElapsedTime(&out->walk_ms, d.ov_t[1 + d.last_overlap], d.ev[4]));
-    out->n_nodes = d.last_nodes;
-    out->keccak_launches = d.last_keccak_launches;
-    out->other_launches = d.last_other_launches;
-    return MPTV_OK;
-  }
   CK(cudaEventElapsedTime(&out->bin_ms, d.ev[0], d.ev[1]));
   CK(cudaEventElapsedTime(&out->keccak_ms, d.ev[1], d.ev[2]));
   CK(cudaEventElapsedTime(&out->parse_ms, d.ev[2], d.ev[3]));

@@ -645,16 +645,10 @@ __device__ bool fast_one(const DeviceBatch& b, uint64_t p, bool dependent, const
 __global__ void __launch_bounds__(256) k_verify_fast(const DeviceBatch b, int wave, const uint8_t* __restrict__ digests,
                                                      const uint32_t* __restrict__ meta, uint8_t* status_out,
                                                      uint64_t* value_off_out, uint32_t* value_len_out,
-                                                     uint32_t* __restrict__ defer_list, uint32_t* __restrict__ defer_count,
-                                                     const NodeRange range) {
+                                                     uint32_t* __restrict__ defer_list, uint32_t* __restrict__ defer_count) {
   const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool defer = false;
-  bool mine = p < b.n_proofs;
-  if (mine && range.hi != 0xffffffffu) {  // overlapped pipeline: only the proofs that END in this node range
-    const uint32_t e = b.proof_first[p + 1] - b.node_base;
-    mine = (e > range.lo || (range.first && e == 0)) && e <= range.hi;
-  }
-  if (mine) {
+  if (p < b.n_proofs) {
     const bool dependent = b.root_from_proof != nullptr && b.root_from_proof[p] >= 0;
     if (dependent == (wave == 1))
       defer = !fast_one(b, p, dependent, digests, meta, status_out, value_off_out, value_len_out);
@@ -681,11 +675,8 @@ cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, co
 
 cudaError_t launch_verify_walk(const DeviceBatch& b, const uint8_t* digests, const uint32_t* meta, int wave,
                                int lanes_per_proof, uint8_t* status, uint64_t* value_off, uint32_t* value_len,
-                               uint32_t* defer /* [1 + n_proofs] or NULL = no fast path */, int sm_count, cudaStream_t st,
-                               const NodeRange* range) {
+                               uint32_t* defer /* [1 + n_proofs] or NULL = no fast path */, int sm_count, cudaStream_t st) {
   if (b.n_proofs == 0) return cudaSuccess;
-  if (range && !defer) return cudaErrorInvalidValue;  // ranges select proofs in K2f; K2b only sees its list
-  const NodeRange all = {0u, 0xffffffffu, 1};
   const int G = lanes_per_proof;
   const uint64_t threads = b.n_proofs * (uint64_t)G;
   uint64_t blocks = (threads + 255) / 256;
@@ -695,7 +686,7 @@ cudaError_t launch_verify_walk(const DeviceBatch& b, const uint8_t* digests, con
     cudaError_t e = cudaMemsetAsync(defer, 0, sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
     k_verify_fast<<<(unsigned)((b.n_proofs + 255) / 256), 256, 0, st>>>(b, wave, digests, meta, status, value_off, value_len,
-                                                                        defer + 1, defer, range ? *range : all);
+                                                                        defer + 1, defer);
     list = defer + 1;
     count = defer;
     blocks = std::min<uint64_t>(blocks, (uint64_t)sm_count * MPTV_WALK_MINB);  // the deferred list is short: one resident wave
