@@ -15,6 +15,7 @@ SOURCES = ["keccak_kernels.cu", "verify_kernels.cu", "rebuild_kernels.cu", "dedu
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-pthread", "-shared", "-cudart", "static",
+    "-Xlinker", "-z,defs",  # an unresolved symbol fails the build here, not at dlopen time on the GPU box
 ]
 
 
