@@ -63,6 +63,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--pageable", action="store_true", help="e2e from ordinary (pageable) host memory instead of pinned")
+    ap.add_argument("--borsh", action="store_true",
+                    help="also time the streamed borsh entry (blobs in, verdicts out) against flatten-then-verify; adds e2e_borsh")
     ap.add_argument("--l2-fetch", type=int, default=0, help="L2 fetch granularity hint in bytes (32/64/128; 0 = leave the default)")
     ap.add_argument("--dedup", action="store_true",
                     help="SECONDARY number: hash each distinct node of the batch once (dedup_nodes option); the "
@@ -668,6 +670,43 @@ def main():
                    timer="host wall clock around the blocking C-ABI call")
         assert (est == st).all() and (evoff == voff).all() and (evlen == vlen).all(), "host and device entries disagree"
 
+    # ---- optional: from borsh(MerkleProofInput) blobs, the prover's input format
+    e2e_borsh = None
+    if a.borsh and passes == 1 and b.root_from_proof is None:
+        import ctypes
+        from workload import gen
+        blobs, boff = gen.batch_to_borsh(b, pinned=False)
+        L = z.load_library()
+        for _ in range(2):
+            bst, bvoff, bvlen = ver.verify_borsh(blobs, boff)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            bst, bvoff, bvlen = ver.verify_borsh(blobs, boff)
+        dt_stream = (time.perf_counter() - t0) / a.steps
+        assert (bst == st).all() and (bvlen == vlen).all(), "borsh stream and device entry disagree"
+        ok = np.nonzero(bst == 0)[0][:2000]
+        for i in ok:
+            assert blobs[int(bvoff[i]):int(bvoff[i]) + int(bvlen[i])].tobytes() == b.value(int(voff[i]), int(vlen[i]))
+        # the same work in series: flatten into recycled pinned buffers, then the host-buffer entry
+        h = ctypes.c_void_p()
+        ts = []
+        for it in range(a.steps + 1):
+            t0 = time.perf_counter()
+            rc = L.mptv_flatten_borsh(blobs.ctypes.data, boff.ctypes.data, n_proofs, 0, 1, ctypes.byref(h))
+            assert rc == 0
+            hb = z.crypto_ops.batch_from_handle(L, h, n_proofs)
+            t1 = time.perf_counter()
+            ver.verify_batch(hb)
+            t2 = time.perf_counter()
+            ts.append((t1 - t0, t2 - t1))
+        L.mptv_host_batch_free(h)
+        fl, vf = np.array(ts[1:]).mean(axis=0)
+        e2e_borsh = dict(value=n_proofs / dt_stream, unit=UNIT, ms_per_step=dt_stream * 1e3, borsh_bytes=int(len(blobs)),
+                         serial=dict(value=n_proofs / (fl + vf), flatten_ms=fl * 1e3, verify_batch_ms=vf * 1e3),
+                         note="mptv_verify_borsh (flatten of chunk c+1 overlaps copy + kernels of chunk c) vs "
+                              "mptv_flatten_borsh into recycled pinned buffers followed by mptv_verify_batch")
+
     # ---- roofline of the dominant kernel (K1), rank 0's device
     perm_executed = int(tm.n_unique_perm) if a.dedup else n_perm
     full_config2 = a.workload == "config2" and not a.dedup and n_proofs == 1_000_000 and a.accounts == 10_000_000
@@ -685,7 +724,7 @@ def main():
                 keccak_f_per_sec=all_perm / (ms_per_step * 1e-3),
                 kernel_ms=dict(bin=float(kavg[0]), keccak=float(kavg[1]), parse=float(kavg[2]), walk=float(kavg[3]),
                                total=float(kavg[4])),
-                roofline=roofline, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
+                roofline=roofline, e2e=e2e, e2e_borsh=e2e_borsh, gpu_launches=int(launches), clocks=clocks)
 
     if a.dedup:
         line["dedup"] = dict(unique_nodes=int(tm.n_unique_nodes), nodes=n_nodes, keccak_f_executed=int(tm.n_unique_perm),

@@ -122,6 +122,16 @@ int mptv_verify_batch(mptv_ctx* ctx, const mptv_batch* in, mptv_result* out);
  * modified.  hash_key == NULL behaves exactly like mptv_verify_batch. */
 int mptv_verify_batch_hashed_keys(mptv_ctx* ctx, const mptv_batch* in, const uint8_t* hash_key, mptv_result* out);
 
+/* borsh blobs in, verdicts out, in ONE pipelined call (the prover's input format, prover/src/bin/main.rs:41,67):
+ * blob i = blobs[blob_off[i] .. blob_off[i+1]) holds borsh(MerkleProofInput) (crypto-ops/src/types.rs:4-9).  Each
+ * pipeline chunk is flattened by `n_threads` host threads (<= 0: all cores) straight into page-locked staging,
+ * crosses PCIe as one copy and is verified while the next chunk is being flattened, so the call runs at the
+ * speed of the flattener instead of flatten + copy in series.  out->value_off[i] is the offset of the returned
+ * value INSIDE `blobs` (the value is a slice of a node, the node a slice of its blob).  A blob whose root_hash
+ * is not 32 bytes gets MPTV_ST_BAD_ROOT_LEN; a malformed blob fails the whole call with MPTV_ERR_ARG. */
+int mptv_verify_borsh(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads,
+                      mptv_result* out);
+
 /* Device-resident entry: every pointer is DEVICE memory on the context's device `dev_index`.
  * Asynchronous on `stream` (a cudaStream_t, NULL = the context's own stream for that device). */
 int mptv_verify_batch_device(mptv_ctx* ctx, int dev_index, const mptv_batch* in, mptv_result* out,
@@ -145,7 +155,8 @@ int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops
 
 /* options (name, value):
  *   "lanes_per_proof"  K2b lanes per proof: 0 = choose from nodes/proof, else 8, 16 or 32
- *   "chunk_bytes"      node bytes per pipeline chunk of the host-buffer entry
+ *   "chunk_bytes"      node bytes per pipeline chunk of the host-buffer entry (default 96 MiB)
+ *   "borsh_chunk_bytes" borsh bytes per pipeline chunk of mptv_verify_borsh (default 32 MiB)
  *   "binning"          K0 rate-block binning on / off              (default 1)
  *   "fused_classify"   K1 also classifies plain branches / leaves  (default 1)
  *   "fast_walk"        K2f thread-per-proof chain check + K2b on the deferred rest (default 1)

@@ -1,0 +1,49 @@
+"""mptv_verify_borsh (blobs in, verdicts out) on the config-2 batch: chunk size x host threads sweep, beside the
+serial flatten-then-verify.   python tools/borsh_stream_bench.py [n_proofs]      (on a B200)"""
+import ctypes
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import zk_state_proofs_b200 as z  # noqa: E402
+from workload import gen  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+sys.argv = ["bench.py", "--workload", "config2", "--proofs", str(n)]
+a = bench.parse_args()
+ver = z.Verifier([0])
+b, _ = bench.build_batch(a, 0, pinned=True)
+blobs, boff = gen.batch_to_borsh(b)
+print(f"{n} proofs, {len(blobs) / 1e9:.2f} GB of borsh, {os.cpu_count()} host cores", flush=True)
+ref = ver.verify_batch(b)
+for _ in range(2):
+    t0 = time.perf_counter(); ver.verify_batch(b); dt = time.perf_counter() - t0
+print(f"mptv_verify_batch on the pre-flattened pinned batch: {dt * 1e3:.1f} ms = {n / dt / 1e6:.2f} M proofs/s", flush=True)
+for mb in (8, 16, 24, 32, 64):
+    for th in (8, 0):
+        ver.set_option("borsh_chunk_bytes", mb << 20)
+        best = 1e9
+        for it in range(4):
+            t0 = time.perf_counter()
+            st, voff, vlen = ver.verify_borsh(blobs, boff, threads=th)
+            dt = time.perf_counter() - t0
+            if it:
+                best = min(best, dt)
+        assert (st == ref[0]).all() and (vlen == ref[2]).all()
+        print(f"chunk {mb:4d} MB threads {th or os.cpu_count():2d}: {best * 1e3:7.1f} ms = {n / best / 1e6:6.2f} M proofs/s", flush=True)
+ver.set_option("borsh_chunk_bytes", 32 << 20)
+L = z.load_library()
+h = ctypes.c_void_p()
+for it in range(3):
+    t0 = time.perf_counter()
+    assert L.mptv_flatten_borsh(blobs.ctypes.data, boff.ctypes.data, n, 0, 1, ctypes.byref(h)) == 0
+    t1 = time.perf_counter()
+    ver.verify_batch(z.crypto_ops.batch_from_handle(L, h, n))
+    t2 = time.perf_counter()
+print(f"serial: flatten {1e3 * (t1 - t0):.1f} ms + verify_batch {1e3 * (t2 - t1):.1f} ms = {n / (t2 - t0) / 1e6:.2f} M proofs/s")
+L.mptv_host_batch_free(h)

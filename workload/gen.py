@@ -36,6 +36,8 @@ def lib():
         L.mptgen_proofs_plan.argtypes = [vp, vp, vp, u64, u64, vp, vp, i32]
         L.mptgen_proofs_emit.argtypes = [vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, i32]
         L.mptgen_keccak256.argtypes = [vp, u64, vp]
+        L.mptgen_csr_to_borsh.restype = u64
+        L.mptgen_csr_to_borsh.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, i32]
         _LIB = L
     return _LIB
 
@@ -238,3 +240,17 @@ def block_tries(n_blocks: int, per_block: int = 300, kind: str = "tx", seed: int
     np.cumsum(np.tile(klen, n_tries), out=key_off[1:])
     trie_first = (np.arange(n_tries + 1, dtype=np.uint64) * per_block).astype(np.uint32)
     return z.KvBatch(key_bytes, key_off, value_bytes, value_off, lens, trie_first)
+
+
+def batch_to_borsh(b, pinned: bool = False):
+    """A CSR batch as borsh(MerkleProofInput) blobs (one uint8 array + [n + 1] uint64 offsets), the format a
+    prover's input file holds (crypto-ops/src/types.rs:4-9); input of mptv_verify_borsh / mptv_flatten_borsh."""
+    L = lib()
+    n = b.n_proofs
+    off = np.zeros(n + 1, np.uint64)
+    args = [b.node_bytes.ctypes.data, b.node_off.ctypes.data, b.node_len.ctypes.data, b.proof_first.ctypes.data, n,
+            b.roots.ctypes.data, b.key_bytes.ctypes.data, b.key_off.ctypes.data, off.ctypes.data]
+    total = int(L.mptgen_csr_to_borsh(*args, None, 1))
+    blobs = _alloc(total + 16, np.uint8, pinned)
+    L.mptgen_csr_to_borsh(*args, blobs.ctypes.data, _threads())
+    return blobs[:total], off

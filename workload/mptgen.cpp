@@ -542,4 +542,45 @@ int mptgen_proofs_emit(void* h, const int64_t* sel, const uint8_t* mut, uint64_t
 
 void mptgen_keccak256(const uint8_t* in, uint64_t len, uint8_t out[32]) { keccak256(in, len, out); }
 
+// CSR batch -> borsh(MerkleProofInput) blobs, as a prover's input file holds them (crypto-ops/src/types.rs:4-9:
+// u32-LE count / length prefixes).  blob_off [n + 1] is written first (call with blobs == NULL to size the
+// buffer: returns the total byte count), then the blobs, multi-threaded.
+uint64_t mptgen_csr_to_borsh(const uint8_t* node_bytes, const uint64_t* node_off, const uint32_t* node_len,
+                             const uint32_t* proof_first, uint64_t n_proofs, const uint8_t* roots,
+                             const uint8_t* key_bytes, const uint32_t* key_off, uint64_t* blob_off, uint8_t* blobs,
+                             int n_threads) {
+  blob_off[0] = 0;
+  for (uint64_t p = 0; p < n_proofs; p++) {
+    uint64_t sz = 4 + 4 + 32 + 4 + (uint64_t)(key_off[p + 1] - key_off[p]);
+    for (uint32_t i = proof_first[p]; i < proof_first[p + 1]; i++) sz += 4 + (uint64_t)node_len[i];
+    blob_off[p + 1] = blob_off[p] + sz;
+  }
+  if (!blobs) return blob_off[n_proofs];
+  auto put32 = [](uint8_t* q, uint32_t v) { q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16); q[3] = (uint8_t)(v >> 24); };
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  std::vector<std::thread> th;
+  const uint64_t per = (n_proofs + n_threads - 1) / n_threads;
+  for (int t = 0; t < n_threads; t++) {
+    const uint64_t lo = std::min(n_proofs, per * t), hi = std::min(n_proofs, lo + per);
+    if (lo >= hi) continue;
+    th.emplace_back([=] {
+      for (uint64_t p = lo; p < hi; p++) {
+        uint8_t* q = blobs + blob_off[p];
+        put32(q, proof_first[p + 1] - proof_first[p]); q += 4;
+        for (uint32_t i = proof_first[p]; i < proof_first[p + 1]; i++) {
+          put32(q, node_len[i]); q += 4;
+          memcpy(q, node_bytes + node_off[i], node_len[i]); q += node_len[i];
+        }
+        put32(q, 32); q += 4;
+        memcpy(q, roots + 32 * p, 32); q += 32;
+        const uint32_t kl = key_off[p + 1] - key_off[p];
+        put32(q, kl); q += 4;
+        if (kl) memcpy(q, key_bytes + key_off[p], kl);
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  return blob_off[n_proofs];
+}
+
 }  // extern "C"

@@ -279,15 +279,19 @@ def flatten_borsh(blobs: Sequence[bytes], threads: int = 0, pinned: bool = False
     rc = L.mptv_flatten_borsh(buf.ctypes.data, off.ctypes.data, n, threads, 1 if pinned else 0, ctypes.byref(h))
     if rc != 0:
         raise ValueError(f"mptv_flatten_borsh: {L.mptv_strerror(rc).decode()} (malformed borsh MerkleProofInput?)")
-    owner = _HostBatchOwner(L, h)
+    b = batch_from_handle(L, h, n)
+    b._owner = _HostBatchOwner(L, h)
+    return b
+
+
+def batch_from_handle(L, h, n: int) -> Batch:
+    """Batch view of a mptv_host_batch handle (no ownership: the caller frees or recycles the handle)."""
     v = ctypes.cast(L.mptv_host_batch_view(h), ctypes.POINTER(_CBatch)).contents
     bad = _view(L.mptv_host_batch_bad_root(h), n, np.uint8).astype(bool)
-    b = Batch(_view(v.node_bytes, v.node_bytes_len, np.uint8), _view(v.node_off, v.n_nodes, np.uint64),
-              _view(v.node_len, v.n_nodes, np.uint32), _view(v.proof_first, n + 1, np.uint32),
-              _view(v.roots, 32 * n, np.uint8), _view(v.key_bytes, int(_view(v.key_off, n + 1, np.uint32)[-1]) + 16, np.uint8),
-              _view(v.key_off, n + 1, np.uint32), None, bad if bad.any() else None)
-    b._owner = owner
-    return b
+    return Batch(_view(v.node_bytes, v.node_bytes_len, np.uint8), _view(v.node_off, v.n_nodes, np.uint64),
+                 _view(v.node_len, v.n_nodes, np.uint32), _view(v.proof_first, n + 1, np.uint32),
+                 _view(v.roots, 32 * n, np.uint8), _view(v.key_bytes, int(_view(v.key_off, n + 1, np.uint32)[-1]) + 16, np.uint8),
+                 _view(v.key_off, n + 1, np.uint32), None, bad if bad.any() else None)
 
 
 @dataclass
@@ -473,6 +477,8 @@ def load_library():
     L.mptv_status_name.argtypes = [i32]
     L.mptv_verify_batch.restype = i32
     L.mptv_verify_batch.argtypes = [vp, ctypes.POINTER(_CBatch), ctypes.POINTER(_CResult)]
+    L.mptv_verify_borsh.restype = i32
+    L.mptv_verify_borsh.argtypes = [vp, vp, vp, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(_CResult)]
     L.mptv_verify_batch_hashed_keys.restype = i32
     L.mptv_verify_batch_hashed_keys.argtypes = [vp, ctypes.POINTER(_CBatch), vp, ctypes.POINTER(_CResult)]
     L.mptv_verify_batch_device.restype = i32
@@ -596,6 +602,29 @@ class Verifier:
             status[b.bad_root_len] = 6
             voff[b.bad_root_len] = 0
             vlen[b.bad_root_len] = 0
+        return status, voff, vlen
+
+    def verify_borsh(self, blobs, blob_off=None, threads: int = 0):
+        """mptv_verify_borsh: borsh(MerkleProofInput) blobs in, verdicts out, flattening pipelined with the copies
+        and kernels.  `blobs` is a sequence of bytes objects, or one uint8 array with `blob_off` ([n + 1] uint64).
+        Returns (status, value_off, value_len); value_off indexes the CONCATENATED blobs."""
+        if blob_off is None:
+            n = len(blobs)
+            lens = np.fromiter((len(x) for x in blobs), dtype=np.int64, count=n)
+            blob_off = np.zeros(n + 1, np.uint64)
+            np.cumsum(lens, out=blob_off[1:])
+            blobs = np.frombuffer(b"".join(bytes(x) for x in blobs) + b"\0", np.uint8)
+        buf = np.ascontiguousarray(blobs, np.uint8)
+        off = np.ascontiguousarray(blob_off, np.uint64)
+        n = len(off) - 1
+        status = np.zeros(n, np.uint8)
+        voff = np.zeros(n, np.uint64)
+        vlen = np.zeros(n, np.uint32)
+        if n <= 0:
+            return status, voff, vlen
+        cr = _CResult(_ptr(status), _ptr(voff), _ptr(vlen))
+        self._check(self.lib.mptv_verify_borsh(self.ctx, buf.ctypes.data, off.ctypes.data, n, threads, ctypes.byref(cr)),
+                    "mptv_verify_borsh")
         return status, voff, vlen
 
     # -- device-resident entry: pointers are raw device addresses (ints), e.g. torch tensors' data_ptr()

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/mptv.h"
+#include "host_codec.h"
 #include "kernels.h"
 
 namespace mptv {
@@ -51,6 +52,12 @@ struct Slot {
   cudaStream_t stream = nullptr;
   HostBuf h_results, h_in;
   uint64_t pend_p0 = 0, pend_np = 0;  // results of this proof range are in flight into the staging buffers
+  // streamed borsh entry: the chunk was flattened into h_in; these locate its index arrays there, node_src maps
+  // each node back to its position in the caller's blobs (results are reported as offsets into the blobs)
+  bool pend_borsh = false;
+  size_t h_node_off = 0, h_node_len = 0, h_proof_first = 0;
+  std::vector<uint64_t> node_src;
+  std::vector<BlobShape> shapes;  // of the chunk's blobs (bad_root decides their verdict at drain time)
   DevBuf node_bytes, node_off, node_len, proof_first, roots, key_bytes, key_off, rfp;
   DevBuf results, in_pack;
   DevBuf digests, meta, order, bins, defer, dedup;
@@ -131,6 +138,7 @@ struct mptv_ctx {
   std::mutex err_mu;  // the host entries run one thread per device
   int lanes_per_proof = 0;          // 0 = auto
   uint64_t chunk_bytes = 96ull << 20;  // node bytes per pipeline chunk of the host-buffer path
+  uint64_t borsh_chunk_bytes = 32ull << 20;  // borsh bytes per chunk of mptv_verify_borsh (smaller: less exposed head / tail)
   int binning = 1;
   int fused_classify = 1;  // K1 also classifies plain branches / leaves (K2a fast path)
   int dedup_nodes = 0;     // hash each DISTINCT node once (secondary mode, reported separately)
@@ -168,6 +176,7 @@ inline void quiesce(Device& d) {
   for (Slot& s : d.slot) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     s.pend_np = 0;
+    s.pend_borsh = false;
   }
 }
 

@@ -23,6 +23,11 @@
 #include <vector>
 
 #include "../../include/mptv.h"
+#include "host_codec.h"
+
+using mptv::BlobShape;
+using mptv::borsh_shape;
+using mptv::parallel_for;
 
 struct mptv_host_batch {
   mptv_batch view;
@@ -52,48 +57,6 @@ void* host_alloc(mptv_host_batch* hb, int slot, size_t bytes) {
   }
   if (p) { hb->blocks[slot] = p; hb->cap[slot] = want; }
   return p;
-}
-
-inline bool rd_u32(const uint8_t* p, const uint8_t* end, uint32_t& v) {
-  if (end - p < 4) return false;
-  v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
-  return true;
-}
-
-struct Shape { uint32_t n_nodes; uint32_t key_len; uint64_t padded_bytes; uint8_t ok; uint8_t bad_root; };
-
-// pass 1: walk one blob, no copies
-Shape shape_of(const uint8_t* p, const uint8_t* end) {
-  Shape s = {0, 0, 0, 0, 0};
-  uint32_t n, len;
-  if (!rd_u32(p, end, n)) return s;
-  p += 4;
-  for (uint32_t i = 0; i < n; i++) {
-    if (!rd_u32(p, end, len) || (uint64_t)(end - p - 4) < len) return s;
-    p += 4 + len;
-    s.padded_bytes += ((uint64_t)len + 15) & ~15ull;
-  }
-  s.n_nodes = n;
-  if (!rd_u32(p, end, len) || (uint64_t)(end - p - 4) < len) return s;
-  s.bad_root = len != 32;
-  p += 4 + len;
-  if (!rd_u32(p, end, len) || (uint64_t)(end - p - 4) < len) return s;
-  s.key_len = len;
-  p += 4 + len;
-  s.ok = p == end;  // borsh::from_slice rejects trailing bytes
-  return s;
-}
-
-template <class F>
-void parallel_for(uint64_t n, int n_threads, F f) {
-  if (n_threads <= 1 || n < 1024) { f(0, n); return; }
-  std::vector<std::thread> th;
-  const uint64_t per = (n + n_threads - 1) / n_threads;
-  for (int t = 0; t < n_threads; t++) {
-    const uint64_t lo = std::min(n, per * t), hi = std::min(n, lo + per);
-    if (lo < hi) th.emplace_back([=] { f(lo, hi); });
-  }
-  for (auto& x : th) x.join();
 }
 
 // ---- RLP writers (alloy-rlp Encodable)
@@ -144,12 +107,12 @@ static int flatten_borsh_run(const uint8_t* blobs, const uint64_t* blob_off, uin
   mptv_host_batch* reuse = *out;  // NULL, or a handle from an earlier call whose buffers are recycled
   if (reuse && reuse->pinned != (pinned != 0)) return MPTV_ERR_ARG;
   if (n_threads <= 0) n_threads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-  std::vector<Shape> sh(n);
+  std::vector<BlobShape> sh(n);
   std::atomic<int> bad(0);
   parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi) {
     for (uint64_t i = lo; i < hi; i++) {
       if (blob_off[i + 1] < blob_off[i]) { bad = 1; continue; }
-      sh[i] = shape_of(blobs + blob_off[i], blobs + blob_off[i + 1]);
+      sh[i] = borsh_shape(blobs + blob_off[i], blobs + blob_off[i + 1]);
       if (!sh[i].ok) bad = 1;
     }
   });
@@ -185,24 +148,13 @@ static int flatten_borsh_run(const uint8_t* blobs, const uint64_t* blob_off, uin
   // pass 2: copy
   parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi) {
     for (uint64_t i = lo; i < hi; i++) {
-      const uint8_t* p = blobs + blob_off[i] + 4;
-      uint64_t k = node_first[i], o = byte_first[i];
-      proof_first[i] = (uint32_t)k;
-      for (uint32_t j = 0; j < sh[i].n_nodes; j++) {
-        const uint32_t len = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
-        memcpy(node_bytes + o, p + 4, len);
-        const uint64_t pad = (((uint64_t)len + 15) & ~15ull) - len;
-        if (pad) memset(node_bytes + o + len, 0, pad);
-        node_off[k] = o; node_len[k] = len;
-        k++; o += len + pad; p += 4 + len;
-      }
-      const uint32_t rl = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
-      if (rl == 32) memcpy(roots + 32 * i, p + 4, 32); else memset(roots + 32 * i, 0, 32);
-      hb->bad_root[i] = rl != 32;
-      p += 4 + rl;
+      proof_first[i] = (uint32_t)node_first[i];
       key_off[i] = (uint32_t)key_first[i];
-      memcpy(key_bytes + key_first[i], p + 4, sh[i].key_len);
+      hb->bad_root[i] = sh[i].bad_root;
+      mptv::borsh_copy(blobs + blob_off[i], sh[i], node_bytes, byte_first[i], node_off, node_len, node_first[i],
+                       roots + 32 * i, key_bytes + key_first[i], nullptr, blobs);
     }
+    _mm_sfence();  // the nodes were written with non-temporal stores
   });
   hb->view.node_bytes = node_bytes; hb->view.node_bytes_len = nb;
   hb->view.node_off = node_off; hb->view.node_len = node_len; hb->view.n_nodes = nn;

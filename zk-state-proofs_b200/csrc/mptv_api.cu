@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "ctx.h"
+#include "host_codec.h"
 
 using namespace mptv;
 
@@ -194,6 +195,9 @@ int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
   } else if (!strcmp(name, "chunk_bytes")) {
     if (value < (1 << 16)) return MPTV_ERR_ARG;
     ctx->chunk_bytes = (uint64_t)value;
+  } else if (!strcmp(name, "borsh_chunk_bytes")) {
+    if (value < (1 << 12)) return MPTV_ERR_ARG;
+    ctx->borsh_chunk_bytes = (uint64_t)value;
   } else if (!strcmp(name, "binning")) {
     ctx->binning = value ? 1 : 0;
   } else if (!strcmp(name, "fused_classify")) {
@@ -468,9 +472,213 @@ int run_slice(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result* out, 
   return rc;
 }
 
+// ------------------------------------------------------------------ streamed borsh entry
+// borsh blobs -> verdicts in one pipeline: a chunk is sized by its blob bytes, walked (pass 1: shapes) and
+// copied (pass 2: non-temporal stores) by a pool of host threads straight into the slot's page-locked block,
+// crosses PCIe as ONE copy, runs the device pipeline, and its results come back while the host is already
+// flattening the next chunk into the next slot.
+struct BorshStream {
+  const uint8_t* blobs;
+  const uint64_t* blob_off;
+};
+
+int drain_slot_borsh(mptv_ctx* ctx, Slot& s, mptv_result* out, WorkerPool& pool) {
+  CK(cudaStreamSynchronize(s.stream));
+  if (!s.pend_np) return MPTV_OK;
+  const uint64_t np = s.pend_np;
+  const uint8_t* r = static_cast<const uint8_t*>(s.h_results.p);
+  const uint64_t* voff = reinterpret_cast<const uint64_t*>(r);
+  const uint32_t* vlen = reinterpret_cast<const uint32_t*>(r + 8 * np);
+  const uint8_t* status = r + 12 * np;
+  const uint8_t* h = static_cast<const uint8_t*>(s.h_in.p);
+  const uint64_t* node_off = reinterpret_cast<const uint64_t*>(h + s.h_node_off);
+  const uint32_t* node_len = reinterpret_cast<const uint32_t*>(h + s.h_node_len);
+  const uint32_t* proof_first = reinterpret_cast<const uint32_t*>(h + s.h_proof_first);
+  const int T = pool.size();
+  const uint64_t per = (np + T - 1) / T;
+  pool.run([&](int t) {
+    const uint64_t lo = std::min(np, per * t), hi = std::min(np, lo + per);
+    for (uint64_t i = lo; i < hi; i++) {
+      const uint64_t p = s.pend_p0 + i;
+      uint8_t st = status[i];
+      uint64_t vo = 0;
+      uint32_t vl = 0;
+      if (s.shapes[i].bad_root) st = MPTV_ST_BAD_ROOT_LEN;  // the guests' try_into().unwrap() comes first
+      else if (st == MPTV_ST_OK) {
+        // the value is a slice of one node of this proof: report it as a slice of the caller's blobs
+        vl = vlen[i];
+        for (uint32_t k = proof_first[i]; k < proof_first[i + 1]; k++)
+          if (node_off[k] <= voff[i] && voff[i] + vl <= node_off[k] + node_len[k]) {
+            vo = s.node_src[k] + (voff[i] - node_off[k]);
+            break;
+          }
+      }
+      out->status[p] = st; out->value_off[p] = vo; out->value_len[p] = vl;
+    }
+  });
+  s.pend_np = 0;
+  s.pend_borsh = false;
+  return MPTV_OK;
+}
+
+int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv_result* out, uint64_t p0, uint64_t p1,
+                           WorkerPool& pool) {
+  if (p1 <= p0) return MPTV_OK;
+  CK(cudaSetDevice(d.id));
+  const int T = pool.size();
+  struct Tot { uint64_t nodes, bytes, keys; };
+  std::vector<Tot> tot(T);
+  size_t ci = 0;
+  for (uint64_t cs = p0; cs < p1; ci++) {
+    // the chunk: as many blobs as fit borsh_chunk_bytes of input (the arena is within a few % of that)
+    uint64_t ce = (uint64_t)(std::upper_bound(in.blob_off + cs + 1, in.blob_off + p1 + 1, in.blob_off[cs] + ctx->borsh_chunk_bytes) -
+                             in.blob_off);
+    if (ce > cs + 1) ce--;
+    if (ce > p1) ce = p1;
+    Slot& s = d.slot[ci % kSlots];
+    cudaStream_t st = s.stream;
+    int rc = drain_slot_borsh(ctx, s, out, pool);
+    if (rc != MPTV_OK) return rc;
+    const uint64_t np = ce - cs;
+    if (s.shapes.size() < np) s.shapes.resize(np + np / 8);
+    // shared between the workers of this chunk
+    std::atomic<int> bad(0);
+    int err = MPTV_OK;
+    size_t o_bytes = 0, o_off = 0, o_len = 0, o_pf = 0, o_roots = 0, o_keys = 0, o_koff = 0, total = 0;
+    uint64_t nn = 0, nbytes = 0, kbytes = 0;
+    const uint64_t per = (np + T - 1) / T;
+    pool.run([&](int t) {
+      const uint64_t lo = std::min(np, per * t), hi = std::min(np, lo + per);
+      // pass 1: shapes of my blobs
+      Tot my = {0, 0, 0};
+      for (uint64_t i = lo; i < hi; i++) {
+        const uint64_t p = cs + i;
+        BlobShape sh = {0, 0, 0, 0, 0};
+        if (in.blob_off[p + 1] >= in.blob_off[p]) sh = borsh_shape(in.blobs + in.blob_off[p], in.blobs + in.blob_off[p + 1]);
+        if (!sh.ok) bad.store(1, std::memory_order_relaxed);
+        s.shapes[i] = sh;
+        my.nodes += sh.n_nodes; my.bytes += sh.padded_bytes; my.keys += sh.key_len;
+      }
+      tot[t] = my;
+      pool.barrier();
+      if (t == 0) {  // totals -> layout of the packed block (same on host and device) -> buffers
+        for (int k = 0; k < T; k++) { nn += tot[k].nodes; nbytes += tot[k].bytes; kbytes += tot[k].keys; }
+        if (bad.load() || nn > 0xfffffff0ull || kbytes > 0xfffffff0ull) err = MPTV_ERR_ARG;
+        else {
+          size_t o = 0;
+          auto take = [&](size_t bytes) { const size_t at = o; o += up16(bytes); return at; };
+          o_bytes = take(nbytes + 16); o_off = take(8 * nn); o_len = take(4 * nn); o_pf = take(4 * (np + 1));
+          o_roots = take(32 * np); o_keys = take(kbytes + 16); o_koff = take(4 * (np + 1));
+          total = o;
+          if (s.h_in.reserve(total) != cudaSuccess || s.in_pack.reserve(total) != cudaSuccess) {
+            cudaGetLastError();
+            err = MPTV_ERR_NOMEM;
+          } else if (s.node_src.size() < nn) s.node_src.resize(nn + nn / 8);
+        }
+      }
+      pool.barrier();
+      if (err != MPTV_OK) return;
+      // pass 2: copy my blobs
+      uint64_t k = 0, ob = 0, ok = 0;
+      for (int q = 0; q < t; q++) { k += tot[q].nodes; ob += tot[q].bytes; ok += tot[q].keys; }
+      uint8_t* h = static_cast<uint8_t*>(s.h_in.p);
+      uint64_t* node_off = reinterpret_cast<uint64_t*>(h + o_off);
+      uint32_t* node_len = reinterpret_cast<uint32_t*>(h + o_len);
+      uint32_t* proof_first = reinterpret_cast<uint32_t*>(h + o_pf);
+      uint32_t* key_off = reinterpret_cast<uint32_t*>(h + o_koff);
+      for (uint64_t i = lo; i < hi; i++) {
+        const BlobShape& sh = s.shapes[i];
+        proof_first[i] = (uint32_t)k;
+        key_off[i] = (uint32_t)ok;
+        borsh_copy(in.blobs + in.blob_off[cs + i], sh, h + o_bytes, ob, node_off, node_len, k, h + o_roots + 32 * i,
+                   h + o_keys + ok, s.node_src.data(), in.blobs);
+        k += sh.n_nodes; ob += sh.padded_bytes; ok += sh.key_len;
+      }
+      _mm_sfence();  // the nodes were written with non-temporal stores; the DMA engine reads them next
+    });
+    if (err == MPTV_ERR_ARG) return fail_msg(ctx, err, "mptv_verify_borsh: a blob is not a well-formed borsh(MerkleProofInput)");
+    if (err != MPTV_OK) return fail_msg(ctx, err, "mptv_verify_borsh: staging allocation failed");
+    uint8_t* h = static_cast<uint8_t*>(s.h_in.p);
+    uint8_t* dv = s.in_pack.as<uint8_t>();
+    reinterpret_cast<uint32_t*>(h + o_pf)[np] = (uint32_t)nn;
+    reinterpret_cast<uint32_t*>(h + o_koff)[np] = (uint32_t)kbytes;
+    memset(h + o_bytes + nbytes, 0, 16);
+    memset(h + o_keys + kbytes, 0, 16);
+    CK(cudaMemcpyAsync(dv, h, total, cudaMemcpyHostToDevice, st));
+    DeviceBatch b;
+    b.node_bytes = dv + o_bytes; b.node_off = reinterpret_cast<const uint64_t*>(dv + o_off);
+    b.node_len = reinterpret_cast<const uint32_t*>(dv + o_len);
+    b.proof_first = reinterpret_cast<const uint32_t*>(dv + o_pf); b.roots = dv + o_roots;
+    b.key_bytes = dv + o_keys; b.key_off = reinterpret_cast<const uint32_t*>(dv + o_koff);
+    b.root_from_proof = nullptr;
+    b.n_nodes = nn; b.n_proofs = np;
+    b.byte_base = 0; b.node_base = 0; b.key_base = 0; b.proof_base = 0;
+    CK(s.results.reserve(13 * np + 16));
+    CK(s.h_results.reserve(13 * np + 16));
+    uint8_t* res = s.results.as<uint8_t>();
+    rc = run_pipeline(ctx, d, b, s.digests, s.meta, s.order, s.bins, s.defer, s.dedup, res + 12 * np,
+                      reinterpret_cast<uint64_t*>(res), reinterpret_cast<uint32_t*>(res + 8 * np), st, false);
+    if (rc != MPTV_OK) return rc;
+    CK(cudaMemcpyAsync(s.h_results.p, res, 13 * np, cudaMemcpyDeviceToHost, st));
+    s.pend_p0 = cs; s.pend_np = np; s.pend_borsh = true;
+    s.h_node_off = o_off; s.h_node_len = o_len; s.h_proof_first = o_pf;
+    cs = ce;
+  }
+  for (int k = 0; k < kSlots; k++) {
+    const int rc = drain_slot_borsh(ctx, d.slot[k], out, pool);
+    if (rc != MPTV_OK) return rc;
+  }
+  return MPTV_OK;
+}
+
+int run_slice_borsh(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv_result* out, uint64_t p0, uint64_t p1, int n_threads) {
+  WorkerPool pool(n_threads);
+  const int rc = run_slice_borsh_chunks(ctx, d, in, out, p0, p1, pool);
+  if (rc != MPTV_OK) quiesce(d);
+  return rc;
+}
+
+int verify_borsh_run(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, mptv_result* out) {
+  if (!ctx || !out) return MPTV_ERR_ARG;
+  if (n == 0) return MPTV_OK;
+  if (!blobs || !blob_off || !out->status || !out->value_off || !out->value_len) return MPTV_ERR_ARG;
+  for (uint64_t i = 0; i < n; i++)
+    if (blob_off[i + 1] < blob_off[i]) return MPTV_ERR_ARG;  // the chunking below searches the offsets
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  const BorshStream in = {blobs, blob_off};
+  const int nd = (int)ctx->dev.size();
+  std::vector<uint64_t> cut(nd + 1, 0);
+  cut[nd] = n;
+  const uint64_t total = blob_off[n] - blob_off[0];
+  for (int k = 1; k < nd; k++)
+    cut[k] = (uint64_t)(std::lower_bound(blob_off, blob_off + n + 1, blob_off[0] + total / nd * k) - blob_off);
+  for (int k = 1; k <= nd; k++) if (cut[k] < cut[k - 1]) cut[k] = cut[k - 1];
+  std::vector<int> rcs(nd, MPTV_OK);
+  if (nd == 1) {
+    rcs[0] = run_slice_borsh(ctx, ctx->dev[0], in, out, cut[0], cut[1], n_threads);
+  } else {
+    std::vector<std::thread> th;
+    const int per = std::max(1, n_threads / nd);
+    for (int k = 0; k < nd; k++)
+      th.emplace_back([&, k] { rcs[k] = run_slice_borsh(ctx, ctx->dev[k], in, out, cut[k], cut[k + 1], per); });
+    for (auto& t : th) t.join();
+  }
+  for (int k = 0; k < nd; k++) if (rcs[k] != MPTV_OK) return rcs[k];
+  return MPTV_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+int mptv_verify_borsh(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads,
+                      mptv_result* out) {
+  try {  // host tables sized by n; the C ABI never throws
+    return verify_borsh_run(ctx, blobs, blob_off, n, n_threads, out);
+  } catch (...) {
+    return MPTV_ERR_NOMEM;
+  }
+}
 
 int mptv_verify_batch(mptv_ctx* ctx, const mptv_batch* in, mptv_result* out) {
   if (!ctx || !in || !out) return MPTV_ERR_ARG;
