@@ -142,6 +142,9 @@ class Verifier {
       blobs.insert(blobs.end(), b.begin(), b.end());
       off[i + 1] = blobs.size();
     }
+    // Large plain batches go through the streamed entry: blobs in, verdicts out, the flattening of one chunk
+    // overlapping the copy and the kernels of the previous ones
+    if (!root_from_proof && blobs.size() > (8u << 20)) return verify_borsh(blobs.data(), off.data(), inputs.size());
     // Large batches are flattened straight into PAGE-LOCKED buffers (kept and recycled across calls): the
     // host-buffer entry then streams them at PCIe speed (a copy from pageable memory runs ~5x slower).
     // Small ones stay pageable: mptv_verify_batch packs them into its own pinned staging block anyway.
@@ -162,6 +165,22 @@ class Verifier {
     for (size_t p = 0; p < n; p++) {
       out[p].status = bad[p] ? MPTV_ST_BAD_ROOT_LEN : status[p];
       if (out[p].ok()) out[p].value.assign(b.node_bytes + voff[p], b.node_bytes + voff[p] + vlen[p]);
+    }
+    return out;
+  }
+
+  // borsh(MerkleProofInput) blobs (blob i = blobs[off[i] .. off[i+1])) -> outcomes, through mptv_verify_borsh
+  std::vector<Outcome> verify_borsh(const uint8_t* blobs, const uint64_t* off, size_t n) {
+    std::vector<Outcome> out(n);
+    if (n == 0) return out;
+    std::vector<uint8_t> status(n);
+    std::vector<uint64_t> voff(n);
+    std::vector<uint32_t> vlen(n);
+    mptv_result r{status.data(), voff.data(), vlen.data()};
+    check(mptv_verify_borsh(ctx_, blobs, off, n, 0, &r), "mptv_verify_borsh");
+    for (size_t p = 0; p < n; p++) {
+      out[p].status = status[p];
+      if (out[p].ok()) out[p].value.assign(blobs + voff[p], blobs + voff[p] + vlen[p]);  // a slice of the blob itself
     }
     return out;
   }

@@ -37,6 +37,7 @@ extern "C" {
     fn mptv_strerror(err: c_int) -> *const c_char;
     fn mptv_verify_batch(ctx: *mut MptvCtx, input: *const MptvBatch, out: *mut MptvResult) -> c_int;
     fn mptv_verify_batch_hashed_keys(ctx: *mut MptvCtx, input: *const MptvBatch, hash_key: *const u8, out: *mut MptvResult) -> c_int;
+    fn mptv_verify_borsh(ctx: *mut MptvCtx, blobs: *const u8, blob_off: *const u64, n: u64, n_threads: c_int, out: *mut MptvResult) -> c_int;
     fn mptv_flatten_borsh(blobs: *const u8, blob_off: *const u64, n: u64, n_threads: c_int, pinned: c_int, out: *mut *mut MptvHostBatch) -> c_int;
     fn mptv_host_batch_view(hb: *const MptvHostBatch) -> *const MptvBatch;
     fn mptv_host_batch_bad_root(hb: *const MptvHostBatch) -> *const u8;
@@ -103,6 +104,26 @@ impl Verifier {
     /// The batched entry of the north star: `verify_merkle_proofs(&[MerkleProofInput])`.
     pub fn verify_merkle_proofs(&mut self, inputs: &[MerkleProofInput]) -> Vec<Result<Vec<u8>, VerifyError>> {
         self.run(inputs, None, None)
+    }
+
+    /// The same for inputs that already exist as borsh blobs (the prover's input file, prover/src/bin/main.rs:41,67):
+    /// blob i = `blobs[off[i]..off[i + 1]]`.  One pipelined call: a chunk is flattened while the previous ones are
+    /// copied and verified; every value comes back as a slice of `blobs`.
+    pub fn verify_borsh_blobs(&mut self, blobs: &[u8], off: &[u64]) -> Vec<Result<Vec<u8>, VerifyError>> {
+        let n = off.len().saturating_sub(1);
+        if n == 0 {
+            return Vec::new();
+        }
+        let (mut status, mut voff, mut vlen) = (vec![0u8; n], vec![0u64; n], vec![0u32; n]);
+        let mut res = MptvResult { status: status.as_mut_ptr(), value_off: voff.as_mut_ptr(), value_len: vlen.as_mut_ptr() };
+        let rc = unsafe { mptv_verify_borsh(self.ctx, blobs.as_ptr(), off.as_ptr(), n as u64, 0, &mut res) };
+        assert_eq!(rc, 0, "mptv_verify_borsh failed (malformed borsh?)");
+        (0..n)
+            .map(|p| match VerifyError::from_status(status[p]) {
+                None => Ok(blobs[voff[p] as usize..voff[p] as usize + vlen[p] as usize].to_vec()),
+                Some(e) => Err(e),
+            })
+            .collect()
     }
 
     /// `root_from_proof[p] = d >= 0`: proof p is verified under the storage_root of the account returned by the

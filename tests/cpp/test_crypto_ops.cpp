@@ -129,6 +129,40 @@ static void test_transaction_proof_roundtrip() {
   CHECK(o.size() == 1 && o[0].status == MPTV_ST_KEY_NOT_FOUND);
 }
 
+// the batched entry on a batch large enough for the streamed borsh path (> 8 MB of blobs): every tx of 40 blocks
+// proven and verified, plus one absent index per block, against the element-wise answers
+static void test_large_batch_takes_the_streamed_path() {
+  crypto_ops::Verifier& v = crypto_ops::default_verifier();
+  std::vector<crypto_ops::MerkleProofInput> inputs;
+  std::vector<Bytes> want;
+  uint64_t s = 1234567;
+  for (int blk = 0; blk < 40; blk++) {
+    std::vector<Bytes> txs;
+    for (int i = 0; i < 150; i++) {
+      Bytes t(300 + (i * 53 + blk * 7) % 900, 0);
+      for (auto& b : t) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; b = (uint8_t)s; }
+      t[0] = 0x02;
+      txs.push_back(t);
+    }
+    for (uint32_t target = 0; target <= 150; target++) {  // 150 is absent
+      inputs.push_back(trie_utils::transaction_proof_inputs(v, txs, target));
+      want.push_back(target < 150 ? txs[target] : Bytes{});
+    }
+  }
+  size_t blob_bytes = 0;
+  for (auto& in : inputs) blob_bytes += in.to_borsh().size();
+  CHECK(blob_bytes > (8u << 20));
+  std::vector<crypto_ops::Outcome> o = v.verify_merkle_proofs(inputs);
+  CHECK(o.size() == inputs.size());
+  for (size_t i = 0; i < o.size(); i++) {
+    if (want[i].empty()) CHECK(o[i].status == MPTV_ST_KEY_NOT_FOUND);
+    else CHECK(o[i].ok() && o[i].value == want[i]);
+  }
+  inputs[5].root_hash.pop_back();  // 31-byte root: the guests' try_into().unwrap()
+  o = v.verify_merkle_proofs(inputs);
+  CHECK(o[5].status == MPTV_ST_BAD_ROOT_LEN && o[4].ok() && o[6].ok());
+}
+
 int main(int argc, char** argv) {
   const std::string mode = argc > 1 ? argv[1] : "--cpu";
   test_encode_receipt();
@@ -137,6 +171,7 @@ int main(int argc, char** argv) {
   if (mode == "--gpu") {
     test_verify_merkle_proof_known_answers();
     test_transaction_proof_roundtrip();
+    test_large_batch_takes_the_streamed_path();
   }
   printf("%s: %d failure(s)\n", mode.c_str(), g_fail);
   return g_fail ? 1 : 0;
