@@ -36,6 +36,17 @@ def test_one_context_two_devices_matches_one_device(verifier):
     for x, y in zip(one, got):
         assert (x == y).all()
     assert (two.trie_roots(kv) == verifier.trie_roots(kv)).all()
+    # the streamed borsh entry over two devices (blobs cut by bytes, one host thread pool per device)
+    from workload import gen
+    acc = gen.account_batch(gen.SynthTrie(300_000, 2, kind=0), 30_000, seed=5)
+    blobs, off = gen.batch_to_borsh(acc)
+    two.set_option("borsh_chunk_bytes", 2 << 20)
+    s1, o1, l1 = verifier.verify_borsh(blobs, off)
+    s2, o2, l2 = two.verify_borsh(blobs, off)
+    assert (s1 == s2).all() and (o1 == o2).all() and (l1 == l2).all() and (s1 == 0).all()
+    ref = verifier.verify_batch(acc)
+    for i in range(0, acc.n_proofs, 97):
+        assert blobs[int(o2[i]):int(o2[i]) + int(l2[i])].tobytes() == acc.value(int(ref[1][i]), int(ref[2][i]))
     two.close()
 
 
