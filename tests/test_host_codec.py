@@ -85,3 +85,21 @@ def test_property_borsh_roundtrip_and_flatten_agree():
         assert (gb == wb).all()
 
     check()
+
+
+def test_host_pool_nt_copy_and_borsh_walkers_cpp(tmp_path):
+    """tests/cpp/test_host_pool.cpp: the worker pool + barrier behind mptv_verify_borsh (also under
+    -fsanitize=thread when the toolchain has it), the non-temporal node copy, the borsh walkers."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tests", "cpp", "test_host_pool.cpp")
+    exe = str(tmp_path / "test_host_pool")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-pthread", src, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    tsan = str(tmp_path / "test_host_pool_tsan")
+    if subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-pthread", src, "-o", tsan],
+                      capture_output=True).returncode == 0:
+        r = subprocess.run([tsan], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, r.stdout + r.stderr
