@@ -109,7 +109,7 @@ def test_separate_contexts_from_separate_threads(golden):
 
 def test_large_fuzz_corpus_matches_oracle(verifier, oracle):
     """40 k generated + mutated + malformed + deeply nested + corrupted-and-re-sealed cases (oracle/fuzzgen.py), GPU
-    verdict and value == C restatement (which agrees with the reference ELF on 15 M such cases, profiles/r01_fuzz_oracle_vs_elf.txt)"""
+    verdict and value == C restatement (which agrees with the reference ELF on 27 M such cases, profiles/r01_fuzz_oracle_vs_elf.txt)"""
     import zk_state_proofs_b200 as z
     from oracle.fuzzgen import corpus
     cases = corpus(777, oracle.keccak256, 150, 8000, 12000, 8000, 12000, 2000)
