@@ -345,6 +345,79 @@ def nested_cases(rng: random.Random, keccak, n: int):
     return out
 
 
+def deep_nested_cases(rng: random.Random, keccak, n: int, depths=(64, 65, 100, 128, 129, 200, 500, 1000, 2000)):
+    """Inline nodes nested 64 ... 2 000 levels deep (built bottom-up, no recursion): mostly inline branches -- the
+    levels that need a decode frame each -- with inline extensions mixed in (the decoder's tail calls), decorated
+    siblings (hash references, inline leaves, small nested branches) and, with probability `corrupt`, ONE decode
+    fault planted at a random level in a slot before or after the nested child, so that it is met on the way down
+    or only after the decoder has unwound from the full depth below it.  The reference accepts any depth."""
+    out = []
+    for it in range(n):
+        depth = depths[it % len(depths)] + rng.choice([0, 0, 1, -1, 7])
+        corrupt_level = rng.randrange(depth) if rng.random() < 0.45 else -1
+        corrupt_after = rng.random() < 0.6
+        as_root = rng.random() < 0.15
+        # bottom leaf
+        nlevels = depth
+        kinds = [("ext" if rng.random() < 0.12 else "branch") for _ in range(nlevels)]
+        ext_nibs = {lvl: [rng.randrange(16) for _ in range(rng.randint(1, 2))] for lvl in range(nlevels) if kinds[lvl] == "ext"}
+        above = (0 if as_root else 1) + sum(1 for k in kinds if k == "branch") + sum(len(v) for v in ext_nibs.values())
+        path_below = []  # nibbles from the current node down to the value
+        n_leaf = rng.randint(0, 3)
+        if (above + n_leaf) & 1:
+            n_leaf += 1  # the whole key is byte aligned
+        nib = [rng.randrange(16) for _ in range(n_leaf)]
+        val = rng.choice([b"\x05", b"\xcc", b"", rng.randbytes(3), rng.randbytes(20)])
+        hp = bytearray(hex_prefix(nib, True))
+        if corrupt_level == -2:
+            hp[0] = (hp[0] & 0x0F) | 0x40
+        node = rlp_list([rlp_str(bytes(hp)), rlp_str(val)])
+        path_below = list(nib)
+        for lvl in range(nlevels - 1, -1, -1):
+            if kinds[lvl] == "ext":
+                en = ext_nibs[lvl]
+                if lvl == corrupt_level and rng.random() < 0.3:
+                    en = []  # empty extension path: a raw panic in the reference
+                node = rlp_list([rlp_str(hex_prefix(en, False)), node])
+                path_below = en + path_below
+                continue
+            slot = rng.randrange(16)
+            slots = []
+            for i in range(16):
+                if i == slot:
+                    slots.append(node)
+                    continue
+                r = rng.random()
+                if lvl == corrupt_level and ((i > slot) == corrupt_after) and rng.random() < 0.5:
+                    slots.append(rng.choice([rlp_str(rng.randbytes(31)), rlp_str(rng.randbytes(33)), rlp_list([b"\x01", b"\x02", b"\x03"]),
+                                             rlp_list([rlp_str(b"\x45\x01"), rlp_str(b"v")]), rlp_list([rlp_str(b""), rlp_str(b"v")])]))
+                elif r < 0.93: slots.append(b"\x80")
+                elif r < 0.96: slots.append(rlp_str(rng.randbytes(32)))
+                elif r < 0.99: slots.append(_inline_leaf(rng, True))
+                else: slots.append(_nested(rng, 2, 0, 0.0)[0])
+            bval = b"\x80" if rng.random() < 0.97 else rlp_str(rng.randbytes(rng.randint(1, 9)))
+            node = rlp_list(slots + [bval])
+            path_below = [slot] + path_below
+        if as_root:
+            proof, root, nibs = [node], keccak(node), path_below
+        else:
+            slot = rng.randrange(16)
+            slots = [b"\x80"] * 16
+            slots[slot] = rlp_str(keccak(node))
+            rootn = rlp_list(slots + [b"\x80"])
+            proof, root, nibs = [rootn, node], keccak(rootn), [slot] + path_below
+        if len(nibs) & 1:
+            nibs = nibs + [rng.randrange(16)]
+        key = bytes((nibs[i] << 4) | nibs[i + 1] for i in range(0, len(nibs), 2))
+        r = rng.random()
+        if r < 0.12 and key:   # a neighbouring key: leaves the path somewhere inside the nesting
+            k = bytearray(key); i = rng.randrange(len(k)); k[i] ^= 1 << rng.randrange(8); key = bytes(k)
+        elif r < 0.16:
+            key = key[:-1]
+        out.append(dict(root=root, proof=proof, key=key, tag=f"deep/{'root' if as_root else 'child'}-{depth}"))
+    return out
+
+
 def resealed_cases(rng: random.Random, keccak, base, n: int):
     """Corrupt ONE node of a valid root-first proof at the byte level (bit flips, inserted / deleted / overwritten
     bytes, truncation) and then RE-SEAL the chain: every ancestor gets the corrupted child's new hash and the

@@ -50,11 +50,6 @@ def test_golden_vectors_from_reference_elf(verifier, golden, lanes, walk_mode):
     for v, r in zip(vs, res):
         got_status = r.status if isinstance(r, z.VerifyPanic) else 0
         got_value = None if isinstance(r, z.VerifyPanic) else r
-        if v["tag"].startswith("deviation/"):
-            # the documented nesting limit: the reference accepts, oracle and GPU do not
-            if got_status != 3:
-                bad.append((v["tag"], got_status, 3))
-            continue
         if got_status != v["status"] or got_value != v["value_b"]:
             bad.append((v["tag"], got_status, v["status"]))
     verifier.set_option("lanes_per_proof", 0)

@@ -14,10 +14,9 @@ constexpr int kBinNodesPerBlock = 4096;  // nodes handled by one CTA of the binn
 constexpr int kKeccakThreads = 128;      // K1 CTA size: one node per thread
 constexpr int kKeccakMinBlocks = 4;      // resident CTAs / SM  (=> <= 128 registers / thread)
 
-// K2a DFS stack.  Inline extensions chain as tail calls (no stack); inline nodes under a BRANCH nested
-// deeper than this -- >= 1.1 KB of purpose-built bytes, an inline node being < 32 bytes in any real trie --
-// are rejected as InvalidData where the reference would recurse on (same rule in oracle/mpt_oracle.c).
-constexpr int kMaxInlineDepth = 64;
+// K2a keeps this many DFS frames (a window over the innermost levels; deeper nests are re-walked from the top of
+// the node when the decode returns past the window -- verify_kernels.cu replay_frames).  Power of two.
+constexpr int kInlineWindow = 64;
 
 // verdict classes, 1:1 with the reference's outcomes (include/mptv.h MPTV_ST_*)
 enum : uint32_t {
@@ -50,6 +49,7 @@ struct DeviceBatch {
   const uint8_t* roots;
   const uint8_t* key_bytes;
   const uint32_t* key_off;
+  const uint32_t* key_len;         // null: key p = [key_off[p], key_off[p+1]); else key_len[p] bytes at key_off[p] (keys placed freely)
   const int32_t* root_from_proof;  // may be null
   // slice view of a larger CSR (host-buffer pipeline): the arrays above hold the slice, but their
   // VALUES are still global indices / offsets; these bases translate them.  All 0 for a whole batch.

@@ -86,6 +86,43 @@ __device__ __forceinline__ bool value_item_canonical(const Hdr& t) {
   return !t.is_list && !(t.hdr_len == 1 && t.payload_len == 1);
 }
 
+// The DFS keeps the most recent kInlineWindow frames (a circular window indexed by absolute depth).  Inline
+// extensions chain as tail calls and use no frame; only inline nodes under a BRANCH do.  When the walk returns to a
+// frame that has fallen out of the window -- inline branches nested deeper than 64 levels: >= 1.1 KB of
+// purpose-built bytes, an inline node being < 32 bytes in any real trie -- the window is rebuilt by walking down
+// again from the top of the node along the path to the child that just ended (`cend` = its end).  Every list on
+// that path was validated on the way down, so the replay only skips over sibling headers: 17 header decodes a level,
+// once per 64 levels of unwinding.  No depth limit, no scratch memory: the reference recurses without a limit too
+// (and is itself quadratic in the depth).
+__device__ int replay_frames(const uint8_t* p, const Hdr& top, uint32_t cend, Frame* st, int& base) {
+  uint32_t lst = 0;
+  Hdr lh = top;
+  int d = 0;
+  for (;;) {
+    const int cnt = scan_items(p, lst, lh);  // 2 or 17: validated when the walk first came through here
+    const uint32_t lend = lst + lh.hdr_len + lh.payload_len;
+    uint32_t q = lst + lh.hdr_len, e = q, idx = 0;
+    Hdr t;
+    for (;; idx++) {  // the item that contains byte cend - 1
+      rlp_hdr(p + q, lend - q, t);
+      e = q + t.hdr_len + t.payload_len;
+      if (cend <= e) break;
+      q = e;
+    }
+    if (cnt == 17) {
+      // a branch on the path: its frame as it was when the walk descended into this child
+      Frame& f = st[d & (kInlineWindow - 1)];
+      f.pos = e; f.end = lend; f.cnt = 17; f.idx = (uint8_t)(idx + 1); f.leaf = 0; f.top = lst == 0 ? 1 : 0;
+      if (e == cend) break;  // ... and this one is the parent of the child that ended
+      d++;
+    }
+    lst = q;  // descend (a 2-item list is an extension: its child shares the frame, the depth stays)
+    lh = t;
+  }
+  base = d >= kInlineWindow ? d - kInlineWindow + 1 : 0;
+  return d;
+}
+
 __device__ uint32_t parse_node(const uint8_t* p, uint32_t n) {
   Hdr h;
   if (!rlp_hdr(p, n, h)) return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);
@@ -100,8 +137,8 @@ __device__ uint32_t parse_node(const uint8_t* p, uint32_t n) {
     }
     return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);
   }
-  Frame st[kMaxInlineDepth];
-  int sp = 0;
+  Frame st[kInlineWindow];
+  int depth = 0, base = 0;  // absolute depth of the current frame / of the oldest frame still in the window
   {
     int c = scan_items(p, 0, h);
     if (c != 2 && c != 17) return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);
@@ -110,9 +147,15 @@ __device__ uint32_t parse_node(const uint8_t* p, uint32_t n) {
   }
   uint32_t top_kind = st[0].cnt == 17 ? kKindBranch : kKindExt;
   uint32_t mask = 0, fast = st[0].cnt == 17 ? 1u : 0u;
-  while (sp >= 0) {
-    Frame& f = st[sp];
-    if (f.idx == f.cnt) { sp--; continue; }
+  for (;;) {
+    Frame& f = st[depth & (kInlineWindow - 1)];
+    if (f.idx == f.cnt) {
+      if (depth == 0) break;
+      const uint32_t cend = f.end;  // the list that just ended
+      depth--;
+      if (depth < base) depth = replay_frames(p, h, cend, st, base);
+      continue;
+    }
     Hdr t;
     rlp_hdr(p + f.pos, f.end - f.pos, t);  // validated by scan_items
     const uint32_t item = f.pos;
@@ -154,15 +197,14 @@ __device__ uint32_t parse_node(const uint8_t* p, uint32_t n) {
         int c = scan_items(p, item, t);
         if (c != 2 && c != 17) return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);
         // An extension's child is the LAST item of its list: nothing of the parent is left to visit, so
-        // the child takes over the parent's frame (a tail call) -- chains of inline extensions, 2 bytes
-        // a level, may be arbitrarily deep.  Only inline nodes under a BRANCH consume stack.
-        const bool tail = f.cnt == 2;
-        if (!tail) {
-          if (sp + 1 >= kMaxInlineDepth) return make_meta(kKindEmpty, kDecErr, 0, 0, 0, 0);  // documented limit
-          sp++;
+        // the child takes over the parent's frame (a tail call).  Only inline nodes under a BRANCH take a frame.
+        if (f.cnt != 2) {
+          depth++;
+          if (depth - base >= kInlineWindow) base++;  // the oldest frame falls out of the window (rebuilt on return)
         }
-        st[sp].pos = item + t.hdr_len; st[sp].end = item + t.hdr_len + t.payload_len;
-        st[sp].cnt = (uint8_t)c; st[sp].idx = 0; st[sp].leaf = 0; st[sp].top = 0;
+        Frame& g = st[depth & (kInlineWindow - 1)];
+        g.pos = item + t.hdr_len; g.end = item + t.hdr_len + t.payload_len;
+        g.cnt = (uint8_t)c; g.idx = 0; g.leaf = 0; g.top = 0;
       } else if (t.payload_len == 32) {
         if (f.top) mask |= 1u << i;
       } else if (t.payload_len != 0) {
@@ -252,7 +294,7 @@ __device__ void walk_one(const DeviceBatch& b, int wave, const Group<G>& g, cons
 
   const uint32_t a = proof_first[p] - b.node_base, n = proof_first[p + 1] - proof_first[p];
   const uint8_t* key = b.key_bytes + (b.key_off[p] - b.key_base);
-  const uint32_t klen = b.key_off[p + 1] - b.key_off[p];
+  const uint32_t klen = b.key_len ? b.key_len[p] : b.key_off[p + 1] - b.key_off[p];
 
   uint32_t status = kStOk;
   uint64_t voff = 0;
@@ -568,7 +610,7 @@ __device__ bool fast_one(const DeviceBatch& b, uint64_t p, bool dependent, const
   const uint32_t a = b.proof_first[p] - b.node_base, n = b.proof_first[p + 1] - b.proof_first[p];
   if (n == 0) return false;
   const uint8_t* key = b.key_bytes + (b.key_off[p] - b.key_base);
-  const uint32_t klen = b.key_off[p + 1] - b.key_off[p];
+  const uint32_t klen = b.key_len ? b.key_len[p] : b.key_off[p + 1] - b.key_off[p];
   const uint8_t* rp = b.roots + 32 * p;
   if (dependent) {
     // storage-circuit main.rs:10-27: the root is the storage_root of the account the earlier proof returned
