@@ -132,6 +132,17 @@ int mptv_verify_batch_hashed_keys(mptv_ctx* ctx, const mptv_batch* in, const uin
 int mptv_verify_borsh(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads,
                       mptv_result* out);
 
+/* What the host-fed entries (mptv_verify_batch, mptv_verify_borsh) moved since the context was created or the
+ * counters were last reset: summed over the context's devices. */
+typedef struct mptv_host_stats {
+  uint64_t chunks;
+  uint64_t nodes, nodes_aliased;  /* supplied nodes / those aliased to an identical node instead of copied again */
+  uint64_t node_bytes_supplied;   /* padded bytes of all supplied nodes                                      */
+  uint64_t node_bytes_placed;     /* ... of the nodes actually staged and copied                             */
+  uint64_t h2d_bytes, d2h_bytes;  /* bytes that crossed PCIe, counted from the copies issued                 */
+} mptv_host_stats;
+int mptv_host_stats_get(mptv_ctx* ctx, mptv_host_stats* out, int reset);
+
 /* Device-resident entry: every pointer is DEVICE memory on the context's device `dev_index`.
  * Asynchronous on `stream` (a cudaStream_t, NULL = the context's own stream for that device). */
 int mptv_verify_batch_device(mptv_ctx* ctx, int dev_index, const mptv_batch* in, mptv_result* out,
@@ -157,6 +168,9 @@ int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops
  *   "lanes_per_proof"  K2b lanes per proof: 0 = choose from nodes/proof, else 8, 16 or 32
  *   "chunk_bytes"      node bytes per pipeline chunk of the host-buffer entry (default 96 MiB)
  *   "borsh_chunk_bytes" borsh bytes per pipeline chunk of mptv_verify_borsh (default 32 MiB)
+ *   "host_dedup"       mptv_verify_borsh aliases byte-identical nodes of a chunk instead of staging and copying them
+ *                      again (default 1).  Transfer de-duplication only: every supplied node is still hashed on the
+ *                      device, results are identical
  *   "binning"          K0 rate-block binning on / off              (default 1)
  *   "fused_classify"   K1 also classifies plain branches / leaves  (default 1)
  *   "fast_walk"        K2f thread-per-proof chain check + K2b on the deferred rest (default 1)
@@ -256,6 +270,25 @@ int mptv_trie_proofs(mptv_ctx* ctx, const mptv_kv_batch* in, const mptv_proof_ta
 typedef struct mptv_host_batch mptv_host_batch;
 int mptv_flatten_borsh(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, int pinned,
                        mptv_host_batch** out);
+/* Same input and output, in ONE pass over the blobs, with flags:
+ *   MPTV_FLATTEN_ALIAS_DUPLICATES  a node that is byte-identical (exact compare) to an earlier node of the input is
+ *       not stored again: its node_off points at the first copy.  Proofs against one trie share their upper nodes, so
+ *       the arena shrinks several-fold (config 2: 3.1 GB -> ~0.5 GB) and so does what mptv_verify_batch has to move.
+ *       Verification results are identical: the device still hashes every supplied node.
+ * The batch's node_bytes block also holds the index arrays (node_off values are offsets into that block); nodes are
+ * NOT laid out in index order.  info (may be NULL) reports what was shared. */
+#define MPTV_FLATTEN_ALIAS_DUPLICATES 1u
+typedef struct mptv_flatten_info {
+  uint64_t n_nodes, nodes_aliased;
+  uint64_t node_bytes_supplied; /* sum of padded node lengths */
+  uint64_t node_bytes_placed;   /* ... of the nodes actually stored */
+} mptv_flatten_info;
+int mptv_flatten_borsh_ex(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, int pinned,
+                          unsigned flags, mptv_host_batch** out, mptv_flatten_info* info);
+/* The host stage of mptv_verify_borsh alone (no device needed): the same chunk loop and builder into ordinary memory.
+ * Timed by the caller, it is the ceiling of the streamed entry on this host with these threads. */
+int mptv_borsh_flatten_probe(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, uint64_t chunk_bytes,
+                             int alias_duplicates, mptv_flatten_info* info);
 const mptv_batch* mptv_host_batch_view(const mptv_host_batch* hb);
 const uint8_t* mptv_host_batch_bad_root(const mptv_host_batch* hb); /* [n_proofs] */
 void mptv_host_batch_free(mptv_host_batch* hb);

@@ -103,3 +103,89 @@ def test_host_pool_nt_copy_and_borsh_walkers_cpp(tmp_path):
                       capture_output=True).returncode == 0:
         r = subprocess.run([tsan], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, r.stdout + r.stderr
+
+
+def _node_view(b, k):
+    o, n = int(b.node_off[k]), int(b.node_len[k])
+    return b.node_bytes[o:o + n].tobytes()
+
+
+def test_flatten_borsh_ex_single_pass_and_aliasing(golden, oracle):
+    """mptv_flatten_borsh_ex (csrc/host_flatten.h): the one-pass builder reproduces every node, root and key of the
+    blobs; with MPTV_FLATTEN_ALIAS_DUPLICATES byte-identical nodes share one copy, and the oracle gives the same
+    verdicts and values on the aliased arena as on the plain one."""
+    import zk_state_proofs_b200 as z
+    inputs = [z.MerkleProofInput(v["proof_b"], v["root_b"], v["key_b"]) for v in golden["vectors"]]
+    inputs += [z.MerkleProofInput([], b"", b""), z.MerkleProofInput([b""], b"\x01" * 31, b"\x05" * 40)]
+    # many proofs against one trie: the shared upper nodes (>= 128 bytes) are what aliasing removes
+    from oracle.pytrie import Trie
+    import random
+    rng = random.Random(5)
+    kv = {oracle.keccak256(bytes([i, j])): rng.randbytes(70) for i in range(40) for j in range(40)}
+    t = Trie(kv, oracle.keccak256)
+    keys = list(kv)
+    inputs += [z.MerkleProofInput(t.proof(k), t.root, k) for k in keys[:600]]
+    blobs = [i.to_borsh() for i in inputs]
+    want = z.flatten(inputs)
+    ref = oracle.verify_batch(dict(node_bytes=want.node_bytes, node_off=want.node_off, node_len=want.node_len,
+                                   proof_first=want.proof_first, roots=want.roots, key_bytes=want.key_bytes,
+                                   key_off=want.key_off), nthreads=2)
+    for alias in (False, True):
+        for threads in (1, 3, 0):
+            got, info = z.flatten_borsh_ex(blobs, threads=threads, alias_duplicates=alias)
+            assert got.n_proofs == want.n_proofs and got.n_nodes == want.n_nodes == info.n_nodes
+            assert (got.node_len == want.node_len).all() and (got.proof_first == want.proof_first).all()
+            assert (got.roots == want.roots).all() and (got.key_off == want.key_off).all()
+            assert (got.node_off % 16 == 0).all()
+            k = int(want.key_off[-1])
+            assert (got.key_bytes[:k] == want.key_bytes[:k]).all()
+            assert ((got.bad_root_len if got.bad_root_len is not None else np.zeros(len(inputs), bool)) ==
+                    (want.bad_root_len if want.bad_root_len is not None else np.zeros(len(inputs), bool))).all()
+            for kk in range(want.n_nodes):
+                assert _node_view(got, kk) == _node_view(want, kk), kk
+            distinct_offsets = len(set(got.node_off.tolist()))
+            if alias:
+                assert info.nodes_aliased > 1000 and info.node_bytes_placed < info.node_bytes_supplied - 128 * info.nodes_aliased + 1
+                assert distinct_offsets <= want.n_nodes - info.nodes_aliased + 1
+            else:
+                assert info.nodes_aliased == 0 and info.node_bytes_placed == info.node_bytes_supplied
+            r = oracle.verify_batch(dict(node_bytes=got.node_bytes, node_off=got.node_off, node_len=got.node_len,
+                                         proof_first=got.proof_first, roots=got.roots, key_bytes=got.key_bytes,
+                                         key_off=got.key_off), nthreads=2)
+            assert (r[0] == ref[0]).all() and (r[2] == ref[2]).all()
+            for i in np.nonzero(r[0] == 0)[0]:
+                assert got.value(int(r[1][i]), int(r[2][i])) == want.value(int(ref[1][i]), int(ref[2][i]))
+
+
+def test_flatten_ex_never_aliases_nodes_that_differ_in_one_byte():
+    """the fingerprint only selects candidates: nodes that agree on every sampled word but differ elsewhere stay apart"""
+    import zk_state_proofs_b200 as z
+    base = bytearray(b"\xf9\x02\x11" + b"\xa0" + bytes(range(200)) * 3)[:532]
+    nodes = []
+    for pos in range(0, 532, 1):
+        n = bytearray(base)
+        n[pos] ^= 0x40
+        nodes.append(bytes(n))
+    nodes += nodes[:50] + [bytes(base)] * 3
+    inputs = [z.MerkleProofInput(nodes[i:i + 7], b"\xaa" * 32, b"\x01") for i in range(0, len(nodes), 7)]
+    got, info = z.flatten_borsh_ex([i.to_borsh() for i in inputs], threads=2, alias_duplicates=True)
+    flat = [n for i in inputs for n in i.proof]
+    # 404 of the 532 variants agree on every sampled word: they chain in one bucket and only the first few (the probe
+    # budget) are recorded, so not every later duplicate is shared -- but nothing that differs is ever merged
+    assert 3 <= info.nodes_aliased <= 53
+    for k, n in enumerate(flat):
+        assert _node_view(got, k) == n
+
+
+def test_flatten_ex_rejects_what_borsh_rejects_and_probe_runs():
+    import zk_state_proofs_b200 as z
+    good = z.MerkleProofInput([b"\x01\x02" * 100], b"\xaa" * 32, b"\x07").to_borsh()
+    for bad in [good[:-1], good + b"\x00", good[:3], b"\xff\xff\xff\xff" + good[4:], b"", good[:11]]:
+        with pytest.raises(ValueError):
+            z.flatten_borsh_ex([good, bad])
+        with pytest.raises(ValueError):
+            z.borsh_flatten_probe([good, bad])
+    dt, info = z.borsh_flatten_probe([good] * 1000, threads=2, chunk_bytes=1 << 14)
+    assert info.n_nodes == 1000 and info.nodes_aliased > 900 and dt > 0
+    b, info = z.flatten_borsh_ex([])
+    assert b.n_proofs == 0

@@ -1,5 +1,6 @@
-"""mptv_verify_borsh (blobs in, verdicts out) on the config-2 batch: chunk size x host threads sweep, beside the
-serial flatten-then-verify.   python tools/borsh_stream_bench.py [n_proofs]      (on a B200)"""
+"""mptv_verify_borsh (blobs in, verdicts out) on the config-2 batch: host_dedup x chunk size x host threads sweep,
+with the bytes that crossed PCIe (mptv_host_stats) and the host stage alone (mptv_borsh_flatten_probe) beside it,
+and the serial flatten-then-verify.   python tools/borsh_stream_bench.py [n_proofs] [quick]      (on a B200)"""
 import ctypes
 import os
 import sys
@@ -14,29 +15,43 @@ import zk_state_proofs_b200 as z  # noqa: E402
 from workload import gen  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+quick = len(sys.argv) > 2
 sys.argv = ["bench.py", "--workload", "config2", "--proofs", str(n)]
 a = bench.parse_args()
 ver = z.Verifier([0])
 b, _ = bench.build_batch(a, 0, pinned=True)
 blobs, boff = gen.batch_to_borsh(b)
-print(f"{n} proofs, {len(blobs) / 1e9:.2f} GB of borsh, {os.cpu_count()} host cores", flush=True)
+cores = os.cpu_count()
+print(f"{n} proofs, {len(blobs) / 1e9:.2f} GB of borsh, {cores} host cores", flush=True)
 ref = ver.verify_batch(b)
 for _ in range(2):
     t0 = time.perf_counter(); ver.verify_batch(b); dt = time.perf_counter() - t0
 print(f"mptv_verify_batch on the pre-flattened pinned batch: {dt * 1e3:.1f} ms = {n / dt / 1e6:.2f} M proofs/s", flush=True)
-for mb in (8, 16, 24, 32, 64):
-    for th in (8, 0):
-        ver.set_option("borsh_chunk_bytes", mb << 20)
-        best = 1e9
-        for it in range(4):
-            t0 = time.perf_counter()
-            st, voff, vlen = ver.verify_borsh(blobs, boff, threads=th)
-            dt = time.perf_counter() - t0
-            if it:
-                best = min(best, dt)
-        assert (st == ref[0]).all() and (vlen == ref[2]).all()
-        print(f"chunk {mb:4d} MB threads {th or os.cpu_count():2d}: {best * 1e3:7.1f} ms = {n / best / 1e6:6.2f} M proofs/s", flush=True)
+for dd in (1, 0):
+    ver.set_option("host_dedup", dd)
+    for mb in ((32,) if quick else (8, 16, 32, 64, 128)):
+        for th in ((cores,) if quick else sorted({4, 8, 12, cores})):
+            ver.set_option("borsh_chunk_bytes", mb << 20)
+            best = 1e9
+            for it in range(4):
+                ver.host_stats(reset=True)
+                t0 = time.perf_counter()
+                st, voff, vlen = ver.verify_borsh(blobs, boff, threads=th)
+                dt = time.perf_counter() - t0
+                if it:
+                    best = min(best, dt)
+            hs = ver.host_stats()
+            assert (st == ref[0]).all() and (vlen == ref[2]).all()
+            pt = min(z.borsh_flatten_probe(blobs, boff, threads=th, chunk_bytes=mb << 20, alias_duplicates=bool(dd))[0]
+                     for _ in range(3))
+            print(f"host_dedup {dd} chunk {mb:4d} MB threads {th:2d}: {best * 1e3:7.1f} ms = {n / best / 1e6:6.2f} M proofs/s | "
+                  f"H2D {hs.h2d_bytes / 1e9:5.2f} GB ({hs.h2d_bytes / best / 1e9:5.1f} GB/s), aliased {hs.nodes_aliased}/{hs.nodes} nodes, "
+                  f"{hs.chunks} chunks | host stage alone {pt * 1e3:6.1f} ms ({len(blobs) / pt / 1e9:5.1f} GB/s read)", flush=True)
 ver.set_option("borsh_chunk_bytes", 32 << 20)
+ver.set_option("host_dedup", 1)
+ok = np.nonzero(st == 0)[0][:5000]
+for i in ok:
+    assert blobs[int(voff[i]):int(voff[i]) + int(vlen[i])].tobytes() == b.value(int(ref[1][i]), int(ref[2][i]))
 L = z.load_library()
 h = ctypes.c_void_p()
 for it in range(3):

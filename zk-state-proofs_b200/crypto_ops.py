@@ -284,6 +284,65 @@ def flatten_borsh(blobs: Sequence[bytes], threads: int = 0, pinned: bool = False
     return b
 
 
+class FlattenInfo(ctypes.Structure):
+    """include/mptv.h `mptv_flatten_info`"""
+    _fields_ = [("n_nodes", ctypes.c_uint64), ("nodes_aliased", ctypes.c_uint64),
+                ("node_bytes_supplied", ctypes.c_uint64), ("node_bytes_placed", ctypes.c_uint64)]
+
+
+class HostStats(ctypes.Structure):
+    """include/mptv.h `mptv_host_stats`"""
+    _fields_ = [("chunks", ctypes.c_uint64), ("nodes", ctypes.c_uint64), ("nodes_aliased", ctypes.c_uint64),
+                ("node_bytes_supplied", ctypes.c_uint64), ("node_bytes_placed", ctypes.c_uint64),
+                ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64)]
+
+
+FLATTEN_ALIAS_DUPLICATES = 1
+
+
+def _blob_arrays(blobs, blob_off=None):
+    """sequence of bytes objects, or one uint8 array + [n + 1] uint64 offsets -> (uint8 array, uint64 offsets)"""
+    if blob_off is None:
+        n = len(blobs)
+        lens = np.fromiter((len(x) for x in blobs), dtype=np.int64, count=n)
+        blob_off = np.zeros(n + 1, np.uint64)
+        np.cumsum(lens, out=blob_off[1:])
+        blobs = np.frombuffer(b"".join(bytes(x) for x in blobs) + b"\0", np.uint8)
+    return np.ascontiguousarray(blobs, np.uint8), np.ascontiguousarray(blob_off, np.uint64)
+
+
+def flatten_borsh_ex(blobs, blob_off=None, threads: int = 0, pinned: bool = False, alias_duplicates: bool = True):
+    """mptv_flatten_borsh_ex: one pass over the blobs; byte-identical nodes are stored once and aliased.
+    -> (Batch, FlattenInfo).  The Batch's node_bytes block also holds the index arrays."""
+    L = load_library()
+    buf, off = _blob_arrays(blobs, blob_off)
+    n = len(off) - 1
+    h = ctypes.c_void_p()
+    info = FlattenInfo()
+    rc = L.mptv_flatten_borsh_ex(buf.ctypes.data, off.ctypes.data, n, threads, 1 if pinned else 0,
+                                 FLATTEN_ALIAS_DUPLICATES if alias_duplicates else 0, ctypes.byref(h), ctypes.byref(info))
+    if rc != 0:
+        raise ValueError(f"mptv_flatten_borsh_ex: {L.mptv_strerror(rc).decode()} (malformed borsh MerkleProofInput?)")
+    b = batch_from_handle(L, h, n)
+    b._owner = _HostBatchOwner(L, h)
+    return b, info
+
+
+def borsh_flatten_probe(blobs, blob_off=None, threads: int = 0, chunk_bytes: int = 32 << 20, alias_duplicates: bool = True):
+    """mptv_borsh_flatten_probe: the host stage of verify_borsh alone -> (seconds, FlattenInfo)"""
+    import time
+    L = load_library()
+    buf, off = _blob_arrays(blobs, blob_off)
+    info = FlattenInfo()
+    t0 = time.perf_counter()
+    rc = L.mptv_borsh_flatten_probe(buf.ctypes.data, off.ctypes.data, len(off) - 1, threads, chunk_bytes,
+                                    1 if alias_duplicates else 0, ctypes.byref(info))
+    dt = time.perf_counter() - t0
+    if rc != 0:
+        raise ValueError(f"mptv_borsh_flatten_probe: {L.mptv_strerror(rc).decode()}")
+    return dt, info
+
+
 def batch_from_handle(L, h, n: int) -> Batch:
     """Batch view of a mptv_host_batch handle (no ownership: the caller frees or recycles the handle)."""
     v = ctypes.cast(L.mptv_host_batch_view(h), ctypes.POINTER(_CBatch)).contents
@@ -504,6 +563,12 @@ def load_library():
                                    ctypes.POINTER(_CProofsOut)]
     L.mptv_flatten_borsh.restype = i32
     L.mptv_flatten_borsh.argtypes = [vp, vp, u64, i32, i32, ctypes.POINTER(vp)]
+    L.mptv_flatten_borsh_ex.restype = i32
+    L.mptv_flatten_borsh_ex.argtypes = [vp, vp, u64, i32, i32, ctypes.c_uint, ctypes.POINTER(vp), ctypes.POINTER(FlattenInfo)]
+    L.mptv_borsh_flatten_probe.restype = i32
+    L.mptv_borsh_flatten_probe.argtypes = [vp, vp, u64, i32, u64, i32, ctypes.POINTER(FlattenInfo)]
+    L.mptv_host_stats_get.restype = i32
+    L.mptv_host_stats_get.argtypes = [vp, ctypes.POINTER(HostStats), i32]
     L.mptv_host_batch_view.restype = vp
     L.mptv_host_batch_view.argtypes = [vp]
     L.mptv_host_batch_bad_root.restype = vp
@@ -608,14 +673,7 @@ class Verifier:
         """mptv_verify_borsh: borsh(MerkleProofInput) blobs in, verdicts out, flattening pipelined with the copies
         and kernels.  `blobs` is a sequence of bytes objects, or one uint8 array with `blob_off` ([n + 1] uint64).
         Returns (status, value_off, value_len); value_off indexes the CONCATENATED blobs."""
-        if blob_off is None:
-            n = len(blobs)
-            lens = np.fromiter((len(x) for x in blobs), dtype=np.int64, count=n)
-            blob_off = np.zeros(n + 1, np.uint64)
-            np.cumsum(lens, out=blob_off[1:])
-            blobs = np.frombuffer(b"".join(bytes(x) for x in blobs) + b"\0", np.uint8)
-        buf = np.ascontiguousarray(blobs, np.uint8)
-        off = np.ascontiguousarray(blob_off, np.uint64)
+        buf, off = _blob_arrays(blobs, blob_off)
         n = len(off) - 1
         status = np.zeros(n, np.uint8)
         voff = np.zeros(n, np.uint64)
@@ -644,6 +702,12 @@ class Verifier:
                                                          n_nodes, digests,
                                                          ctypes.c_void_p(stream) if stream else None),
                     "mptv_keccak256_batch_device")
+
+    def host_stats(self, reset: bool = False) -> HostStats:
+        """what the host-fed entries moved (chunks, nodes aliased, bytes over PCIe) since the last reset"""
+        t = HostStats()
+        self._check(self.lib.mptv_host_stats_get(self.ctx, ctypes.byref(t), 1 if reset else 0), "mptv_host_stats_get")
+        return t
 
     def last_timings(self, dev_index: int = 0) -> Timings:
         t = Timings()

@@ -11,6 +11,7 @@
 
 #include "../../include/mptv.h"
 #include "host_codec.h"
+#include "host_flatten.h"
 #include "kernels.h"
 
 namespace mptv {
@@ -57,7 +58,7 @@ struct Slot {
   bool pend_borsh = false;
   size_t h_node_off = 0, h_node_len = 0, h_proof_first = 0;
   std::vector<uint64_t> node_src;
-  std::vector<BlobShape> shapes;  // of the chunk's blobs (bad_root decides their verdict at drain time)
+  std::vector<uint8_t> bad_root;  // of the chunk's blobs: root_hash.len() != 32 decides their verdict at drain time
   DevBuf node_bytes, node_off, node_len, proof_first, roots, key_bytes, key_off, rfp;
   DevBuf results, in_pack;
   DevBuf digests, meta, order, bins, defer, dedup;
@@ -128,6 +129,8 @@ struct Device {
   uint64_t last_nodes = 0;
   uint32_t last_keccak_launches = 0, last_other_launches = 0;
   Rebuild rb;
+  DedupTable dedup_tab;  // host-side candidate table of the streamed borsh entry (one chunk at a time)
+  mptv_host_stats hstat = {0, 0, 0, 0, 0, 0, 0};  // of the host-fed entries since the last reset
 };
 
 }  // namespace mptv
@@ -142,6 +145,7 @@ struct mptv_ctx {
   int binning = 1;
   int fused_classify = 1;  // K1 also classifies plain branches / leaves (K2a fast path)
   int dedup_nodes = 0;     // hash each DISTINCT node once (secondary mode, reported separately)
+  int host_dedup = 1;      // streamed borsh entry: alias byte-identical nodes of a chunk instead of copying them again
   int fast_walk = 1;       // K2f decides chain-shaped proofs one thread each; K2b gets the deferred rest
   int long_leaf_bin = mptv::kLongLeafBin;  // rebuild: leaves in rate-block bins >= this are hashed in their own launch ...
   int long_leaf_ctas = 1;            // ... with this many K1L CTAs (of 4 warps) per SM

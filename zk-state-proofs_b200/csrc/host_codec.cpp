@@ -24,6 +24,7 @@
 
 #include "../../include/mptv.h"
 #include "host_codec.h"
+#include "host_flatten.h"
 
 using mptv::BlobShape;
 using mptv::borsh_shape;
@@ -168,6 +169,124 @@ int mptv_flatten_borsh(const uint8_t* blobs, const uint64_t* blob_off, uint64_t 
                        mptv_host_batch** out) {
   try {  // the C ABI never throws: the per-input tables below are sized by the caller's n
     return flatten_borsh_run(blobs, blob_off, n, n_threads, pinned, out);
+  } catch (...) {
+    return MPTV_ERR_NOMEM;
+  }
+}
+
+// Single pass + optional aliasing of byte-identical nodes (host_flatten.h).  Block 0 of the handle holds the index
+// arrays and the workers' byte regions; the keys are re-packed into the public prefix-array form (32 bytes a proof).
+static int flatten_borsh_ex_run(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, int pinned,
+                                unsigned flags, mptv_host_batch** out, mptv_flatten_info* info) {
+  if (!out || (n && (!blobs || !blob_off))) return MPTV_ERR_ARG;
+  if (flags & ~(unsigned)MPTV_FLATTEN_ALIAS_DUPLICATES) return MPTV_ERR_ARG;
+  mptv_host_batch* reuse = *out;
+  if (reuse && reuse->pinned != (pinned != 0)) return MPTV_ERR_ARG;
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  if (n < 256) n_threads = 1;
+  mptv::WorkerPool pool(n_threads);
+  mptv::DedupTable table;
+  const bool alias = (flags & MPTV_FLATTEN_ALIAS_DUPLICATES) != 0;
+  if (alias) {
+    // one chunk = the whole input: a node worth sharing is >= 128 bytes, so bytes / 128 bounds the entries
+    const uint64_t bytes = n ? blob_off[n] - blob_off[0] : 0;
+    if (!table.reserve((size_t)std::min<uint64_t>(bytes / 256 + 1024, 1ull << 24))) return MPTV_ERR_NOMEM;
+    table.new_epoch();
+  }
+  mptv_host_batch* hb = reuse ? reuse : new mptv_host_batch();
+  hb->pinned = pinned != 0;
+  auto fail = [&](int rc) {
+    if (!reuse) mptv_host_batch_free(hb);
+    return rc;
+  };
+  mptv::BorshChunkJob job = {blobs, blob_off, 0, n, alias ? &table : nullptr};
+  mptv::ChunkLayout L;
+  std::vector<uint8_t> bad;
+  const int rc = mptv::flatten_borsh_chunk(pool, job, [&](size_t total) { return (uint8_t*)host_alloc(hb, 0, total); }, L,
+                                           nullptr, &bad);
+  if (rc != MPTV_OK) return fail(rc);
+  uint8_t* block = (uint8_t*)hb->blocks[0];
+  const uint32_t* koff = reinterpret_cast<const uint32_t*>(block + L.o_koff);
+  const uint32_t* klen = reinterpret_cast<const uint32_t*>(block + L.o_klen);
+  uint64_t kbytes = 0;
+  for (uint64_t i = 0; i < n; i++) kbytes += klen[i];
+  if (kbytes > 0xfffffff0ull) return fail(MPTV_ERR_ARG);
+  uint8_t* key_bytes = (uint8_t*)host_alloc(hb, 5, kbytes + 16);
+  uint32_t* key_off = (uint32_t*)host_alloc(hb, 6, 4 * (n + 1));
+  hb->bad_root = (uint8_t*)host_alloc(hb, 7, n);
+  if (!key_bytes || !key_off || !hb->bad_root) return fail(MPTV_ERR_NOMEM);
+  uint64_t o = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    key_off[i] = (uint32_t)o;
+    if (klen[i]) memcpy(key_bytes + o, block + koff[i], klen[i]);
+    o += klen[i];
+    hb->bad_root[i] = bad[i];
+  }
+  key_off[n] = (uint32_t)o;
+  memset(key_bytes + o, 0, 16);
+  hb->view.node_bytes = block; hb->view.node_bytes_len = L.total;
+  hb->view.node_off = reinterpret_cast<const uint64_t*>(block + L.o_off);
+  hb->view.node_len = reinterpret_cast<const uint32_t*>(block + L.o_len);
+  hb->view.n_nodes = L.nn;
+  hb->view.proof_first = reinterpret_cast<const uint32_t*>(block + L.o_pf);
+  hb->view.n_proofs = n; hb->view.roots = block + L.o_roots;
+  hb->view.key_bytes = key_bytes; hb->view.key_off = key_off; hb->view.root_from_proof = nullptr;
+  if (info) {
+    info->n_nodes = L.nn; info->nodes_aliased = L.nodes_aliased;
+    info->node_bytes_supplied = L.node_bytes_supplied; info->node_bytes_placed = L.node_bytes_placed;
+  }
+  *out = hb;
+  return MPTV_OK;
+}
+
+int mptv_flatten_borsh_ex(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, int pinned,
+                          unsigned flags, mptv_host_batch** out, mptv_flatten_info* info) {
+  try {
+    return flatten_borsh_ex_run(blobs, blob_off, n, n_threads, pinned, flags, out, info);
+  } catch (...) {
+    return MPTV_ERR_NOMEM;
+  }
+}
+
+// The host stage of mptv_verify_borsh run ALONE (no device, ordinary memory): the same chunk loop, the same
+// builder, three recycled blocks.  Its rate is the ceiling of the streamed entry on this host.
+int mptv_borsh_flatten_probe(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, uint64_t chunk_bytes,
+                             int alias_duplicates, mptv_flatten_info* info) {
+  if (n && (!blobs || !blob_off)) return MPTV_ERR_ARG;
+  try {
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (chunk_bytes < 4096) chunk_bytes = 32ull << 20;
+    mptv::WorkerPool pool(n_threads);
+    mptv::DedupTable table;
+    if (alias_duplicates && !table.reserve((size_t)std::min<uint64_t>(chunk_bytes / 128 + 1024, 1ull << 22))) return MPTV_ERR_NOMEM;
+    // recycled across calls (like the page-locked staging of the real entry): page faults are paid once
+    struct Blk { uint8_t* p = nullptr; size_t cap = 0; };
+    static thread_local Blk block[3];
+    mptv_flatten_info acc = {0, 0, 0, 0};
+    size_t ci = 0;
+    for (uint64_t cs = 0; cs < n; ci++) {
+      uint64_t ce = (uint64_t)(std::upper_bound(blob_off + cs + 1, blob_off + n + 1, blob_off[cs] + chunk_bytes) - blob_off);
+      if (ce > cs + 1) ce--;
+      if (ce > n) ce = n;
+      table.new_epoch();
+      mptv::BorshChunkJob job = {blobs, blob_off, cs, ce, alias_duplicates ? &table : nullptr};
+      mptv::ChunkLayout L;
+      Blk& blk = block[ci % 3];
+      const int rc = mptv::flatten_borsh_chunk(pool, job, [&](size_t total) {
+        if (blk.cap < total) {
+          free(blk.p);
+          blk.cap = total + total / 8;
+          if (posix_memalign((void**)&blk.p, 64, blk.cap) != 0) { blk.p = nullptr; blk.cap = 0; }
+        }
+        return blk.p;
+      }, L, nullptr, nullptr);
+      if (rc != MPTV_OK) return rc;
+      acc.n_nodes += L.nn; acc.nodes_aliased += L.nodes_aliased;
+      acc.node_bytes_supplied += L.node_bytes_supplied; acc.node_bytes_placed += L.node_bytes_placed;
+      cs = ce;
+    }
+    if (info) *info = acc;
+    return MPTV_OK;
   } catch (...) {
     return MPTV_ERR_NOMEM;
   }

@@ -16,6 +16,7 @@
 
 #include "ctx.h"
 #include "host_codec.h"
+#include "host_flatten.h"
 
 using namespace mptv;
 
@@ -196,8 +197,10 @@ int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
     if (value < (1 << 16)) return MPTV_ERR_ARG;
     ctx->chunk_bytes = (uint64_t)value;
   } else if (!strcmp(name, "borsh_chunk_bytes")) {
-    if (value < (1 << 12)) return MPTV_ERR_ARG;
+    if (value < (1 << 12) || value > (1ll << 31)) return MPTV_ERR_ARG;
     ctx->borsh_chunk_bytes = (uint64_t)value;
+  } else if (!strcmp(name, "host_dedup")) {
+    ctx->host_dedup = value ? 1 : 0;
   } else if (!strcmp(name, "binning")) {
     ctx->binning = value ? 1 : 0;
   } else if (!strcmp(name, "fused_classify")) {
@@ -243,7 +246,7 @@ int mptv_verify_batch_device(mptv_ctx* ctx, int dev_index, const mptv_batch* in,
   DeviceBatch b;
   b.node_bytes = in->node_bytes; b.node_off = in->node_off; b.node_len = in->node_len; b.n_nodes = in->n_nodes;
   b.proof_first = in->proof_first; b.n_proofs = in->n_proofs; b.roots = in->roots;
-  b.key_bytes = in->key_bytes; b.key_off = in->key_off; b.root_from_proof = in->root_from_proof;
+  b.key_bytes = in->key_bytes; b.key_off = in->key_off; b.key_len = nullptr; b.root_from_proof = in->root_from_proof;
   b.byte_base = 0; b.node_base = 0; b.key_base = 0; b.proof_base = 0;
   return run_pipeline(ctx, d, b, d.digests, d.meta, d.order, d.bins, d.defer, d.dedup, out->status, out->value_off, out->value_len,
                       st, true);
@@ -274,6 +277,18 @@ int mptv_keccak256_batch_device(mptv_ctx* ctx, int dev_index, const uint8_t* nod
   CK(cudaEventRecord(d.ev[4], st));
   d.last_stream = st; d.have_timing = true; d.last_nodes = n_nodes;
   d.last_keccak_launches = n_nodes ? 1 : 0; d.last_other_launches = ctx->binning ? 3 : 0;
+  return MPTV_OK;
+}
+
+int mptv_host_stats_get(mptv_ctx* ctx, mptv_host_stats* out, int reset) {
+  if (!ctx || !out) return MPTV_ERR_ARG;
+  memset(out, 0, sizeof *out);
+  for (Device& d : ctx->dev) {
+    out->chunks += d.hstat.chunks; out->nodes += d.hstat.nodes; out->nodes_aliased += d.hstat.nodes_aliased;
+    out->node_bytes_supplied += d.hstat.node_bytes_supplied; out->node_bytes_placed += d.hstat.node_bytes_placed;
+    out->h2d_bytes += d.hstat.h2d_bytes; out->d2h_bytes += d.hstat.d2h_bytes;
+    if (reset) memset(&d.hstat, 0, sizeof d.hstat);
+  }
   return MPTV_OK;
 }
 
@@ -424,6 +439,7 @@ int run_slice_chunks(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result
                               ? reinterpret_cast<const int32_t*>(put(in->root_from_proof + c.p0, 4 * np, 4 * np))
                               : nullptr;
       CK(cudaMemcpyAsync(dv, h, o, cudaMemcpyHostToDevice, st));
+      d.hstat.h2d_bytes += o;
     } else {
       CK(s.node_bytes.reserve(nbytes + 16));
       CK(s.node_off.reserve(8 * nn + 8));
@@ -442,12 +458,14 @@ int run_slice_chunks(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result
       CK(cudaMemcpyAsync(s.key_off.p, in->key_off + c.p0, 4 * (np + 1), cudaMemcpyHostToDevice, st));
       if (in->root_from_proof)
         CK(cudaMemcpyAsync(s.rfp.p, in->root_from_proof + c.p0, 4 * np, cudaMemcpyHostToDevice, st));
+      d.hstat.h2d_bytes += nbytes + 12 * nn + 8 * (np + 1) + 32 * np + kbytes + (in->root_from_proof ? 4 * np : 0);
       b.node_bytes = s.node_bytes.as<uint8_t>(); b.node_off = s.node_off.as<uint64_t>();
       b.node_len = s.node_len.as<uint32_t>();
       b.proof_first = s.proof_first.as<uint32_t>(); b.roots = s.roots.as<uint8_t>();
       b.key_bytes = s.key_bytes.as<uint8_t>(); b.key_off = s.key_off.as<uint32_t>();
       b.root_from_proof = in->root_from_proof ? s.rfp.as<int32_t>() : nullptr;
     }
+    b.key_len = nullptr;
     b.n_nodes = nn; b.n_proofs = np;
     b.byte_base = byte0; b.node_base = n0; b.key_base = k0; b.proof_base = c.p0;
     CK(s.results.reserve(13 * np + 16));
@@ -457,6 +475,8 @@ int run_slice_chunks(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result
                       reinterpret_cast<uint64_t*>(res), reinterpret_cast<uint32_t*>(res + 8 * np), st, false);
     if (rc != MPTV_OK) return rc;
     CK(cudaMemcpyAsync(s.h_results.p, res, 13 * np, cudaMemcpyDeviceToHost, st));
+    d.hstat.chunks++; d.hstat.nodes += nn; d.hstat.node_bytes_supplied += nbytes; d.hstat.node_bytes_placed += nbytes;
+    d.hstat.d2h_bytes += 13 * np;
     s.pend_p0 = c.p0; s.pend_np = np;
   }
   for (int k = 0; k < kSlots; k++) {
@@ -503,9 +523,10 @@ int drain_slot_borsh(mptv_ctx* ctx, Slot& s, mptv_result* out, WorkerPool& pool)
       uint8_t st = status[i];
       uint64_t vo = 0;
       uint32_t vl = 0;
-      if (s.shapes[i].bad_root) st = MPTV_ST_BAD_ROOT_LEN;  // the guests' try_into().unwrap() comes first
+      if (s.bad_root[i]) st = MPTV_ST_BAD_ROOT_LEN;  // the guests' try_into().unwrap() comes first
       else if (st == MPTV_ST_OK) {
-        // the value is a slice of one node of this proof: report it as a slice of the caller's blobs
+        // the value is a slice of one node of this proof (or of the identical node it aliases): report it as a
+        // slice of the caller's blobs, inside THIS proof's own copy of the node
         vl = vlen[i];
         for (uint32_t k = proof_first[i]; k < proof_first[i + 1]; k++)
           if (node_off[k] <= voff[i] && voff[i] + vl <= node_off[k] + node_len[k]) {
@@ -525,12 +546,12 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
                            WorkerPool& pool) {
   if (p1 <= p0) return MPTV_OK;
   CK(cudaSetDevice(d.id));
-  const int T = pool.size();
-  struct Tot { uint64_t nodes, bytes, keys; };
-  std::vector<Tot> tot(T);
+  const bool alias = ctx->host_dedup != 0;
+  if (alias && !d.dedup_tab.reserve((size_t)std::min<uint64_t>(ctx->borsh_chunk_bytes / 128 + 1024, 1ull << 22)))
+    return fail_msg(ctx, MPTV_ERR_NOMEM, "mptv_verify_borsh: host table allocation failed");
   size_t ci = 0;
   for (uint64_t cs = p0; cs < p1; ci++) {
-    // the chunk: as many blobs as fit borsh_chunk_bytes of input (the arena is within a few % of that)
+    // the chunk: as many blobs as fit borsh_chunk_bytes of input
     uint64_t ce = (uint64_t)(std::upper_bound(in.blob_off + cs + 1, in.blob_off + p1 + 1, in.blob_off[cs] + ctx->borsh_chunk_bytes) -
                              in.blob_off);
     if (ce > cs + 1) ce--;
@@ -540,78 +561,45 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
     int rc = drain_slot_borsh(ctx, s, out, pool);
     if (rc != MPTV_OK) return rc;
     const uint64_t np = ce - cs;
-    if (s.shapes.size() < np) s.shapes.resize(np + np / 8);
-    // shared between the workers of this chunk
-    std::atomic<int> bad(0);
-    int err = MPTV_OK;
-    size_t o_bytes = 0, o_off = 0, o_len = 0, o_pf = 0, o_roots = 0, o_keys = 0, o_koff = 0, total = 0;
-    uint64_t nn = 0, nbytes = 0, kbytes = 0;
-    const uint64_t per = (np + T - 1) / T;
-    pool.run([&](int t) {
-      const uint64_t lo = std::min(np, per * t), hi = std::min(np, lo + per);
-      // pass 1: shapes of my blobs
-      Tot my = {0, 0, 0};
-      for (uint64_t i = lo; i < hi; i++) {
-        const uint64_t p = cs + i;
-        BlobShape sh = {0, 0, 0, 0, 0};
-        if (in.blob_off[p + 1] >= in.blob_off[p]) sh = borsh_shape(in.blobs + in.blob_off[p], in.blobs + in.blob_off[p + 1]);
-        if (!sh.ok) bad.store(1, std::memory_order_relaxed);
-        s.shapes[i] = sh;
-        my.nodes += sh.n_nodes; my.bytes += sh.padded_bytes; my.keys += sh.key_len;
+    // one pass over the chunk's blobs, straight into the slot's page-locked block; a node identical to one already
+    // placed in this chunk is aliased, not copied (host_flatten.h)
+    if (alias) d.dedup_tab.new_epoch();
+    const BorshChunkJob job = {in.blobs, in.blob_off, cs, ce, alias ? &d.dedup_tab : nullptr};
+    ChunkLayout L;
+    rc = flatten_borsh_chunk(pool, job, [&](size_t total) -> uint8_t* {
+      if (s.h_in.reserve(total) != cudaSuccess || s.in_pack.reserve(total) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
       }
-      tot[t] = my;
-      pool.barrier();
-      if (t == 0) {  // totals -> layout of the packed block (same on host and device) -> buffers
-        for (int k = 0; k < T; k++) { nn += tot[k].nodes; nbytes += tot[k].bytes; kbytes += tot[k].keys; }
-        if (bad.load() || nn > 0xfffffff0ull || kbytes > 0xfffffff0ull) err = MPTV_ERR_ARG;
-        else {
-          size_t o = 0;
-          auto take = [&](size_t bytes) { const size_t at = o; o += up16(bytes); return at; };
-          o_bytes = take(nbytes + 16); o_off = take(8 * nn); o_len = take(4 * nn); o_pf = take(4 * (np + 1));
-          o_roots = take(32 * np); o_keys = take(kbytes + 16); o_koff = take(4 * (np + 1));
-          total = o;
-          if (s.h_in.reserve(total) != cudaSuccess || s.in_pack.reserve(total) != cudaSuccess) {
-            cudaGetLastError();
-            err = MPTV_ERR_NOMEM;
-          } else if (s.node_src.size() < nn) s.node_src.resize(nn + nn / 8);
-        }
-      }
-      pool.barrier();
-      if (err != MPTV_OK) return;
-      // pass 2: copy my blobs
-      uint64_t k = 0, ob = 0, ok = 0;
-      for (int q = 0; q < t; q++) { k += tot[q].nodes; ob += tot[q].bytes; ok += tot[q].keys; }
-      uint8_t* h = static_cast<uint8_t*>(s.h_in.p);
-      uint64_t* node_off = reinterpret_cast<uint64_t*>(h + o_off);
-      uint32_t* node_len = reinterpret_cast<uint32_t*>(h + o_len);
-      uint32_t* proof_first = reinterpret_cast<uint32_t*>(h + o_pf);
-      uint32_t* key_off = reinterpret_cast<uint32_t*>(h + o_koff);
-      for (uint64_t i = lo; i < hi; i++) {
-        const BlobShape& sh = s.shapes[i];
-        proof_first[i] = (uint32_t)k;
-        key_off[i] = (uint32_t)ok;
-        borsh_copy(in.blobs + in.blob_off[cs + i], sh, h + o_bytes, ob, node_off, node_len, k, h + o_roots + 32 * i,
-                   h + o_keys + ok, s.node_src.data(), in.blobs);
-        k += sh.n_nodes; ob += sh.padded_bytes; ok += sh.key_len;
-      }
-      _mm_sfence();  // the nodes were written with non-temporal stores; the DMA engine reads them next
-    });
-    if (err == MPTV_ERR_ARG) return fail_msg(ctx, err, "mptv_verify_borsh: a blob is not a well-formed borsh(MerkleProofInput)");
-    if (err != MPTV_OK) return fail_msg(ctx, err, "mptv_verify_borsh: staging allocation failed");
+      return static_cast<uint8_t*>(s.h_in.p);
+    }, L, &s.node_src, &s.bad_root);
+    if (rc == MPTV_ERR_ARG) return fail_msg(ctx, rc, "mptv_verify_borsh: a blob is not a well-formed borsh(MerkleProofInput)");
+    if (rc != MPTV_OK) return fail_msg(ctx, rc, "mptv_verify_borsh: staging allocation failed");
     uint8_t* h = static_cast<uint8_t*>(s.h_in.p);
     uint8_t* dv = s.in_pack.as<uint8_t>();
-    reinterpret_cast<uint32_t*>(h + o_pf)[np] = (uint32_t)nn;
-    reinterpret_cast<uint32_t*>(h + o_koff)[np] = (uint32_t)kbytes;
-    memset(h + o_bytes + nbytes, 0, 16);
-    memset(h + o_keys + kbytes, 0, 16);
-    CK(cudaMemcpyAsync(dv, h, total, cudaMemcpyHostToDevice, st));
+    // what was written: the index arrays, then each worker's used prefix of its region (neighbours merged when the
+    // unused gap between them is small)
+    size_t c0 = 0, c1 = L.index_end;
+    uint64_t moved = 0;
+    for (size_t t = 0; t <= L.region_begin.size(); t++) {
+      const bool last = t == L.region_begin.size();
+      if (!last && L.region_used[t] == 0) continue;
+      if (!last && L.region_begin[t] <= c1 + 4096) { c1 = L.region_begin[t] + L.region_used[t]; continue; }
+      CK(cudaMemcpyAsync(dv + c0, h + c0, c1 - c0, cudaMemcpyHostToDevice, st));
+      moved += c1 - c0;
+      if (!last) { c0 = L.region_begin[t]; c1 = c0 + L.region_used[t]; }
+    }
+    d.hstat.chunks++; d.hstat.nodes += L.nn; d.hstat.nodes_aliased += L.nodes_aliased;
+    d.hstat.node_bytes_supplied += L.node_bytes_supplied; d.hstat.node_bytes_placed += L.node_bytes_placed;
+    d.hstat.h2d_bytes += moved; d.hstat.d2h_bytes += 13 * np;
     DeviceBatch b;
-    b.node_bytes = dv + o_bytes; b.node_off = reinterpret_cast<const uint64_t*>(dv + o_off);
-    b.node_len = reinterpret_cast<const uint32_t*>(dv + o_len);
-    b.proof_first = reinterpret_cast<const uint32_t*>(dv + o_pf); b.roots = dv + o_roots;
-    b.key_bytes = dv + o_keys; b.key_off = reinterpret_cast<const uint32_t*>(dv + o_koff);
+    b.node_bytes = dv; b.node_off = reinterpret_cast<const uint64_t*>(dv + L.o_off);
+    b.node_len = reinterpret_cast<const uint32_t*>(dv + L.o_len);
+    b.proof_first = reinterpret_cast<const uint32_t*>(dv + L.o_pf); b.roots = dv + L.o_roots;
+    b.key_bytes = dv; b.key_off = reinterpret_cast<const uint32_t*>(dv + L.o_koff);
+    b.key_len = reinterpret_cast<const uint32_t*>(dv + L.o_klen);
     b.root_from_proof = nullptr;
-    b.n_nodes = nn; b.n_proofs = np;
+    b.n_nodes = L.nn; b.n_proofs = np;
     b.byte_base = 0; b.node_base = 0; b.key_base = 0; b.proof_base = 0;
     CK(s.results.reserve(13 * np + 16));
     CK(s.h_results.reserve(13 * np + 16));
@@ -621,7 +609,7 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
     if (rc != MPTV_OK) return rc;
     CK(cudaMemcpyAsync(s.h_results.p, res, 13 * np, cudaMemcpyDeviceToHost, st));
     s.pend_p0 = cs; s.pend_np = np; s.pend_borsh = true;
-    s.h_node_off = o_off; s.h_node_len = o_len; s.h_proof_first = o_pf;
+    s.h_node_off = L.o_off; s.h_node_len = L.o_len; s.h_proof_first = L.o_pf;
     cs = ce;
   }
   for (int k = 0; k < kSlots; k++) {
