@@ -140,6 +140,9 @@ typedef struct mptv_host_stats {
   uint64_t node_bytes_supplied;   /* padded bytes of all supplied nodes                                      */
   uint64_t node_bytes_placed;     /* ... of the nodes actually staged and copied                             */
   uint64_t h2d_bytes, d2h_bytes;  /* bytes that crossed PCIe, counted from the copies issued                 */
+  /* mptv_verify_borsh, microseconds of the calling thread (summed over devices): flattening chunks, waiting for a
+   * free slot / the last chunk, mapping results back to blob offsets, and the whole call */
+  uint64_t flatten_us, wait_us, map_us, call_us;
 } mptv_host_stats;
 int mptv_host_stats_get(mptv_ctx* ctx, mptv_host_stats* out, int reset);
 

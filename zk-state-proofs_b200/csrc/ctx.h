@@ -51,6 +51,7 @@ constexpr size_t kPackedChunkBytes = 256 << 10;  // chunks up to this size cross
 
 struct Slot {
   cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;  // streamed borsh entry: the slot's chunk is through the device (blocking-sync event)
   HostBuf h_results, h_in;
   uint64_t pend_p0 = 0, pend_np = 0;  // results of this proof range are in flight into the staging buffers
   // streamed borsh entry: the chunk was flattened into h_in; these locate its index arrays there, node_src maps
@@ -68,7 +69,8 @@ struct Slot {
     for (DevBuf* b : all) b->release();
     h_results.release(); h_in.release();
     if (stream) cudaStreamDestroy(stream);
-    stream = nullptr;
+    if (done) cudaEventDestroy(done);
+    stream = nullptr; done = nullptr;
   }
 };
 
@@ -130,7 +132,7 @@ struct Device {
   uint32_t last_keccak_launches = 0, last_other_launches = 0;
   Rebuild rb;
   DedupTable dedup_tab;  // host-side candidate table of the streamed borsh entry (one chunk at a time)
-  mptv_host_stats hstat = {0, 0, 0, 0, 0, 0, 0};  // of the host-fed entries since the last reset
+  mptv_host_stats hstat = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // of the host-fed entries since the last reset
 };
 
 }  // namespace mptv

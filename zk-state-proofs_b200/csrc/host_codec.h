@@ -93,23 +93,35 @@ void parallel_for(uint64_t n, int n_threads, F f) {
 
 // A few worker threads that live for one call: run(f) executes f(tid) on all of them (tid 0 = the caller) and
 // returns when every one is done; barrier() may be used inside f (all threads must reach it).
+// The streamed entries call run() a hundred times per call, a chunk every few hundred microseconds, so a handoff
+// through a condition variable (tens of microseconds of wake-up latency, twice per chunk) would cost a sixth of the
+// call.  Workers therefore SPIN for the next job for a short while and only then go to sleep; the caller does the same
+// for completion.  Every wait is bounded spinning followed by yield / sleep, so the pool also behaves when there are
+// more threads than cores (a preempted worker is not waited for by fifteen spinning ones).
 class WorkerPool {
  public:
   explicit WorkerPool(int n) : n_(n < 1 ? 1 : n) {
     for (int t = 1; t < n_; t++) th_.emplace_back([this, t] { loop(t); });
   }
   ~WorkerPool() {
-    { std::lock_guard<std::mutex> g(mu_); stop_ = true; gen_++; }
+    { std::lock_guard<std::mutex> g(mu_); stop_ = true; gen_.fetch_add(1, std::memory_order_release); }
     cv_.notify_all();
     for (auto& x : th_) x.join();
   }
   int size() const { return n_; }
   void run(const std::function<void(int)>& f) {
-    { std::lock_guard<std::mutex> g(mu_); job_ = &f; pending_ = n_ - 1; gen_++; }
-    cv_.notify_all();
+    job_ = &f;
+    pending_.store(n_ - 1, std::memory_order_relaxed);
+    {
+      // the generation is bumped under the mutex so that a worker that decided to sleep cannot miss it
+      std::lock_guard<std::mutex> g(mu_);
+      gen_.fetch_add(1, std::memory_order_release);
+    }
+    if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
     f(0);
-    std::unique_lock<std::mutex> lk(mu_);
-    done_.wait(lk, [this] { return pending_ == 0; });
+    for (int spins = 0; pending_.load(std::memory_order_acquire) != 0; spins++) {
+      if (spins < kSpin) _mm_pause(); else std::this_thread::yield();
+    }
   }
   void barrier() {
     const int g = bar_gen_.load(std::memory_order_acquire);
@@ -117,35 +129,40 @@ class WorkerPool {
       bar_count_.store(0, std::memory_order_relaxed);
       bar_gen_.fetch_add(1, std::memory_order_release);
     } else {
-      while (bar_gen_.load(std::memory_order_acquire) == g) _mm_pause();
+      for (int spins = 0; bar_gen_.load(std::memory_order_acquire) == g; spins++) {
+        if (spins < kSpin) _mm_pause(); else std::this_thread::yield();
+      }
     }
   }
 
  private:
+  static constexpr int kSpin = 20000;  // ~ 50-100 us of pause instructions before giving the core away
   void loop(int t) {
     uint64_t last = 0;
     for (;;) {
-      const std::function<void(int)>* job;
-      {
+      // wait for the next generation: spin first, then sleep
+      int spins = 0;
+      while (gen_.load(std::memory_order_acquire) == last) {
+        if (++spins < kSpin) { _mm_pause(); continue; }
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return gen_ != last; });
-        if (stop_) return;
-        last = gen_;
-        job = job_;
+        sleepers_.fetch_add(1, std::memory_order_acq_rel);
+        cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != last; });
+        sleepers_.fetch_sub(1, std::memory_order_acq_rel);
       }
-      (*job)(t);
-      std::lock_guard<std::mutex> g(mu_);
-      if (--pending_ == 0) done_.notify_one();
+      last = gen_.load(std::memory_order_acquire);
+      if (stop_) return;
+      (*job_)(t);
+      pending_.fetch_sub(1, std::memory_order_acq_rel);
     }
   }
   int n_;
   std::vector<std::thread> th_;
   std::mutex mu_;
-  std::condition_variable cv_, done_;
+  std::condition_variable cv_;
   const std::function<void(int)>* job_ = nullptr;
-  uint64_t gen_ = 0;
-  int pending_ = 0;
-  bool stop_ = false;
+  std::atomic<uint64_t> gen_{0};
+  std::atomic<int> pending_{0}, sleepers_{0};
+  std::atomic<bool> stop_{false};
   std::atomic<int> bar_count_{0}, bar_gen_{0};
 };
 

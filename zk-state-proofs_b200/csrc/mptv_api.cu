@@ -10,6 +10,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -287,6 +290,8 @@ int mptv_host_stats_get(mptv_ctx* ctx, mptv_host_stats* out, int reset) {
     out->chunks += d.hstat.chunks; out->nodes += d.hstat.nodes; out->nodes_aliased += d.hstat.nodes_aliased;
     out->node_bytes_supplied += d.hstat.node_bytes_supplied; out->node_bytes_placed += d.hstat.node_bytes_placed;
     out->h2d_bytes += d.hstat.h2d_bytes; out->d2h_bytes += d.hstat.d2h_bytes;
+    out->flatten_us += d.hstat.flatten_us; out->wait_us += d.hstat.wait_us; out->map_us += d.hstat.map_us;
+    out->call_us += d.hstat.call_us;
     if (reset) memset(&d.hstat, 0, sizeof d.hstat);
   }
   return MPTV_OK;
@@ -502,9 +507,9 @@ struct BorshStream {
   const uint64_t* blob_off;
 };
 
-int drain_slot_borsh(mptv_ctx* ctx, Slot& s, mptv_result* out, WorkerPool& pool) {
-  CK(cudaStreamSynchronize(s.stream));
-  if (!s.pend_np) return MPTV_OK;
+// results of a finished chunk (already in the slot's page-locked result block) -> the caller's arrays
+void map_results_borsh(Slot& s, mptv_result* out, WorkerPool& pool) {
+  if (!s.pend_np) return;
   const uint64_t np = s.pend_np;
   const uint8_t* r = static_cast<const uint8_t*>(s.h_results.p);
   const uint64_t* voff = reinterpret_cast<const uint64_t*>(r);
@@ -539,7 +544,103 @@ int drain_slot_borsh(mptv_ctx* ctx, Slot& s, mptv_result* out, WorkerPool& pool)
   });
   s.pend_np = 0;
   s.pend_borsh = false;
+}
+
+// The streamed entry runs as two parties per device.  The PRODUCER (the calling thread and its worker pool) flattens
+// chunk after chunk into the slots' page-locked blocks and maps finished results back to blob offsets; the SUBMITTER
+// (one thread) issues each filled slot's copies and kernels and waits for the device.  The producer therefore never
+// stalls on CUDA calls: the 20-odd launches and copies of a chunk overlap the flattening of the next one.
+struct BorshPipe {
+  enum { kFree = 0, kFilled, kInFlight, kDone };
+  std::mutex mu;
+  std::condition_variable cv;
+  int state[kSlots];
+  ChunkLayout layout[kSlots];
+  uint64_t produced = 0;  // chunks handed to the submitter
+  bool producer_done = false;
+  int err = MPTV_OK;
+};
+
+int submit_borsh_chunk(mptv_ctx* ctx, Device& d, Slot& s, const ChunkLayout& L) {
+  cudaStream_t st = s.stream;
+  const uint64_t np = L.np;
+  uint8_t* h = static_cast<uint8_t*>(s.h_in.p);
+  uint8_t* dv = s.in_pack.as<uint8_t>();
+  // what was written: the index arrays, then each worker's used prefix of its region (neighbours merged when the
+  // unused gap between them is small)
+  size_t c0 = 0, c1 = L.index_end;
+  uint64_t moved = 0;
+  for (size_t t = 0; t <= L.region_begin.size(); t++) {
+    const bool last = t == L.region_begin.size();
+    if (!last && L.region_used[t] == 0) continue;
+    if (!last && L.region_begin[t] <= c1 + 4096) { c1 = L.region_begin[t] + L.region_used[t]; continue; }
+    CK(cudaMemcpyAsync(dv + c0, h + c0, c1 - c0, cudaMemcpyHostToDevice, st));
+    moved += c1 - c0;
+    if (!last) { c0 = L.region_begin[t]; c1 = c0 + L.region_used[t]; }
+  }
+  d.hstat.chunks++; d.hstat.nodes += L.nn; d.hstat.nodes_aliased += L.nodes_aliased;
+  d.hstat.node_bytes_supplied += L.node_bytes_supplied; d.hstat.node_bytes_placed += L.node_bytes_placed;
+  d.hstat.h2d_bytes += moved; d.hstat.d2h_bytes += 13 * np;
+  DeviceBatch b;
+  b.node_bytes = dv; b.node_off = reinterpret_cast<const uint64_t*>(dv + L.o_off);
+  b.node_len = reinterpret_cast<const uint32_t*>(dv + L.o_len);
+  b.proof_first = reinterpret_cast<const uint32_t*>(dv + L.o_pf); b.roots = dv + L.o_roots;
+  b.key_bytes = dv; b.key_off = reinterpret_cast<const uint32_t*>(dv + L.o_koff);
+  b.key_len = reinterpret_cast<const uint32_t*>(dv + L.o_klen);
+  b.root_from_proof = nullptr;
+  b.n_nodes = L.nn; b.n_proofs = np;
+  b.byte_base = 0; b.node_base = 0; b.key_base = 0; b.proof_base = 0;
+  CK(s.results.reserve(13 * np + 16));
+  CK(s.h_results.reserve(13 * np + 16));
+  uint8_t* res = s.results.as<uint8_t>();
+  const int rc = run_pipeline(ctx, d, b, s.digests, s.meta, s.order, s.bins, s.defer, s.dedup, res + 12 * np,
+                              reinterpret_cast<uint64_t*>(res), reinterpret_cast<uint32_t*>(res + 8 * np), st, false);
+  if (rc != MPTV_OK) return rc;
+  CK(cudaMemcpyAsync(s.h_results.p, res, 13 * np, cudaMemcpyDeviceToHost, st));
+  if (!s.done) CK(cudaEventCreateWithFlags(&s.done, cudaEventBlockingSync | cudaEventDisableTiming));
+  CK(cudaEventRecord(s.done, st));
   return MPTV_OK;
+}
+
+void borsh_submitter(mptv_ctx* ctx, Device& d, BorshPipe& P) {
+  int rc = MPTV_OK;
+  if (cudaSetDevice(d.id) != cudaSuccess) rc = MPTV_ERR_CUDA;
+  auto fail = [&](int e) {
+    std::lock_guard<std::mutex> g(P.mu);
+    if (P.err == MPTV_OK) P.err = e;
+    P.cv.notify_all();
+  };
+  if (rc != MPTV_OK) { fail(rc); return; }
+  uint64_t c = 0;
+  for (;; c++) {
+    const int k = (int)(c % kSlots);
+    {
+      std::unique_lock<std::mutex> lk(P.mu);
+      P.cv.wait(lk, [&] { return P.err != MPTV_OK || c < P.produced || P.producer_done; });
+      if (P.err != MPTV_OK) return;
+      if (c >= P.produced) break;  // the producer is done and chunk c does not exist
+    }
+    rc = submit_borsh_chunk(ctx, d, d.slot[k], P.layout[k]);
+    if (rc != MPTV_OK) { fail(rc); return; }
+    {
+      std::lock_guard<std::mutex> g(P.mu);
+      P.state[k] = BorshPipe::kInFlight;
+    }
+    if (c > 0) {  // wait for the chunk before: the device always has the newest chunk queued behind it
+      const int pk = (int)((c - 1) % kSlots);
+      if (cudaEventSynchronize(d.slot[pk].done) != cudaSuccess) { fail(fail_cuda(ctx, cudaGetLastError(), "mptv_verify_borsh")); return; }
+      std::lock_guard<std::mutex> g(P.mu);
+      P.state[pk] = BorshPipe::kDone;
+      P.cv.notify_all();
+    }
+  }
+  if (c > 0) {
+    const int pk = (int)((c - 1) % kSlots);
+    if (cudaEventSynchronize(d.slot[pk].done) != cudaSuccess) { fail(fail_cuda(ctx, cudaGetLastError(), "mptv_verify_borsh")); return; }
+    std::lock_guard<std::mutex> g(P.mu);
+    P.state[pk] = BorshPipe::kDone;
+    P.cv.notify_all();
+  }
 }
 
 int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv_result* out, uint64_t p0, uint64_t p1,
@@ -549,73 +650,79 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
   const bool alias = ctx->host_dedup != 0;
   if (alias && !d.dedup_tab.reserve((size_t)std::min<uint64_t>(ctx->borsh_chunk_bytes / 128 + 1024, 1ull << 22)))
     return fail_msg(ctx, MPTV_ERR_NOMEM, "mptv_verify_borsh: host table allocation failed");
+  BorshPipe P;
+  for (int k = 0; k < kSlots; k++) P.state[k] = BorshPipe::kFree;
+  double t_wait = 0, t_map = 0, t_flat = 0, t_join = 0;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
+  std::thread submitter([&] { borsh_submitter(ctx, d, P); });
+  int rc = MPTV_OK;
+  const char* why = nullptr;
   size_t ci = 0;
-  for (uint64_t cs = p0; cs < p1; ci++) {
+  for (uint64_t cs = p0; cs < p1 && rc == MPTV_OK; ci++) {
     // the chunk: as many blobs as fit borsh_chunk_bytes of input
     uint64_t ce = (uint64_t)(std::upper_bound(in.blob_off + cs + 1, in.blob_off + p1 + 1, in.blob_off[cs] + ctx->borsh_chunk_bytes) -
                              in.blob_off);
     if (ce > cs + 1) ce--;
     if (ce > p1) ce = p1;
-    Slot& s = d.slot[ci % kSlots];
-    cudaStream_t st = s.stream;
-    int rc = drain_slot_borsh(ctx, s, out, pool);
-    if (rc != MPTV_OK) return rc;
-    const uint64_t np = ce - cs;
+    const int k = (int)(ci % kSlots);
+    Slot& s = d.slot[k];
+    bool have_results = false;
+    double t0 = now();
+    {
+      // the slot's previous chunk (three chunks back) must be through the device before its blocks are reused
+      std::unique_lock<std::mutex> lk(P.mu);
+      P.cv.wait(lk, [&] { return P.err != MPTV_OK || P.state[k] == BorshPipe::kFree || P.state[k] == BorshPipe::kDone; });
+      if (P.err != MPTV_OK) { rc = P.err; break; }
+      have_results = P.state[k] == BorshPipe::kDone;
+    }
+    double t1 = now();
+    if (have_results) map_results_borsh(s, out, pool);
+    double t2 = now();
+    t_wait += t1 - t0; t_map += t2 - t1;
     // one pass over the chunk's blobs, straight into the slot's page-locked block; a node identical to one already
     // placed in this chunk is aliased, not copied (host_flatten.h)
     if (alias) d.dedup_tab.new_epoch();
     const BorshChunkJob job = {in.blobs, in.blob_off, cs, ce, alias ? &d.dedup_tab : nullptr};
-    ChunkLayout L;
     rc = flatten_borsh_chunk(pool, job, [&](size_t total) -> uint8_t* {
       if (s.h_in.reserve(total) != cudaSuccess || s.in_pack.reserve(total) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
       }
       return static_cast<uint8_t*>(s.h_in.p);
-    }, L, &s.node_src, &s.bad_root);
-    if (rc == MPTV_ERR_ARG) return fail_msg(ctx, rc, "mptv_verify_borsh: a blob is not a well-formed borsh(MerkleProofInput)");
-    if (rc != MPTV_OK) return fail_msg(ctx, rc, "mptv_verify_borsh: staging allocation failed");
-    uint8_t* h = static_cast<uint8_t*>(s.h_in.p);
-    uint8_t* dv = s.in_pack.as<uint8_t>();
-    // what was written: the index arrays, then each worker's used prefix of its region (neighbours merged when the
-    // unused gap between them is small)
-    size_t c0 = 0, c1 = L.index_end;
-    uint64_t moved = 0;
-    for (size_t t = 0; t <= L.region_begin.size(); t++) {
-      const bool last = t == L.region_begin.size();
-      if (!last && L.region_used[t] == 0) continue;
-      if (!last && L.region_begin[t] <= c1 + 4096) { c1 = L.region_begin[t] + L.region_used[t]; continue; }
-      CK(cudaMemcpyAsync(dv + c0, h + c0, c1 - c0, cudaMemcpyHostToDevice, st));
-      moved += c1 - c0;
-      if (!last) { c0 = L.region_begin[t]; c1 = c0 + L.region_used[t]; }
+    }, P.layout[k], &s.node_src, &s.bad_root);
+    if (rc != MPTV_OK) {
+      why = rc == MPTV_ERR_ARG ? "mptv_verify_borsh: a blob is not a well-formed borsh(MerkleProofInput)"
+                               : "mptv_verify_borsh: staging allocation failed";
+      break;
     }
-    d.hstat.chunks++; d.hstat.nodes += L.nn; d.hstat.nodes_aliased += L.nodes_aliased;
-    d.hstat.node_bytes_supplied += L.node_bytes_supplied; d.hstat.node_bytes_placed += L.node_bytes_placed;
-    d.hstat.h2d_bytes += moved; d.hstat.d2h_bytes += 13 * np;
-    DeviceBatch b;
-    b.node_bytes = dv; b.node_off = reinterpret_cast<const uint64_t*>(dv + L.o_off);
-    b.node_len = reinterpret_cast<const uint32_t*>(dv + L.o_len);
-    b.proof_first = reinterpret_cast<const uint32_t*>(dv + L.o_pf); b.roots = dv + L.o_roots;
-    b.key_bytes = dv; b.key_off = reinterpret_cast<const uint32_t*>(dv + L.o_koff);
-    b.key_len = reinterpret_cast<const uint32_t*>(dv + L.o_klen);
-    b.root_from_proof = nullptr;
-    b.n_nodes = L.nn; b.n_proofs = np;
-    b.byte_base = 0; b.node_base = 0; b.key_base = 0; b.proof_base = 0;
-    CK(s.results.reserve(13 * np + 16));
-    CK(s.h_results.reserve(13 * np + 16));
-    uint8_t* res = s.results.as<uint8_t>();
-    rc = run_pipeline(ctx, d, b, s.digests, s.meta, s.order, s.bins, s.defer, s.dedup, res + 12 * np,
-                      reinterpret_cast<uint64_t*>(res), reinterpret_cast<uint32_t*>(res + 8 * np), st, false);
-    if (rc != MPTV_OK) return rc;
-    CK(cudaMemcpyAsync(s.h_results.p, res, 13 * np, cudaMemcpyDeviceToHost, st));
-    s.pend_p0 = cs; s.pend_np = np; s.pend_borsh = true;
-    s.h_node_off = L.o_off; s.h_node_len = L.o_len; s.h_proof_first = L.o_pf;
+    t_flat += now() - t2;
+    s.pend_p0 = cs; s.pend_np = ce - cs; s.pend_borsh = true;
+    s.h_node_off = P.layout[k].o_off; s.h_node_len = P.layout[k].o_len; s.h_proof_first = P.layout[k].o_pf;
+    {
+      std::lock_guard<std::mutex> g(P.mu);
+      P.state[k] = BorshPipe::kFilled;
+      P.produced++;
+      P.cv.notify_all();
+    }
     cs = ce;
   }
-  for (int k = 0; k < kSlots; k++) {
-    const int rc = drain_slot_borsh(ctx, d.slot[k], out, pool);
-    if (rc != MPTV_OK) return rc;
+  {
+    std::lock_guard<std::mutex> g(P.mu);
+    if (rc != MPTV_OK && P.err == MPTV_OK) P.err = rc;  // stops the submitter
+    P.producer_done = true;
+    P.cv.notify_all();
   }
+  double tj = now();
+  submitter.join();
+  t_join = now() - tj;
+  // where the producer's time went (mptv_host_stats): flattening is the work, the rest is what the pipeline costs
+  d.hstat.flatten_us += (uint64_t)(t_flat * 1e6); d.hstat.wait_us += (uint64_t)((t_wait + t_join) * 1e6);
+  d.hstat.map_us += (uint64_t)(t_map * 1e6); d.hstat.call_us += (uint64_t)((now() - t_begin) * 1e6);
+  if (rc == MPTV_OK) rc = P.err;
+  if (rc != MPTV_OK) return why ? fail_msg(ctx, rc, why) : rc;
+  for (int k = 0; k < kSlots; k++)
+    if (P.state[k] == BorshPipe::kDone) map_results_borsh(d.slot[k], out, pool);
   return MPTV_OK;
 }
 
@@ -632,7 +739,12 @@ int verify_borsh_run(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_o
   if (!blobs || !blob_off || !out->status || !out->value_off || !out->value_len) return MPTV_ERR_ARG;
   for (uint64_t i = 0; i < n; i++)
     if (blob_off[i + 1] < blob_off[i]) return MPTV_ERR_ARG;  // the chunking below searches the offsets
-  if (n_threads <= 0) n_threads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  // all cores but one per device: the submitter thread of each device needs a share of a core for its CUDA calls
+  if (n_threads <= 0) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nd = (unsigned)ctx->dev.size();
+    n_threads = (int)std::max(1u, std::min(32u * nd, hw > 2 * nd ? hw - nd : hw));
+  }
   const BorshStream in = {blobs, blob_off};
   const int nd = (int)ctx->dev.size();
   std::vector<uint64_t> cut(nd + 1, 0);
