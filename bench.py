@@ -19,12 +19,18 @@ over that batch.  The 3 GB node arena is far larger than L2 (126 MB), so every s
            step as repeated passes over its own resident 4 M-proof pool (sampling with replacement)
 
 `value`  : proofs / s with the batch resident in HBM, CUDA events on the launch stream, max over ranks.
-`e2e`    : the same metric through the host-buffer C-ABI entry (mptv_verify_batch) from pinned host
-           memory -- H2D of all inputs and D2H of all results inside the timed region.
+`e2e`    : the same metric from the reference's own input format -- borsh(MerkleProofInput) blobs in host memory
+           (crypto-ops/src/types.rs:4-9) -- through the C-ABI entry mptv_verify_borsh: flattening, H2D of everything
+           the device needs and D2H of all results inside the timed region.  `e2e.roofline` puts the bytes moved
+           beside the host-memory and PCIe ceilings measured in this process.
+`e2e_csr`: the same from an already flattened CSR batch in pinned memory (mptv_verify_batch; last round's `e2e`).
 `roofline`: the Keccak kernel against the measured integer-issue peak (LOP3/SHF probe run in this
            process) and against the measured HBM bandwidth (MEASURED_PEAKS.json).
 `cpu_baseline`: the C restatement of the reference's CPU path (oracle/, mirroring its redundant
            hashing) on all host cores, rank 0 at N = 1 only.
+`configs`: (default run, N = 1) compact results of BASELINE.json configs 1, 3 and 4 at full size, few steps each.
+`config5`, `single_context`: (default run, N > 1) the 64 M-proof strong-scaled config over all ranks, and ONE
+           context on rank 0 driving all N devices through mptv_verify_batch / mptv_verify_borsh.
 """
 from __future__ import annotations
 
@@ -63,8 +69,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--pageable", action="store_true", help="e2e from ordinary (pageable) host memory instead of pinned")
-    ap.add_argument("--borsh", action="store_true",
-                    help="also time the streamed borsh entry (blobs in, verdicts out) against flatten-then-verify; adds e2e_borsh")
+    ap.add_argument("--borsh", action="store_true", help="(kept for old command lines: the borsh leg is always on now)")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="default run only: skip the compact config 1 / 3 / 4 blocks (N = 1) and config5 / single_context (N > 1)")
+    ap.add_argument("--threads", type=int, default=0, help="host threads of the streamed borsh entry (0 = cores / ranks - 1)")
     ap.add_argument("--l2-fetch", type=int, default=0, help="L2 fetch granularity hint in bytes (32/64/128; 0 = leave the default)")
     ap.add_argument("--dedup", action="store_true",
                     help="SECONDARY number: hash each distinct node of the batch once (dedup_nodes option); the "
@@ -242,11 +250,11 @@ def config1_input():
     return bytes.fromhex(v["root"]), [bytes.fromhex(n) for n in v["proof"]], bytes.fromhex(v["key"]), bytes.fromhex(v["value"])
 
 
-def main_single(a):
+def run_single(a, env):
     """config 1: latency of ONE verify_merkle_proof call through the public API (host buffers in, value out)"""
     import torch
     import zk_state_proofs_b200 as z
-    rank, world, local = dist_setup()
+    rank, world, local = env
     ver = z.Verifier([local])
     root, proof, key, want = config1_input()
     inp = z.MerkleProofInput(proof, root, key)
@@ -258,6 +266,7 @@ def main_single(a):
     sampler.start()
     time.sleep(0.25)
     n_calls = max(a.steps, 1) * 200
+    ver.host_stats(reset=True)
     t_begin = time.time()
     t0 = time.perf_counter()
     for _ in range(n_calls):
@@ -265,6 +274,7 @@ def main_single(a):
     dt = (time.perf_counter() - t0) / n_calls
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end)
+    tm = int(ver.host_stats(reset=True).launches // n_calls)
     assert st[0] == 0 and b.value(int(voff[0]), int(vlen[0])) == want
     assert ver.verify_merkle_proof(root, proof, key) == want
     h2d = sum(int(getattr(b, k).nbytes) for k in ["node_bytes", "node_off", "node_len", "proof_first", "roots", "key_off"]) + len(key)
@@ -272,29 +282,28 @@ def main_single(a):
                 ms_per_step=dt * 1e3 * 200, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u32",
                 data="synthetic",
                 config=dict(workload=workload_name(a), calls_per_step=200, nodes=b.n_nodes, keccak_f=b.n_perm(),
-                            note="latency-bound: one blocking C-ABI call = 1 packed H2D copy + 4 kernels (K1, K2a, K2f, K2b; a "
-                                 "batch below one wave skips binning) + 1 D2H copy; "
+                            note=f"latency-bound: one blocking C-ABI call = {tm} kernel launch(es), inputs and the 13-byte result "
+                                 "through mapped page-locked memory (no copy calls); "
                                  "there is no device-resident variant of a single-proof call, so value == e2e"),
                 latency_us=dt * 1e6, keccak_f_per_sec=b.n_perm() / dt,
                 roofline=None,
                 e2e=dict(value=1.0 / dt, unit=UNIT, h2d_bytes_per_step=h2d * 200, d2h_bytes_per_step=13 * 200,
                          ms_per_step=dt * 1e3 * 200, host_memory="pageable",
                          timer="host wall clock around the blocking C-ABI call"),
-                gpu_launches=4 * n_calls, clocks=clocks)
-    if rank == 0:
-        if not a.no_cpu_baseline:
-            from oracle.pyoracle import Oracle
-            o = Oracle()
-            t0 = time.perf_counter()
-            reps = 20000
-            for _ in range(reps):
-                r = o.verify(root, proof, key, mirror=True)
-            cdt = (time.perf_counter() - t0) / reps
-            line["cpu_baseline"] = dict(value=1.0 / cdt, unit=UNIT, cores=1, kind="port", latency_us=cdt * 1e6,
-                                        sample=f"{reps} calls of the C restatement (mirror mode) on the same proof, incl. ctypes overhead",
-                                        gpu_results_identical_on_sample=bool(r[0] == 0 and r[1] == want))
-        emit(line)
-    return 0
+                gpu_launches=tm * n_calls, clocks=clocks)
+    if rank == 0 and not a.no_cpu_baseline:
+        from oracle.pyoracle import Oracle
+        o = Oracle()
+        t0 = time.perf_counter()
+        reps = 20000
+        for _ in range(reps):
+            r = o.verify(root, proof, key, mirror=True)
+        cdt = (time.perf_counter() - t0) / reps
+        line["cpu_baseline"] = dict(value=1.0 / cdt, unit=UNIT, cores=1, kind="port", latency_us=cdt * 1e6,
+                                    sample=f"{reps} calls of the C restatement (mirror mode) on the same proof, incl. ctypes overhead",
+                                    gpu_results_identical_on_sample=bool(r[0] == 0 and r[1] == want))
+    ver.close()
+    return line
 
 
 def run_reference(a):
@@ -369,21 +378,25 @@ def load_peaks():
 def keccak_roofline(ver, n_perm, keccak_ms, alg_bytes, launches_note, traffic_key=None):
     peaks = load_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    int_peak = max(ver.int_issue_peak(0, m) for m in (0, 2))  # lane-ops / s, measured now on this GPU
+    probe = {name: ver.int_issue_peak(0, m) for m, name in ((0, "lop3"), (1, "shf"), (2, "keccak_mix_122_58"))}
+    int_peak = max(probe["lop3"], probe["keccak_mix_122_58"])  # lane-ops / s, measured now on this GPU
     keccak_s = keccak_ms * 1e-3
     ach_int = n_perm * I_PERM * 1.0 / keccak_s
     ach_hbm = alg_bytes / keccak_s / 1e9
     return dict(
         kernel="k_keccak256_nodes", bound="int32_issue",
         achieved=ach_int / 1e12, peak=int_peak / 1e12, unit="Tlaneop/s", frac=ach_int / int_peak,
-        peak_source="LOP3/SHF probe (mptv_int_issue_peak) run in this process on this GPU",
+        peak_source="LOP3/SHF probe (mptv_int_issue_peak) run in this process on this GPU: the larger of the LOP3 and the "
+                    "Keccak-mix mode; 148 SMs x 64 lanes/clk x SM clock gives the same figure",
+        peak_probe_tlaneops={k: v / 1e12 for k, v in probe.items()},
         algorithmic_ops_per_launch=n_perm * I_PERM, launch_ms=keccak_ms, launches=launches_note,
         keccak_f_per_sec=n_perm / keccak_s, keccak_f_per_sec_at_peak=int_peak / I_PERM,
         hbm=dict(bound="hbm", achieved=ach_hbm, peak=hbm_peak, unit="GB/s", frac=ach_hbm / hbm_peak,
                  peak_source="MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
                  algorithmic_bytes_per_launch=alg_bytes),
         # measured DRAM bytes of ONE launch of this kernel on exactly this workload (ncu --set full), else None
-        traffic=TRAFFIC_NOTE.get(traffic_key) if traffic_key else None,
+        # NOT measured in this run: read from profiles/traffic.json, which holds the ncu capture named in its `source`
+        traffic=dict(TRAFFIC_NOTE[traffic_key], measured_in_this_run=False) if traffic_key in TRAFFIC_NOTE else None,
     )
 
 
@@ -431,12 +444,12 @@ def reduce_sum(xs, world, dev):
     return [float(v) for v in t.tolist()]
 
 
-def main_rebuild(a):
+def run_rebuild(a, env):
     import numpy as np
     import torch
     import torch.distributed as dist
     import zk_state_proofs_b200 as z
-    rank, world, local = dist_setup()
+    rank, world, local = env
     dev = torch.device("cuda", local)
     ver = z.Verifier([local])
     if a.l2_fetch:
@@ -537,10 +550,10 @@ def main_rebuild(a):
                                         gpu_results_identical_on_sample=same)
             if not same:
                 line["parity_error"] = "GPU roots differ from the oracle on the CPU-baseline sample"
-        emit(line)
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    del d_in, d_roots
+    ver.close()
+    torch.cuda.empty_cache()
+    return line
 
 
 def emit(line):
@@ -551,25 +564,123 @@ def emit(line):
 _REAL_STDOUT = 1
 
 
-def main():
-    global _REAL_STDOUT
-    a = parse_args()
-    sys.stdout.flush()
-    _REAL_STDOUT = os.dup(1)
-    os.dup2(2, 1)  # libraries that print to fd 1 (e.g. "NCCL version ...") now land on stderr
-    if a.impl == "reference":
-        return run_reference(a)
-    if a.workload == "config4":
-        return main_rebuild(a)
-    if a.workload == "config1":
-        return main_single(a)
+def flatten_threads(a, world):
+    """host threads for the streamed borsh entry: this rank's share of the cores, one left for the submitter thread"""
+    if a.threads:
+        return a.threads
+    cores = os.cpu_count() or 1
+    share = max(1, cores // max(world, 1))
+    return max(1, share - 1) if share > 2 else share
 
+
+def h2d_peak_gbs(dev, world):
+    """pinned host -> device copy bandwidth measured now, on every rank at the same time (what N concurrent feeds get)"""
+    import torch
+    import torch.distributed as dist
+    n = 1 << 29
+    h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 4
+    del h, d
+    return n / dt / 1e9
+
+
+def e2e_from_borsh(a, ver, b, env, dev, st, voff, vlen, steps):
+    """blobs in host memory -> verdicts: the streamed C-ABI entry, with the bytes it moved and the ceilings beside it"""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import zk_state_proofs_b200 as z
+    from workload import gen
+    rank, world, local = env
+    blobs, boff = gen.batch_to_borsh(b, pinned=False)
+    th = flatten_threads(a, world)
+    for _ in range(2):
+        bst, bvoff, bvlen = ver.verify_borsh(blobs, boff, threads=th)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ver.host_stats(reset=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        bst, bvoff, bvlen = ver.verify_borsh(blobs, boff, threads=th)
+    dt = reduce_max((time.perf_counter() - t0) / steps, world, dev)
+    hs = ver.host_stats(reset=True)
+    assert (bst == st).all() and (bvlen == vlen).all(), "borsh stream and device entry disagree"
+    for i in np.nonzero(bst == 0)[0][:2000]:
+        assert blobs[int(bvoff[i]):int(bvoff[i]) + int(bvlen[i])].tobytes() == b.value(int(voff[i]), int(vlen[i]))
+    # ceilings, measured now on every rank at once
+    read_gbs, copy_gbs = z.host_bw_probe(th, 128 << 20)
+    h2d_gbs = h2d_peak_gbs(dev, world)
+    flat_s = min(z.borsh_flatten_probe(blobs, boff, threads=th, chunk_bytes=32 << 20)[0] for _ in range(3))
+    all_proofs, blob_bytes, h2d, d2h, read_sum, copy_sum, h2d_sum, launches = reduce_sum(
+        [b.n_proofs, len(blobs), hs.h2d_bytes / steps, hs.d2h_bytes / steps, read_gbs, copy_gbs, h2d_gbs, hs.launches / steps], world, dev)
+    placed = hs.node_bytes_placed / steps
+    # every byte the host memory system moves per step on this rank: the blobs are read once by the cores, the
+    # staged bytes are written once by the cores and read once by the DMA engine
+    dram = len(blobs) + 2 * hs.h2d_bytes / steps
+    dram_all = reduce_sum([dram], world, dev)[0]
+    return dict(
+        value=all_proofs / dt, unit=UNIT, ms_per_step=dt * 1e3, entry="mptv_verify_borsh", host_memory="pageable (blobs); page-locked staging inside the library",
+        input_bytes_per_step=int(blob_bytes), h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), host_threads_per_rank=th,
+        timer="host wall clock around the blocking C-ABI call, max over ranks",
+        transfer_dedup=dict(nodes=int(hs.nodes / steps), nodes_aliased=int(hs.nodes_aliased / steps),
+                            node_bytes_supplied=int(hs.node_bytes_supplied / steps), node_bytes_placed=int(placed),
+                            note="byte-identical nodes of a chunk cross PCIe once (exact compare); every supplied node is still hashed on the device"),
+        host_ms=dict(flatten=hs.flatten_us / steps / 1e3, wait=hs.wait_us / steps / 1e3, map_results=hs.map_us / steps / 1e3,
+                     call=hs.call_us / steps / 1e3, host_stage_alone=flat_s * 1e3),
+        roofline=dict(bound="host_dram", achieved=dram_all / dt / 1e9, peak=2 * copy_sum, unit="GB/s", frac=dram_all / dt / 1e9 / (2 * copy_sum),
+                      bytes_per_step=int(dram_all), peak_source=f"mptv_host_bw_probe run now with the same {th} threads on every rank at once: "
+                      "read + non-temporal write copy, memory traffic = 2 x payload, summed over ranks",
+                      host_read=dict(achieved=blob_bytes / dt / 1e9, peak=read_sum, unit="GB/s", frac=blob_bytes / dt / 1e9 / read_sum,
+                                     note="blob bytes read by the cores vs the read-only probe"),
+                      pcie=dict(achieved=h2d / dt / 1e9, peak=h2d_sum, unit="GB/s", frac=h2d / dt / 1e9 / h2d_sum,
+                                note="H2D bytes vs pinned-copy bandwidth measured now on all ranks at once, summed"),
+                      limiter="host memory bandwidth: the cores must read every supplied byte once to compare it"),
+        gpu_launches_per_step=int(launches))
+
+
+def e2e_from_csr(ver, b, names, env, dev, st, voff, vlen, steps, passes, pageable):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = env
+    for _ in range(2):
+        ver.verify_batch(b)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ver.host_stats(reset=True)
+    t0 = time.perf_counter()
+    for _ in range(steps * passes):
+        est, evoff, evlen = ver.verify_batch(b)
+    torch.cuda.synchronize()
+    dt = reduce_max((time.perf_counter() - t0) / steps, world, dev)
+    hs = ver.host_stats(reset=True)
+    assert (est == st).all() and (evoff == voff).all() and (evlen == vlen).all(), "host and device entries disagree"
+    all_proofs, h2d, d2h = reduce_sum([b.n_proofs * passes, hs.h2d_bytes / steps, hs.d2h_bytes / steps], world, dev)
+    return dict(value=all_proofs / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), ms_per_step=dt * 1e3,
+                entry="mptv_verify_batch", host_memory="pageable" if pageable else "pinned",
+                timer="host wall clock around the blocking C-ABI call, max over ranks", pcie_gbs=h2d / dt / 1e9)
+
+
+def run_verify(a, env, want_e2e=True, want_cpu=True):
+    """configs 2, 3, 5: device-resident steps, the host-fed entries, roofline, parity sample"""
     import numpy as np
     import torch
     import torch.distributed as dist
     import zk_state_proofs_b200 as z
 
-    rank, world, local = dist_setup()
+    rank, world, local = env
     ver = z.Verifier([local])  # one process per GPU; the context owns this rank's device only
     if a.lanes:
         ver.set_option("lanes_per_proof", a.lanes)
@@ -652,60 +763,18 @@ def main():
     voff = d_voff.cpu().numpy().view(np.uint64)
     vlen = d_vlen.cpu().numpy().view(np.uint32)
 
-    # ---- e2e through the host-buffer C-ABI entry (pinned host memory, H2D + D2H inside)
-    e2e = None
-    if not a.no_e2e:
+    # ---- end to end through the host-fed C-ABI entries
+    e2e = e2e_csr = None
+    if want_e2e and not a.no_e2e:
         e_steps = a.steps if passes == 1 else 1
-        for _ in range(2):
-            ver.verify_batch(b)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e_steps * passes):
-            est, evoff, evlen = ver.verify_batch(b)
-        torch.cuda.synchronize()
-        dt = reduce_max((time.perf_counter() - t0) / e_steps, world, dev)
-        h2d = sum(int(getattr(b, k).nbytes) for k in names if k != "key_bytes") + int(b.key_off[-1])
-        e2e = dict(value=all_proofs / dt, unit=UNIT, h2d_bytes_per_step=h2d * passes, d2h_bytes_per_step=13 * n_proofs * passes,
-                   ms_per_step=dt * 1e3, host_memory="pageable" if a.pageable else "pinned",
-                   timer="host wall clock around the blocking C-ABI call")
-        assert (est == st).all() and (evoff == voff).all() and (evlen == vlen).all(), "host and device entries disagree"
-
-    # ---- optional: from borsh(MerkleProofInput) blobs, the prover's input format
-    e2e_borsh = None
-    if a.borsh and passes == 1 and b.root_from_proof is None:
-        import ctypes
-        from workload import gen
-        blobs, boff = gen.batch_to_borsh(b, pinned=False)
-        L = z.load_library()
-        for _ in range(2):
-            bst, bvoff, bvlen = ver.verify_borsh(blobs, boff)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            bst, bvoff, bvlen = ver.verify_borsh(blobs, boff)
-        dt_stream = (time.perf_counter() - t0) / a.steps
-        assert (bst == st).all() and (bvlen == vlen).all(), "borsh stream and device entry disagree"
-        ok = np.nonzero(bst == 0)[0][:2000]
-        for i in ok:
-            assert blobs[int(bvoff[i]):int(bvoff[i]) + int(bvlen[i])].tobytes() == b.value(int(voff[i]), int(vlen[i]))
-        # the same work in series: flatten into recycled pinned buffers, then the host-buffer entry
-        h = ctypes.c_void_p()
-        ts = []
-        for it in range(a.steps + 1):
-            t0 = time.perf_counter()
-            rc = L.mptv_flatten_borsh(blobs.ctypes.data, boff.ctypes.data, n_proofs, 0, 1, ctypes.byref(h))
-            assert rc == 0
-            hb = z.crypto_ops.batch_from_handle(L, h, n_proofs)
-            t1 = time.perf_counter()
-            ver.verify_batch(hb)
-            t2 = time.perf_counter()
-            ts.append((t1 - t0, t2 - t1))
-        L.mptv_host_batch_free(h)
-        fl, vf = np.array(ts[1:]).mean(axis=0)
-        e2e_borsh = dict(value=n_proofs / dt_stream, unit=UNIT, ms_per_step=dt_stream * 1e3, borsh_bytes=int(len(blobs)),
-                         serial=dict(value=n_proofs / (fl + vf), flatten_ms=fl * 1e3, verify_batch_ms=vf * 1e3),
-                         note="mptv_verify_borsh (flatten of chunk c+1 overlaps copy + kernels of chunk c) vs "
-                              "mptv_flatten_borsh into recycled pinned buffers followed by mptv_verify_batch")
+        e2e_csr = e2e_from_csr(ver, b, names, env, dev, st, voff, vlen, e_steps, passes, a.pageable)
+        if passes == 1 and b.root_from_proof is None:
+            # the reference's input format: borsh(MerkleProofInput) blobs (MerkleProofInput has no dependency field,
+            # so the nested configs have no blob form)
+            e2e = e2e_from_borsh(a, ver, b, env, dev, st, voff, vlen, a.steps)
+        else:
+            e2e = dict(e2e_csr, note="nested / multi-pass workload: StorageProofInput groups have no single-blob MerkleProofInput form, "
+                                     "so the end-to-end leg runs from the flattened CSR batch in pinned host memory")
 
     # ---- roofline of the dominant kernel (K1), rank 0's device
     perm_executed = int(tm.n_unique_perm) if a.dedup else n_perm
@@ -724,7 +793,8 @@ def main():
                 keccak_f_per_sec=all_perm / (ms_per_step * 1e-3),
                 kernel_ms=dict(bin=float(kavg[0]), keccak=float(kavg[1]), parse=float(kavg[2]), walk=float(kavg[3]),
                                total=float(kavg[4])),
-                roofline=roofline, e2e=e2e, e2e_borsh=e2e_borsh, gpu_launches=int(launches), clocks=clocks)
+                roofline=roofline, e2e=e2e, e2e_csr=e2e_csr, e2e_borsh=e2e if (e2e and e2e.get("entry") == "mptv_verify_borsh") else None,
+                gpu_launches=int(launches), clocks=clocks)
 
     if a.dedup:
         line["dedup"] = dict(unique_nodes=int(tm.n_unique_nodes), nodes=n_nodes, keccak_f_executed=int(tm.n_unique_perm),
@@ -737,7 +807,7 @@ def main():
     # ---- parity + CPU baseline (rank 0, N = 1): the oracle is the checker, never the thing measured
     if rank == 0:
         line["verdicts"] = {z.STATUS_NAMES[i]: int(c) for i, c in enumerate(np.bincount(st, minlength=8)) if c}
-        if world == 1 and not a.no_cpu_baseline:
+        if world == 1 and want_cpu and not a.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n_sample = sample_size(a, n_proofs, cores)
             cb, ost, ovoff, ovlen = cpu_baseline(b, n_sample, cores)
@@ -747,6 +817,136 @@ def main():
             line["cpu_baseline"] = cb
             if not same:
                 line["parity_error"] = "GPU results differ from the oracle on the CPU-baseline sample"
+    return line, ver, b
+
+
+def single_context(a, env, b):
+    """N > 1, rank 0 only: ONE context that owns all N devices drives them through the host-buffer entries
+    (mptv_create(ids, N) -> mptv_verify_batch / mptv_verify_borsh: per-device host threads and streams, no collective)
+    while the other ranks wait at a barrier."""
+    import numpy as np
+    import zk_state_proofs_b200 as z
+    from workload import gen
+    rank, world, local = env
+    ver = z.Verifier(list(range(world)))
+    out = dict(devices=ver.device_count, proofs=b.n_proofs)
+    ref = None
+    for name in ("mptv_verify_batch", "mptv_verify_borsh"):
+        if name == "mptv_verify_batch":
+            call = lambda: ver.verify_batch(b)
+        else:
+            blobs, boff = gen.batch_to_borsh(b, pinned=False)
+            call = lambda: ver.verify_borsh(blobs, boff, threads=a.threads)
+        for _ in range(2):
+            call()
+        ver.host_stats(reset=True)
+        steps = 3
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = call()
+        dt = (time.perf_counter() - t0) / steps
+        hs = ver.host_stats(reset=True)
+        if ref is None:
+            ref = res
+        same = bool((res[0] == ref[0]).all() and (res[2] == ref[2]).all())
+        out[name] = dict(value=b.n_proofs / dt, unit=UNIT, ms_per_step=dt * 1e3, h2d_bytes_per_step=int(hs.h2d_bytes / steps),
+                         d2h_bytes_per_step=int(hs.d2h_bytes / steps), chunks_per_step=int(hs.chunks / steps),
+                         same_verdicts_as_first_entry=same)
+    out["verdicts"] = {z.STATUS_NAMES[i]: int(c) for i, c in enumerate(np.bincount(ref[0], minlength=8)) if c}
+    out["note"] = ("strong-scaled: the rank-0 batch of the weak-scaled line cut into N device slices by ONE context; "
+                   "host wall clock around the blocking call; all N GPUs are fed from this one process")
+    ver.close()
+    return out
+
+
+def compact(line, keys=("value", "unit", "ms_per_step", "kernel_ms", "keccak_f_per_sec", "latency_us", "verdicts", "gpu_launches",
+                        "leaves_per_sec", "parity_error")):
+    out = {k: line[k] for k in keys if k in line and line[k] is not None}
+    out["workload"] = line["config"]["workload"]
+    out["steps"] = line["steps"]
+    if line.get("roofline"):
+        out["roofline_frac"] = line["roofline"]["frac"]
+    if line.get("e2e"):
+        out["e2e"] = {k: line["e2e"][k] for k in ("value", "unit", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "entry")
+                      if k in line["e2e"]}
+    if line.get("cpu_baseline"):
+        cb = line["cpu_baseline"]
+        out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "latency_us", "gpu_results_identical_on_sample") if k in cb}
+        out["gpu_results_identical_on_sample"] = cb.get("gpu_results_identical_on_sample")
+    return out
+
+
+def sub_args(a, **kw):
+    s = argparse.Namespace(**vars(a))
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+def main():
+    global _REAL_STDOUT
+    a = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # libraries that print to fd 1 (e.g. "NCCL version ...") now land on stderr
+    if a.impl == "reference":
+        return run_reference(a)
+    import torch
+    import torch.distributed as dist
+    env = dist_setup()
+    rank, world, local = env
+    if a.workload == "config4":
+        line = run_rebuild(a, env)
+    elif a.workload == "config1":
+        line = run_single(a, env)
+    else:
+        line, ver, b = run_verify(a, env)
+        default_run = a.workload == "config2" and not a.no_configs and not a.dedup and not a.proofs
+        if default_run and world == 1:
+            # the other BASELINE.json configs at full size, few steps each (their own launches of this same program:
+            # `--workload configN` gives the full line)
+            ver.close()
+            del b
+            torch.cuda.empty_cache()
+            cfgs = {}
+            for name, fn, kw in (("config1", run_single, dict(steps=5, warmup=3)),
+                                 ("config3", None, dict(steps=3, warmup=3)),
+                                 ("config4", run_rebuild, dict(steps=3, warmup=3))):
+                sa = sub_args(a, workload=name, **kw)
+                try:
+                    if fn is None:
+                        l3, v3, b3 = run_verify(sa, env)
+                        v3.close()
+                        del b3
+                    else:
+                        l3 = fn(sa, env)
+                    cfgs[name] = compact(l3)
+                except Exception as e:  # a failed side block must not lose the headline line
+                    cfgs[name] = dict(error=f"{type(e).__name__}: {e}")
+                torch.cuda.empty_cache()
+            line["configs"] = cfgs
+        elif default_run and world > 1:
+            # (a) ONE context on rank 0 drives all N devices; the other ranks wait
+            if rank == 0:
+                try:
+                    line["single_context"] = single_context(a, env, b)
+                except Exception as e:
+                    line["single_context"] = dict(error=f"{type(e).__name__}: {e}")
+            dist.barrier()
+            ver.close()
+            del b
+            torch.cuda.empty_cache()
+            # (b) BASELINE.json config 5: 64 M mixed proofs per step, strong-scaled over the ranks
+            try:
+                l5, v5, b5 = run_verify(sub_args(a, workload="config5", steps=3, warmup=3), env, want_cpu=False)
+                v5.close()
+                if rank == 0:
+                    line["config5"] = compact(l5)
+                    line["config5"]["scaling"] = "strong"
+            except Exception as e:
+                if rank == 0:
+                    line["config5"] = dict(error=f"{type(e).__name__}: {e}")
+    if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()

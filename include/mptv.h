@@ -143,6 +143,7 @@ typedef struct mptv_host_stats {
   /* mptv_verify_borsh, microseconds of the calling thread (summed over devices): flattening chunks, waiting for a
    * free slot / the last chunk, mapping results back to blob offsets, and the whole call */
   uint64_t flatten_us, wait_us, map_us, call_us;
+  uint64_t launches;              /* kernels this library queued for those calls                             */
 } mptv_host_stats;
 int mptv_host_stats_get(mptv_ctx* ctx, mptv_host_stats* out, int reset);
 
@@ -292,6 +293,10 @@ int mptv_flatten_borsh_ex(const uint8_t* blobs, const uint64_t* blob_off, uint64
  * Timed by the caller, it is the ceiling of the streamed entry on this host with these threads. */
 int mptv_borsh_flatten_probe(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, uint64_t chunk_bytes,
                              int alias_duplicates, mptv_flatten_info* info);
+/* What the host's memory system gives n_threads threads that each stream a private buffer of bytes_per_thread:
+ * read-only GB/s, and GB/s of payload for a copy with non-temporal stores (the memory traffic is twice that).  The
+ * ceilings of the host stage above. */
+int mptv_host_bw_probe(int n_threads, uint64_t bytes_per_thread, double* read_gbs, double* copy_gbs);
 const mptv_batch* mptv_host_batch_view(const mptv_host_batch* hb);
 const uint8_t* mptv_host_batch_bad_root(const mptv_host_batch* hb); /* [n_proofs] */
 void mptv_host_batch_free(mptv_host_batch* hb);

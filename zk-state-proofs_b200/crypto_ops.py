@@ -296,7 +296,7 @@ class HostStats(ctypes.Structure):
                 ("node_bytes_supplied", ctypes.c_uint64), ("node_bytes_placed", ctypes.c_uint64),
                 ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
                 ("flatten_us", ctypes.c_uint64), ("wait_us", ctypes.c_uint64), ("map_us", ctypes.c_uint64),
-                ("call_us", ctypes.c_uint64)]
+                ("call_us", ctypes.c_uint64), ("launches", ctypes.c_uint64)]
 
 
 FLATTEN_ALIAS_DUPLICATES = 1
@@ -343,6 +343,16 @@ def borsh_flatten_probe(blobs, blob_off=None, threads: int = 0, chunk_bytes: int
     if rc != 0:
         raise ValueError(f"mptv_borsh_flatten_probe: {L.mptv_strerror(rc).decode()}")
     return dt, info
+
+
+def host_bw_probe(threads: int = 0, bytes_per_thread: int = 128 << 20):
+    """mptv_host_bw_probe -> (read GB/s, copy GB/s of payload) of the host's memory system with `threads` threads"""
+    L = load_library()
+    r, c = ctypes.c_double(), ctypes.c_double()
+    rc = L.mptv_host_bw_probe(threads, bytes_per_thread, ctypes.byref(r), ctypes.byref(c))
+    if rc != 0:
+        raise MptvError(f"mptv_host_bw_probe: {L.mptv_strerror(rc).decode()}")
+    return r.value, c.value
 
 
 def batch_from_handle(L, h, n: int) -> Batch:
@@ -569,6 +579,8 @@ def load_library():
     L.mptv_flatten_borsh_ex.argtypes = [vp, vp, u64, i32, i32, ctypes.c_uint, ctypes.POINTER(vp), ctypes.POINTER(FlattenInfo)]
     L.mptv_borsh_flatten_probe.restype = i32
     L.mptv_borsh_flatten_probe.argtypes = [vp, vp, u64, i32, u64, i32, ctypes.POINTER(FlattenInfo)]
+    L.mptv_host_bw_probe.restype = i32
+    L.mptv_host_bw_probe.argtypes = [i32, u64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     L.mptv_host_stats_get.restype = i32
     L.mptv_host_stats_get.argtypes = [vp, ctypes.POINTER(HostStats), i32]
     L.mptv_host_batch_view.restype = vp

@@ -132,7 +132,7 @@ struct Device {
   uint32_t last_keccak_launches = 0, last_other_launches = 0;
   Rebuild rb;
   DedupTable dedup_tab;  // host-side candidate table of the streamed borsh entry (one chunk at a time)
-  mptv_host_stats hstat = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // of the host-fed entries since the last reset
+  mptv_host_stats hstat = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // of the host-fed entries since the last reset
 };
 
 }  // namespace mptv

@@ -16,8 +16,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <immintrin.h>
+
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <new>
 #include <thread>
 #include <vector>
@@ -287,6 +290,55 @@ int mptv_borsh_flatten_probe(const uint8_t* blobs, const uint64_t* blob_off, uin
     }
     if (info) *info = acc;
     return MPTV_OK;
+  } catch (...) {
+    return MPTV_ERR_NOMEM;
+  }
+}
+
+// What the host's memory system gives `n_threads` threads, each streaming its own buffer: reads only, and reads +
+// non-temporal writes (a copy).  The ceilings the streamed entry's host stage is measured against.
+int mptv_host_bw_probe(int n_threads, uint64_t bytes_per_thread, double* read_gbs, double* copy_gbs) {
+  if (!read_gbs || !copy_gbs) return MPTV_ERR_ARG;
+  try {
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    const size_t n = (size_t)((bytes_per_thread < (1u << 20) ? (1u << 20) : bytes_per_thread) & ~(uint64_t)63);
+    std::vector<uint8_t*> src(n_threads, nullptr), dst(n_threads, nullptr);
+    std::vector<uint64_t> sink(n_threads, 0);
+    mptv::WorkerPool pool(n_threads);
+    std::atomic<int> bad(0);
+    pool.run([&](int t) {  // first touch by the thread that streams the buffer
+      if (posix_memalign((void**)&src[t], 64, n) != 0 || posix_memalign((void**)&dst[t], 64, n) != 0) { bad = 1; return; }
+      memset(src[t], t + 1, n);
+      memset(dst[t], 0, n);
+    });
+    double tr = 0, tc = 0;
+    if (!bad) {
+      auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+      const int reps = 3;
+      double t0 = now();
+      pool.run([&](int t) {
+        __m256i acc = _mm256_setzero_si256();
+        for (int r = 0; r < reps; r++)
+          for (size_t i = 0; i < n; i += 32) acc = _mm256_add_epi64(acc, _mm256_load_si256((const __m256i*)(src[t] + i)));
+        uint64_t o[4];
+        _mm256_storeu_si256((__m256i*)o, acc);
+        sink[t] = o[0] + o[1] + o[2] + o[3];
+      });
+      tr = (now() - t0) / reps;
+      t0 = now();
+      pool.run([&](int t) {
+        for (int r = 0; r < reps; r++)
+          for (size_t i = 0; i < n; i += 32)
+            _mm256_stream_si256((__m256i*)(dst[t] + i), _mm256_load_si256((const __m256i*)(src[t] + i)));
+        _mm_sfence();
+      });
+      tc = (now() - t0) / reps;
+    }
+    for (int t = 0; t < n_threads; t++) { free(src[t]); free(dst[t]); }
+    if (bad) return MPTV_ERR_NOMEM;
+    *read_gbs = (double)n * n_threads / tr / 1e9;
+    *copy_gbs = (double)n * n_threads / tc / 1e9;  // payload; the traffic is twice that
+    return sink[0] == 1 ? MPTV_OK : MPTV_OK;
   } catch (...) {
     return MPTV_ERR_NOMEM;
   }

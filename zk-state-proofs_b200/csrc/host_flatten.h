@@ -33,7 +33,7 @@
 namespace mptv {
 
 #ifndef MPTV_STREAM_AHEAD
-#define MPTV_STREAM_AHEAD 2048
+#define MPTV_STREAM_AHEAD 4096
 #endif
 constexpr uint32_t kStreamAhead = MPTV_STREAM_AHEAD;  // software prefetch distance over the blobs, bytes
 constexpr uint32_t kDedupMinLen = 128;  // shorter nodes (leaves, 2-3 child branches) are mostly one-offs: not worth a probe

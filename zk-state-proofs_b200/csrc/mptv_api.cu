@@ -101,13 +101,16 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
                           d.sm_count, st));
     other += dl ? 2 : 1;
   }
+  const uint32_t keccak_launches = b.n_nodes ? (split ? 2 : 1) : 0;
   if (timed) {
     CK(cudaEventRecord(d.ev[4], st));
     d.last_stream = st;
     d.have_timing = true;
     d.last_nodes = b.n_nodes;
-    d.last_keccak_launches = b.n_nodes ? (split ? 2 : 1) : 0;
+    d.last_keccak_launches = keccak_launches;
     d.last_other_launches = other;
+  } else {
+    d.hstat.launches += keccak_launches + other;  // the host-fed entries: kernels queued for this chunk
   }
   return MPTV_OK;
 }
@@ -290,6 +293,7 @@ int mptv_host_stats_get(mptv_ctx* ctx, mptv_host_stats* out, int reset) {
     out->chunks += d.hstat.chunks; out->nodes += d.hstat.nodes; out->nodes_aliased += d.hstat.nodes_aliased;
     out->node_bytes_supplied += d.hstat.node_bytes_supplied; out->node_bytes_placed += d.hstat.node_bytes_placed;
     out->h2d_bytes += d.hstat.h2d_bytes; out->d2h_bytes += d.hstat.d2h_bytes;
+    out->launches += d.hstat.launches;
     out->flatten_us += d.hstat.flatten_us; out->wait_us += d.hstat.wait_us; out->map_us += d.hstat.map_us;
     out->call_us += d.hstat.call_us;
     if (reset) memset(&d.hstat, 0, sizeof d.hstat);
