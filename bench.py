@@ -70,6 +70,9 @@ def parse_args():
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--pageable", action="store_true", help="e2e from ordinary (pageable) host memory instead of pinned")
     ap.add_argument("--borsh", action="store_true", help="(kept for old command lines: the borsh leg is always on now)")
+    ap.add_argument("--shuffled", action="store_true",
+                    help="config2 with the node order of EVERY proof shuffled (the reference accepts: a proof is a set): "
+                         "nothing is chain-shaped, so K2f defers 100 %% of the batch to the cooperative walk K2b -- its worst case")
     ap.add_argument("--no-configs", action="store_true",
                     help="default run only: skip the compact config 1 / 3 / 4 blocks (N = 1) and config5 / single_context (N > 1)")
     ap.add_argument("--threads", type=int, default=0, help="host threads of the streamed borsh entry (0 = cores / ranks - 1)")
@@ -93,7 +96,8 @@ def workload_name(a):
                 "trie, txs 100-300 B, seed 1), one proof per call")
     if a.workload == "config2":
         return (f"config2: {n_proofs_of(a)} account proofs vs synthetic {a.accounts}-account state trie "
-                f"(key=keccak(address), value=account RLP), seed 2")
+                f"(key=keccak(address), value=account RLP), seed 2" +
+                (" [EVERY proof's node order shuffled: 100 % deferred to K2b, its worst case -- secondary number]" if a.shuffled else ""))
     if a.workload == "config3":
         return (f"config3: {n_proofs_of(a)} nested proofs = {n_proofs_of(a) // 4} groups x (1 account proof in a "
                 f"{a.accounts}-account state trie + 3 ERC-20 slot proofs in one of {a.tokens} {a.slots}-slot storage "
@@ -114,7 +118,7 @@ def build_batch(a, rank, pinned):
     if a.workload == "config2":
         trie = gen.SynthTrie(a.accounts, 2, kind=0)
         t1 = time.time()
-        batch = gen.account_batch(trie, n, seed=2 + 1000 * rank, pinned=pinned)
+        batch = gen.account_batch(trie, n, seed=2 + 1000 * rank, pinned=pinned, force_mut=6 if a.shuffled else 0)
         trie.close()
     else:
         seed = 3 if a.workload == "config3" else 5
@@ -276,6 +280,16 @@ def run_single(a, env):
     clocks = sampler.stop(t_begin, t_end)
     tm = int(ver.host_stats(reset=True).launches // n_calls)
     assert st[0] == 0 and b.value(int(voff[0]), int(vlen[0])) == want
+    # the same call without the Python mirror's per-call allocations: prebuilt ctypes structures, raw C-ABI entry
+    import ctypes
+    from zk_state_proofs_b200 import crypto_ops as co
+    cb = co._CBatch(b.node_bytes.ctypes.data, len(b.node_bytes), b.node_off.ctypes.data, b.node_len.ctypes.data, b.n_nodes,
+                    b.proof_first.ctypes.data, 1, b.roots.ctypes.data, b.key_bytes.ctypes.data, b.key_off.ctypes.data, None)
+    cr = co._CResult(st.ctypes.data, voff.ctypes.data, vlen.ctypes.data)
+    t0 = time.perf_counter()
+    for _ in range(n_calls):
+        ver.lib.mptv_verify_batch(ver.ctx, ctypes.byref(cb), ctypes.byref(cr))
+    raw_dt = (time.perf_counter() - t0) / n_calls
     assert ver.verify_merkle_proof(root, proof, key) == want
     h2d = sum(int(getattr(b, k).nbytes) for k in ["node_bytes", "node_off", "node_len", "proof_first", "roots", "key_off"]) + len(key)
     line = dict(metric=METRIC, value=1.0 / dt, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
@@ -283,9 +297,10 @@ def run_single(a, env):
                 data="synthetic",
                 config=dict(workload=workload_name(a), calls_per_step=200, nodes=b.n_nodes, keccak_f=b.n_perm(),
                             note=f"latency-bound: one blocking C-ABI call = {tm} kernel launch(es), inputs and the 13-byte result "
-                                 "through mapped page-locked memory (no copy calls); "
+                                 "through mapped page-locked memory (no copy calls); the floor is one thread's Keccak chain "
+                                 "(4320 alu instructions x 2 issue cycles = 4.4 us per rate block, 4 blocks for the longest node); "
                                  "there is no device-resident variant of a single-proof call, so value == e2e"),
-                latency_us=dt * 1e6, keccak_f_per_sec=b.n_perm() / dt,
+                latency_us=dt * 1e6, latency_us_c_abi=raw_dt * 1e6, keccak_f_per_sec=b.n_perm() / dt,
                 roofline=None,
                 e2e=dict(value=1.0 / dt, unit=UNIT, h2d_bytes_per_step=h2d * 200, d2h_bytes_per_step=13 * 200,
                          ms_per_step=dt * 1e3 * 200, host_memory="pageable",
@@ -859,7 +874,7 @@ def single_context(a, env, b):
     return out
 
 
-def compact(line, keys=("value", "unit", "ms_per_step", "kernel_ms", "keccak_f_per_sec", "latency_us", "verdicts", "gpu_launches",
+def compact(line, keys=("value", "unit", "ms_per_step", "kernel_ms", "keccak_f_per_sec", "latency_us", "latency_us_c_abi", "verdicts", "gpu_launches",
                         "leaves_per_sec", "parity_error")):
     out = {k: line[k] for k in keys if k in line and line[k] is not None}
     out["workload"] = line["config"]["workload"]
@@ -901,7 +916,7 @@ def main():
         line = run_single(a, env)
     else:
         line, ver, b = run_verify(a, env)
-        default_run = a.workload == "config2" and not a.no_configs and not a.dedup and not a.proofs
+        default_run = a.workload == "config2" and not a.no_configs and not a.dedup and not a.proofs and not a.shuffled
         if default_run and world == 1:
             # the other BASELINE.json configs at full size, few steps each (their own launches of this same program:
             # `--workload configN` gives the full line)

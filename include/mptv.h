@@ -175,6 +175,9 @@ int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops
  *   "host_dedup"       mptv_verify_borsh aliases byte-identical nodes of a chunk instead of staging and copying them
  *                      again (default 1).  Transfer de-duplication only: every supplied node is still hashed on the
  *                      device, results are identical
+ *   "latency_path"     a call whose (chunk of the) batch fits one CTA -- at most 128 nodes, 32 proofs, 64 KiB packed;
+ *                      every single verify_merkle_proof call does -- is verified by ONE kernel launch that reads the
+ *                      inputs from, and writes the results to, mapped page-locked memory (default 1)
  *   "binning"          K0 rate-block binning on / off              (default 1)
  *   "fused_classify"   K1 also classifies plain branches / leaves  (default 1)
  *   "fast_walk"        K2f thread-per-proof chain check + K2b on the deferred rest (default 1)

@@ -151,10 +151,13 @@ def _assemble(parts, n_proofs, rfp, pinned):
 
 
 def account_batch(trie: SynthTrie, n_proofs: int, seed: int, p_excl: float = 0.0, p_mut: float = 0.0,
-                  pinned: bool = False):
-    """config 2: account proofs for addresses sampled uniformly from the trie."""
+                  pinned: bool = False, force_mut: int = 0):
+    """config 2: account proofs for addresses sampled uniformly from the trie.  force_mut (1 ... 7) applies that one
+    mutator to EVERY proof (6 = node order shuffled: still accepted by the reference, but nothing is chain-shaped)."""
     rng = np.random.default_rng(seed)
     sel, mut = draw_mix(rng, n_proofs, p_excl, p_mut, trie.n_keys)
+    if force_mut:
+        mut[:] = force_mut
     slot = np.arange(n_proofs, dtype=np.uint64)
     return _assemble([(trie, sel, mut, seed, slot)], n_proofs, None, pinned)
 

@@ -131,6 +131,10 @@ struct Device {
   uint64_t last_nodes = 0;
   uint32_t last_keccak_launches = 0, last_other_launches = 0;
   Rebuild rb;
+  // latency path: a page-locked mailbox mapped into the device's address space (inputs, then results + sequence word)
+  uint8_t* mb_host = nullptr;
+  uint8_t* mb_dev = nullptr;
+  uint32_t mb_seq = 0;
   DedupTable dedup_tab;  // host-side candidate table of the streamed borsh entry (one chunk at a time)
   mptv_host_stats hstat = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // of the host-fed entries since the last reset
 };
@@ -148,6 +152,7 @@ struct mptv_ctx {
   int fused_classify = 1;  // K1 also classifies plain branches / leaves (K2a fast path)
   int dedup_nodes = 0;     // hash each DISTINCT node once (secondary mode, reported separately)
   int host_dedup = 1;      // streamed borsh entry: alias byte-identical nodes of a chunk instead of copying them again
+  int latency_path = 1;    // batches that fit one CTA: one launch, mapped page-locked memory both ways (single_kernels.cu)
   int fast_walk = 1;       // K2f decides chain-shaped proofs one thread each; K2b gets the deferred rest
   int long_leaf_bin = mptv::kLongLeafBin;  // rebuild: leaves in rate-block bins >= this are hashed in their own launch ...
   int long_leaf_ctas = 1;            // ... with this many K1L CTAs (of 4 warps) per SM

@@ -11,6 +11,7 @@ constexpr int kNumBins = 128;            // rate-block-count bins (K0)
 constexpr int kLongLeafBin = 33;         // nodes of more than 32 rate blocks (> 4.3 KB) are hashed in a launch of their own
 constexpr int kBinScratchWords = 2 * kNumBins + 4;  // hist | cursor | K1 tile counter
 constexpr int kBinNodesPerBlock = 4096;  // nodes handled by one CTA of the binning kernels
+constexpr int kWalkThreads = 256;        // K2b CTA size (the latency kernel runs the same walk with fewer threads)
 constexpr int kKeccakThreads = 128;      // K1 CTA size: one node per thread
 constexpr int kKeccakMinBlocks = 4;      // resident CTAs / SM  (=> <= 128 registers / thread)
 
@@ -88,6 +89,26 @@ cudaError_t launch_verify_walk(const DeviceBatch& b, const uint8_t* digests, con
                                int lanes_per_proof, uint8_t* status, uint64_t* value_off, uint32_t* value_len,
                                uint32_t* defer /* scratch [1 + n_proofs]; NULL = K2b on every proof */, int sm_count,
                                cudaStream_t st);
+
+// ------------------------------------------------------------------ latency path (single_kernels.cu)
+// A batch of at most kSmallMaxNodes nodes / kSmallMaxProofs proofs whose packed form fits kSmallMaxPack bytes is
+// verified by ONE launch of one CTA, inputs and results through mapped page-locked memory.
+constexpr int kSmallThreads = 128;       // one warp per scheduler: the critical path is one thread's Keccak chain
+constexpr uint32_t kSmallMaxNodes = 128, kSmallMaxProofs = 32;
+constexpr uint32_t kSmallMaxPack = 64 << 10;
+constexpr int kSmallMaxSmem = 96 << 10;  // pack + guard + digests + records + results
+constexpr uint32_t kSmallOutBytes = 16 + 13 * kSmallMaxProofs + 16 + 64;  // + room for the optional phase clocks (MPTV_SMALL_TIMING)
+struct SmallHeader {
+  uint32_t n_nodes, n_proofs, total;                             // total = bytes of the pack
+  uint32_t o_bytes, o_off, o_len, o_pf, o_roots, o_keys, o_koff, o_rfp, has_rfp;  // arrays inside the pack
+  uint32_t scratch, results;                                     // shared-memory offsets of the kernel's own arrays
+  uint32_t seq;                                                  // written to the mailbox when the results are there
+  uint32_t node_base, key_base;
+  uint64_t byte_base, proof_base;                                // the slice translation of DeviceBatch
+};
+cudaError_t small_init_device();
+cudaError_t launch_verify_small(const uint8_t* mailbox_dev, const SmallHeader& h, uint8_t* out_dev, int lanes_per_proof,
+                                cudaStream_t st);
 
 // ------------------------------------------------------------------ K4: trie rebuild (rebuild_kernels.cu)
 constexpr int kTrieThreads = 128;       // CTA of k_trie_structure (one trie per CTA)

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -167,6 +168,18 @@ int mptv_create(const int* device_ids, int n_devices, mptv_ctx** out) {
     }
     if (e == cudaSuccess) { d.sm_count = prop.multiProcessorCount; e = kernels_init_device(); }
     if (e == cudaSuccess) e = trie_init_device();
+    if (e == cudaSuccess) e = small_init_device();
+    if (e == cudaSuccess) {
+      void* hp = nullptr;
+      e = cudaHostAlloc(&hp, kSmallMaxPack + kSmallOutBytes + 64, cudaHostAllocMapped | cudaHostAllocPortable);
+      if (e == cudaSuccess) {
+        d.mb_host = static_cast<uint8_t*>(hp);
+        memset(d.mb_host, 0, kSmallMaxPack + kSmallOutBytes + 64);
+        void* dp = nullptr;
+        e = cudaHostGetDevicePointer(&dp, hp, 0);
+        d.mb_dev = static_cast<uint8_t*>(dp);
+      }
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
     for (int s = 0; s < kSlots && e == cudaSuccess; s++) e = cudaStreamCreateWithFlags(&d.slot[s].stream, cudaStreamNonBlocking);
     for (int k = 0; k < 6 && e == cudaSuccess; k++) e = cudaEventCreate(&d.ev[k]);
@@ -188,6 +201,8 @@ void mptv_destroy(mptv_ctx* ctx) {
     d.digests.release(); d.meta.release(); d.order.release(); d.bins.release(); d.defer.release(); d.dedup.release();
     for (int k = 0; k < kSlots; k++) d.slot[k].release();
     d.rb.release();
+    if (d.mb_host) cudaFreeHost(d.mb_host);
+    d.mb_host = d.mb_dev = nullptr;
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
     if (d.stream) cudaStreamDestroy(d.stream);
   }
@@ -207,6 +222,8 @@ int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
     ctx->borsh_chunk_bytes = (uint64_t)value;
   } else if (!strcmp(name, "host_dedup")) {
     ctx->host_dedup = value ? 1 : 0;
+  } else if (!strcmp(name, "latency_path")) {
+    ctx->latency_path = value ? 1 : 0;
   } else if (!strcmp(name, "binning")) {
     ctx->binning = value ? 1 : 0;
   } else if (!strcmp(name, "fused_classify")) {
@@ -285,6 +302,16 @@ int mptv_keccak256_batch_device(mptv_ctx* ctx, int dev_index, const uint8_t* nod
   d.last_keccak_launches = n_nodes ? 1 : 0; d.last_other_launches = ctx->binning ? 3 : 0;
   return MPTV_OK;
 }
+
+#ifdef MPTV_SMALL_TIMING
+// diagnostic build only (tools/build_variant.py smalltiming -DMPTV_SMALL_TIMING): SM clocks at the phase boundaries of
+// the last latency-path launch on device 0, relative to its start
+int mptv_debug_small_clocks(mptv_ctx* ctx, long long out5[5]) {
+  if (!ctx || ctx->dev.empty() || !ctx->dev[0].mb_host) return MPTV_ERR_ARG;
+  memcpy(out5, ctx->dev[0].mb_host + kSmallMaxPack + 16 + 13 * kSmallMaxProofs + 16, 5 * sizeof(long long));
+  return MPTV_OK;
+}
+#endif
 
 int mptv_host_stats_get(mptv_ctx* ctx, mptv_host_stats* out, int reset) {
   if (!ctx || !out) return MPTV_ERR_ARG;
@@ -423,6 +450,57 @@ int run_slice_chunks(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result
     const size_t nbytes = (size_t)(byte1 - byte0), kbytes = (size_t)(k1 - k0);
     const size_t small_total = up16(nbytes + 16) + up16(8 * nn) + up16(4 * nn) + 2 * up16(4 * (np + 1)) + up16(32 * np) +
                                up16(kbytes + 16) + (in->root_from_proof ? up16(4 * np) : 0);
+    if (ctx->latency_path && nn <= kSmallMaxNodes && np <= kSmallMaxProofs && small_total + 64 <= kSmallMaxPack && !ctx->dedup_nodes) {
+      // latency path (single_kernels.cu): the whole chunk is packed into the mapped mailbox and verified by ONE launch
+      // that reads it over PCIe and stores the results back; the host polls the sequence word -- no copy calls, no
+      // stream synchronisation.  (A slot that still owes results was drained above.)
+      uint8_t* h = d.mb_host;
+      SmallHeader sh;
+      memset(&sh, 0, sizeof sh);
+      size_t o = 0;
+      auto put = [&](const void* src, size_t bytes, size_t reserve_bytes) {
+        if (bytes) memcpy(h + o, src, bytes);
+        const uint32_t at = (uint32_t)o;
+        o += up16(reserve_bytes);
+        return at;
+      };
+      sh.o_bytes = put(in->node_bytes + byte0, nbytes, nbytes + 16);
+      sh.o_off = put(in->node_off + n0, 8 * nn, 8 * nn);
+      sh.o_len = put(in->node_len + n0, 4 * nn, 4 * nn);
+      sh.o_pf = put(in->proof_first + c.p0, 4 * (np + 1), 4 * (np + 1));
+      sh.o_roots = put(in->roots + 32 * c.p0, 32 * np, 32 * np);
+      sh.o_keys = put(in->key_bytes + k0, kbytes, kbytes + 16);
+      sh.o_koff = put(in->key_off + c.p0, 4 * (np + 1), 4 * (np + 1));
+      sh.has_rfp = in->root_from_proof ? 1 : 0;
+      if (in->root_from_proof) sh.o_rfp = put(in->root_from_proof + c.p0, 4 * np, 4 * np);
+      sh.total = (uint32_t)o;
+      sh.n_nodes = (uint32_t)nn; sh.n_proofs = (uint32_t)np;
+      sh.scratch = (uint32_t)up16(o + 144);  // one rate block of slack: the last node's final block is read whole
+      sh.results = sh.scratch + 32 * (uint32_t)nn + (uint32_t)up16(4 * nn);
+      sh.byte_base = byte0; sh.node_base = n0; sh.key_base = k0; sh.proof_base = c.p0;
+      sh.seq = ++d.mb_seq ? d.mb_seq : ++d.mb_seq;  // never 0
+      uint8_t* ho = d.mb_host + kSmallMaxPack;
+      CK(launch_verify_small(d.mb_dev, sh, d.mb_dev + kSmallMaxPack, pick_lanes(ctx, nn, np), st));
+      d.hstat.launches += 1; d.hstat.chunks++; d.hstat.nodes += nn; d.hstat.node_bytes_supplied += nbytes;
+      d.hstat.node_bytes_placed += nbytes; d.hstat.h2d_bytes += o; d.hstat.d2h_bytes += 13 * np + 4;
+      // poll the sequence word (the kernel runs ~10-20 us); fall back to the stream if it does not show up
+      volatile uint32_t* seqw = reinterpret_cast<volatile uint32_t*>(ho);
+      bool seen = false;
+      for (uint32_t spin = 0; spin < (1u << 22); spin++) {
+        if (*seqw == sh.seq) { seen = true; break; }
+        _mm_pause();
+      }
+      if (!seen) CK(cudaStreamSynchronize(st));
+      if (*seqw != sh.seq) {
+        const cudaError_t e = cudaStreamSynchronize(st);
+        return fail_cuda(ctx, e != cudaSuccess ? e : cudaErrorUnknown, "mptv_verify_batch: latency kernel did not complete");
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+      memcpy(out->value_off + c.p0, ho + 16, 8 * np);
+      memcpy(out->value_len + c.p0, ho + 16 + 8 * np, 4 * np);
+      memcpy(out->status + c.p0, ho + 16 + 12 * np, np);
+      continue;
+    }
     if (small_total <= kPackedChunkBytes) {
       // small chunk (a single verify_merkle_proof call, a handful of proofs): every input array is packed
       // into one page-locked staging block and crosses PCIe as ONE copy -- latency, not bandwidth, matters
