@@ -95,7 +95,8 @@ typedef struct mptv_timings {
   float walk_ms;    /* K2b walk (both waves)            */
   float total_ms;
   uint64_t n_nodes;
-  uint64_t n_perm;  /* Keccak-f permutations = sum ceil((len+1)/136); filled when known, else 0 */
+  uint64_t n_perm;  /* reserved, always 0: the verify entries do not count permutations (sum ceil((len+1)/136) over
+                       the caller's node_len gives it; a dedup_nodes run reports its executed count below)     */
   uint32_t keccak_launches, other_launches;
   uint64_t n_unique_nodes; /* "dedup_nodes" runs: distinct nodes actually hashed (0 otherwise) ... */
   uint64_t n_unique_perm;  /* ... and their Keccak-f count                                        */
@@ -319,6 +320,38 @@ typedef struct mptv_log {
 } mptv_log;
 uint64_t mptv_encode_receipt(int prefix, int status, uint64_t cumulative_gas_used, const uint8_t* bloom256,
                              const mptv_log* logs, uint32_t n_logs, uint8_t* out, uint64_t cap);
+
+/* ---- ABI layout pins.  Bindings mirror these structures field by field (Rust #[repr(C)] in
+ * integration/rust/crypto-ops-gpu/src/lib.rs, ctypes.Structure in zk-state-proofs_b200/crypto_ops.py); a change of
+ * size or field offset on the LP64 targets this library is built for must fail the build here, not corrupt a call. */
+#define MPTV_ABI_PIN(name, cond) typedef char mptv_abi_pin_##name[(cond) ? 1 : -1]
+MPTV_ABI_PIN(batch_size, sizeof(mptv_batch) == 88);
+MPTV_ABI_PIN(batch_node_bytes_len, offsetof(mptv_batch, node_bytes_len) == 8);
+MPTV_ABI_PIN(batch_node_off, offsetof(mptv_batch, node_off) == 16);
+MPTV_ABI_PIN(batch_node_len, offsetof(mptv_batch, node_len) == 24);
+MPTV_ABI_PIN(batch_n_nodes, offsetof(mptv_batch, n_nodes) == 32);
+MPTV_ABI_PIN(batch_proof_first, offsetof(mptv_batch, proof_first) == 40);
+MPTV_ABI_PIN(batch_n_proofs, offsetof(mptv_batch, n_proofs) == 48);
+MPTV_ABI_PIN(batch_roots, offsetof(mptv_batch, roots) == 56);
+MPTV_ABI_PIN(batch_key_bytes, offsetof(mptv_batch, key_bytes) == 64);
+MPTV_ABI_PIN(batch_key_off, offsetof(mptv_batch, key_off) == 72);
+MPTV_ABI_PIN(batch_root_from_proof, offsetof(mptv_batch, root_from_proof) == 80);
+MPTV_ABI_PIN(result_size, sizeof(mptv_result) == 24);
+MPTV_ABI_PIN(result_value_off, offsetof(mptv_result, value_off) == 8);
+MPTV_ABI_PIN(result_value_len, offsetof(mptv_result, value_len) == 16);
+MPTV_ABI_PIN(kv_batch_size, sizeof(mptv_kv_batch) == 72);
+MPTV_ABI_PIN(kv_value_bytes_len, offsetof(mptv_kv_batch, value_bytes_len) == 24);
+MPTV_ABI_PIN(kv_n_items, offsetof(mptv_kv_batch, n_items) == 48);
+MPTV_ABI_PIN(kv_n_tries, offsetof(mptv_kv_batch, n_tries) == 64);
+MPTV_ABI_PIN(proof_targets_size, sizeof(mptv_proof_targets) == 32);
+MPTV_ABI_PIN(proofs_out_size, sizeof(mptv_proofs_out) == 64);
+MPTV_ABI_PIN(proofs_out_n_nodes, offsetof(mptv_proofs_out, n_nodes) == 48);
+MPTV_ABI_PIN(timings_size, sizeof(mptv_timings) == 64);
+MPTV_ABI_PIN(rebuild_timings_size, sizeof(mptv_rebuild_timings) == 64);
+MPTV_ABI_PIN(host_stats_size, sizeof(mptv_host_stats) == 96);
+MPTV_ABI_PIN(flatten_info_size, sizeof(mptv_flatten_info) == 32);
+MPTV_ABI_PIN(log_size, sizeof(mptv_log) == 40);
+#undef MPTV_ABI_PIN
 
 /* page-locked host memory for arenas that are handed to mptv_verify_batch */
 void* mptv_alloc_pinned(size_t bytes);

@@ -28,6 +28,8 @@ pub struct MptvResult {
     pub value_off: *mut u64,
     pub value_len: *mut u32,
 }
+// the layout include/mptv.h pins (MPTV_ABI_PIN): a mismatch fails the build on either side
+const _: () = assert!(std::mem::size_of::<MptvBatch>() == 88 && std::mem::size_of::<MptvResult>() == 24);
 pub enum MptvCtx {}
 pub enum MptvHostBatch {}
 

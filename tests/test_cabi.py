@@ -92,3 +92,19 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
                            "-Wl,-rpath," + libdir])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and "rlp(300) has 3 bytes" in out.stdout
+
+
+def test_binding_structures_match_the_pinned_abi_layout():
+    """include/mptv.h pins sizeof / offsetof of every structure (MPTV_ABI_PIN: the header does not compile if one
+    moves); the ctypes mirrors must have the same sizes and field offsets"""
+    import ctypes
+    from zk_state_proofs_b200 import crypto_ops as co
+    sizes = dict(_CBatch=88, _CResult=24, _CKvBatch=72, _CProofTargets=32, _CProofsOut=64, Timings=64, RebuildTimings=64,
+                 HostStats=96, FlattenInfo=32, _CLog=40)
+    for name, want in sizes.items():
+        assert ctypes.sizeof(getattr(co, name)) == want, name
+    assert [getattr(co._CBatch, f).offset for f, _ in co._CBatch._fields_] == [0, 8, 16, 24, 32, 40, 48, 56, 64, 72, 80]
+    assert [getattr(co._CResult, f).offset for f, _ in co._CResult._fields_] == [0, 8, 16]
+    assert co._CKvBatch.n_items.offset == 48 and co._CKvBatch.n_tries.offset == 64 and co._CProofsOut.n_nodes.offset == 48
+    src = open(os.path.join(ROOT, "include", "mptv.h")).read()
+    assert src.count("MPTV_ABI_PIN(") >= 25

@@ -237,3 +237,41 @@ def test_prefix_heavy_random_tries_on_gpu(verifier, oracle, leaf_mode):
         got = _proofs(b)
         for (t, k), nodes in zip(targets, got):
             assert nodes == oracle.trie_get_proof(d, t, k)[1], (seed, t, k.hex())
+
+
+def test_receipt_path_closes_from_the_leaf_encoder(verifier, oracle, leaf_mode):
+    """the reference's real receipt path end to end (trie-utils/src/receipt.rs:8-38 insert_receipt,
+    proofs/receipt.rs:49-92): leaves built by mptv_encode_receipt -- legacy and typed (EIP-2718 prefix), 0 ... 40 logs
+    with 0 ... 4 topics and 0 ... 512 bytes of data -- keyed alloy_rlp::encode(index), tries rebuilt on the GPU, the
+    proof of EVERY receipt extracted (mptv_trie_proofs) and verified (mptv_verify_batch): each returns exactly the
+    encoded receipt, and the roots equal the CPU restatement's"""
+    import random
+    import zk_state_proofs_b200 as z
+    rng = random.Random(77)
+    tries, flat = [], []
+    for t in range(12):
+        n = rng.choice([1, 2, 17, 128, 129, 300])
+        leaves = []
+        for i in range(n):
+            logs = [z.Log(rng.randbytes(20), [rng.randbytes(32) for _ in range(rng.randrange(5))], rng.randbytes(rng.choice([0, 1, 3, 64, 512])))
+                    for _ in range(rng.choice([0, 0, 1, 2, 5, 40]))]
+            prefix = rng.choice([None, None, 1, 2, 0x7e])
+            leaf = z.encode_receipt(rng.random() < 0.9, rng.randrange(1 << rng.choice([8, 24, 40])), rng.randbytes(256), logs, prefix=prefix)
+            assert (leaf[0] == prefix) if prefix is not None else leaf[0] >= 0xc0
+            leaves.append(leaf)
+        tries.append([(z.rlp_index_native(i), v) for i, v in enumerate(leaves)])
+        flat += leaves
+    kv = z.flatten_kv(tries)
+    d = kv.as_dict()
+    want_roots = oracle.trie_roots(d, nthreads=4)[0]
+    targets = [(t, k) for t, items in enumerate(tries) for k, _ in items]
+    roots, b = verifier.trie_proofs(kv, targets)
+    assert (roots == want_roots).all()
+    st, voff, vlen = verifier.verify_batch(b)
+    assert (st == 0).all()
+    for q, leaf in enumerate(flat):
+        assert b.value(int(voff[q]), int(vlen[q])) == leaf, q
+    # the reference-shaped single call on one of them: the Python mirror of get_ethereum_receipt_proof_inputs minus RPC
+    inp = verifier.transaction_proof_inputs([v for _, v in tries[5]], 1 if len(tries[5]) > 1 else 0)
+    assert verifier.verify_merkle_proof(inp.root_hash, inp.proof, inp.key) == tries[5][1 if len(tries[5]) > 1 else 0][1]
+    assert inp.root_hash == want_roots[5].tobytes()

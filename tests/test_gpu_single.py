@@ -106,3 +106,4 @@ def test_storage_guest_flow_is_one_launch(verifier, oracle):
         except z.VerifyPanic as e:
             got = e.status
         assert got == want
+        assert verifier.host_stats().launches == 1  # account + storage proofs + the key hashes: one launch

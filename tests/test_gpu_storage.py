@@ -103,3 +103,40 @@ def test_hashed_keys_entry_equals_two_step_flow(verifier, oracle):
     for x, y in zip(got, want):
         assert (x == y).all()
     assert (got[0] == 0).sum() > 60 and (got[0] == 4).sum() >= 20
+
+
+def test_hashed_keys_on_the_device_all_key_lengths_both_paths(verifier, oracle):
+    """k_prepare_keys (batch pipeline) and the latency kernel's key step hash the flagged keys on the device, straight
+    from the packed key arena: keys of 0 ... 300 bytes (every rate-block boundary case), flagged and unflagged mixed,
+    small batches (one launch) and large ones (chunked) give what hashing on the host first gives"""
+    import numpy as np
+    import zk_state_proofs_b200 as z
+    from oracle.pytrie import Trie
+    k = oracle.keccak256
+    rng = random.Random(21)
+    lens = [0, 1, 31, 32, 33, 64, 134, 135, 136, 137, 271, 272, 273, 300]
+    raw = [rng.randbytes(n) for n in lens for _ in range(3)]
+    t = Trie({k(r): rng.randbytes(rng.randrange(1, 40)) for r in raw}, k)
+    for n_items, chunk in ((7, 96 << 20), (len(raw), 96 << 20), (len(raw), 1 << 16)):
+        items, flags, want = [], [], []
+        for i, r in enumerate(raw[:n_items]):
+            if i % 3 == 2:   # unflagged: the caller hashed already
+                items.append(z.MerkleProofInput(t.proof(k(r)), t.root, k(r))); flags.append(0)
+            else:
+                items.append(z.MerkleProofInput(t.proof(k(r)), t.root, r)); flags.append(1)
+            want.append(oracle.verify(t.root, t.proof(k(r)), k(r))[:2])
+        b = z.flatten(items)
+        verifier.set_option("chunk_bytes", chunk)
+        try:
+            for lp in (1, 0):
+                verifier.set_option("latency_path", lp)
+                st, voff, vlen = verifier.verify_batch_hashed_keys(b, np.array(flags, np.uint8))
+                for p, (ws, wv) in enumerate(want):
+                    assert st[p] == ws == 0 and b.value(int(voff[p]), int(vlen[p])) == wv, (n_items, chunk, lp, p)
+                # without the flags the raw keys are not what the trie holds (absent, or into an unproven subtree)
+                st2, _, _ = verifier.verify_batch(b)
+                assert all(st2[p] == 0 for p in range(n_items) if not flags[p])
+                assert all(st2[p] in (3, 4) for p in range(n_items) if flags[p])
+        finally:
+            verifier.set_option("chunk_bytes", 96 << 20)
+            verifier.set_option("latency_path", 1)

@@ -844,40 +844,36 @@ class Verifier:
     def verify_storage_proof_input(self, inp: StorageProofInput) -> List[bytes]:
         """The risc0 storage guest (storage-circuit/src/main.rs:6-31): account proof under
         address_keccak, then every storage proof under the account's storage_root with key
-        keccak(storage_key).  Returns the verified storage values; raises VerifyPanic like the guest."""
-        n = min(len(inp.storage_proofs), len(inp.storage_keys))  # .zip() in the guest: the shorter list decides
-        hashed = self._keccak_many(inp.storage_keys[:n])
-        items = [MerkleProofInput(inp.account_proof, inp.root_hash, bytes(inp.address_keccak))]
-        rfp = [-1]
-        for pr, k in zip(inp.storage_proofs, hashed):
-            items.append(MerkleProofInput(pr, b"\x00" * 32, k))
-            rfp.append(0)
-        res = self.verify_merkle_proofs(items, rfp)
-        for r in res:
-            if isinstance(r, VerifyPanic):
-                raise r
-        return res[1:]
+        keccak(storage_key).  Returns the verified storage values; raises VerifyPanic like the guest.
+        ONE C-ABI call: the storage keys are hashed on the device (mptv_verify_batch_hashed_keys) and the roots of
+        the storage proofs are taken on the device from the verified account leaf."""
+        r = self.verify_storage_proof_inputs([inp])[0]
+        if isinstance(r, VerifyPanic):
+            raise r
+        return r
 
     def verify_storage_proof_inputs(self, inputs: Sequence[StorageProofInput]):
         """Batched storage guest: every input's account proof and all of its storage proofs in ONE
-        device batch (storage keys hashed in one Keccak launch, storage roots taken on the device from
-        the verified account leaves).  -> per input: list of storage values, or the VerifyPanic the
+        device batch (storage keys hashed on the device from the caller's raw keys, storage roots taken on the
+        device from the verified account leaves).  -> per input: list of storage values, or the VerifyPanic the
         guest would have died with (the first failing proof in the guest's order)."""
         # the guest zips storage_proofs with storage_keys (main.rs:18-21): the shorter list decides
-        pairs = [list(zip(inp.storage_proofs, inp.storage_keys)) for inp in inputs]
-        hashed = self._keccak_many([k for ps in pairs for _, k in ps])
-        items, rfp, spans = [], [], []
-        hk = 0
-        for inp, ps in zip(inputs, pairs):
+        items, rfp, hk, spans = [], [], [], []
+        for inp in inputs:
             a = len(items)
             items.append(MerkleProofInput(inp.account_proof, inp.root_hash, bytes(inp.address_keccak)))
             rfp.append(-1)
-            for pr, _ in ps:
-                items.append(MerkleProofInput(pr, b"\x00" * 32, hashed[hk]))
+            hk.append(0)
+            for pr, key in zip(inp.storage_proofs, inp.storage_keys):
+                items.append(MerkleProofInput(pr, b"\x00" * 32, bytes(key)))  # raw slot: digest_keccak(&key) happens on the device
                 rfp.append(a)
-                hk += 1
+                hk.append(1)
             spans.append((a, len(items)))
-        res = self.verify_merkle_proofs(items, rfp) if items else []
+        res = []
+        if items:
+            b = flatten(items, rfp)
+            status, voff, vlen = self.verify_batch_hashed_keys(b, np.array(hk, np.uint8))
+            res = [b.value(int(voff[p]), int(vlen[p])) if status[p] == 0 else VerifyPanic(int(status[p])) for p in range(len(items))]
         out = []
         for a, e in spans:
             bad = next((r for r in res[a:e] if isinstance(r, VerifyPanic)), None)

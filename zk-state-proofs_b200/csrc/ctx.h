@@ -62,10 +62,11 @@ struct Slot {
   std::vector<uint8_t> bad_root;  // of the chunk's blobs: root_hash.len() != 32 decides their verdict at drain time
   DevBuf node_bytes, node_off, node_len, proof_first, roots, key_bytes, key_off, rfp;
   DevBuf results, in_pack;
+  DevBuf hk_flags, hk_off, hk_len;  // mptv_verify_batch_hashed_keys: the chunk's flags and the key records built on the device
   DevBuf digests, meta, order, bins, defer, dedup;
   void release() {
     DevBuf* all[] = {&node_bytes, &node_off, &node_len, &proof_first, &roots, &key_bytes, &key_off, &rfp,
-                     &results, &in_pack, &digests, &meta, &order, &bins, &defer, &dedup};
+                     &results, &in_pack, &digests, &meta, &order, &bins, &defer, &dedup, &hk_flags, &hk_off, &hk_len};
     for (DevBuf* b : all) b->release();
     h_results.release(); h_in.release();
     if (stream) cudaStreamDestroy(stream);

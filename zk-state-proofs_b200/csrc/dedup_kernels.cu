@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) k_dedup_insert(const uint8_t* __restrict_
                                                       const uint64_t* __restrict__ node_off, const uint32_t* __restrict__ node_len,
                                                       uint32_t n_nodes, unsigned long long* __restrict__ keys,
                                                       uint32_t* __restrict__ vals, uint32_t mask, uint32_t* __restrict__ slot_of) {
-  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const uint32_t i = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3);  // 64-bit: 8 n_nodes threads may exceed 2^32
   const uint32_t lane = threadIdx.x & 31u, l8 = lane & 7u;
   if (i >= n_nodes) return;  // uniform per group of 8
   const uint32_t gmask = 0xffu << (lane & ~7u);
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_dedup_resolve(const uint8_t* __restrict
                                                        const uint64_t* __restrict__ node_off, const uint32_t* __restrict__ node_len,
                                                        uint32_t n_nodes, const uint32_t* __restrict__ vals,
                                                        const uint32_t* __restrict__ slot_of, uint32_t* __restrict__ dup_of) {
-  const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const uint32_t gid = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3);  // 64-bit, as in k_dedup_insert
   const uint32_t lane = threadIdx.x & 31u, l8 = lane & 7u;
   if (gid >= n_nodes) return;  // uniform per group of 8
   const uint32_t gmask = 0xffu << (lane & ~7u);

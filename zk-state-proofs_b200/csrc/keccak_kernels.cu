@@ -483,6 +483,61 @@ k_keccak256_leaves(const TrieBatchDev in, const uint4* __restrict__ rec, const u
   }
 }
 
+// ------------------------------------------------------------------ key preparation (storage guest)
+// The storage guest looks every storage slot up under digest_keccak(key)
+// (/root/reference/circuits/risc0-storage-proof/storage-proof-circuit/storage-circuit/src/main.rs:26,
+// /root/reference/trie-utils/tests/storage.rs:78).  mptv_verify_batch_hashed_keys does that on the device, inside the
+// chunk pipeline and straight from the caller's key arena: one thread per proof writes the proof's (offset, length)
+// key record, and for a flagged proof first hashes the key (byte loads: the arena is packed, keys are short) into
+// the 32-byte slot behind the raw keys.
+__global__ void __launch_bounds__(128) k_prepare_keys(const uint8_t* __restrict__ key_bytes, const uint32_t* __restrict__ key_off,
+                                                      uint32_t key_base, const uint8_t* __restrict__ hash_key, uint64_t n_proofs,
+                                                      uint8_t* __restrict__ hashed /* 32 n_proofs, 16-byte aligned */,
+                                                      uint32_t hashed_off /* = hashed - key_bytes */,
+                                                      uint32_t* __restrict__ off_out, uint32_t* __restrict__ len_out) {
+  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_proofs) return;
+  const uint32_t o = key_off[p] - key_base, len = key_off[p + 1] - key_off[p];
+  if (!hash_key[p]) { off_out[p] = o; len_out[p] = len; return; }
+  const uint8_t* k = key_bytes + o;
+  uint32_t lo[25], hi[25];
+#pragma unroll
+  for (int i = 0; i < 25; i++) { lo[i] = 0; hi[i] = 0; }
+  for (uint32_t base = 0;; base += 136) {
+    const uint32_t valid = len - base;  // message bytes from the start of this block
+#pragma unroll
+    for (int j = 0; j < 34; j++) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const uint32_t at = 4u * j + c;
+        uint32_t byte = 0;
+        if (at < valid) byte = __ldg(k + base + at);
+        else if (at == valid) byte = 0x01;  // pad10*1 with the Keccak delimiter (keccak.rs:7 v256)
+        w |= byte << (8 * c);
+      }
+      if (j & 1) hi[j >> 1] ^= w; else lo[j >> 1] ^= w;
+    }
+    if (valid < 136u) hi[16] ^= 0x80000000u;
+    keccak_f1600(lo, hi);
+    if (valid < 136u) break;
+  }
+  uint4* out = reinterpret_cast<uint4*>(hashed + 32 * p);
+  out[0] = make_uint4(lo[0], hi[0], lo[1], hi[1]);
+  out[1] = make_uint4(lo[2], hi[2], lo[3], hi[3]);
+  off_out[p] = hashed_off + 32u * (uint32_t)p;
+  len_out[p] = 32;
+}
+
+cudaError_t launch_prepare_keys(const uint8_t* key_bytes, const uint32_t* key_off, uint32_t key_base, const uint8_t* hash_key,
+                                uint64_t n_proofs, uint8_t* hashed, uint32_t hashed_off, uint32_t* off_out, uint32_t* len_out,
+                                cudaStream_t st) {
+  if (n_proofs == 0) return cudaSuccess;
+  k_prepare_keys<<<(unsigned)((n_proofs + 127) / 128), 128, 0, st>>>(key_bytes, key_off, key_base, hash_key, n_proofs, hashed, hashed_off,
+                                                                   off_out, len_out);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ host launchers
 size_t keccak_smem_bytes() { return (size_t)kStages * kKeccakThreads * kSlotBytes; }
 

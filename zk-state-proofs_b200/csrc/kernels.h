@@ -79,6 +79,12 @@ cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base
                                    uint8_t* digests, uint32_t* meta, uint32_t* tile_counter /* 1 u32 of scratch or NULL */,
                                    int sm_count, cudaStream_t st, const uint32_t* split = nullptr, int long_ctas = 1);
 
+// storage guest: per-proof key records (offset from key_bytes, length); the keys of proofs with hash_key[p] != 0 are
+// replaced by their Keccak-256, written to hashed[32 p ..] (hashed_off = hashed - key_bytes, same allocation)
+cudaError_t launch_prepare_keys(const uint8_t* key_bytes, const uint32_t* key_off, uint32_t key_base, const uint8_t* hash_key,
+                                uint64_t n_proofs, uint8_t* hashed, uint32_t hashed_off, uint32_t* off_out, uint32_t* len_out,
+                                cudaStream_t st);
+
 // K2a: meta[i] = eager-decode record of node i.  only_slow: leave records != kMetaSlow untouched
 cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
                                const uint32_t* node_len, uint64_t n_nodes, uint32_t* meta, bool only_slow,
@@ -101,6 +107,7 @@ constexpr uint32_t kSmallOutBytes = 16 + 13 * kSmallMaxProofs + 16 + 64;  // + r
 struct SmallHeader {
   uint32_t n_nodes, n_proofs, total;                             // total = bytes of the pack
   uint32_t o_bytes, o_off, o_len, o_pf, o_roots, o_keys, o_koff, o_rfp, has_rfp;  // arrays inside the pack
+  uint32_t o_hk, has_hk, hk_scratch;                             // hash_key flags (hashed-keys entry) and the kernel's key records
   uint32_t scratch, results;                                     // shared-memory offsets of the kernel's own arrays
   uint32_t seq;                                                  // written to the mailbox when the results are there
   uint32_t node_base, key_base;

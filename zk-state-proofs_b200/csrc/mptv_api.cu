@@ -163,7 +163,7 @@ int mptv_create(const int* device_ids, int n_devices, mptv_ctx** out) {
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, d.id);
     if (e == cudaSuccess && (prop.major != 10 || prop.minor != 0)) {  // the library holds sm_100a code only
       fprintf(stderr, "mptv_create: device %d is sm_%d%d, this library is built for sm_100a (B200)\n", d.id, prop.major, prop.minor);
-      delete ctx;
+      mptv_destroy(ctx);  // streams / events of the devices set up before this one
       return MPTV_ERR_NODEV;
     }
     if (e == cudaSuccess) { d.sm_count = prop.multiProcessorCount; e = kernels_init_device(); }
@@ -395,9 +395,11 @@ int validate_slice(const mptv_batch* in, uint64_t p0, uint64_t p1) {
     const uint64_t o = in->node_off[i];
     if (o & 15) return MPTV_ERR_ALIGN;
     if (in->node_len[i] > kMaxNodeLen) return MPTV_ERR_ARG;
+    // the node must lie inside the caller's arena: checked without forming o + len (a huge offset must not wrap),
+    // and exactly -- only the up-to-15 padding bytes after a node, which are never hashed, may be past the end
+    if (o > in->node_bytes_len || in->node_len[i] > in->node_bytes_len - o) return MPTV_ERR_ARG;
     if (o < prev_end && i > n0) return MPTV_ERR_ARG;  // nodes must be laid out in index order
     prev_end = o + in->node_len[i];
-    if (((prev_end + 15) & ~15ull) > ((in->node_bytes_len + 15) & ~15ull)) return MPTV_ERR_ARG;
   }
   return MPTV_OK;
 }
@@ -419,7 +421,8 @@ int drain_slot(mptv_ctx* ctx, Slot& s, mptv_result* out) {
 inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // run one device's slice [p0, p1): chunked, multi-buffered H2D -> kernels -> D2H
-int run_slice_chunks(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result* out, uint64_t p0, uint64_t p1) {
+int run_slice_chunks(mptv_ctx* ctx, Device& d, const mptv_batch* in, const uint8_t* hash_key, mptv_result* out, uint64_t p0,
+                     uint64_t p1) {
   if (p1 <= p0) return MPTV_OK;
   CK(cudaSetDevice(d.id));
   int rc = MPTV_OK;
@@ -473,10 +476,13 @@ int run_slice_chunks(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result
       sh.o_koff = put(in->key_off + c.p0, 4 * (np + 1), 4 * (np + 1));
       sh.has_rfp = in->root_from_proof ? 1 : 0;
       if (in->root_from_proof) sh.o_rfp = put(in->root_from_proof + c.p0, 4 * np, 4 * np);
+      sh.has_hk = hash_key ? 1 : 0;
+      if (hash_key) sh.o_hk = put(hash_key + c.p0, np, np);
       sh.total = (uint32_t)o;
       sh.n_nodes = (uint32_t)nn; sh.n_proofs = (uint32_t)np;
       sh.scratch = (uint32_t)up16(o + 144);  // one rate block of slack: the last node's final block is read whole
       sh.results = sh.scratch + 32 * (uint32_t)nn + (uint32_t)up16(4 * nn);
+      if (hash_key) { sh.hk_scratch = sh.results; sh.results += 40 * (uint32_t)np; }  // hashed keys 32 np | offsets 4 np | lengths 4 np
       sh.byte_base = byte0; sh.node_base = n0; sh.key_base = k0; sh.proof_base = c.p0;
       sh.seq = ++d.mb_seq ? d.mb_seq : ++d.mb_seq;  // never 0
       uint8_t* ho = d.mb_host + kSmallMaxPack;
@@ -501,7 +507,7 @@ int run_slice_chunks(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result
       memcpy(out->status + c.p0, ho + 16 + 12 * np, np);
       continue;
     }
-    if (small_total <= kPackedChunkBytes) {
+    if (small_total <= kPackedChunkBytes && !hash_key) {
       // small chunk (a single verify_merkle_proof call, a handful of proofs): every input array is packed
       // into one page-locked staging block and crosses PCIe as ONE copy -- latency, not bandwidth, matters
       CK(s.h_in.reserve(small_total));
@@ -527,15 +533,24 @@ int run_slice_chunks(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result
                               : nullptr;
       CK(cudaMemcpyAsync(dv, h, o, cudaMemcpyHostToDevice, st));
       d.hstat.h2d_bytes += o;
+      b.key_len = nullptr;
+      b.key_base = k0;
     } else {
       CK(s.node_bytes.reserve(nbytes + 16));
       CK(s.node_off.reserve(8 * nn + 8));
       CK(s.node_len.reserve(4 * nn + 4));
       CK(s.proof_first.reserve(4 * (np + 1)));
       CK(s.roots.reserve(32 * np));
-      CK(s.key_bytes.reserve(kbytes + 16));
+      const size_t hashed_off = up16(kbytes + 16);  // keccak256 of the flagged keys goes behind the raw keys, same allocation
+      CK(s.key_bytes.reserve(hash_key ? hashed_off + 32 * np : kbytes + 16));
       CK(s.key_off.reserve(4 * (np + 1)));
       if (in->root_from_proof) CK(s.rfp.reserve(4 * np));
+      if (hash_key) {
+        CK(s.hk_flags.reserve(np));
+        CK(s.hk_off.reserve(4 * np));
+        CK(s.hk_len.reserve(4 * np));
+        CK(cudaMemcpyAsync(s.hk_flags.p, hash_key + c.p0, np, cudaMemcpyHostToDevice, st));
+      }
       CK(cudaMemcpyAsync(s.node_bytes.p, in->node_bytes + byte0, nbytes, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(s.node_off.p, in->node_off + n0, 8 * nn, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(s.node_len.p, in->node_len + n0, 4 * nn, cudaMemcpyHostToDevice, st));
@@ -551,10 +566,19 @@ int run_slice_chunks(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result
       b.proof_first = s.proof_first.as<uint32_t>(); b.roots = s.roots.as<uint8_t>();
       b.key_bytes = s.key_bytes.as<uint8_t>(); b.key_off = s.key_off.as<uint32_t>();
       b.root_from_proof = in->root_from_proof ? s.rfp.as<int32_t>() : nullptr;
+      b.key_len = nullptr;
+      b.key_base = k0;
+      if (hash_key) {
+        // the storage guest's digest_keccak(key) on the device, straight from the caller's key arena
+        CK(launch_prepare_keys(s.key_bytes.as<uint8_t>(), s.key_off.as<uint32_t>(), k0, s.hk_flags.as<uint8_t>(), np,
+                               s.key_bytes.as<uint8_t>() + hashed_off, (uint32_t)hashed_off, s.hk_off.as<uint32_t>(),
+                               s.hk_len.as<uint32_t>(), st));
+        d.hstat.launches += 1; d.hstat.h2d_bytes += np;
+        b.key_off = s.hk_off.as<uint32_t>(); b.key_len = s.hk_len.as<uint32_t>(); b.key_base = 0;
+      }
     }
-    b.key_len = nullptr;
     b.n_nodes = nn; b.n_proofs = np;
-    b.byte_base = byte0; b.node_base = n0; b.key_base = k0; b.proof_base = c.p0;
+    b.byte_base = byte0; b.node_base = n0; b.proof_base = c.p0;
     CK(s.results.reserve(13 * np + 16));
     CK(s.h_results.reserve(13 * np + 16));
     uint8_t* res = s.results.as<uint8_t>();
@@ -573,8 +597,8 @@ int run_slice_chunks(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result
   return MPTV_OK;
 }
 
-int run_slice(mptv_ctx* ctx, Device& d, const mptv_batch* in, mptv_result* out, uint64_t p0, uint64_t p1) {
-  const int rc = run_slice_chunks(ctx, d, in, out, p0, p1);
+int run_slice(mptv_ctx* ctx, Device& d, const mptv_batch* in, const uint8_t* hash_key, mptv_result* out, uint64_t p0, uint64_t p1) {
+  const int rc = run_slice_chunks(ctx, d, in, hash_key, out, p0, p1);
   if (rc != MPTV_OK) quiesce(d);  // earlier chunks may still be reading the caller's buffers / owe results
   return rc;
 }
@@ -862,7 +886,7 @@ int mptv_verify_borsh(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_
   }
 }
 
-int mptv_verify_batch(mptv_ctx* ctx, const mptv_batch* in, mptv_result* out) {
+static int verify_batch_impl(mptv_ctx* ctx, const mptv_batch* in, const uint8_t* hash_key, mptv_result* out) {
   if (!ctx || !in || !out) return MPTV_ERR_ARG;
   if (in->n_proofs == 0) return MPTV_OK;
   if (!in->node_off || !in->node_len || !in->proof_first || !in->roots || !in->key_off || !out->status ||
@@ -894,60 +918,30 @@ int mptv_verify_batch(mptv_ctx* ctx, const mptv_batch* in, mptv_result* out) {
   }
   std::vector<int> rcs(nd, MPTV_OK);
   if (nd == 1) {
-    rcs[0] = run_slice(ctx, ctx->dev[0], in, out, cut[0], cut[1]);
+    rcs[0] = run_slice(ctx, ctx->dev[0], in, hash_key, out, cut[0], cut[1]);
   } else {
     std::vector<std::thread> th;
     for (int k = 0; k < nd; k++)
-      th.emplace_back([&, k] { rcs[k] = run_slice(ctx, ctx->dev[k], in, out, cut[k], cut[k + 1]); });
+      th.emplace_back([&, k] { rcs[k] = run_slice(ctx, ctx->dev[k], in, hash_key, out, cut[k], cut[k + 1]); });
     for (auto& t : th) t.join();
   }
   for (int k = 0; k < nd; k++) if (rcs[k] != MPTV_OK) return rcs[k];
   return MPTV_OK;
 }
 
-static int verify_batch_hashed_keys_run(mptv_ctx* ctx, const mptv_batch* in, const uint8_t* hash_key, mptv_result* out) {
-  if (!hash_key) return mptv_verify_batch(ctx, in, out);
-  if (!ctx || !in || !out) return MPTV_ERR_ARG;
-  if (in->n_proofs == 0) return MPTV_OK;
-  if (!in->key_off) return MPTV_ERR_ARG;
-  const uint64_t n = in->n_proofs;
-  // 1. the flagged keys as a 16-byte aligned arena -> keccak256 on the device
-  std::vector<uint64_t> koff;
-  std::vector<uint32_t> klen;
-  std::vector<uint8_t> arena;
-  for (uint64_t p = 0; p < n; p++) {
-    if (!hash_key[p]) continue;
-    if (in->key_off[p + 1] < in->key_off[p]) return MPTV_ERR_ARG;
-    const uint32_t l = in->key_off[p + 1] - in->key_off[p];
-    koff.push_back(arena.size());
-    klen.push_back(l);
-    if (l) arena.insert(arena.end(), in->key_bytes + in->key_off[p], in->key_bytes + in->key_off[p] + l);
-    arena.resize((arena.size() + 15) & ~(size_t)15, 0);
+int mptv_verify_batch(mptv_ctx* ctx, const mptv_batch* in, mptv_result* out) {
+  try {  // per-device threads / slice tables; the C ABI never throws
+    return verify_batch_impl(ctx, in, nullptr, out);
+  } catch (...) {
+    return MPTV_ERR_NOMEM;
   }
-  arena.resize(arena.size() + 16, 0);
-  std::vector<uint8_t> dig(32 * koff.size() + 1);
-  int rc = mptv_keccak256_batch(ctx, arena.data(), arena.size(), koff.data(), klen.data(), koff.size(), dig.data());
-  if (rc != MPTV_OK) return rc;
-  // 2. the same batch with those keys replaced by their digests
-  std::vector<uint8_t> keys;
-  std::vector<uint32_t> off(n + 1, 0);
-  size_t h = 0;
-  for (uint64_t p = 0; p < n; p++) {
-    if (hash_key[p]) { keys.insert(keys.end(), dig.begin() + 32 * h, dig.begin() + 32 * h + 32); h++; }
-    else keys.insert(keys.end(), in->key_bytes + in->key_off[p], in->key_bytes + in->key_off[p + 1]);
-    if (keys.size() > 0xfffffff0ull) return MPTV_ERR_ARG;
-    off[p + 1] = (uint32_t)keys.size();
-  }
-  keys.resize(keys.size() + 16, 0);
-  mptv_batch b = *in;
-  b.key_bytes = keys.data();
-  b.key_off = off.data();
-  return mptv_verify_batch(ctx, &b, out);
 }
 
+// The flags travel with each chunk and the flagged keys are hashed on the device inside the chunk pipeline
+// (k_prepare_keys), straight from the caller's key arena: no host-side key table, no extra pass over the batch.
 int mptv_verify_batch_hashed_keys(mptv_ctx* ctx, const mptv_batch* in, const uint8_t* hash_key, mptv_result* out) {
-  try {  // the key tables below are host vectors sized by the batch; the C ABI never throws
-    return verify_batch_hashed_keys_run(ctx, in, hash_key, out);
+  try {
+    return verify_batch_impl(ctx, in, hash_key, out);
   } catch (...) {
     return MPTV_ERR_NOMEM;
   }
@@ -961,7 +955,7 @@ static int keccak256_batch_run(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_
   for (uint64_t i = 0; i < n_nodes; i++) {
     if (node_off[i] & 15) return MPTV_ERR_ALIGN;
     if (node_len[i] > kMaxNodeLen) return MPTV_ERR_ARG;
-    if (((node_off[i] + node_len[i] + 15) & ~15ull) > ((node_bytes_len + 15) & ~15ull)) return MPTV_ERR_ARG;
+    if (node_off[i] > node_bytes_len || node_len[i] > node_bytes_len - node_off[i]) return MPTV_ERR_ARG;  // no wrap, exact end
   }
   Device& d = ctx->dev[0];
   Slot& s = d.slot[0];

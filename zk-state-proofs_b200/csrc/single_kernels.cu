@@ -59,6 +59,34 @@ __device__ void keccak256_shared(const uint8_t* p, uint32_t len, uint32_t out[8]
   out[4] = lo[2]; out[5] = hi[2]; out[6] = lo[3]; out[7] = hi[3];
 }
 
+// the same for a short message at any alignment (a storage key): byte loads
+__device__ void keccak256_bytes(const uint8_t* p, uint32_t len, uint32_t out[8]) {
+  uint32_t lo[25], hi[25];
+#pragma unroll
+  for (int i = 0; i < 25; i++) { lo[i] = 0; hi[i] = 0; }
+  for (uint32_t base = 0;; base += 136) {
+    const uint32_t valid = len - base;
+#pragma unroll
+    for (int j = 0; j < 34; j++) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const uint32_t at = 4u * j + c;
+        uint32_t byte = 0;
+        if (at < valid) byte = p[base + at];
+        else if (at == valid) byte = 0x01;
+        w |= byte << (8 * c);
+      }
+      if (j & 1) hi[j >> 1] ^= w; else lo[j >> 1] ^= w;
+    }
+    if (valid < 136u) hi[16] ^= 0x80000000u;
+    keccak_f1600(lo, hi);
+    if (valid < 136u) break;
+  }
+  out[0] = lo[0]; out[1] = hi[0]; out[2] = lo[1]; out[3] = hi[1];
+  out[4] = lo[2]; out[5] = hi[2]; out[6] = lo[3]; out[7] = hi[3];
+}
+
 template <int G>
 __global__ void __launch_bounds__(kSmallThreads, 1)
 k_verify_small(const uint8_t* __restrict__ mailbox /* mapped page-locked host memory */, SmallHeader h,
@@ -91,6 +119,26 @@ k_verify_small(const uint8_t* __restrict__ mailbox /* mapped page-locked host me
   b.key_len = nullptr;
   b.root_from_proof = h.has_rfp ? reinterpret_cast<const int32_t*>(sm + h.o_rfp) : nullptr;
   b.byte_base = h.byte_base; b.node_base = h.node_base; b.key_base = h.key_base; b.proof_base = h.proof_base;
+  // ---- 1b. the storage guest's digest_keccak(key) for the flagged proofs (mptv_verify_batch_hashed_keys), on the
+  // threads the node loop below uses last
+  if (h.has_hk) {
+    uint8_t* hashed = sm + h.hk_scratch;
+    uint32_t* koff2 = reinterpret_cast<uint32_t*>(hashed + 32u * h.n_proofs);
+    uint32_t* klen2 = koff2 + h.n_proofs;
+    const uint8_t* flags = sm + h.o_hk;
+    for (uint32_t p = kSmallThreads - 1 - tid; p < h.n_proofs; p += kSmallThreads) {
+      const uint32_t o = b.key_off[p] - b.key_base, len = b.key_off[p + 1] - b.key_off[p];
+      if (!flags[p]) { koff2[p] = o; klen2[p] = len; continue; }
+      uint32_t d[8];
+      keccak256_bytes(b.key_bytes + o, len, d);
+      uint4* q = reinterpret_cast<uint4*>(hashed + 32u * p);
+      q[0] = make_uint4(d[0], d[1], d[2], d[3]);
+      q[1] = make_uint4(d[4], d[5], d[6], d[7]);
+      koff2[p] = (uint32_t)(hashed - b.key_bytes) + 32u * p;
+      klen2[p] = 32;
+    }
+    b.key_off = koff2; b.key_len = klen2; b.key_base = 0;
+  }
   // ---- 2. digest_keccak + decode_node of every supplied node, one thread each.  Consecutive nodes go to different
   // warps (schedulers): a warp instruction occupies its scheduler's 16-lane alu pipe for two cycles however few lanes
   // are active, so nodes that share a warp gain nothing and serialise wherever their code paths differ (last-block

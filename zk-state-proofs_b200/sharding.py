@@ -49,9 +49,9 @@ def take_slice(b: Batch, p0: int, p1: int) -> Batch:
     rfp = None
     if b.root_from_proof is not None:
         rfp = b.root_from_proof[p0:p1].copy()
-        rfp[rfp >= 0] -= p0
-        if (rfp < -1).any():
+        if ((rfp >= 0) & (rfp < p0)).any():  # checked on the ORIGINAL values: p0 - 1 would rebase to -1 = "independent"
             raise ValueError("slice separates a storage proof from its account proof")
+        rfp[rfp >= 0] -= p0
     node_bytes = b.node_bytes[byte0:byte1 + 16]
     if len(node_bytes) < byte1 - byte0 + 16:
         node_bytes = np.concatenate([node_bytes, np.zeros(byte1 - byte0 + 16 - len(node_bytes), np.uint8)])
