@@ -153,7 +153,8 @@ int mptv_host_stats_get(mptv_ctx* ctx, mptv_host_stats* out, int reset);
 int mptv_verify_batch_device(mptv_ctx* ctx, int dev_index, const mptv_batch* in, mptv_result* out,
                              void* stream);
 
-/* digest_keccak over a whole CSR arena: digests32[32i..] = keccak256(node i).  Host buffers. */
+/* digest_keccak over a whole CSR arena: digests32[32i..] = keccak256(node i).  Host buffers; the nodes are cut into
+ * contiguous index ranges with equal shares of the bytes, one per device of the context (no inter-device traffic). */
 int mptv_keccak256_batch(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node_bytes_len,
                          const uint64_t* node_off, const uint32_t* node_len, uint64_t n_nodes,
                          uint8_t* digests32);

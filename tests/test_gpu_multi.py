@@ -47,6 +47,15 @@ def test_one_context_two_devices_matches_one_device(verifier):
     ref = verifier.verify_batch(acc)
     for i in range(0, acc.n_proofs, 97):
         assert blobs[int(o2[i]):int(o2[i]) + int(l2[i])].tobytes() == acc.value(int(ref[1][i]), int(ref[2][i]))
+    # digest_keccak over an arena, cut into index ranges over the two devices (mptv_keccak256_batch), and the
+    # hashed-keys entry on two devices
+    d1 = verifier.keccak256_batch(acc.node_bytes, acc.node_off, acc.node_len)
+    d2 = two.keccak256_batch(acc.node_bytes, acc.node_off, acc.node_len)
+    assert (d1 == d2).all() and len(d2) == acc.n_nodes
+    flags = np.zeros(acc.n_proofs, np.uint8)
+    h1 = verifier.verify_batch_hashed_keys(acc, flags)
+    h2 = two.verify_batch_hashed_keys(acc, flags)
+    assert all((x == y).all() for x, y in zip(h1, h2)) and (h2[0] == 0).all()
     two.close()
 
 

@@ -947,49 +947,95 @@ int mptv_verify_batch_hashed_keys(mptv_ctx* ctx, const mptv_batch* in, const uin
   }
 }
 
+// one device's share [i0, i1) of a host arena: the byte range its nodes span goes up as one copy
+static int keccak256_slice(mptv_ctx* ctx, Device& d, const uint8_t* node_bytes, uint64_t node_bytes_len, const uint64_t* node_off,
+                           const uint32_t* node_len, uint64_t i0, uint64_t i1, uint8_t* digests32) {
+  if (i1 <= i0) return MPTV_OK;
+  const uint64_t n = i1 - i0;
+  uint64_t lo = ~0ull, hi = 0;
+  for (uint64_t i = i0; i < i1; i++) {
+    lo = std::min(lo, node_off[i]);
+    hi = std::max(hi, node_off[i] + node_len[i]);
+  }
+  Slot& s = d.slot[0];
+  CK(cudaSetDevice(d.id));
+  cudaStream_t st = s.stream;
+  const uint64_t span = ((hi - lo) + 15) & ~15ull;
+  const uint64_t avail = std::min(span, node_bytes_len - lo);  // the padding after the last node may lie past the caller's arena
+  CK(s.node_bytes.reserve(span + 16));
+  CK(s.node_off.reserve(8 * n));
+  CK(s.node_len.reserve(4 * n));
+  CK(s.digests.reserve(32 * n));
+  CK(s.order.reserve(4 * n));
+  CK(s.bins.reserve(kBinScratchWords * sizeof(uint32_t)));
+  if (avail < span + 16) CK(cudaMemsetAsync(s.node_bytes.as<uint8_t>() + avail, 0, span + 16 - avail, st));
+  CK(cudaMemcpyAsync(s.node_bytes.p, node_bytes + lo, avail, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.node_off.p, node_off + i0, 8 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.node_len.p, node_len + i0, 4 * n, cudaMemcpyHostToDevice, st));
+  const uint32_t* ord = nullptr;
+  if (ctx->binning) {
+    CK(launch_bin_nodes(s.node_len.as<uint32_t>(), nullptr, n, s.bins.as<uint32_t>(), s.order.as<uint32_t>(), st, nullptr,
+                        nullptr, ctx->long_leaf_bin));
+    ord = s.order.as<uint32_t>();
+  }
+  // node_off values stay the caller's: byte_base = lo translates them
+  CK(launch_keccak256_nodes(s.node_bytes.as<uint8_t>(), lo, s.node_off.as<uint64_t>(), s.node_len.as<uint32_t>(), ord, n,
+                            s.digests.as<uint8_t>(), nullptr, s.bins.as<uint32_t>() + 2 * kNumBins, d.sm_count, st,
+                            ord ? bin_split_word(s.bins.as<uint32_t>()) : nullptr, ctx->long_leaf_ctas));
+  CK(cudaMemcpyAsync(digests32 + 32 * i0, s.digests.p, 32 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MPTV_OK;
+}
+
+// digest_keccak over a whole arena: the nodes are cut into contiguous index ranges with equal shares of the bytes,
+// one per device of the context (host thread + stream each, no inter-device traffic)
 static int keccak256_batch_run(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node_bytes_len, const uint64_t* node_off,
                                const uint32_t* node_len, uint64_t n_nodes, uint8_t* digests32) {
   if (!ctx || (n_nodes && (!node_bytes || !node_off || !node_len || !digests32))) return MPTV_ERR_ARG;
   if (n_nodes == 0) return MPTV_OK;
   if (n_nodes > 0xfffffff0ull) return MPTV_ERR_ARG;
+  uint64_t total = 0;
   for (uint64_t i = 0; i < n_nodes; i++) {
     if (node_off[i] & 15) return MPTV_ERR_ALIGN;
     if (node_len[i] > kMaxNodeLen) return MPTV_ERR_ARG;
     if (node_off[i] > node_bytes_len || node_len[i] > node_bytes_len - node_off[i]) return MPTV_ERR_ARG;  // no wrap, exact end
+    total += node_len[i];
   }
-  Device& d = ctx->dev[0];
-  Slot& s = d.slot[0];
-  CK(cudaSetDevice(d.id));
-  cudaStream_t st = s.stream;
-  const uint64_t padded = (node_bytes_len + 15) & ~15ull;
-  CK(s.node_bytes.reserve(padded + 16));
-  CK(s.node_off.reserve(8 * n_nodes));
-  CK(s.node_len.reserve(4 * n_nodes));
-  CK(s.digests.reserve(32 * n_nodes));
-  CK(s.order.reserve(4 * n_nodes));
-  CK(s.bins.reserve(kBinScratchWords * sizeof(uint32_t)));
-  CK(cudaMemsetAsync(s.node_bytes.p, 0, padded + 16, st));
-  CK(cudaMemcpyAsync(s.node_bytes.p, node_bytes, node_bytes_len, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(s.node_off.p, node_off, 8 * n_nodes, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(s.node_len.p, node_len, 4 * n_nodes, cudaMemcpyHostToDevice, st));
-  const uint32_t* ord = nullptr;
-  if (ctx->binning) {
-    CK(launch_bin_nodes(s.node_len.as<uint32_t>(), nullptr, n_nodes, s.bins.as<uint32_t>(), s.order.as<uint32_t>(), st, nullptr,
-                        nullptr, ctx->long_leaf_bin));
-    ord = s.order.as<uint32_t>();
+  const int nd = (n_nodes < 4096) ? 1 : (int)ctx->dev.size();  // a small call is not worth the threads
+  std::vector<uint64_t> cut(nd + 1, 0);
+  cut[nd] = n_nodes;
+  if (nd > 1) {
+    uint64_t acc = 0;
+    int k = 1;
+    for (uint64_t i = 0; i < n_nodes && k < nd; i++) {
+      acc += node_len[i];
+      while (k < nd && acc >= total / nd * k) cut[k++] = i + 1;
+    }
+    for (; k < nd; k++) cut[k] = n_nodes;
   }
-  CK(launch_keccak256_nodes(s.node_bytes.as<uint8_t>(), 0, s.node_off.as<uint64_t>(), s.node_len.as<uint32_t>(), ord,
-                            n_nodes, s.digests.as<uint8_t>(), nullptr, s.bins.as<uint32_t>() + 2 * kNumBins, d.sm_count, st,
-                            ord ? bin_split_word(s.bins.as<uint32_t>()) : nullptr, ctx->long_leaf_ctas));
-  CK(cudaMemcpyAsync(digests32, s.digests.p, 32 * n_nodes, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  std::vector<int> rcs(nd, MPTV_OK);
+  if (nd == 1) rcs[0] = keccak256_slice(ctx, ctx->dev[0], node_bytes, node_bytes_len, node_off, node_len, 0, n_nodes, digests32);
+  else {
+    std::vector<std::thread> th;
+    for (int k = 0; k < nd; k++)
+      th.emplace_back([&, k] {
+        rcs[k] = keccak256_slice(ctx, ctx->dev[k], node_bytes, node_bytes_len, node_off, node_len, cut[k], cut[k + 1], digests32);
+      });
+    for (auto& t : th) t.join();
+  }
+  for (int k = 0; k < nd; k++) if (rcs[k] != MPTV_OK) return rcs[k];
   return MPTV_OK;
 }
 
 int mptv_keccak256_batch(mptv_ctx* ctx, const uint8_t* node_bytes, uint64_t node_bytes_len, const uint64_t* node_off,
                          const uint32_t* node_len, uint64_t n_nodes, uint8_t* digests32) {
-  const int rc = keccak256_batch_run(ctx, node_bytes, node_bytes_len, node_off, node_len, n_nodes, digests32);
-  if (rc != MPTV_OK && ctx && !ctx->dev.empty()) quiesce(ctx->dev[0]);
+  int rc;
+  try {
+    rc = keccak256_batch_run(ctx, node_bytes, node_bytes_len, node_off, node_len, n_nodes, digests32);
+  } catch (...) {
+    rc = MPTV_ERR_NOMEM;
+  }
+  if (rc != MPTV_OK && ctx) for (Device& d : ctx->dev) quiesce(d);
   return rc;
 }
 
