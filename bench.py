@@ -618,7 +618,7 @@ def e2e_from_borsh(a, ver, b, env, dev, st, voff, vlen, steps):
     import zk_state_proofs_b200 as z
     from workload import gen
     rank, world, local = env
-    blobs, boff = gen.batch_to_borsh(b, pinned=False)
+    blobs, boff = gen.batch_to_borsh(b, pinned=False)  # ordinary memory, as a prover's input file read into a Vec<u8> would be
     th = flatten_threads(a, world)
     for _ in range(2):
         bst, bvoff, bvlen = ver.verify_borsh(blobs, boff, threads=th)
@@ -641,12 +641,16 @@ def e2e_from_borsh(a, ver, b, env, dev, st, voff, vlen, steps):
     all_proofs, blob_bytes, h2d, d2h, read_sum, copy_sum, h2d_sum, launches = reduce_sum(
         [b.n_proofs, len(blobs), hs.h2d_bytes / steps, hs.d2h_bytes / steps, read_gbs, copy_gbs, h2d_gbs, hs.launches / steps], world, dev)
     placed = hs.node_bytes_placed / steps
-    # every byte the host memory system moves per step on this rank: the blobs are read once by the cores, the
-    # staged bytes are written once by the cores and read once by the DMA engine
-    dram = len(blobs) + 2 * hs.h2d_bytes / steps
+    # every byte the host memory system moves per step on this rank: the blobs are read once by the cores; what is
+    # staged is written once by the cores and read once by the DMA engine; in pull mode the placed node bytes are not
+    # staged but read once more, by the device, straight from the blobs
+    pulled = hs.node_bytes_placed / steps if hs.pull_chunks else 0
+    dram = len(blobs) + 2 * (hs.h2d_bytes / steps - pulled) + pulled
     dram_all = reduce_sum([dram], world, dev)[0]
     return dict(
-        value=all_proofs / dt, unit=UNIT, ms_per_step=dt * 1e3, entry="mptv_verify_borsh", host_memory="pageable (blobs); page-locked staging inside the library",
+        value=all_proofs / dt, unit=UNIT, ms_per_step=dt * 1e3, entry="mptv_verify_borsh",
+        host_memory="pageable blobs, page-locked staging inside the library",
+        pull_chunks_per_step=int(hs.pull_chunks / steps), chunks_per_step=int(hs.chunks / steps),
         input_bytes_per_step=int(blob_bytes), h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), host_threads_per_rank=th,
         timer="host wall clock around the blocking C-ABI call, max over ranks",
         transfer_dedup=dict(nodes=int(hs.nodes / steps), nodes_aliased=int(hs.nodes_aliased / steps),

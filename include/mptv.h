@@ -145,6 +145,8 @@ typedef struct mptv_host_stats {
    * free slot / the last chunk, mapping results back to blob offsets, and the whole call */
   uint64_t flatten_us, wait_us, map_us, call_us;
   uint64_t launches;              /* kernels this library queued for those calls                             */
+  uint64_t pull_chunks;           /* mptv_verify_borsh chunks whose node bytes the device fetched itself from
+                                     page-locked blobs (h2d_bytes counts those bytes too)                    */
 } mptv_host_stats;
 int mptv_host_stats_get(mptv_ctx* ctx, mptv_host_stats* out, int reset);
 
@@ -174,6 +176,12 @@ int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops
  *   "lanes_per_proof"  K2b lanes per proof: 0 = choose from nodes/proof, else 8, 16 or 32
  *   "chunk_bytes"      node bytes per pipeline chunk of the host-buffer entry (default 96 MiB)
  *   "borsh_chunk_bytes" borsh bytes per pipeline chunk of mptv_verify_borsh (default 32 MiB)
+ *   "pull_pinned"      mptv_verify_borsh, blobs in page-locked memory (mptv_alloc_pinned, cudaHostAlloc, cudaHostRegister):
+ *                      the staging copy carries only the index arrays and a gather list, and a kernel fetches the node
+ *                      bytes straight from the blobs over PCIe -- the cores do not copy them and the DMA engine does not
+ *                      read them a second time.  Default 0: on the measured hosts the kernel's small PCIe reads reach
+ *                      30 GB/s against the copy engine's 55 and slow the flattening threads down (71 vs 50 ms per
+ *                      million config-2 proofs, profiles/r02_borsh_pull_quick.txt)
  *   "host_dedup"       mptv_verify_borsh aliases byte-identical nodes of a chunk instead of staging and copying them
  *                      again (default 1).  Transfer de-duplication only: every supplied node is still hashed on the
  *                      device, results are identical
@@ -349,7 +357,7 @@ MPTV_ABI_PIN(proofs_out_size, sizeof(mptv_proofs_out) == 64);
 MPTV_ABI_PIN(proofs_out_n_nodes, offsetof(mptv_proofs_out, n_nodes) == 48);
 MPTV_ABI_PIN(timings_size, sizeof(mptv_timings) == 64);
 MPTV_ABI_PIN(rebuild_timings_size, sizeof(mptv_rebuild_timings) == 64);
-MPTV_ABI_PIN(host_stats_size, sizeof(mptv_host_stats) == 96);
+MPTV_ABI_PIN(host_stats_size, sizeof(mptv_host_stats) == 104);
 MPTV_ABI_PIN(flatten_info_size, sizeof(mptv_flatten_info) == 32);
 MPTV_ABI_PIN(log_size, sizeof(mptv_log) == 40);
 #undef MPTV_ABI_PIN

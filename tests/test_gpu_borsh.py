@@ -12,20 +12,53 @@ def _concat(blobs):
     return np.frombuffer(b"".join(blobs) + b"\0", np.uint8), off
 
 
+class _Pinned:
+    """a page-locked copy of a byte array (mptv_alloc_pinned): with such blobs mptv_verify_borsh runs in pull mode --
+    the device gathers the node bytes straight from them"""
+
+    def __init__(self, buf, lead=0):
+        import ctypes
+        import zk_state_proofs_b200 as z
+        self.lib = z.load_library()
+        self.ptr = self.lib.mptv_alloc_pinned(len(buf) + lead + 64)
+        assert self.ptr
+        whole = np.ctypeslib.as_array(ctypes.cast(self.ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(len(buf) + lead + 64,))
+        self.arr = whole[lead:lead + len(buf)]   # `lead` shifts every blob to another alignment
+        self.arr[:] = buf
+
+    def __del__(self):
+        try:
+            self.lib.mptv_free_pinned(self.ptr)
+        except Exception:
+            pass
+
+
+@pytest.mark.parametrize("pinned", [0, 1, 2])
 @pytest.mark.parametrize("host_dedup", [1, 0])
 @pytest.mark.parametrize("chunk_bytes", [1 << 12, 1 << 16, 32 << 20])
-def test_golden_vectors_through_the_borsh_stream(verifier, golden, chunk_bytes, host_dedup):
+def test_golden_vectors_through_the_borsh_stream(verifier, golden, chunk_bytes, host_dedup, pinned):
+    """pinned = 1, 2: the blobs are page-locked (at two alignments), so the entry runs in PULL mode -- staging carries
+    the index arrays and a gather list, k_gather fetches the node and key bytes from the blobs over PCIe"""
     import zk_state_proofs_b200 as z
     vs = golden["vectors"]
     blobs = [z.MerkleProofInput(v["proof_b"], v["root_b"], v["key_b"]).to_borsh() for v in vs]
     buf, off = _concat(blobs)
+    keep = None
+    if pinned:
+        keep = _Pinned(buf, lead=(0, 7)[pinned - 1])
+        buf = keep.arr
     verifier.set_option("borsh_chunk_bytes", chunk_bytes)
     verifier.set_option("host_dedup", host_dedup)
+    verifier.set_option("pull_pinned", 1)   # off by default (measured slower end to end); page-locked blobs are pulled when on
+    verifier.host_stats(reset=True)
     try:
         st, voff, vlen = verifier.verify_borsh(buf, off, threads=4)
     finally:
         verifier.set_option("borsh_chunk_bytes", 32 << 20)
         verifier.set_option("host_dedup", 1)
+        verifier.set_option("pull_pinned", 0)
+    hs = verifier.host_stats()
+    assert (hs.pull_chunks == hs.chunks) if pinned else (hs.pull_chunks == 0)   # page-locked blobs: every chunk is pulled
     assert st.tolist() == [v["expect_status"] for v in vs]
     for v, s, o, l in zip(vs, st, voff, vlen):
         if s == 0:
@@ -48,15 +81,18 @@ def test_fuzz_corpus_stream_equals_flatten_then_verify(verifier, oracle):
     b = z.flatten_borsh(blobs)
     st, voff, vlen = verifier.verify_batch(b)
     aliased = {}
-    for dd in (1, 0):
+    pin = _Pinned(buf, lead=3)
+    for dd, src in ((1, buf), (0, buf), (1, pin.arr), (0, pin.arr)):
         verifier.set_option("borsh_chunk_bytes", 1 << 20)
         verifier.set_option("host_dedup", dd)
+        verifier.set_option("pull_pinned", 1)
         verifier.host_stats(reset=True)
         try:
-            st2, voff2, vlen2 = verifier.verify_borsh(buf, off)
+            st2, voff2, vlen2 = verifier.verify_borsh(src, off)
         finally:
             verifier.set_option("borsh_chunk_bytes", 32 << 20)
             verifier.set_option("host_dedup", 1)
+            verifier.set_option("pull_pinned", 0)
         hs = verifier.host_stats()
         aliased[dd] = (hs.nodes_aliased, hs.h2d_bytes)
         assert hs.nodes == b.n_nodes and hs.d2h_bytes == 13 * len(blobs)

@@ -16,13 +16,16 @@ from workload import gen  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 quick = len(sys.argv) > 2
+pinned_blobs = len(sys.argv) > 3  # page-locked blobs: the entry runs in pull mode
 sys.argv = ["bench.py", "--workload", "config2", "--proofs", str(n)]
 a = bench.parse_args()
 ver = z.Verifier([0])
+if len(sys.argv) > 3:
+    ver.set_option("pull_pinned", 1)
 b, _ = bench.build_batch(a, 0, pinned=True)
-blobs, boff = gen.batch_to_borsh(b)
+blobs, boff = gen.batch_to_borsh(b, pinned=pinned_blobs)
 cores = os.cpu_count()
-print(f"{n} proofs, {len(blobs) / 1e9:.2f} GB of borsh, {cores} host cores", flush=True)
+print(f"{n} proofs, {len(blobs) / 1e9:.2f} GB of borsh ({'page-locked: pull mode' if pinned_blobs else 'pageable'}), {cores} host cores", flush=True)
 ref = ver.verify_batch(b)
 for _ in range(2):
     t0 = time.perf_counter(); ver.verify_batch(b); dt = time.perf_counter() - t0
@@ -46,7 +49,7 @@ for dd in (1, 0):
                      for _ in range(3))
             print(f"host_dedup {dd} chunk {mb:4d} MB threads {th or cores - 1:2d}: {best * 1e3:7.1f} ms = {n / best / 1e6:6.2f} M proofs/s | "
                   f"H2D {hs.h2d_bytes / 1e9:5.2f} GB ({hs.h2d_bytes / best / 1e9:5.1f} GB/s), aliased {hs.nodes_aliased}/{hs.nodes} nodes, "
-                  f"{hs.chunks} chunks | host stage alone {pt * 1e3:6.1f} ms ({len(blobs) / pt / 1e9:5.1f} GB/s read)", flush=True)
+                  f"{hs.chunks} chunks ({hs.pull_chunks} pulled), flatten {hs.flatten_us / 1e3:.1f} ms | host stage alone {pt * 1e3:6.1f} ms ({len(blobs) / pt / 1e9:5.1f} GB/s read)", flush=True)
 ver.set_option("borsh_chunk_bytes", 32 << 20)
 ver.set_option("host_dedup", 1)
 ok = np.nonzero(st == 0)[0][:5000]

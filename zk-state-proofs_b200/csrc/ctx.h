@@ -137,7 +137,7 @@ struct Device {
   uint8_t* mb_dev = nullptr;
   uint32_t mb_seq = 0;
   DedupTable dedup_tab;  // host-side candidate table of the streamed borsh entry (one chunk at a time)
-  mptv_host_stats hstat = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // of the host-fed entries since the last reset
+  mptv_host_stats hstat = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // of the host-fed entries since the last reset
 };
 
 }  // namespace mptv
@@ -152,6 +152,7 @@ struct mptv_ctx {
   int binning = 1;
   int fused_classify = 1;  // K1 also classifies plain branches / leaves (K2a fast path)
   int dedup_nodes = 0;     // hash each DISTINCT node once (secondary mode, reported separately)
+  int pull_pinned = 0;     // streamed borsh entry, page-locked blobs: the device gathers the placed node bytes itself (measured slower: off)
   int host_dedup = 1;      // streamed borsh entry: alias byte-identical nodes of a chunk instead of copying them again
   int latency_path = 1;    // batches that fit one CTA: one launch, mapped page-locked memory both ways (single_kernels.cu)
   int fast_walk = 1;       // K2f decides chain-shaped proofs one thread each; K2b gets the deferred rest

@@ -202,10 +202,10 @@ static int flatten_borsh_ex_run(const uint8_t* blobs, const uint64_t* blob_off, 
     if (!reuse) mptv_host_batch_free(hb);
     return rc;
   };
-  mptv::BorshChunkJob job = {blobs, blob_off, 0, n, alias ? &table : nullptr};
+  mptv::BorshChunkJob job = {blobs, blob_off, 0, n, alias ? &table : nullptr, false};
   mptv::ChunkLayout L;
   std::vector<uint8_t> bad;
-  const int rc = mptv::flatten_borsh_chunk(pool, job, [&](size_t total) { return (uint8_t*)host_alloc(hb, 0, total); }, L,
+  const int rc = mptv::flatten_borsh_chunk(pool, job, [&](size_t total, size_t) { return (uint8_t*)host_alloc(hb, 0, total); }, L,
                                            nullptr, &bad);
   if (rc != MPTV_OK) return fail(rc);
   uint8_t* block = (uint8_t*)hb->blocks[0];
@@ -272,10 +272,10 @@ int mptv_borsh_flatten_probe(const uint8_t* blobs, const uint64_t* blob_off, uin
       if (ce > cs + 1) ce--;
       if (ce > n) ce = n;
       table.new_epoch();
-      mptv::BorshChunkJob job = {blobs, blob_off, cs, ce, alias_duplicates ? &table : nullptr};
+      mptv::BorshChunkJob job = {blobs, blob_off, cs, ce, alias_duplicates ? &table : nullptr, false};
       mptv::ChunkLayout L;
       Blk& blk = block[ci % 3];
-      const int rc = mptv::flatten_borsh_chunk(pool, job, [&](size_t total) {
+      const int rc = mptv::flatten_borsh_chunk(pool, job, [&](size_t total, size_t) {
         if (blk.cap < total) {
           free(blk.p);
           blk.cap = total + total / 8;

@@ -107,6 +107,10 @@ struct ChunkLayout {
   size_t o_off = 0, o_len = 0, o_pf = 0, o_roots = 0, o_koff = 0, o_klen = 0;  // index arrays
   size_t index_end = 0;  // [0, index_end) is one contiguous copy
   size_t total = 0;      // extent of the block (worst case: nothing aliased)
+  // pull mode (the input is page-locked: the device fetches the placed bytes itself): one gather record per placed
+  // node / key in [o_gather, o_gather + 16 n_gather); the host block ends at host_total, the byte regions exist on
+  // the device only
+  size_t o_gather = 0, n_gather = 0, host_total = 0;
   std::vector<size_t> region_begin, region_used;  // per worker: its byte region and how much of it was written
   // statistics of the build
   uint64_t node_bytes_supplied = 0;  // sum of the padded lengths of all supplied nodes
@@ -119,8 +123,8 @@ struct FlattenStats {
 };
 
 // Flatten blobs [cs, ce) (borsh(MerkleProofInput), /root/reference/crypto-ops/src/types.rs:4-9) into a staging block.
-//   get_block(total) -> base pointer of a block of at least `total` bytes (called once, by worker 0, between the
-//   phases; nullptr = allocation failed).
+//   get_block(host_bytes, device_bytes) -> base pointer of a host block of at least host_bytes (called once, by
+//   worker 0, between the phases; the device copy needs device_bytes; nullptr = allocation failed).
 // Arrays inside the block: node_off u64[nn] (offsets from the block base), node_len u32[nn], proof_first u32[np+1],
 // roots u8[32 np], key_off u32[np] + key_len u32[np] (keys live in the byte regions), then the workers' byte regions.
 // node_src[k] (host only, may be null) = position of node k's bytes in `blobs`; bad_root[i] = root_hash.len() != 32.
@@ -130,7 +134,12 @@ struct BorshChunkJob {
   const uint64_t* blob_off;
   uint64_t cs, ce;
   DedupTable* table;  // null = no de-duplication
+  bool pull = false;  // write gather records instead of copying bytes (the caller's blobs are device-accessible)
 };
+// what the device's gather kernel executes: len bytes at blobs + src -> block + 16 * dst16, padded with zeros to 16
+struct GatherRec { uint64_t src; uint32_t dst16; uint32_t len; };
+static_assert(sizeof(GatherRec) == 16, "one uint4 on the device");
+constexpr uint32_t kGatherUnused = 0xffffffffu;
 template <class GetBlock>
 int flatten_borsh_chunk(WorkerPool& pool, const BorshChunkJob& job, GetBlock get_block, ChunkLayout& L,
                         std::vector<uint64_t>* node_src, std::vector<uint8_t>* bad_root);
@@ -209,7 +218,14 @@ struct RegionWriter {
       if (bn == kBounce) flush_lines(false);
     }
   }
+  GatherRec* rec = nullptr;   // pull mode: my gather list (next free record), else null
+  const uint8_t* src_base = nullptr;
   inline void put_bytes(uint8_t* dst, const uint8_t* src, uint32_t len) {
+    if (rec) {  // the device fetches the bytes from the caller's page-locked blobs: nothing is read or written here
+      rec->src = (uint64_t)(src - src_base); rec->dst16 = (uint32_t)((size_t)(dst - base) >> 4); rec->len = len;
+      rec++;
+      return;
+    }
     if (!table) { copy_node_stream(dst, src, len); return; }
     if (!bounce_on) { bounce_on = true; flushed = (size_t)(dst - base); }  // first use: dst is my region's (64-byte aligned) start
     append(src, len);
@@ -262,11 +278,18 @@ int flatten_borsh_chunk(WorkerPool& pool, const BorshChunkJob& job, GetBlock get
         L.o_off = take(8 * nn); L.o_len = take(4 * nn); L.o_pf = take(4 * (np + 1)); L.o_roots = take(32 * np);
         L.o_koff = take(4 * np); L.o_klen = take(4 * np);
         L.index_end = o;
+        if (job.pull) {  // one record per node and per key at most, each worker's list behind the one before
+          L.o_gather = o;
+          L.n_gather = nn + np;
+          o += up64z(16 * (nn + np));
+          L.host_total = o;
+        }
         for (int k = 0; k < T; k++) { L.region_begin[k] = o; o += up64z(tot[k].bound) + 64; }
         L.total = o + 64;
+        if (!job.pull) L.host_total = L.total;
         if (L.total > 0xfffffff00ull) err.store(MPTV_ERR_ARG);  // offsets are kept in 16-byte units in 32 bits
         else {
-          block = get_block(L.total);
+          block = get_block(L.host_total, L.total);
           if (!block) err.store(MPTV_ERR_NOMEM);
           else {
             if (node_src && node_src->size() < nn) node_src->resize(nn + nn / 8);
@@ -288,6 +311,14 @@ int flatten_borsh_chunk(WorkerPool& pool, const BorshChunkJob& job, GetBlock get
     uint8_t* roots = block + L.o_roots;
     RegionWriter w;  // on my stack: the cursor and counters change with every node (no false sharing)
     w.base = block; w.at = L.region_begin[t]; w.end = w.at + up64z(tot[t].bound); w.table = job.table;
+    GatherRec* rec_end = nullptr;
+    if (job.pull) {
+      uint64_t r0 = 0;
+      for (int q = 0; q < t; q++) r0 += tot[q].nodes + (std::min(np, per * (q + 1)) - std::min(np, per * q));
+      w.rec = reinterpret_cast<GatherRec*>(block + L.o_gather) + r0;
+      rec_end = w.rec + tot[t].nodes + (hi - lo);
+      w.src_base = job.blobs;
+    }
     // fingerprint of the node whose length word is at q, computed one node ahead so that its table entry is in the
     // cache by the time the node is placed (0 when the node is not a candidate or does not fit the blob)
     // (two stages: the entry is prefetched two nodes ahead, the first copy's bytes one node ahead)
@@ -349,8 +380,12 @@ int flatten_borsh_chunk(WorkerPool& pool, const BorshChunkJob& job, GetBlock get
       if (!ok) { err.store(MPTV_ERR_ARG); return; }
     }
     // a node count that lied (more nodes announced than present) was caught above; fewer is impossible (k is exact)
-    if (w.table) { static const uint8_t z16[16] = {0}; w.put_bytes(block + w.at, z16, 16); }  // K1 stages whole 16-byte chunks:
-    else memset(block + w.at, 0, 16);                                                        // the bytes after my last node must be readable
+    if (job.pull) {
+      for (; w.rec < rec_end; w.rec++) { w.rec->src = 0; w.rec->dst16 = 0; w.rec->len = kGatherUnused; }  // aliased nodes left these free
+    } else {
+      if (w.table) { static const uint8_t z16[16] = {0}; w.put_bytes(block + w.at, z16, 16); }  // K1 stages whole 16-byte chunks:
+      else memset(block + w.at, 0, 16);                                                        // the bytes after my last node must be readable
+    }
     w.at += 16;
     w.finish();
     _mm_sfence();  // non-temporal stores: the DMA engine (or another thread) reads them next

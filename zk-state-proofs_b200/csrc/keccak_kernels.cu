@@ -483,6 +483,76 @@ k_keccak256_leaves(const TrieBatchDev in, const uint4* __restrict__ rec, const u
   }
 }
 
+// ------------------------------------------------------------------ gather (pull mode of the streamed borsh entry)
+// One warp per record: the lanes read the 16-byte aligned chunks that cover the source bytes (mapped page-locked host
+// memory: one PCIe read per chunk, each chunk read once -- the neighbour's half comes by shuffle), shift them to the
+// destination's alignment and store whole 16-byte chunks, the tail padded with zeros.
+__device__ __forceinline__ uint4 shift_bytes(const uint4& a, const uint4& b, uint32_t sh /* 0..15, warp-uniform */) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  const uint32_t bits = 8u * (sh & 3u);
+  uint4 o;
+  switch (sh >> 2) {
+    case 0: o.x = __funnelshift_r(w[0], w[1], bits); o.y = __funnelshift_r(w[1], w[2], bits); o.z = __funnelshift_r(w[2], w[3], bits); o.w = __funnelshift_r(w[3], w[4], bits); break;
+    case 1: o.x = __funnelshift_r(w[1], w[2], bits); o.y = __funnelshift_r(w[2], w[3], bits); o.z = __funnelshift_r(w[3], w[4], bits); o.w = __funnelshift_r(w[4], w[5], bits); break;
+    case 2: o.x = __funnelshift_r(w[2], w[3], bits); o.y = __funnelshift_r(w[3], w[4], bits); o.z = __funnelshift_r(w[4], w[5], bits); o.w = __funnelshift_r(w[5], w[6], bits); break;
+    default: o.x = __funnelshift_r(w[3], w[4], bits); o.y = __funnelshift_r(w[4], w[5], bits); o.z = __funnelshift_r(w[5], w[6], bits); o.w = __funnelshift_r(w[6], w[7], bits); break;
+  }
+  return o;
+}
+
+__global__ void __launch_bounds__(256) k_gather(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ dst_base,
+                                                const uint4* __restrict__ recs, uint32_t n_recs) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r = warp; r < n_recs; r += n_warps) {
+    const uint4 rec = __ldg(recs + r);
+    const uint32_t len = rec.w;
+    if (len == 0xffffffffu) continue;
+    const uint8_t* src = src_base + (((uint64_t)rec.y << 32) | rec.x);
+    uint4* dst = reinterpret_cast<uint4*>(dst_base + 16ull * rec.z);
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+    const uint4* a = reinterpret_cast<const uint4*>(src - sh);
+    const uint32_t n_dst = (len + 15u) >> 4, n_src = (sh + len + 15u) >> 4;  // aligned chunks written / read
+    for (uint32_t base = 0; base < n_dst; base += 32) {
+      const uint32_t c = base + lane;
+      uint4 lo = make_uint4(0, 0, 0, 0), extra = make_uint4(0, 0, 0, 0);
+      if (c < n_src) lo = a[c];
+      if (lane == 0 && base + 32 < n_src) extra = a[base + 32];  // the chunk after this round's last: lane 31's other half
+      uint4 hi;
+      hi.x = __shfl_down_sync(0xffffffffu, lo.x, 1); hi.y = __shfl_down_sync(0xffffffffu, lo.y, 1);
+      hi.z = __shfl_down_sync(0xffffffffu, lo.z, 1); hi.w = __shfl_down_sync(0xffffffffu, lo.w, 1);
+      const uint4 e = make_uint4(__shfl_sync(0xffffffffu, extra.x, 0), __shfl_sync(0xffffffffu, extra.y, 0),
+                                 __shfl_sync(0xffffffffu, extra.z, 0), __shfl_sync(0xffffffffu, extra.w, 0));
+      if (lane == 31) hi = e;
+      if (c < n_dst) {
+        uint4 o = shift_bytes(lo, hi, sh);
+        const uint32_t left = len - 16u * c;  // message bytes from this chunk on
+        if (left < 16u) {  // zero the padding
+          uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int keep = (int)left - 4 * k;
+            w[k] &= keep >= 4 ? 0xffffffffu : (keep <= 0 ? 0u : ((1u << (8 * keep)) - 1u));
+          }
+          o = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        dst[c] = o;
+      }
+    }
+  }
+}
+
+cudaError_t launch_gather(const uint8_t* src_base, uint8_t* dst_base, const uint4* recs, uint32_t n_recs, int sm_count,
+                          cudaStream_t st) {
+  if (n_recs == 0) return cudaSuccess;
+  const uint32_t warps_needed = n_recs;
+  uint32_t blocks = (warps_needed + 7) / 8;
+  const uint32_t cap = (uint32_t)sm_count * 8;  // a resident wave: the records are few per chunk and PCIe sets the pace
+  if (blocks > cap) blocks = cap;
+  k_gather<<<blocks, 256, 0, st>>>(src_base, dst_base, recs, n_recs);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ key preparation (storage guest)
 // The storage guest looks every storage slot up under digest_keccak(key)
 // (/root/reference/circuits/risc0-storage-proof/storage-proof-circuit/storage-circuit/src/main.rs:26,

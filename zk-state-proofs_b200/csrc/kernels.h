@@ -85,6 +85,12 @@ cudaError_t launch_prepare_keys(const uint8_t* key_bytes, const uint32_t* key_of
                                 uint64_t n_proofs, uint8_t* hashed, uint32_t hashed_off, uint32_t* off_out, uint32_t* len_out,
                                 cudaStream_t st);
 
+// pull mode of the streamed borsh entry: records (src offset u64, dst / 16 u32, len u32; len 0xffffffff = unused) ->
+// dst_base + 16 dst16 receives len bytes of src_base + src, zero-padded to a multiple of 16.  src_base is mapped
+// page-locked HOST memory (the caller's blobs): the loads cross PCIe.
+cudaError_t launch_gather(const uint8_t* src_base, uint8_t* dst_base, const uint4* recs, uint32_t n_recs, int sm_count,
+                          cudaStream_t st);
+
 // K2a: meta[i] = eager-decode record of node i.  only_slow: leave records != kMetaSlow untouched
 cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
                                const uint32_t* node_len, uint64_t n_nodes, uint32_t* meta, bool only_slow,

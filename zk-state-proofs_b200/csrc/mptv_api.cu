@@ -220,6 +220,8 @@ int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
   } else if (!strcmp(name, "borsh_chunk_bytes")) {
     if (value < (1 << 12) || value > (1ll << 31)) return MPTV_ERR_ARG;
     ctx->borsh_chunk_bytes = (uint64_t)value;
+  } else if (!strcmp(name, "pull_pinned")) {
+    ctx->pull_pinned = value ? 1 : 0;
   } else if (!strcmp(name, "host_dedup")) {
     ctx->host_dedup = value ? 1 : 0;
   } else if (!strcmp(name, "latency_path")) {
@@ -320,7 +322,7 @@ int mptv_host_stats_get(mptv_ctx* ctx, mptv_host_stats* out, int reset) {
     out->chunks += d.hstat.chunks; out->nodes += d.hstat.nodes; out->nodes_aliased += d.hstat.nodes_aliased;
     out->node_bytes_supplied += d.hstat.node_bytes_supplied; out->node_bytes_placed += d.hstat.node_bytes_placed;
     out->h2d_bytes += d.hstat.h2d_bytes; out->d2h_bytes += d.hstat.d2h_bytes;
-    out->launches += d.hstat.launches;
+    out->launches += d.hstat.launches; out->pull_chunks += d.hstat.pull_chunks;
     out->flatten_us += d.hstat.flatten_us; out->wait_us += d.hstat.wait_us; out->map_us += d.hstat.map_us;
     out->call_us += d.hstat.call_us;
     if (reset) memset(&d.hstat, 0, sizeof d.hstat);
@@ -611,6 +613,7 @@ int run_slice(mptv_ctx* ctx, Device& d, const mptv_batch* in, const uint8_t* has
 struct BorshStream {
   const uint8_t* blobs;
   const uint64_t* blob_off;
+  bool pinned;  // the blobs are page-locked and mapped: the devices can fetch node bytes from them directly (pull mode)
 };
 
 // results of a finished chunk (already in the slot's page-locked result block) -> the caller's arrays
@@ -662,12 +665,13 @@ struct BorshPipe {
   std::condition_variable cv;
   int state[kSlots];
   ChunkLayout layout[kSlots];
+  const uint8_t* blobs_dev = nullptr;  // pull mode: the caller's blobs as the device sees them
   uint64_t produced = 0;  // chunks handed to the submitter
   bool producer_done = false;
   int err = MPTV_OK;
 };
 
-int submit_borsh_chunk(mptv_ctx* ctx, Device& d, Slot& s, const ChunkLayout& L) {
+int submit_borsh_chunk(mptv_ctx* ctx, Device& d, Slot& s, const ChunkLayout& L, const uint8_t* blobs_dev) {
   cudaStream_t st = s.stream;
   const uint64_t np = L.np;
   uint8_t* h = static_cast<uint8_t*>(s.h_in.p);
@@ -676,6 +680,13 @@ int submit_borsh_chunk(mptv_ctx* ctx, Device& d, Slot& s, const ChunkLayout& L) 
   // unused gap between them is small)
   size_t c0 = 0, c1 = L.index_end;
   uint64_t moved = 0;
+  if (L.n_gather) {
+    // pull mode: index arrays + gather list in one copy, then the device fetches the placed bytes itself
+    CK(cudaMemcpyAsync(dv, h, L.host_total, cudaMemcpyHostToDevice, st));
+    CK(launch_gather(blobs_dev, dv, reinterpret_cast<const uint4*>(dv + L.o_gather), (uint32_t)L.n_gather, d.sm_count, st));
+    moved = L.host_total + L.node_bytes_placed;  // what crosses PCIe: the block, and the bytes the kernel reads
+    d.hstat.launches += 1; d.hstat.pull_chunks += 1;
+  } else
   for (size_t t = 0; t <= L.region_begin.size(); t++) {
     const bool last = t == L.region_begin.size();
     if (!last && L.region_used[t] == 0) continue;
@@ -726,7 +737,7 @@ void borsh_submitter(mptv_ctx* ctx, Device& d, BorshPipe& P) {
       if (P.err != MPTV_OK) return;
       if (c >= P.produced) break;  // the producer is done and chunk c does not exist
     }
-    rc = submit_borsh_chunk(ctx, d, d.slot[k], P.layout[k]);
+    rc = submit_borsh_chunk(ctx, d, d.slot[k], P.layout[k], P.blobs_dev);
     if (rc != MPTV_OK) { fail(rc); return; }
     {
       std::lock_guard<std::mutex> g(P.mu);
@@ -756,7 +767,18 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
   const bool alias = ctx->host_dedup != 0;
   if (alias && !d.dedup_tab.reserve((size_t)std::min<uint64_t>(ctx->borsh_chunk_bytes / 128 + 1024, 1ull << 22)))
     return fail_msg(ctx, MPTV_ERR_NOMEM, "mptv_verify_borsh: host table allocation failed");
+  // pull mode: the caller's blobs are page-locked, so each chunk's staging carries only the index arrays and a gather
+  // list, and a kernel fetches the placed node bytes straight from the blobs over PCIe -- the cores neither copy them
+  // nor does the DMA engine read them a second time from a staging block
+  const uint8_t* blobs_dev = nullptr;
+  bool pull = false;
+  if (in.pinned && ctx->pull_pinned) {
+    void* dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, const_cast<uint8_t*>(in.blobs), 0) == cudaSuccess && dp) { blobs_dev = static_cast<const uint8_t*>(dp); pull = true; }
+    else cudaGetLastError();
+  }
   BorshPipe P;
+  P.blobs_dev = blobs_dev;
   for (int k = 0; k < kSlots; k++) P.state[k] = BorshPipe::kFree;
   double t_wait = 0, t_map = 0, t_flat = 0, t_join = 0;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -789,9 +811,9 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
     // one pass over the chunk's blobs, straight into the slot's page-locked block; a node identical to one already
     // placed in this chunk is aliased, not copied (host_flatten.h)
     if (alias) d.dedup_tab.new_epoch();
-    const BorshChunkJob job = {in.blobs, in.blob_off, cs, ce, alias ? &d.dedup_tab : nullptr};
-    rc = flatten_borsh_chunk(pool, job, [&](size_t total) -> uint8_t* {
-      if (s.h_in.reserve(total) != cudaSuccess || s.in_pack.reserve(total) != cudaSuccess) {
+    const BorshChunkJob job = {in.blobs, in.blob_off, cs, ce, alias ? &d.dedup_tab : nullptr, pull};
+    rc = flatten_borsh_chunk(pool, job, [&](size_t host_bytes, size_t dev_bytes) -> uint8_t* {
+      if (s.h_in.reserve(host_bytes) != cudaSuccess || s.in_pack.reserve(dev_bytes) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
       }
@@ -851,7 +873,16 @@ int verify_borsh_run(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_o
     const unsigned nd = (unsigned)ctx->dev.size();
     n_threads = (int)std::max(1u, std::min(32u * nd, hw > 2 * nd ? hw - nd : hw));
   }
-  const BorshStream in = {blobs, blob_off};
+  // page-locked input?  (mptv_alloc_pinned / cudaHostAlloc / cudaHostRegister: first and last byte must both be)
+  bool pinned = false;
+  {
+    cudaPointerAttributes a0, a1;
+    const uint64_t last = blob_off[n] > blob_off[0] ? blob_off[n] - 1 : blob_off[0];
+    if (cudaPointerGetAttributes(&a0, blobs + blob_off[0]) == cudaSuccess && cudaPointerGetAttributes(&a1, blobs + last) == cudaSuccess)
+      pinned = a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
+  const BorshStream in = {blobs, blob_off, pinned};
   const int nd = (int)ctx->dev.size();
   std::vector<uint64_t> cut(nd + 1, 0);
   cut[nd] = n;
