@@ -1,5 +1,7 @@
 """Large differential fuzz of the CUDA path against the C restatement (which is itself fuzzed against the reference
-ELF by oracle/fuzz_vs_ref.py): every fuzz family of oracle/fuzzgen.py, all walk configurations.
+ELF by oracle/fuzz_vs_ref.py): every fuzz family of oracle/fuzzgen.py incl. the deep inline nests, all walk
+configurations, the streamed borsh entry with transfer de-duplication, and the one-launch latency path on random
+small groups.
     python tools/fuzz_gpu_vs_oracle.py [n_seeds] [first_seed]"""
 import os
 import sys
@@ -10,7 +12,9 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import zk_state_proofs_b200 as z
-from oracle.fuzzgen import corpus
+import random
+
+from oracle.fuzzgen import corpus, deep_nested_cases
 from oracle.pyoracle import Oracle
 
 n_seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 10
@@ -22,7 +26,9 @@ total, bad, hist = 0, 0, Counter()
 t0 = time.time()
 for seed in range(first, first + n_seeds):
     cases = corpus(seed, o.keccak256, 300, 15000, 20000, 15000, 30000, 4000)
-    b = z.flatten_borsh([z.MerkleProofInput(c["proof"], c["root"], c["key"]).to_borsh() for c in cases], threads=0)
+    cases += deep_nested_cases(random.Random(seed), o.keccak256, 45)
+    blobs = [z.MerkleProofInput(c["proof"], c["root"], c["key"]).to_borsh() for c in cases]
+    b = z.flatten_borsh(blobs, threads=0)
     d = dict(node_bytes=b.node_bytes, node_off=b.node_off, node_len=b.node_len, proof_first=b.proof_first,
              roots=b.roots, key_bytes=b.key_bytes, key_off=b.key_off)
     ost, ovoff, ovlen, _, _ = o.verify_batch(d, nthreads=os.cpu_count() or 1)
@@ -38,7 +44,37 @@ for seed in range(first, first + n_seeds):
         bad += len(diff)
         for i in diff[:5]:
             print("MISMATCH", seed, m, cases[i]["tag"], int(st[i]), int(ost[i]))
+    for k, v in modes[0].items():
+        ver.set_option(k, v)
+    # the streamed borsh entry, byte-identical nodes of a chunk aliased (values come back as slices of the blobs)
+    boff = np.zeros(len(blobs) + 1, np.uint64)
+    np.cumsum([len(x) for x in blobs], out=boff[1:])
+    buf = np.frombuffer(b"".join(blobs) + b"\0", np.uint8)
+    ver.set_option("borsh_chunk_bytes", 1 << 20)
+    st, voff, vlen = ver.verify_borsh(buf, boff)
+    ver.set_option("borsh_chunk_bytes", 32 << 20)
+    diff = np.nonzero((st != ost) | (vlen != ovlen))[0]
+    for i in np.nonzero(st == 0)[0][::7]:
+        if buf[int(voff[i]):int(voff[i]) + int(vlen[i])].tobytes() != b.value(int(ovoff[i]), int(ovlen[i])):
+            diff = np.append(diff, i)
+    bad += len(diff)
+    for i in diff[:5]:
+        print("MISMATCH borsh stream", seed, cases[i]["tag"], int(st[i]), int(ost[i]))
+    # the one-launch latency path: random groups of 1 ... 32 proofs per call
+    rng = random.Random(seed)
+    for _ in range(1500):
+        k = rng.choice([1, 1, 1, 2, 4, 9, 32])
+        idx = [rng.randrange(len(cases)) for _ in range(k)]
+        sb = z.flatten([z.MerkleProofInput(cases[i]["proof"], cases[i]["root"], cases[i]["key"]) for i in idx])
+        st, voff, vlen = ver.verify_batch(sb)
+        for j, i in enumerate(idx):
+            want_v = b.value(int(ovoff[i]), int(ovlen[i])) if ost[i] == 0 else b""
+            got_v = sb.value(int(voff[j]), int(vlen[j])) if st[j] == 0 else b""
+            if int(st[j]) != int(ost[i]) or got_v != want_v:
+                bad += 1
+                print("MISMATCH latency path", seed, cases[i]["tag"], int(st[j]), int(ost[i]))
     total += len(cases)
     hist.update(ost.tolist())
     print(f"seed {seed}: {len(cases)} cases x {len(modes)} modes, cumulative mismatches {bad}, {time.time() - t0:.0f} s", flush=True)
-print(f"TOTAL {total} cases x {len(modes)} walk configurations: {bad} mismatches; verdict histogram {dict(sorted(hist.items()))}")
+print(f"TOTAL {total} cases x ({len(modes)} walk configurations + borsh stream with aliasing) + 1500 latency-path groups per seed: {bad} mismatches; "
+      f"verdict histogram {dict(sorted(hist.items()))}")
