@@ -254,7 +254,9 @@ int mptv_last_rebuild_timings(mptv_ctx* ctx, int dev_index, mptv_rebuild_timings
  * the encoded nodes on the key's path, root first (the root always, other nodes only when referenced
  * by hash; for an absent key the path that proves its absence).  The output is laid out as an
  * mptv_batch arena (every node on a 16-byte boundary), so {proof q, roots32[trie[q]], key q} can be
- * handed straight to mptv_verify_batch.  Host buffers, device 0 of the context. */
+ * handed straight to mptv_verify_batch.  Host buffers.  When the targets are grouped by trie in ascending order (the
+ * usual shape) the tries and their targets are cut into contiguous slices over the devices of the context, like
+ * mptv_trie_roots; otherwise device 0 does the call. */
 typedef struct mptv_proof_targets {
   const uint32_t* trie;      /* [n_targets] trie the key is looked up in */
   const uint8_t* key_bytes;  /* target q key = key_bytes[key_off[q] .. key_off[q+1]) */

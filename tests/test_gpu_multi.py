@@ -36,6 +36,19 @@ def test_one_context_two_devices_matches_one_device(verifier):
     for x, y in zip(one, got):
         assert (x == y).all()
     assert (two.trie_roots(kv) == verifier.trie_roots(kv)).all()
+    # rebuild + get_proof: trie-ordered targets are cut over the two devices with their tries, unordered ones go to device 0
+    import zk_state_proofs_b200 as z2
+    keys = [z2.rlp_index(i) for i in (0, 1, 15, 127, 128, 299, 300)]
+    ordered = [(t, k) for t in range(kv.n_tries) for k in keys]
+    shuffled = ordered[::-1]
+    for targets in (ordered, shuffled):
+        r1, b1 = verifier.trie_proofs(kv, targets)
+        r2, b2 = two.trie_proofs(kv, targets)
+        assert (r1 == r2).all() and (b1.proof_first == b2.proof_first).all() and (b1.node_len == b2.node_len).all()
+        assert (b1.node_off == b2.node_off).all() and (b1.node_bytes == b2.node_bytes).all()
+        s1 = verifier.verify_batch(b1)
+        s2 = two.verify_batch(b2)
+        assert all((x == y).all() for x, y in zip(s1, s2)) and set(s1[0].tolist()) == {0, 4}
     # the streamed borsh entry over two devices (blobs cut by bytes, one host thread pool per device)
     from workload import gen
     acc = gen.account_batch(gen.SynthTrie(300_000, 2, kind=0), 30_000, seed=5)

@@ -165,8 +165,8 @@ struct mptv_ctx {
 namespace mptv {
 
 inline int fail_cuda(mptv_ctx* c, cudaError_t e, const char* where) {
-  char buf[256];
-  snprintf(buf, sizeof buf, "%s: %s", where, cudaGetErrorString(e));
+  char buf[640];
+  snprintf(buf, sizeof buf, "%.500s: %s", where, cudaGetErrorString(e));
   if (c) { std::lock_guard<std::mutex> g(c->err_mu); c->err = buf; }
   if (e == cudaErrorMemoryAllocation) {
     cudaGetLastError();  // not sticky: the context stays usable for a smaller batch

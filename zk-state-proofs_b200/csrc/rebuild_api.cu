@@ -284,6 +284,90 @@ int mptv_trie_roots(mptv_ctx* ctx, const mptv_kv_batch* in, uint8_t* roots32) {
   return MPTV_OK;
 }
 
+// One device's share of mptv_trie_proofs: tries [t0, t1) and the targets [q0, q1) that look into them.
+struct ProofSlice {
+  uint64_t t0 = 0, t1 = 0, q0 = 0, q1 = 0;
+  uint32_t n_nodes = 0;   // phase 1 out: nodes / padded bytes of the slice's proofs
+  uint64_t n_bytes = 0;
+  TrieBatchDev b;
+  int rc = MPTV_OK;
+};
+
+// phase 1: rebuild the slice's tries, hand back their roots, count the proof nodes of its targets
+static int trie_proofs_count(mptv_ctx* ctx, Device& d, const mptv_kv_batch* in, const mptv_proof_targets* tg, uint8_t* roots32,
+                             ProofSlice& sl) {
+  Rebuild& rb = d.rb;
+  CK(cudaSetDevice(d.id));
+  cudaStream_t st = d.stream;
+  const uint64_t nt = sl.t1 - sl.t0, nq = sl.q1 - sl.q0;
+  if (nt == 0) return MPTV_OK;
+  int rc = upload_kv(ctx, d, in, sl.t0, sl.t1, rb.stage[0], sl.b, st);
+  if (rc != MPTV_OK) return rc;
+  CK(rb.out_roots.reserve(32 * nt));
+  rc = rebuild_on_device(ctx, d, sl.b, rb.out_roots.as<uint8_t>(), st);
+  if (rc != MPTV_OK) return rc;
+  CK(cudaMemcpyAsync(roots32 + 32 * sl.t0, rb.out_roots.p, 32 * nt, cudaMemcpyDeviceToHost, st));
+  if (nq == 0) { CK(cudaStreamSynchronize(st)); return MPTV_OK; }
+  TrieWork w;
+  w.rec = rb.rec.as<uint4>(); w.off = rb.off.as<uint64_t>(); w.len = rb.len.as<uint32_t>();
+  w.digests = rb.digests.as<uint8_t>(); w.tcount = rb.tcount.as<uint32_t>(); w.lvl_list = rb.lvl_list.as<uint32_t>();
+  w.sum = rb.sum.as<TrieSummary>();
+  const uint32_t k0 = tg->key_off[sl.q0], kb = tg->key_off[sl.q1] - k0;
+  // trie indices and key offsets relative to the slice
+  std::vector<uint32_t> ltrie(nq), lkoff(nq + 1);
+  for (uint64_t q = 0; q < nq; q++) ltrie[q] = tg->trie[sl.q0 + q] - (uint32_t)sl.t0;
+  for (uint64_t q = 0; q <= nq; q++) lkoff[q] = tg->key_off[sl.q0 + q] - k0;
+  CK(rb.q_trie.reserve(4 * nq));
+  CK(rb.q_key_bytes.reserve((size_t)kb + 16));
+  CK(rb.q_key_off.reserve(4 * (nq + 1)));
+  CK(rb.q_cnt.reserve(4 * nq));
+  CK(rb.q_bytes.reserve(8 * nq));
+  CK(rb.q_proof_first.reserve(4 * (nq + 1)));
+  CK(rb.q_byte_first.reserve(8 * (nq + 1)));
+  CK(cudaMemcpyAsync(rb.q_trie.p, ltrie.data(), 4 * nq, cudaMemcpyHostToDevice, st));
+  if (kb) CK(cudaMemcpyAsync(rb.q_key_bytes.p, tg->key_bytes + k0, kb, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(rb.q_key_off.p, lkoff.data(), 4 * (nq + 1), cudaMemcpyHostToDevice, st));
+  CK(launch_trie_proof_count(sl.b, w, rb.q_trie.as<uint32_t>(), rb.q_key_bytes.as<uint8_t>(), rb.q_key_off.as<uint32_t>(),
+                             (uint32_t)nq, rb.q_cnt.as<uint32_t>(), rb.q_bytes.as<uint64_t>(),
+                             rb.q_proof_first.as<uint32_t>(), rb.q_byte_first.as<uint64_t>(), st));
+  CK(cudaMemcpyAsync(&sl.n_nodes, rb.q_proof_first.as<uint32_t>() + nq, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&sl.n_bytes, rb.q_byte_first.as<uint64_t>() + nq, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));  // (the pageable copies above were staged by the driver before returning)
+  return MPTV_OK;
+}
+
+// phase 2: emit the slice's proofs and copy them to their place in the caller's arrays
+static int trie_proofs_emit(mptv_ctx* ctx, Device& d, const ProofSlice& sl, mptv_proofs_out* out, uint64_t node_base, uint64_t byte_base) {
+  const uint64_t nq = sl.q1 - sl.q0;
+  if (nq == 0) return MPTV_OK;
+  Rebuild& rb = d.rb;
+  CK(cudaSetDevice(d.id));
+  cudaStream_t st = d.stream;
+  TrieWork w;
+  w.rec = rb.rec.as<uint4>(); w.off = rb.off.as<uint64_t>(); w.len = rb.len.as<uint32_t>();
+  w.digests = rb.digests.as<uint8_t>(); w.tcount = rb.tcount.as<uint32_t>(); w.lvl_list = rb.lvl_list.as<uint32_t>();
+  w.sum = rb.sum.as<TrieSummary>();
+  CK(rb.q_out_bytes.reserve((size_t)sl.n_bytes + 16));
+  CK(rb.q_out_off.reserve(8 * (size_t)sl.n_nodes + 8));
+  CK(rb.q_out_len.reserve(4 * (size_t)sl.n_nodes + 4));
+  CK(cudaMemsetAsync(rb.q_out_bytes.p, 0, (size_t)sl.n_bytes + 16, st));
+  CK(launch_trie_proof_emit(sl.b, w, rb.arena.as<uint8_t>(), rb.q_trie.as<uint32_t>(), rb.q_key_bytes.as<uint8_t>(),
+                            rb.q_key_off.as<uint32_t>(), (uint32_t)nq, rb.q_proof_first.as<uint32_t>(),
+                            rb.q_byte_first.as<uint64_t>(), rb.q_out_bytes.as<uint8_t>(), rb.q_out_off.as<uint64_t>(),
+                            rb.q_out_len.as<uint32_t>(), rb.leaves_in_arena, st));
+  if (sl.n_bytes) CK(cudaMemcpyAsync(out->node_bytes + byte_base, rb.q_out_bytes.p, (size_t)sl.n_bytes, cudaMemcpyDeviceToHost, st));
+  if (sl.n_nodes) {
+    CK(cudaMemcpyAsync(out->node_off + node_base, rb.q_out_off.p, 8 * (size_t)sl.n_nodes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->node_len + node_base, rb.q_out_len.p, 4 * (size_t)sl.n_nodes, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaMemcpyAsync(out->proof_first + sl.q0, rb.q_proof_first.p, 4 * nq, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  // the slice's offsets and node indices were relative to the slice: move them to their place in the whole output
+  if (byte_base) for (uint64_t i = 0; i < sl.n_nodes; i++) out->node_off[node_base + i] += byte_base;
+  if (node_base) for (uint64_t q = 0; q < nq; q++) out->proof_first[sl.q0 + q] += (uint32_t)node_base;
+  return MPTV_OK;
+}
+
 static int trie_proofs_run(mptv_ctx* ctx, const mptv_kv_batch* in, const mptv_proof_targets* tg, uint8_t* roots32,
                            mptv_proofs_out* out) {
   if (!ctx || !in || !tg || !out) return MPTV_ERR_ARG;
@@ -293,73 +377,74 @@ static int trie_proofs_run(mptv_ctx* ctx, const mptv_kv_batch* in, const mptv_pr
   if (in->n_tries == 0) return nq ? MPTV_ERR_ARG : MPTV_OK;
   const int ck = check_kv(in, roots32);
   if (ck != MPTV_OK) return ck;
+  bool ordered = true;  // targets grouped by trie in ascending order: the usual shape, and what lets the devices share them
   for (uint64_t q = 0; q < nq; q++) {
     if (tg->trie[q] >= in->n_tries || tg->key_off[q + 1] < tg->key_off[q] ||
         tg->key_off[q + 1] - tg->key_off[q] > (uint32_t)kTrieMaxKeyLen)
       return MPTV_ERR_ARG;
+    if (q && tg->trie[q] < tg->trie[q - 1]) ordered = false;
   }
-  Device& d = ctx->dev[0];
-  Rebuild& rb = d.rb;
-  CK(cudaSetDevice(d.id));
-  cudaStream_t st = d.stream;
-  TrieBatchDev b;
-  int rc = upload_kv(ctx, d, in, 0, in->n_tries, rb.stage[0], b, st);
-  if (rc != MPTV_OK) return rc;
-  CK(rb.out_roots.reserve(32 * in->n_tries));
-  rc = rebuild_on_device(ctx, d, b, rb.out_roots.as<uint8_t>(), st);
-  if (rc != MPTV_OK) return rc;
-  CK(cudaMemcpyAsync(roots32, rb.out_roots.p, 32 * in->n_tries, cudaMemcpyDeviceToHost, st));
-  if (nq == 0) { CK(cudaStreamSynchronize(st)); return MPTV_OK; }
-  TrieWork w;
-  w.rec = rb.rec.as<uint4>(); w.off = rb.off.as<uint64_t>(); w.len = rb.len.as<uint32_t>();
-  w.digests = rb.digests.as<uint8_t>(); w.tcount = rb.tcount.as<uint32_t>(); w.lvl_list = rb.lvl_list.as<uint32_t>();
-  w.sum = rb.sum.as<TrieSummary>();
-  const uint32_t kb = tg->key_off[nq];
-  CK(rb.q_trie.reserve(4 * nq));
-  CK(rb.q_key_bytes.reserve((size_t)kb + 16));
-  CK(rb.q_key_off.reserve(4 * (nq + 1)));
-  CK(rb.q_cnt.reserve(4 * nq));
-  CK(rb.q_bytes.reserve(8 * nq));
-  CK(rb.q_proof_first.reserve(4 * (nq + 1)));
-  CK(rb.q_byte_first.reserve(8 * (nq + 1)));
-  CK(cudaMemcpyAsync(rb.q_trie.p, tg->trie, 4 * nq, cudaMemcpyHostToDevice, st));
-  if (kb) CK(cudaMemcpyAsync(rb.q_key_bytes.p, tg->key_bytes, kb, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(rb.q_key_off.p, tg->key_off, 4 * (nq + 1), cudaMemcpyHostToDevice, st));
-  CK(launch_trie_proof_count(b, w, rb.q_trie.as<uint32_t>(), rb.q_key_bytes.as<uint8_t>(), rb.q_key_off.as<uint32_t>(),
-                             (uint32_t)nq, rb.q_cnt.as<uint32_t>(), rb.q_bytes.as<uint64_t>(),
-                             rb.q_proof_first.as<uint32_t>(), rb.q_byte_first.as<uint64_t>(), st));
-  uint32_t total_nodes = 0;
-  uint64_t total_bytes = 0;
-  CK(cudaMemcpyAsync(&total_nodes, rb.q_proof_first.as<uint32_t>() + nq, 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(&total_bytes, rb.q_byte_first.as<uint64_t>() + nq, 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  out->n_nodes = total_nodes;
-  out->node_bytes_len = total_bytes + 16;
-  if (total_nodes > out->nodes_cap || total_bytes + 16 > out->node_bytes_cap || !out->node_bytes || !out->node_off ||
+  // tries are cut into contiguous slices with equal shares of the value bytes, one per device (no inter-device
+  // traffic); the targets of a slice are then a contiguous range of the (trie-ordered) target list
+  int nd = (int)ctx->dev.size();
+  if (!ordered || in->n_tries < 8ull * nd) nd = 1;
+  std::vector<ProofSlice> sl(nd);
+  {
+    uint64_t t = 0, q = 0;
+    for (int k = 0; k < nd; k++) {
+      sl[k].t0 = t;
+      if (k == nd - 1) t = in->n_tries;
+      else {
+        const uint64_t target = in->value_bytes_len / nd * (k + 1);
+        uint64_t lo = t, hi = in->n_tries;
+        while (lo < hi) {
+          const uint64_t mid = (lo + hi) / 2;
+          const uint32_t fi = in->trie_first[mid];
+          const uint64_t off = fi < in->n_items ? in->value_off[fi] : in->value_bytes_len;
+          if (off < target) lo = mid + 1; else hi = mid;
+        }
+        t = lo;
+      }
+      sl[k].t1 = t;
+      sl[k].q0 = q;
+      if (nd == 1) q = nq;
+      else while (q < nq && tg->trie[q] < t) q++;
+      sl[k].q1 = q;
+    }
+  }
+  auto for_each_device = [&](auto&& fn) {
+    if (nd == 1) { sl[0].rc = fn(0); return; }
+    std::vector<std::thread> th;
+    for (int k = 0; k < nd; k++) th.emplace_back([&, k] { sl[k].rc = fn(k); });
+    for (auto& x : th) x.join();
+  };
+  for_each_device([&](int k) { return trie_proofs_count(ctx, ctx->dev[k], in, tg, roots32, sl[k]); });
+  for (int k = 0; k < nd; k++) if (sl[k].rc != MPTV_OK) return sl[k].rc;
+  if (nq == 0) return MPTV_OK;
+  std::vector<uint64_t> node_base(nd + 1, 0), byte_base(nd + 1, 0);
+  for (int k = 0; k < nd; k++) { node_base[k + 1] = node_base[k] + sl[k].n_nodes; byte_base[k + 1] = byte_base[k] + sl[k].n_bytes; }
+  out->n_nodes = node_base[nd];
+  out->node_bytes_len = byte_base[nd] + 16;
+  if (node_base[nd] > 0xfffffff0ull) return MPTV_ERR_ARG;
+  if (node_base[nd] > out->nodes_cap || byte_base[nd] + 16 > out->node_bytes_cap || !out->node_bytes || !out->node_off ||
       !out->node_len)
     return MPTV_ERR_NOMEM;  // n_nodes / node_bytes_len hold what is required
-  CK(rb.q_out_bytes.reserve((size_t)total_bytes + 16));
-  CK(rb.q_out_off.reserve(8 * (size_t)total_nodes + 8));
-  CK(rb.q_out_len.reserve(4 * (size_t)total_nodes + 4));
-  CK(cudaMemsetAsync(rb.q_out_bytes.p, 0, (size_t)total_bytes + 16, st));
-  CK(launch_trie_proof_emit(b, w, rb.arena.as<uint8_t>(), rb.q_trie.as<uint32_t>(), rb.q_key_bytes.as<uint8_t>(),
-                            rb.q_key_off.as<uint32_t>(), (uint32_t)nq, rb.q_proof_first.as<uint32_t>(),
-                            rb.q_byte_first.as<uint64_t>(), rb.q_out_bytes.as<uint8_t>(), rb.q_out_off.as<uint64_t>(),
-                            rb.q_out_len.as<uint32_t>(), rb.leaves_in_arena, st));
-  CK(cudaMemcpyAsync(out->node_bytes, rb.q_out_bytes.p, (size_t)total_bytes + 16, cudaMemcpyDeviceToHost, st));
-  if (total_nodes) {
-    CK(cudaMemcpyAsync(out->node_off, rb.q_out_off.p, 8 * (size_t)total_nodes, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out->node_len, rb.q_out_len.p, 4 * (size_t)total_nodes, cudaMemcpyDeviceToHost, st));
-  }
-  CK(cudaMemcpyAsync(out->proof_first, rb.q_proof_first.p, 4 * (nq + 1), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  for_each_device([&](int k) { return trie_proofs_emit(ctx, ctx->dev[k], sl[k], out, node_base[k], byte_base[k]); });
+  for (int k = 0; k < nd; k++) if (sl[k].rc != MPTV_OK) return sl[k].rc;
+  out->proof_first[nq] = (uint32_t)node_base[nd];
+  memset(out->node_bytes + byte_base[nd], 0, 16);
   return MPTV_OK;
 }
 
 int mptv_trie_proofs(mptv_ctx* ctx, const mptv_kv_batch* in, const mptv_proof_targets* tg, uint8_t* roots32,
                      mptv_proofs_out* out) {
-  const int rc = trie_proofs_run(ctx, in, tg, roots32, out);
-  if (rc != MPTV_OK && ctx && !ctx->dev.empty()) quiesce(ctx->dev[0]);
+  int rc;
+  try {
+    rc = trie_proofs_run(ctx, in, tg, roots32, out);
+  } catch (...) {
+    rc = MPTV_ERR_NOMEM;
+  }
+  if (rc != MPTV_OK && rc != MPTV_ERR_NOMEM && ctx) for (Device& d : ctx->dev) quiesce(d);
   return rc;
 }
 

@@ -157,10 +157,19 @@ k_verify_small(const uint8_t* __restrict__ mailbox /* mapped page-locked host me
   __syncthreads();
   MPTV_TS(2);
   // ---- 3. the walk: G lanes per proof, independent proofs first, then the ones whose root is an account's storage_root
+  // A chain-shaped proof (what get_proof emits) is settled by ONE thread with K2f's check -- a few hundred
+  // instructions instead of the cooperative walk's thousands, which matter here because every instruction of a
+  // one-shot kernel is fetched cold; only what it defers goes to walk_one.
   const Group<G> g;
+  __shared__ uint8_t s_need[kSmallMaxProofs];
   for (int wave = 0; wave < (h.has_rfp ? 2 : 1); wave++) {
+    if (tid < h.n_proofs) {
+      const bool dependent = b.root_from_proof != nullptr && b.root_from_proof[tid] >= 0;
+      s_need[tid] = (dependent == (wave == 1)) && !fast_one(b, tid, dependent, digests, meta, status, value_off, value_len);
+    }
+    __syncthreads();
     for (uint32_t p = tid / G; p < h.n_proofs; p += kSmallThreads / G)  // uniform per group
-      walk_one<G>(b, wave, g, p, digests, meta, status, value_off, value_len);
+      if (s_need[p]) walk_one<G>(b, wave, g, p, digests, meta, status, value_off, value_len);
     __syncthreads();
   }
   MPTV_TS(3);
