@@ -76,6 +76,10 @@ def parse_args():
     ap.add_argument("--no-configs", action="store_true",
                     help="default run only: skip the compact config 1 / 3 / 4 blocks (N = 1) and config5 / single_context (N > 1)")
     ap.add_argument("--threads", type=int, default=0, help="host threads of the streamed borsh entry (0 = cores / ranks - 1)")
+    ap.add_argument("--borsh-mode", type=int, default=-1, choices=[-1, 0, 1, 2],
+                    help="mptv_verify_borsh mode of the e2e leg: 0 = the host flattens and aliases duplicate nodes (fewest PCIe bytes), "
+                         "1 = the device flattens the page-locked blobs (the cores touch nothing), 2 = both at once; "
+                         "-1 (default) = 0 on one GPU, 1 when several ranks share the host's memory system")
     ap.add_argument("--l2-fetch", type=int, default=0, help="L2 fetch granularity hint in bytes (32/64/128; 0 = leave the default)")
     ap.add_argument("--dedup", action="store_true",
                     help="SECONDARY number: hash each distinct node of the batch once (dedup_nodes option); the "
@@ -618,8 +622,10 @@ def e2e_from_borsh(a, ver, b, env, dev, st, voff, vlen, steps):
     import zk_state_proofs_b200 as z
     from workload import gen
     rank, world, local = env
-    blobs, boff = gen.batch_to_borsh(b, pinned=False)  # ordinary memory, as a prover's input file read into a Vec<u8> would be
+    blobs, boff = gen.batch_to_borsh(b, pinned=not a.pageable)  # page-locked unless --pageable (the device-flatten mode needs it)
     th = flatten_threads(a, world)
+    mode = a.borsh_mode if a.borsh_mode >= 0 else (1 if world > 1 and not a.pageable else 0)
+    ver.set_option("borsh_mode", mode)
     for _ in range(2):
         bst, bvoff, bvlen = ver.verify_borsh(blobs, boff, threads=th)
     if world > 1:
@@ -638,6 +644,7 @@ def e2e_from_borsh(a, ver, b, env, dev, st, voff, vlen, steps):
     read_gbs, copy_gbs = z.host_bw_probe(th, 128 << 20)
     h2d_gbs = h2d_peak_gbs(dev, world)
     flat_s = min(z.borsh_flatten_probe(blobs, boff, threads=th, chunk_bytes=32 << 20)[0] for _ in range(3))
+    ver.set_option("borsh_mode", 0)
     all_proofs, blob_bytes, h2d, d2h, read_sum, copy_sum, h2d_sum, launches = reduce_sum(
         [b.n_proofs, len(blobs), hs.h2d_bytes / steps, hs.d2h_bytes / steps, read_gbs, copy_gbs, h2d_gbs, hs.launches / steps], world, dev)
     placed = hs.node_bytes_placed / steps
@@ -645,11 +652,19 @@ def e2e_from_borsh(a, ver, b, env, dev, st, voff, vlen, steps):
     # staged is written once by the cores and read once by the DMA engine; in pull mode the placed node bytes are not
     # staged but read once more, by the device, straight from the blobs
     pulled = hs.node_bytes_placed / steps if hs.pull_chunks else 0
-    dram = len(blobs) + 2 * (hs.h2d_bytes / steps - pulled) + pulled
+    if hs.device_chunks == hs.chunks:   # device flatten: the blobs are read once, by the DMA engine; the cores touch nothing
+        dram = hs.h2d_bytes / steps
+    else:
+        dram = len(blobs) + 2 * (hs.h2d_bytes / steps - pulled) + pulled
     dram_all = reduce_sum([dram], world, dev)[0]
     return dict(
         value=all_proofs / dt, unit=UNIT, ms_per_step=dt * 1e3, entry="mptv_verify_borsh",
-        host_memory="pageable blobs, page-locked staging inside the library",
+        host_memory=("pageable blobs, page-locked staging inside the library" if a.pageable else "page-locked blobs"),
+        borsh_mode={0: "0: the host flattens (one pass, byte-identical nodes of a chunk aliased), staging copied by the DMA engine",
+                    1: "1: the blobs cross PCIe as they are and the device flattens them (borsh_kernels.cu): several ranks share one "
+                       "host memory system, so the cores touch nothing",
+                    2: "2: both pipelines at once"}[mode],
+        device_chunks_per_step=int(hs.device_chunks / steps),
         pull_chunks_per_step=int(hs.pull_chunks / steps), chunks_per_step=int(hs.chunks / steps),
         input_bytes_per_step=int(blob_bytes), h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), host_threads_per_rank=th,
         timer="host wall clock around the blocking C-ABI call, max over ranks",
@@ -665,7 +680,8 @@ def e2e_from_borsh(a, ver, b, env, dev, st, voff, vlen, steps):
                                      note="blob bytes read by the cores vs the read-only probe"),
                       pcie=dict(achieved=h2d / dt / 1e9, peak=h2d_sum, unit="GB/s", frac=h2d / dt / 1e9 / h2d_sum,
                                 note="H2D bytes vs pinned-copy bandwidth measured now on all ranks at once, summed"),
-                      limiter="host memory bandwidth: the cores must read every supplied byte once to compare it"),
+                      limiter=("host memory bandwidth: the cores must read every supplied byte once to compare it" if mode == 0 else
+                               "the host's memory system / PCIe: every blob byte is read once by the DMA engines of all ranks")),
         gpu_launches_per_step=int(launches))
 
 
@@ -854,7 +870,8 @@ def single_context(a, env, b):
         if name == "mptv_verify_batch":
             call = lambda: ver.verify_batch(b)
         else:
-            blobs, boff = gen.batch_to_borsh(b, pinned=False)
+            blobs, boff = gen.batch_to_borsh(b, pinned=not a.pageable)
+            ver.set_option("borsh_mode", a.borsh_mode if a.borsh_mode >= 0 else (0 if a.pageable else 1))
             call = lambda: ver.verify_borsh(blobs, boff, threads=a.threads)
         for _ in range(2):
             call()

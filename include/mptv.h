@@ -147,6 +147,7 @@ typedef struct mptv_host_stats {
   uint64_t launches;              /* kernels this library queued for those calls                             */
   uint64_t pull_chunks;           /* mptv_verify_borsh chunks whose node bytes the device fetched itself from
                                      page-locked blobs (h2d_bytes counts those bytes too)                    */
+  uint64_t device_chunks;         /* mptv_verify_borsh chunks flattened on the device ("borsh_mode" 1)         */
 } mptv_host_stats;
 int mptv_host_stats_get(mptv_ctx* ctx, mptv_host_stats* out, int reset);
 
@@ -176,6 +177,16 @@ int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops
  *   "lanes_per_proof"  K2b lanes per proof: 0 = choose from nodes/proof, else 8, 16 or 32
  *   "chunk_bytes"      node bytes per pipeline chunk of the host-buffer entry (default 96 MiB)
  *   "borsh_chunk_bytes" borsh bytes per pipeline chunk of mptv_verify_borsh (default 32 MiB)
+ *   "borsh_mode"       mptv_verify_borsh: 0 (default) = the HOST flattens: a pool of threads reads every blob once and
+ *                      stages the nodes, byte-identical nodes of a chunk only once ("host_dedup") -- fewest PCIe bytes,
+ *                      the right mode when one GPU has the host to itself; 1 = the DEVICE flattens: the blobs, which
+ *                      must be in page-locked memory, cross PCIe as they are and kernels lay the nodes out -- the cores
+ *                      touch nothing, the right mode when several GPUs share one host's memory system; 2 = BOTH at once
+ *                      on each device: the host pipeline takes chunks from the front of the device's blob range, the
+ *                      device pipeline from its back, until they meet -- one is bound by the cores, the other by PCIe
+ *                      (1 and 2 fall back to 0 for pageable blobs)
+ *   "hybrid_device_pct" borsh_mode 2: the share (1 ... 100 %, default 24) of the bytes the device pipeline may take; it
+ *                      is bound by PCIe and unthrottled would starve the host pipeline's copies
  *   "pull_pinned"      mptv_verify_borsh, blobs in page-locked memory (mptv_alloc_pinned, cudaHostAlloc, cudaHostRegister):
  *                      the staging copy carries only the index arrays and a gather list, and a kernel fetches the node
  *                      bytes straight from the blobs over PCIe -- the cores do not copy them and the DMA engine does not
@@ -359,7 +370,7 @@ MPTV_ABI_PIN(proofs_out_size, sizeof(mptv_proofs_out) == 64);
 MPTV_ABI_PIN(proofs_out_n_nodes, offsetof(mptv_proofs_out, n_nodes) == 48);
 MPTV_ABI_PIN(timings_size, sizeof(mptv_timings) == 64);
 MPTV_ABI_PIN(rebuild_timings_size, sizeof(mptv_rebuild_timings) == 64);
-MPTV_ABI_PIN(host_stats_size, sizeof(mptv_host_stats) == 104);
+MPTV_ABI_PIN(host_stats_size, sizeof(mptv_host_stats) == 112);
 MPTV_ABI_PIN(flatten_info_size, sizeof(mptv_flatten_info) == 32);
 MPTV_ABI_PIN(log_size, sizeof(mptv_log) == 40);
 #undef MPTV_ABI_PIN

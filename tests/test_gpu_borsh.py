@@ -123,3 +123,58 @@ def test_bad_root_length_empty_and_malformed_blobs(verifier, golden):
     # and the context is usable afterwards
     st, _, _ = verifier.verify_borsh([good])
     assert st.tolist() == [0]
+
+
+@pytest.mark.parametrize("lead", [0, 5])
+@pytest.mark.parametrize("chunk_bytes", [1 << 12, 1 << 16, 32 << 20])
+def test_device_flatten_mode(verifier, golden, oracle, chunk_bytes, lead):
+    """borsh_mode 1: the page-locked blobs cross PCIe as they are and kernels flatten them (borsh_kernels.cu): same
+    verdicts, the same value slices inside each proof's own blob as the host-flatten mode, BAD_ROOT_LEN, empty proofs,
+    and a malformed blob fails the call"""
+    import zk_state_proofs_b200 as z
+    from oracle.fuzzgen import corpus
+    vs = golden["vectors"]
+    blobs = [z.MerkleProofInput(v["proof_b"], v["root_b"], v["key_b"]).to_borsh() for v in vs]
+    cases = corpus(4242 + lead, oracle.keccak256, 30, 1500, 2000, 1200, 1500, 600)
+    blobs += [z.MerkleProofInput(c["proof"], c["root"], c["key"]).to_borsh() for c in cases]
+    v0 = next(v for v in vs if v["status"] == 0)
+    blobs += [z.MerkleProofInput(v0["proof_b"], v0["root_b"][:31], v0["key_b"]).to_borsh(), z.MerkleProofInput([], v0["root_b"], b"").to_borsh(),
+              z.MerkleProofInput([b""], b"", b"").to_borsh()]
+    buf, off = _concat(blobs)
+    want = verifier.verify_borsh(buf, off, threads=4)          # host flatten, pageable
+    pin = _Pinned(buf, lead=lead)
+    verifier.set_option("borsh_mode", 1)
+    verifier.set_option("borsh_chunk_bytes", chunk_bytes)
+    verifier.host_stats(reset=True)
+    try:
+        got = verifier.verify_borsh(pin.arr, off)
+        hs = verifier.host_stats()
+        assert hs.device_chunks == hs.chunks > 0 and hs.nodes == sum(len(z.MerkleProofInput.from_borsh(b).proof) for b in blobs[-3:]) + \
+            sum(len(v["proof_b"]) for v in vs) + sum(len(c["proof"]) for c in cases)
+        for x, y in zip(got, want):
+            assert (x == y).all()
+        assert got[0][-3:].tolist() == [6, 1, 6]
+        # hybrid: the host pipeline takes chunks from the front, the device pipeline from the back, at the same time
+        verifier.set_option("borsh_mode", 2)
+        verifier.host_stats(reset=True)
+        both = verifier.verify_borsh(pin.arr, off, threads=4)
+        hs = verifier.host_stats()
+        assert all((x == y).all() for x, y in zip(both, want)) and hs.nodes == verifier.host_stats().nodes
+        assert 0 < hs.device_chunks < hs.chunks or chunk_bytes >= (32 << 20)
+        verifier.set_option("borsh_mode", 1)
+        # pageable blobs fall back to the host flatten
+        verifier.host_stats(reset=True)
+        again = verifier.verify_borsh(buf, off, threads=4)
+        assert verifier.host_stats().device_chunks == 0 and all((x == y).all() for x, y in zip(again, want))
+        # what borsh::from_slice rejects fails the whole call, wherever it sits; the context stays usable
+        good = blobs[0]
+        for bad in (good[:-1], good + b"\0", good[:3], b"", b"\xff\xff\xff\xff" + good[4:]):
+            b2, o2 = _concat([good] * 40 + [bad] + [good] * 40)
+            p2 = _Pinned(b2, lead=lead)
+            with pytest.raises(z.MptvError):
+                verifier.verify_borsh(p2.arr, o2)
+        st, _, _ = verifier.verify_borsh(_Pinned(_concat([good])[0]).arr, _concat([good])[1])
+        assert st.tolist() == [vs[0]["status"]]
+    finally:
+        verifier.set_option("borsh_mode", 0)
+        verifier.set_option("borsh_chunk_bytes", 32 << 20)

@@ -52,6 +52,43 @@ for dd in (1, 0):
                   f"{hs.chunks} chunks ({hs.pull_chunks} pulled), flatten {hs.flatten_us / 1e3:.1f} ms | host stage alone {pt * 1e3:6.1f} ms ({len(blobs) / pt / 1e9:5.1f} GB/s read)", flush=True)
 ver.set_option("borsh_chunk_bytes", 32 << 20)
 ver.set_option("host_dedup", 1)
+# device flatten: page-locked blobs cross PCIe as they are, kernels lay the nodes out
+pblobs, pboff = gen.batch_to_borsh(b, pinned=True)
+ver.set_option("borsh_mode", 1)
+for mb in (16, 32, 64):
+    ver.set_option("borsh_chunk_bytes", mb << 20)
+    best = 1e9
+    for it in range(4):
+        ver.host_stats(reset=True)
+        t0 = time.perf_counter()
+        dst, dvoff, dvlen = ver.verify_borsh(pblobs, pboff)
+        dt = time.perf_counter() - t0
+        if it:
+            best = min(best, dt)
+    hs = ver.host_stats()
+    assert (dst == ref[0]).all() and (dvlen == ref[2]).all() and (dvoff == voff).all()
+    print(f"device flatten chunk {mb:4d} MB: {best * 1e3:7.1f} ms = {n / best / 1e6:6.2f} M proofs/s | H2D {hs.h2d_bytes / 1e9:5.2f} GB "
+          f"({hs.h2d_bytes / best / 1e9:5.1f} GB/s), {hs.device_chunks} chunks on the device", flush=True)
+# hybrid: both pipelines on the one device, chunks from the two ends of the input
+ver.set_option("borsh_mode", 2)
+for mb, pct in ((32, 15), (32, 20), (32, 24), (32, 30), (32, 40), (16, 24), (64, 24)):
+    for th in (0,):
+        ver.set_option("borsh_chunk_bytes", mb << 20)
+        ver.set_option("hybrid_device_pct", pct)
+        best = 1e9
+        for it in range(5):
+            ver.host_stats(reset=True)
+            t0 = time.perf_counter()
+            dst, dvoff, dvlen = ver.verify_borsh(pblobs, pboff, threads=th)
+            dt = time.perf_counter() - t0
+            if it:
+                best = min(best, dt)
+        hs = ver.host_stats()
+        assert (dst == ref[0]).all() and (dvlen == ref[2]).all() and (dvoff == voff).all()
+        print(f"hybrid {pct:2d} % chunk {mb:4d} MB threads {th or cores - 1:2d}: {best * 1e3:7.1f} ms = {n / best / 1e6:6.2f} M proofs/s | H2D {hs.h2d_bytes / 1e9:5.2f} GB "
+              f"({hs.h2d_bytes / best / 1e9:5.1f} GB/s), {hs.device_chunks} of {hs.chunks} chunks on the device, aliased {hs.nodes_aliased}", flush=True)
+ver.set_option("borsh_mode", 0)
+ver.set_option("borsh_chunk_bytes", 32 << 20)
 ok = np.nonzero(st == 0)[0][:5000]
 for i in ok:
     assert blobs[int(voff[i]):int(voff[i]) + int(vlen[i])].tobytes() == b.value(int(ref[1][i]), int(ref[2][i]))

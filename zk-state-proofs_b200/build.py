@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmptv.so")
 OBJ = os.path.join(HERE, "..", "build", "obj")
-SOURCES = ["keccak_kernels.cu", "verify_kernels.cu", "single_kernels.cu", "rebuild_kernels.cu", "dedup_kernels.cu",
+SOURCES = ["keccak_kernels.cu", "verify_kernels.cu", "single_kernels.cu", "borsh_kernels.cu", "rebuild_kernels.cu", "dedup_kernels.cu",
            "microbench.cu", "mptv_api.cu", "rebuild_api.cu", "host_codec.cpp", "host_flatten.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMPILE_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O2,-pthread,-mavx2"]

@@ -296,7 +296,8 @@ class HostStats(ctypes.Structure):
                 ("node_bytes_supplied", ctypes.c_uint64), ("node_bytes_placed", ctypes.c_uint64),
                 ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
                 ("flatten_us", ctypes.c_uint64), ("wait_us", ctypes.c_uint64), ("map_us", ctypes.c_uint64),
-                ("call_us", ctypes.c_uint64), ("launches", ctypes.c_uint64), ("pull_chunks", ctypes.c_uint64)]
+                ("call_us", ctypes.c_uint64), ("launches", ctypes.c_uint64), ("pull_chunks", ctypes.c_uint64),
+                ("device_chunks", ctypes.c_uint64)]
 
 
 FLATTEN_ALIAS_DUPLICATES = 1

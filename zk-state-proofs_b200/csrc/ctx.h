@@ -63,15 +63,22 @@ struct Slot {
   DevBuf node_bytes, node_off, node_len, proof_first, roots, key_bytes, key_off, rfp;
   DevBuf results, in_pack;
   DevBuf hk_flags, hk_off, hk_len;  // mptv_verify_batch_hashed_keys: the chunk's flags and the key records built on the device
+  // device flatten mode of mptv_verify_borsh: the chunk's blobs as the caller wrote them, and what the walk kernels produce
+  DevBuf f_img, f_off, f_nodes, f_bytes, f_flags, f_node_first, f_byte_first, f_totals;
+  HostBuf f_h_off, f_h_totals;
+  cudaEvent_t f_counted = nullptr;  // the chunk is on the device and counted (totals are in f_h_totals)
+  uint64_t f_cs = 0, f_ce = 0;
   DevBuf digests, meta, order, bins, defer, dedup;
   void release() {
     DevBuf* all[] = {&node_bytes, &node_off, &node_len, &proof_first, &roots, &key_bytes, &key_off, &rfp,
-                     &results, &in_pack, &digests, &meta, &order, &bins, &defer, &dedup, &hk_flags, &hk_off, &hk_len};
+                     &results, &in_pack, &digests, &meta, &order, &bins, &defer, &dedup, &hk_flags, &hk_off, &hk_len,
+                     &f_img, &f_off, &f_nodes, &f_bytes, &f_flags, &f_node_first, &f_byte_first, &f_totals};
     for (DevBuf* b : all) b->release();
-    h_results.release(); h_in.release();
+    h_results.release(); h_in.release(); f_h_off.release(); f_h_totals.release();
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
-    stream = nullptr; done = nullptr;
+    if (f_counted) cudaEventDestroy(f_counted);
+    stream = nullptr; done = nullptr; f_counted = nullptr;
   }
 };
 
@@ -118,6 +125,7 @@ struct Rebuild {
 };
 
 constexpr int kSlots = 3;  // pipeline depth of the host-buffer path (H2D / kernels / D2H in flight)
+constexpr int kSlotsTotal = 2 * kSlots;  // the hybrid borsh mode runs a second pipeline (device flatten) on slots 3 .. 5
 
 struct Device {
   int id = 0;
@@ -125,7 +133,8 @@ struct Device {
   cudaStream_t stream = nullptr;  // device-resident entry
   DevBuf digests, meta, order, bins, defer, dedup;  // scratch of the device-resident entry
   uint64_t last_unique_nodes = 0, last_unique_perm = 0;  // of the last dedup_nodes run
-  Slot slot[kSlots];
+  Slot slot[kSlotsTotal];
+  mptv_host_stats hstat2 = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // of the second pipeline's thread (hybrid mode); summed on read
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaStream_t last_stream = nullptr;
   bool have_timing = false;
@@ -137,7 +146,7 @@ struct Device {
   uint8_t* mb_dev = nullptr;
   uint32_t mb_seq = 0;
   DedupTable dedup_tab;  // host-side candidate table of the streamed borsh entry (one chunk at a time)
-  mptv_host_stats hstat = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // of the host-fed entries since the last reset
+  mptv_host_stats hstat = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // of the host-fed entries since the last reset
 };
 
 }  // namespace mptv
@@ -152,6 +161,9 @@ struct mptv_ctx {
   int binning = 1;
   int fused_classify = 1;  // K1 also classifies plain branches / leaves (K2a fast path)
   int dedup_nodes = 0;     // hash each DISTINCT node once (secondary mode, reported separately)
+  int borsh_mode = 0;      // mptv_verify_borsh: 0 = the host flattens (and aliases), 1 = the device flattens page-locked blobs,
+                           // 2 = both at once on one device, chunks handed out from the two ends of the input
+  int hybrid_device_pct = 24;  // borsh_mode 2: share of a device's blob bytes its device-flatten pipeline may take
   int pull_pinned = 0;     // streamed borsh entry, page-locked blobs: the device gathers the placed node bytes itself (measured slower: off)
   int host_dedup = 1;      // streamed borsh entry: alias byte-identical nodes of a chunk instead of copying them again
   int latency_path = 1;    // batches that fit one CTA: one launch, mapped page-locked memory both ways (single_kernels.cu)
@@ -186,7 +198,7 @@ inline int fail_msg(mptv_ctx* c, int rc, const char* msg) {
 inline void quiesce(Device& d) {
   cudaSetDevice(d.id);
   if (d.stream) cudaStreamSynchronize(d.stream);
-  for (Slot& s : d.slot) {
+  for (Slot& s : d.slot) {  // both pipelines' slots
     if (s.stream) cudaStreamSynchronize(s.stream);
     s.pend_np = 0;
     s.pend_borsh = false;

@@ -91,6 +91,21 @@ cudaError_t launch_prepare_keys(const uint8_t* key_bytes, const uint32_t* key_of
 cudaError_t launch_gather(const uint8_t* src_base, uint8_t* dst_base, const uint4* recs, uint32_t n_recs, int sm_count,
                           cudaStream_t st);
 
+// device flatten (borsh_kernels.cu): a chunk of borsh(MerkleProofInput) blobs, resident on the device as the caller
+// wrote them (img, blob i = [off[i], off[i + 1])), becomes the CSR arrays of a DeviceBatch.
+// count: per-blob node count / padded bytes / flags (bit 0 well-formed, bit 1 root_hash.len() != 32), their exclusive
+// scans, and totals = {nodes, bytes, malformed blobs}.  emit (only when no blob is malformed): index arrays and one
+// gather record per node and key for launch_gather.  map: results in place -> offsets into the caller's blobs.
+cudaError_t launch_blob_count(const uint8_t* img, const uint64_t* off, uint32_t np, uint32_t* n_nodes, uint64_t* n_bytes, uint8_t* flags,
+                              uint32_t* node_first, uint64_t* byte_first, unsigned long long* totals, cudaStream_t st);
+cudaError_t launch_blob_emit(const uint8_t* img, const uint64_t* off, uint32_t np, uint32_t nn, const uint32_t* node_first,
+                             const uint64_t* byte_first, uint64_t arena_off, uint64_t blob_base, uint64_t* node_off, uint32_t* node_len,
+                             uint64_t* node_src, uint32_t* proof_first, uint8_t* roots, uint32_t* key_off, uint32_t* key_len,
+                             uint4* recs, cudaStream_t st);
+cudaError_t launch_blob_map(uint32_t np, const uint8_t* flags, const uint32_t* proof_first, const uint64_t* node_off,
+                            const uint32_t* node_len, const uint64_t* node_src, uint8_t* status, uint64_t* value_off,
+                            uint32_t* value_len, cudaStream_t st);
+
 // K2a: meta[i] = eager-decode record of node i.  only_slow: leave records != kMetaSlow untouched
 cudaError_t launch_parse_nodes(const uint8_t* node_bytes, uint64_t byte_base, const uint64_t* node_off,
                                const uint32_t* node_len, uint64_t n_nodes, uint32_t* meta, bool only_slow,

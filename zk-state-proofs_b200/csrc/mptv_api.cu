@@ -36,7 +36,7 @@ int pick_lanes(const mptv_ctx* ctx, uint64_t n_nodes, uint64_t n_proofs) {
 // The whole device pipeline for one device-resident (slice of a) batch: K0 -> K1 -> K2a -> K2b.
 int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests, DevBuf& meta, DevBuf& order,
                  DevBuf& bins, DevBuf& defer, DevBuf& dedup, uint8_t* status, uint64_t* value_off, uint32_t* value_len, cudaStream_t st,
-                 bool timed) {
+                 bool timed, mptv_host_stats* hs = nullptr /* whose launch counter (default: the device's) */) {
   CK(digests.reserve(32 * (size_t)b.n_nodes + 32));
   CK(meta.reserve(4 * (size_t)b.n_nodes + 4));
   CK(order.reserve(4 * (size_t)b.n_nodes + 4));
@@ -53,7 +53,7 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
   const bool dd = ctx->dedup_nodes && !one_wave && b.n_nodes <= (1ull << 30);  // the table has 2^k >= 2 n slots, k <= 31
   uint64_t n_hash = b.n_nodes;
   uint32_t* dup_of = nullptr;
-  d.last_unique_nodes = 0; d.last_unique_perm = 0;
+  if (timed || dd) { d.last_unique_nodes = 0; d.last_unique_perm = 0; }
   if (dd) {
     uint32_t tsz = 1;
     while (tsz < 2 * b.n_nodes) tsz <<= 1;
@@ -111,7 +111,7 @@ int run_pipeline(mptv_ctx* ctx, Device& d, const DeviceBatch& b, DevBuf& digests
     d.last_keccak_launches = keccak_launches;
     d.last_other_launches = other;
   } else {
-    d.hstat.launches += keccak_launches + other;  // the host-fed entries: kernels queued for this chunk
+    (hs ? *hs : d.hstat).launches += keccak_launches + other;  // the host-fed entries: kernels queued for this chunk
   }
   return MPTV_OK;
 }
@@ -181,7 +181,7 @@ int mptv_create(const int* device_ids, int n_devices, mptv_ctx** out) {
       }
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
-    for (int s = 0; s < kSlots && e == cudaSuccess; s++) e = cudaStreamCreateWithFlags(&d.slot[s].stream, cudaStreamNonBlocking);
+    for (int s = 0; s < kSlotsTotal && e == cudaSuccess; s++) e = cudaStreamCreateWithFlags(&d.slot[s].stream, cudaStreamNonBlocking);
     for (int k = 0; k < 6 && e == cudaSuccess; k++) e = cudaEventCreate(&d.ev[k]);
     if (e != cudaSuccess) {
       fprintf(stderr, "mptv_create: device %d: %s\n", d.id, cudaGetErrorString(e));
@@ -199,7 +199,7 @@ void mptv_destroy(mptv_ctx* ctx) {
     cudaSetDevice(d.id);
     cudaDeviceSynchronize();
     d.digests.release(); d.meta.release(); d.order.release(); d.bins.release(); d.defer.release(); d.dedup.release();
-    for (int k = 0; k < kSlots; k++) d.slot[k].release();
+    for (int k = 0; k < kSlotsTotal; k++) d.slot[k].release();
     d.rb.release();
     if (d.mb_host) cudaFreeHost(d.mb_host);
     d.mb_host = d.mb_dev = nullptr;
@@ -220,6 +220,12 @@ int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
   } else if (!strcmp(name, "borsh_chunk_bytes")) {
     if (value < (1 << 12) || value > (1ll << 31)) return MPTV_ERR_ARG;
     ctx->borsh_chunk_bytes = (uint64_t)value;
+  } else if (!strcmp(name, "borsh_mode")) {
+    if (value < 0 || value > 2) return MPTV_ERR_ARG;
+    ctx->borsh_mode = (int)value;
+  } else if (!strcmp(name, "hybrid_device_pct")) {
+    if (value < 1 || value > 100) return MPTV_ERR_ARG;
+    ctx->hybrid_device_pct = (int)value;
   } else if (!strcmp(name, "pull_pinned")) {
     ctx->pull_pinned = value ? 1 : 0;
   } else if (!strcmp(name, "host_dedup")) {
@@ -322,10 +328,16 @@ int mptv_host_stats_get(mptv_ctx* ctx, mptv_host_stats* out, int reset) {
     out->chunks += d.hstat.chunks; out->nodes += d.hstat.nodes; out->nodes_aliased += d.hstat.nodes_aliased;
     out->node_bytes_supplied += d.hstat.node_bytes_supplied; out->node_bytes_placed += d.hstat.node_bytes_placed;
     out->h2d_bytes += d.hstat.h2d_bytes; out->d2h_bytes += d.hstat.d2h_bytes;
-    out->launches += d.hstat.launches; out->pull_chunks += d.hstat.pull_chunks;
+    out->launches += d.hstat.launches; out->pull_chunks += d.hstat.pull_chunks; out->device_chunks += d.hstat.device_chunks;
     out->flatten_us += d.hstat.flatten_us; out->wait_us += d.hstat.wait_us; out->map_us += d.hstat.map_us;
     out->call_us += d.hstat.call_us;
-    if (reset) memset(&d.hstat, 0, sizeof d.hstat);
+    {
+      const mptv_host_stats& h2 = d.hstat2;
+      out->chunks += h2.chunks; out->nodes += h2.nodes; out->node_bytes_supplied += h2.node_bytes_supplied;
+      out->node_bytes_placed += h2.node_bytes_placed; out->h2d_bytes += h2.h2d_bytes; out->d2h_bytes += h2.d2h_bytes;
+      out->launches += h2.launches; out->device_chunks += h2.device_chunks;
+    }
+    if (reset) { memset(&d.hstat, 0, sizeof d.hstat); memset(&d.hstat2, 0, sizeof d.hstat2); }
   }
   return MPTV_OK;
 }
@@ -616,6 +628,44 @@ struct BorshStream {
   bool pinned;  // the blobs are page-locked and mapped: the devices can fetch node bytes from them directly (pull mode)
 };
 
+// Hands out the chunks of one device's blob range [front, back).  One pipeline takes them from the front; in the
+// hybrid mode a second pipeline takes them from the back at the same time, so the two share the range in proportion
+// to their speeds without anyone having to guess a split.
+struct ChunkFeeder {
+  const uint64_t* blob_off;
+  uint64_t front, back;
+  const uint64_t p0, p1;
+  int device_pct;  // hybrid: the share of the bytes the back (device) pipeline may take
+  std::mutex mu;
+  ChunkFeeder(const uint64_t* off, uint64_t a, uint64_t b, int pct) : blob_off(off), front(a), back(b), p0(a), p1(b), device_pct(pct) {}
+  bool take_front(uint64_t chunk_bytes, uint64_t& cs, uint64_t& ce) {
+    std::lock_guard<std::mutex> g(mu);
+    if (front >= back) return false;
+    cs = front;
+    ce = (uint64_t)(std::upper_bound(blob_off + cs + 1, blob_off + back + 1, blob_off[cs] + chunk_bytes) - blob_off);
+    if (ce > cs + 1) ce--;
+    if (ce > back) ce = back;
+    front = ce;
+    return true;
+  }
+  // 1 = got a chunk, 0 = nothing left, -1 = not now: the back pipeline is ahead of its share.  The device pipeline is
+  // bound by PCIe and would otherwise take chunks as fast as the link moves them, starving the host pipeline's copies
+  // (and every byte it takes costs 2.4 x the PCIe bytes of a byte the host pipeline flattens).
+  int take_back(uint64_t chunk_bytes, uint64_t& cs, uint64_t& ce) {
+    std::lock_guard<std::mutex> g(mu);
+    if (front >= back) return 0;
+    const uint64_t front_bytes = blob_off[front] - blob_off[p0], back_bytes = blob_off[p1] - blob_off[back];
+    if (device_pct < 100 && (back_bytes + chunk_bytes / 2) * (100 - device_pct) > (front_bytes + chunk_bytes) * device_pct) return -1;
+    ce = back;
+    const uint64_t want = blob_off[ce] > chunk_bytes ? blob_off[ce] - chunk_bytes : 0;
+    cs = (uint64_t)(std::lower_bound(blob_off + front, blob_off + ce, want) - blob_off);
+    if (cs >= ce) cs = ce - 1;
+    if (cs < front) cs = front;
+    back = cs;
+    return 1;
+  }
+};
+
 // results of a finished chunk (already in the slot's page-locked result block) -> the caller's arrays, by the pool
 // (on the submitter thread the same loop took ~0.3 ms a chunk and made that thread the bottleneck)
 void map_results_borsh(Slot& s, mptv_result* out, WorkerPool& pool) {
@@ -773,9 +823,8 @@ void borsh_submitter(mptv_ctx* ctx, Device& d, BorshPipe& P) {
   }
 }
 
-int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv_result* out, uint64_t p0, uint64_t p1,
+int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv_result* out, ChunkFeeder& feed,
                            WorkerPool& pool) {
-  if (p1 <= p0) return MPTV_OK;
   CK(cudaSetDevice(d.id));
   const bool alias = ctx->host_dedup != 0;
   if (alias && !d.dedup_tab.reserve((size_t)std::min<uint64_t>(ctx->borsh_chunk_bytes / 128 + 1024, 1ull << 22)))
@@ -800,12 +849,8 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
   int rc = MPTV_OK;
   const char* why = nullptr;
   size_t ci = 0;
-  for (uint64_t cs = p0; cs < p1 && rc == MPTV_OK; ci++) {
-    // the chunk: as many blobs as fit borsh_chunk_bytes of input
-    uint64_t ce = (uint64_t)(std::upper_bound(in.blob_off + cs + 1, in.blob_off + p1 + 1, in.blob_off[cs] + ctx->borsh_chunk_bytes) -
-                             in.blob_off);
-    if (ce > cs + 1) ce--;
-    if (ce > p1) ce = p1;
+  uint64_t cs = 0, ce = 0;
+  for (; rc == MPTV_OK && feed.take_front(ctx->borsh_chunk_bytes, cs, ce); ci++) {  // as many blobs as fit borsh_chunk_bytes of input
     const int k = (int)(ci % kSlots);
     Slot& s = d.slot[k];
     bool have_results = false;
@@ -846,7 +891,6 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
       P.produced++;
       P.cv.notify_all();
     }
-    cs = ce;
   }
   {
     std::lock_guard<std::mutex> g(P.mu);
@@ -867,9 +911,150 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
   return MPTV_OK;
 }
 
+// ------------------------------------------------------------------ device flatten ("borsh_mode" 1)
+// The blobs are page-locked: each chunk crosses PCIe as the caller wrote it and is flattened on the device
+// (borsh_kernels.cu); the cores touch nothing but the chunk's offsets.  Two phases per chunk, pipelined over the slots:
+//   A  copy the chunk + its offsets, walk the blobs (count), scan, read the totals back
+//   B  (once A's totals are here) lay out the pack, walk again (emit), gather, verify, map the results, read them back
+// A of chunk c + 1 is queued before B of chunk c, so its copy runs beside chunk c's kernels and B never waits for its
+// totals.  One thread per device; no worker pool.
+int borsh_device_phase_a(mptv_ctx* ctx, mptv_host_stats& hs, Slot& s, const BorshStream& in, uint64_t cs, uint64_t ce) {
+  cudaStream_t st = s.stream;
+  const uint64_t np = ce - cs, b0 = in.blob_off[cs], nbytes = in.blob_off[ce] - b0;
+  CK(s.f_img.reserve(nbytes + 32));
+  CK(s.f_off.reserve(8 * (np + 1)));
+  CK(s.f_h_off.reserve(8 * (np + 1)));
+  CK(s.f_nodes.reserve(4 * np + 4));
+  CK(s.f_bytes.reserve(8 * np + 8));
+  CK(s.f_flags.reserve(np + 16));
+  CK(s.f_node_first.reserve(4 * (np + 1)));
+  CK(s.f_byte_first.reserve(8 * (np + 1)));
+  CK(s.f_totals.reserve(32));
+  CK(s.f_h_totals.reserve(32));
+  if (!s.f_counted) CK(cudaEventCreateWithFlags(&s.f_counted, cudaEventBlockingSync | cudaEventDisableTiming));
+  uint64_t* ho = static_cast<uint64_t*>(s.f_h_off.p);
+  for (uint64_t i = 0; i <= np; i++) ho[i] = in.blob_off[cs + i] - b0;
+  CK(cudaMemcpyAsync(s.f_img.p, in.blobs + b0, nbytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.f_off.p, ho, 8 * (np + 1), cudaMemcpyHostToDevice, st));
+  CK(launch_blob_count(s.f_img.as<uint8_t>(), s.f_off.as<uint64_t>(), (uint32_t)np, s.f_nodes.as<uint32_t>(), s.f_bytes.as<uint64_t>(),
+                       s.f_flags.as<uint8_t>(), s.f_node_first.as<uint32_t>(), s.f_byte_first.as<uint64_t>(),
+                       s.f_totals.as<unsigned long long>(), st));
+  CK(cudaMemcpyAsync(s.f_h_totals.p, s.f_totals.p, 24, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(s.f_counted, st));
+  s.f_cs = cs; s.f_ce = ce;
+  hs.h2d_bytes += nbytes + 8 * (np + 1); hs.launches += 2;
+  return MPTV_OK;
+}
+
+int borsh_device_phase_b(mptv_ctx* ctx, Device& d, mptv_host_stats& hs, Slot& s, const BorshStream& in) {
+  cudaStream_t st = s.stream;
+  const uint64_t cs = s.f_cs, np = s.f_ce - s.f_cs, b0 = in.blob_off[cs];
+  CK(cudaEventSynchronize(s.f_counted));
+  const unsigned long long* tot = static_cast<const unsigned long long*>(s.f_h_totals.p);
+  const uint64_t nn = tot[0], nbytes = tot[1];
+  if (tot[2]) return fail_msg(ctx, MPTV_ERR_ARG, "mptv_verify_borsh: a blob is not a well-formed borsh(MerkleProofInput)");
+  if (nn > 0xfffffff0ull) return MPTV_ERR_ARG;
+  // the pack: index arrays, gather records, then the byte arena (every node on a 16-byte boundary)
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 63) & ~(size_t)63; return at; };
+  const size_t o_off = take(8 * nn), o_len = take(4 * nn), o_src = take(8 * nn), o_pf = take(4 * (np + 1)), o_roots = take(32 * np),
+               o_koff = take(4 * np), o_klen = take(4 * np), o_recs = take(16 * (nn + np)), o_arena = take(nbytes + 64);
+  if (o > 0xfffffff00ull) return MPTV_ERR_ARG;  // key offsets are 32-bit offsets into the pack
+  CK(s.in_pack.reserve(o + 16));
+  uint8_t* dv = s.in_pack.as<uint8_t>();
+  CK(launch_blob_emit(s.f_img.as<uint8_t>(), s.f_off.as<uint64_t>(), (uint32_t)np, (uint32_t)nn, s.f_node_first.as<uint32_t>(),
+                      s.f_byte_first.as<uint64_t>(), o_arena, b0, reinterpret_cast<uint64_t*>(dv + o_off),
+                      reinterpret_cast<uint32_t*>(dv + o_len), reinterpret_cast<uint64_t*>(dv + o_src),
+                      reinterpret_cast<uint32_t*>(dv + o_pf), dv + o_roots, reinterpret_cast<uint32_t*>(dv + o_koff),
+                      reinterpret_cast<uint32_t*>(dv + o_klen), reinterpret_cast<uint4*>(dv + o_recs), st));
+  CK(launch_gather(s.f_img.as<uint8_t>(), dv, reinterpret_cast<const uint4*>(dv + o_recs), (uint32_t)(nn + np), d.sm_count, st));
+  DeviceBatch b;
+  b.node_bytes = dv; b.node_off = reinterpret_cast<const uint64_t*>(dv + o_off);
+  b.node_len = reinterpret_cast<const uint32_t*>(dv + o_len);
+  b.proof_first = reinterpret_cast<const uint32_t*>(dv + o_pf); b.roots = dv + o_roots;
+  b.key_bytes = dv; b.key_off = reinterpret_cast<const uint32_t*>(dv + o_koff);
+  b.key_len = reinterpret_cast<const uint32_t*>(dv + o_klen);
+  b.root_from_proof = nullptr;
+  b.n_nodes = nn; b.n_proofs = np;
+  b.byte_base = 0; b.node_base = 0; b.key_base = 0; b.proof_base = 0;
+  CK(s.results.reserve(13 * np + 16));
+  CK(s.h_results.reserve(13 * np + 16));
+  uint8_t* res = s.results.as<uint8_t>();
+  const int rc = run_pipeline(ctx, d, b, s.digests, s.meta, s.order, s.bins, s.defer, s.dedup, res + 12 * np,
+                              reinterpret_cast<uint64_t*>(res), reinterpret_cast<uint32_t*>(res + 8 * np), st, false, &hs);
+  if (rc != MPTV_OK) return rc;
+  CK(launch_blob_map((uint32_t)np, s.f_flags.as<uint8_t>(), b.proof_first, b.node_off, b.node_len,
+                     reinterpret_cast<const uint64_t*>(dv + o_src), res + 12 * np, reinterpret_cast<uint64_t*>(res),
+                     reinterpret_cast<uint32_t*>(res + 8 * np), st));
+  CK(cudaMemcpyAsync(s.h_results.p, res, 13 * np, cudaMemcpyDeviceToHost, st));
+  if (!s.done) CK(cudaEventCreateWithFlags(&s.done, cudaEventBlockingSync | cudaEventDisableTiming));
+  CK(cudaEventRecord(s.done, st));
+  s.pend_p0 = cs; s.pend_np = np;
+  hs.chunks++; hs.device_chunks++; hs.nodes += nn; hs.node_bytes_supplied += nbytes;
+  hs.node_bytes_placed += nbytes; hs.d2h_bytes += 13 * np + 24; hs.launches += 3;
+  return MPTV_OK;
+}
+
+int borsh_device_drain(mptv_ctx* ctx, Slot& s, mptv_result* out) {
+  if (!s.pend_np) return MPTV_OK;
+  CK(cudaEventSynchronize(s.done));
+  const uint8_t* h = static_cast<const uint8_t*>(s.h_results.p);
+  memcpy(out->value_off + s.pend_p0, h, 8 * s.pend_np);
+  memcpy(out->value_len + s.pend_p0, h + 8 * s.pend_np, 4 * s.pend_np);
+  memcpy(out->status + s.pend_p0, h + 12 * s.pend_np, s.pend_np);
+  s.pend_np = 0;
+  return MPTV_OK;
+}
+
+int run_slice_borsh_device(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv_result* out, ChunkFeeder& feed, bool second) {
+  CK(cudaSetDevice(d.id));
+  const int slot0 = second ? kSlots : 0;  // the hybrid mode's second pipeline: its own slots, chunks from the back, twice the size
+  mptv_host_stats& hs = second ? d.hstat2 : d.hstat;
+  const uint64_t chunk_bytes = ctx->borsh_chunk_bytes;
+  const double t_begin = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  Slot* prev = nullptr;
+  size_t ci = 0;
+  int rc = MPTV_OK;
+  uint64_t cs = 0, ce = 0;
+  for (; rc == MPTV_OK; ci++) {
+    if (second) {
+      int got;
+      while ((got = feed.take_back(chunk_bytes, cs, ce)) < 0) std::this_thread::sleep_for(std::chrono::microseconds(100));
+      if (!got) break;
+    } else if (!feed.take_front(chunk_bytes, cs, ce)) break;
+    Slot& s = d.slot[slot0 + ci % kSlots];
+    rc = borsh_device_drain(ctx, s, out);  // the slot's chunk of three chunks ago
+    if (rc == MPTV_OK) rc = borsh_device_phase_a(ctx, hs, s, in, cs, ce);
+    if (rc == MPTV_OK && prev) rc = borsh_device_phase_b(ctx, d, hs, *prev, in);
+    prev = &s;
+  }
+  if (rc == MPTV_OK && prev) rc = borsh_device_phase_b(ctx, d, hs, *prev, in);
+  for (int k = 0; k < kSlots && rc == MPTV_OK; k++) rc = borsh_device_drain(ctx, d.slot[slot0 + k], out);
+  if (!second) hs.call_us += (uint64_t)((std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_begin) * 1e6);
+  return rc;
+}
+
 int run_slice_borsh(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv_result* out, uint64_t p0, uint64_t p1, int n_threads) {
-  WorkerPool pool(n_threads);
-  const int rc = run_slice_borsh_chunks(ctx, d, in, out, p0, p1, pool);
+  if (p1 <= p0) return MPTV_OK;
+  ChunkFeeder feed(in.blob_off, p0, p1, ctx->hybrid_device_pct);
+  int rc = MPTV_OK;
+  if (ctx->borsh_mode == 1 && in.pinned) {
+    rc = run_slice_borsh_device(ctx, d, in, out, feed, false);
+  } else if (ctx->borsh_mode == 2 && in.pinned) {
+    // hybrid: the host flattens (and aliases) chunks from the front of the range while the device flattens chunks from
+    // its back -- the first is bound by the cores and the host's memory, the second by PCIe, so together they use both
+    int rc_b = MPTV_OK;
+    std::thread second([&] { rc_b = run_slice_borsh_device(ctx, d, in, out, feed, true); });
+    {
+      WorkerPool pool(n_threads > 1 ? n_threads - 1 : 1);  // one core less: the second pipeline's thread issues CUDA calls too
+      rc = run_slice_borsh_chunks(ctx, d, in, out, feed, pool);
+    }
+    second.join();
+    if (rc == MPTV_OK) rc = rc_b;
+  } else {
+    WorkerPool pool(n_threads);
+    rc = run_slice_borsh_chunks(ctx, d, in, out, feed, pool);
+  }
   if (rc != MPTV_OK) quiesce(d);
   return rc;
 }
