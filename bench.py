@@ -35,6 +35,7 @@ over that batch.  The 3 GB node arena is far larger than L2 (126 MB), so every s
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -963,11 +964,17 @@ def main():
             line["configs"] = cfgs
         elif default_run and world > 1:
             # (a) ONE context on rank 0 drives all N devices; the other ranks wait
+            # (they wait on the rendezvous store, in a socket read: an NCCL barrier would park a spinning kernel on every
+            # other GPU, and this context's kernels would have to share those GPUs with it, time slice by time slice)
+            store = dist.distributed_c10d._get_default_store()
             if rank == 0:
                 try:
                     line["single_context"] = single_context(a, env, b)
                 except Exception as e:
                     line["single_context"] = dict(error=f"{type(e).__name__}: {e}")
+                store.set("mptv_single_context_done", "1")
+            else:
+                store.wait(["mptv_single_context_done"], datetime.timedelta(minutes=20))
             dist.barrier()
             ver.close()
             del b

@@ -744,7 +744,20 @@ __global__ void __launch_bounds__(256) k_trie_proof_emit(const TrieBatchDev in, 
     } else {
       const uint4* s = reinterpret_cast<const uint4*>(arena + w.off[node]);  // 16-byte aligned slots on both sides
       uint4* d = reinterpret_cast<uint4*>(out_bytes + o);
-      for (uint32_t i = lane; i < (len + 15u) / 16u; i += 32) d[i] = s[i];
+      for (uint32_t i = lane; i < (len + 15u) / 16u; i += 32) {
+        uint4 x = s[i];
+        const int r = (int)len - 16 * (int)i;  // the slot's padding in the arena is whatever an earlier call left: emit zeros
+        if (r < 16) {
+          uint32_t wd[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const int keep = r - 4 * c;
+            wd[c] &= keep >= 4 ? 0xffffffffu : (keep <= 0 ? 0u : ((1u << (8 * keep)) - 1u));
+          }
+          x = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        }
+        d[i] = x;
+      }
     }
     if (lane == 0) { out_off[k] = o; out_len[k] = len; }
     k++;
