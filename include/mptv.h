@@ -176,7 +176,8 @@ int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops
 /* options (name, value):
  *   "lanes_per_proof"  K2b lanes per proof: 0 = choose from nodes/proof, else 8, 16 or 32
  *   "chunk_bytes"      node bytes per pipeline chunk of the host-buffer entry (default 96 MiB)
- *   "borsh_chunk_bytes" borsh bytes per pipeline chunk of mptv_verify_borsh (default 32 MiB)
+ *   "borsh_chunk_bytes" borsh bytes per pipeline chunk of mptv_verify_borsh (default 32 MiB; the device pipeline of
+ *                      borsh_mode 1 / 2 takes chunks of twice this)
  *   "borsh_mode"       mptv_verify_borsh: 0 (default) = the HOST flattens: a pool of threads reads every blob once and
  *                      stages the nodes, byte-identical nodes of a chunk only once ("host_dedup") -- fewest PCIe bytes,
  *                      the right mode when one GPU has the host to itself; 1 = the DEVICE flattens: the blobs, which
@@ -184,7 +185,9 @@ int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops
  *                      touch nothing, the right mode when several GPUs share one host's memory system; 2 = BOTH at once
  *                      on each device: the host pipeline takes chunks from the front of the device's blob range, the
  *                      device pipeline from its back, until they meet -- one is bound by the cores, the other by PCIe
- *                      (1 and 2 fall back to 0 for pageable blobs)
+ *                      (1 and 2 fall back to 0 for pageable blobs).  Measured per million config-2 proofs (DESIGN.md
+ *                      sections 6, 7): one GPU 50 / 62 / 50-59 ms in mode 0 / 1 / 2; eight GPUs behind one host 25 M
+ *                      proofs/s in mode 0, 54 M in mode 1.  Results are identical in all three
  *   "hybrid_device_pct" borsh_mode 2: the share (1 ... 100 %, default 24) of the bytes the device pipeline may take; it
  *                      is bound by PCIe and unthrottled would starve the host pipeline's copies
  *   "pull_pinned"      mptv_verify_borsh, blobs in page-locked memory (mptv_alloc_pinned, cudaHostAlloc, cudaHostRegister):
