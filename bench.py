@@ -585,11 +585,14 @@ _REAL_STDOUT = 1
 
 
 def flatten_threads(a, world):
-    """host threads for the streamed borsh entry: this rank's share of the cores, one left for the submitter thread"""
+    """host threads for the streamed borsh entry: this rank's share of the cores, less two when there are at least
+    eight (the submitter thread and this process's other threads; the library's own default), else less one"""
     if a.threads:
         return a.threads
     cores = os.cpu_count() or 1
     share = max(1, cores // max(world, 1))
+    if share >= 8:
+        return share - 2
     return max(1, share - 1) if share > 2 else share
 
 

@@ -125,7 +125,11 @@ struct Rebuild {
 };
 
 constexpr int kSlots = 3;  // pipeline depth of the host-buffer path (H2D / kernels / D2H in flight)
-constexpr int kSlotsTotal = 2 * kSlots;  // the hybrid borsh mode runs a second pipeline (device flatten) on slots 3 .. 5
+// mptv_verify_borsh, host flatten: the producer may run this many chunks ahead of the device.  Three are enough when
+// the pipeline has the copy engine to itself; beside the hybrid mode's 64 MB blob copies (1.2 ms each, during which a
+// 14 MB staging copy waits) three slots stalled the producer for ~1 ms per device chunk.
+constexpr int kBorshSlots = 6;
+constexpr int kSlotsTotal = kBorshSlots + kSlots;  // the hybrid borsh mode runs a second pipeline (device flatten) on the last three
 
 struct Device {
   int id = 0;

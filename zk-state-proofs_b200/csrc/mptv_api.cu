@@ -726,8 +726,8 @@ struct BorshPipe {
   enum { kFree = 0, kFilled, kInFlight, kDone };
   std::mutex mu;
   std::condition_variable cv;
-  int state[kSlots];
-  ChunkLayout layout[kSlots];
+  int state[kBorshSlots];
+  ChunkLayout layout[kBorshSlots];
   const uint8_t* blobs_dev = nullptr;  // pull mode: the caller's blobs as the device sees them
   uint64_t produced = 0;  // chunks handed to the submitter
   bool producer_done = false;
@@ -793,7 +793,7 @@ void borsh_submitter(mptv_ctx* ctx, Device& d, BorshPipe& P) {
   if (rc != MPTV_OK) { fail(rc); return; }
   uint64_t c = 0;
   for (;; c++) {
-    const int k = (int)(c % kSlots);
+    const int k = (int)(c % kBorshSlots);
     {
       std::unique_lock<std::mutex> lk(P.mu);
       P.cv.wait(lk, [&] { return P.err != MPTV_OK || c < P.produced || P.producer_done; });
@@ -807,7 +807,7 @@ void borsh_submitter(mptv_ctx* ctx, Device& d, BorshPipe& P) {
       P.state[k] = BorshPipe::kInFlight;
     }
     if (c > 0) {  // wait for the chunk before: the device always has the newest chunk queued behind it
-      const int pk = (int)((c - 1) % kSlots);
+      const int pk = (int)((c - 1) % kBorshSlots);
       if (cudaEventSynchronize(d.slot[pk].done) != cudaSuccess) { fail(fail_cuda(ctx, cudaGetLastError(), "mptv_verify_borsh")); return; }
       std::lock_guard<std::mutex> g(P.mu);
       P.state[pk] = BorshPipe::kDone;
@@ -815,7 +815,7 @@ void borsh_submitter(mptv_ctx* ctx, Device& d, BorshPipe& P) {
     }
   }
   if (c > 0) {
-    const int pk = (int)((c - 1) % kSlots);
+    const int pk = (int)((c - 1) % kBorshSlots);
     if (cudaEventSynchronize(d.slot[pk].done) != cudaSuccess) { fail(fail_cuda(ctx, cudaGetLastError(), "mptv_verify_borsh")); return; }
     std::lock_guard<std::mutex> g(P.mu);
     P.state[pk] = BorshPipe::kDone;
@@ -841,7 +841,7 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
   }
   BorshPipe P;
   P.blobs_dev = blobs_dev;
-  for (int k = 0; k < kSlots; k++) P.state[k] = BorshPipe::kFree;
+  for (int k = 0; k < kBorshSlots; k++) P.state[k] = BorshPipe::kFree;
   double t_wait = 0, t_map = 0, t_flat = 0, t_join = 0;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_begin = now();
@@ -851,12 +851,12 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
   size_t ci = 0;
   uint64_t cs = 0, ce = 0;
   for (; rc == MPTV_OK && feed.take_front(ctx->borsh_chunk_bytes, cs, ce); ci++) {  // as many blobs as fit borsh_chunk_bytes of input
-    const int k = (int)(ci % kSlots);
+    const int k = (int)(ci % kBorshSlots);
     Slot& s = d.slot[k];
     bool have_results = false;
     double t0 = now();
     {
-      // the slot's previous chunk (three chunks back) must be through the device before its blocks are reused
+      // the slot's previous chunk (kBorshSlots chunks back) must be through the device before its blocks are reused
       std::unique_lock<std::mutex> lk(P.mu);
       P.cv.wait(lk, [&] { return P.err != MPTV_OK || P.state[k] == BorshPipe::kFree || P.state[k] == BorshPipe::kDone; });
       if (P.err != MPTV_OK) { rc = P.err; break; }
@@ -906,7 +906,7 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
   d.hstat.map_us += (uint64_t)(t_map * 1e6); d.hstat.call_us += (uint64_t)((now() - t_begin) * 1e6);
   if (rc == MPTV_OK) rc = P.err;
   if (rc != MPTV_OK) return why ? fail_msg(ctx, rc, why) : rc;
-  for (int k = 0; k < kSlots; k++)
+  for (int k = 0; k < kBorshSlots; k++)
     if (P.state[k] == BorshPipe::kDone) map_results_borsh(d.slot[k], out, pool);
   return MPTV_OK;
 }
@@ -1008,7 +1008,7 @@ int borsh_device_drain(mptv_ctx* ctx, Slot& s, mptv_result* out) {
 
 int run_slice_borsh_device(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv_result* out, ChunkFeeder& feed, bool second) {
   CK(cudaSetDevice(d.id));
-  const int slot0 = second ? kSlots : 0;  // the hybrid mode's second pipeline: its own slots, chunks from the back
+  const int slot0 = second ? kBorshSlots : 0;  // the hybrid mode's second pipeline: its own slots, chunks from the back
   mptv_host_stats& hs = second ? d.hstat2 : d.hstat;
   // Chunks of twice borsh_chunk_bytes: there is no host stage whose head a small chunk would shorten, and this thread's
   // ~25 CUDA calls and two event waits per chunk (~0.3 ms) must stay well below the chunk's copy time or the copy
@@ -1068,11 +1068,13 @@ int verify_borsh_run(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_o
   if (!blobs || !blob_off || !out->status || !out->value_off || !out->value_len) return MPTV_ERR_ARG;
   for (uint64_t i = 0; i < n; i++)
     if (blob_off[i + 1] < blob_off[i]) return MPTV_ERR_ARG;  // the chunking below searches the offsets
-  // all cores but one per device: the submitter thread of each device needs a share of a core for its CUDA calls
+  // all cores but two per device: the submitter thread of each device needs a share of a core for its CUDA calls, and
+  // the pool's barriers cost more than a core's worth of work as soon as one of its threads is descheduled (16-core
+  // box, 1 M config-2 proofs: 48.9 ms with 15 threads, 46.0 ms with 14)
   if (n_threads <= 0) {
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const unsigned nd = (unsigned)ctx->dev.size();
-    n_threads = (int)std::max(1u, std::min(32u * nd, hw > 2 * nd ? hw - nd : hw));
+    n_threads = (int)std::max(1u, std::min(32u * nd, hw >= 8 * nd ? hw - 2 * nd : (hw > 2 * nd ? hw - nd : hw)));
   }
   // page-locked input?  (mptv_alloc_pinned / cudaHostAlloc / cudaHostRegister: first and last byte must both be)
   bool pinned = false;
