@@ -168,7 +168,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -273,7 +273,7 @@ def run_single(a, env):
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.25)
+    keep_busy(lambda: ver.verify_batch(b))
     n_calls = max(a.steps, 1) * 200
     ver.host_stats(reset=True)
     t_begin = time.time()
@@ -430,6 +430,16 @@ except Exception:
     pass
 
 
+def keep_busy(fn, seconds=0.25):
+    """untimed extra warm-up while the clock sampler starts: the GPU must not sit idle right before the timed region
+    (an idle quarter of a second lets the clocks drop, and the first timed steps then run on the ramp)"""
+    import torch
+    t0 = time.time()
+    while time.time() - t0 < seconds:
+        fn()
+        torch.cuda.synchronize()
+
+
 def dist_setup():
     import torch
     import torch.distributed as dist
@@ -499,7 +509,7 @@ def run_rebuild(a, env):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.25)
+    keep_busy(step)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin = time.time()
@@ -768,7 +778,7 @@ def run_verify(a, env, want_e2e=True, want_cpu=True):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.25)
+    keep_busy(step)
     # ---- timed region: exactly K steps
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
