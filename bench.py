@@ -647,9 +647,11 @@ def e2e_from_borsh(a, ver, b, env, dev, st, voff, vlen, steps):
     torch.cuda.synchronize()
     ver.host_stats(reset=True)
     t0 = time.perf_counter()
+    marks = [t0]
     for _ in range(steps):
         bst, bvoff, bvlen = ver.verify_borsh(blobs, boff, threads=th)
-    dt = reduce_max((time.perf_counter() - t0) / steps, world, dev)
+        marks.append(time.perf_counter())
+    dt = reduce_max((marks[-1] - t0) / steps, world, dev)
     hs = ver.host_stats(reset=True)
     assert (bst == st).all() and (bvlen == vlen).all(), "borsh stream and device entry disagree"
     for i in np.nonzero(bst == 0)[0][:2000]:
@@ -673,6 +675,7 @@ def e2e_from_borsh(a, ver, b, env, dev, st, voff, vlen, steps):
     dram_all = reduce_sum([dram], world, dev)[0]
     return dict(
         value=all_proofs / dt, unit=UNIT, ms_per_step=dt * 1e3, entry="mptv_verify_borsh",
+        step_ms_rank0=[round((y - x) * 1e3, 2) for x, y in zip(marks, marks[1:])],
         host_memory=("pageable blobs, page-locked staging inside the library" if a.pageable else "page-locked blobs"),
         borsh_mode={0: "0: the host flattens (one pass, byte-identical nodes of a chunk aliased), staging copied by the DMA engine",
                     1: "1: the blobs cross PCIe as they are and the device flattens them (borsh_kernels.cu): several ranks share one "

@@ -1,7 +1,7 @@
 """Large differential fuzz of the CUDA path against the C restatement (which is itself fuzzed against the reference
 ELF by oracle/fuzz_vs_ref.py): every fuzz family of oracle/fuzzgen.py incl. the deep inline nests, all walk
-configurations, the streamed borsh entry with transfer de-duplication, and the one-launch latency path on random
-small groups.
+configurations, the streamed borsh entry with transfer de-duplication, its device-flatten and hybrid modes on
+page-locked blobs, and the one-launch latency path on random small groups.
     python tools/fuzz_gpu_vs_oracle.py [n_seeds] [first_seed]"""
 import os
 import sys
@@ -60,6 +60,23 @@ for seed in range(first, first + n_seeds):
     bad += len(diff)
     for i in diff[:5]:
         print("MISMATCH borsh stream", seed, cases[i]["tag"], int(st[i]), int(ost[i]))
+    # the same blobs in page-locked memory, flattened on the device (borsh_mode 1) and by both pipelines at once (2):
+    # verdicts, value offsets and lengths must equal the host-flatten mode's exactly
+    import torch
+    pin = torch.empty(len(buf) + 64, dtype=torch.uint8, pin_memory=True)
+    lead = seed % 16  # any alignment of the blob image
+    pbuf = pin.numpy()[lead:lead + len(buf)]
+    pbuf[:] = buf
+    for mode, chunk in ((1, 1 << 19), (2, 1 << 19), (1, 32 << 20)):
+        ver.set_option("borsh_mode", mode)
+        ver.set_option("borsh_chunk_bytes", chunk)
+        st1, voff1, vlen1 = ver.verify_borsh(pbuf, boff)
+        d1 = np.nonzero((st1 != st) | (voff1 != voff) | (vlen1 != vlen))[0]
+        bad += len(d1)
+        for i in d1[:5]:
+            print("MISMATCH borsh mode", mode, seed, cases[i]["tag"], int(st1[i]), int(st[i]))
+    ver.set_option("borsh_mode", 0)
+    ver.set_option("borsh_chunk_bytes", 32 << 20)
     # the one-launch latency path: random groups of 1 ... 32 proofs per call
     rng = random.Random(seed)
     for _ in range(1500):
@@ -76,5 +93,5 @@ for seed in range(first, first + n_seeds):
     total += len(cases)
     hist.update(ost.tolist())
     print(f"seed {seed}: {len(cases)} cases x {len(modes)} modes, cumulative mismatches {bad}, {time.time() - t0:.0f} s", flush=True)
-print(f"TOTAL {total} cases x ({len(modes)} walk configurations + borsh stream with aliasing) + 1500 latency-path groups per seed: {bad} mismatches; "
+print(f"TOTAL {total} cases x ({len(modes)} walk configurations + borsh stream with aliasing + device-flatten and hybrid borsh modes) + 1500 latency-path groups per seed: {bad} mismatches; "
       f"verdict histogram {dict(sorted(hist.items()))}")
