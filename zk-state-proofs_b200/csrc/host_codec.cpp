@@ -202,7 +202,7 @@ static int flatten_borsh_ex_run(const uint8_t* blobs, const uint64_t* blob_off, 
     if (!reuse) mptv_host_batch_free(hb);
     return rc;
   };
-  mptv::BorshChunkJob job = {blobs, blob_off, 0, n, alias ? &table : nullptr, false};
+  mptv::BorshChunkJob job = {blobs, blob_off, 0, n, alias ? &table : nullptr, false, /*key_off_16=*/true};
   mptv::ChunkLayout L;
   std::vector<uint8_t> bad;
   const int rc = mptv::flatten_borsh_chunk(pool, job, [&](size_t total, size_t) { return (uint8_t*)host_alloc(hb, 0, total); }, L,
@@ -221,7 +221,7 @@ static int flatten_borsh_ex_run(const uint8_t* blobs, const uint64_t* blob_off, 
   uint64_t o = 0;
   for (uint64_t i = 0; i < n; i++) {
     key_off[i] = (uint32_t)o;
-    if (klen[i]) memcpy(key_bytes + o, block + koff[i], klen[i]);
+    if (klen[i]) memcpy(key_bytes + o, block + ((uint64_t)koff[i] << 4), klen[i]);
     o += klen[i];
     hb->bad_root[i] = bad[i];
   }

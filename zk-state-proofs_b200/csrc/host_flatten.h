@@ -135,6 +135,9 @@ struct BorshChunkJob {
   uint64_t cs, ce;
   DedupTable* table;  // null = no de-duplication
   bool pull = false;  // write gather records instead of copying bytes (the caller's blobs are device-accessible)
+  // key offsets in 16-byte units (keys start on 16-byte boundaries): a block of up to 64 GiB instead of 4 GiB.  The
+  // device reads byte offsets, so only mptv_flatten_borsh_ex, which re-packs the keys anyway, asks for this.
+  bool key_off_16 = false;
 };
 // what the device's gather kernel executes: len bytes at blobs + src -> block + 16 * dst16, padded with zeros to 16
 struct GatherRec { uint64_t src; uint32_t dst16; uint32_t len; };
@@ -178,11 +181,11 @@ struct RegionWriter {
     placed += padded;
     return o;
   }
-  inline uint32_t put_key(const uint8_t* src, uint32_t len) {
+  inline size_t put_key(const uint8_t* src, uint32_t len) {
     const size_t o = at;
     if (len) put_bytes(base + o, src, len);
     at += up16z(len);
-    return (uint32_t)o;
+    return o;
   }
   // Every byte is written once and next read by the DMA engine, so it should go out with non-temporal stores (no
   // read-for-ownership of the staging lines).  Without a table the node is streamed directly.  With a table that
@@ -287,7 +290,8 @@ int flatten_borsh_chunk(WorkerPool& pool, const BorshChunkJob& job, GetBlock get
         for (int k = 0; k < T; k++) { L.region_begin[k] = o; o += up64z(tot[k].bound) + 64; }
         L.total = o + 64;
         if (!job.pull) L.host_total = L.total;
-        if (L.total > 0xfffffff00ull) err.store(MPTV_ERR_ARG);  // offsets are kept in 16-byte units in 32 bits
+        // node offsets are kept in 16-byte units in 32 bits (the table), key offsets as 32-bit bytes unless key_off_16
+        if (L.total > (job.key_off_16 ? 0xfffffff00ull : 0xffffff00ull)) err.store(MPTV_ERR_ARG);
         else {
           block = get_block(L.host_total, L.total);
           if (!block) err.store(MPTV_ERR_NOMEM);
@@ -372,7 +376,8 @@ int flatten_borsh_chunk(WorkerPool& pool, const BorshChunkJob& job, GetBlock get
         if (end - p < 4 || (uint64_t)(end - p - 4) < (kl = rd_u32(p))) ok = false;
       }
       if (ok) {
-        key_off[i] = w.put_key(p + 4, kl);
+        const size_t ko = w.put_key(p + 4, kl);
+        key_off[i] = job.key_off_16 ? (uint32_t)(ko >> 4) : (uint32_t)ko;
         key_len[i] = kl;
         p += 4 + kl;
         if (p != end) ok = false;  // borsh::from_slice rejects trailing bytes

@@ -959,7 +959,7 @@ int borsh_device_phase_b(mptv_ctx* ctx, Device& d, mptv_host_stats& hs, Slot& s,
   auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 63) & ~(size_t)63; return at; };
   const size_t o_off = take(8 * nn), o_len = take(4 * nn), o_src = take(8 * nn), o_pf = take(4 * (np + 1)), o_roots = take(32 * np),
                o_koff = take(4 * np), o_klen = take(4 * np), o_recs = take(16 * (nn + np)), o_arena = take(nbytes + 64);
-  if (o > 0xfffffff00ull) return MPTV_ERR_ARG;  // key offsets are 32-bit offsets into the pack
+  if (o > 0xffffff00ull) return fail_msg(ctx, MPTV_ERR_ARG, "mptv_verify_borsh: one blob needs more than 4 GiB");  // key offsets are 32-bit byte offsets into the pack
   CK(s.in_pack.reserve(o + 16));
   uint8_t* dv = s.in_pack.as<uint8_t>();
   CK(launch_blob_emit(s.f_img.as<uint8_t>(), s.f_off.as<uint64_t>(), (uint32_t)np, (uint32_t)nn, s.f_node_first.as<uint32_t>(),
