@@ -660,7 +660,7 @@ def e2e_from_borsh(a, ver, b, env, dev, st, voff, vlen, steps):
     read_gbs, copy_gbs = z.host_bw_probe(th, 128 << 20)
     h2d_gbs = h2d_peak_gbs(dev, world)
     flat_s = min(z.borsh_flatten_probe(blobs, boff, threads=th, chunk_bytes=32 << 20)[0] for _ in range(3))
-    ver.set_option("borsh_mode", 0)
+    ver.set_option("borsh_mode", -1)
     all_proofs, blob_bytes, h2d, d2h, read_sum, copy_sum, h2d_sum, launches = reduce_sum(
         [b.n_proofs, len(blobs), hs.h2d_bytes / steps, hs.d2h_bytes / steps, read_gbs, copy_gbs, h2d_gbs, hs.launches / steps], world, dev)
     placed = hs.node_bytes_placed / steps
@@ -888,7 +888,7 @@ def single_context(a, env, b):
             call = lambda: ver.verify_batch(b)
         else:
             blobs, boff = gen.batch_to_borsh(b, pinned=not a.pageable)
-            ver.set_option("borsh_mode", a.borsh_mode if a.borsh_mode >= 0 else (0 if a.pageable else 1))
+            ver.set_option("borsh_mode", a.borsh_mode)  # -1: the library's own choice (device flatten for page-locked blobs on several devices)
             call = lambda: ver.verify_borsh(blobs, boff, threads=a.threads)
         for _ in range(2):
             call()

@@ -178,7 +178,8 @@ int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops
  *   "chunk_bytes"      node bytes per pipeline chunk of the host-buffer entry (default 96 MiB)
  *   "borsh_chunk_bytes" borsh bytes per pipeline chunk of mptv_verify_borsh (default 32 MiB; the device pipeline of
  *                      borsh_mode 1 / 2 takes chunks of twice this)
- *   "borsh_mode"       mptv_verify_borsh: 0 (default) = the HOST flattens: a pool of threads reads every blob once and
+ *   "borsh_mode"       mptv_verify_borsh: -1 (default) = 0 when the context has one device, 1 when it drives several;
+ *                      0 = the HOST flattens: a pool of threads reads every blob once and
  *                      stages the nodes, byte-identical nodes of a chunk only once ("host_dedup") -- fewest PCIe bytes,
  *                      the right mode when one GPU has the host to itself; 1 = the DEVICE flattens: the blobs, which
  *                      must be in page-locked memory, cross PCIe as they are and kernels lay the nodes out -- the cores

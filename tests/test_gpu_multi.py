@@ -60,6 +60,17 @@ def test_one_context_two_devices_matches_one_device(verifier):
     ref = verifier.verify_batch(acc)
     for i in range(0, acc.n_proofs, 97):
         assert blobs[int(o2[i]):int(o2[i]) + int(l2[i])].tobytes() == acc.value(int(ref[1][i]), int(ref[2][i]))
+    # the same blobs page-locked: a context with several devices flattens them on the devices by itself (borsh_mode -1)
+    pblobs, poff = gen.batch_to_borsh(acc, pinned=True)
+    two.host_stats(reset=True)
+    s3, o3, l3 = two.verify_borsh(pblobs, poff)
+    hs = two.host_stats()
+    assert hs.device_chunks == hs.chunks > 1 and (s3 == s1).all() and (o3 == o1).all() and (l3 == l1).all()
+    two.set_option("borsh_mode", 0)
+    two.host_stats(reset=True)
+    s4, o4, l4 = two.verify_borsh(pblobs, poff)
+    assert two.host_stats().device_chunks == 0 and (s4 == s1).all() and (o4 == o1).all() and (l4 == l1).all()
+    two.set_option("borsh_mode", -1)
     # digest_keccak over an arena, cut into index ranges over the two devices (mptv_keccak256_batch), and the
     # hashed-keys entry on two devices
     d1 = verifier.keccak256_batch(acc.node_bytes, acc.node_off, acc.node_len)

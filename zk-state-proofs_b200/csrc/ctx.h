@@ -165,8 +165,8 @@ struct mptv_ctx {
   int binning = 1;
   int fused_classify = 1;  // K1 also classifies plain branches / leaves (K2a fast path)
   int dedup_nodes = 0;     // hash each DISTINCT node once (secondary mode, reported separately)
-  int borsh_mode = 0;      // mptv_verify_borsh: 0 = the host flattens (and aliases), 1 = the device flattens page-locked blobs,
-                           // 2 = both at once on one device, chunks handed out from the two ends of the input
+  int borsh_mode = -1;     // mptv_verify_borsh: -1 = automatic (0 on one device, 1 on several), 0 = the host flattens (and aliases),
+                           // 1 = the device flattens page-locked blobs, 2 = both at once, chunks handed out from the two ends
   int hybrid_device_pct = 24;  // borsh_mode 2: share of a device's blob bytes its device-flatten pipeline may take
   int pull_pinned = 0;     // streamed borsh entry, page-locked blobs: the device gathers the placed node bytes itself (measured slower: off)
   int host_dedup = 1;      // streamed borsh entry: alias byte-identical nodes of a chunk instead of copying them again

@@ -221,7 +221,7 @@ int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
     if (value < (1 << 12) || value > (1ll << 31)) return MPTV_ERR_ARG;
     ctx->borsh_chunk_bytes = (uint64_t)value;
   } else if (!strcmp(name, "borsh_mode")) {
-    if (value < 0 || value > 2) return MPTV_ERR_ARG;
+    if (value < -1 || value > 2) return MPTV_ERR_ARG;
     ctx->borsh_mode = (int)value;
   } else if (!strcmp(name, "hybrid_device_pct")) {
     if (value < 1 || value > 100) return MPTV_ERR_ARG;
@@ -1041,9 +1041,12 @@ int run_slice_borsh(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv_result
   if (p1 <= p0) return MPTV_OK;
   ChunkFeeder feed(in.blob_off, p0, p1, ctx->hybrid_device_pct);
   int rc = MPTV_OK;
-  if (ctx->borsh_mode == 1 && in.pinned) {
+  // automatic: one device has the host's cores and memory to itself and the host flatten moves the fewest PCIe bytes;
+  // several devices of one context share them, and the device flatten costs the host one DMA read per byte
+  const int mode = ctx->borsh_mode >= 0 ? ctx->borsh_mode : (ctx->dev.size() > 1 ? 1 : 0);
+  if (mode == 1 && in.pinned) {
     rc = run_slice_borsh_device(ctx, d, in, out, feed, false);
-  } else if (ctx->borsh_mode == 2 && in.pinned) {
+  } else if (mode == 2 && in.pinned) {
     // hybrid: the host flattens (and aliases) chunks from the front of the range while the device flattens chunks from
     // its back -- the first is bound by the cores and the host's memory, the second by PCIe, so together they use both
     int rc_b = MPTV_OK;
