@@ -133,6 +133,24 @@ int mptv_verify_batch_hashed_keys(mptv_ctx* ctx, const mptv_batch* in, const uin
 int mptv_verify_borsh(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads,
                       mptv_result* out);
 
+/* The risc0 storage guest over a batch of its own inputs (circuits/risc0-storage-proof/.../storage-circuit/src/main.rs:6-31):
+ * blob i holds borsh(StorageProofInput) (crypto-ops/src/types.rs:11-19).  For every input the account proof is verified
+ * under address_keccak against root_hash, then storage_proofs zipped with storage_keys (the shorter list decides,
+ * main.rs:18-21), each under keccak256(storage key) -- hashed on the device -- against the storage_root of the verified
+ * account leaf.  Same pipeline as mptv_verify_borsh (host flatten, byte-identical nodes of a chunk cross PCIe once).
+ *   proof_first[n_inputs + 1]  out: input i owns results [proof_first[i], proof_first[i+1]): its account proof first,
+ *                              then its storage proofs in order.  Written by the first pass, before anything is verified.
+ *   results_cap                entries the arrays of `out` hold.  Fewer than proof_first[n_inputs] (e.g. 0, to ask):
+ *                              MPTV_ERR_NOMEM, with proof_first filled in.
+ *   input_status[n_inputs]     out, may be NULL: MPTV_ST_OK (the guest commits the storage values), else the status of the
+ *                              first proof that fails in the guest's order; an account leaf that is not
+ *                              rlp([nonce, balance, storage_root, code_hash]) (decode_exact(..).unwrap(), main.rs:15) gives
+ *                              MPTV_ST_DEP_FAILED, also for an input without storage proofs.
+ * out->value_off[p] is an offset into `blobs`.  root_hash.len() != 32 gives the account proof MPTV_ST_BAD_ROOT_LEN and the
+ * storage proofs MPTV_ST_DEP_FAILED; a malformed blob fails the whole call with MPTV_ERR_ARG. */
+int mptv_verify_storage_borsh(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_off, uint64_t n_inputs, int n_threads,
+                              uint64_t* proof_first, uint8_t* input_status, uint64_t results_cap, mptv_result* out);
+
 /* What the host-fed entries (mptv_verify_batch, mptv_verify_borsh) moved since the context was created or the
  * counters were last reset: summed over the context's devices. */
 typedef struct mptv_host_stats {
@@ -319,6 +337,14 @@ typedef struct mptv_flatten_info {
 } mptv_flatten_info;
 int mptv_flatten_borsh_ex(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, int pinned,
                           unsigned flags, mptv_host_batch** out, mptv_flatten_info* info);
+/* The same for borsh(StorageProofInput) blobs (crypto-ops/src/types.rs:11-19): each input becomes its account proof
+ * (key = address_keccak, root = root_hash) followed by min(storage_proofs.len(), storage_keys.len()) storage proofs
+ * (key = the RAW storage key, root_from_proof = the account proof), i.e. the batch mptv_verify_batch_hashed_keys takes
+ * together with *hash_key (one flag per proof, owned by the handle): the host half of mptv_verify_storage_borsh.
+ * proof_first [n_inputs + 1] as there. */
+int mptv_flatten_storage_borsh(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n_inputs, int n_threads, int pinned,
+                               unsigned flags, mptv_host_batch** out, mptv_flatten_info* info, uint64_t* proof_first,
+                               const uint8_t** hash_key);
 /* The host stage of mptv_verify_borsh alone (no device needed): the same chunk loop and builder into ordinary memory.
  * Timed by the caller, it is the ceiling of the streamed entry on this host with these threads. */
 int mptv_borsh_flatten_probe(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, uint64_t chunk_bytes,

@@ -189,3 +189,40 @@ def test_flatten_ex_rejects_what_borsh_rejects_and_probe_runs():
     assert info.n_nodes == 1000 and info.nodes_aliased > 900 and dt > 0
     b, info = z.flatten_borsh_ex([])
     assert b.n_proofs == 0
+
+
+def test_storage_borsh_flattener_matches_the_structs(oracle):
+    """mptv_flatten_storage_borsh (the host half of mptv_verify_storage_borsh): every StorageProofInput becomes its
+    account proof + min(#storage_proofs, #storage_keys) storage proofs with raw keys, hash flags and root_from_proof
+    (crypto-ops/src/types.rs:11-19, storage-circuit/src/main.rs:10-27), with and without aliasing, 1 and 3 threads"""
+    import zk_state_proofs_b200 as z
+    from tests.test_gpu_storage_borsh import _inputs
+    inputs = _inputs(oracle, 11, 300)
+    blobs = [i.to_borsh() for i in inputs]
+    for alias in (False, True):
+        for th in (1, 3):
+            b, hk, pf, info = z.flatten_storage_borsh(blobs, threads=th, alias_duplicates=alias)
+            q = 0
+            for i, inp in enumerate(inputs):
+                used = min(len(inp.storage_proofs), len(inp.storage_keys))
+                assert int(pf[i]) == q and int(pf[i + 1]) == q + 1 + used
+                items = [(inp.account_proof, inp.address_keccak, -1, 0)] + \
+                        [(inp.storage_proofs[j], inp.storage_keys[j], q, 1) for j in range(used)]
+                for j, (pr, key, r, h) in enumerate(items):
+                    p = q + j
+                    f, e = int(b.proof_first[p]), int(b.proof_first[p + 1])
+                    assert e - f == len(pr)
+                    for k, nd in enumerate(pr):
+                        no, nl = int(b.node_off[f + k]), int(b.node_len[f + k])
+                        assert bytes(b.node_bytes[no:no + nl]) == nd
+                    assert bytes(b.key_bytes[int(b.key_off[p]):int(b.key_off[p + 1])]) == bytes(key)
+                    assert int(b.root_from_proof[p]) == r and int(hk[p]) == h
+                    assert bytes(b.roots[32 * p:32 * p + 32]) == (inp.root_hash if (j == 0 and len(inp.root_hash) == 32) else bytes(32))
+                assert bool(b.bad_root_len is not None and b.bad_root_len[q]) == (len(inp.root_hash) != 32)
+                q += 1 + used
+            assert (info.nodes_aliased > 0) == alias and info.n_nodes == sum(len(p) for p in [i.account_proof for i in inputs]) + \
+                sum(len(pr) for i in inputs for pr in i.storage_proofs[:min(len(i.storage_proofs), len(i.storage_keys))])
+    good = blobs[0]
+    for bad in (good[:-1], good + b"\0", good[:3], b"", b"\xff\xff\xff\xff" + good[4:], good[:-33]):
+        with pytest.raises(ValueError):
+            z.flatten_storage_borsh(blobs[:5] + [bad] + blobs[5:])

@@ -331,6 +331,32 @@ def flatten_borsh_ex(blobs, blob_off=None, threads: int = 0, pinned: bool = Fals
     return b, info
 
 
+def flatten_storage_borsh(blobs, blob_off=None, threads: int = 0, pinned: bool = False, alias_duplicates: bool = False):
+    """mptv_flatten_storage_borsh: borsh(StorageProofInput) blobs -> (Batch with root_from_proof, hash_key u8[n_proofs],
+    proof_first u64[n_inputs + 1], FlattenInfo): what Verifier.verify_batch_hashed_keys takes."""
+    L = load_library()
+    buf, off = _blob_arrays(blobs, blob_off)
+    n = len(off) - 1
+    h = ctypes.c_void_p()
+    info = FlattenInfo()
+    pf = np.zeros(n + 1, np.uint64)
+    hk = ctypes.c_void_p()
+    L.mptv_flatten_storage_borsh.restype = ctypes.c_int32
+    L.mptv_flatten_storage_borsh.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_uint,
+                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    rc = L.mptv_flatten_storage_borsh(buf.ctypes.data, off.ctypes.data, n, threads, 1 if pinned else 0,
+                                      FLATTEN_ALIAS_DUPLICATES if alias_duplicates else 0, ctypes.byref(h), ctypes.byref(info),
+                                      pf.ctypes.data, ctypes.byref(hk))
+    if rc != 0:
+        raise ValueError(f"mptv_flatten_storage_borsh: {L.mptv_strerror(rc).decode()} (malformed borsh StorageProofInput?)")
+    npr = int(pf[n])
+    b = batch_from_handle(L, h, npr)
+    v = ctypes.cast(L.mptv_host_batch_view(h), ctypes.POINTER(_CBatch)).contents
+    b.root_from_proof = _view(v.root_from_proof, npr, np.uint32).view(np.int32)
+    b._owner = _HostBatchOwner(L, h)
+    return b, _view(hk.value, npr, np.uint8).copy(), pf, info
+
+
 def borsh_flatten_probe(blobs, blob_off=None, threads: int = 0, chunk_bytes: int = 32 << 20, alias_duplicates: bool = True):
     """mptv_borsh_flatten_probe: the host stage of verify_borsh alone -> (seconds, FlattenInfo)"""
     import time
@@ -551,6 +577,8 @@ def load_library():
     L.mptv_verify_batch.argtypes = [vp, ctypes.POINTER(_CBatch), ctypes.POINTER(_CResult)]
     L.mptv_verify_borsh.restype = i32
     L.mptv_verify_borsh.argtypes = [vp, vp, vp, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(_CResult)]
+    L.mptv_verify_storage_borsh.restype = i32
+    L.mptv_verify_storage_borsh.argtypes = [vp, vp, vp, ctypes.c_uint64, ctypes.c_int, vp, vp, ctypes.c_uint64, ctypes.POINTER(_CResult)]
     L.mptv_verify_batch_hashed_keys.restype = i32
     L.mptv_verify_batch_hashed_keys.argtypes = [vp, ctypes.POINTER(_CBatch), vp, ctypes.POINTER(_CResult)]
     L.mptv_verify_batch_device.restype = i32
@@ -699,6 +727,46 @@ class Verifier:
         self._check(self.lib.mptv_verify_borsh(self.ctx, buf.ctypes.data, off.ctypes.data, n, threads, ctypes.byref(cr)),
                     "mptv_verify_borsh")
         return status, voff, vlen
+
+    def verify_storage_borsh(self, blobs, blob_off=None, threads: int = 0, n_proofs: Optional[int] = None):
+        """mptv_verify_storage_borsh: borsh(StorageProofInput) blobs in (the storage guest's own input,
+        storage-circuit/src/main.rs:6-9), the guest's flow for every input out.  Returns
+        (proof_first u64[n + 1], input_status u8[n], status, value_off, value_len): input i owns the results
+        [proof_first[i], proof_first[i + 1]) -- its account proof, then its storage proofs; value_off indexes the
+        CONCATENATED blobs.  n_proofs: the total, when the caller knows it (saves the sizing call)."""
+        buf, off = _blob_arrays(blobs, blob_off)
+        n = len(off) - 1
+        pf = np.zeros(max(n, 0) + 1, np.uint64)
+        ist = np.zeros(max(n, 0), np.uint8)
+        if n <= 0:
+            return pf, ist, np.zeros(0, np.uint8), np.zeros(0, np.uint64), np.zeros(0, np.uint32)
+        args = (self.ctx, buf.ctypes.data, off.ctypes.data, n, threads, _ptr(pf), _ptr(ist))
+        if n_proofs is None:
+            rc = self.lib.mptv_verify_storage_borsh(*args, 0, None)  # first pass only: how many proofs the guest verifies
+            if rc != -4:  # MPTV_ERR_NOMEM: proof_first now holds the layout
+                self._check(rc, "mptv_verify_storage_borsh")
+            n_proofs = int(pf[n])
+        status = np.zeros(n_proofs, np.uint8)
+        voff = np.zeros(n_proofs, np.uint64)
+        vlen = np.zeros(n_proofs, np.uint32)
+        cr = _CResult(_ptr(status), _ptr(voff), _ptr(vlen))
+        self._check(self.lib.mptv_verify_storage_borsh(*args, n_proofs, ctypes.byref(cr)), "mptv_verify_storage_borsh")
+        return pf, ist, status, voff, vlen
+
+    def verify_storage_proof_inputs_borsh(self, inputs: Sequence[StorageProofInput]):
+        """verify_storage_proof_inputs through the wire format: the inputs are serialised as the prover would write them
+        and streamed through mptv_verify_storage_borsh.  -> per input: the list of storage values, or the VerifyPanic
+        the guest would have died with."""
+        blobs = [inp.to_borsh() for inp in inputs]
+        buf, off = _blob_arrays(blobs, None)
+        pf, ist, status, voff, vlen = self.verify_storage_borsh(buf, off)
+        out = []
+        for i in range(len(blobs)):
+            if ist[i]:
+                out.append(VerifyPanic(int(ist[i])))
+            else:
+                out.append([buf[int(voff[q]):int(voff[q]) + int(vlen[q])].tobytes() for q in range(int(pf[i]) + 1, int(pf[i + 1]))])
+        return out
 
     # -- device-resident entry: pointers are raw device addresses (ints), e.g. torch tensors' data_ptr()
     def verify_batch_device(self, dev_index: int, ptrs: dict, n_nodes: int, n_proofs: int, out_ptrs: dict,

@@ -179,9 +179,13 @@ int mptv_flatten_borsh(const uint8_t* blobs, const uint64_t* blob_off, uint64_t 
 
 // Single pass + optional aliasing of byte-identical nodes (host_flatten.h).  Block 0 of the handle holds the index
 // arrays and the workers' byte regions; the keys are re-packed into the public prefix-array form (32 bytes a proof).
+// storage: the blobs are borsh(StorageProofInput); proof_first [n + 1] and *hash_key (one flag per proof, inside the
+// handle's block) are written as well, and the batch carries root_from_proof
 static int flatten_borsh_ex_run(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, int pinned,
-                                unsigned flags, mptv_host_batch** out, mptv_flatten_info* info) {
+                                unsigned flags, mptv_host_batch** out, mptv_flatten_info* info, bool storage = false,
+                                uint64_t* proof_first = nullptr, const uint8_t** hash_key = nullptr) {
   if (!out || (n && (!blobs || !blob_off))) return MPTV_ERR_ARG;
+  if (storage && (!proof_first || !hash_key)) return MPTV_ERR_ARG;
   if (flags & ~(unsigned)MPTV_FLATTEN_ALIAS_DUPLICATES) return MPTV_ERR_ARG;
   mptv_host_batch* reuse = *out;
   if (reuse && reuse->pinned != (pinned != 0)) return MPTV_ERR_ARG;
@@ -202,12 +206,25 @@ static int flatten_borsh_ex_run(const uint8_t* blobs, const uint64_t* blob_off, 
     if (!reuse) mptv_host_batch_free(hb);
     return rc;
   };
-  mptv::BorshChunkJob job = {blobs, blob_off, 0, n, alias ? &table : nullptr, false, /*key_off_16=*/true};
   mptv::ChunkLayout L;
   std::vector<uint8_t> bad;
-  const int rc = mptv::flatten_borsh_chunk(pool, job, [&](size_t total, size_t) { return (uint8_t*)host_alloc(hb, 0, total); }, L,
-                                           nullptr, &bad);
+  auto get_block = [&](size_t total, size_t) { return (uint8_t*)host_alloc(hb, 0, total); };
+  int rc;
+  uint64_t n_in = n;  // inputs; n becomes the number of proofs
+  if (storage) {
+    mptv::StorageIndex idx;
+    rc = mptv::skim_storage_inputs(pool, blobs, blob_off, n, idx);
+    if (rc != MPTV_OK) return fail(rc);
+    memcpy(proof_first, idx.proof_first.data(), 8 * (n + 1));
+    mptv::StorageChunkJob job = {blobs, blob_off, 0, n, alias ? &table : nullptr, &idx, /*key_off_16=*/true};
+    rc = mptv::flatten_storage_chunk(pool, job, get_block, L, nullptr, &bad);
+    n = idx.proof_first[n_in];
+  } else {
+    mptv::BorshChunkJob job = {blobs, blob_off, 0, n, alias ? &table : nullptr, false, /*key_off_16=*/true};
+    rc = mptv::flatten_borsh_chunk(pool, job, get_block, L, nullptr, &bad);
+  }
   if (rc != MPTV_OK) return fail(rc);
+  (void)n_in;
   uint8_t* block = (uint8_t*)hb->blocks[0];
   const uint32_t* koff = reinterpret_cast<const uint32_t*>(block + L.o_koff);
   const uint32_t* klen = reinterpret_cast<const uint32_t*>(block + L.o_klen);
@@ -234,6 +251,10 @@ static int flatten_borsh_ex_run(const uint8_t* blobs, const uint64_t* blob_off, 
   hb->view.proof_first = reinterpret_cast<const uint32_t*>(block + L.o_pf);
   hb->view.n_proofs = n; hb->view.roots = block + L.o_roots;
   hb->view.key_bytes = key_bytes; hb->view.key_off = key_off; hb->view.root_from_proof = nullptr;
+  if (storage) {
+    hb->view.root_from_proof = reinterpret_cast<const int32_t*>(block + L.o_rfp);
+    *hash_key = block + L.o_hk;
+  }
   if (info) {
     info->n_nodes = L.nn; info->nodes_aliased = L.nodes_aliased;
     info->node_bytes_supplied = L.node_bytes_supplied; info->node_bytes_placed = L.node_bytes_placed;
@@ -246,6 +267,16 @@ int mptv_flatten_borsh_ex(const uint8_t* blobs, const uint64_t* blob_off, uint64
                           unsigned flags, mptv_host_batch** out, mptv_flatten_info* info) {
   try {
     return flatten_borsh_ex_run(blobs, blob_off, n, n_threads, pinned, flags, out, info);
+  } catch (...) {
+    return MPTV_ERR_NOMEM;
+  }
+}
+
+int mptv_flatten_storage_borsh(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n_inputs, int n_threads, int pinned,
+                               unsigned flags, mptv_host_batch** out, mptv_flatten_info* info, uint64_t* proof_first,
+                               const uint8_t** hash_key) {
+  try {
+    return flatten_borsh_ex_run(blobs, blob_off, n_inputs, n_threads, pinned, flags, out, info, true, proof_first, hash_key);
   } catch (...) {
     return MPTV_ERR_NOMEM;
   }

@@ -22,6 +22,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <utility>
 #include <vector>
@@ -111,6 +112,12 @@ struct ChunkLayout {
   // node / key in [o_gather, o_gather + 16 n_gather); the host block ends at host_total, the byte regions exist on
   // the device only
   size_t o_gather = 0, n_gather = 0, host_total = 0;
+  // borsh(StorageProofInput) chunks (flatten_storage_chunk): the proofs form groups -- an account proof and the storage
+  // proofs that take their root from its verified leaf -- and the storage keys are hashed on the device:
+  // root_from_proof i32[np] (chunk-relative, -1 = none), hash_key u8[np]; device only: the key records the kernels read
+  // after k_prepare_keys (offset u32[np], length u32[np]) and the 32-byte hashed keys
+  bool groups = false;
+  size_t o_rfp = 0, o_hk = 0, o_hkoff = 0, o_hklen = 0, o_hashed = 0;
   std::vector<size_t> region_begin, region_used;  // per worker: its byte region and how much of it was written
   // statistics of the build
   uint64_t node_bytes_supplied = 0;  // sum of the padded lengths of all supplied nodes
@@ -398,6 +405,255 @@ int flatten_borsh_chunk(WorkerPool& pool, const BorshChunkJob& job, GetBlock get
   });
   if (err.load()) return err.load();
   reinterpret_cast<uint32_t*>(block + L.o_pf)[np] = (uint32_t)L.nn;
+  for (int t = 0; t < T; t++) {
+    L.region_used[t] = wr[t].at - L.region_begin[t];
+    L.node_bytes_supplied += wr[t].supplied; L.node_bytes_placed += wr[t].placed; L.nodes_aliased += wr[t].aliased;
+  }
+  return MPTV_OK;
+}
+
+// ------------------------------------------------------------------------------------------ borsh(StorageProofInput)
+// /root/reference/crypto-ops/src/types.rs:11-19: account_proof Vec<Vec<u8>>, storage_proofs Vec<Vec<Vec<u8>>>,
+// root_hash Vec<u8>, account_key Vec<u8>, storage_keys Vec<Vec<u8>>, address_keccak [u8; 32] -- the input of the risc0
+// storage guest (circuits/risc0-storage-proof/.../storage-circuit/src/main.rs:6-31), which verifies the account
+// proof under address_keccak and then zips storage_proofs with storage_keys (the shorter list decides, main.rs:18-21),
+// verifying each under keccak(key) against the account's storage_root.  account_key is never read by the guest.
+//
+// One input = 1 + min(#storage_proofs, #storage_keys) proofs.  The storage keys lie BEHIND the proofs in the blob, so
+// how many of the storage proofs count is only known at the end: a first pass over the length prefixes (one cache
+// line per node) indexes every input, and the streaming pass then places exactly the nodes that count.
+struct StorageIndex {
+  std::vector<uint64_t> proof_first, node_first;  // [n + 1] prefix sums over the inputs: the guest's proofs / their nodes
+  std::vector<uint32_t> root_at;                  // [n] where root_hash's length word sits inside blob i
+};
+
+// walks the length prefixes of one Vec<Vec<u8>> at p; false = does not fit [p, end)
+inline bool skim_vec_vec(const uint8_t*& p, const uint8_t* end, uint64_t& n_out, bool nodes) {
+  if (end - p < 4) return false;
+  const uint64_t n = rd_u32(p);
+  p += 4;
+  if (n > (uint64_t)(end - p) / 4) return false;  // every element costs at least its length word
+  for (uint64_t j = 0; j < n; j++) {
+    if (end - p < 4) return false;
+    const uint32_t len = rd_u32(p);
+    if ((uint64_t)(end - p - 4) < len || (nodes && len > kMaxNodeLen)) return false;
+    p += 4 + len;
+  }
+  n_out = n;
+  return true;
+}
+
+// what borsh::from_slice::<StorageProofInput> accepts; proofs / nodes = what the guest goes on to verify
+inline bool skim_storage_input(const uint8_t* p, const uint8_t* end, uint64_t& proofs, uint64_t& nodes, uint32_t& root_at,
+                               std::vector<uint64_t>& cum /* scratch */) {
+  const uint8_t* start = p;
+  if ((uint64_t)(end - p) > 0xfffffff0ull) return false;  // positions inside a blob are kept in 32 bits
+  uint64_t n_acc = 0, m = 0, k = 0, x = 0;
+  if (!skim_vec_vec(p, end, n_acc, true)) return false;
+  if (end - p < 4) return false;
+  m = rd_u32(p);
+  p += 4;
+  if (m > (uint64_t)(end - p) / 4) return false;
+  cum.clear();
+  cum.push_back(0);
+  for (uint64_t j = 0; j < m; j++) {
+    if (!skim_vec_vec(p, end, x, true)) return false;
+    cum.push_back(cum.back() + x);
+  }
+  root_at = (uint32_t)(p - start);
+  for (int f = 0; f < 2; f++) {  // root_hash, account_key
+    if (end - p < 4) return false;
+    const uint32_t len = rd_u32(p);
+    if ((uint64_t)(end - p - 4) < len) return false;
+    p += 4 + len;
+  }
+  if (!skim_vec_vec(p, end, k, false)) return false;
+  if (end - p != 32) return false;  // address_keccak, and nothing after it
+  const uint64_t used = std::min(m, k);
+  proofs = 1 + used;
+  nodes = n_acc + cum[used];
+  return true;
+}
+
+// index inputs [0, n): MPTV_OK or MPTV_ERR_ARG (a blob is not a well-formed borsh(StorageProofInput))
+inline int skim_storage_inputs(WorkerPool& pool, const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, StorageIndex& idx) {
+  idx.proof_first.assign(n + 1, 0);
+  idx.node_first.assign(n + 1, 0);
+  idx.root_at.assign(n, 0);
+  const int T = pool.size();
+  std::atomic<int> err(0);
+  // equal shares of the BYTES (inputs differ in size by the number of storage proofs they carry)
+  const uint64_t total = n ? blob_off[n] - blob_off[0] : 0;
+  pool.run([&](int t) {
+    const uint64_t lo = (uint64_t)(std::lower_bound(blob_off, blob_off + n, blob_off[0] + total / T * t) - blob_off);
+    const uint64_t hi = t == T - 1 ? n : (uint64_t)(std::lower_bound(blob_off, blob_off + n, blob_off[0] + total / T * (t + 1)) - blob_off);
+    std::vector<uint64_t> cum;
+    for (uint64_t i = lo; i < hi; i++) {
+      uint64_t pr = 0, nd = 0;
+      if (blob_off[i + 1] < blob_off[i] ||
+          !skim_storage_input(blobs + blob_off[i], blobs + blob_off[i + 1], pr, nd, idx.root_at[i], cum)) { err.store(MPTV_ERR_ARG); return; }
+      idx.proof_first[i + 1] = pr;
+      idx.node_first[i + 1] = nd;
+    }
+  });
+  if (err.load()) return err.load();
+  for (uint64_t i = 0; i < n; i++) { idx.proof_first[i + 1] += idx.proof_first[i]; idx.node_first[i + 1] += idx.node_first[i]; }
+  return MPTV_OK;
+}
+
+struct StorageChunkJob {
+  const uint8_t* blobs;
+  const uint64_t* blob_off;
+  uint64_t cs, ce;           // inputs of the chunk
+  DedupTable* table;
+  const StorageIndex* idx;   // of the whole call
+  bool key_off_16 = false;   // as BorshChunkJob::key_off_16
+};
+
+// Flatten inputs [cs, ce) into a staging block laid out like flatten_borsh_chunk's, plus the group arrays (ChunkLayout).
+// Proof order inside the chunk = the guest's: each input's account proof, then its storage proofs.
+template <class GetBlock>
+int flatten_storage_chunk(WorkerPool& pool, const StorageChunkJob& job, GetBlock get_block, ChunkLayout& L,
+                          std::vector<uint64_t>* node_src, std::vector<uint8_t>* bad_root) {
+  const int T = pool.size();
+  const StorageIndex& X = *job.idx;
+  const uint64_t ni = job.ce - job.cs;
+  const uint64_t np = X.proof_first[job.ce] - X.proof_first[job.cs], nn = X.node_first[job.ce] - X.node_first[job.cs];
+  std::vector<RegionWriter> wr(T);
+  std::vector<uint64_t> bound(T, 0);
+  std::atomic<int> err(0);
+  uint8_t* block = nullptr;
+  L = ChunkLayout();
+  L.np = np; L.nn = nn; L.groups = true;
+  L.region_begin.assign(T, 0);
+  L.region_used.assign(T, 0);
+  if (nn > 0xfffffff0ull || np > 0x7ffffff0ull) return MPTV_ERR_ARG;
+  const uint64_t per = (ni + T - 1) / T;
+  {
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += up64z(bytes); return at; };
+    L.o_off = take(8 * nn); L.o_len = take(4 * nn); L.o_pf = take(4 * (np + 1)); L.o_roots = take(32 * np);
+    L.o_koff = take(4 * np); L.o_klen = take(4 * np); L.o_rfp = take(4 * np); L.o_hk = take(np);
+    L.index_end = o;
+    L.o_hkoff = take(4 * np); L.o_hklen = take(4 * np); L.o_hashed = take(32 * np);  // written by the device
+    for (int t = 0; t < T; t++) {
+      const uint64_t lo = job.cs + std::min(ni, per * t), hi = job.cs + std::min(ni, per * (t + 1));
+      // every node and every key padded to 16: the blob bytes bound what is placed
+      bound[t] = (job.blob_off[hi] - job.blob_off[lo]) + 16 * ((X.node_first[hi] - X.node_first[lo]) + (X.proof_first[hi] - X.proof_first[lo]) + 1);
+      L.region_begin[t] = o;
+      o += up64z(bound[t]) + 64;
+    }
+    L.total = o + 64;
+    L.host_total = L.total;
+    if (L.total > (job.key_off_16 ? 0xfffffff00ull : 0xffffff00ull)) return MPTV_ERR_ARG;  // as flatten_borsh_chunk
+    block = get_block(L.host_total, L.total);
+    if (!block) return MPTV_ERR_NOMEM;
+    if (node_src && node_src->size() < nn) node_src->resize(nn + nn / 8);
+    if (bad_root && bad_root->size() < np) bad_root->resize(np + np / 8);
+  }
+  pool.run([&](int t) {
+    const uint64_t lo = job.cs + std::min(ni, per * t), hi = job.cs + std::min(ni, per * (t + 1));
+    uint64_t k = X.node_first[lo] - X.node_first[job.cs];     // next node index of the chunk
+    uint64_t pi = X.proof_first[lo] - X.proof_first[job.cs];  // next proof index of the chunk
+    uint64_t* node_off = reinterpret_cast<uint64_t*>(block + L.o_off);
+    uint32_t* node_len = reinterpret_cast<uint32_t*>(block + L.o_len);
+    uint32_t* proof_first = reinterpret_cast<uint32_t*>(block + L.o_pf);
+    uint32_t* key_off = reinterpret_cast<uint32_t*>(block + L.o_koff);
+    uint32_t* key_len = reinterpret_cast<uint32_t*>(block + L.o_klen);
+    int32_t* rfp = reinterpret_cast<int32_t*>(block + L.o_rfp);
+    uint8_t* hk = block + L.o_hk;
+    uint8_t* roots = block + L.o_roots;
+    RegionWriter w;
+    w.base = block; w.at = L.region_begin[t]; w.end = w.at + up64z(bound[t]); w.table = job.table;
+    auto look_ahead = [&](const uint8_t* q, const uint8_t* end) -> uint64_t {
+      if (!job.table || end - q < 4) return 0;
+      const uint32_t len = rd_u32(q);
+      if (len < kDedupMinLen || (uint64_t)(end - q - 4) < len) return 0;
+      const uint64_t fp = node_fingerprint(q + 4, len);
+      job.table->prefetch(fp);
+      return fp;
+    };
+    auto next_node = [&](const uint8_t* q, const uint8_t* end) -> const uint8_t* {
+      if (end - q < 4) return nullptr;
+      const uint32_t len = rd_u32(q);
+      return (uint64_t)(end - q - 4) < len ? nullptr : q + 4 + len;
+    };
+    // the nodes of the Vec<Vec<u8>> at p become the next proof of the chunk (same look-ahead as flatten_borsh_chunk)
+    auto place_proof = [&](const uint8_t*& p, const uint8_t* end) -> bool {
+      if (end - p < 4) return false;
+      const uint32_t n = rd_u32(p);
+      p += 4;
+      proof_first[pi] = (uint32_t)k;
+      uint64_t fp = n ? look_ahead(p, end) : 0;
+      const uint8_t* p1 = n > 1 ? next_node(p, end) : nullptr;
+      uint64_t fp1 = p1 ? look_ahead(p1, end) : 0;
+      for (uint32_t j = 0; j < n; j++) {
+        if (end - p < 4) return false;
+        const uint32_t len = rd_u32(p);
+        if ((uint64_t)(end - p - 4) < len || len > kMaxNodeLen) return false;
+        for (uint32_t pf = 0; pf < len + 4; pf += 64) __builtin_prefetch(p + kStreamAhead + pf);
+        const uint8_t* p2 = (p1 && j + 2 < n) ? next_node(p1, end) : nullptr;
+        const uint64_t fp2 = p2 ? look_ahead(p2, end) : 0;
+        if (fp1) job.table->prefetch_source(fp1, rd_u32(p1));
+        node_off[k] = w.put_node(p + 4, len, fp);
+        fp = fp1; fp1 = fp2; p1 = p2;
+        node_len[k] = len;
+        if (node_src) (*node_src)[k] = (uint64_t)(p + 4 - job.blobs);
+        k++;
+        p += 4 + len;
+      }
+      pi++;
+      return true;
+    };
+    for (uint64_t i = lo; i < hi; i++) {
+      const uint8_t* start = job.blobs + job.blob_off[i];
+      const uint8_t* end = job.blobs + job.blob_off[i + 1];
+      const uint8_t* p = start;
+      const uint64_t acc = pi, used = X.proof_first[i + 1] - X.proof_first[i] - 1;
+      bool ok = place_proof(p, end);  // account_proof
+      if (ok && end - p < 4) ok = false;
+      if (ok) p += 4;                 // storage_proofs.len(): the index knows how many count
+      for (uint64_t j = 0; ok && j < used; j++) ok = place_proof(p, end);
+      if (ok && X.root_at[i] > (uint64_t)(end - start) - 4) ok = false;
+      if (!ok) { err.store(MPTV_ERR_ARG); return; }
+      p = start + X.root_at[i];  // (past the storage proofs that have no key)
+      const uint32_t rl = rd_u32(p);
+      if ((uint64_t)(end - p - 4) < rl) { err.store(MPTV_ERR_ARG); return; }
+      if (rl == 32) memcpy(roots + 32 * acc, p + 4, 32); else memset(roots + 32 * acc, 0, 32);
+      if (bad_root) (*bad_root)[acc] = rl != 32;  // the guest's try_into().unwrap() (main.rs:11)
+      p += 4 + rl;
+      uint32_t al = 0;
+      if (end - p < 4 || (uint64_t)(end - p - 4) < (al = rd_u32(p))) { err.store(MPTV_ERR_ARG); return; }
+      p += 4 + al;               // account_key: never read by the guest
+      if (end - p < 4) { err.store(MPTV_ERR_ARG); return; }
+      p += 4;                    // storage_keys.len()
+      rfp[acc] = -1; hk[acc] = 0;
+      for (uint64_t j = 0; j < used; j++) {
+        uint32_t kl = 0;
+        if (end - p < 4 || (uint64_t)(end - p - 4) < (kl = rd_u32(p))) { err.store(MPTV_ERR_ARG); return; }
+        const uint64_t q = acc + 1 + j;
+        const size_t ko = w.put_key(p + 4, kl);  // the RAW slot: digest_keccak(&key) runs on the device (main.rs:26)
+        key_off[q] = job.key_off_16 ? (uint32_t)(ko >> 4) : (uint32_t)ko;
+        key_len[q] = kl;
+        memset(roots + 32 * q, 0, 32);                // taken on the device from the verified account leaf
+        rfp[q] = (int32_t)acc; hk[q] = 1;
+        if (bad_root) (*bad_root)[q] = 0;
+        p += 4 + kl;
+      }
+      if (end - start < 32) { err.store(MPTV_ERR_ARG); return; }
+      const size_t ako = w.put_key(end - 32, 32);  // address_keccak
+      key_off[acc] = job.key_off_16 ? (uint32_t)(ako >> 4) : (uint32_t)ako;
+      key_len[acc] = 32;
+    }
+    if (w.table) { static const uint8_t z16[16] = {0}; w.put_bytes(block + w.at, z16, 16); }
+    else memset(block + w.at, 0, 16);
+    w.at += 16;
+    w.finish();
+    _mm_sfence();
+    wr[t] = w;
+  });
+  if (err.load()) return err.load();
+  reinterpret_cast<uint32_t*>(block + L.o_pf)[np] = (uint32_t)nn;
   for (int t = 0; t < T; t++) {
     L.region_used[t] = wr[t].at - L.region_begin[t];
     L.node_bytes_supplied += wr[t].supplied; L.node_bytes_placed += wr[t].placed; L.nodes_aliased += wr[t].aliased;

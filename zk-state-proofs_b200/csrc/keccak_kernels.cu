@@ -561,13 +561,14 @@ cudaError_t launch_gather(const uint8_t* src_base, uint8_t* dst_base, const uint
 // key record, and for a flagged proof first hashes the key (byte loads: the arena is packed, keys are short) into
 // the 32-byte slot behind the raw keys.
 __global__ void __launch_bounds__(128) k_prepare_keys(const uint8_t* __restrict__ key_bytes, const uint32_t* __restrict__ key_off,
+                                                      const uint32_t* __restrict__ key_len_in /* null: key_off is a prefix array */,
                                                       uint32_t key_base, const uint8_t* __restrict__ hash_key, uint64_t n_proofs,
                                                       uint8_t* __restrict__ hashed /* 32 n_proofs, 16-byte aligned */,
                                                       uint32_t hashed_off /* = hashed - key_bytes */,
                                                       uint32_t* __restrict__ off_out, uint32_t* __restrict__ len_out) {
   const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_proofs) return;
-  const uint32_t o = key_off[p] - key_base, len = key_off[p + 1] - key_off[p];
+  const uint32_t o = key_off[p] - key_base, len = key_len_in ? key_len_in[p] : key_off[p + 1] - key_off[p];
   if (!hash_key[p]) { off_out[p] = o; len_out[p] = len; return; }
   const uint8_t* k = key_bytes + o;
   uint32_t lo[25], hi[25];
@@ -601,10 +602,10 @@ __global__ void __launch_bounds__(128) k_prepare_keys(const uint8_t* __restrict_
 
 cudaError_t launch_prepare_keys(const uint8_t* key_bytes, const uint32_t* key_off, uint32_t key_base, const uint8_t* hash_key,
                                 uint64_t n_proofs, uint8_t* hashed, uint32_t hashed_off, uint32_t* off_out, uint32_t* len_out,
-                                cudaStream_t st) {
+                                cudaStream_t st, const uint32_t* key_len_in) {
   if (n_proofs == 0) return cudaSuccess;
-  k_prepare_keys<<<(unsigned)((n_proofs + 127) / 128), 128, 0, st>>>(key_bytes, key_off, key_base, hash_key, n_proofs, hashed, hashed_off,
-                                                                   off_out, len_out);
+  k_prepare_keys<<<(unsigned)((n_proofs + 127) / 128), 128, 0, st>>>(key_bytes, key_off, key_len_in, key_base, hash_key, n_proofs, hashed,
+                                                                   hashed_off, off_out, len_out);
   return cudaGetLastError();
 }
 

@@ -83,7 +83,7 @@ cudaError_t launch_keccak256_nodes(const uint8_t* node_bytes, uint64_t byte_base
 // replaced by their Keccak-256, written to hashed[32 p ..] (hashed_off = hashed - key_bytes, same allocation)
 cudaError_t launch_prepare_keys(const uint8_t* key_bytes, const uint32_t* key_off, uint32_t key_base, const uint8_t* hash_key,
                                 uint64_t n_proofs, uint8_t* hashed, uint32_t hashed_off, uint32_t* off_out, uint32_t* len_out,
-                                cudaStream_t st);
+                                cudaStream_t st, const uint32_t* key_len_in = nullptr /* key_off holds (offset) records, this the lengths */);
 
 // pull mode of the streamed borsh entry: records (src offset u64, dst / 16 u32, len u32; len 0xffffffff = unused) ->
 // dst_base + 16 dst16 receives len bytes of src_base + src, zero-padded to a multiple of 16.  src_base is mapped

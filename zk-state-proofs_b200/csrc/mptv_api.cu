@@ -626,6 +626,7 @@ struct BorshStream {
   const uint8_t* blobs;
   const uint64_t* blob_off;
   bool pinned;  // the blobs are page-locked and mapped: the devices can fetch node bytes from them directly (pull mode)
+  const StorageIndex* storage = nullptr;  // set: the blobs are borsh(StorageProofInput), indexed by skim_storage_inputs
 };
 
 // Hands out the chunks of one device's blob range [front, back).  One pipeline takes them from the front; in the
@@ -768,6 +769,18 @@ int submit_borsh_chunk(mptv_ctx* ctx, Device& d, Slot& s, const ChunkLayout& L, 
   b.key_bytes = dv; b.key_off = reinterpret_cast<const uint32_t*>(dv + L.o_koff);
   b.key_len = reinterpret_cast<const uint32_t*>(dv + L.o_klen);
   b.root_from_proof = nullptr;
+  if (L.groups) {
+    // borsh(StorageProofInput): the storage keys are the raw slots -- digest_keccak(&key) (storage-circuit/src/main.rs:26)
+    // runs here, one thread per proof, and the kernels read the key records it writes; every storage proof takes its
+    // root from the verified leaf of its input's account proof
+    CK(launch_prepare_keys(dv, reinterpret_cast<const uint32_t*>(dv + L.o_koff), 0, dv + L.o_hk, np, dv + L.o_hashed,
+                           (uint32_t)L.o_hashed, reinterpret_cast<uint32_t*>(dv + L.o_hkoff),
+                           reinterpret_cast<uint32_t*>(dv + L.o_hklen), st, reinterpret_cast<const uint32_t*>(dv + L.o_klen)));
+    d.hstat.launches += 1;
+    b.key_off = reinterpret_cast<const uint32_t*>(dv + L.o_hkoff);
+    b.key_len = reinterpret_cast<const uint32_t*>(dv + L.o_hklen);
+    b.root_from_proof = reinterpret_cast<const int32_t*>(dv + L.o_rfp);
+  }
   b.n_nodes = L.nn; b.n_proofs = np;
   b.byte_base = 0; b.node_base = 0; b.key_base = 0; b.proof_base = 0;
   CK(s.results.reserve(13 * np + 16));
@@ -834,7 +847,7 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
   // nor does the DMA engine read them a second time from a staging block
   const uint8_t* blobs_dev = nullptr;
   bool pull = false;
-  if (in.pinned && ctx->pull_pinned) {
+  if (in.pinned && ctx->pull_pinned && !in.storage) {
     void* dp = nullptr;
     if (cudaHostGetDevicePointer(&dp, const_cast<uint8_t*>(in.blobs), 0) == cudaSuccess && dp) { blobs_dev = static_cast<const uint8_t*>(dp); pull = true; }
     else cudaGetLastError();
@@ -869,21 +882,29 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
     // one pass over the chunk's blobs, straight into the slot's page-locked block; a node identical to one already
     // placed in this chunk is aliased, not copied (host_flatten.h)
     if (alias) d.dedup_tab.new_epoch();
-    const BorshChunkJob job = {in.blobs, in.blob_off, cs, ce, alias ? &d.dedup_tab : nullptr, pull};
-    rc = flatten_borsh_chunk(pool, job, [&](size_t host_bytes, size_t dev_bytes) -> uint8_t* {
+    auto get_block = [&](size_t host_bytes, size_t dev_bytes) -> uint8_t* {
       if (s.h_in.reserve(host_bytes) != cudaSuccess || s.in_pack.reserve(dev_bytes) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
       }
       return static_cast<uint8_t*>(s.h_in.p);
-    }, P.layout[k], &s.node_src, &s.bad_root);
+    };
+    if (in.storage) {
+      const StorageChunkJob job = {in.blobs, in.blob_off, cs, ce, alias ? &d.dedup_tab : nullptr, in.storage};
+      rc = flatten_storage_chunk(pool, job, get_block, P.layout[k], &s.node_src, &s.bad_root);
+    } else {
+      const BorshChunkJob job = {in.blobs, in.blob_off, cs, ce, alias ? &d.dedup_tab : nullptr, pull};
+      rc = flatten_borsh_chunk(pool, job, get_block, P.layout[k], &s.node_src, &s.bad_root);
+    }
     if (rc != MPTV_OK) {
-      why = rc == MPTV_ERR_ARG ? "mptv_verify_borsh: a blob is not a well-formed borsh(MerkleProofInput)"
+      why = rc == MPTV_ERR_ARG ? "mptv_verify_borsh: a blob is not a well-formed borsh(MerkleProofInput) / borsh(StorageProofInput), or one blob needs more than 4 GiB"
                                : "mptv_verify_borsh: staging allocation failed";
       break;
     }
     t_flat += now() - t2;
-    s.pend_p0 = cs; s.pend_np = ce - cs; s.pend_borsh = true;
+    // results are indexed by proof: blob i of the MerkleProofInput stream is proof i, input i of the storage stream owns
+    // proofs [proof_first[i], proof_first[i + 1])
+    s.pend_p0 = in.storage ? in.storage->proof_first[cs] : cs; s.pend_np = P.layout[k].np; s.pend_borsh = true;
     s.h_node_off = P.layout[k].o_off; s.h_node_len = P.layout[k].o_len; s.h_proof_first = P.layout[k].o_pf;
     {
       std::lock_guard<std::mutex> g(P.mu);
@@ -1043,7 +1064,7 @@ int run_slice_borsh(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv_result
   int rc = MPTV_OK;
   // automatic: one device has the host's cores and memory to itself and the host flatten moves the fewest PCIe bytes;
   // several devices of one context share them, and the device flatten costs the host one DMA read per byte
-  const int mode = ctx->borsh_mode >= 0 ? ctx->borsh_mode : (ctx->dev.size() > 1 ? 1 : 0);
+  const int mode = in.storage ? 0 : ctx->borsh_mode >= 0 ? ctx->borsh_mode : (ctx->dev.size() > 1 ? 1 : 0);  // (the storage stream has the host flatten only)
   if (mode == 1 && in.pinned) {
     rc = run_slice_borsh_device(ctx, d, in, out, feed, false);
   } else if (mode == 2 && in.pinned) {
@@ -1110,9 +1131,121 @@ int verify_borsh_run(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_o
   return MPTV_OK;
 }
 
+// ------------------------------------------------------------------ borsh(StorageProofInput) stream
+// strict canonical RLP header (alloy-rlp Header::decode), as rlp_hdr of verify_device.cuh
+bool host_rlp_hdr(const uint8_t* p, uint32_t n, bool& is_list, uint32_t& hdr_len, uint32_t& payload_len) {
+  if (n == 0) return false;
+  const uint32_t b = p[0];
+  if (b < 0x80) { is_list = false; hdr_len = 0; payload_len = 1; return true; }
+  if (b < 0xB8) {
+    is_list = false; hdr_len = 1; payload_len = b - 0x80;
+    if (payload_len == 1 && (n < 2 || p[1] < 0x80)) return false;
+  } else if (b < 0xC0 || b >= 0xF8) {
+    is_list = b >= 0xF8;
+    const uint32_t ll = is_list ? b - 0xF7 : b - 0xB7;
+    if (n < 1 + ll || p[1] == 0 || ll > 4) return false;
+    uint32_t v = 0;
+    for (uint32_t i = 0; i < ll; i++) v = (v << 8) | p[1 + i];
+    if (v < 56) return false;
+    hdr_len = 1 + ll; payload_len = v;
+  } else {
+    is_list = true; hdr_len = 1; payload_len = b - 0xC0;
+  }
+  return (uint64_t)hdr_len + payload_len <= (uint64_t)n;
+}
+
+// alloy_rlp::decode_exact::<Account> (storage-circuit/src/main.rs:15), the rule set of account_storage_root_off on the
+// device: rlp([nonce u64, balance U256, storage_root B256, code_hash B256]) and nothing else
+bool host_account_decodes(const uint8_t* v, uint32_t n) {
+  bool lst, tl;
+  uint32_t hl, pl, thl, tpl;
+  if (!host_rlp_hdr(v, n, lst, hl, pl) || !lst || hl + pl != n) return false;
+  uint32_t q = hl;
+  for (int i = 0; i < 4; i++) {
+    if (!host_rlp_hdr(v + q, n - q, tl, thl, tpl) || tl) return false;
+    if (i == 0 && tpl > 8) return false;
+    if (i == 1 && tpl > 32) return false;
+    if (i < 2 && tpl > 0 && v[q + thl] == 0) return false;
+    if (i >= 2 && tpl != 32) return false;
+    q += thl + tpl;
+  }
+  return q == n;
+}
+
+int verify_storage_borsh_run(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads,
+                             uint64_t* proof_first, uint8_t* input_status, uint64_t results_cap, mptv_result* out) {
+  if (!ctx || !proof_first) return MPTV_ERR_ARG;
+  proof_first[0] = 0;
+  if (n == 0) return MPTV_OK;
+  if (!blobs || !blob_off) return MPTV_ERR_ARG;
+  for (uint64_t i = 0; i < n; i++)
+    if (blob_off[i + 1] < blob_off[i]) return MPTV_ERR_ARG;
+  const int nd = (int)ctx->dev.size();
+  if (n_threads <= 0) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (int)std::max(1u, std::min(32u * nd, hw >= 8u * nd ? hw - 2 * nd : (hw > 2u * nd ? hw - nd : hw)));
+  }
+  // pass 1: the length prefixes of every input -> how many proofs (and nodes) the guest verifies for it
+  StorageIndex idx;
+  {
+    WorkerPool pool(n < 64 ? 1 : n_threads);
+    const int rc = skim_storage_inputs(pool, blobs, blob_off, n, idx);
+    if (rc != MPTV_OK) return fail_msg(ctx, rc, "mptv_verify_storage_borsh: a blob is not a well-formed borsh(StorageProofInput)");
+  }
+  memcpy(proof_first, idx.proof_first.data(), 8 * (n + 1));
+  const uint64_t np = idx.proof_first[n];
+  if (results_cap < np || !out || !out->status || !out->value_off || !out->value_len) return MPTV_ERR_NOMEM;  // proof_first[n] = what is required
+  // pass 2: the stream, cut over the devices by blob bytes at input boundaries
+  const BorshStream in = {blobs, blob_off, false, &idx};
+  std::vector<uint64_t> cut(nd + 1, 0);
+  cut[nd] = n;
+  const uint64_t total = blob_off[n] - blob_off[0];
+  for (int k = 1; k < nd; k++)
+    cut[k] = (uint64_t)(std::lower_bound(blob_off, blob_off + n + 1, blob_off[0] + total / nd * k) - blob_off);
+  for (int k = 1; k <= nd; k++) if (cut[k] < cut[k - 1]) cut[k] = cut[k - 1];
+  std::vector<int> rcs(nd, MPTV_OK);
+  if (nd == 1) {
+    rcs[0] = run_slice_borsh(ctx, ctx->dev[0], in, out, cut[0], cut[1], n_threads);
+  } else {
+    std::vector<std::thread> th;
+    const int per = std::max(1, n_threads / nd);
+    for (int k = 0; k < nd; k++)
+      th.emplace_back([&, k] { rcs[k] = run_slice_borsh(ctx, ctx->dev[k], in, out, cut[k], cut[k + 1], per); });
+    for (auto& t : th) t.join();
+  }
+  for (int k = 0; k < nd; k++) if (rcs[k] != MPTV_OK) return rcs[k];
+  // the guest's outcome per input: the first proof that fails, in its order; an account leaf that is not an Account
+  // (decode_exact(...).unwrap(), main.rs:15) fails the input even when it carries no storage proof
+  if (input_status) {
+    WorkerPool pool(n < 4096 ? 1 : n_threads);
+    const int T = pool.size();
+    const uint64_t per = (n + T - 1) / T;
+    pool.run([&](int t) {
+      const uint64_t lo = std::min(n, per * t), hi = std::min(n, lo + per);
+      for (uint64_t i = lo; i < hi; i++) {
+        const uint64_t a = idx.proof_first[i], e = idx.proof_first[i + 1];
+        uint8_t st = out->status[a];
+        if (st == MPTV_ST_OK && !host_account_decodes(blobs + out->value_off[a], out->value_len[a])) st = MPTV_ST_DEP_FAILED;
+        for (uint64_t q = a + 1; st == MPTV_ST_OK && q < e; q++) st = out->status[q];
+        input_status[i] = st;
+      }
+    });
+  }
+  return MPTV_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+int mptv_verify_storage_borsh(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_off, uint64_t n_inputs, int n_threads,
+                              uint64_t* proof_first, uint8_t* input_status, uint64_t results_cap, mptv_result* out) {
+  try {
+    return verify_storage_borsh_run(ctx, blobs, blob_off, n_inputs, n_threads, proof_first, input_status, results_cap, out);
+  } catch (...) {
+    return MPTV_ERR_NOMEM;
+  }
+}
 
 int mptv_verify_borsh(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads,
                       mptv_result* out) {
