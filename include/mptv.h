@@ -133,6 +133,13 @@ int mptv_verify_batch_hashed_keys(mptv_ctx* ctx, const mptv_batch* in, const uin
 int mptv_verify_borsh(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads,
                       mptv_result* out);
 
+/* alloy_rlp::decode_exact::<Account>(value) of the storage guest (storage-circuit/src/main.rs:15) on the host: 1 and the
+ * 32-byte storage_root (storage_root32 may be NULL) when `value` is exactly rlp([nonce u64, balance U256, storage_root
+ * B256, code_hash B256]) in canonical form, else 0 -- the guest's unwrap() panics.  The same rule the device applies
+ * before a storage proof may take its root from an account leaf; a shim needs it for inputs WITHOUT storage proofs,
+ * where the guest still decodes the leaf. */
+int mptv_account_storage_root(const uint8_t* value, uint32_t len, uint8_t* storage_root32);
+
 /* The risc0 storage guest over a batch of its own inputs (circuits/risc0-storage-proof/.../storage-circuit/src/main.rs:6-31):
  * blob i holds borsh(StorageProofInput) (crypto-ops/src/types.rs:11-19).  For every input the account proof is verified
  * under address_keccak against root_hash, then storage_proofs zipped with storage_keys (the shorter list decides,

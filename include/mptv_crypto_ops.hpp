@@ -233,6 +233,9 @@ class Verifier {
     std::vector<Bytes> values;
     for (size_t i = 0; i < res.size(); i++) {
       if (!res[i].ok()) throw VerifyPanic(res[i].status);
+      // decode_exact::<Account>(..).unwrap() (main.rs:15) runs even when no storage proof follows
+      if (i == 0 && !mptv_account_storage_root(res[0].value.data(), (uint32_t)res[0].value.size(), nullptr))
+        throw VerifyPanic(MPTV_ST_DEP_FAILED);
       if (i) values.push_back(res[i].value);
     }
     return values;

@@ -226,3 +226,35 @@ def test_storage_borsh_flattener_matches_the_structs(oracle):
     for bad in (good[:-1], good + b"\0", good[:3], b"", b"\xff\xff\xff\xff" + good[4:], good[:-33]):
         with pytest.raises(ValueError):
             z.flatten_storage_borsh(blobs[:5] + [bad] + blobs[5:])
+
+
+def test_account_decode_on_the_host_matches_the_oracle(oracle):
+    """mptv_account_storage_root = alloy_rlp::decode_exact::<Account> of the storage guest (main.rs:15), the rule the
+    device applies too (oracle: mpto_account_storage_root)"""
+    import random
+    import zk_state_proofs_b200 as z
+    from oracle.pytrie import rlp_list, rlp_str, rlp_uint
+    rng = random.Random(1)
+    ok = 0
+    for _ in range(5000):
+        k = rng.random()
+        items = [rlp_uint(rng.randrange(0, 1 << rng.choice([0, 7, 8, 63, 64, 70]))),
+                 rlp_uint(rng.randrange(0, 1 << rng.choice([0, 8, 255, 256, 260]))),
+                 rlp_str(rng.randbytes(rng.choice([32, 32, 32, 31, 33, 0]))), rlp_str(rng.randbytes(rng.choice([32, 32, 32, 31])))]
+        if k < 0.1:
+            items = items[:3]
+        elif k < 0.2:
+            items.append(b"\x80")
+        elif k < 0.25:
+            items[1] = rlp_str(b"\x00" + rng.randbytes(3))  # leading zero
+        elif k < 0.3:
+            items[0] = b"\x00"
+        v = rlp_list(items)
+        if k > 0.95:
+            v += b"\x00"
+        elif k > 0.9:
+            v = v[:-1]
+        got = z.account_storage_root(v)
+        assert got == oracle.account_storage_root(v)
+        ok += got is not None
+    assert 500 < ok < 4500 and z.account_storage_root(b"") is None and z.account_storage_root(b"\xc0") is None

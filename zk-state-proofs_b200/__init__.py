@@ -21,6 +21,7 @@ from .crypto_ops import (  # noqa: F401
     flatten_borsh,
     flatten_borsh_ex,
     flatten_storage_borsh,
+    account_storage_root,
     borsh_flatten_probe,
     host_bw_probe,
     flatten_kv,
@@ -36,7 +37,7 @@ from .crypto_ops import (  # noqa: F401
 )
 
 __all__ = [
-    "Log", "encode_receipt", "flatten_borsh", "flatten_borsh_ex", "flatten_storage_borsh", "borsh_flatten_probe", "host_bw_probe", "rlp_index_native",
+    "Log", "encode_receipt", "flatten_borsh", "flatten_borsh_ex", "flatten_storage_borsh", "account_storage_root", "borsh_flatten_probe", "host_bw_probe", "rlp_index_native",
     "Batch", "KvBatch", "flatten_kv", "ordered_trie_root", "rlp_index", "trie_roots", "MerkleProofInput", "MptvError", "StorageProofInput", "VerifyPanic", "Verifier",
     "STATUS_NAMES", "digest_keccak", "flatten", "lib_path", "load_library", "verify_merkle_proof",
     "verify_merkle_proofs", "verify_storage_proof_input",

@@ -357,6 +357,16 @@ def flatten_storage_borsh(blobs, blob_off=None, threads: int = 0, pinned: bool =
     return b, _view(hk.value, npr, np.uint8).copy(), pf, info
 
 
+def account_storage_root(value: bytes) -> Optional[bytes]:
+    """mptv_account_storage_root: the storage guest's alloy_rlp::decode_exact::<Account>(value) (main.rs:15) ->
+    the 32-byte storage_root, or None where the guest's unwrap() panics."""
+    L = load_library()
+    L.mptv_account_storage_root.restype = ctypes.c_int
+    L.mptv_account_storage_root.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p]
+    out = ctypes.create_string_buffer(32)
+    return out.raw if L.mptv_account_storage_root(bytes(value), len(value), out) else None
+
+
 def borsh_flatten_probe(blobs, blob_off=None, threads: int = 0, chunk_bytes: int = 32 << 20, alias_duplicates: bool = True):
     """mptv_borsh_flatten_probe: the host stage of verify_borsh alone -> (seconds, FlattenInfo)"""
     import time
@@ -946,6 +956,9 @@ class Verifier:
         out = []
         for a, e in spans:
             bad = next((r for r in res[a:e] if isinstance(r, VerifyPanic)), None)
+            # decode_exact::<Account>(..).unwrap() (main.rs:15) runs even when no storage proof follows
+            if bad is None and e == a + 1 and account_storage_root(res[a]) is None:
+                bad = VerifyPanic(7)
             out.append(bad if bad is not None else res[a + 1:e])
         return out
 

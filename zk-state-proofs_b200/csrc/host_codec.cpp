@@ -272,6 +272,50 @@ int mptv_flatten_borsh_ex(const uint8_t* blobs, const uint64_t* blob_off, uint64
   }
 }
 
+// strict canonical RLP header (alloy-rlp Header::decode), as rlp_hdr of verify_device.cuh
+static bool host_rlp_hdr(const uint8_t* p, uint32_t n, bool& is_list, uint32_t& hdr_len, uint32_t& payload_len) {
+  if (n == 0) return false;
+  const uint32_t b = p[0];
+  if (b < 0x80) { is_list = false; hdr_len = 0; payload_len = 1; return true; }
+  if (b < 0xB8) {
+    is_list = false; hdr_len = 1; payload_len = b - 0x80;
+    if (payload_len == 1 && (n < 2 || p[1] < 0x80)) return false;
+  } else if (b < 0xC0 || b >= 0xF8) {
+    is_list = b >= 0xF8;
+    const uint32_t ll = is_list ? b - 0xF7 : b - 0xB7;
+    if (n < 1 + ll || p[1] == 0 || ll > 4) return false;
+    uint32_t v = 0;
+    for (uint32_t i = 0; i < ll; i++) v = (v << 8) | p[1 + i];
+    if (v < 56) return false;
+    hdr_len = 1 + ll; payload_len = v;
+  } else {
+    is_list = true; hdr_len = 1; payload_len = b - 0xC0;
+  }
+  return (uint64_t)hdr_len + payload_len <= (uint64_t)n;
+}
+
+// alloy_rlp::decode_exact::<Account> (storage-circuit/src/main.rs:15), the rule set of account_storage_root_off on the
+// device: rlp([nonce u64, balance U256, storage_root B256, code_hash B256]) and nothing else
+int mptv_account_storage_root(const uint8_t* v, uint32_t n, uint8_t* storage_root32) {
+  if (!v) return 0;
+  bool lst, tl;
+  uint32_t hl, pl, thl, tpl, at = 0;
+  if (!host_rlp_hdr(v, n, lst, hl, pl) || !lst || hl + pl != n) return 0;
+  uint32_t q = hl;
+  for (int i = 0; i < 4; i++) {
+    if (!host_rlp_hdr(v + q, n - q, tl, thl, tpl) || tl) return 0;
+    if (i == 0 && tpl > 8) return 0;
+    if (i == 1 && tpl > 32) return 0;
+    if (i < 2 && tpl > 0 && v[q + thl] == 0) return 0;
+    if (i >= 2 && tpl != 32) return 0;
+    if (i == 2) at = q + thl;
+    q += thl + tpl;
+  }
+  if (q != n) return 0;
+  if (storage_root32) memcpy(storage_root32, v + at, 32);
+  return 1;
+}
+
 int mptv_flatten_storage_borsh(const uint8_t* blobs, const uint64_t* blob_off, uint64_t n_inputs, int n_threads, int pinned,
                                unsigned flags, mptv_host_batch** out, mptv_flatten_info* info, uint64_t* proof_first,
                                const uint8_t** hash_key) {

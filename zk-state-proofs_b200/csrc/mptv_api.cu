@@ -1132,46 +1132,6 @@ int verify_borsh_run(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_o
 }
 
 // ------------------------------------------------------------------ borsh(StorageProofInput) stream
-// strict canonical RLP header (alloy-rlp Header::decode), as rlp_hdr of verify_device.cuh
-bool host_rlp_hdr(const uint8_t* p, uint32_t n, bool& is_list, uint32_t& hdr_len, uint32_t& payload_len) {
-  if (n == 0) return false;
-  const uint32_t b = p[0];
-  if (b < 0x80) { is_list = false; hdr_len = 0; payload_len = 1; return true; }
-  if (b < 0xB8) {
-    is_list = false; hdr_len = 1; payload_len = b - 0x80;
-    if (payload_len == 1 && (n < 2 || p[1] < 0x80)) return false;
-  } else if (b < 0xC0 || b >= 0xF8) {
-    is_list = b >= 0xF8;
-    const uint32_t ll = is_list ? b - 0xF7 : b - 0xB7;
-    if (n < 1 + ll || p[1] == 0 || ll > 4) return false;
-    uint32_t v = 0;
-    for (uint32_t i = 0; i < ll; i++) v = (v << 8) | p[1 + i];
-    if (v < 56) return false;
-    hdr_len = 1 + ll; payload_len = v;
-  } else {
-    is_list = true; hdr_len = 1; payload_len = b - 0xC0;
-  }
-  return (uint64_t)hdr_len + payload_len <= (uint64_t)n;
-}
-
-// alloy_rlp::decode_exact::<Account> (storage-circuit/src/main.rs:15), the rule set of account_storage_root_off on the
-// device: rlp([nonce u64, balance U256, storage_root B256, code_hash B256]) and nothing else
-bool host_account_decodes(const uint8_t* v, uint32_t n) {
-  bool lst, tl;
-  uint32_t hl, pl, thl, tpl;
-  if (!host_rlp_hdr(v, n, lst, hl, pl) || !lst || hl + pl != n) return false;
-  uint32_t q = hl;
-  for (int i = 0; i < 4; i++) {
-    if (!host_rlp_hdr(v + q, n - q, tl, thl, tpl) || tl) return false;
-    if (i == 0 && tpl > 8) return false;
-    if (i == 1 && tpl > 32) return false;
-    if (i < 2 && tpl > 0 && v[q + thl] == 0) return false;
-    if (i >= 2 && tpl != 32) return false;
-    q += thl + tpl;
-  }
-  return q == n;
-}
-
 int verify_storage_borsh_run(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads,
                              uint64_t* proof_first, uint8_t* input_status, uint64_t results_cap, mptv_result* out) {
   if (!ctx || !proof_first) return MPTV_ERR_ARG;
@@ -1225,7 +1185,7 @@ int verify_storage_borsh_run(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t
       for (uint64_t i = lo; i < hi; i++) {
         const uint64_t a = idx.proof_first[i], e = idx.proof_first[i + 1];
         uint8_t st = out->status[a];
-        if (st == MPTV_ST_OK && !host_account_decodes(blobs + out->value_off[a], out->value_len[a])) st = MPTV_ST_DEP_FAILED;
+        if (st == MPTV_ST_OK && !mptv_account_storage_root(blobs + out->value_off[a], out->value_len[a], nullptr)) st = MPTV_ST_DEP_FAILED;
         for (uint64_t q = a + 1; st == MPTV_ST_OK && q < e; q++) st = out->status[q];
         input_status[i] = st;
       }
