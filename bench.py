@@ -107,7 +107,8 @@ def workload_name(a):
         return (f"config3: {n_proofs_of(a)} nested proofs = {n_proofs_of(a) // 4} groups x (1 account proof in a "
                 f"{a.accounts}-account state trie + 3 ERC-20 slot proofs in one of {a.tokens} {a.slots}-slot storage "
                 f"tries, root taken from the verified account leaf); 80% inclusion / 10% exclusion / 10% mutated "
-                f"(7 mutators), seed 3")
+                f"(7 mutators), seed 3; every storage key has a pre-image (an absent / wrong key is keccak of 32 random "
+                f"bytes), so the batch also exists as borsh(StorageProofInput) blobs")
     if a.workload == "config5":
         return (f"config5: {a.total_proofs} mixed proofs per step over all GPUs (half account, half storage with "
                 f"its account in the same shard, 2% mutated), as repeated passes over a resident "
@@ -130,7 +131,7 @@ def build_batch(a, rank, pinned):
         state, tokens = gen.make_state_and_tokens(a.accounts, a.tokens, a.slots, seed=seed)
         t1 = time.time()
         if a.workload == "config3":
-            batch = gen.nested_batch(state, tokens, n // 4, seed=seed + 1000 * rank, pinned=pinned)
+            batch = gen.nested_batch(state, tokens, n // 4, seed=seed + 1000 * rank, pinned=pinned, raw_keys=True)
         else:
             batch = gen.mixed_batch(state, tokens, n, seed=seed + 1000 * rank, pinned=pinned)
         state.close()
@@ -702,6 +703,54 @@ def e2e_from_borsh(a, ver, b, env, dev, st, voff, vlen, steps):
         gpu_launches_per_step=int(launches))
 
 
+def e2e_from_storage_borsh(a, ver, b, env, dev, st, voff, vlen, steps):
+    """the nested workload from ITS wire format: one borsh(StorageProofInput) blob per group in ordinary host memory ->
+    the storage guest's flow for every input (mptv_verify_storage_borsh), flattening, copies and results inside"""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from workload import gen
+    rank, world, local = env
+    blobs, boff, gf = gen.batch_to_storage_borsh(b, pinned=False)
+    th = flatten_threads(a, world)
+    call = lambda: ver.verify_storage_borsh(blobs, boff, threads=th, n_proofs=b.n_proofs)
+    for _ in range(2):
+        pf, ist, bst, bvoff, bvlen = call()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ver.host_stats(reset=True)
+    t0 = time.perf_counter()
+    marks = [t0]
+    for _ in range(steps):
+        pf, ist, bst, bvoff, bvlen = call()
+        marks.append(time.perf_counter())
+    dt = reduce_max((marks[-1] - t0) / steps, world, dev)
+    hs = ver.host_stats(reset=True)
+    assert (pf == gf).all() and (bst == st).all() and (bvlen == vlen).all(), "storage stream and device entry disagree"
+    for i in np.nonzero(bst == 0)[0][:2000]:
+        assert blobs[int(bvoff[i]):int(bvoff[i]) + int(bvlen[i])].tobytes() == b.value(int(voff[i]), int(vlen[i]))
+    # the guest's outcome per input: the first failing proof of the group
+    first_bad = np.array([next((int(s) for s in st[int(gf[g]):int(gf[g + 1])] if s), 0) for g in range(0, len(gf) - 1, 997)])
+    assert (ist[::997] == first_bad).all()
+    all_proofs, blob_bytes, h2d, d2h, launches = reduce_sum(
+        [b.n_proofs, len(blobs), hs.h2d_bytes / steps, hs.d2h_bytes / steps, hs.launches / steps], world, dev)
+    return dict(value=all_proofs / dt, unit=UNIT, ms_per_step=dt * 1e3, entry="mptv_verify_storage_borsh",
+                step_ms_rank0=[round((y - x) * 1e3, 2) for x, y in zip(marks, marks[1:])],
+                inputs_per_step=int(len(gf) - 1), host_memory="pageable blobs, page-locked staging inside the library",
+                input_bytes_per_step=int(blob_bytes), h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                host_threads_per_rank=th, chunks_per_step=int(hs.chunks / steps),
+                timer="host wall clock around the blocking C-ABI call (index pass + stream), max over ranks",
+                transfer_dedup=dict(nodes=int(hs.nodes / steps), nodes_aliased=int(hs.nodes_aliased / steps),
+                                    node_bytes_supplied=int(hs.node_bytes_supplied / steps),
+                                    node_bytes_placed=int(hs.node_bytes_placed / steps)),
+                host_ms=dict(flatten=hs.flatten_us / steps / 1e3, wait=hs.wait_us / steps / 1e3,
+                             map_results=hs.map_us / steps / 1e3, call=hs.call_us / steps / 1e3),
+                gpu_launches_per_step=int(launches),
+                note="storage keys cross PCIe un-hashed and are hashed on the device (digest_keccak(&key), main.rs:26); "
+                     "storage roots are taken on the device from the verified account leaves")
+
+
 def e2e_from_csr(ver, b, names, env, dev, st, voff, vlen, steps, passes, pageable):
     import torch
     import torch.distributed as dist
@@ -824,6 +873,9 @@ def run_verify(a, env, want_e2e=True, want_cpu=True):
             # the reference's input format: borsh(MerkleProofInput) blobs (MerkleProofInput has no dependency field,
             # so the nested configs have no blob form)
             e2e = e2e_from_borsh(a, ver, b, env, dev, st, voff, vlen, a.steps)
+        elif passes == 1 and getattr(b, "raw_keys", None) is not None:
+            # the nested workload's own wire format: one borsh(StorageProofInput) per group (types.rs:11-19)
+            e2e = e2e_from_storage_borsh(a, ver, b, env, dev, st, voff, vlen, a.steps)
         else:
             e2e = dict(e2e_csr, note="nested / multi-pass workload: StorageProofInput groups have no single-blob MerkleProofInput form, "
                                      "so the end-to-end leg runs from the flattened CSR batch in pinned host memory")

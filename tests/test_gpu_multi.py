@@ -80,6 +80,14 @@ def test_one_context_two_devices_matches_one_device(verifier):
     h1 = verifier.verify_batch_hashed_keys(acc, flags)
     h2 = two.verify_batch_hashed_keys(acc, flags)
     assert all((x == y).all() for x, y in zip(h1, h2)) and (h2[0] == 0).all()
+    # the storage guest's wire format over two devices (inputs cut by bytes at input boundaries)
+    state, tokens = gen.make_state_and_tokens(100_000, 3, 10_000, seed=3)
+    nb = gen.nested_batch(state, tokens, 8_000, seed=9, raw_keys=True)
+    sblobs, soff, gf = gen.batch_to_storage_borsh(nb)
+    two.set_option("borsh_chunk_bytes", 1 << 20)
+    r1 = verifier.verify_storage_borsh(sblobs, soff)
+    r2 = two.verify_storage_borsh(sblobs, soff)
+    assert all((x == y).all() for x, y in zip(r1, r2)) and (r2[0] == gf).all() and len(set(r2[2].tolist())) >= 5
     two.close()
 
 

@@ -150,3 +150,25 @@ def test_storage_borsh_malformed_blobs_fail_the_call(verifier, oracle):
     pf, ist, st, _, _ = verifier.verify_storage_borsh(blobs)  # the context stays usable
     assert len(st) == int(pf[-1])
     assert verifier.verify_storage_borsh([])[0].tolist() == [0]
+
+
+def test_storage_borsh_stream_at_scale_equals_the_csr_batch(verifier):
+    """the nested synthetic workload (config 3 shape: 80 / 10 / 10, all mutators) written out as StorageProofInput blobs
+    and streamed back in gives, proof for proof, what the flattened batch gives through mptv_verify_batch"""
+    from workload import gen
+    state, tokens = gen.make_state_and_tokens(200_000, 3, 20_000, seed=3)
+    nb = gen.nested_batch(state, tokens, 20_000, seed=9, raw_keys=True)
+    blobs, off, gf = gen.batch_to_storage_borsh(nb)
+    st, voff, vlen = verifier.verify_batch(nb)
+    assert len(set(st.tolist())) >= 5
+    for chunk in (1 << 20, 32 << 20):
+        verifier.set_option("borsh_chunk_bytes", chunk)
+        pf, ist, bst, bvoff, bvlen = verifier.verify_storage_borsh(blobs, off)
+        assert (pf == gf).all() and (bst == st).all() and (bvlen == vlen).all()
+        for i in np.nonzero(bst == 0)[0][::13]:
+            assert blobs[int(bvoff[i]):int(bvoff[i]) + int(bvlen[i])].tobytes() == nb.value(int(voff[i]), int(vlen[i]))
+        for g in range(0, len(gf) - 1, 7):
+            assert int(ist[g]) == next((int(s) for s in st[int(gf[g]):int(gf[g + 1])] if s), 0)
+    verifier.set_option("borsh_chunk_bytes", 32 << 20)
+    hs = verifier.host_stats()
+    assert hs.nodes_aliased > 0

@@ -34,7 +34,10 @@ def lib():
         L.mptgen_trie_entry.restype = ctypes.c_uint32
         L.mptgen_trie_entry.argtypes = [vp, u64, vp, vp]
         L.mptgen_proofs_plan.argtypes = [vp, vp, vp, u64, u64, vp, vp, i32]
-        L.mptgen_proofs_emit.argtypes = [vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, i32]
+        L.mptgen_proofs_emit.argtypes = [vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
+        L.mptgen_trie_raw_keys.argtypes = [vp, i32]
+        L.mptgen_csr_to_storage_borsh.restype = u64
+        L.mptgen_csr_to_storage_borsh.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, i32]
         L.mptgen_keccak256.argtypes = [vp, u64, vp]
         L.mptgen_csr_to_borsh.restype = u64
         L.mptgen_csr_to_borsh.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, i32]
@@ -87,11 +90,17 @@ class SynthTrie:
                                  bc.ctypes.data, _threads())
         return nc, bc
 
-    def emit(self, sel, mut, seed2, slot, proof_first, byte_first, node_bytes, node_off, node_len, roots, keys32):
+    def emit(self, sel, mut, seed2, slot, proof_first, byte_first, node_bytes, node_off, node_len, roots, keys32, raw32=None):
         lib().mptgen_proofs_emit(self.h, sel.ctypes.data, mut.ctypes.data, len(sel), seed2,
                                  None if slot is None else slot.ctypes.data, proof_first.ctypes.data,
                                  byte_first.ctypes.data, node_bytes.ctypes.data, node_off.ctypes.data,
-                                 node_len.ctypes.data, roots.ctypes.data, keys32.ctypes.data, _threads())
+                                 node_len.ctypes.data, roots.ctypes.data, keys32.ctypes.data, _threads(),
+                                 None if raw32 is None else raw32.ctypes.data)
+
+    def set_raw_keys(self, on: bool = True):
+        """storage tries: every proof key gets a pre-image (an absent / wrong key is keccak(32 random bytes) instead of
+        32 random bytes), so that the batch has a StorageProofInput wire form; set before plan / emit"""
+        lib().mptgen_trie_raw_keys(self.h, 1 if on else 0)
 
 
 def _alloc(n, dtype, pinned):
@@ -120,8 +129,9 @@ def draw_mix(rng: np.random.Generator, n: int, p_excl: float, p_mut: float, n_ke
     return sel, mut
 
 
-def _assemble(parts, n_proofs, rfp, pinned):
-    """parts: list of (trie, sel, mut, seed2, slot u64[]) covering every proof slot exactly once."""
+def _assemble(parts, n_proofs, rfp, pinned, raw_keys=False):
+    """parts: list of (trie, sel, mut, seed2, slot u64[]) covering every proof slot exactly once.
+    raw_keys: also keep every key's pre-image (batch.raw_keys u8[32 n]: the storage slot; for an account proof its key)."""
     import zk_state_proofs_b200 as z
     nc_all = np.zeros(n_proofs, np.uint32)
     bc_all = np.zeros(n_proofs, np.uint64)
@@ -139,15 +149,19 @@ def _assemble(parts, n_proofs, rfp, pinned):
     node_len = _alloc(n_nodes, np.uint32, pinned)
     roots = _alloc(32 * n_proofs, np.uint8, pinned)
     keys = _alloc(32 * n_proofs + 16, np.uint8, pinned)
+    raw = np.zeros(32 * n_proofs, np.uint8) if raw_keys else None
     for trie, sel, mut, seed2, slot in parts:
-        trie.emit(sel, mut, seed2, slot, proof_first, byte_first, node_bytes, node_off, node_len, roots, keys)
+        trie.emit(sel, mut, seed2, slot, proof_first, byte_first, node_bytes, node_off, node_len, roots, keys, raw)
     key_off = _alloc(n_proofs + 1, np.uint32, pinned)
     key_off[:] = np.arange(n_proofs + 1, dtype=np.uint32) * 32
     r = None
     if rfp is not None:
         r = _alloc(n_proofs, np.int32, pinned)
         r[:] = rfp
-    return z.Batch(node_bytes, node_off, node_len, proof_first, roots, keys, key_off, r, None)
+    b = z.Batch(node_bytes, node_off, node_len, proof_first, roots, keys, key_off, r, None)
+    if raw_keys:
+        b.raw_keys = raw
+    return b
 
 
 def account_batch(trie: SynthTrie, n_proofs: int, seed: int, p_excl: float = 0.0, p_mut: float = 0.0,
@@ -163,9 +177,12 @@ def account_batch(trie: SynthTrie, n_proofs: int, seed: int, p_excl: float = 0.0
 
 
 def nested_batch(state: SynthTrie, tokens, n_groups: int, seed: int, k_storage: int = 3, p_excl: float = 0.10,
-                 p_mut: float = 0.10, pinned: bool = False):
+                 p_mut: float = 0.10, pinned: bool = False, raw_keys: bool = False):
     """config 3: groups of (1 account proof + k storage proofs whose root is the account's
-    storage_root).  `state` must have been built with pool_roots = [t.root for t in tokens]."""
+    storage_root).  `state` must have been built with pool_roots = [t.root for t in tokens].
+    raw_keys: the storage keys keep their pre-images (batch.raw_keys), see SynthTrie.set_raw_keys -> batch_to_storage_borsh."""
+    for tok in tokens:
+        tok.set_raw_keys(raw_keys)
     rng = np.random.default_rng(seed)
     P = len(tokens)
     G = 1 + k_storage
@@ -190,7 +207,7 @@ def nested_batch(state: SynthTrie, tokens, n_groups: int, seed: int, k_storage: 
     base = (np.arange(n_groups, dtype=np.int32) * G)
     for j in range(1, G):
         rfp[base + j] = base
-    return _assemble(parts, n, rfp, pinned)
+    return _assemble(parts, n, rfp, pinned, raw_keys)
 
 
 def mixed_batch(state: SynthTrie, tokens, n_proofs: int, seed: int, p_mut: float = 0.02, pinned: bool = False):
@@ -257,3 +274,23 @@ def batch_to_borsh(b, pinned: bool = False):
     blobs = _alloc(total + 16, np.uint8, pinned)
     L.mptgen_csr_to_borsh(*args, blobs.ctypes.data, _threads())
     return blobs[:total], off
+
+
+def batch_to_storage_borsh(b, pinned: bool = False):
+    """A nested CSR batch made with raw_keys=True as borsh(StorageProofInput) blobs (crypto-ops/src/types.rs:11-19), one per
+    group -- the storage guest's input (storage-circuit/src/main.rs:6-9); input of mptv_verify_storage_borsh.
+    -> (blobs u8[], blob_off u64[n_groups + 1], group_first u64[n_groups + 1])"""
+    L = lib()
+    n = b.n_proofs
+    gf = np.zeros(n + 1, np.uint64)
+    off = np.zeros(n + 1, np.uint64)
+    ng = ctypes.c_uint64()
+    rfp = np.ascontiguousarray(b.root_from_proof, np.int32)
+    args = [b.node_bytes.ctypes.data, b.node_off.ctypes.data, b.node_len.ctypes.data, b.proof_first.ctypes.data, n,
+            b.roots.ctypes.data, b.key_bytes.ctypes.data, b.raw_keys.ctypes.data, rfp.ctypes.data, gf.ctypes.data,
+            ctypes.byref(ng), off.ctypes.data]
+    total = int(L.mptgen_csr_to_storage_borsh(*args, None, 1))
+    blobs = _alloc(total + 16, np.uint8, pinned)
+    L.mptgen_csr_to_storage_borsh(*args, blobs.ctypes.data, _threads())
+    g = int(ng.value)
+    return blobs[:total], off[:g + 1].copy(), gf[:g + 1].copy()

@@ -135,6 +135,10 @@ struct Trie {
   Part p;
   uint32_t root = NONE;
   H256 root_hash;
+  // storage tries (kind 1): every proof key has a pre-image, as the wire form of the nested workload needs
+  // (StorageProofInput carries RAW storage keys, the guest hashes them): the key of an absent / wrong-key proof is
+  // keccak(32 random bytes) instead of 32 random bytes -- the same distribution
+  bool raw_keys = false;
 };
 
 inline int nib(const H256& k, int i) { return (i & 1) ? (k[i >> 1] & 15) : (k[i >> 1] >> 4); }
@@ -328,20 +332,25 @@ void build_trie(Trie& t, int nthreads) {
 }
 
 // key of ORIGINAL index i
-void make_key(const Trie& t, uint64_t i, H256& out) {
+// the storage slot of ORIGINAL index i: keccak(pad32(holder) || pad32(index)), the Solidity mapping layout
+void make_slot(const Trie& t, uint64_t i, uint8_t slot[32]) {
   SplitMix r(mix(t.seed, i));
+  uint8_t pre[64] = {0};
+  r.fill(pre + 12, 20);
+  pre[63] = (uint8_t)(t.seed & 7);
+  keccak256(pre, 64, slot);
+}
+
+void make_key(const Trie& t, uint64_t i, H256& out) {
   if (t.kind == 0) {
+    SplitMix r(mix(t.seed, i));
     uint8_t addr[20];
     r.fill(addr, 20);
     keccak256(addr, 20, out.data());  // account.rs:54  key = keccak(address)
   } else {
-    // Solidity mapping slot keccak(pad32(holder) || pad32(index)); trie key = keccak(slot)
-    uint8_t pre[64] = {0};
-    r.fill(pre + 12, 20);
-    pre[63] = (uint8_t)(t.seed & 7);
     uint8_t slot[32];
-    keccak256(pre, 64, slot);
-    keccak256(slot, 32, out.data());  // tests/storage.rs:78 digest_keccak(slot)
+    make_slot(t, i, slot);
+    keccak256(slot, 32, out.data());  // tests/storage.rs:78 digest_keccak(slot): trie key = keccak(slot)
   }
 }
 
@@ -384,9 +393,22 @@ void walk(const Trie& t, const H256& key, Path& out) {
   }
 }
 
-void proof_key(const Trie& t, int64_t sel, uint64_t seed2, uint64_t i, H256& key) {
-  if (sel >= 0) key = t.keys[t.src_pos[(uint32_t)sel]];
-  else { SplitMix r(mix(seed2 ^ 0xabcdef, i)); r.fill(key.data(), 32); }  // absent w.h.p.
+// raw (may be null): the key's pre-image when the trie keeps one (Trie::raw_keys), else a copy of the key
+void proof_key(const Trie& t, int64_t sel, uint64_t seed2, uint64_t i, H256& key, uint8_t* raw = nullptr) {
+  const bool pre = t.raw_keys && t.kind == 1;
+  if (sel >= 0) {
+    key = t.keys[t.src_pos[(uint32_t)sel]];
+    if (raw) { if (pre) make_slot(t, (uint64_t)sel, raw); else memcpy(raw, key.data(), 32); }
+    return;
+  }
+  SplitMix r(mix(seed2 ^ 0xabcdef, i));
+  r.fill(key.data(), 32);  // absent w.h.p.
+  if (pre) {
+    uint8_t slot[32];
+    memcpy(slot, key.data(), 32);
+    keccak256(slot, 32, key.data());
+    if (raw) memcpy(raw, slot, 32);
+  } else if (raw) memcpy(raw, key.data(), 32);
 }
 
 inline uint32_t pad16(uint32_t n) { return (n + 15u) & ~15u; }
@@ -399,8 +421,8 @@ struct Emit {  // one proof after mutation: list of (source bytes, len) + flips 
   bool wrong_key = false;
 };
 
-void plan_one(const Trie& t, int64_t sel, uint8_t mut, uint64_t seed2, uint64_t i, Emit& e, H256& key) {
-  proof_key(t, sel, seed2, i, key);
+void plan_one(const Trie& t, int64_t sel, uint8_t mut, uint64_t seed2, uint64_t i, Emit& e, H256& key, uint8_t* raw = nullptr) {
+  proof_key(t, sel, seed2, i, key, raw);
   Path p;
   walk(t, key, p);
   e.n = p.n;
@@ -415,7 +437,16 @@ void plan_one(const Trie& t, int64_t sel, uint8_t mut, uint64_t seed2, uint64_t 
       break;
     case MUT_DROP_LAST: if (e.n) e.n--; break;
     case MUT_DROP_ROOT: if (e.n) { memmove(e.ids, e.ids + 1, sizeof(uint32_t) * (e.n - 1)); e.n--; } break;
-    case MUT_WRONG_KEY: e.wrong_key = true; r.fill(key.data(), 32); break;
+    case MUT_WRONG_KEY:
+      e.wrong_key = true;
+      r.fill(key.data(), 32);
+      if (t.raw_keys && t.kind == 1) {
+        uint8_t slot[32];
+        memcpy(slot, key.data(), 32);
+        keccak256(slot, 32, key.data());
+        if (raw) memcpy(raw, slot, 32);
+      } else if (raw) memcpy(raw, key.data(), 32);
+      break;
     case MUT_SHUFFLE:
       for (uint32_t k = e.n; k > 1; k--) { uint32_t j = (uint32_t)(r.next() % k); std::swap(e.ids[k - 1], e.ids[j]); }
       break;
@@ -513,13 +544,13 @@ int mptgen_proofs_plan(void* h, const int64_t* sel, const uint8_t* mut, uint64_t
 int mptgen_proofs_emit(void* h, const int64_t* sel, const uint8_t* mut, uint64_t n, uint64_t seed2,
                        const uint64_t* slot, const uint32_t* proof_first, const uint64_t* byte_first,
                        uint8_t* node_bytes, uint64_t* node_off, uint32_t* node_len, uint8_t* roots,
-                       uint8_t* keys32, int nthreads) {
+                       uint8_t* keys32, int nthreads, uint8_t* raw32 /* may be NULL: the keys' pre-images (mptgen_trie_raw_keys) */) {
   Trie* t = (Trie*)h;
   parallel_for(n, nthreads, [&](uint64_t lo, uint64_t hi) {
     for (uint64_t i = lo; i < hi; i++) {
       Emit e; H256 key;
-      plan_one(*t, sel[i], mut ? mut[i] : 0, seed2, i, e, key);
       const uint64_t s = slot ? slot[i] : i;
+      plan_one(*t, sel[i], mut ? mut[i] : 0, seed2, i, e, key, raw32 ? raw32 + 32 * s : nullptr);
       uint32_t ni = proof_first[s];
       uint64_t bo = byte_first[s];
       for (uint32_t k = 0; k < e.n; k++) {
@@ -541,6 +572,67 @@ int mptgen_proofs_emit(void* h, const int64_t* sel, const uint8_t* mut, uint64_t
 }
 
 void mptgen_keccak256(const uint8_t* in, uint64_t len, uint8_t out[32]) { keccak256(in, len, out); }
+
+// storage tries: from now on every proof key has a pre-image (see Trie::raw_keys); set before plan / emit
+void mptgen_trie_raw_keys(void* h, int on) { ((Trie*)h)->raw_keys = on != 0; }
+
+// Nested CSR batch -> borsh(StorageProofInput) blobs (crypto-ops/src/types.rs:11-19), one per group: a proof with
+// root_from_proof == -1 is an input's account proof (key = address_keccak, root = root_hash), the proofs behind it
+// that name it are its storage proofs, raw32 holds their un-hashed storage keys.  account_key is left empty (the
+// guest never reads it).  group_first [n_groups + 1] (proof index of every account proof) and blob_off
+// [n_groups + 1] are written first (blobs == NULL: returns the total size), then the blobs, multi-threaded.
+uint64_t mptgen_csr_to_storage_borsh(const uint8_t* node_bytes, const uint64_t* node_off, const uint32_t* node_len,
+                                     const uint32_t* proof_first, uint64_t n_proofs, const uint8_t* roots,
+                                     const uint8_t* keys32, const uint8_t* raw32, const int32_t* rfp, uint64_t* group_first,
+                                     uint64_t* n_groups_out, uint64_t* blob_off, uint8_t* blobs, int n_threads) {
+  uint64_t g = 0;
+  for (uint64_t p = 0; p < n_proofs; p++)
+    if (rfp[p] < 0) group_first[g++] = p;
+  group_first[g] = n_proofs;
+  *n_groups_out = g;
+  blob_off[0] = 0;
+  for (uint64_t i = 0; i < g; i++) {
+    const uint64_t a = group_first[i], e = group_first[i + 1];
+    uint64_t sz = 4 + 4 + (4 + 32) + 4 + 4 + 32;  // account count, storage count, root_hash, account_key (empty), key count, address_keccak
+    for (uint64_t p = a; p < e; p++) {
+      if (p > a) sz += 4 + (4 + 32);  // the proof's node count, its key
+      for (uint32_t k = proof_first[p]; k < proof_first[p + 1]; k++) sz += 4 + (uint64_t)node_len[k];
+    }
+    blob_off[i + 1] = blob_off[i] + sz;
+  }
+  if (!blobs) return blob_off[g];
+  auto put32 = [](uint8_t* q, uint32_t v) { q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16); q[3] = (uint8_t)(v >> 24); };
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  std::vector<std::thread> th;
+  const uint64_t per = (g + n_threads - 1) / n_threads;
+  for (int t = 0; t < n_threads; t++) {
+    const uint64_t lo = std::min(g, per * t), hi = std::min(g, lo + per);
+    if (lo >= hi) continue;
+    th.emplace_back([=] {
+      auto put_proof = [&](uint8_t*& q, uint64_t p) {
+        put32(q, proof_first[p + 1] - proof_first[p]); q += 4;
+        for (uint32_t k = proof_first[p]; k < proof_first[p + 1]; k++) {
+          put32(q, node_len[k]); q += 4;
+          memcpy(q, node_bytes + node_off[k], node_len[k]); q += node_len[k];
+        }
+      };
+      for (uint64_t i = lo; i < hi; i++) {
+        const uint64_t a = group_first[i], e = group_first[i + 1];
+        uint8_t* q = blobs + blob_off[i];
+        put_proof(q, a);
+        put32(q, (uint32_t)(e - a - 1)); q += 4;
+        for (uint64_t p = a + 1; p < e; p++) put_proof(q, p);
+        put32(q, 32); q += 4; memcpy(q, roots + 32 * a, 32); q += 32;
+        put32(q, 0); q += 4;  // account_key
+        put32(q, (uint32_t)(e - a - 1)); q += 4;
+        for (uint64_t p = a + 1; p < e; p++) { put32(q, 32); q += 4; memcpy(q, raw32 + 32 * p, 32); q += 32; }
+        memcpy(q, keys32 + 32 * a, 32);
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  return blob_off[g];
+}
 
 // CSR batch -> borsh(MerkleProofInput) blobs, as a prover's input file holds them (crypto-ops/src/types.rs:4-9:
 // u32-LE count / length prefixes).  blob_off [n + 1] is written first (call with blobs == NULL to size the
