@@ -744,8 +744,8 @@ def e2e_from_storage_borsh(a, ver, b, env, dev, st, voff, vlen, steps):
                 transfer_dedup=dict(nodes=int(hs.nodes / steps), nodes_aliased=int(hs.nodes_aliased / steps),
                                     node_bytes_supplied=int(hs.node_bytes_supplied / steps),
                                     node_bytes_placed=int(hs.node_bytes_placed / steps)),
-                host_ms=dict(flatten=hs.flatten_us / steps / 1e3, wait=hs.wait_us / steps / 1e3,
-                             map_results=hs.map_us / steps / 1e3, call=hs.call_us / steps / 1e3),
+                host_ms=dict(index_pass=hs.index_us / steps / 1e3, flatten=hs.flatten_us / steps / 1e3, wait=hs.wait_us / steps / 1e3,
+                             map_results=hs.map_us / steps / 1e3, stream=hs.call_us / steps / 1e3),
                 gpu_launches_per_step=int(launches),
                 note="storage keys cross PCIe un-hashed and are hashed on the device (digest_keccak(&key), main.rs:26); "
                      "storage roots are taken on the device from the verified account leaves")

@@ -148,7 +148,9 @@ int mptv_account_storage_root(const uint8_t* value, uint32_t len, uint8_t* stora
  *   proof_first[n_inputs + 1]  out: input i owns results [proof_first[i], proof_first[i+1]): its account proof first,
  *                              then its storage proofs in order.  Written by the first pass, before anything is verified.
  *   results_cap                entries the arrays of `out` hold.  Fewer than proof_first[n_inputs] (e.g. 0, to ask):
- *                              MPTV_ERR_NOMEM, with proof_first filled in.
+ *                              MPTV_ERR_NOMEM, with proof_first filled in and nothing verified.  A caller that built the
+ *                              blobs knows the count (the sum of 1 + min(storage_proofs.len(), storage_keys.len())) and
+ *                              needs one call.
  *   input_status[n_inputs]     out, may be NULL: MPTV_ST_OK (the guest commits the storage values), else the status of the
  *                              first proof that fails in the guest's order; an account leaf that is not
  *                              rlp([nonce, balance, storage_root, code_hash]) (decode_exact(..).unwrap(), main.rs:15) gives
@@ -173,6 +175,8 @@ typedef struct mptv_host_stats {
   uint64_t pull_chunks;           /* mptv_verify_borsh chunks whose node bytes the device fetched itself from
                                      page-locked blobs (h2d_bytes counts those bytes too)                    */
   uint64_t device_chunks;         /* mptv_verify_borsh chunks flattened on the device ("borsh_mode" 1)         */
+  uint64_t index_us;              /* mptv_verify_storage_borsh: the pass over the inputs' length prefixes that runs
+                                     before the stream (not part of call_us)                                 */
 } mptv_host_stats;
 int mptv_host_stats_get(mptv_ctx* ctx, mptv_host_stats* out, int reset);
 
@@ -407,7 +411,7 @@ MPTV_ABI_PIN(proofs_out_size, sizeof(mptv_proofs_out) == 64);
 MPTV_ABI_PIN(proofs_out_n_nodes, offsetof(mptv_proofs_out, n_nodes) == 48);
 MPTV_ABI_PIN(timings_size, sizeof(mptv_timings) == 64);
 MPTV_ABI_PIN(rebuild_timings_size, sizeof(mptv_rebuild_timings) == 64);
-MPTV_ABI_PIN(host_stats_size, sizeof(mptv_host_stats) == 112);
+MPTV_ABI_PIN(host_stats_size, sizeof(mptv_host_stats) == 120);
 MPTV_ABI_PIN(flatten_info_size, sizeof(mptv_flatten_info) == 32);
 MPTV_ABI_PIN(log_size, sizeof(mptv_log) == 40);
 #undef MPTV_ABI_PIN

@@ -100,7 +100,7 @@ def test_binding_structures_match_the_pinned_abi_layout():
     import ctypes
     from zk_state_proofs_b200 import crypto_ops as co
     sizes = dict(_CBatch=88, _CResult=24, _CKvBatch=72, _CProofTargets=32, _CProofsOut=64, Timings=64, RebuildTimings=64,
-                 HostStats=112, FlattenInfo=32, _CLog=40)
+                 HostStats=120, FlattenInfo=32, _CLog=40)
     for name, want in sizes.items():
         assert ctypes.sizeof(getattr(co, name)) == want, name
     assert [getattr(co._CBatch, f).offset for f, _ in co._CBatch._fields_] == [0, 8, 16, 24, 32, 40, 48, 56, 64, 72, 80]

@@ -169,6 +169,12 @@ def test_storage_borsh_stream_at_scale_equals_the_csr_batch(verifier):
             assert blobs[int(bvoff[i]):int(bvoff[i]) + int(bvlen[i])].tobytes() == nb.value(int(voff[i]), int(vlen[i]))
         for g in range(0, len(gf) - 1, 7):
             assert int(ist[g]) == next((int(s) for s in st[int(gf[g]):int(gf[g + 1])] if s), 0)
+    # a result capacity that is too small (the stream stops at the chunk that does not fit and reports the real count),
+    # exactly right, and too large
+    verifier.set_option("borsh_chunk_bytes", 1 << 20)
+    for cap in (5, nb.n_proofs // 2, nb.n_proofs, nb.n_proofs + 1000):
+        pf, ist, bst, bvoff, bvlen = verifier.verify_storage_borsh(blobs, off, n_proofs=cap)
+        assert (pf == gf).all() and len(bst) == nb.n_proofs and (bst == st).all() and (bvlen == vlen).all()
     verifier.set_option("borsh_chunk_bytes", 32 << 20)
     hs = verifier.host_stats()
-    assert hs.nodes_aliased > 0
+    assert hs.nodes_aliased > 0 and hs.index_us > 0

@@ -297,7 +297,7 @@ class HostStats(ctypes.Structure):
                 ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
                 ("flatten_us", ctypes.c_uint64), ("wait_us", ctypes.c_uint64), ("map_us", ctypes.c_uint64),
                 ("call_us", ctypes.c_uint64), ("launches", ctypes.c_uint64), ("pull_chunks", ctypes.c_uint64),
-                ("device_chunks", ctypes.c_uint64)]
+                ("device_chunks", ctypes.c_uint64), ("index_us", ctypes.c_uint64)]
 
 
 FLATTEN_ALIAS_DUPLICATES = 1
@@ -756,12 +756,18 @@ class Verifier:
             if rc != -4:  # MPTV_ERR_NOMEM: proof_first now holds the layout
                 self._check(rc, "mptv_verify_storage_borsh")
             n_proofs = int(pf[n])
-        status = np.zeros(n_proofs, np.uint8)
-        voff = np.zeros(n_proofs, np.uint64)
-        vlen = np.zeros(n_proofs, np.uint32)
-        cr = _CResult(_ptr(status), _ptr(voff), _ptr(vlen))
-        self._check(self.lib.mptv_verify_storage_borsh(*args, n_proofs, ctypes.byref(cr)), "mptv_verify_storage_borsh")
-        return pf, ist, status, voff, vlen
+        for attempt in range(2):
+            status = np.zeros(n_proofs, np.uint8)
+            voff = np.zeros(n_proofs, np.uint64)
+            vlen = np.zeros(n_proofs, np.uint32)
+            cr = _CResult(_ptr(status), _ptr(voff), _ptr(vlen))
+            rc = self.lib.mptv_verify_storage_borsh(*args, n_proofs, ctypes.byref(cr))
+            if rc == -4 and attempt == 0 and int(pf[n]) > n_proofs:  # the caller's count was too small: proof_first[n] is the real one
+                n_proofs = int(pf[n])
+                continue
+            self._check(rc, "mptv_verify_storage_borsh")
+            break
+        return pf, ist, status[:int(pf[n])], voff[:int(pf[n])], vlen[:int(pf[n])]
 
     def verify_storage_proof_inputs_borsh(self, inputs: Sequence[StorageProofInput]):
         """verify_storage_proof_inputs through the wire format: the inputs are serialised as the prover would write them

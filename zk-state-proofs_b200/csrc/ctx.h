@@ -138,7 +138,7 @@ struct Device {
   DevBuf digests, meta, order, bins, defer, dedup;  // scratch of the device-resident entry
   uint64_t last_unique_nodes = 0, last_unique_perm = 0;  // of the last dedup_nodes run
   Slot slot[kSlotsTotal];
-  mptv_host_stats hstat2 = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // of the second pipeline's thread (hybrid mode); summed on read
+  mptv_host_stats hstat2 = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // of the second pipeline's thread (hybrid mode); summed on read
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaStream_t last_stream = nullptr;
   bool have_timing = false;
@@ -150,7 +150,7 @@ struct Device {
   uint8_t* mb_dev = nullptr;
   uint32_t mb_seq = 0;
   DedupTable dedup_tab;  // host-side candidate table of the streamed borsh entry (one chunk at a time)
-  mptv_host_stats hstat = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // of the host-fed entries since the last reset
+  mptv_host_stats hstat = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // of the host-fed entries since the last reset
 };
 
 }  // namespace mptv
