@@ -40,6 +40,8 @@ extern "C" {
     fn mptv_verify_batch(ctx: *mut MptvCtx, input: *const MptvBatch, out: *mut MptvResult) -> c_int;
     fn mptv_verify_batch_hashed_keys(ctx: *mut MptvCtx, input: *const MptvBatch, hash_key: *const u8, out: *mut MptvResult) -> c_int;
     fn mptv_verify_borsh(ctx: *mut MptvCtx, blobs: *const u8, blob_off: *const u64, n: u64, n_threads: c_int, out: *mut MptvResult) -> c_int;
+    fn mptv_verify_storage_borsh(ctx: *mut MptvCtx, blobs: *const u8, blob_off: *const u64, n_inputs: u64, n_threads: c_int,
+                                 proof_first: *mut u64, input_status: *mut u8, results_cap: u64, out: *mut MptvResult) -> c_int;
     fn mptv_flatten_borsh(blobs: *const u8, blob_off: *const u64, n: u64, n_threads: c_int, pinned: c_int, out: *mut *mut MptvHostBatch) -> c_int;
     fn mptv_host_batch_view(hb: *const MptvHostBatch) -> *const MptvBatch;
     fn mptv_host_batch_bad_root(hb: *const MptvHostBatch) -> *const u8;
@@ -126,6 +128,40 @@ impl Verifier {
                 Some(e) => Err(e),
             })
             .collect()
+    }
+
+    /// The storage guest (storage-circuit/src/main.rs:6-31) over inputs that exist as borsh(StorageProofInput) bytes:
+    /// per input the committed storage values, or what the guest would have panicked with.  `n_proofs` = the sum over the
+    /// inputs of 1 + min(storage_proofs.len(), storage_keys.len()) when the caller knows it (else 0: one sizing call more).
+    pub fn verify_storage_borsh_blobs(&mut self, blobs: &[u8], off: &[u64], n_proofs: usize) -> Vec<Result<Vec<Vec<u8>>, VerifyError>> {
+        let n = off.len().saturating_sub(1);
+        if n == 0 {
+            return Vec::new();
+        }
+        let mut first = vec![0u64; n + 1];
+        let mut ist = vec![0u8; n];
+        let mut cap = n_proofs;
+        loop {
+            let (mut status, mut voff, mut vlen) = (vec![0u8; cap], vec![0u64; cap], vec![0u32; cap]);
+            let mut res = MptvResult { status: status.as_mut_ptr(), value_off: voff.as_mut_ptr(), value_len: vlen.as_mut_ptr() };
+            let rc = unsafe {
+                mptv_verify_storage_borsh(self.ctx, blobs.as_ptr(), off.as_ptr(), n as u64, 0, first.as_mut_ptr(), ist.as_mut_ptr(),
+                                          cap as u64, &mut res)
+            };
+            if rc == -4 && first[n] as usize > cap {
+                cap = first[n] as usize; // MPTV_ERR_NOMEM: proof_first holds the layout, nothing was verified
+                continue;
+            }
+            assert_eq!(rc, 0, "mptv_verify_storage_borsh failed (malformed borsh?)");
+            return (0..n)
+                .map(|i| match VerifyError::from_status(ist[i]) {
+                    Some(e) => Err(e),
+                    None => Ok((first[i] as usize + 1..first[i + 1] as usize)
+                        .map(|p| blobs[voff[p] as usize..voff[p] as usize + vlen[p] as usize].to_vec())
+                        .collect()),
+                })
+                .collect();
+        }
     }
 
     /// `root_from_proof[p] = d >= 0`: proof p is verified under the storage_root of the account returned by the
