@@ -226,6 +226,8 @@ int mptv_int_issue_peak(mptv_ctx* ctx, int dev_index, int mode, double* lane_ops
  *                      read them a second time.  Default 0: on the measured hosts the kernel's small PCIe reads reach
  *                      30 GB/s against the copy engine's 55 and slow the flattening threads down (71 vs 50 ms per
  *                      million config-2 proofs, profiles/r02_borsh_pull_quick.txt)
+ *   "wc_staging"       mptv_verify_borsh / mptv_verify_storage_borsh stage the node bytes of a chunk in write-combining
+ *                      page-locked memory (default 0: no measurable gain on the measured hosts, profiles/r02_wc_staging_probe.txt)
  *   "host_dedup"       mptv_verify_borsh aliases byte-identical nodes of a chunk instead of staging and copying them
  *                      again (default 1).  Transfer de-duplication only: every supplied node is still hashed on the
  *                      device, results are identical

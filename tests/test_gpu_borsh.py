@@ -178,3 +178,33 @@ def test_device_flatten_mode(verifier, golden, oracle, chunk_bytes, lead):
     finally:
         verifier.set_option("borsh_mode", 0)
         verifier.set_option("borsh_chunk_bytes", 32 << 20)
+
+
+@pytest.mark.parametrize("chunk_bytes", [1 << 12, 1 << 20])
+def test_write_combining_staging_gives_identical_results(verifier, golden, oracle, chunk_bytes):
+    """"wc_staging": the chunk's node bytes are staged in write-combining page-locked memory (a block of their own, the
+    index arrays stay where the result mapping can read them): same verdicts, same value slices, both streams"""
+    import zk_state_proofs_b200 as z
+    from oracle.fuzzgen import corpus
+    from tests.test_gpu_storage_borsh import _inputs
+    vs = golden["vectors"]
+    blobs = [z.MerkleProofInput(v["proof_b"], v["root_b"], v["key_b"]).to_borsh() for v in vs]
+    blobs += [z.MerkleProofInput(c["proof"], c["root"], c["key"]).to_borsh() for c in corpus(99, oracle.keccak256, 30, 1500, 2000, 1200, 1500, 600)]
+    buf, off = _concat(blobs)
+    sblobs = [i.to_borsh() for i in _inputs(oracle, 5, 300)]
+    verifier.set_option("borsh_chunk_bytes", chunk_bytes)
+    try:
+        for dd in (1, 0):
+            verifier.set_option("host_dedup", dd)
+            verifier.set_option("wc_staging", 0)
+            want = verifier.verify_borsh(buf, off, threads=4)
+            swant = verifier.verify_storage_borsh(sblobs, threads=3)
+            verifier.set_option("wc_staging", 1)
+            got = verifier.verify_borsh(buf, off, threads=4)
+            sgot = verifier.verify_storage_borsh(sblobs, threads=3)
+            assert all((x == y).all() for x, y in zip(got, want)) and all((x == y).all() for x, y in zip(sgot, swant))
+            assert len(set(want[0].tolist())) >= 6
+    finally:
+        verifier.set_option("wc_staging", 0)
+        verifier.set_option("host_dedup", 1)
+        verifier.set_option("borsh_chunk_bytes", 32 << 20)

@@ -35,11 +35,12 @@ struct DevBuf {
 struct HostBuf {  // page-locked staging (an async copy from / into pageable memory would stall the pipeline)
   void* p = nullptr;
   size_t cap = 0;
+  unsigned flags = cudaHostAllocDefault;  // cudaHostAllocWriteCombined: written once with streaming stores, never read by the cores
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
     if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
     size_t want = n + n / 8 + 256;
-    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(&p, want, flags);
     if (e == cudaSuccess) cap = want;
     return e;
   }
@@ -53,6 +54,7 @@ struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;  // streamed borsh entry: the slot's chunk is through the device (blocking-sync event)
   HostBuf h_results, h_in;
+  HostBuf h_wc;  // streamed borsh entry, "wc_staging": the byte regions of the chunk in write-combining memory (h_in keeps the index arrays)
   uint64_t pend_p0 = 0, pend_np = 0;  // results of this proof range are in flight into the staging buffers
   // streamed borsh entry: the chunk was flattened into h_in; these locate its index arrays there, node_src maps
   // each node back to its position in the caller's blobs (results are reported as offsets into the blobs)
@@ -74,7 +76,7 @@ struct Slot {
                      &results, &in_pack, &digests, &meta, &order, &bins, &defer, &dedup, &hk_flags, &hk_off, &hk_len,
                      &f_img, &f_off, &f_nodes, &f_bytes, &f_flags, &f_node_first, &f_byte_first, &f_totals};
     for (DevBuf* b : all) b->release();
-    h_results.release(); h_in.release(); f_h_off.release(); f_h_totals.release();
+    h_results.release(); h_in.release(); h_wc.release(); f_h_off.release(); f_h_totals.release();
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
     if (f_counted) cudaEventDestroy(f_counted);
@@ -170,6 +172,7 @@ struct mptv_ctx {
   int hybrid_device_pct = 24;  // borsh_mode 2: share of a device's blob bytes its device-flatten pipeline may take
   int pull_pinned = 0;     // streamed borsh entry, page-locked blobs: the device gathers the placed node bytes itself (measured slower: off)
   int host_dedup = 1;      // streamed borsh entry: alias byte-identical nodes of a chunk instead of copying them again
+  int wc_staging = 0;      // streamed borsh entry: stage the node bytes in write-combining page-locked memory (no cache snoops by the DMA reads)
   int latency_path = 1;    // batches that fit one CTA: one launch, mapped page-locked memory both ways (single_kernels.cu)
   int fast_walk = 1;       // K2f decides chain-shaped proofs one thread each; K2b gets the deferred rest
   int long_leaf_bin = mptv::kLongLeafBin;  // rebuild: leaves in rate-block bins >= this are hashed in their own launch ...

@@ -119,6 +119,10 @@ struct ChunkLayout {
   bool groups = false;
   size_t o_rfp = 0, o_hk = 0, o_hkoff = 0, o_hklen = 0, o_hashed = 0;
   std::vector<size_t> region_begin, region_used;  // per worker: its byte region and how much of it was written
+  // The byte regions may live in a host block of their own (write-combining staging): then get_block sets this to that
+  // block's address MINUS index_end, so that region offsets stay offsets of the one device pack.  Null: the regions
+  // follow the index arrays in the block get_block returned.
+  uint8_t* region_base = nullptr;
   // statistics of the build
   uint64_t node_bytes_supplied = 0;  // sum of the padded lengths of all supplied nodes
   uint64_t node_bytes_placed = 0;    // ... of those actually written (the rest are aliases)
@@ -321,7 +325,7 @@ int flatten_borsh_chunk(WorkerPool& pool, const BorshChunkJob& job, GetBlock get
     uint32_t* key_len = reinterpret_cast<uint32_t*>(block + L.o_klen);
     uint8_t* roots = block + L.o_roots;
     RegionWriter w;  // on my stack: the cursor and counters change with every node (no false sharing)
-    w.base = block; w.at = L.region_begin[t]; w.end = w.at + up64z(tot[t].bound); w.table = job.table;
+    w.base = L.region_base ? L.region_base : block; w.at = L.region_begin[t]; w.end = w.at + up64z(tot[t].bound); w.table = job.table;
     GatherRec* rec_end = nullptr;
     if (job.pull) {
       uint64_t r0 = 0;
@@ -395,8 +399,8 @@ int flatten_borsh_chunk(WorkerPool& pool, const BorshChunkJob& job, GetBlock get
     if (job.pull) {
       for (; w.rec < rec_end; w.rec++) { w.rec->src = 0; w.rec->dst16 = 0; w.rec->len = kGatherUnused; }  // aliased nodes left these free
     } else {
-      if (w.table) { static const uint8_t z16[16] = {0}; w.put_bytes(block + w.at, z16, 16); }  // K1 stages whole 16-byte chunks:
-      else memset(block + w.at, 0, 16);                                                        // the bytes after my last node must be readable
+      if (w.table) { static const uint8_t z16[16] = {0}; w.put_bytes(w.base + w.at, z16, 16); }  // K1 stages whole 16-byte chunks:
+      else memset(w.base + w.at, 0, 16);                                                        // the bytes after my last node must be readable
     }
     w.at += 16;
     w.finish();
@@ -604,7 +608,7 @@ int flatten_storage_chunk(WorkerPool& pool, const StorageChunkJob& job, GetBlock
     uint8_t* hk = block + L.o_hk;
     uint8_t* roots = block + L.o_roots;
     RegionWriter w;
-    w.base = block; w.at = L.region_begin[t]; w.end = w.at + up64z(bound[t]); w.table = job.table;
+    w.base = L.region_base ? L.region_base : block; w.at = L.region_begin[t]; w.end = w.at + up64z(bound[t]); w.table = job.table;
     auto look_ahead = [&](const uint8_t* q, const uint8_t* end) -> uint64_t {
       if (!job.table || end - q < 4) return 0;
       const uint32_t len = rd_u32(q);
@@ -685,8 +689,8 @@ int flatten_storage_chunk(WorkerPool& pool, const StorageChunkJob& job, GetBlock
       key_off[acc] = job.key_off_16 ? (uint32_t)(ako >> 4) : (uint32_t)ako;
       key_len[acc] = 32;
     }
-    if (w.table) { static const uint8_t z16[16] = {0}; w.put_bytes(block + w.at, z16, 16); }
-    else memset(block + w.at, 0, 16);
+    if (w.table) { static const uint8_t z16[16] = {0}; w.put_bytes(w.base + w.at, z16, 16); }
+    else memset(w.base + w.at, 0, 16);
     w.at += 16;
     w.finish();
     _mm_sfence();

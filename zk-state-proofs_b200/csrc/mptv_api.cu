@@ -228,6 +228,8 @@ int mptv_set_option(mptv_ctx* ctx, const char* name, int64_t value) {
     ctx->hybrid_device_pct = (int)value;
   } else if (!strcmp(name, "pull_pinned")) {
     ctx->pull_pinned = value ? 1 : 0;
+  } else if (!strcmp(name, "wc_staging")) {
+    ctx->wc_staging = value ? 1 : 0;
   } else if (!strcmp(name, "host_dedup")) {
     ctx->host_dedup = value ? 1 : 0;
   } else if (!strcmp(name, "latency_path")) {
@@ -750,14 +752,24 @@ int submit_borsh_chunk(mptv_ctx* ctx, Device& d, Slot& s, const ChunkLayout& L, 
     CK(launch_gather(blobs_dev, dv, reinterpret_cast<const uint4*>(dv + L.o_gather), (uint32_t)L.n_gather, d.sm_count, st));
     moved = L.host_total + L.node_bytes_placed;  // what crosses PCIe: the block, and the bytes the kernel reads
     d.hstat.launches += 1; d.hstat.pull_chunks += 1;
-  } else
-  for (size_t t = 0; t <= L.region_begin.size(); t++) {
-    const bool last = t == L.region_begin.size();
-    if (!last && L.region_used[t] == 0) continue;
-    if (!last && L.region_begin[t] <= c1 + 4096) { c1 = L.region_begin[t] + L.region_used[t]; continue; }
-    CK(cudaMemcpyAsync(dv + c0, h + c0, c1 - c0, cudaMemcpyHostToDevice, st));
-    moved += c1 - c0;
-    if (!last) { c0 = L.region_begin[t]; c1 = c0 + L.region_used[t]; }
+  } else {
+    const uint8_t* src = h;  // where pack offset c0 lives on the host
+    if (L.region_base) {     // the regions have a block of their own: the index arrays go first, as a copy of their own
+      CK(cudaMemcpyAsync(dv, h, L.index_end, cudaMemcpyHostToDevice, st));
+      moved += L.index_end;
+      src = L.region_base;
+      c0 = c1 = L.region_begin.empty() ? L.index_end : L.region_begin[0];
+    }
+    for (size_t t = 0; t <= L.region_begin.size(); t++) {
+      const bool last = t == L.region_begin.size();
+      if (!last && L.region_used[t] == 0) continue;
+      if (!last && L.region_begin[t] <= c1 + 4096) { c1 = L.region_begin[t] + L.region_used[t]; continue; }
+      if (c1 > c0) {
+        CK(cudaMemcpyAsync(dv + c0, src + c0, c1 - c0, cudaMemcpyHostToDevice, st));
+        moved += c1 - c0;
+      }
+      if (!last) { c0 = L.region_begin[t]; c1 = c0 + L.region_used[t]; }
+    }
   }
   d.hstat.chunks++; d.hstat.nodes += L.nn; d.hstat.nodes_aliased += L.nodes_aliased;
   d.hstat.node_bytes_supplied += L.node_bytes_supplied; d.hstat.node_bytes_placed += L.node_bytes_placed;
@@ -883,9 +895,19 @@ int run_slice_borsh_chunks(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv
     // placed in this chunk is aliased, not copied (host_flatten.h)
     if (alias) d.dedup_tab.new_epoch();
     auto get_block = [&](size_t host_bytes, size_t dev_bytes) -> uint8_t* {
-      if (s.h_in.reserve(host_bytes) != cudaSuccess || s.in_pack.reserve(dev_bytes) != cudaSuccess) {
+      ChunkLayout& L = P.layout[k];  // (index_end is known by now)
+      const bool split = ctx->wc_staging && !pull && L.index_end > 0 && host_bytes > L.index_end;
+      if (s.in_pack.reserve(dev_bytes) != cudaSuccess || s.h_in.reserve(split ? L.index_end : host_bytes) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
+      }
+      if (split) {
+        // the node bytes are written once with streaming stores and read only by the DMA engine: write-combining
+        // memory takes the cores' caches out of those reads (no snoops); the index arrays stay cacheable, the result
+        // mapping reads them back
+        s.h_wc.flags = cudaHostAllocWriteCombined;
+        if (s.h_wc.reserve(host_bytes - L.index_end) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        L.region_base = static_cast<uint8_t*>(s.h_wc.p) - L.index_end;
       }
       return static_cast<uint8_t*>(s.h_in.p);
     };
