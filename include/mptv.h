@@ -125,7 +125,7 @@ int mptv_verify_batch_hashed_keys(mptv_ctx* ctx, const mptv_batch* in, const uin
 
 /* borsh blobs in, verdicts out, in ONE pipelined call (the prover's input format, prover/src/bin/main.rs:41,67):
  * blob i = blobs[blob_off[i] .. blob_off[i+1]) holds borsh(MerkleProofInput) (crypto-ops/src/types.rs:4-9).  Each
- * pipeline chunk is flattened by `n_threads` host threads (<= 0: all cores) straight into page-locked staging,
+ * pipeline chunk is flattened by `n_threads` host threads (<= 0: all cores but two per device of the context) straight into page-locked staging,
  * crosses PCIe as one copy and is verified while the next chunk is being flattened, so the call runs at the
  * speed of the flattener instead of flatten + copy in series.  out->value_off[i] is the offset of the returned
  * value INSIDE `blobs` (the value is a slice of a node, the node a slice of its blob).  A blob whose root_hash
