@@ -87,6 +87,42 @@ struct StorageProofInput {
   Bytes account_key;
   std::vector<Bytes> storage_keys;
   B256 address_keccak{};
+  // borsh derive order = field order; the fixed-size array has no length prefix
+  Bytes to_borsh() const {
+    Bytes o;
+    borsh_put_u32(o, (uint32_t)account_proof.size());
+    for (const Bytes& n : account_proof) borsh_put_bytes(o, n);
+    borsh_put_u32(o, (uint32_t)storage_proofs.size());
+    for (const std::vector<Bytes>& pr : storage_proofs) {
+      borsh_put_u32(o, (uint32_t)pr.size());
+      for (const Bytes& n : pr) borsh_put_bytes(o, n);
+    }
+    borsh_put_bytes(o, root_hash);
+    borsh_put_bytes(o, account_key);
+    borsh_put_u32(o, (uint32_t)storage_keys.size());
+    for (const Bytes& k : storage_keys) borsh_put_bytes(o, k);
+    o.insert(o.end(), address_keccak.begin(), address_keccak.end());
+    return o;
+  }
+  static StorageProofInput from_borsh(const uint8_t* data, size_t len) {
+    BorshReader r{data, data + len};
+    StorageProofInput s;
+    for (uint32_t n = r.u32(), i = 0; i < n; i++) s.account_proof.push_back(r.bytes());
+    for (uint32_t m = r.u32(), j = 0; j < m; j++) {
+      s.storage_proofs.emplace_back();
+      for (uint32_t n = r.u32(), i = 0; i < n; i++) s.storage_proofs.back().push_back(r.bytes());
+    }
+    s.root_hash = r.bytes();
+    s.account_key = r.bytes();
+    for (uint32_t k = r.u32(), i = 0; i < k; i++) s.storage_keys.push_back(r.bytes());
+    if (r.end - r.p != 32) throw std::invalid_argument("borsh: StorageProofInput must end with the 32-byte address_keccak");
+    memcpy(s.address_keccak.data(), r.p, 32);
+    return s;
+  }
+  bool operator==(const StorageProofInput& o) const {
+    return account_proof == o.account_proof && storage_proofs == o.storage_proofs && root_hash == o.root_hash &&
+           account_key == o.account_key && storage_keys == o.storage_keys && address_keccak == o.address_keccak;
+  }
 };
 
 // what the reference would have panicked with
@@ -239,6 +275,50 @@ class Verifier {
       if (i) values.push_back(res[i].value);
     }
     return values;
+  }
+
+  // The storage guest over a batch of inputs that exist as bytes: blob i = blobs[off[i] .. off[i+1]) holds
+  // borsh(StorageProofInput) (types.rs:11-19, main.rs:6-9).  Per input: the committed storage values, or the status
+  // the guest dies with (first failing proof in its order).  One streamed call (mptv_verify_storage_borsh).
+  struct StorageOutcome {
+    int status = MPTV_ST_OK;
+    std::vector<Bytes> values;
+    bool ok() const { return status == MPTV_ST_OK; }
+  };
+  std::vector<StorageOutcome> verify_storage_borsh(const uint8_t* blobs, const uint64_t* off, size_t n, size_t n_proofs = 0) {
+    std::vector<StorageOutcome> out(n);
+    if (n == 0) return out;
+    std::vector<uint64_t> first(n + 1);
+    std::vector<uint8_t> ist(n), status;
+    std::vector<uint64_t> voff;
+    std::vector<uint32_t> vlen;
+    for (size_t cap = n_proofs;;) {
+      status.assign(cap, 0); voff.assign(cap, 0); vlen.assign(cap, 0);
+      mptv_result r{status.data(), voff.data(), vlen.data()};
+      const int rc = mptv_verify_storage_borsh(ctx_, blobs, off, n, 0, first.data(), ist.data(), cap, &r);
+      if (rc == MPTV_ERR_NOMEM && first[n] > cap) { cap = (size_t)first[n]; continue; }  // proof_first holds the layout
+      check(rc, "mptv_verify_storage_borsh");
+      break;
+    }
+    for (size_t i = 0; i < n; i++) {
+      out[i].status = ist[i];
+      if (!out[i].ok()) continue;
+      for (uint64_t p = first[i] + 1; p < first[i + 1]; p++) out[i].values.emplace_back(blobs + voff[p], blobs + voff[p] + vlen[p]);
+    }
+    return out;
+  }
+  std::vector<StorageOutcome> verify_storage_proof_inputs(const std::vector<StorageProofInput>& inputs) {
+    Bytes blobs;
+    std::vector<uint64_t> off{0};
+    size_t n_proofs = 0;
+    for (const StorageProofInput& in : inputs) {
+      const Bytes b = in.to_borsh();
+      blobs.insert(blobs.end(), b.begin(), b.end());
+      off.push_back(blobs.size());
+      n_proofs += 1 + std::min(in.storage_proofs.size(), in.storage_keys.size());
+    }
+    blobs.resize(blobs.size() + 16, 0);
+    return verify_storage_borsh(blobs.data(), off.data(), inputs.size(), n_proofs);
   }
 
   void check(int rc, const char* what) {

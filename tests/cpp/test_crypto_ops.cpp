@@ -71,6 +71,38 @@ static void test_borsh_and_keys() {
   mptv_host_batch_free(hb);
 }
 
+// crypto-ops/src/types.rs:11-19: the borsh form of the storage guest's input, and what its host flattener makes of it
+static void test_storage_input_borsh() {
+  crypto_ops::StorageProofInput s;
+  s.account_proof = {unhex("c482208080"), unhex("")};
+  s.storage_proofs = {{unhex("c582208081ff")}, {}, {unhex("01"), unhex("0203")}};
+  s.root_hash = Bytes(32, 7);
+  s.account_key = unhex("aabb");
+  s.storage_keys = {unhex("01"), Bytes(32, 9)};  // one key fewer than proofs: the guest's zip drops the third proof
+  s.address_keccak.fill(5);
+  const Bytes w = s.to_borsh();
+  CHECK(crypto_ops::StorageProofInput::from_borsh(w.data(), w.size()) == s);
+  bool threw = false;
+  try { crypto_ops::StorageProofInput::from_borsh(w.data(), w.size() - 1); } catch (const std::invalid_argument&) { threw = true; }
+  CHECK(threw);
+  uint64_t off[2] = {0, w.size()}, first[2] = {9, 9};
+  mptv_host_batch* hb = nullptr;
+  const uint8_t* hk = nullptr;
+  CHECK(mptv_flatten_storage_borsh(w.data(), off, 1, 1, 0, 0, &hb, nullptr, first, &hk) == MPTV_OK);
+  const mptv_batch* v = mptv_host_batch_view(hb);
+  CHECK(first[0] == 0 && first[1] == 3 && v->n_proofs == 3 && v->n_nodes == 3);  // account proof (2 nodes) + 2 storage proofs (1 + 0 nodes)
+  CHECK(v->proof_first[1] == 2 && v->proof_first[2] == 3 && v->proof_first[3] == 3);
+  CHECK(v->root_from_proof[0] == -1 && v->root_from_proof[1] == 0 && v->root_from_proof[2] == 0 && hk[0] == 0 && hk[1] == 1 && hk[2] == 1);
+  CHECK(v->key_off[1] - v->key_off[0] == 32 && v->key_off[2] - v->key_off[1] == 1 && v->key_off[3] - v->key_off[2] == 32);
+  CHECK(v->roots[0] == 7 && v->roots[32] == 0);
+  mptv_host_batch_free(hb);
+  // the guest's Account decode on the host
+  uint8_t root[32];
+  const Bytes acct = unhex("f84605820100a01111111111111111111111111111111111111111111111111111111111111111a02222222222222222222222222222222222222222222222222222222222222222");
+  CHECK(mptv_account_storage_root(acct.data(), (uint32_t)acct.size(), root) == 1 && root[0] == 0x11 && root[31] == 0x11);
+  CHECK(mptv_account_storage_root(acct.data(), (uint32_t)acct.size() - 1, nullptr) == 0);
+}
+
 static void test_no_gpu_is_loud() {
   bool threw = false;
   try { crypto_ops::Verifier v({0}); } catch (const crypto_ops::MptvError&) { threw = true; }
@@ -131,6 +163,43 @@ static void test_transaction_proof_roundtrip() {
 
 // the batched entry on a batch large enough for the streamed borsh path (> 8 MB of blobs): every tx of 40 blocks
 // proven and verified, plus one absent index per block, against the element-wise answers
+// the storage guest's batched mirror through the wire format: inputs whose "account" leaf is a transaction (no
+// Account), a wrong root, a 31-byte root -- what the guest dies with, input by input
+static void test_storage_inputs_through_the_wire_format() {
+  crypto_ops::Verifier& v = crypto_ops::default_verifier();
+  std::vector<Bytes> txs;
+  uint64_t s = 424242;
+  for (int i = 0; i < 60; i++) {
+    Bytes t(120 + (i * 11) % 90, 0);
+    for (auto& b : t) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; b = (uint8_t)s; }
+    t[0] = 0x02;
+    txs.push_back(t);
+  }
+  std::vector<crypto_ops::StorageProofInput> ins;
+  for (uint32_t target : {3u, 17u, 59u, 60u}) {
+    crypto_ops::MerkleProofInput m = trie_utils::transaction_proof_inputs(v, txs, target);
+    crypto_ops::StorageProofInput in;
+    in.account_proof = m.proof;
+    in.root_hash = m.root_hash;
+    // (a transaction trie is keyed by rlp(index), not by a 32-byte hash: under address_keccak the key is simply absent)
+    in.address_keccak.fill(0);
+    memcpy(in.address_keccak.data(), m.key.data(), std::min<size_t>(32, m.key.size()));
+    in.storage_proofs = {m.proof};
+    in.storage_keys = {unhex("01")};
+    ins.push_back(in);
+  }
+  ins[1].root_hash[0] ^= 1;
+  ins[2].root_hash.pop_back();
+  std::vector<crypto_ops::Verifier::StorageOutcome> o = v.verify_storage_proof_inputs(ins);
+  CHECK(o.size() == 4);
+  for (size_t i = 0; i < o.size(); i++) {
+    int want = -1;
+    try { v.verify_storage_proof_input(ins[i]); want = MPTV_ST_OK; } catch (const crypto_ops::VerifyPanic& e) { want = e.status; }
+    CHECK(o[i].status == want && want != MPTV_ST_OK);
+  }
+  CHECK(o[1].status == MPTV_ST_INVALID_STATE_ROOT && o[2].status == MPTV_ST_BAD_ROOT_LEN);
+}
+
 static void test_large_batch_takes_the_streamed_path() {
   crypto_ops::Verifier& v = crypto_ops::default_verifier();
   std::vector<crypto_ops::MerkleProofInput> inputs;
@@ -167,11 +236,13 @@ int main(int argc, char** argv) {
   const std::string mode = argc > 1 ? argv[1] : "--cpu";
   test_encode_receipt();
   test_borsh_and_keys();
+  test_storage_input_borsh();
   if (mode == "--cpu-nogpu") test_no_gpu_is_loud();
   if (mode == "--gpu") {
     test_verify_merkle_proof_known_answers();
     test_transaction_proof_roundtrip();
     test_large_batch_takes_the_streamed_path();
+    test_storage_inputs_through_the_wire_format();
   }
   printf("%s: %d failure(s)\n", mode.c_str(), g_fail);
   return g_fail ? 1 : 0;
