@@ -169,6 +169,14 @@ def test_storage_borsh_stream_at_scale_equals_the_csr_batch(verifier):
             assert blobs[int(bvoff[i]):int(bvoff[i]) + int(bvlen[i])].tobytes() == nb.value(int(voff[i]), int(vlen[i]))
         for g in range(0, len(gf) - 1, 7):
             assert int(ist[g]) == next((int(s) for s in st[int(gf[g]):int(gf[g + 1])] if s), 0)
+    # the host half on its own: mptv_flatten_storage_borsh -> mptv_verify_batch_hashed_keys gives the same verdicts and values
+    import zk_state_proofs_b200 as z
+    fb, hk, fpf, info = z.flatten_storage_borsh(blobs, off)
+    assert (fpf == gf).all() and int(hk.sum()) == nb.n_proofs - (len(gf) - 1)
+    fst, fvoff, fvlen = verifier.verify_batch_hashed_keys(fb, hk)
+    assert (fst == st).all() and (fvlen == vlen).all()
+    for i in np.nonzero(fst == 0)[0][::29]:
+        assert fb.value(int(fvoff[i]), int(fvlen[i])) == nb.value(int(voff[i]), int(vlen[i]))
     # a result capacity that is too small (the stream stops at the chunk that does not fit and reports the real count),
     # exactly right, and too large
     verifier.set_option("borsh_chunk_bytes", 1 << 20)
