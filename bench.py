@@ -262,6 +262,7 @@ def config1_input():
 
 def run_single(a, env):
     """config 1: latency of ONE verify_merkle_proof call through the public API (host buffers in, value out)"""
+    import numpy as np
     import torch
     import zk_state_proofs_b200 as z
     rank, world, local = env
@@ -297,6 +298,16 @@ def run_single(a, env):
         ver.lib.mptv_verify_batch(ver.ctx, ctypes.byref(cb), ctypes.byref(cr))
     raw_dt = (time.perf_counter() - t0) / n_calls
     assert ver.verify_merkle_proof(root, proof, key) == want
+    # the same proof as the bytes a guest receives (borsh(MerkleProofInput)): flattened on the calling thread, one launch
+    blob = np.frombuffer(inp.to_borsh() + b"\0" * 16, np.uint8)
+    boff = np.array([0, len(blob) - 16], np.uint64)
+    for _ in range(50):
+        ver.lib.mptv_verify_borsh(ver.ctx, blob.ctypes.data, boff.ctypes.data, 1, 0, ctypes.byref(cr))
+    t0 = time.perf_counter()
+    for _ in range(n_calls):
+        ver.lib.mptv_verify_borsh(ver.ctx, blob.ctypes.data, boff.ctypes.data, 1, 0, ctypes.byref(cr))
+    borsh_dt = (time.perf_counter() - t0) / n_calls
+    assert st[0] == 0 and blob[int(voff[0]):int(voff[0]) + int(vlen[0])].tobytes() == want
     h2d = sum(int(getattr(b, k).nbytes) for k in ["node_bytes", "node_off", "node_len", "proof_first", "roots", "key_off"]) + len(key)
     line = dict(metric=METRIC, value=1.0 / dt, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
                 ms_per_step=dt * 1e3 * 200, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u32",
@@ -306,7 +317,7 @@ def run_single(a, env):
                                  "through mapped page-locked memory (no copy calls); the floor is one thread's Keccak chain "
                                  "(4320 alu instructions x 2 issue cycles = 4.4 us per rate block, 4 blocks for the longest node); "
                                  "there is no device-resident variant of a single-proof call, so value == e2e"),
-                latency_us=dt * 1e6, latency_us_c_abi=raw_dt * 1e6, keccak_f_per_sec=b.n_perm() / dt,
+                latency_us=dt * 1e6, latency_us_c_abi=raw_dt * 1e6, latency_us_borsh_c_abi=borsh_dt * 1e6, keccak_f_per_sec=b.n_perm() / dt,
                 roofline=None,
                 e2e=dict(value=1.0 / dt, unit=UNIT, h2d_bytes_per_step=h2d * 200, d2h_bytes_per_step=13 * 200,
                          ms_per_step=dt * 1e3 * 200, host_memory="pageable",
@@ -967,7 +978,7 @@ def single_context(a, env, b):
     return out
 
 
-def compact(line, keys=("value", "unit", "ms_per_step", "kernel_ms", "keccak_f_per_sec", "latency_us", "latency_us_c_abi", "verdicts", "gpu_launches",
+def compact(line, keys=("value", "unit", "ms_per_step", "kernel_ms", "keccak_f_per_sec", "latency_us", "latency_us_c_abi", "latency_us_borsh_c_abi", "verdicts", "gpu_launches",
                         "leaves_per_sec", "parity_error")):
     out = {k: line[k] for k in keys if k in line and line[k] is not None}
     out["workload"] = line["config"]["workload"]

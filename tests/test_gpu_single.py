@@ -107,3 +107,49 @@ def test_storage_guest_flow_is_one_launch(verifier, oracle):
             got = e.status
         assert got == want
         assert verifier.host_stats().launches == 1  # account + storage proofs + the key hashes: one launch
+
+
+def test_one_borsh_blob_per_call_is_one_launch(verifier, golden, oracle):
+    """mptv_verify_borsh / mptv_verify_storage_borsh with a handful of inputs: flattened on the calling thread and
+    verified by ONE launch (no worker pool, no chunk pipeline): the reference's verdict and value for every golden
+    vector one blob per call, the guest's outcome for every storage input one blob per call, values reported as
+    slices of the blob"""
+    import zk_state_proofs_b200 as z
+    from tests.test_gpu_storage_borsh import _guest_flow, _inputs
+    bad, small_calls = [], 0
+    for v in golden["vectors"]:
+        blob = z.MerkleProofInput(v["proof_b"], v["root_b"], v["key_b"]).to_borsh()
+        verifier.host_stats(reset=True)
+        st, voff, vlen = verifier.verify_borsh([blob])
+        hs = verifier.host_stats()
+        want_st = 6 if len(v["root_b"]) != 32 else v["status"]
+        got_v = blob[int(voff[0]):int(voff[0]) + int(vlen[0])] if st[0] == 0 else None
+        if (int(st[0]), got_v) != (want_st, v["value_b"] if want_st == 0 else None):
+            bad.append((v["tag"], int(st[0]), want_st))
+        if len(blob) <= (32 << 10) and len(v["proof_b"]) <= 100 and len(v["root_b"]) == 32:
+            small_calls += 1
+            assert hs.launches == 1 and hs.chunks <= 1, (v["tag"], hs.launches)
+    assert not bad, (len(bad), bad[:10])
+    assert small_calls > 2500
+    inputs = _inputs(oracle, 123, n_groups=250)
+    want = _guest_flow(oracle, inputs)
+    one_launch = 0
+    for inp, w in zip(inputs, want):
+        blob = inp.to_borsh()
+        verifier.host_stats(reset=True)
+        pf, ist, st, voff, vlen = verifier.verify_storage_borsh([blob])
+        hs = verifier.host_stats()
+        if isinstance(w, z.VerifyPanic):
+            assert int(ist[0]) == w.status
+        else:
+            assert ist[0] == 0 and [blob[int(voff[q]):int(voff[q]) + int(vlen[q])] for q in range(1, int(pf[1]))] == w
+        if len(blob) <= (32 << 10):
+            one_launch += hs.launches == 1
+    assert one_launch > 200
+    # a few inputs in one call still take the path; results equal the one-by-one answers
+    blobs = [i.to_borsh() for i in inputs[:6]]
+    verifier.host_stats(reset=True)
+    pf, ist, st, voff, vlen = verifier.verify_storage_borsh(blobs)
+    if sum(len(b) for b in blobs) <= (40 << 10) and int(pf[-1]) <= 32:
+        assert verifier.host_stats().launches == 1
+    assert [int(x) for x in ist] == [0 if isinstance(w, list) else w.status for w in want[:6]]

@@ -24,6 +24,10 @@
 
 using namespace mptv;
 
+extern "C" {
+static int verify_batch_impl(mptv_ctx* ctx, const mptv_batch* in, const uint8_t* hash_key, mptv_result* out);  // defined with the C entries below
+}
+
 namespace {
 
 int pick_lanes(const mptv_ctx* ctx, uint64_t n_nodes, uint64_t n_proofs) {
@@ -1108,12 +1112,86 @@ int run_slice_borsh(mptv_ctx* ctx, Device& d, const BorshStream& in, mptv_result
   return rc;
 }
 
+// A handful of inputs (one verify_merkle_proof call's MerkleProofInput, one StorageProofInput): no worker pool, no
+// submitter thread, no chunk pipeline -- the blobs are flattened on the calling thread into a small block and handed to
+// the batch entry, which verifies them with ONE kernel launch through the mapped mailbox (the latency path).
+// storage: the index of the inputs when the blobs are borsh(StorageProofInput), else null.
+constexpr uint64_t kSmallBorshBytes = 40 << 10;
+int run_small_borsh(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, const StorageIndex* storage,
+                    mptv_result* out) {
+  WorkerPool pool(1);
+  ChunkLayout L;
+  std::vector<uint64_t> node_src;
+  std::vector<uint8_t> bad;
+  uint8_t* block = nullptr;
+  size_t block_cap = 0;
+  auto get_block = [&](size_t host_bytes, size_t) -> uint8_t* {
+    block_cap = (host_bytes + 127) & ~(size_t)63;
+    block = static_cast<uint8_t*>(aligned_alloc(64, block_cap));
+    return block;
+  };
+  struct Free { uint8_t*& p; ~Free() { free(p); } } guard{block};
+  int rc;
+  if (storage) {
+    const StorageChunkJob job = {blobs, blob_off, 0, n, nullptr, storage};
+    rc = flatten_storage_chunk(pool, job, get_block, L, &node_src, &bad);
+  } else {
+    const BorshChunkJob job = {blobs, blob_off, 0, n, nullptr, false};
+    rc = flatten_borsh_chunk(pool, job, get_block, L, &node_src, &bad);
+  }
+  if (rc != MPTV_OK)
+    return fail_msg(ctx, rc, rc == MPTV_ERR_ARG ? "mptv_verify_borsh: a blob is not well-formed borsh" : "mptv_verify_borsh: allocation failed");
+  const uint64_t np = L.np;
+  const uint64_t* node_off = reinterpret_cast<const uint64_t*>(block + L.o_off);
+  const uint32_t* node_len = reinterpret_cast<const uint32_t*>(block + L.o_len);
+  const uint32_t* proof_first = reinterpret_cast<const uint32_t*>(block + L.o_pf);
+  const uint32_t* koff = reinterpret_cast<const uint32_t*>(block + L.o_koff);
+  const uint32_t* klen = reinterpret_cast<const uint32_t*>(block + L.o_klen);
+  // the public batch form keeps the keys as a prefix array
+  std::vector<uint8_t> kb;
+  std::vector<uint32_t> ko(np + 1, 0);
+  for (uint64_t p = 0; p < np; p++) {
+    kb.insert(kb.end(), block + koff[p], block + koff[p] + klen[p]);
+    ko[p + 1] = (uint32_t)kb.size();
+  }
+  kb.resize(kb.size() + 16, 0);
+  mptv_batch b;
+  memset(&b, 0, sizeof b);
+  b.node_bytes = block; b.node_bytes_len = block_cap;
+  b.node_off = node_off; b.node_len = node_len; b.n_nodes = L.nn;
+  b.proof_first = proof_first; b.n_proofs = np; b.roots = block + L.o_roots;
+  b.key_bytes = kb.data(); b.key_off = ko.data();
+  b.root_from_proof = L.groups ? reinterpret_cast<const int32_t*>(block + L.o_rfp) : nullptr;
+  std::vector<uint8_t> st(np);
+  std::vector<uint64_t> vo(np);
+  std::vector<uint32_t> vl(np);
+  mptv_result r = {st.data(), vo.data(), vl.data()};
+  rc = verify_batch_impl(ctx, &b, L.groups ? block + L.o_hk : nullptr, &r);
+  if (rc != MPTV_OK) return rc;
+  for (uint64_t p = 0; p < np; p++) {
+    uint8_t s8 = st[p];
+    uint64_t v = 0;
+    uint32_t l = 0;
+    if (bad[p]) s8 = MPTV_ST_BAD_ROOT_LEN;  // the guests' try_into().unwrap() comes first
+    else if (s8 == MPTV_ST_OK) {
+      l = vl[p];
+      // the first node of the proof that holds the value, reported inside this proof's own blob
+      for (uint32_t k = proof_first[p]; k < proof_first[p + 1]; k++)
+        if (node_off[k] <= vo[p] && vo[p] + l <= node_off[k] + node_len[k]) { v = node_src[k] + (vo[p] - node_off[k]); break; }
+    }
+    out->status[p] = s8; out->value_off[p] = v; out->value_len[p] = l;
+  }
+  return MPTV_OK;
+}
+
 int verify_borsh_run(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t* blob_off, uint64_t n, int n_threads, mptv_result* out) {
   if (!ctx || !out) return MPTV_ERR_ARG;
   if (n == 0) return MPTV_OK;
   if (!blobs || !blob_off || !out->status || !out->value_off || !out->value_len) return MPTV_ERR_ARG;
   for (uint64_t i = 0; i < n; i++)
     if (blob_off[i + 1] < blob_off[i]) return MPTV_ERR_ARG;  // the chunking below searches the offsets
+  if (ctx->latency_path && n <= kSmallMaxProofs && blob_off[n] - blob_off[0] <= kSmallBorshBytes)
+    return run_small_borsh(ctx, blobs, blob_off, n, nullptr, out);
   // all cores but two per device: the submitter thread of each device needs a share of a core for its CUDA calls, and
   // the pool's barriers cost more than a core's worth of work as soon as one of its threads is descheduled (16-core
   // box, 1 M config-2 proofs: 48.9 ms with 15 threads, 46.0 ms with 14)
@@ -1181,6 +1259,10 @@ int verify_storage_borsh_run(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t
   }
   memcpy(proof_first, idx.proof_first.data(), 8 * (n + 1));
   if (results_cap < idx.proof_first[n] || !out || !out->status || !out->value_off || !out->value_len) return MPTV_ERR_NOMEM;  // proof_first[n] = what is required
+  if (ctx->latency_path && idx.proof_first[n] <= kSmallMaxProofs && blob_off[n] - blob_off[0] <= kSmallBorshBytes) {
+    const int rc = run_small_borsh(ctx, blobs, blob_off, n, &idx, out);  // one StorageProofInput: one kernel launch
+    if (rc != MPTV_OK) return rc;
+  } else {
   // pass 2: the stream, cut over the devices by blob bytes at input boundaries
   const BorshStream in = {blobs, blob_off, false, &idx};
   std::vector<uint64_t> cut(nd + 1, 0);
@@ -1200,6 +1282,7 @@ int verify_storage_borsh_run(mptv_ctx* ctx, const uint8_t* blobs, const uint64_t
     for (auto& t : th) t.join();
   }
   for (int k = 0; k < nd; k++) if (rcs[k] != MPTV_OK) return rcs[k];
+  }
   // the guest's outcome per input: the first proof that fails, in its order; an account leaf that is not an Account
   // (decode_exact(...).unwrap(), main.rs:15) fails the input even when it carries no storage proof
   if (input_status) {
