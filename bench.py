@@ -169,7 +169,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
