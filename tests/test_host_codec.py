@@ -258,3 +258,55 @@ def test_account_decode_on_the_host_matches_the_oracle(oracle):
         assert got == oracle.account_storage_root(v)
         ok += got is not None
     assert 500 < ok < 4500 and z.account_storage_root(b"") is None and z.account_storage_root(b"\xc0") is None
+
+
+def test_storage_borsh_parser_accepts_exactly_what_the_mirror_accepts(oracle):
+    """untrusted bytes: valid StorageProofInput blobs with corrupted length words, truncations, trailing bytes and bit
+    flips -- mptv_flatten_storage_borsh accepts a blob iff the Python mirror's from_borsh (borsh::from_slice semantics)
+    does, lays it out identically when it does, and never reads outside the blob"""
+    import random
+    import struct
+    import zk_state_proofs_b200 as z
+    from tests.test_gpu_storage_borsh import _inputs
+    blobs = [i.to_borsh() for i in _inputs(oracle, 31, 120)]
+    rng = random.Random(7)
+    n_acc = n_rej = 0
+    for it in range(2000):
+        b = bytearray(blobs[rng.randrange(len(blobs))])
+        k = rng.random()
+        if k < 0.3:
+            p = rng.randrange(0, len(b) - 4)
+            struct.pack_into("<I", b, p, rng.choice([0, 1, 2, 3, 5, 0xffffffff, 0x7fffffff, len(b), len(b) - p, rng.randrange(0, 1 << 16)]))
+        elif k < 0.5:
+            b = b[:rng.randrange(0, len(b))]
+        elif k < 0.6:
+            b = b + bytes(rng.randrange(1, 40))
+        elif k < 0.8:
+            b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
+        else:
+            struct.pack_into("<I", b, 0, rng.choice([0, 1, 2, 0xffffffff, rng.randrange(0, 64)]))
+        b = bytes(b)
+        try:
+            want = z.StorageProofInput.from_borsh(b)
+        except Exception:
+            want = None
+        try:
+            fb, hk, pf, info = z.flatten_storage_borsh([blobs[0], b, blobs[1]])
+        except ValueError:
+            assert want is None, (it, len(b))
+            n_rej += 1
+            continue
+        assert want is not None, (it, len(b))
+        n_acc += 1
+        used = min(len(want.storage_proofs), len(want.storage_keys))
+        q = int(pf[1])
+        assert int(pf[2]) - q == 1 + used
+        for j, pr in enumerate([want.account_proof] + want.storage_proofs[:used]):
+            f, e = int(fb.proof_first[q + j]), int(fb.proof_first[q + j + 1])
+            assert e - f == len(pr)
+            for kx, nd in enumerate(pr):
+                no, nl = int(fb.node_off[f + kx]), int(fb.node_len[f + kx])
+                assert bytes(fb.node_bytes[no:no + nl]) == nd
+        for j in range(used):
+            assert bytes(fb.key_bytes[int(fb.key_off[q + 1 + j]):int(fb.key_off[q + 2 + j])]) == bytes(want.storage_keys[j])
+    assert n_acc > 300 and n_rej > 300
