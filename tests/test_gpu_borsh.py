@@ -176,7 +176,7 @@ def test_device_flatten_mode(verifier, golden, oracle, chunk_bytes, lead):
         st, _, _ = verifier.verify_borsh(_Pinned(_concat([good])[0]).arr, _concat([good])[1])
         assert st.tolist() == [vs[0]["status"]]
     finally:
-        verifier.set_option("borsh_mode", 0)
+        verifier.set_option("borsh_mode", -1)
         verifier.set_option("borsh_chunk_bytes", 32 << 20)
 
 
@@ -207,4 +207,57 @@ def test_write_combining_staging_gives_identical_results(verifier, golden, oracl
     finally:
         verifier.set_option("wc_staging", 0)
         verifier.set_option("host_dedup", 1)
+        verifier.set_option("borsh_chunk_bytes", 32 << 20)
+
+
+def test_device_flatten_parser_accepts_exactly_what_the_mirror_accepts(verifier, golden):
+    """borsh_mode 1 on untrusted bytes: good blobs with corrupted length words, truncations, trailing bytes and bit flips.
+    The device's walk over the length prefixes (k_blob_count) accepts a blob iff MerkleProofInput.from_borsh does; an
+    accepted call gives the host-flatten mode's results"""
+    import random
+    import struct
+    import zk_state_proofs_b200 as z
+    vs = [v for v in golden["vectors"] if v["status"] == 0][:200]
+    good = [z.MerkleProofInput(v["proof_b"], v["root_b"], v["key_b"]).to_borsh() for v in vs]
+    rng = random.Random(3)
+    verifier.set_option("borsh_chunk_bytes", 1 << 14)
+    n_acc = n_rej = 0
+    try:
+        for it in range(400):
+            b = bytearray(good[rng.randrange(len(good))])
+            k = rng.random()
+            if k < 0.35:
+                p = rng.randrange(0, len(b) - 4)
+                struct.pack_into("<I", b, p, rng.choice([0, 1, 2, 3, 0xffffffff, 0x7fffffff, len(b), len(b) - p, rng.randrange(0, 1 << 12)]))
+            elif k < 0.5:
+                b = b[:rng.randrange(0, len(b))]
+            elif k < 0.6:
+                b = b + bytes(rng.randrange(1, 40))
+            elif k < 0.8:
+                b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
+            else:
+                struct.pack_into("<I", b, 0, rng.choice([0, 1, 2, 0xffffffff, rng.randrange(0, 64)]))
+            b = bytes(b)
+            try:
+                z.MerkleProofInput.from_borsh(b)
+                ok = True
+            except Exception:
+                ok = False
+            at = rng.randrange(0, 60)
+            buf, off = _concat(good[:at] + [b] + good[at:60])
+            pin = _Pinned(buf, lead=it % 7)
+            verifier.set_option("borsh_mode", 1)
+            try:
+                got = verifier.verify_borsh(pin.arr, off)
+                assert ok, (it, len(b))
+                n_acc += 1
+                verifier.set_option("borsh_mode", 0)
+                want = verifier.verify_borsh(buf, off, threads=2)
+                assert all((x == y).all() for x, y in zip(got, want))
+            except z.MptvError:
+                assert not ok, (it, len(b))
+                n_rej += 1
+        assert n_acc > 60 and n_rej > 60
+    finally:
+        verifier.set_option("borsh_mode", -1)
         verifier.set_option("borsh_chunk_bytes", 32 << 20)
