@@ -318,6 +318,7 @@ int flatten_borsh_chunk(WorkerPool& pool, const BorshChunkJob& job, GetBlock get
     // ---- phase 1: one streaming pass over my blobs
     uint64_t k = 0;
     for (int q = 0; q < t; q++) k += tot[q].nodes;
+    const uint64_t k_end = k + tot[t].nodes;  // (a caller that rewrites the blobs during the call must not get past its share of the arrays)
     uint64_t* node_off = reinterpret_cast<uint64_t*>(block + L.o_off);
     uint32_t* node_len = reinterpret_cast<uint32_t*>(block + L.o_len);
     uint32_t* proof_first = reinterpret_cast<uint32_t*>(block + L.o_pf);
@@ -357,11 +358,11 @@ int flatten_borsh_chunk(WorkerPool& pool, const BorshChunkJob& job, GetBlock get
       const uint32_t n = rd_u32(p);
       p += 4;
       proof_first[i] = (uint32_t)k;
-      bool ok = true;
+      bool ok = n <= k_end - k;
       uint64_t fp = n ? look_ahead(p, end) : 0;  // of node j
       const uint8_t* p1 = n > 1 ? next_node(p, end) : nullptr;
       uint64_t fp1 = p1 ? look_ahead(p1, end) : 0;  // of node j + 1
-      for (uint32_t j = 0; j < n; j++) {
+      for (uint32_t j = 0; ok && j < n; j++) {
         if (end - p < 4) { ok = false; break; }
         const uint32_t len = rd_u32(p);
         if ((uint64_t)(end - p - 4) < len || len > kMaxNodeLen) { ok = false; break; }
@@ -599,6 +600,8 @@ int flatten_storage_chunk(WorkerPool& pool, const StorageChunkJob& job, GetBlock
     const uint64_t lo = job.cs + std::min(ni, per * t), hi = job.cs + std::min(ni, per * (t + 1));
     uint64_t k = X.node_first[lo] - X.node_first[job.cs];     // next node index of the chunk
     uint64_t pi = X.proof_first[lo] - X.proof_first[job.cs];  // next proof index of the chunk
+    // (a caller that rewrites the blobs between the index pass and this one must not get past my share of the arrays)
+    const uint64_t k_end = X.node_first[hi] - X.node_first[job.cs], pi_end = X.proof_first[hi] - X.proof_first[job.cs];
     uint64_t* node_off = reinterpret_cast<uint64_t*>(block + L.o_off);
     uint32_t* node_len = reinterpret_cast<uint32_t*>(block + L.o_len);
     uint32_t* proof_first = reinterpret_cast<uint32_t*>(block + L.o_pf);
@@ -624,9 +627,10 @@ int flatten_storage_chunk(WorkerPool& pool, const StorageChunkJob& job, GetBlock
     };
     // the nodes of the Vec<Vec<u8>> at p become the next proof of the chunk (same look-ahead as flatten_borsh_chunk)
     auto place_proof = [&](const uint8_t*& p, const uint8_t* end) -> bool {
-      if (end - p < 4) return false;
+      if (end - p < 4 || pi >= pi_end) return false;
       const uint32_t n = rd_u32(p);
       p += 4;
+      if (n > k_end - k) return false;
       proof_first[pi] = (uint32_t)k;
       uint64_t fp = n ? look_ahead(p, end) : 0;
       const uint8_t* p1 = n > 1 ? next_node(p, end) : nullptr;
