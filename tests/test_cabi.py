@@ -91,7 +91,22 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
                            os.path.join(ROOT, "tests", "c", "cabi_smoke.c"), "-o", exe, "-L", libdir, "-l:libmptv.so",
                            "-Wl,-rpath," + libdir])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
-    assert out.returncode == 0 and "rlp(300) has 3 bytes" in out.stdout
+    assert out.returncode == 0 and "rlp(300) has 3 bytes" in out.stdout and "storage entries: ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_c_program_runs_the_storage_guest_entry_on_the_gpu(tmp_path):
+    """the same plain-C program on a B200: mptv_verify_storage_borsh answers from C"""
+    import subprocess
+    import zk_state_proofs_b200 as z
+    z.load_library()
+    exe = str(tmp_path / "cabi_smoke")
+    libdir = os.path.dirname(z.lib_path())
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "cabi_smoke.c"), "-o", exe, "-L", libdir, "-l:libmptv.so",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "mptv_verify_storage_borsh -> 0, input status 1" in out.stdout and "storage entries: ok" in out.stdout, out.stdout + out.stderr
 
 
 def test_binding_structures_match_the_pinned_abi_layout():
